@@ -1,0 +1,184 @@
+"""CPU suite: pin the oracle (oracle/) against fixtures produced by the
+reference's own modules (tests/golden/make_golden.py).  fp32 on both sides,
+so tolerances are a few ulp; ids are exact."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from oracle import embed, fm, losses, retrieval, towers
+
+TOL = dict(rtol=1e-5, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def ut():
+    return load_golden("user_tower.pt")
+
+
+def _oracle_tower(ut):
+    m = towers.UserTowerOracle(SimpleNamespace(**ut["args"]))
+    m.load_state_dict(ut["state"], strict=True)      # same parameter names as the reference (8b)
+    return m.eval()
+
+
+def test_user_tower_state_dict_names(ut):
+    m = towers.UserTowerOracle(SimpleNamespace(**ut["args"]))
+    assert set(m.state_dict().keys()) == set(ut["state"].keys())
+
+
+def test_seq_front_bit_exact(ut):
+    m = _oracle_tower(ut)
+    i = ut["inputs"]
+    x = m.embed_front(i["pretrained_vecs"], **{k: i[k] for k in towers.SEQ_INPUTS})
+    assert torch.equal(x, ut["seq_front"])           # same op order -> bit-exact in fp32
+
+
+def test_padding_row_is_returned_not_zero(ut):
+    # invariant 1: padding_idx rows are non-zero in SASRecUserTower and ARE gathered in forward
+    assert ut["state"]["item_id_emb.weight"][0].abs().sum() > 0
+    assert (ut["inputs"]["item_ids"] == 0).any()
+
+
+def test_static_front(ut):
+    m = _oracle_tower(ut)
+    i = ut["inputs"]
+    x = m.static_front(i["cont_feats"], **{k: i[k] for k in towers.STATIC_INPUTS})
+    assert torch.equal(x, ut["static_front"])
+
+
+def test_user_tower_forward_and_grads(ut):
+    m = _oracle_tower(ut)
+    out = m(**ut["inputs"], training_mode=True)
+    torch.testing.assert_close(out, ut["out_train"], **TOL)
+    assert not ut["out_eval"].isnan().any()
+    torch.testing.assert_close(m(**ut["inputs"], training_mode=False).detach(), ut["out_eval"], **TOL)
+    (out * ut["cotangent"]).sum().backward()
+    g = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(g) == set(ut["grads"])
+    for k in g:
+        torch.testing.assert_close(g[k], ut["grads"][k], rtol=1e-4, atol=1e-6, msg=k)
+    # invariant 1: padding row never receives gradient; invariant 2: masked gates get exact zeros
+    assert g["item_id_emb.weight"][0].abs().sum() == 0
+    assert ut["grads"]["type_emb.weight"].abs().sum() == 0
+    assert (ut["grads"]["seq_gate"][2:] == 0).all() and (ut["grads"]["seq_gate"][:2] != 0).all()
+
+
+def test_normalized_rows():
+    im = load_golden("item_matrix.pt")
+    w = im["state"]["item_matrix.weight"].clone().requires_grad_(True)
+    rows = embed.normalized_rows(w, im["target_ids"])
+    torch.testing.assert_close(rows, im["rows"], **TOL)
+    (rows * im["cotangent"]).sum().backward()
+    torch.testing.assert_close(w.grad, im["grad_weight"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def lg():
+    return load_golden("losses.pt")
+
+
+def _check(lg, name, fn, wrt, *a, **k):
+    leaves = [x.clone().requires_grad_(True) for x in wrt]
+    r = fn(*leaves, *a, **k)
+    stats = None
+    if isinstance(r, tuple):
+        r, stats = r
+    torch.testing.assert_close(r, lg[name]["loss"], rtol=1e-5, atol=1e-6)
+    r.backward()
+    for got, want in zip(leaves, lg[name]["grads"]):
+        torch.testing.assert_close(got.grad, want, rtol=1e-4, atol=1e-7)
+    if stats is not None:
+        for key, v in lg[name]["stats"].items():
+            assert stats[key] == pytest.approx(v, rel=1e-5), key
+
+
+def test_c1_simcse(lg):
+    c = lg["c1"]
+    e1, e2 = c["E1"].clone().requires_grad_(True), c["E2"].clone().requires_grad_(True)
+    loss = losses.simcse_loss(e1, e2, c["temperature"])
+    torch.testing.assert_close(loss, c["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    torch.testing.assert_close(e1.grad, c["grads"][0], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(e2.grad, c["grads"][1], rtol=1e-4, atol=1e-7)
+
+
+def test_c2(lg):
+    _check(lg, "c2", losses.inbatch_corrected_logq_loss, [lg["U"], lg["table"]], lg["tgt"], lg["uid"], lg["logq"],
+           temperature=0.1, lambda_logq=1.0)
+    _check(lg, "c2_nologq", losses.inbatch_corrected_logq_loss, [lg["U"], lg["table"]], lg["tgt"], lg["uid"],
+           lg["logq"], temperature=0.07, lambda_logq=0.0)
+
+
+def test_c3(lg):
+    _check(lg, "c3", losses.duorec_loss_refined, [lg["U"], lg["U2"]], lg["tgt"], temperature=0.1, lambda_sup=0.1)
+    _check(lg, "c3_nosup", losses.duorec_loss_refined, [lg["U"], lg["U2"]], lg["tgt"], temperature=0.1,
+           lambda_sup=0.0)
+    _check(lg, "c3_distinct", losses.duorec_loss_refined, [lg["U"], lg["U2"]], lg["tgt_distinct"],
+           temperature=0.1, lambda_sup=0.1)
+
+
+def test_c4(lg):
+    _check(lg, "c4", losses.full_batch_hard_emphasis_loss, [lg["U"], lg["table"]], lg["tgt"], lg["logq"],
+           top_k_percent=0.05, hard_margin=0.01, hnm_threshold=0.90, temperature=0.15, lambda_logq=1.0)
+
+
+def test_c5(lg):
+    _check(lg, "c5_hnm", losses.inbatch_hnm_corrected_loss_with_stats, [lg["U"], lg["table"]], lg["tgt"], lg["logq"],
+           top_k_percent=0.05, hnm_threshold=0.90, temperature=0.1, lambda_logq=0.7)
+    _check(lg, "c5_mixed", losses.inbatch_mixed_hnm_loss_with_stats, [lg["U"], lg["table"]], lg["tgt"], lg["logq"],
+           lg["mixed_random_indices"], top_k_percent=0.05)
+    v = lg["table"][lg["tgt"]]
+    _check(lg, "c5_logq", losses.logq_correction_loss, [lg["U"], v], lg["tgt"], lg["probs"], temperature=0.07,
+           lambda_logq=0.5)
+    _check(lg, "c5_eff", losses.efficient_corrected_logq_loss, [lg["U"], v], lg["tgt"], lg["logq"], temperature=0.1,
+           lambda_logq=0.1)
+
+
+def test_retrieval():
+    r = load_golden("retrieval.pt")
+    for k in (12, 20, 100, 500):
+        sc, ids = retrieval.retrieve_topk(r["U"], r["I"], k)
+        assert torch.equal(ids, r[f"k{k}"]["ids"])
+        torch.testing.assert_close(sc, r[f"k{k}"]["scores"], rtol=0, atol=0)
+    sc, ids = retrieval.retrieve_topk(r["U"], r["I"], 20, mask_index0=True)
+    assert torch.equal(ids, r["gnn_k20"]["ids"]) and not (ids == 0).any()
+    t = r["ties_k12"]
+    sc, ids = retrieval.retrieve_topk(r["U"], t["I"], 12)
+    torch.testing.assert_close(sc, t["scores"], rtol=0, atol=0)
+    assert torch.equal(retrieval.canonical_ids(sc, ids), retrieval.canonical_ids(t["scores"], t["ids"]))
+
+
+def test_item_front():
+    g = load_golden("item_front.pt")
+    s, i = g["state"], g["inputs"]
+    std = embed.std_front(i["std_input"], s["std_embedding.weight"], s["std_field_emb"], s["std_ln.weight"],
+                          s["std_ln.bias"])
+    torch.testing.assert_close(std, g["std_out"], **TOL)
+    e = "bert_model.embeddings."
+    we, rv = embed.re_front(i["re_input_ids"], i["re_attn_mask"], s[e + "word_embeddings.weight"],
+                            s[e + "position_embeddings.weight"], s[e + "token_type_embeddings.weight"],
+                            s[e + "LayerNorm.weight"], s[e + "LayerNorm.bias"],
+                            s["re_proj.0.weight"], s["re_proj.0.bias"], s["re_proj.1.weight"], s["re_proj.1.bias"],
+                            s["re_field_position"], s["re_ln.weight"], s["re_ln.bias"], g["bert_ln_eps"])
+    torch.testing.assert_close(we, g["word_embs"], **TOL)
+    torch.testing.assert_close(rv, g["re_out"], rtol=1e-4, atol=1e-5)
+    assert s["std_embedding.weight"][0].abs().sum() == 0          # invariant 1 (item side: zero pad row)
+    assert g["grad_std_embedding"][0].abs().sum() == 0
+
+
+def test_hybrid_user_gathers():
+    h = load_golden("hybrid_user.pt")
+    t, i = h["tables"], h["inputs"]
+    assert torch.equal(embed.gather_rows(t["gnn_user_emb"], i["u_idx"]), h["gathered"]["gnn_user_emb"])
+    assert torch.equal(embed.gather_rows(t["item_content_emb"], i["seq_ids"]), h["gathered"]["item_content_emb"])
+    assert torch.equal(embed.gather_rows(t["gnn_item_emb"], i["seq_ids"]), h["gathered"]["gnn_item_emb"])
+    assert torch.equal(embed.hybrid_time_rows(t["time_emb"], i["seq_deltas"]), h["gathered"]["time_emb"])
+    assert torch.equal(embed.gather_rows(t["channel_emb"], i["u_cat"]), h["gathered"]["channel_emb"])
+
+
+def test_fm_identity():
+    x = torch.randn(32, 39, 16, dtype=torch.float64)
+    torch.testing.assert_close(fm.fm_second_order(x), fm.fm_pairwise(x), rtol=1e-10, atol=1e-10)
