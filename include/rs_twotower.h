@@ -1,0 +1,253 @@
+/*
+ * rs_twotower.h -- C ABI of the B200 (sm_100a) two-tower hot-path library
+ * (librs_twotower.so).
+ *
+ * The reference (DotBlossom/LLM-driven_content-based-feature_recommendation_system)
+ * is pure Python/PyTorch and has NO plugin registry, operator table or FFI
+ * (SURVEY.md 8b): its boundary for this path is the nn.Module.forward / loss
+ * function surface.  The host mirror of that surface lives in the Python
+ * package next to this library; underneath it every arithmetic step crosses
+ * THIS boundary.  Each entry point below names the reference lines (relative
+ * to the reference checkout) whose ATen calls it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the comment says "host".  The caller owns every buffer; the library never
+ *     allocates or frees device memory.  Scratch is passed in as `workspace`
+ *     (size from the matching *_workspace_bytes()).
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered,
+ *     no host synchronisation happens inside any call.
+ *   - ids are int64 (the reference's torch.long).  dtype codes: RS_F32/F16/BF16.
+ *   - return value: 0 on success, otherwise a cudaError_t value or one of the
+ *     RS_ERR_* codes (>= 10000); rs_error_string() describes it.  The Python
+ *     mirror raises RuntimeError, like the reference's PyTorch calls would.
+ *   - `oob_flag` (int*, may be NULL): set to 1 by a kernel that meets an id
+ *     outside [0, rows).  Such a row reads as zeros / is not accumulated.  The
+ *     reference raises IndexError (CPU) or a device assert (CUDA) there; the
+ *     host mirror turns the flag into IndexError when asked to check.
+ *   - thread-safety: re-entrant; no global mutable state.
+ */
+#ifndef RS_TWOTOWER_H_
+#define RS_TWOTOWER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_F32 0
+#define RS_F16 1
+#define RS_BF16 2
+
+#define RS_ERR_BAD_ARG 10001
+#define RS_ERR_UNSUPPORTED 10002
+#define RS_ERR_WORKSPACE 10003
+
+#define RS_MAX_TABLES 8
+
+int rs_abi_version(void);
+const char* rs_error_string(int code);
+
+/* ------------------------------------------------------------------ gathers */
+
+/* out[i,:] = table[min(ids[i], clamp_max) , :]   (clamp_max < 0: no clamp)
+ * Replaces aten::embedding / index at: tower_code/v1_usertower_train.py:760
+ * (pretrained_lookup[item_ids]), tower_code/v1_refine_usertower.py:833
+ * (item_tower_emb[target_ids]), tower_code/mined_inference.py:670,687-688,705
+ * (gnn_user_emb / item_content_emb / gnn_item_emb / channel_emb) and :695
+ * (time_emb(seq_deltas.clamp(max=1000))).  dim % 4 == 0 (dim % 8 for 16-bit). */
+int rs_gather_rows(const void* table, int table_dtype, int64_t rows, int64_t dim,
+                   const int64_t* ids, int64_t n, int64_t clamp_max,
+                   void* out, int out_dtype, int* oob_flag, void* stream);
+
+/* d_table[ids[i],:] += scale * d_out[i,:]  for ids[i] != padding_idx  (padding_idx < 0: none).
+ * fp32 vector atomics (red.global.add.v4.f32).  d_table is fp32 and is NOT cleared.
+ * Replaces aten::embedding_dense_backward (autograd of the gathers above and of
+ * item_tower.py:239,270 -> BERT word_embeddings [30522,768]). */
+int rs_scatter_add_rows(const void* d_out, int d_out_dtype, const int64_t* ids, int64_t n, int64_t dim,
+                        int64_t rows, int64_t padding_idx, int64_t clamp_max, float scale,
+                        float* d_table, int* oob_flag, void* stream);
+
+/* Deterministic variant: sort (id, position) by id with a stable LSD radix sort, then
+ * segment-reduce in position order.  d_table must be zero-filled (rows not hit stay 0).
+ * `sorted_*` may be NULL (then built inside `workspace`), or a cache filled by
+ * rs_sort_ids() for the same `ids`. */
+size_t rs_sort_ids_workspace_bytes(int64_t n);
+int rs_sort_ids(const int64_t* ids, int64_t n, int64_t rows, int64_t clamp_max,
+                int32_t* sorted_ids, int32_t* sorted_pos, void* workspace, size_t workspace_bytes,
+                int* oob_flag, void* stream);
+size_t rs_segment_reduce_workspace_bytes(int64_t n, int64_t dim);
+int rs_segment_reduce_rows(const void* d_out, int d_out_dtype, const int32_t* sorted_ids,
+                           const int32_t* sorted_pos, int64_t n, int64_t dim, int64_t rows,
+                           int64_t padding_idx, const float* scale_dev /* device scalar or NULL (=1) */,
+                           const float* dot_table /* optional [rows,dim]: also emit sum_i <dot_table[id_i], d_out[i]> */,
+                           float* d_table, float* dot_out /* device scalar, accumulated, or NULL */,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------ U1: SASRec sequence front */
+
+/* out[p,:] = base[p,:] + sum_t gates[t] * tables[t][ids[t][p],:] + pos_table[p % L,:]
+ * in the reference's order of operations (product rounded, then added, left to
+ * right, position row last) -> bit-exact in fp32.
+ * Replaces tower_code/v1_refine_usertower.py:447-456 (6x aten::embedding + 7
+ * elementwise kernels + the in-place adds).  `ids`, `tables`, `table_rows` are
+ * HOST arrays of n_tables entries; gates is a device array [n_tables]
+ * (sigmoid(seq_gate) * s_mask, :434-438).  base may be NULL, pos_table may be NULL.
+ * The forward returns the STORED row for id 0 (padding rows are non-zero, :408-409). */
+int rs_seq_front_fwd(const void* base, int base_dtype,
+                     const int64_t* const* ids, const float* const* tables, const int64_t* table_rows,
+                     int n_tables, const float* gates,
+                     const float* pos_table, int64_t L, int64_t P, int64_t dim,
+                     void* out, int out_dtype, int* oob_flag, void* stream);
+
+/* U3: backward of the above (autograd of :447-456, i.e. 6x embedding_dense_backward
+ * + the gate products, tower_code/v1_usertower_train.py:850).
+ *   d_tables[t][id,:] += gates[t] * dx[p,:]   for id = ids[t][p] != padding_idx
+ *   d_gates[t]         = sum_p < tables[t][ids[t][p],:], dx[p,:] >      (padding rows INCLUDED)
+ *   d_pos[l,:]         = sum_b dx[b*L + l,:]
+ * `big_mode[t]` (host): 0 = table is reduced by the caller with
+ * rs_segment_reduce_rows (this call skips its rows and its gate dot), 1 = vector
+ * atomics here, 2 = small table (rows <= 64): privatised per-warp copies, no
+ * atomics, deterministic.  d_tables must be zero-filled by the caller for modes 1/2
+ * (mode 2 overwrites).  d_gates / d_pos are overwritten. */
+size_t rs_seq_front_bwd_workspace_bytes(int64_t P, int64_t L, int64_t dim, int n_tables,
+                                        const int64_t* table_rows, const int* big_mode);
+int rs_seq_front_bwd(const void* dx, int dx_dtype,
+                     const int64_t* const* ids, const float* const* tables, const int64_t* table_rows,
+                     const int* big_mode, int n_tables, const float* gates,
+                     int64_t L, int64_t P, int64_t dim, int64_t padding_idx,
+                     float* const* d_tables, float* d_gates, float* d_pos,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------- U2: SASRec static front */
+
+/* out[b, :] = concat_i( gates[i] * tables[i][ids[i][b], :] , gates[9] * relu(cont[b,:] @ W^T + bias) )
+ * 9 tiny tables (dims 16,16,16,16,4,4,4,4,4) + Linear(4->16): [B,100].
+ * Replaces tower_code/v1_refine_usertower.py:472-491 (~25 launches). */
+int rs_static_front_fwd(const int64_t* const* ids /*host[9]*/, const float* const* tables /*host[9]*/,
+                        const int64_t* table_rows /*host[9]*/, const float* cont /*[B,4]*/,
+                        const float* cont_w /*[16,4]*/, const float* cont_b /*[16]*/,
+                        const float* gates /*dev[10]*/, int64_t B, float* out /*[B,100]*/,
+                        int* oob_flag, void* stream);
+/* backward: d_tables[i] (overwritten, padding row 0 excluded), d_gates[10], d_cont_w, d_cont_b. */
+size_t rs_static_front_bwd_workspace_bytes(int64_t B);
+int rs_static_front_bwd(const float* d_out /*[B,100]*/, const int64_t* const* ids, const float* const* tables,
+                        const int64_t* table_rows, const float* cont, const float* cont_w, const float* cont_b,
+                        const float* gates, int64_t B, int64_t padding_idx,
+                        float* const* d_tables, float* d_gates, float* d_cont_w, float* d_cont_b,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------- U4: normalised item-matrix rows */
+
+/* out[i,:] = table[ids[i],:] / max(||table[ids[i],:]||_2, eps);  inv_norm[i] = 1/max(||.||,eps)
+ * Same values as F.normalize(table, p=2, dim=1)[ids] (tower_code/v1_usertower_train.py:810-811
+ * + v1_refine_usertower.py:833) without normalising the other 100k rows. */
+int rs_normalized_rows_fwd(const float* table, int64_t rows, int64_t dim, const int64_t* ids, int64_t n,
+                           float eps, void* out, int out_dtype, float* inv_norm, int* oob_flag, void* stream);
+/* d_table[id,:] += inv_norm * (g - v <v,g>)  with v the normalised row (rows at the eps
+ * clamp: inv_norm * g).  The reference lets gradient flow into row 0 here (plain
+ * indexing, not nn.Embedding) -- so does this. */
+int rs_normalized_rows_bwd(const void* d_out, int d_out_dtype, const float* table, int64_t rows, int64_t dim,
+                           const int64_t* ids, int64_t n, float eps, float* d_table, void* stream);
+
+/* ------------------------------------------------------ I1/I2: item fronts */
+
+/* I1: out[r,:] = LayerNorm(table[ids[r],:] + field_emb[r % n_fields,:]) -- item_tower.py:239-241.
+ * mean/rstd [n] are saved for the backward. */
+int rs_std_front_fwd(const float* table, int64_t rows, int64_t dim, const int64_t* ids, int64_t n,
+                     const float* field_emb, int64_t n_fields, const float* ln_w, const float* ln_b, float eps,
+                     void* out, int out_dtype, float* mean, float* rstd, int* oob_flag, void* stream);
+
+/* I2: HF BertEmbeddings under no_grad: out[r,t,:] = LN(word[ids[r,t]] + type[0] + pos[t]) (eps 1e-12),
+ * then dropout(p) with a counter-based RNG when p > 0 (item_tower.py:248-249; the module is in
+ * train mode there, SURVEY.md 8c invariant 6). */
+int rs_bert_embed_fwd(const float* word, int64_t vocab, const float* pos, const float* type0,
+                      const float* ln_w, const float* ln_b, float eps, const int64_t* ids, int64_t n_seq,
+                      int64_t T, int64_t dim, float dropout_p, uint64_t seed,
+                      void* out, int out_dtype, int* oob_flag, void* stream);
+
+/* I2 tail: out[r,:] = sum_t feats[r,t,:]*mask[r,t] / max(sum_t mask[r,t], 1e-9) -- item_tower.py:254-257 */
+int rs_masked_mean_fwd(const void* feats, int feats_dtype, const int64_t* mask, int64_t n_seq, int64_t T,
+                       int64_t dim, float* out, void* stream);
+int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, int64_t T, int64_t dim,
+                       void* d_feats, int d_feats_dtype, void* stream);
+
+/* -------------------------------------------- C1..C5: fused in-batch softmax */
+
+/* One pass over S = scale * (A @ B^T) - col_bias, [M,N], never written to memory:
+ *   masked (i,j): j != i+diag_offset and (key_a_row[i]==key_a_col[j] or key_b_row[i]==key_b_col[j])
+ *                 -> S = mask_value  (-inf in C2/C3/C4; -1e4 / -1e9 in C5)
+ *   RS_CE_DIAG_MASK: the diagonal itself is masked (SupCon, v1_refine_usertower.py:613)
+ *   RS_CE_DIAG_RAW:  the diagonal logit skips col_bias (positive recovery, mined_inference.py:774-775)
+ *   RS_CE_SUPCON:    additionally pos_sum[i] = sum_j [key_a equal, key != 0, j != diag] S_ij and pos_cnt[i]
+ * Keys are compared on their low 32 bits: ids must lie in [0, 2^32) (item ids and batch-row user ids do).
+ * Outputs per row: lse[i] = logsumexp_j S_ij, diag[i] = S_{i,i+diag_offset}.
+ * A,B are bf16 or fp16 [M,K] / [N,K] row-major, K == 128 (tcgen05 kind::f16, fp32 accumulate in TMEM).
+ * Replaces mm + div + masks + masked_fill + cross_entropy at item_tower.py:1076-1082,
+ * tower_code/v1_refine_usertower.py:836-861, :588-625, :794-815, mined_inference.py:738-789. */
+#define RS_CE_DIAG_MASK 1
+#define RS_CE_DIAG_RAW 2
+#define RS_CE_SUPCON 4
+typedef struct {
+  const void* a;            /* [M,K] */
+  const void* b;            /* [N,K] */
+  int ab_dtype;             /* RS_BF16 or RS_F16 */
+  int64_t M, N, K;
+  float scale;              /* 1/temperature */
+  const float* col_bias;    /* [N] or NULL: lambda*logq[tgt_j] */
+  const int64_t* key_a_row; /* [M] or NULL */
+  const int64_t* key_a_col; /* [N] */
+  const int64_t* key_b_row; /* [M] or NULL */
+  const int64_t* key_b_col; /* [N] */
+  int64_t diag_offset;      /* label of row i is column i + diag_offset */
+  float mask_value;
+  int flags;
+} rs_ce_problem;
+size_t rs_ce_workspace_bytes(const rs_ce_problem* p);
+int rs_ce_fwd(const rs_ce_problem* p /*host*/, float* lse /*[M]*/, float* diag /*[M]*/,
+              float* pos_sum /*[M] or NULL*/, float* pos_cnt /*[M] or NULL*/,
+              void* workspace, size_t workspace_bytes, void* stream);
+/* Backward.  With upstream per-row weights (the gradients of the scalar loss w.r.t. lse, diag, pos_sum):
+ *   dS_ij = w_lse[i] * softmax_ij + w_diag[i] * [j == i+diag_offset] + w_pos[i] * [positive ij]
+ *   dA = scale * dS @ B   [M,K],   dB = scale * dS^T @ A   [N,K]     (fp32, overwritten)
+ * S is recomputed tile by tile on the tensor cores, dS goes TMEM -> registers -> bf16/fp16 tile in
+ * shared memory -> second tcgen05.mma; neither S nor dS ever reaches HBM.  Masked entries get no
+ * gradient (masked_fill semantics); with RS_CE_DIAG_RAW the diagonal's bias is not differentiated.
+ * w_diag / w_pos may be NULL (= 0). */
+int rs_ce_bwd(const rs_ce_problem* p /*host*/, const float* lse, const float* w_lse /*[M]*/,
+              const float* w_diag /*[M] or NULL*/, const float* w_pos /*[M] or NULL*/, float* dA, float* dB,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------- R1: top-k retrieval */
+
+/* ids/scores[b, 0..k) = top-k over items of <users[b,:], items[j,:]>, fp32, sorted by
+ * (score desc, id asc); item 0 excluded when mask_index0.  The [b, n_items] score matrix
+ * is never written.  Replaces matmul + topk at tower_code/v1_usertower_train.py:672-675,
+ * mined_inference.py:901-909,1103-1108,1536-1543, temp_model/ranker_skelet.py:193-196.
+ * k <= 1024. */
+size_t rs_topk_workspace_bytes(int64_t n_users, int64_t n_items, int64_t dim, int64_t k);
+int rs_retrieve_topk(const float* users, int64_t n_users, const float* items, int64_t n_items, int64_t dim,
+                     int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------- F1: FM / DeepFM */
+
+/* No reference implementation exists: follows deepctr-torch 0.2.9 FM.
+ * ids [B,F] local ids, offsets [F] (device) first row of each field in the concatenated
+ * tables; emb [sum_vocab,k] fp32 (k in {4,8,16,32,64,128}), lin [sum_vocab] or NULL.
+ *   fm[b]  = 0.5 * sum_d( (sum_f v)^2 - sum_f v^2 )  (+ sum_f lin[id] when lin != NULL)
+ *   concat [B,F*k] (optional, may be NULL): the gathered rows, input of the deep MLP. */
+int rs_fm_fwd(const int64_t* ids, const int64_t* offsets, int64_t B, int64_t F, const float* emb, int64_t k,
+              const float* lin, int64_t total_rows, float* fm, void* concat, int concat_dtype,
+              int* oob_flag, void* stream);
+/* d_emb[row,:] += d_fm[b]*(S_b - v) + d_concat[b,f,:];  d_lin[row] += d_fm[b]  (vector atomics). */
+int rs_fm_bwd(const int64_t* ids, const int64_t* offsets, int64_t B, int64_t F, const float* emb, int64_t k,
+              const float* d_fm, const void* d_concat, int d_concat_dtype, int64_t total_rows,
+              float* d_emb, float* d_lin, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_TWOTOWER_H_ */

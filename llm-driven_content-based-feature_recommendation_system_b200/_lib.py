@@ -1,0 +1,153 @@
+"""ctypes binding of librs_twotower.so -- the C ABI declared in include/rs_twotower.h.
+
+There is NO fallback: if the library is missing or a symbol cannot be bound,
+importing the product package's ops raises.  (The CPU oracle under oracle/ is
+test infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librs_twotower.so")
+
+RS_F32, RS_F16, RS_BF16 = 0, 1, 2
+RS_CE_DIAG_MASK, RS_CE_DIAG_RAW, RS_CE_SUPCON = 1, 2, 4
+RS_MAX_TABLES = 8
+
+_DT = {torch.float32: RS_F32, torch.float16: RS_F16, torch.bfloat16: RS_BF16}
+_DT_INV = {v: k for k, v in _DT.items()}
+
+vp, i64, i32, f32, u64, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_size_t
+
+
+class CEProblem(C.Structure):
+    """Mirror of rs_ce_problem."""
+    _fields_ = [("a", vp), ("b", vp), ("ab_dtype", i32), ("M", i64), ("N", i64), ("K", i64), ("scale", f32),
+                ("col_bias", vp), ("key_a_row", vp), ("key_a_col", vp), ("key_b_row", vp), ("key_b_col", vp),
+                ("diag_offset", i64), ("mask_value", f32), ("flags", i32)]
+
+
+# name -> (restype, argtypes); must list every function of include/rs_twotower.h
+PROTOTYPES = {
+    "rs_abi_version": (i32, []),
+    "rs_error_string": (C.c_char_p, [i32]),
+    "rs_gather_rows": (i32, [vp, i32, i64, i64, vp, i64, i64, vp, i32, vp, vp]),
+    "rs_scatter_add_rows": (i32, [vp, i32, vp, i64, i64, i64, i64, i64, f32, vp, vp, vp]),
+    "rs_sort_ids_workspace_bytes": (sz, [i64]),
+    "rs_sort_ids": (i32, [vp, i64, i64, i64, vp, vp, vp, sz, vp, vp]),
+    "rs_segment_reduce_workspace_bytes": (sz, [i64, i64]),
+    "rs_segment_reduce_rows": (i32, [vp, i32, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "rs_seq_front_fwd": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, i64, i64, i64, vp, i32, vp, vp]),
+    "rs_seq_front_bwd_workspace_bytes": (sz, [i64, i64, i64, i32, vp, vp]),
+    "rs_seq_front_bwd": (i32, [vp, i32, vp, vp, vp, vp, i32, vp, i64, i64, i64, i64, vp, vp, vp, vp, sz, vp]),
+    "rs_static_front_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp]),
+    "rs_static_front_bwd_workspace_bytes": (sz, [i64]),
+    "rs_static_front_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "rs_normalized_rows_fwd": (i32, [vp, i64, i64, vp, i64, f32, vp, i32, vp, vp, vp]),
+    "rs_normalized_rows_bwd": (i32, [vp, i32, vp, i64, i64, vp, i64, f32, vp, vp]),
+    "rs_std_front_fwd": (i32, [vp, i64, i64, vp, i64, vp, i64, vp, vp, f32, vp, i32, vp, vp, vp, vp]),
+    "rs_bert_embed_fwd": (i32, [vp, i64, vp, vp, vp, vp, f32, vp, i64, i64, i64, f32, u64, vp, i32, vp, vp]),
+    "rs_masked_mean_fwd": (i32, [vp, i32, vp, i64, i64, i64, vp, vp]),
+    "rs_masked_mean_bwd": (i32, [vp, vp, i64, i64, i64, vp, i32, vp]),
+    "rs_ce_workspace_bytes": (sz, [C.POINTER(CEProblem)]),
+    "rs_ce_fwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
+    "rs_ce_bwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "rs_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),
+    "rs_retrieve_topk": (i32, [vp, i64, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
+    "rs_fm_fwd": (i32, [vp, vp, i64, i64, vp, i64, vp, i64, vp, vp, i32, vp, vp]),
+    "rs_fm_bwd": (i32, [vp, vp, i64, i64, vp, i64, vp, vp, i32, i64, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every prototype.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python {os.path.join(_HERE, 'build.py')}` "
+            "(or __graft_entry__.build()).  This package has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().rs_error_string(code).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {code})")
+
+
+def dt(t) -> int:
+    d = t if isinstance(t, torch.dtype) else t.dtype
+    try:
+        return _DT[d]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {d}; expected float32/float16/bfloat16") from None
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return _DT_INV[code]
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ptr_array(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() if t is not None else 0 for t in ts])
+
+
+def i64_array(xs):
+    return (C.c_int64 * len(xs))(*xs)
+
+
+def i32_array(xs):
+    return (C.c_int * len(xs))(*xs)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rs_twotower ops run on CUDA tensors only (sm_100a); there is no CPU fallback")
+
+
+_oob = {}
+
+
+def oob_flag(device):
+    """Per-device int32 word set by kernels that meet an out-of-range id."""
+    key = torch.device(device).index or 0
+    f = _oob.get(key)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=device)
+        _oob[key] = f
+    return f
+
+
+def check_ids(device=None):
+    """Raise IndexError if any kernel since the last call saw an id outside its table
+    (the reference raises IndexError on CPU / a device-side assert on CUDA).  Synchronises."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    f = oob_flag(dev)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise IndexError("index out of range in an rs_twotower embedding lookup")
+
+
+def workspace(nbytes: int, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

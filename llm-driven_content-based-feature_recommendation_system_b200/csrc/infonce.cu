@@ -1,0 +1,820 @@
+// C1..C5: fused in-batch softmax cross-entropy on the 5th-gen tensor cores.
+//
+//   S = scale * (A @ B^T) - col_bias  (+ id masks)      [M, N], K = 128
+//
+// forward  : per-row logsumexp / diagonal logit / SupCon sums, S never leaves the SM
+// backward : S recomputed, dS -> bf16 tile in shared memory -> second tcgen05.mma (dS @ B), ditto
+//
+// Structure (one CTA per SM, persistent over (row block, column range) work items):
+//   warp 0     TMA producer      cp.async.bulk.tensor (SWIZZLE_128B) -> smem ring, mbarrier complete_tx
+//   warp 1     MMA issuer        one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM
+//   warps 2-9  two epilogue warpgroups, alternating tiles: tcgen05.ld TMEM -> registers, one thread per
+//              row (no shuffles), online logsumexp in the log2 domain
+// TMEM: two 128-column S accumulators (+ one 128-column dS@X accumulator in the backward).
+#include "common.cuh"
+#include "../../include/rs_twotower.h"
+#include <cuda.h>
+
+namespace rs {
+
+#define CE_BM 128
+#define CE_BN 128
+#define CE_K 128
+#define CE_STAGES 4
+#define CE_BWD_STAGES 3
+#define CE_TILE_BYTES (CE_BN * CE_K * 2)           // 32 KB: two SWIZZLE_128B boxes of [128 rows x 64 cols]
+#define CE_BOX_BYTES (CE_TILE_BYTES / 2)
+#define CE_THREADS 320
+#define CE_LOG2E 1.4426950408889634f
+#define CE_LN2 0.6931471805599453f
+
+#define MODE_PLAIN 0
+#define MODE_GENERAL 1
+#define MODE_SUPCON 2
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must fault (trap), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// smem matrix descriptors (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
+//   K-major  (rows = M/N index, 128 B of K per row): LBO field 1, SBO = 1024 B (8-row group pitch)
+//   MN-major (rows = K index, 128 B of MN per row, two 16 KB boxes along MN): LBO = 16 KB, SBO = 1024 B
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(CE_BOX_BYTES >> 4) << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, fp32 accumulate, M = 128, N = 128
+__host__ __device__ inline uint32_t make_idesc(int ab_dtype, bool b_mn_major, bool a_mn_major) {
+  const uint32_t fmt = (ab_dtype == RS_BF16) ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(CE_BN >> 3) << 17) | ((uint32_t)(CE_BM >> 4) << 24);
+}
+
+struct CeShared {
+  uint64_t full[CE_STAGES], empty[CE_STAGES];
+  uint64_t a_full[2], a_empty[2];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t p_full[2], p_empty[2];          // backward: dS tile in smem ready / consumed by the tensor core
+  uint64_t d2_full, d2_empty;              // backward: dS@X accumulator complete / drained
+  uint32_t tmem_base;
+  uint32_t pad;
+  // per epilogue warpgroup [wg][buf]: column metadata of the tile in flight (broadcast reads)
+  float col_bias[2][2][CE_BN];             // log2 units
+  uint32_t col_ka[2][2][CE_BN];
+  uint32_t col_kb[2][2][CE_BN];
+  float col_lse[2][2][CE_BN];              // backward, transposed pass (log2 units)
+  float col_wl[2][2][CE_BN], col_wd[2][2][CE_BN], col_wp[2][2][CE_BN];
+  float xm[CE_BM], xl[CE_BM], xps[CE_BM], xpc[CE_BM];   // cross-warpgroup combine (forward)
+};
+
+struct CeParams {
+  int64_t M, N;                 // rows of the row side / of the column side of THIS pass
+  float scale2;                 // scale * log2(e)
+  float mask2;                  // mask_value * log2(e)
+  const float* col_bias;        // natural units, may be null (forward, backward pass A)
+  const float* row_bias;        // backward pass B (transposed) only
+  const int64_t* key_a_row; const int64_t* key_a_col;
+  const int64_t* key_b_row; const int64_t* key_b_col;
+  int64_t diag_offset;          // the diagonal column of row r is r + diag_offset
+  int flags;
+  int tiles_per_item, nsplit, row_blocks, col_tiles;
+  uint32_t idesc_s;             // S = A B^T   (both K-major)
+  uint32_t idesc_g;             // G = dS X    (dS K-major from smem, X MN-major)
+  float* part_m; float* part_l; float* part_ps; float* part_pc; float* diag_out;     // forward
+  const float* lse; const float* w_lse; const float* w_diag; const float* w_pos;     // backward, by ORIGINAL row
+  float* part_out;              // backward: [nsplit][M][128]
+  float out_scale;
+};
+
+__device__ __forceinline__ void item_coords(const CeParams& p, int item, int& rb, int& sp, int& ct_lo, int& ct_hi) {
+  rb = item / p.nsplit;
+  sp = item % p.nsplit;
+  ct_lo = sp * p.tiles_per_item;
+  ct_hi = min(ct_lo + p.tiles_per_item, p.col_tiles);
+}
+
+__device__ __forceinline__ void ce_setup(CeShared& sh, int warp, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                         uint32_t tmem_cols) {
+  if (warp == 0 && (threadIdx.x & 31) == 0) {
+    prefetch_tmap(mapA);
+    prefetch_tmap(mapB);
+    for (int i = 0; i < CE_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh.a_full[i], 1); mbar_init(&sh.a_empty[i], 1);
+      mbar_init(&sh.tmem_full[i], 1); mbar_init(&sh.tmem_empty[i], 128);
+      mbar_init(&sh.p_full[i], 128); mbar_init(&sh.p_empty[i], 1);
+    }
+    mbar_init(&sh.d2_full, 1);
+    mbar_init(&sh.d2_empty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&sh.tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+template <int NSTAGE, int NABUF>
+__device__ __forceinline__ void producer_role(const CeParams& p, CeShared& sh, uint8_t* sA, uint8_t* sB,
+                                              const CUtensorMap* mapA, const CUtensorMap* mapB) {
+  uint32_t it = 0, item_n = 0;
+  const int n_items = p.row_blocks * p.nsplit;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+    int rb, sp, lo, hi;
+    item_coords(p, item, rb, sp, lo, hi);
+    const uint32_t ab = item_n % NABUF;
+    mbar_wait(&sh.a_empty[ab], ((item_n / NABUF) & 1) ^ 1);
+    mbar_expect_tx(&sh.a_full[ab], CE_TILE_BYTES);
+    tma_load_2d(mapA, &sh.a_full[ab], sA + ab * CE_TILE_BYTES, 0, rb * CE_BM);
+    tma_load_2d(mapA, &sh.a_full[ab], sA + ab * CE_TILE_BYTES + CE_BOX_BYTES, 64, rb * CE_BM);
+    for (int ct = lo; ct < hi; ++ct, ++it) {
+      const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+      mbar_wait(&sh.empty[s], ph ^ 1);
+      mbar_expect_tx(&sh.full[s], CE_TILE_BYTES);
+      tma_load_2d(mapB, &sh.full[s], sB + s * CE_TILE_BYTES, 0, ct * CE_BN);
+      tma_load_2d(mapB, &sh.full[s], sB + s * CE_TILE_BYTES + CE_BOX_BYTES, 64, ct * CE_BN);
+    }
+  }
+}
+
+// S(tile) = A_block @ B_tile^T into TMEM accumulator g = it & 1
+template <int NSTAGE>
+__device__ __forceinline__ void issue_s(const CeParams& p, CeShared& sh, uint8_t* sB, uint64_t adesc,
+                                        uint32_t tmem_base, uint32_t it) {
+  const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1, g = it & 1, ng = it >> 1;
+  mbar_wait(&sh.tmem_empty[g], (ng & 1) ^ 1);
+  mbar_wait(&sh.full[s], ph);
+  tc_fence_after();
+  const uint64_t bdesc = desc_kmajor(smem_u32(sB + s * CE_TILE_BYTES));
+#pragma unroll
+  for (int k = 0; k < CE_K / 16; ++k) {
+    const uint64_t off = (uint64_t)(((k >> 2) * CE_BOX_BYTES + (k & 3) * 32) >> 4);
+    umma_f16(tmem_base + g * CE_BN, adesc + off, bdesc + off, p.idesc_s, k > 0 ? 1u : 0u);
+  }
+  umma_commit(&sh.tmem_full[g]);
+}
+
+// stage the metadata of column tile `ct` for warpgroup wg into buffer buf (one column per thread)
+template <bool BWD_T>
+__device__ __forceinline__ void stage_cols(const CeParams& p, CeShared& sh, int wg, int buf, int ct, int t128) {
+  const int64_t c = (int64_t)ct * CE_BN + t128;
+  const bool ok = c < p.N;
+  sh.col_bias[wg][buf][t128] = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
+  sh.col_ka[wg][buf][t128] = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
+  sh.col_kb[wg][buf][t128] = (ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
+  if (BWD_T) {
+    sh.col_lse[wg][buf][t128] = ok ? __ldg(p.lse + c) * CE_LOG2E : 0.f;
+    sh.col_wl[wg][buf][t128] = ok ? __ldg(p.w_lse + c) : 0.f;
+    sh.col_wd[wg][buf][t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) : 0.f;
+    sh.col_wp[wg][buf][t128] = (ok && p.w_pos) ? __ldg(p.w_pos + c) : 0.f;
+  }
+}
+
+// logits of one 32-column chunk (log2 domain), masks applied; EDGE tiles also handle the diagonal and col >= N
+template <int MODE, bool EDGE>
+__device__ __forceinline__ void logits_chunk(const uint32_t (&r)[32], float (&v)[32], unsigned& posbits,
+                                             unsigned& diagbit, const float* __restrict__ bias2,
+                                             const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
+                                             float rowbias2, uint32_t my_ka, uint32_t my_kb, const CeParams& p,
+                                             int64_t col0, int64_t jd) {
+  posbits = 0u;
+  diagbit = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float a = __uint_as_float(r[j]);
+    float s;
+    bool masked = false, pos = false;
+    if (MODE == MODE_PLAIN) {
+      s = a * p.scale2;
+    } else {
+      s = fmaf(a, p.scale2, -(bias2[j] + rowbias2));
+      const bool ea = ka[j] == my_ka;
+      if (MODE == MODE_GENERAL) masked = ea | (kb[j] == my_kb);
+      else pos = ea && (my_ka != 0u);
+    }
+    if (EDGE) {
+      const int64_t col = col0 + j;
+      if (col == jd) {
+        diagbit |= 1u << j;
+        pos = false;
+        masked = (p.flags & RS_CE_DIAG_MASK) != 0;
+        if (p.flags & RS_CE_DIAG_RAW) s = a * p.scale2;
+      }
+      s = masked ? p.mask2 : s;
+      if (col >= p.N) { s = -INFINITY; pos = false; }
+    } else if (MODE == MODE_GENERAL) {
+      s = masked ? p.mask2 : s;
+    }
+    if (MODE == MODE_SUPCON && pos) posbits |= 1u << j;
+    v[j] = s;
+  }
+}
+
+// ================================================================================ forward kernel
+template <int MODE>
+__global__ void __launch_bounds__(CE_THREADS, 1)
+ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const CeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;
+  uint8_t* sB = base + 2 * CE_TILE_BYTES;
+  CeShared& sh = *reinterpret_cast<CeShared*>(base + (2 + CE_STAGES) * CE_TILE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ce_setup(sh, warp, &mapA, &mapB, 256);
+  const uint32_t tmem_base = sh.tmem_base;
+  const int n_items = p.row_blocks * p.nsplit;
+
+  if (warp == 0) {
+    if (lane == 0) producer_role<CE_STAGES, 2>(p, sh, sA, sB, &mapA, &mapB);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, item_n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        int rb, sp, lo, hi;
+        item_coords(p, item, rb, sp, lo, hi);
+        const uint32_t ab = item_n & 1;
+        mbar_wait(&sh.a_full[ab], (item_n >> 1) & 1);
+        const uint64_t adesc = desc_kmajor(smem_u32(sA + ab * CE_TILE_BYTES));
+        for (int ct = lo; ct < hi; ++ct, ++it) {
+          issue_s<CE_STAGES>(p, sh, sB, adesc, tmem_base, it);
+          umma_commit(&sh.empty[it % CE_STAGES]);
+        }
+        umma_commit(&sh.a_empty[ab]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warpgroups
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+    const int rloc = quarter * 32 + lane;
+    const int t128 = (warp - 2 - 4 * wg) * 32 + lane;   // 0..127 within the warpgroup (staging index)
+    uint32_t it = 0, nuse = 0;                          // nuse: tiles this warpgroup has consumed
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int rb, sp, lo, hi;
+      item_coords(p, item, rb, sp, lo, hi);
+      const int64_t row = (int64_t)rb * CE_BM + rloc;
+      const bool row_ok = row < p.M;
+      uint32_t my_ka = 0xFFFFFFFFu, my_kb = 0xFFFFFFFFu;
+      if (MODE != MODE_PLAIN && row_ok) {
+        if (p.key_a_row) my_ka = (uint32_t)__ldg(p.key_a_row + row);
+        if (p.key_b_row) my_kb = (uint32_t)__ldg(p.key_b_row + row);
+      }
+      const int64_t jd = row + p.diag_offset;
+      const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;   // diag col span
+      float m = -INFINITY, l = 0.f, ps = 0.f, pc = 0.f;
+      for (int ct = lo; ct < hi; ++ct, ++it) {
+        if ((int)(it & 1) != wg) continue;
+        const int buf = nuse & 1;
+        stage_cols<false>(p, sh, wg, buf, ct, t128);
+        named_bar_sync(1 + wg, 128);
+        mbar_wait(&sh.tmem_full[wg], nuse & 1);
+        tc_fence_after();
+        const int64_t c0 = (int64_t)ct * CE_BN;
+        const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          float v[32];
+          unsigned posbits, diagbit;
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN + ch * 32), r);
+          tmem_ld_wait();
+          const float* b2 = &sh.col_bias[wg][buf][ch * 32];
+          const uint32_t* ka = &sh.col_ka[wg][buf][ch * 32];
+          const uint32_t* kb = &sh.col_kb[wg][buf][ch * 32];
+          if (edge) logits_chunk<MODE, true>(r, v, posbits, diagbit, b2, ka, kb, 0.f, my_ka, my_kb, p, c0 + ch * 32, jd);
+          else logits_chunk<MODE, false>(r, v, posbits, diagbit, b2, ka, kb, 0.f, my_ka, my_kb, p, c0 + ch * 32, jd);
+          float cmax = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+          const float m_new = fmaxf(m, cmax);
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          l *= ex2(m - m_use);
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) { acc0 += ex2(v[j] - m_use); acc1 += ex2(v[j + 1] - m_use); }
+          l += acc0 + acc1;
+          m = m_new;
+          if (MODE == MODE_SUPCON) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (posbits & (1u << j)) { ps += v[j]; pc += 1.f; }
+          }
+          if (edge && diagbit && row_ok) {
+            float dv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (diagbit & (1u << j)) dv = v[j];
+            p.diag_out[row] = dv * CE_LN2;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&sh.tmem_empty[wg]);
+        ++nuse;
+      }
+      // ---- combine the two warpgroups' running (max, sum) and write this split's partial
+      if (wg == 1) { sh.xm[rloc] = m; sh.xl[rloc] = l; sh.xps[rloc] = ps; sh.xpc[rloc] = pc; }
+      named_bar_sync(3, 256);
+      if (wg == 0 && row_ok) {
+        const float m1 = sh.xm[rloc], l1 = sh.xl[rloc];
+        const float mm = fmaxf(m, m1);
+        const float mu = (mm == -INFINITY) ? 0.f : mm;
+        const float ll = l * ex2(m - mu) + l1 * ex2(m1 - mu);
+        const int64_t o = (int64_t)sp * p.M + row;
+        p.part_m[o] = mm;
+        p.part_l[o] = ll;
+        if (MODE == MODE_SUPCON) { p.part_ps[o] = ps + sh.xps[rloc]; p.part_pc[o] = pc + sh.xpc[rloc]; }
+      }
+      named_bar_sync(3, 256);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+__global__ void ce_fwd_finalize(int64_t M, int nsplit, const float* __restrict__ part_m,
+                                const float* __restrict__ part_l, const float* __restrict__ part_ps,
+                                const float* __restrict__ part_pc, float* __restrict__ lse,
+                                float* __restrict__ pos_sum, float* __restrict__ pos_cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  float mm = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, part_m[(int64_t)s * M + r]);
+  const float mu = (mm == -INFINITY) ? 0.f : mm;
+  float ll = 0.f, ps = 0.f, pc = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    ll += part_l[(int64_t)s * M + r] * exp2f(part_m[(int64_t)s * M + r] - mu);
+    if (pos_sum) { ps += part_ps[(int64_t)s * M + r]; pc += part_pc[(int64_t)s * M + r]; }
+  }
+  lse[r] = (mm + log2f(ll)) * CE_LN2;
+  if (pos_sum) { pos_sum[r] = ps * CE_LN2; pos_cnt[r] = pc; }
+}
+
+// ================================================================================ backward kernel
+// One pass computes out[r,:] = out_scale * sum_c coef(r,c) * X[c,:] for the rows r of the row side.
+//   pass A (TRANSPOSED = false): rows = A rows i, cols = B rows j, coef = dS_ij, lse/w per ROW  -> dA
+//   pass B (TRANSPOSED = true):  rows = B rows j, cols = A rows i, coef = dS_ij, lse/w per COL  -> dB
+template <int MODE, bool TRANSPOSED>
+__global__ void __launch_bounds__(CE_THREADS, 1)
+ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const CeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                                       // 1 x 32 KB (row-side operand of the item)
+  uint8_t* sB = base + CE_TILE_BYTES;                       // CE_BWD_STAGES x 32 KB (column-side tiles X)
+  uint8_t* sP = base + (1 + CE_BWD_STAGES) * CE_TILE_BYTES; // 2 x 32 KB (dS tiles, 16-bit, K-major SWIZZLE_128B)
+  CeShared& sh = *reinterpret_cast<CeShared*>(base + (3 + CE_BWD_STAGES) * CE_TILE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ce_setup(sh, warp, &mapA, &mapB, 512);
+  const uint32_t tmem_base = sh.tmem_base;
+  const int n_items = p.row_blocks * p.nsplit;
+
+  if (warp == 0) {
+    if (lane == 0) producer_role<CE_BWD_STAGES, 1>(p, sh, sA, sB, &mapA, &mapB);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, item_n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        int rb, sp, lo, hi;
+        item_coords(p, item, rb, sp, lo, hi);
+        const uint32_t ab = 0;
+        const uint32_t nt = (uint32_t)(hi - lo), it0 = it;
+        mbar_wait(&sh.a_full[ab], item_n & 1);
+        const uint64_t adesc = desc_kmajor(smem_u32(sA + ab * CE_TILE_BYTES));
+        mbar_wait(&sh.d2_empty, (item_n & 1) ^ 1);      // previous item's dS@X accumulator has been drained
+        tc_fence_after();
+        issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, it0);
+        for (uint32_t t = it0; t < it0 + nt; ++t) {
+          // S(t+1) is issued before dS(t)@X so that the other epilogue warpgroup has work meanwhile
+          if (t + 1 < it0 + nt) issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, t + 1);
+          const uint32_t s = t % CE_BWD_STAGES, g = t & 1, ng = t >> 1;
+          mbar_wait(&sh.p_full[g], ng & 1);
+          tc_fence_after();
+          const uint64_t pdesc = desc_kmajor(smem_u32(sP + g * CE_TILE_BYTES));
+          const uint64_t xdesc = desc_mnmajor(smem_u32(sB + s * CE_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < CE_BN / 16; ++k) {
+            const uint64_t aoff = (uint64_t)(((k >> 2) * CE_BOX_BYTES + (k & 3) * 32) >> 4);   // 16 columns c of dS
+            const uint64_t boff = (uint64_t)((k * 16 * 128) >> 4);                              // 16 rows c of X
+            umma_f16(tmem_base + 2 * CE_BN, pdesc + aoff, xdesc + boff, p.idesc_g, (t > it0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&sh.p_empty[g]);
+          umma_commit(&sh.empty[s]);
+        }
+        it = it0 + nt;
+        umma_commit(&sh.d2_full);
+        umma_commit(&sh.a_empty[ab]);
+      }
+    }
+  } else {
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int rloc = quarter * 32 + lane;
+    const int t128 = (warp - 2 - 4 * wg) * 32 + lane;
+    uint32_t it = 0, nuse = 0, item_n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+      int rb, sp, lo, hi;
+      item_coords(p, item, rb, sp, lo, hi);
+      const int64_t row = (int64_t)rb * CE_BM + rloc;
+      const bool row_ok = row < p.M;
+      uint32_t my_ka = 0xFFFFFFFFu, my_kb = 0xFFFFFFFFu;
+      if (MODE != MODE_PLAIN && row_ok) {
+        if (p.key_a_row) my_ka = (uint32_t)__ldg(p.key_a_row + row);
+        if (p.key_b_row) my_kb = (uint32_t)__ldg(p.key_b_row + row);
+      }
+      float rowbias2 = 0.f, lse2 = 0.f, wl = 0.f, wd = 0.f, wp = 0.f;
+      if (row_ok) {
+        if (TRANSPOSED) { if (p.row_bias) rowbias2 = __ldg(p.row_bias + row) * CE_LOG2E; }
+        else {
+          lse2 = __ldg(p.lse + row) * CE_LOG2E;
+          wl = __ldg(p.w_lse + row);
+          if (p.w_diag) wd = __ldg(p.w_diag + row);
+          if (p.w_pos) wp = __ldg(p.w_pos + row);
+        }
+      }
+      const int64_t jd = row + p.diag_offset;
+      const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;
+      for (int ct = lo; ct < hi; ++ct, ++it) {
+        if ((int)(it & 1) != wg) continue;
+        const int buf = nuse & 1;
+        stage_cols<TRANSPOSED>(p, sh, wg, buf, ct, t128);
+        named_bar_sync(1 + wg, 128);
+        mbar_wait(&sh.tmem_full[wg], nuse & 1);
+        mbar_wait(&sh.p_empty[wg], (nuse & 1) ^ 1);     // the tensor core is done with this warpgroup's dS buffer
+        tc_fence_after();
+        const int64_t c0 = (int64_t)ct * CE_BN;
+        const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
+        uint8_t* prow = sP + wg * CE_TILE_BYTES + rloc * 128;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          float v[32];
+          unsigned posbits, diagbit;
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN + ch * 32), r);
+          tmem_ld_wait();
+          const float* b2 = &sh.col_bias[wg][buf][ch * 32];
+          const uint32_t* ka = &sh.col_ka[wg][buf][ch * 32];
+          const uint32_t* kb = &sh.col_kb[wg][buf][ch * 32];
+          if (edge) logits_chunk<MODE, true>(r, v, posbits, diagbit, b2, ka, kb, rowbias2, my_ka, my_kb, p, c0 + ch * 32, jd);
+          else logits_chunk<MODE, false>(r, v, posbits, diagbit, b2, ka, kb, rowbias2, my_ka, my_kb, p, c0 + ch * 32, jd);
+          // coef = w_lse * softmax + w_diag [diag] + w_pos [positive]
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float c;
+            if (TRANSPOSED) {
+              c = sh.col_wl[wg][buf][ch * 32 + j] * ex2(v[j] - sh.col_lse[wg][buf][ch * 32 + j]);
+              if (edge && (diagbit & (1u << j))) c += sh.col_wd[wg][buf][ch * 32 + j];
+              if (MODE == MODE_SUPCON && (posbits & (1u << j))) c += sh.col_wp[wg][buf][ch * 32 + j];
+            } else {
+              c = wl * ex2(v[j] - lse2);
+              if (edge && (diagbit & (1u << j))) c += wd;
+              if (MODE == MODE_SUPCON && (posbits & (1u << j))) c += wp;
+            }
+            v[j] = c;
+          }
+          // 32 coefficients -> 4 x 16 B chunks of this row in the K-major SWIZZLE_128B tile
+          const int box = ch >> 1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            if (p.idesc_s & (1u << 7)) {
+              u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+              u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+            } else {
+              u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
+              u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
+            }
+            const int chunk = ((ch & 1) * 4 + q) ^ (rloc & 7);
+            *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = u;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&sh.tmem_empty[wg]);
+        fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
+        mbar_arrive(&sh.p_full[wg]);
+        ++nuse;
+      }
+      // ---- drain the dS@X accumulator: warpgroup wg takes columns [64*wg, 64*wg+64)
+      mbar_wait(&sh.d2_full, item_n & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        const int d0 = wg * 64 + h * 32;
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * CE_BN + d0), r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = p.part_out + ((int64_t)sp * p.M + row) * CE_K + d0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) =
+                make_float4(__uint_as_float(r[j]) * p.out_scale, __uint_as_float(r[j + 1]) * p.out_scale,
+                            __uint_as_float(r[j + 2]) * p.out_scale, __uint_as_float(r[j + 3]) * p.out_scale);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh.d2_empty);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+__global__ void ce_bwd_reduce(const float* __restrict__ part, int nsplit, int64_t n4, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < nsplit; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(part + ((int64_t)k * n4 + i) * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i * 4) = s;
+}
+
+}  // namespace rs
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace rs;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// [rows, 128] 16-bit row-major -> boxes of [128 rows x 64 cols], SWIZZLE_128B, OOB rows read as zero
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dtype) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return RS_ERR_UNSUPPORTED;
+  const cuuint64_t gdim[2] = {(cuuint64_t)CE_K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)CE_K * 2};
+  const cuuint32_t box[2] = {64, CE_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, dtype == RS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                         const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RS_OK : RS_ERR_BAD_ARG;
+}
+
+struct CePlan { int row_blocks, col_tiles, tiles_per_item, nsplit, grid; };
+static CePlan ce_plan(int64_t rows, int64_t cols, int target_items_per_sm) {
+  CePlan pl;
+  pl.row_blocks = (int)((rows + CE_BM - 1) / CE_BM);
+  pl.col_tiles = (int)((cols + CE_BN - 1) / CE_BN);
+  const int64_t pairs = (int64_t)pl.row_blocks * pl.col_tiles;
+  int64_t tpi = pairs / ((int64_t)RS_NUM_SMS * target_items_per_sm);
+  if (tpi < 1) tpi = 1;
+  if (tpi > pl.col_tiles) tpi = pl.col_tiles;
+  pl.tiles_per_item = (int)tpi;
+  pl.nsplit = (pl.col_tiles + pl.tiles_per_item - 1) / pl.tiles_per_item;
+  const int64_t items = (int64_t)pl.row_blocks * pl.nsplit;
+  pl.grid = (int)(items < RS_NUM_SMS ? items : RS_NUM_SMS);
+  return pl;
+}
+#define CE_FWD_ITEMS_PER_SM 8
+#define CE_BWD_ITEMS_PER_SM 3
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t ce_smem_bytes(bool bwd) {
+  return (size_t)(bwd ? (3 + CE_BWD_STAGES) : (2 + CE_STAGES)) * CE_TILE_BYTES + sizeof(CeShared) + 1024;
+}
+
+static int ce_validate(const rs_ce_problem* p) {
+  if (!p || !p->a || !p->b || p->M <= 0 || p->N <= 0) return RS_ERR_BAD_ARG;
+  if (p->K != CE_K) return RS_ERR_UNSUPPORTED;
+  if (p->ab_dtype != RS_BF16 && p->ab_dtype != RS_F16) return RS_ERR_BAD_ARG;
+  if ((p->key_a_row != nullptr) != (p->key_a_col != nullptr)) return RS_ERR_BAD_ARG;
+  if ((p->key_b_row != nullptr) != (p->key_b_col != nullptr)) return RS_ERR_BAD_ARG;
+  if ((p->flags & RS_CE_SUPCON) && !p->key_a_row) return RS_ERR_BAD_ARG;
+  return RS_OK;
+}
+static int ce_mode(const rs_ce_problem* p) {
+  if (p->flags & RS_CE_SUPCON) return MODE_SUPCON;
+  if (p->col_bias || p->key_a_row || p->key_b_row) return MODE_GENERAL;
+  return MODE_PLAIN;
+}
+
+extern "C" size_t rs_ce_workspace_bytes(const rs_ce_problem* p) {
+  if (ce_validate(p) != RS_OK) return 256;
+  const CePlan f = ce_plan(p->M, p->N, CE_FWD_ITEMS_PER_SM);
+  const size_t fwd = 4 * al256((size_t)f.nsplit * p->M * sizeof(float));
+  const CePlan ba = ce_plan(p->M, p->N, CE_BWD_ITEMS_PER_SM);
+  const CePlan bb = ce_plan(p->N, p->M, CE_BWD_ITEMS_PER_SM);
+  const size_t bwd_a = (size_t)ba.nsplit * p->M * CE_K * sizeof(float);
+  const size_t bwd_b = (size_t)bb.nsplit * p->N * CE_K * sizeof(float);
+  size_t m = fwd;
+  if (bwd_a > m) m = bwd_a;
+  if (bwd_b > m) m = bwd_b;
+  return m + 256;
+}
+
+static void fill_common(CeParams& k, const rs_ce_problem* p, const CePlan& pl) {
+  k.scale2 = p->scale * CE_LOG2E;
+  k.mask2 = p->mask_value * CE_LOG2E;
+  k.flags = p->flags;
+  k.tiles_per_item = pl.tiles_per_item;
+  k.nsplit = pl.nsplit;
+  k.row_blocks = pl.row_blocks;
+  k.col_tiles = pl.col_tiles;
+  k.idesc_s = make_idesc(p->ab_dtype, false, false);
+  k.idesc_g = make_idesc(p->ab_dtype, true, false);
+}
+
+extern "C" int rs_ce_fwd(const rs_ce_problem* p, float* lse, float* diag, float* pos_sum, float* pos_cnt,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ce_validate(p);
+  if (rc != RS_OK) return rc;
+  if (!lse || !diag || !workspace) return RS_ERR_BAD_ARG;
+  const int mode = ce_mode(p);
+  if (mode == MODE_SUPCON && (!pos_sum || !pos_cnt)) return RS_ERR_BAD_ARG;
+  const CePlan pl = ce_plan(p->M, p->N, CE_FWD_ITEMS_PER_SM);
+  const size_t pb = al256((size_t)pl.nsplit * p->M * sizeof(float));
+  if (workspace_bytes < 4 * pb) return RS_ERR_WORKSPACE;
+  CUtensorMap mapA, mapB;
+  if ((rc = make_map(&mapA, p->a, p->M, p->ab_dtype)) != RS_OK) return rc;
+  if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
+  CeParams k = {};
+  fill_common(k, p, pl);
+  k.M = p->M; k.N = p->N;
+  k.col_bias = p->col_bias;
+  k.key_a_row = p->key_a_row; k.key_a_col = p->key_a_col;
+  k.key_b_row = p->key_b_row; k.key_b_col = p->key_b_col;
+  k.diag_offset = p->diag_offset;
+  char* ws = (char*)workspace;
+  k.part_m = (float*)ws; k.part_l = (float*)(ws + pb); k.part_ps = (float*)(ws + 2 * pb); k.part_pc = (float*)(ws + 3 * pb);
+  k.diag_out = diag;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = ce_smem_bytes(false);
+#define LAUNCH_FWD(MODE)                                                                                 \
+  do {                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(ce_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                                 \
+    ce_fwd_kernel<MODE><<<pl.grid, CE_THREADS, smem, st>>>(mapA, mapB, k);                               \
+  } while (0)
+  if (mode == MODE_PLAIN) LAUNCH_FWD(MODE_PLAIN);
+  else if (mode == MODE_GENERAL) LAUNCH_FWD(MODE_GENERAL);
+  else LAUNCH_FWD(MODE_SUPCON);
+  RS_LAUNCH_CHECK();
+  ce_fwd_finalize<<<(int)((p->M + 255) / 256), 256, 0, st>>>(p->M, pl.nsplit, k.part_m, k.part_l, k.part_ps, k.part_pc,
+                                                             lse, mode == MODE_SUPCON ? pos_sum : nullptr, pos_cnt);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+template <bool TRANSPOSED>
+static int launch_bwd_pass(const rs_ce_problem* p, int mode, const CeParams& k, const CUtensorMap& mA,
+                           const CUtensorMap& mB, int grid, cudaStream_t st) {
+  const size_t smem = ce_smem_bytes(true);
+#define LAUNCH_BWD(MODE)                                                                                            \
+  do {                                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(ce_bwd_kernel<MODE, TRANSPOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                                \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    ce_bwd_kernel<MODE, TRANSPOSED><<<grid, CE_THREADS, smem, st>>>(mA, mB, k);                                     \
+  } while (0)
+  if (mode == MODE_PLAIN) LAUNCH_BWD(MODE_PLAIN);
+  else if (mode == MODE_GENERAL) LAUNCH_BWD(MODE_GENERAL);
+  else LAUNCH_BWD(MODE_SUPCON);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* w_lse, const float* w_diag,
+                         const float* w_pos, float* dA, float* dB, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  int rc = ce_validate(p);
+  if (rc != RS_OK) return rc;
+  if (!lse || !w_lse || !workspace || (!dA && !dB)) return RS_ERR_BAD_ARG;
+  if (workspace_bytes < rs_ce_workspace_bytes(p) - 256) return RS_ERR_WORKSPACE;
+  const int mode = ce_mode(p);
+  CUtensorMap mapA, mapB;
+  if ((rc = make_map(&mapA, p->a, p->M, p->ab_dtype)) != RS_OK) return rc;
+  if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dA) {      // pass A: rows = A, cols = B
+    const CePlan pl = ce_plan(p->M, p->N, CE_BWD_ITEMS_PER_SM);
+    CeParams k = {};
+    fill_common(k, p, pl);
+    k.M = p->M; k.N = p->N;
+    k.col_bias = p->col_bias;
+    k.key_a_row = p->key_a_row; k.key_a_col = p->key_a_col;
+    k.key_b_row = p->key_b_row; k.key_b_col = p->key_b_col;
+    k.diag_offset = p->diag_offset;
+    k.lse = lse; k.w_lse = w_lse; k.w_diag = w_diag; k.w_pos = w_pos;
+    k.part_out = (float*)workspace;
+    k.out_scale = p->scale;
+    if ((rc = launch_bwd_pass<false>(p, mode, k, mapA, mapB, pl.grid, st)) != RS_OK) return rc;
+    const int64_t n4 = p->M * CE_K / 4;
+    ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dA);
+    RS_LAUNCH_CHECK();
+  }
+  if (dB) {      // pass B: rows = B, cols = A (transposed roles)
+    const CePlan pl = ce_plan(p->N, p->M, CE_BWD_ITEMS_PER_SM);
+    CeParams k = {};
+    fill_common(k, p, pl);
+    k.M = p->N; k.N = p->M;
+    k.row_bias = p->col_bias;
+    k.key_a_row = p->key_a_col; k.key_a_col = p->key_a_row;
+    k.key_b_row = p->key_b_col; k.key_b_col = p->key_b_row;
+    k.diag_offset = -p->diag_offset;
+    k.lse = lse; k.w_lse = w_lse; k.w_diag = w_diag; k.w_pos = w_pos;
+    k.part_out = (float*)workspace;
+    k.out_scale = p->scale;
+    if ((rc = launch_bwd_pass<true>(p, mode, k, mapB, mapA, pl.grid, st)) != RS_OK) return rc;
+    const int64_t n4 = p->N * CE_K / 4;
+    ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dB);
+    RS_LAUNCH_CHECK();
+  }
+  return RS_OK;
+}

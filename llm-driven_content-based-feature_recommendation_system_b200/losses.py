@@ -1,0 +1,168 @@
+"""In-batch contrastive losses with the reference's signatures, computed by the fused
+tcgen05 softmax kernel (csrc/infonce.cu): the [N,N] logits, the three [N,N] masks and
+the log-softmax temporaries of the reference never exist in memory.
+
+Reference functions mirrored (paths relative to the reference checkout):
+    simcse_loss                        item_tower.py:1075-1082 (inline)
+    inbatch_corrected_logq_loss        tower_code/v1_refine_usertower.py:826-861 (effective def)
+    inbatch_logq_loss_no_user          tower_code/v1_refine_usertower.py:520-573 (shadowed def)
+    duorec_loss_refined                tower_code/v1_refine_usertower.py:576-627
+    logq_correction_loss               tower_code/mined_inference.py:738-749
+    efficient_corrected_logq_loss      tower_code/mined_inference.py:751-789
+
+Precision: the similarity contraction runs on the tensor cores in `COMPUTE_DTYPE`
+(bf16 by default -- BASELINE.json; the reference autocasts its matmul to fp16) with
+fp32 accumulation; softmax, logsumexp and the loss are fp32 like the reference's
+autocast policy (SURVEY.md 8c invariant 5).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+
+COMPUTE_DTYPE = torch.bfloat16
+NEG_INF = float("-inf")
+
+
+def _operand_dtype(*ts) -> torch.dtype:
+    if torch.is_autocast_enabled("cuda"):
+        d = torch.get_autocast_dtype("cuda")
+        if d in (torch.float16, torch.bfloat16):
+            return d
+    for t in ts:
+        if t.dtype in (torch.float16, torch.bfloat16):
+            return t.dtype
+    return COMPUTE_DTYPE
+
+
+class _FusedSoftmax(torch.autograd.Function):
+    """(lse, diag, pos_sum, pos_cnt) = rows of softmax statistics of S = scale*A@B^T - bias (+masks)."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value,
+                flags, dtype):
+        a16, b16 = a.detach().to(dtype).contiguous(), b.detach().to(dtype).contiguous()
+        lse, diag, pos_sum, pos_cnt = torch.ops.rs.ce_fwd(a16, b16, scale, col_bias, key_a_row, key_a_col, key_b_row,
+                                                          key_b_col, diag_offset, mask_value, flags)
+        ctx.save_for_backward(a16, b16, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, lse)
+        ctx.meta = (scale, diag_offset, mask_value, flags, a.dtype, b.dtype)
+        ctx.mark_non_differentiable(pos_cnt)
+        return lse, diag, pos_sum, pos_cnt
+
+    @staticmethod
+    def backward(ctx, g_lse, g_diag, g_pos, _g_cnt):
+        a16, b16, col_bias, kar, kac, kbr, kbc, lse = ctx.saved_tensors
+        scale, diag_offset, mask_value, flags, adt, bdt = ctx.meta
+        M = a16.shape[0]
+        zeros = None
+        if g_lse is None:
+            zeros = torch.zeros(M, dtype=torch.float32, device=a16.device)
+            g_lse = zeros
+        w_pos = g_pos.float().contiguous() if (g_pos is not None and flags & L.RS_CE_SUPCON) else None
+        w_diag = None if g_diag is None else g_diag.float().contiguous()
+        dA, dB = torch.ops.rs.ce_bwd(a16, b16, scale, col_bias, kar, kac, kbr, kbc, diag_offset, mask_value, flags,
+                                     lse, g_lse.float().contiguous(), w_diag, w_pos)
+        return (dA.to(adt), dB.to(bdt)) + (None,) * 10
+
+
+def fused_softmax_stats(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor] = None,
+                        key_a_row: Optional[Tensor] = None, key_a_col: Optional[Tensor] = None,
+                        key_b_row: Optional[Tensor] = None, key_b_col: Optional[Tensor] = None,
+                        diag_offset: int = 0, mask_value: float = NEG_INF, flags: int = 0,
+                        dtype: Optional[torch.dtype] = None):
+    dtype = dtype or _operand_dtype(a, b)
+    if col_bias is not None:
+        col_bias = col_bias.detach().float().contiguous()
+    return _FusedSoftmax.apply(a, b, float(scale), col_bias, key_a_row, key_a_col, key_b_row, key_b_col,
+                               int(diag_offset), float(mask_value), int(flags), dtype)
+
+
+def info_nce(a: Tensor, b: Tensor, temperature: float, **kw) -> Tensor:
+    """mean_i( logsumexp_j S_ij - S_i,i+off ) == F.cross_entropy(S, arange + off)."""
+    lse, diag, _, _ = fused_softmax_stats(a, b, 1.0 / temperature, **kw)
+    return (lse - diag).mean()
+
+
+# --------------------------------------------------------------------------------------------- C1
+def simcse_loss(emb1: Tensor, emb2: Tensor, temperature: float = 0.08) -> Tensor:
+    """(CE(S, diag) + CE(S^T, diag)) / 2 with S = emb1 @ emb2.T / temperature  -- item_tower.py:1075-1082."""
+    return 0.5 * (info_nce(emb1, emb2, temperature) + info_nce(emb2, emb1, temperature))
+
+
+# --------------------------------------------------------------------------------------------- C2
+def inbatch_corrected_logq_loss(user_emb: Tensor, item_tower_emb: Tensor, target_ids: Tensor, user_ids: Tensor,
+                                log_q_tensor: Tensor, temperature: float = 0.1, lambda_logq: float = 1.0) -> Tensor:
+    """tower_code/v1_refine_usertower.py:826-861.  `item_tower_emb` is the (normalised) item table; the
+    rows of the batch targets are gathered here (bit-exact gather, dense scatter-add backward)."""
+    v = ops.gather_rows(item_tower_emb, target_ids)
+    return logq_infonce_rows(user_emb, v, target_ids, user_ids, log_q_tensor, temperature, lambda_logq)
+
+
+def logq_infonce_rows(user_emb: Tensor, item_rows: Tensor, target_ids: Tensor, user_ids: Optional[Tensor],
+                      log_q_tensor: Tensor, temperature: float = 0.1, lambda_logq: float = 1.0,
+                      col_rows: Optional[Tensor] = None, col_target_ids: Optional[Tensor] = None,
+                      col_user_ids: Optional[Tensor] = None, diag_offset: int = 0) -> Tensor:
+    """C2 on already-gathered item rows.  With `col_*` given the columns are a larger (all-gathered)
+    set of negatives and `diag_offset` locates this rank's positives inside it."""
+    cols = item_rows if col_rows is None else col_rows
+    ct = target_ids if col_target_ids is None else col_target_ids
+    cu = user_ids if col_user_ids is None else col_user_ids
+    bias = (log_q_tensor[ct] * lambda_logq) if lambda_logq > 0.0 else None
+    return info_nce(user_emb, cols, temperature, col_bias=bias, key_a_row=target_ids, key_a_col=ct,
+                    key_b_row=user_ids, key_b_col=cu if user_ids is not None else None,
+                    diag_offset=diag_offset, mask_value=NEG_INF)
+
+
+def inbatch_logq_loss_no_user(user_emb, item_tower_emb, target_ids, log_q_tensor, temperature=0.1, lambda_logq=1.0):
+    """The shadowed first definition (tower_code/v1_refine_usertower.py:520-573): same-item mask only."""
+    v = ops.gather_rows(item_tower_emb, target_ids)
+    return logq_infonce_rows(user_emb, v, target_ids, None, log_q_tensor, temperature, lambda_logq)
+
+
+# --------------------------------------------------------------------------------------------- C3
+def duorec_loss_refined(user_emb_1: Tensor, user_emb_2: Tensor, target_ids: Tensor, temperature: float = 0.1,
+                        lambda_sup: float = 0.1) -> Tensor:
+    """tower_code/v1_refine_usertower.py:576-627: InfoNCE(z1, z2) + lambda_sup * SupCon(z1; same target).
+    No host synchronisation: the reference's `if mask.sum() > 0` / `valid_rows.sum() > 0` tests (:608,:623)
+    become arithmetic on device scalars."""
+    z1 = F.normalize(user_emb_1, dim=1)
+    z2 = F.normalize(user_emb_2, dim=1)
+    loss = info_nce(z1, z2, temperature)
+    if lambda_sup > 0:
+        lse, _, pos_sum, pos_cnt = fused_softmax_stats(z1, z1, 1.0 / temperature, key_a_row=target_ids,
+                                                       key_a_col=target_ids, mask_value=NEG_INF,
+                                                       flags=L.RS_CE_DIAG_MASK | L.RS_CE_SUPCON)
+        valid = pos_cnt > 0
+        per_row = torch.where(valid, lse - pos_sum / pos_cnt.clamp(min=1.0), torch.zeros_like(lse))
+        sup = per_row.sum() / valid.sum().clamp(min=1).to(per_row.dtype)
+        loss = loss + lambda_sup * sup
+    return loss
+
+
+# --------------------------------------------------------------------------------------------- C5
+def logq_correction_loss(user_emb, item_emb, pos_item_ids, item_probs, temperature=0.07, lambda_logq=0.0):
+    """tower_code/mined_inference.py:738-749: logQ applied before the division by tau, collisions at -1e4."""
+    bias = None
+    if lambda_logq > 0.0:
+        bias = lambda_logq * torch.log(item_probs[pos_item_ids] + 1e-4) / temperature
+    return info_nce(user_emb, item_emb, temperature, col_bias=bias, key_a_row=pos_item_ids, key_a_col=pos_item_ids,
+                    mask_value=-1e4)
+
+
+def efficient_corrected_logq_loss(user_emb, item_emb, pos_item_ids, precomputed_log_q, temperature=0.1,
+                                  lambda_logq=0.1):
+    """tower_code/mined_inference.py:751-789: logQ on every column, raw positive on the diagonal
+    ("positive recovery" :774-775), collisions at -1e9 (-3e4 when the logits are fp16)."""
+    dtype = _operand_dtype(user_emb, item_emb)
+    bias, flags = None, 0
+    if lambda_logq > 0.0:
+        bias = precomputed_log_q[pos_item_ids] * lambda_logq
+        flags = L.RS_CE_DIAG_RAW
+    return info_nce(user_emb, item_emb, temperature, col_bias=bias, key_a_row=pos_item_ids, key_a_col=pos_item_ids,
+                    mask_value=-30000.0 if dtype == torch.float16 else -1e9, flags=flags, dtype=dtype)

@@ -1,0 +1,649 @@
+"""torch.library custom ops (`torch.ops.rs.*`) over the C ABI, plus their autograd.
+
+Every op is a thin marshalling layer: it allocates outputs with torch, passes raw
+device pointers + sizes + the current CUDA stream to librs_twotower.so, and
+returns.  No arithmetic happens in Python and nothing here touches the CPU
+oracle.  CPU tensors are rejected (no fallback).
+"""
+from __future__ import annotations
+
+import collections
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+_lib = L.load()
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else t.contiguous()
+
+
+def _ids(t: Tensor) -> Tensor:
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _f32(t: Tensor, what: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32 (master weights), got {t.dtype}")
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# primitive ops
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op("rs::gather_rows", mutates_args=())
+def gather_rows_op(table: Tensor, ids: Tensor, clamp_max: int, out_dtype: int) -> Tensor:
+    L.require_cuda(table, ids)
+    table, ids = _c(table), _ids(ids)
+    rows, dim = table.shape
+    out = torch.empty(*ids.shape, dim, dtype=L.torch_dtype(out_dtype), device=table.device)
+    L.check(_lib.rs_gather_rows(L.ptr(table), L.dt(table), rows, dim, L.ptr(ids), ids.numel(), clamp_max,
+                                L.ptr(out), out_dtype, L.ptr(L.oob_flag(table.device)), L.stream()), "rs_gather_rows")
+    return out
+
+
+@gather_rows_op.register_fake
+def _(table, ids, clamp_max, out_dtype):
+    return table.new_empty(*ids.shape, table.shape[1], dtype=L.torch_dtype(out_dtype))
+
+
+_SortEntry = collections.namedtuple("_SortEntry", "ids version rows clamp skeys spos")
+_sort_cache: "collections.OrderedDict[tuple, _SortEntry]" = collections.OrderedDict()
+
+
+def sorted_ids(ids: Tensor, rows: int, clamp_max: int = -1) -> Tuple[Tensor, Tensor]:
+    """Stable (id, position) sort, cached per ids tensor (the two dropout views of a step and the
+    forward/backward of one table share the same ids)."""
+    key = (ids.data_ptr(), ids._version, ids.numel(), rows, clamp_max)
+    e = _sort_cache.get(key)
+    if e is not None and e.ids is ids:
+        return e.skeys, e.spos
+    n = ids.numel()
+    sk = torch.empty(n, dtype=torch.int32, device=ids.device)
+    sp = torch.empty(n, dtype=torch.int32, device=ids.device)
+    wsb = _lib.rs_sort_ids_workspace_bytes(n)
+    ws = L.workspace(wsb, ids.device)
+    L.check(_lib.rs_sort_ids(L.ptr(ids), n, rows, clamp_max, L.ptr(sk), L.ptr(sp), L.ptr(ws), ws.numel(),
+                             L.ptr(L.oob_flag(ids.device)), L.stream()), "rs_sort_ids")
+    _sort_cache[key] = _SortEntry(ids, ids._version, rows, clamp_max, sk, sp)
+    while len(_sort_cache) > 8:
+        _sort_cache.popitem(last=False)
+    return sk, sp
+
+
+@torch.library.custom_op("rs::embedding_dense_bwd", mutates_args=())
+def embedding_dense_bwd_op(grad: Tensor, ids: Tensor, rows: int, padding_idx: int, clamp_max: int,
+                           deterministic: bool) -> Tensor:
+    """Dense [rows, dim] fp32 gradient of gather_rows (== aten::embedding_dense_backward)."""
+    L.require_cuda(grad, ids)
+    ids = _ids(ids)
+    dim = grad.shape[-1]
+    grad = grad.reshape(-1, dim).contiguous()
+    d_table = torch.zeros(rows, dim, dtype=torch.float32, device=grad.device)
+    n = ids.numel()
+    if n == 0:
+        return d_table
+    if deterministic:
+        sk, sp = sorted_ids(ids, rows, clamp_max)
+        wsb = _lib.rs_segment_reduce_workspace_bytes(n, dim)
+        ws = L.workspace(wsb, grad.device)
+        L.check(_lib.rs_segment_reduce_rows(L.ptr(grad), L.dt(grad), L.ptr(sk), L.ptr(sp), n, dim, rows, padding_idx,
+                                            None, None, L.ptr(d_table), None, L.ptr(ws), ws.numel(), L.stream()),
+                "rs_segment_reduce_rows")
+    else:
+        L.check(_lib.rs_scatter_add_rows(L.ptr(grad), L.dt(grad), L.ptr(ids), n, dim, rows, padding_idx, clamp_max,
+                                         1.0, L.ptr(d_table), L.ptr(L.oob_flag(grad.device)), L.stream()),
+                "rs_scatter_add_rows")
+    return d_table
+
+
+@embedding_dense_bwd_op.register_fake
+def _(grad, ids, rows, padding_idx, clamp_max, deterministic):
+    return grad.new_empty(rows, grad.shape[-1], dtype=torch.float32)
+
+
+@torch.library.custom_op("rs::seq_front", mutates_args=())
+def seq_front_op(base: Optional[Tensor], ids: Sequence[Tensor], tables: Sequence[Tensor], gates: Tensor,
+                 pos_table: Optional[Tensor], seq_len: int, out_dtype: int) -> Tensor:
+    L.require_cuda(gates, *ids, *tables)
+    n = len(tables)
+    ids = [_ids(i) for i in ids]
+    tables = [_f32(t, "embedding table") for t in tables]
+    base = _c(base)
+    pos_table = None if pos_table is None else _f32(pos_table, "pos table")
+    dim = tables[0].shape[1] if n else (base.shape[-1] if base is not None else pos_table.shape[1])
+    shape = ids[0].shape if n else base.shape[:-1]
+    P = 1
+    for s in shape:
+        P *= s
+    out = torch.empty(*shape, dim, dtype=L.torch_dtype(out_dtype), device=gates.device)
+    gates = _f32(gates, "gates")
+    L.check(_lib.rs_seq_front_fwd(L.ptr(base), L.dt(base) if base is not None else 0, L.ptr_array(ids),
+                                  L.ptr_array(tables), L.i64_array([t.shape[0] for t in tables]), n, L.ptr(gates),
+                                  L.ptr(pos_table), seq_len, P, dim, L.ptr(out), out_dtype,
+                                  L.ptr(L.oob_flag(gates.device)), L.stream()), "rs_seq_front_fwd")
+    return out
+
+
+@seq_front_op.register_fake
+def _(base, ids, tables, gates, pos_table, seq_len, out_dtype):
+    dim = tables[0].shape[1]
+    return tables[0].new_empty(*ids[0].shape, dim, dtype=L.torch_dtype(out_dtype))
+
+
+# a table this small is reduced in per-warp private shared-memory copies (deterministic, no atomics)
+SMALL_TABLE_ROWS = 24
+
+
+@torch.library.custom_op("rs::seq_front_bwd", mutates_args=())
+def seq_front_bwd_op(dx: Tensor, ids: Sequence[Tensor], tables: Sequence[Tensor], gates: Tensor, seq_len: int,
+                     padding_idx: int, deterministic: bool) -> List[Tensor]:
+    """Returns [d_table_0 .. d_table_{n-1}, d_gates, d_pos]."""
+    L.require_cuda(dx, gates)
+    n = len(tables)
+    ids = [_ids(i) for i in ids]
+    tables = [_f32(t, "embedding table") for t in tables]
+    gates = _f32(gates, "gates")
+    dim = dx.shape[-1]
+    dx = dx.reshape(-1, dim).contiguous()
+    P = dx.shape[0]
+    dev = dx.device
+    rows = [t.shape[0] for t in tables]
+    small_budget = SMALL_TABLE_ROWS
+    mode = []
+    for r in rows:
+        if r <= small_budget:
+            mode.append(2)
+            small_budget -= r
+        else:
+            mode.append(0 if deterministic else 1)
+    d_tables = [torch.zeros(r, dim, dtype=torch.float32, device=dev) for r in rows]
+    d_gates = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+    d_pos = torch.empty(seq_len, dim, dtype=torch.float32, device=dev)
+    rows_a, mode_a = L.i64_array(rows), L.i32_array(mode)
+    wsb = _lib.rs_seq_front_bwd_workspace_bytes(P, seq_len, dim, n, rows_a, mode_a)
+    if wsb == 0:
+        raise RuntimeError("rs_seq_front_bwd: unsupported shape")
+    ws = L.workspace(wsb, dev)
+    L.check(_lib.rs_seq_front_bwd(L.ptr(dx), L.dt(dx), L.ptr_array(ids), L.ptr_array(tables), rows_a, mode_a, n,
+                                  L.ptr(gates), seq_len, P, dim, padding_idx, L.ptr_array(d_tables), L.ptr(d_gates),
+                                  L.ptr(d_pos), L.ptr(ws), ws.numel(), L.stream()), "rs_seq_front_bwd")
+    for t in range(n):
+        if mode[t] != 0:
+            continue
+        sk, sp = sorted_ids(ids[t], rows[t])
+        wsb = _lib.rs_segment_reduce_workspace_bytes(P, dim)
+        ws2 = L.workspace(wsb, dev)
+        L.check(_lib.rs_segment_reduce_rows(L.ptr(dx), L.dt(dx), L.ptr(sk), L.ptr(sp), P, dim, rows[t], padding_idx,
+                                            L.ptr(gates[t:t + 1]), L.ptr(tables[t]), L.ptr(d_tables[t]),
+                                            L.ptr(d_gates[t:t + 1]), L.ptr(ws2), ws2.numel(), L.stream()),
+                "rs_segment_reduce_rows")
+    return d_tables + [d_gates, d_pos]
+
+
+@seq_front_bwd_op.register_fake
+def _(dx, ids, tables, gates, seq_len, padding_idx, deterministic):
+    dim = dx.shape[-1]
+    return [t.new_empty(t.shape) for t in tables] + [gates.new_empty(len(tables)), gates.new_empty(seq_len, dim)]
+
+
+@torch.library.custom_op("rs::static_front", mutates_args=())
+def static_front_op(ids: Sequence[Tensor], tables: Sequence[Tensor], cont: Tensor, cont_w: Tensor, cont_b: Tensor,
+                    gates: Tensor) -> Tensor:
+    L.require_cuda(cont, gates)
+    assert len(ids) == 9 and len(tables) == 9
+    ids = [_ids(i) for i in ids]
+    tables = [_f32(t, "static table") for t in tables]
+    cont, cont_w, cont_b, gates = _f32(cont, "cont"), _f32(cont_w, "cont_w"), _f32(cont_b, "cont_b"), _f32(gates, "g")
+    B = cont.shape[0]
+    out = torch.empty(B, 100, dtype=torch.float32, device=cont.device)
+    L.check(_lib.rs_static_front_fwd(L.ptr_array(ids), L.ptr_array(tables), L.i64_array([t.shape[0] for t in tables]),
+                                     L.ptr(cont), L.ptr(cont_w), L.ptr(cont_b), L.ptr(gates), B, L.ptr(out),
+                                     L.ptr(L.oob_flag(cont.device)), L.stream()), "rs_static_front_fwd")
+    return out
+
+
+@static_front_op.register_fake
+def _(ids, tables, cont, cont_w, cont_b, gates):
+    return cont.new_empty(cont.shape[0], 100)
+
+
+@torch.library.custom_op("rs::static_front_bwd", mutates_args=())
+def static_front_bwd_op(d_out: Tensor, ids: Sequence[Tensor], tables: Sequence[Tensor], cont: Tensor,
+                        cont_w: Tensor, cont_b: Tensor, gates: Tensor, padding_idx: int) -> List[Tensor]:
+    """Returns [d_table_0..8, d_gates[10], d_cont_w[16,4], d_cont_b[16]]."""
+    ids = [_ids(i) for i in ids]
+    tables = [_f32(t, "static table") for t in tables]
+    d_out = _f32(d_out, "d_out")
+    cont, cont_w, cont_b, gates = _f32(cont, "cont"), _f32(cont_w, "cont_w"), _f32(cont_b, "cont_b"), _f32(gates, "g")
+    B, dev = cont.shape[0], cont.device
+    d_tables = [torch.zeros_like(t) for t in tables]
+    d_gates = torch.empty(10, dtype=torch.float32, device=dev)
+    d_w = torch.empty(16, 4, dtype=torch.float32, device=dev)
+    d_b = torch.empty(16, dtype=torch.float32, device=dev)
+    ws = L.workspace(_lib.rs_static_front_bwd_workspace_bytes(B), dev)
+    L.check(_lib.rs_static_front_bwd(L.ptr(d_out), L.ptr_array(ids), L.ptr_array(tables),
+                                     L.i64_array([t.shape[0] for t in tables]), L.ptr(cont), L.ptr(cont_w),
+                                     L.ptr(cont_b), L.ptr(gates), B, padding_idx, L.ptr_array(d_tables),
+                                     L.ptr(d_gates), L.ptr(d_w), L.ptr(d_b), L.ptr(ws), ws.numel(), L.stream()),
+            "rs_static_front_bwd")
+    return d_tables + [d_gates, d_w, d_b]
+
+
+@static_front_bwd_op.register_fake
+def _(d_out, ids, tables, cont, cont_w, cont_b, gates, padding_idx):
+    return [torch.empty_like(t) for t in tables] + [gates.new_empty(10), gates.new_empty(16, 4), gates.new_empty(16)]
+
+
+@torch.library.custom_op("rs::normalized_rows", mutates_args=())
+def normalized_rows_op(table: Tensor, ids: Tensor, eps: float, out_dtype: int) -> Tensor:
+    L.require_cuda(table, ids)
+    table, ids = _f32(table, "item matrix"), _ids(ids)
+    rows, dim = table.shape
+    out = torch.empty(*ids.shape, dim, dtype=L.torch_dtype(out_dtype), device=table.device)
+    L.check(_lib.rs_normalized_rows_fwd(L.ptr(table), rows, dim, L.ptr(ids), ids.numel(), eps, L.ptr(out), out_dtype,
+                                        None, L.ptr(L.oob_flag(table.device)), L.stream()), "rs_normalized_rows_fwd")
+    return out
+
+
+@normalized_rows_op.register_fake
+def _(table, ids, eps, out_dtype):
+    return table.new_empty(*ids.shape, table.shape[1], dtype=L.torch_dtype(out_dtype))
+
+
+@torch.library.custom_op("rs::normalized_rows_bwd", mutates_args=())
+def normalized_rows_bwd_op(grad: Tensor, table: Tensor, ids: Tensor, eps: float) -> Tensor:
+    table, ids = _f32(table, "item matrix"), _ids(ids)
+    rows, dim = table.shape
+    grad = grad.reshape(-1, dim).contiguous()
+    d_table = torch.zeros_like(table)
+    L.check(_lib.rs_normalized_rows_bwd(L.ptr(grad), L.dt(grad), L.ptr(table), rows, dim, L.ptr(ids), ids.numel(),
+                                        eps, L.ptr(d_table), L.stream()), "rs_normalized_rows_bwd")
+    return d_table
+
+
+@normalized_rows_bwd_op.register_fake
+def _(grad, table, ids, eps):
+    return torch.empty_like(table)
+
+
+@torch.library.custom_op("rs::std_front", mutates_args=())
+def std_front_op(table: Tensor, ids: Tensor, field_emb: Tensor, ln_w: Tensor, ln_b: Tensor, eps: float,
+                 out_dtype: int) -> Tensor:
+    L.require_cuda(table, ids)
+    table, ids = _f32(table, "std_embedding"), _ids(ids)
+    field_emb = _f32(field_emb, "std_field_emb").reshape(-1, table.shape[1])
+    rows, dim = table.shape
+    out = torch.empty(*ids.shape, dim, dtype=L.torch_dtype(out_dtype), device=table.device)
+    L.check(_lib.rs_std_front_fwd(L.ptr(table), rows, dim, L.ptr(ids), ids.numel(), L.ptr(field_emb),
+                                  field_emb.shape[0], L.ptr(_f32(ln_w, "ln_w")), L.ptr(_f32(ln_b, "ln_b")), eps,
+                                  L.ptr(out), out_dtype, None, None, L.ptr(L.oob_flag(table.device)), L.stream()),
+            "rs_std_front_fwd")
+    return out
+
+
+@std_front_op.register_fake
+def _(table, ids, field_emb, ln_w, ln_b, eps, out_dtype):
+    return table.new_empty(*ids.shape, table.shape[1], dtype=L.torch_dtype(out_dtype))
+
+
+@torch.library.custom_op("rs::bert_embed", mutates_args=())
+def bert_embed_op(word: Tensor, pos: Tensor, tok_type: Tensor, ln_w: Tensor, ln_b: Tensor, eps: float, ids: Tensor,
+                  dropout_p: float, seed: int, out_dtype: int) -> Tensor:
+    L.require_cuda(word, ids)
+    word, ids = _f32(word, "word_embeddings"), _ids(ids)
+    vocab, dim = word.shape
+    T = ids.shape[-1]
+    pos = _f32(pos, "position_embeddings")
+    if pos.shape[0] < T:
+        raise IndexError("sequence longer than the position table")
+    out = torch.empty(*ids.shape, dim, dtype=L.torch_dtype(out_dtype), device=word.device)
+    L.check(_lib.rs_bert_embed_fwd(L.ptr(word), vocab, L.ptr(pos), L.ptr(_f32(tok_type, "token_type")[0].contiguous()),
+                                   L.ptr(_f32(ln_w, "ln_w")), L.ptr(_f32(ln_b, "ln_b")), eps, L.ptr(ids),
+                                   ids.numel() // T, T, dim, dropout_p, seed, L.ptr(out), out_dtype,
+                                   L.ptr(L.oob_flag(word.device)), L.stream()), "rs_bert_embed_fwd")
+    return out
+
+
+@bert_embed_op.register_fake
+def _(word, pos, tok_type, ln_w, ln_b, eps, ids, dropout_p, seed, out_dtype):
+    return word.new_empty(*ids.shape, word.shape[1], dtype=L.torch_dtype(out_dtype))
+
+
+@torch.library.custom_op("rs::masked_mean", mutates_args=())
+def masked_mean_op(feats: Tensor, mask: Tensor) -> Tensor:
+    L.require_cuda(feats, mask)
+    feats, mask = _c(feats), _ids(mask)
+    R, T, D = feats.shape
+    out = torch.empty(R, D, dtype=torch.float32, device=feats.device)
+    L.check(_lib.rs_masked_mean_fwd(L.ptr(feats), L.dt(feats), L.ptr(mask), R, T, D, L.ptr(out), L.stream()),
+            "rs_masked_mean_fwd")
+    return out
+
+
+@masked_mean_op.register_fake
+def _(feats, mask):
+    return feats.new_empty(feats.shape[0], feats.shape[2], dtype=torch.float32)
+
+
+@torch.library.custom_op("rs::masked_mean_bwd", mutates_args=())
+def masked_mean_bwd_op(d_out: Tensor, mask: Tensor, out_dtype: int) -> Tensor:
+    d_out, mask = _f32(d_out, "d_out"), _ids(mask)
+    R, T = mask.shape
+    D = d_out.shape[1]
+    d_feats = torch.empty(R, T, D, dtype=L.torch_dtype(out_dtype), device=d_out.device)
+    L.check(_lib.rs_masked_mean_bwd(L.ptr(d_out), L.ptr(mask), R, T, D, L.ptr(d_feats), out_dtype, L.stream()),
+            "rs_masked_mean_bwd")
+    return d_feats
+
+
+@masked_mean_bwd_op.register_fake
+def _(d_out, mask, out_dtype):
+    return d_out.new_empty(mask.shape[0], mask.shape[1], d_out.shape[1], dtype=L.torch_dtype(out_dtype))
+
+
+@torch.library.custom_op("rs::retrieve_topk", mutates_args=())
+def retrieve_topk_op(users: Tensor, items: Tensor, k: int, mask_index0: bool) -> Tuple[Tensor, Tensor]:
+    L.require_cuda(users, items)
+    users, items = _f32(users, "user_emb"), _f32(items, "item_emb")
+    nu, dim = users.shape
+    ni = items.shape[0]
+    if k > ni:
+        raise RuntimeError("selected index k out of range")          # torch.topk's message
+    ids = torch.empty(nu, k, dtype=torch.int64, device=users.device)
+    scores = torch.empty(nu, k, dtype=torch.float32, device=users.device)
+    ws = L.workspace(_lib.rs_topk_workspace_bytes(nu, ni, dim, k), users.device)
+    L.check(_lib.rs_retrieve_topk(L.ptr(users), nu, L.ptr(items), ni, dim, k, int(mask_index0), L.ptr(ids),
+                                  L.ptr(scores), L.ptr(ws), ws.numel(), L.stream()), "rs_retrieve_topk")
+    return scores, ids
+
+
+@retrieve_topk_op.register_fake
+def _(users, items, k, mask_index0):
+    return users.new_empty(users.shape[0], k), users.new_empty(users.shape[0], k, dtype=torch.int64)
+
+
+@torch.library.custom_op("rs::fm_fwd", mutates_args=())
+def fm_fwd_op(ids: Tensor, offsets: Tensor, emb: Tensor, lin: Optional[Tensor], want_concat: bool,
+              concat_dtype: int) -> Tuple[Tensor, Tensor]:
+    L.require_cuda(ids, emb)
+    ids, offsets, emb = _ids(ids), _ids(offsets), _f32(emb, "fm embedding table")
+    B, F = ids.shape
+    total, k = emb.shape
+    fm = torch.empty(B, dtype=torch.float32, device=emb.device)
+    concat = torch.empty((B, F * k) if want_concat else (0,), dtype=L.torch_dtype(concat_dtype), device=emb.device)
+    lin_ = None if lin is None else _f32(lin, "fm linear table").reshape(-1)
+    L.check(_lib.rs_fm_fwd(L.ptr(ids), L.ptr(offsets), B, F, L.ptr(emb), k, L.ptr(lin_), total, L.ptr(fm),
+                           L.ptr(concat) if want_concat else None, concat_dtype, L.ptr(L.oob_flag(emb.device)),
+                           L.stream()), "rs_fm_fwd")
+    return fm, concat
+
+
+@fm_fwd_op.register_fake
+def _(ids, offsets, emb, lin, want_concat, concat_dtype):
+    B, F = ids.shape
+    return emb.new_empty(B), emb.new_empty((B, F * emb.shape[1]) if want_concat else (0,),
+                                           dtype=L.torch_dtype(concat_dtype))
+
+
+@torch.library.custom_op("rs::fm_bwd", mutates_args=())
+def fm_bwd_op(ids: Tensor, offsets: Tensor, emb: Tensor, d_fm: Optional[Tensor], d_concat: Optional[Tensor],
+              want_lin: bool) -> Tuple[Tensor, Tensor]:
+    ids, offsets, emb = _ids(ids), _ids(offsets), _f32(emb, "fm embedding table")
+    B, F = ids.shape
+    total, k = emb.shape
+    d_emb = torch.zeros_like(emb)
+    d_lin = torch.zeros(total if want_lin else 0, dtype=torch.float32, device=emb.device)
+    d_fm_ = None if d_fm is None else _f32(d_fm, "d_fm")
+    d_concat = _c(d_concat)
+    L.check(_lib.rs_fm_bwd(L.ptr(ids), L.ptr(offsets), B, F, L.ptr(emb), k, L.ptr(d_fm_), L.ptr(d_concat),
+                           L.dt(d_concat) if d_concat is not None else 0, total, L.ptr(d_emb),
+                           L.ptr(d_lin) if want_lin else None, L.stream()), "rs_fm_bwd")
+    return d_emb, d_lin
+
+
+@fm_bwd_op.register_fake
+def _(ids, offsets, emb, d_fm, d_concat, want_lin):
+    return torch.empty_like(emb), emb.new_empty(emb.shape[0] if want_lin else 0)
+
+
+# ---- fused in-batch softmax -------------------------------------------------------------------
+def _ce_problem(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags):
+    p = L.CEProblem()
+    p.a, p.b = a.data_ptr(), b.data_ptr()
+    p.ab_dtype = L.dt(a)
+    p.M, p.N, p.K = a.shape[0], b.shape[0], a.shape[1]
+    p.scale = scale
+    p.col_bias = col_bias.data_ptr() if col_bias is not None else None
+    p.key_a_row = key_a_row.data_ptr() if key_a_row is not None else None
+    p.key_a_col = key_a_col.data_ptr() if key_a_col is not None else None
+    p.key_b_row = key_b_row.data_ptr() if key_b_row is not None else None
+    p.key_b_col = key_b_col.data_ptr() if key_b_col is not None else None
+    p.diag_offset, p.mask_value, p.flags = diag_offset, mask_value, flags
+    return p
+
+
+def _ce_prepare(a, b, col_bias, keys):
+    if a.dtype not in (torch.bfloat16, torch.float16) or b.dtype != a.dtype:
+        raise TypeError("fused softmax operands must both be bfloat16 or float16")
+    a, b = a.contiguous(), b.contiguous()
+    col_bias = None if col_bias is None else _f32(col_bias, "col_bias")
+    keys = [None if k is None else _ids(k) for k in keys]
+    return a, b, col_bias, keys
+
+
+@torch.library.custom_op("rs::ce_fwd", mutates_args=())
+def ce_fwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], key_a_row: Optional[Tensor],
+              key_a_col: Optional[Tensor], key_b_row: Optional[Tensor], key_b_col: Optional[Tensor],
+              diag_offset: int, mask_value: float, flags: int) -> List[Tensor]:
+    """Returns [lse[M], diag[M], pos_sum[M], pos_cnt[M]] (the last two only meaningful with RS_CE_SUPCON)."""
+    L.require_cuda(a, b)
+    a, b, col_bias, keys = _ce_prepare(a, b, col_bias, [key_a_row, key_a_col, key_b_row, key_b_col])
+    M, dev = a.shape[0], a.device
+    lse = torch.empty(M, dtype=torch.float32, device=dev)
+    diag = torch.empty(M, dtype=torch.float32, device=dev)
+    sup = bool(flags & L.RS_CE_SUPCON)
+    pos_sum = torch.empty(M if sup else 0, dtype=torch.float32, device=dev)
+    pos_cnt = torch.empty(M if sup else 0, dtype=torch.float32, device=dev)
+    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags)
+    ws = L.workspace(_lib.rs_ce_workspace_bytes(p), dev)
+    L.check(_lib.rs_ce_fwd(p, L.ptr(lse), L.ptr(diag), L.ptr(pos_sum) if sup else None,
+                           L.ptr(pos_cnt) if sup else None, L.ptr(ws), ws.numel(), L.stream()), "rs_ce_fwd")
+    return [lse, diag, pos_sum, pos_cnt]
+
+
+@ce_fwd_op.register_fake
+def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags):
+    M = a.shape[0]
+    n = M if flags & L.RS_CE_SUPCON else 0
+    f = lambda k: a.new_empty(k, dtype=torch.float32)
+    return [f(M), f(M), f(n), f(n)]
+
+
+@torch.library.custom_op("rs::ce_bwd", mutates_args=())
+def ce_bwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], key_a_row: Optional[Tensor],
+              key_a_col: Optional[Tensor], key_b_row: Optional[Tensor], key_b_col: Optional[Tensor],
+              diag_offset: int, mask_value: float, flags: int, lse: Tensor, w_lse: Tensor,
+              w_diag: Optional[Tensor], w_pos: Optional[Tensor]) -> List[Tensor]:
+    """Returns [dA[M,K], dB[N,K]] in fp32 for dS = w_lse*softmax + w_diag*[diag] + w_pos*[positive]."""
+    a, b, col_bias, keys = _ce_prepare(a, b, col_bias, [key_a_row, key_a_col, key_b_row, key_b_col])
+    dev = a.device
+    dA = torch.empty(a.shape, dtype=torch.float32, device=dev)
+    dB = torch.empty(b.shape, dtype=torch.float32, device=dev)
+    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags)
+    ws = L.workspace(_lib.rs_ce_workspace_bytes(p), dev)
+    w_diag_ = None if w_diag is None else _f32(w_diag, "w_diag")
+    w_pos_ = None if w_pos is None else _f32(w_pos, "w_pos")
+    L.check(_lib.rs_ce_bwd(p, L.ptr(_f32(lse, "lse")), L.ptr(_f32(w_lse, "w_lse")), L.ptr(w_diag_), L.ptr(w_pos_),
+                           L.ptr(dA), L.ptr(dB), L.ptr(ws), ws.numel(), L.stream()), "rs_ce_bwd")
+    return [dA, dB]
+
+
+@ce_bwd_op.register_fake
+def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags, lse, w_lse,
+      w_diag, w_pos):
+    return [a.new_empty(a.shape, dtype=torch.float32), b.new_empty(b.shape, dtype=torch.float32)]
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd
+# ---------------------------------------------------------------------------------------------
+DETERMINISTIC = True        # sorted segment-reduce backward (default); False -> vector atomics
+
+
+def _out_dtype(*float_inputs) -> int:
+    """Output dtype: the autocast dtype when autocast is on (what nn.Linear would hand on), else fp32."""
+    if torch.is_autocast_enabled("cuda"):
+        return L.dt(torch.get_autocast_dtype("cuda"))
+    return L.RS_F32
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, ids, padding_idx, clamp_max, out_dtype):
+        ctx.save_for_backward(ids)
+        ctx.meta = (table.shape[0], padding_idx, clamp_max, table.dtype)
+        return torch.ops.rs.gather_rows(table, ids, clamp_max, out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        rows, padding_idx, clamp_max, tdt = ctx.meta
+        d = torch.ops.rs.embedding_dense_bwd(g, ids, rows, padding_idx, clamp_max, DETERMINISTIC)
+        return d.to(tdt), None, None, None, None
+
+
+def gather_rows(table: Tensor, ids: Tensor, padding_idx: int = -1, clamp_max: int = -1,
+                out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """`table[ids]` / `F.embedding(ids, table, padding_idx)`; rows are copied bit-exactly."""
+    od = L.dt(out_dtype) if out_dtype is not None else L.dt(table)
+    return _GatherRows.apply(table, ids, padding_idx, clamp_max, od)
+
+
+class _SeqFront(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base, gates, pos_table, padding_idx, out_dtype, n_live, *rest):
+        # rest = ids[0..n) + tables[0..n); the first n_live tables are gathered, the others have a gate
+        # that is hard-masked to 0 (s_mask, v1_refine_usertower.py:437): exact zeros, never read
+        n = len(rest) // 2
+        ids, tables = list(rest[:n]), list(rest[n:])
+        L_ = ids[0].shape[-1]
+        out = torch.ops.rs.seq_front(base, ids[:n_live], tables[:n_live], gates[:n_live].contiguous(), pos_table, L_,
+                                     out_dtype)
+        ctx.save_for_backward(gates, *ids[:n_live], *tables)
+        ctx.meta = (n, n_live, L_, padding_idx, None if base is None else base.dtype, pos_table is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        n, n_live, L_, padding_idx, base_dtype, has_pos = ctx.meta
+        gates = ctx.saved_tensors[0]
+        ids = list(ctx.saved_tensors[1:1 + n_live])
+        tables = list(ctx.saved_tensors[1 + n_live:])
+        res = torch.ops.rs.seq_front_bwd(dx, ids, tables[:n_live], gates[:n_live].contiguous(), L_, padding_idx,
+                                         DETERMINISTIC)
+        d_tables = list(res[:n_live]) + [torch.zeros_like(t) for t in tables[n_live:]]
+        d_gates = torch.zeros_like(gates)
+        d_gates[:n_live] = res[n_live][:n_live]
+        d_pos = res[n_live + 1] if has_pos else None
+        d_base = None if base_dtype is None else dx.to(base_dtype)
+        return (d_base, d_gates, d_pos, None, None, None, *([None] * n), *d_tables)
+
+
+def seq_front(base, ids, tables, gates, pos_table, padding_idx=0, n_live=None, out_dtype=None):
+    """U1: base + sum_t gates[t]*tables[t][ids[t]] + pos_table[arange(L)]  (v1_refine_usertower.py:447-456)."""
+    n_live = len(tables) if n_live is None else n_live
+    od = L.dt(out_dtype) if out_dtype is not None else _out_dtype()
+    return _SeqFront.apply(base, gates, pos_table, padding_idx, od, n_live, *ids, *tables)
+
+
+class _StaticFront(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cont, cont_w, cont_b, gates, padding_idx, *rest):
+        ids, tables = list(rest[:9]), list(rest[9:])
+        ctx.save_for_backward(cont, cont_w, cont_b, gates, *ids, *tables)
+        ctx.padding_idx = padding_idx
+        return torch.ops.rs.static_front(ids, tables, cont, cont_w, cont_b, gates)
+
+    @staticmethod
+    def backward(ctx, g):
+        cont, cont_w, cont_b, gates = ctx.saved_tensors[:4]
+        ids, tables = list(ctx.saved_tensors[4:13]), list(ctx.saved_tensors[13:])
+        res = torch.ops.rs.static_front_bwd(g.float().contiguous(), ids, tables, cont, cont_w, cont_b, gates,
+                                            ctx.padding_idx)
+        return (None, res[10], res[11], res[9], None, *([None] * 9), *res[:9])
+
+
+def static_front(ids, tables, cont, cont_w, cont_b, gates, padding_idx=0):
+    """U2: nine gated tiny gathers + gated relu(Linear(4->16)) -> [B,100]  (v1_refine_usertower.py:472-491)."""
+    return _StaticFront.apply(cont, cont_w, cont_b, gates, padding_idx, *ids, *tables)
+
+
+class _NormalizedRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, ids, eps, out_dtype):
+        ctx.save_for_backward(table, ids)
+        ctx.eps = eps
+        return torch.ops.rs.normalized_rows(table, ids, eps, out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        table, ids = ctx.saved_tensors
+        return torch.ops.rs.normalized_rows_bwd(g, table, ids, ctx.eps), None, None, None
+
+
+def normalized_rows(table, ids, eps: float = 1e-12, out_dtype=None):
+    """U4: F.normalize(table, p=2, dim=1)[ids] without touching the rows that are not asked for."""
+    od = L.dt(out_dtype) if out_dtype is not None else L.RS_F32
+    return _NormalizedRows.apply(table, ids, eps, od)
+
+
+class _MaskedMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, mask):
+        ctx.save_for_backward(mask)
+        ctx.dt = L.dt(feats)
+        return torch.ops.rs.masked_mean(feats, mask)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return torch.ops.rs.masked_mean_bwd(g.float().contiguous(), mask, ctx.dt), None
+
+
+def masked_mean(feats, mask):
+    """I2 tail: sum_t feats*mask / clamp(sum_t mask, 1e-9)  (item_tower.py:254-257)."""
+    return _MaskedMean.apply(feats, mask)
+
+
+class _FM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, offsets, emb, lin, want_concat, concat_dtype):
+        fm, concat = torch.ops.rs.fm_fwd(ids, offsets, emb, lin, want_concat, concat_dtype)
+        ctx.save_for_backward(ids, offsets, emb)
+        ctx.meta = (lin is not None, want_concat, None if lin is None else lin.shape)
+        return fm, concat
+
+    @staticmethod
+    def backward(ctx, d_fm, d_concat):
+        ids, offsets, emb = ctx.saved_tensors
+        has_lin, want_concat, lin_shape = ctx.meta
+        d_emb, d_lin = torch.ops.rs.fm_bwd(ids, offsets, emb, d_fm, d_concat if want_concat else None, has_lin)
+        return None, None, d_emb, (d_lin.reshape(lin_shape) if has_lin else None), None, None
+
+
+def fm_interaction(ids, offsets, emb, lin=None, want_concat=True, concat_dtype=None):
+    """F1: (fm[B] (+ linear term), concat[B,F*k]) from one pass over the gathered field rows."""
+    cd = L.dt(concat_dtype) if concat_dtype is not None else _out_dtype()
+    return _FM.apply(ids, offsets, emb, lin, want_concat, cd)
+
+
+def retrieve_topk(user_emb: Tensor, item_emb: Tensor, k: int, mask_index0: bool = False):
+    """R1: topk(user_emb @ item_emb.T, k) -> (scores, ids); score desc, ties by ascending id."""
+    return torch.ops.rs.retrieve_topk(user_emb.float(), item_emb.float(), k, mask_index0)

@@ -1,0 +1,275 @@
+"""Drop-in towers: same constructor arguments, forward signatures, parameter names and shapes as the
+reference's nn.Modules (so its .pth checkpoints load with strict=True), with the embedding fronts
+running on the hand-written sm_100a kernels.  Everything that is stock torch.nn in the reference
+(nn.TransformerEncoder, the MLPs, HF BERT) stays stock torch.nn here -- it is third-party ATen
+arithmetic on both sides and outside the hot path.
+
+    SASRecUserTower      tower_code/v1_refine_usertower.py:312-510
+    SASRecItemTower      tower_code/v1_usertower_train.py:266-293
+    HybridItemTower      item_tower.py:131-286   (fronts I1/I2; encoder body stock)
+    OptimizedItemTower   item_tower.py:289-305
+    SimCSEModelWrapper   item_tower.py:308-323
+    HybridUserEmbeddings tower_code/mined_inference.py:614-616,634,643 + forward gathers :670,687-688,695,705
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+SEQ_TABLES = ("item_id_emb", "time_emb", "type_emb", "color_emb", "graphic_emb", "section_emb")
+SEQ_GATE_MASK = (1.0, 1.0, 0.0, 0.0, 0.0, 0.0)       # s_mask, v1_refine_usertower.py:437
+STATIC_TABLES = ("age_emb", "price_emb", "cnt_emb", "recency_emb", "channel_emb", "club_status_emb",
+                 "news_freq_emb", "fn_emb", "active_emb")
+
+
+class SASRecUserTower(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        d = self.d_model = args.d_model
+        self.max_len = args.max_len
+        self.dropout_rate = args.dropout
+        self.item_proj = nn.Linear(args.pretrained_dim, d)
+        self.item_id_emb = nn.Embedding(args.num_items + 1, d, padding_idx=0)
+        self.type_emb = nn.Embedding(args.num_prod_types + 1, d, padding_idx=0)
+        self.color_emb = nn.Embedding(args.num_colors + 1, d, padding_idx=0)
+        self.graphic_emb = nn.Embedding(args.num_graphics + 1, d, padding_idx=0)
+        self.section_emb = nn.Embedding(args.num_sections + 1, d, padding_idx=0)
+        self.pos_emb = nn.Embedding(self.max_len, d)
+        self.seq_gate = nn.Parameter(torch.ones(6))
+        self.static_gate = nn.Parameter(torch.ones(10))
+        self.time_emb = nn.Embedding(12, d, padding_idx=0)
+        self.emb_ln = nn.LayerNorm(d)
+        self.emb_dropout = nn.Dropout(self.dropout_rate)
+        layer = nn.TransformerEncoderLayer(d_model=d, nhead=args.nhead, dim_feedforward=2 * d,
+                                           dropout=self.dropout_rate, activation="gelu", norm_first=True,
+                                           batch_first=True)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=args.num_layers)
+        for name, rows, dim in (("age_emb", 11, 16), ("price_emb", 11, 16), ("cnt_emb", 11, 16),
+                                ("recency_emb", 11, 16), ("channel_emb", 4, 4), ("club_status_emb", 4, 4),
+                                ("news_freq_emb", 3, 4), ("fn_emb", 3, 4), ("active_emb", 3, 4)):
+            setattr(self, name, nn.Embedding(rows, dim, padding_idx=0))
+        self.num_cont_feats = 4
+        self.cont_proj = nn.Linear(4, 16)
+        self.static_mlp = nn.Sequential(nn.Linear(100, d), nn.LayerNorm(d), nn.GELU(), nn.Dropout(self.dropout_rate))
+        self.output_proj = nn.Sequential(nn.Linear(2 * d, d), nn.LayerNorm(d), nn.GELU(), nn.Linear(d, d))
+        self.register_buffer("_seq_gate_mask", torch.tensor(SEQ_GATE_MASK), persistent=False)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        # same initialisation as the reference (:399-410); note it overwrites the padding rows (invariant 1)
+        if isinstance(m, nn.Linear):
+            nn.init.kaiming_normal_(m.weight, mode="fan_in", nonlinearity="relu")
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.Embedding):
+            nn.init.normal_(m.weight, mean=0.0, std=0.02)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def get_causal_mask(self, seq_len, device):
+        return torch.triu(torch.ones(seq_len, seq_len, device=device, dtype=torch.bool), diagonal=1)
+
+    def embed_front(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids):
+        """U1 (:447-456): one fused kernel instead of 6 gathers + 13 elementwise passes.  Tables whose gate
+        is hard-masked to zero (type/color/graphic/section) contribute exactly 0 and are not read."""
+        s_g = torch.sigmoid(self.seq_gate) * self._seq_gate_mask
+        base = self.item_proj(pretrained_vecs)
+        ids = [item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids]
+        tables = [getattr(self, n).weight for n in SEQ_TABLES]
+        n_live = sum(1 for m in SEQ_GATE_MASK if m != 0.0)        # live tables come first in SEQ_TABLES
+        return ops.seq_front(base, ids, tables, s_g, self.pos_emb.weight, padding_idx=0, n_live=n_live)
+
+    def static_front(self, age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids,
+                     news_freq_ids, fn_ids, active_ids, cont_feats):
+        """U2 (:472-491): one kernel instead of ~25."""
+        u_g = torch.sigmoid(self.static_gate)
+        ids = [age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
+               fn_ids, active_ids]
+        tables = [getattr(self, n).weight for n in STATIC_TABLES]
+        return ops.static_front(ids, tables, cont_feats.float(), self.cont_proj.weight, self.cont_proj.bias, u_g,
+                                padding_idx=0)
+
+    def forward(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids,
+                age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
+                fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True):
+        seq_len = item_ids.size(1)
+        seq_emb = self.embed_front(pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids,
+                                   section_ids)
+        seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
+        output = self.transformer_encoder(seq_emb, mask=self.get_causal_mask(seq_len, item_ids.device),
+                                          src_key_padding_mask=padding_mask)
+        static_input = self.static_front(age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids,
+                                         club_status_ids, news_freq_ids, fn_ids, active_ids, cont_feats)
+        user_profile_vec = self.static_mlp(static_input)
+        if training_mode:
+            expanded = user_profile_vec.unsqueeze(1).expand(-1, seq_len, -1)
+            final_vec = self.output_proj(torch.cat([output, expanded], dim=-1))
+        else:
+            final_vec = self.output_proj(torch.cat([output[:, -1, :], user_profile_vec], dim=-1))
+        return F.normalize(final_vec, p=2, dim=-1)
+
+
+class SASRecItemTower(nn.Module):
+    def __init__(self, num_items, d_model, log_q_tensor=None):
+        super().__init__()
+        self.item_matrix = nn.Embedding(num_items + 1, d_model, padding_idx=0)
+        self.register_buffer("log_q", log_q_tensor if log_q_tensor is not None else torch.zeros(num_items + 1))
+
+    def get_all_embeddings(self):
+        return self.item_matrix.weight
+
+    def get_log_q(self):
+        return self.log_q
+
+    def set_freeze_state(self, freeze: bool):
+        for p in self.parameters():
+            p.requires_grad = not freeze
+
+    def init_from_pretrained(self, pretrained_vecs):
+        with torch.no_grad():
+            self.item_matrix.weight.copy_(pretrained_vecs)
+
+    def normalized_rows(self, target_ids, out_dtype=None):
+        """`F.normalize(self.item_matrix.weight, p=2, dim=1)[target_ids]` (the loop's lines
+        tower_code/v1_usertower_train.py:810-811 + the gather at v1_refine_usertower.py:833) without
+        normalising -- or differentiating through -- the rows that are not in the batch."""
+        return ops.normalized_rows(self.item_matrix.weight, target_ids, 1e-12, out_dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+class _SEBlock(nn.Module):                      # item_tower.py:41-76 (stock layers; parameter names kept)
+    def __init__(self, dim, dropout=0.2, expansion_factor=4):
+        super().__init__()
+        h = dim * expansion_factor
+        self.block = nn.Sequential(nn.Linear(dim, h), nn.LayerNorm(h), nn.GELU(), nn.Dropout(dropout),
+                                   nn.Linear(h, dim), nn.LayerNorm(dim))
+        self.se_block = nn.Sequential(nn.Linear(dim, dim // 4), nn.ReLU(), nn.Linear(dim // 4, dim), nn.Sigmoid())
+
+    def forward(self, x):
+        y = self.block(x)
+        return x + y * self.se_block(y)
+
+
+class DeepResidualHead(nn.Module):              # item_tower.py:78-128
+    def __init__(self, input_dim, output_dim=128):
+        super().__init__()
+        mid, hid = input_dim * 2, input_dim * 4
+        self.expand_layer1 = nn.Sequential(nn.Linear(input_dim, mid), nn.LayerNorm(mid), nn.GELU(), nn.Dropout(0.1))
+        self.expand_layer2 = nn.Sequential(nn.Linear(mid, hid), nn.LayerNorm(hid), nn.GELU(), nn.Dropout(0.1))
+        self.res_blocks = nn.Sequential(_SEBlock(hid, dropout=0.2), _SEBlock(hid, dropout=0.2))
+        self.final_proj = nn.Linear(hid, output_dim)
+        self.input_skip = nn.Linear(input_dim, output_dim)
+
+    def forward(self, x):
+        return self.final_proj(self.res_blocks(self.expand_layer2(self.expand_layer1(x)))) + self.input_skip(x)
+
+
+class HybridItemTower(nn.Module):
+    """item_tower.py:131-286.  `bert_model` may be injected (any HF BertModel); by default it is loaded
+    like the reference does (`AutoModel.from_pretrained("bert-base-uncased")`, needs the HF cache)."""
+
+    def __init__(self, std_vocab_size: int, num_std_fields: int, embed_dim: int = 128, output_dim: int = 128,
+                 bert_model=None, pad_id: int = 0):
+        super().__init__()
+        self.std_embedding = nn.Embedding(std_vocab_size, embed_dim, padding_idx=pad_id)
+        self.std_field_emb = nn.Parameter(torch.randn(1, num_std_fields, embed_dim))
+        self.std_ln = nn.LayerNorm(embed_dim)
+        self.re_ln = nn.LayerNorm(embed_dim)
+        if bert_model is None:
+            from transformers import AutoModel
+            bert_model = AutoModel.from_pretrained("bert-base-uncased")
+        self.bert_model = bert_model
+        self.bert_config = bert_model.config
+        bert_dim = self.bert_config.hidden_size
+        self.re_proj = nn.Sequential(nn.Linear(bert_dim, embed_dim), nn.LayerNorm(embed_dim), nn.GELU())
+        self.re_field_position = nn.Parameter(torch.randn(1, 9, embed_dim))
+        self.text_proj = nn.Sequential(nn.Linear(bert_dim, embed_dim), nn.LayerNorm(embed_dim), nn.GELU())
+        layer = nn.TransformerEncoderLayer(d_model=embed_dim, nhead=4, dim_feedforward=embed_dim * 4,
+                                           batch_first=True, dropout=0.1, activation="gelu", norm_first=True)
+        self.transformer = nn.TransformerEncoder(layer, num_layers=2, enable_nested_tensor=False)
+        self.head = DeepResidualHead(input_dim=embed_dim, output_dim=output_dim)
+        self._pad_id = pad_id
+
+    # I1 -- item_tower.py:239-241
+    def std_front(self, std_input):
+        if torch.is_grad_enabled() and (self.std_embedding.weight.requires_grad or self.std_field_emb.requires_grad):
+            x = ops.gather_rows(self.std_embedding.weight, std_input, padding_idx=self._pad_id) + self.std_field_emb
+            return self.std_ln(x)
+        return torch.ops.rs.std_front(self.std_embedding.weight, std_input, self.std_field_emb, self.std_ln.weight,
+                                      self.std_ln.bias, self.std_ln.eps, 0)
+
+    # I2 -- item_tower.py:246-261
+    def bert_word_embeddings(self, flat_ids):
+        """`self.bert_model.embeddings(input_ids=...)` under no_grad (:248-249), fused gather+add+LN(+dropout)."""
+        e = self.bert_model.embeddings
+        p = e.dropout.p if (e.training and e.dropout.p > 0) else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+        with torch.no_grad():
+            return torch.ops.rs.bert_embed(e.word_embeddings.weight, e.position_embeddings.weight,
+                                           e.token_type_embeddings.weight, e.LayerNorm.weight, e.LayerNorm.bias,
+                                           e.LayerNorm.eps, flat_ids, p, seed, 0)
+
+    def re_front(self, re_input_ids, re_attn_mask):
+        B = re_input_ids.shape[0]
+        T = re_input_ids.size(-1)
+        word_embs = self.bert_word_embeddings(re_input_ids.reshape(-1, T))
+        re_feats = self.re_proj(word_embs)
+        pooled = ops.masked_mean(re_feats, re_attn_mask.reshape(-1, T))
+        re_vectors = pooled.view(B, 9, -1).to(re_feats.dtype) + self.re_field_position
+        return self.re_ln(re_vectors)
+
+    def forward(self, std_input, re_input_ids, re_attn_mask, text_input_ids, text_attn_mask):
+        std_emb = self.std_front(std_input)
+        re_vectors = self.re_front(re_input_ids, re_attn_mask)
+        bert_out = self.bert_model(input_ids=text_input_ids, attention_mask=text_attn_mask)
+        text_vec = self.text_proj(bert_out.last_hidden_state[:, 0, :]).unsqueeze(1)
+        combined = torch.cat([std_emb.to(text_vec.dtype), re_vectors.to(text_vec.dtype), text_vec], dim=1)
+        out = self.head(self.transformer(combined).mean(dim=1))
+        return F.normalize(out, p=2, dim=1)
+
+
+class OptimizedItemTower(nn.Module):            # item_tower.py:289-305
+    def __init__(self, input_dim=128, output_dim=128):
+        super().__init__()
+        self.layer = nn.Sequential(nn.Linear(input_dim, input_dim), nn.LayerNorm(input_dim), nn.GELU(),
+                                   nn.Linear(input_dim, output_dim))
+
+    def forward(self, x):
+        return F.normalize(self.layer(x), p=2, dim=1)
+
+
+class SimCSEModelWrapper(nn.Module):            # item_tower.py:308-323
+    def __init__(self, encoder: nn.Module, projector: nn.Module):
+        super().__init__()
+        self.encoder = encoder
+        self.projector = projector
+
+    def forward(self, std, re_ids, re_mask, txt_ids, txt_mask):
+        return self.projector(self.encoder(std, re_ids, re_mask, txt_ids, txt_mask))
+
+
+class HybridUserEmbeddings(nn.Module):
+    """The embedding tables of `HybridUserTower` (tower_code/mined_inference.py:614-616,634,643) under
+    their reference names, and its forward-pass gathers (:670,687-688,695,705) -- row H1 of SURVEY.md 8a.
+    None of these tables has a padding_idx: row 0 is a zero row that DOES receive gradient."""
+
+    def __init__(self, gnn_user_init, gnn_item_init, item_content_init):
+        super().__init__()
+        self.gnn_user_emb = nn.Embedding.from_pretrained(gnn_user_init, freeze=False)
+        self.gnn_item_emb = nn.Embedding.from_pretrained(gnn_item_init, freeze=False)
+        self.item_content_emb = nn.Embedding.from_pretrained(item_content_init, freeze=False)
+        self.time_emb = nn.Embedding(1001, 128)
+        self.channel_emb = nn.Embedding(2, 32)
+
+    def forward(self, u_idx, seq_ids, seq_deltas, u_cat):
+        return dict(
+            gnn_user_emb=ops.gather_rows(self.gnn_user_emb.weight, u_idx),
+            item_content_emb=ops.gather_rows(self.item_content_emb.weight, seq_ids),
+            gnn_item_emb=ops.gather_rows(self.gnn_item_emb.weight, seq_ids),
+            time_emb=ops.gather_rows(self.time_emb.weight, seq_deltas, clamp_max=1000),
+            channel_emb=ops.gather_rows(self.channel_emb.weight, u_cat))

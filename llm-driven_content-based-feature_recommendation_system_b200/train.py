@@ -1,0 +1,84 @@
+"""One training step of the two-tower model, mirroring the body of `train_user_tower_all_time`
+(tower_code/v1_usertower_train.py:729-859) without its per-step host synchronisations:
+
+  * `pretrained_lookup[item_ids.cpu()].to(device)` (:760, a D2H sync + CPU gather + H2D of B*L*128
+    floats) becomes a device-resident table gathered by the row-gather kernel;
+  * `output_1[valid_mask]` (:797, boolean indexing = nonzero + sync) becomes a gather with the
+    batch's precomputed valid-position index;
+  * `F.normalize(item_matrix.weight)[targets]` (:810-811) normalises only the gathered rows;
+  * the three `.item()` calls per step (:857-859) are dropped: losses are returned as device scalars.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import losses, ops
+from .synthetic import FORWARD_KEYS
+
+
+def prepare_batch(batch: Dict[str, torch.Tensor], device, non_blocking=True) -> Dict[str, torch.Tensor]:
+    """Host -> device copy of one collated batch (+ the flat index of its valid time steps, computed
+    on the host where the padding mask already lives).  Pin `batch` for an asynchronous copy."""
+    out = {k: v.to(device, non_blocking=non_blocking) for k, v in batch.items()}
+    if "valid_index" not in batch:
+        out["valid_index"] = torch.nonzero(~batch["padding_mask"].reshape(-1)).squeeze(1).to(device,
+                                                                                             non_blocking=non_blocking)
+    return out
+
+
+def add_host_index(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Add `valid_index` / `last_index` (host tensors) so that the device step needs no nonzero()."""
+    valid = ~batch["padding_mask"]
+    B, L = valid.shape
+    batch = dict(batch)
+    batch["valid_index"] = torch.nonzero(valid.reshape(-1)).squeeze(1)
+    last = (valid.sum(dim=1) - 1).clamp(min=0)
+    batch["last_index"] = torch.arange(B) * L + last
+    return batch
+
+
+def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1,
+                   lambda_cl=0.2, loss_scope="all", amp_dtype: Optional[torch.dtype] = torch.bfloat16,
+                   scaler=None, max_norm=5.0):
+    """forward x2 (two dropout views) + C2 + C3 + backward + clip + optimizer step.
+    Returns (total, main, cl) as device scalars.  `batch` comes from prepare_batch(add_host_index(...))."""
+    item_ids = batch["item_ids"]
+    B, L = item_ids.shape
+    if optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        pretrained_vecs = ops.gather_rows(pretrained_lookup, item_ids)
+    kw = {k: batch[k] for k in FORWARD_KEYS}
+    with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+        out1 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True)
+        out2 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True)
+        flat1 = out1.reshape(B * L, -1)
+        flat2 = out2.reshape(B * L, -1)
+        tgt_flat = batch["target_ids"].reshape(-1)
+        idx = batch["valid_index"] if loss_scope == "all" else batch["last_index"]
+        u = F.normalize(ops.gather_rows(flat1, idx), p=2, dim=1)                      # :794-807
+        tgt = tgt_flat[idx]
+        uid = idx // L                                                               # batch row = user id (:801-804)
+        v = item_tower.normalized_rows(tgt)                                          # :810-811 + :833
+        main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq)
+        li = batch["last_index"]                                                     # :830-842
+        cl = losses.duorec_loss_refined(ops.gather_rows(flat1, li), ops.gather_rows(flat2, li), tgt_flat[li],
+                                        lambda_sup=lambda_sup)
+        total = main + lambda_cl * cl
+    if optimizer is not None:
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        if scaler is not None:
+            scaler.scale(total).backward()
+            scaler.unscale_(optimizer)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
+            scaler.step(optimizer)
+            scaler.update()
+        else:
+            total.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
+            optimizer.step()
+        del params
+    return total.detach(), main.detach(), cl.detach()
