@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- two-tower train samples/sec (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): UserTower + ItemTower in-batch InfoNCE training, batch 8192 per
+GPU, L=50, d=128, bf16 autocast, synthetic H&M-shaped data (105,542 articles).  One step = the body of
+the reference's `train_user_tower_all_time` (tower_code/v1_usertower_train.py:729-859): two dropout
+views of SASRecUserTower, logQ-corrected InfoNCE over ALL valid time steps (N ~ 98k rows) with same-item /
+same-user masks, DuoRec on the last step, backward, grad clip, AdamW on both towers.
+
+  value : samples/s with the batch already resident in HBM (device-timed, max over ranks)
+  e2e   : the same step through the public API with HOST (pinned) batches: H2D copies of every input and
+          a D2H read of the losses inside the timed region
+  --impl reference : the reference's algorithm for the same step on the host CPU (oracle port, all host
+          threads) on a bounded sample of the workload (B=256 users of the same batch)
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "llm-driven_content-based-feature_recommendation_system_b200"
+METRIC = "two_tower_train_samples_per_sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--seq-len", type=int, default=50)
+    ap.add_argument("--loss-scope", default="all", choices=["all", "last"])
+    ap.add_argument("--cpu-batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_rate(args, steps, warmup, syn):
+    """The reference's step on the host cores: oracle port (fp32, autocast off -- what the reference runs
+    on a CPU), B=cpu_batch users cut from the same synthetic batch, all-timestep loss."""
+    from oracle import towers as otowers
+    torch.manual_seed(42)
+    nthreads = os.cpu_count() or 1
+    torch.set_num_threads(nthreads)
+    targs = syn.tower_args(max_len=args.seq_len)
+    model = otowers.UserTowerOracle(targs).train()
+    item = otowers.ItemMatrixOracle(syn.N_ITEMS, 128, syn.log_q(syn.N_ITEMS))
+    lookup = syn.pretrained_table(syn.N_ITEMS)
+    with torch.no_grad():
+        item.item_matrix.weight.copy_(lookup)
+    opt = torch.optim.AdamW(list(model.parameters()) + list(item.parameters()), lr=5e-4, weight_decay=1e-4)
+    full = syn.make_batch(args.batch, args.seq_len, syn.N_ITEMS, seed=42)
+    Bc = min(args.cpu_batch, args.batch)
+    b = {k: v[:Bc] for k, v in full.items()}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        batch = {k: b[k] for k in syn.FORWARD_KEYS}
+        batch["pretrained_vecs"] = lookup[b["item_ids"]]             # v1_usertower_train.py:760
+        batch["target_ids"] = b["target_ids"]
+        total, _, _ = otowers.all_timestep_step_loss(model, item, batch)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=5.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return dict(value=Bc / dt, unit="samples/s", cores=nthreads, kind="port",
+                sample=f"B={Bc} users of the B={args.batch} synthetic batch, all-timestep loss, fp32, "
+                       f"{len(times)} timed steps after {warmup} warm-up, {dt * 1e3:.0f} ms/step"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rs_syn = _load_synthetic()
+    steps = max(1, min(args.steps, 20))
+    cb, dt = cpu_reference_step_rate(args, steps, min(args.warmup, 1) if args.warmup else 0, rs_syn)
+    line = dict(metric=METRIC, value=cb["value"], unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=args.warmup,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="two_tower_infonce_train_step", batch_per_gpu=args.batch, seq_len=args.seq_len,
+                            loss_scope="all", note="reference algorithm (CPU oracle port) on a bounded sample"),
+                cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def _load_synthetic():
+    """synthetic.py is pure torch: load it without importing the package (the reference arm must not need
+    the CUDA library)."""
+    spec = importlib.util.spec_from_file_location("_rs_synthetic", os.path.join(ROOT, PKG, "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rs = importlib.import_module(PKG)          # raises if librs_twotower.so is missing: no fallback
+    syn, L = rs.synthetic, rs._lib
+    lib = L.load()
+    torch.manual_seed(42)
+    B, SL = args.batch, args.seq_len
+
+    model = rs.SASRecUserTower(syn.tower_args(max_len=SL)).to(dev).train()
+    item = rs.SASRecItemTower(syn.N_ITEMS, 128, syn.log_q(syn.N_ITEMS)).to(dev)
+    lookup = syn.pretrained_table(syn.N_ITEMS).to(dev)
+    item.init_from_pretrained(lookup)
+    params = list(model.parameters()) + list(item.parameters())
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True)
+
+    def sync_grads():
+        if world == 1:
+            return
+        gs = [p.grad for p in params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        o = 0
+        for g in gs:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+
+    # a small pool of distinct batches (different seeds per rank), pinned on the host + resident copies
+    pool = 3
+    host = [{k: v.pin_memory() for k, v in rs.train.add_host_index(
+        syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + 1000 * rank + i)).items()} for i in range(pool)]
+    resident = [rs.train.prepare_batch(hb, dev) for hb in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    n_valid = int(host[0]["valid_index"].numel())
+
+    def step(b):
+        return rs.train.two_tower_step(model, item, b, lookup, opt, loss_scope=args.loss_scope,
+                                       amp_dtype=torch.bfloat16, grad_hook=sync_grads)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- resident-input run: the headline `value`
+    last = {}
+    for i in range(args.warmup):
+        last["loss"] = step(resident[i % pool])
+    launches0 = lib.rs_launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(args.steps, lambda i: last.__setitem__("loss", step(resident[i % pool])))
+    launches = lib.rs_launch_count() - launches0
+    total, main, cl = [float(x) for x in last["loss"]]
+    assert all(map(lambda v: v == v and abs(v) < 1e6, (total, main, cl))), f"non-finite loss {total, main, cl}"
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end run: host batches in, losses out, every step
+    def e2e_step(i):
+        b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
+        t, m, c = step(b)
+        last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    ms_e2e = timed(args.steps, e2e_step)
+    e2e = dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d_bytes,
+               d2h_bytes_per_step=12, ms_per_step=ms_e2e / args.steps)
+
+    # ---- per-kernel pass (rank 0): CUDA events around every C-ABI call, on the launching stream
+    kernels, roof = {}, None
+    if rank == 0:
+        L.PROFILE = []
+        nprof = 2
+        for i in range(nprof):
+            step(resident[i % pool])
+        torch.cuda.synchronize()
+        prof, L.PROFILE = L.PROFILE, None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, tf_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured" if peaks else "fallback"
+        agg = {}
+        for name, s, e, extra in prof:
+            a = agg.setdefault(name, dict(ms=0.0, calls=0, work=0.0))
+            a["ms"] += s.elapsed_time(e)
+            a["calls"] += 1
+            a["work"] += extra
+        P = B * SL
+        D = 128
+        for name, a in agg.items():
+            per_step_ms = a["ms"] / nprof
+            k = dict(ms_per_step=round(per_step_ms, 4), calls_per_step=a["calls"] / nprof)
+            if name in ("rs_ce_fwd", "rs_ce_bwd"):
+                k.update(bound="tensor", unit="TFLOP/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e12,
+                         peak=tf_peak)
+            elif name == "rs_seq_front_fwd":
+                # per position: base bf16 + 2 live table rows fp32 + out bf16 + 2 ids (pos rows are L2 resident)
+                by = P * (D * 2 + 2 * D * 4 + D * 2 + 2 * 8) * a["calls"] / nprof
+                k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
+            elif name == "rs_seq_front_bwd":
+                by = P * (D * 2 + 8) * a["calls"] / nprof          # one pass over dX (bf16) + time ids
+                k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
+            elif name == "rs_segment_reduce_rows":
+                k.update(bound="hbm", unit="GB/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
+            if "achieved" in k:
+                k["frac"] = k["achieved"] / k["peak"]
+            kernels[name] = k
+        top = max((n for n in kernels if "achieved" in kernels[n]), key=lambda n: kernels[n]["ms_per_step"])
+        t = kernels[top]
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+        except Exception:
+            pass
+        roof = dict(kernel=top, bound=t["bound"], achieved=t["achieved"], peak=t["peak"], unit=t["unit"],
+                    frac=t["frac"], traffic=traffic, peak_source=peak_src, ms_per_step=t["ms_per_step"],
+                    share_of_step=t["ms_per_step"] / (ms / args.steps))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_step_rate(args, 2, 1, syn)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic",
+                    config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B,
+                                global_batch=B * world, seq_len=SL, d_model=128, n_items=syn.N_ITEMS,
+                                loss_scope=args.loss_scope, loss_rows=n_valid if args.loss_scope == "all" else B,
+                                parallelism=f"dp{world} (replicated tables, gradients all-reduced)" if world > 1 else "1 GPU",
+                                l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
+                    e2e=e2e, gpu_launches=int(launches), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
+                    kernels=kernels, loss=dict(total=total, main=main, cl=cl))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

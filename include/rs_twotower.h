@@ -49,6 +49,9 @@ extern "C" {
 
 int rs_abi_version(void);
 const char* rs_error_string(int code);
+/* number of kernels this library has launched in this process (statistics for bench.py's gpu_launches) */
+unsigned long long rs_launch_count(void);
+void rs_count_launches(int n);
 
 /* ------------------------------------------------------------------ gathers */
 

@@ -35,6 +35,8 @@ class CEProblem(C.Structure):
 PROTOTYPES = {
     "rs_abi_version": (i32, []),
     "rs_error_string": (C.c_char_p, [i32]),
+    "rs_launch_count": (C.c_ulonglong, []),
+    "rs_count_launches": (None, [i32]),
     "rs_gather_rows": (i32, [vp, i32, i64, i64, vp, i64, i64, vp, i32, vp, vp]),
     "rs_scatter_add_rows": (i32, [vp, i32, vp, i64, i64, i64, i64, i64, f32, vp, vp, vp]),
     "rs_sort_ids_workspace_bytes": (sz, [i64]),
@@ -63,6 +65,47 @@ PROTOTYPES = {
 }
 
 _lib = None
+PROFILE = None          # set to a list to record (name, start_event, end_event) around every C call
+
+
+def _algorithmic_work(name, args):
+    """Algorithmic flops (fused softmax) or bytes (segment reduce) of one call, for the roofline report."""
+    if name == "rs_ce_fwd":
+        p = args[0]
+        return 2.0 * p.M * p.N * p.K
+    if name == "rs_ce_bwd":                     # per requested side: S recompute + dS@X
+        p = args[0]
+        sides = (args[5] is not None) + (args[6] is not None)
+        return 2.0 * p.M * p.N * p.K * 2 * sides
+    if name == "rs_segment_reduce_rows":        # one read of the gradient rows + the sorted (id, pos) pairs
+        n, dim, esz = args[4], args[5], (4 if args[1] == RS_F32 else 2)
+        return float(n) * (dim * esz + 8)
+    return 0.0
+
+
+class _Proxy:
+    """Attribute access like the ctypes library; optionally brackets each call with CUDA events recorded
+    on the current stream (the stream the kernels are launched on) for bench.py's roofline numbers."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        raw = getattr(self._lib, name)
+
+        def call(*args):
+            if PROFILE is None:
+                return raw(*args)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = raw(*args)
+            e.record()
+            PROFILE.append((name, s, e, _algorithmic_work(name, args)))
+            return rc
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
 
 
 def load():
@@ -78,8 +121,8 @@ def load():
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the .so is stale
         fn.restype, fn.argtypes = res, args
-    _lib = lib
-    return lib
+    _lib = _Proxy(lib)
+    return _lib
 
 
 def check(code: int, what: str):

@@ -17,11 +17,15 @@
 #define RS_MAX_TABLES 8
 #define RS_NUM_SMS 148
 
-#define RS_LAUNCH_CHECK()                      \
+// statistics only (how many kernels this library has launched in this process); see rs_launch_count()
+extern "C" void rs_count_launches(int n);
+#define RS_LAUNCH_CHECK_N(n)                   \
   do {                                         \
     cudaError_t e__ = cudaGetLastError();      \
     if (e__ != cudaSuccess) return (int)e__;   \
+    rs_count_launches(n);                      \
   } while (0)
+#define RS_LAUNCH_CHECK() RS_LAUNCH_CHECK_N(1)
 
 namespace rs {
 

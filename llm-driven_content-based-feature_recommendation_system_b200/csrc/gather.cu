@@ -501,6 +501,11 @@ static inline bool dim_ok(int64_t dim, int dt_a, int dt_b) {
   return true;
 }
 
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void rs_count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+extern "C" unsigned long long rs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" int rs_abi_version(void) { return 1; }
 
 extern "C" const char* rs_error_string(int code) {

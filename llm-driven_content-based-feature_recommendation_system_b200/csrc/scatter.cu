@@ -601,7 +601,7 @@ extern "C" int rs_segment_reduce_rows(const void* d_out, int d_out_dtype, const 
                                                               d_table, partL, partR);                         \
   } while (0)
   DISPATCH_DT(d_out_dtype, GD, if (need <= 1) LAUNCH_SEG(GD, 1); else if (need <= 2) LAUNCH_SEG(GD, 2); else LAUNCH_SEG(GD, 8));
-  RS_LAUNCH_CHECK();
+  RS_LAUNCH_CHECK_N(2);
   if (dot_table) {
     dot_finalize_kernel<<<1, 32, 0, st>>>(dot_part, grid * SEG_WARPS, dot_out);
     RS_LAUNCH_CHECK();

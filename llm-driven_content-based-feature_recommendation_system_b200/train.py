@@ -42,7 +42,7 @@ def add_host_index(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1,
                    lambda_cl=0.2, loss_scope="all", amp_dtype: Optional[torch.dtype] = torch.bfloat16,
-                   scaler=None, max_norm=5.0):
+                   scaler=None, max_norm=5.0, grad_hook=None):
     """forward x2 (two dropout views) + C2 + C3 + backward + clip + optimizer step.
     Returns (total, main, cl) as device scalars.  `batch` comes from prepare_batch(add_host_index(...))."""
     item_ids = batch["item_ids"]
@@ -69,16 +69,18 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
                                         lambda_sup=lambda_sup)
         total = main + lambda_cl * cl
     if optimizer is not None:
-        params = [p for g in optimizer.param_groups for p in g["params"]]
         if scaler is not None:
             scaler.scale(total).backward()
+            if grad_hook is not None:
+                grad_hook()                      # e.g. the data-parallel gradient all-reduce
             scaler.unscale_(optimizer)
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
             scaler.step(optimizer)
             scaler.update()
         else:
             total.backward()
+            if grad_hook is not None:
+                grad_hook()
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
             optimizer.step()
-        del params
     return total.detach(), main.detach(), cl.detach()

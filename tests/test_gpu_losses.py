@@ -1,0 +1,209 @@
+"""GPU parity: fused tcgen05 softmax losses (C1, C2, C3, C5), retrieval (R1) and FM (F1).
+
+Tolerances.  The similarity contraction runs with bf16 (or fp16) operands and fp32 accumulation, the
+reference fixtures are fp32: with unit-norm rows |u.v| error <= ~2^-9 (bf16) / 2^-12 (fp16) per operand,
+times 1/temperature <= 12.5 on the logits.  Loss: atol 2e-2 (bf16) / 3e-3 (fp16).  Gradients: compared
+to the fp32 gradient with atol = 3% (bf16) / 0.5% (fp16) of the largest gradient entry.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from oracle import fm as ofm, losses as olosses, retrieval as oretr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LOSS_TOL = {torch.bfloat16: 2e-2, torch.float16: 3e-3}
+GRAD_TOL = {torch.bfloat16: 3e-2, torch.float16: 5e-3}
+
+
+@pytest.fixture(scope="module")
+def lg():
+    return load_golden("losses.pt")
+
+
+def _run(rs, fn, wrt, dtype, *a, **k):
+    old = rs.losses.COMPUTE_DTYPE
+    rs.losses.COMPUTE_DTYPE = dtype
+    try:
+        leaves = [x.to(DEV).requires_grad_(True) for x in wrt]
+        loss = fn(*leaves, *a, **k)
+        loss.backward()
+        return loss.detach().cpu(), [x.grad.cpu() for x in leaves]
+    finally:
+        rs.losses.COMPUTE_DTYPE = old
+
+
+def _cmp(got, want, dtype):
+    loss, grads = got
+    assert torch.isfinite(loss)
+    assert abs(loss.item() - want["loss"].item()) < LOSS_TOL[dtype], (loss.item(), want["loss"].item())
+    for g, w in zip(grads, want["grads"]):
+        assert torch.isfinite(g).all()
+        assert (g - w).abs().max() <= GRAD_TOL[dtype] * w.abs().max() + 1e-7, ((g - w).abs().max(), w.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_c1_simcse_vs_reference(rs, lg, dtype):
+    c = lg["c1"]
+    _cmp(_run(rs, rs.simcse_loss, [c["E1"], c["E2"]], dtype, c["temperature"]), c, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_c2_vs_reference(rs, lg, dtype):
+    d = lambda k: lg[k].to(DEV)
+    _cmp(_run(rs, rs.inbatch_corrected_logq_loss, [lg["U"], lg["table"]], dtype, d("tgt"), d("uid"), d("logq"),
+              temperature=0.1, lambda_logq=1.0), lg["c2"], dtype)
+    _cmp(_run(rs, rs.inbatch_corrected_logq_loss, [lg["U"], lg["table"]], dtype, d("tgt"), d("uid"), d("logq"),
+              temperature=0.07, lambda_logq=0.0), lg["c2_nologq"], dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_c3_vs_reference(rs, lg, dtype):
+    d = lambda k: lg[k].to(DEV)
+    _cmp(_run(rs, rs.duorec_loss_refined, [lg["U"], lg["U2"]], dtype, d("tgt"), temperature=0.1, lambda_sup=0.1),
+         lg["c3"], dtype)
+    _cmp(_run(rs, rs.duorec_loss_refined, [lg["U"], lg["U2"]], dtype, d("tgt"), temperature=0.1, lambda_sup=0.0),
+         lg["c3_nosup"], dtype)
+    _cmp(_run(rs, rs.duorec_loss_refined, [lg["U"], lg["U2"]], dtype, d("tgt_distinct"), temperature=0.1,
+              lambda_sup=0.1), lg["c3_distinct"], dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_c5_vs_reference(rs, lg, dtype):
+    d = lambda k: lg[k].to(DEV)
+    v = lg["table"][lg["tgt"]]
+    _cmp(_run(rs, rs.logq_correction_loss, [lg["U"], v], dtype, d("tgt"), d("probs"), temperature=0.07,
+              lambda_logq=0.5), lg["c5_logq"], dtype)
+    _cmp(_run(rs, rs.efficient_corrected_logq_loss, [lg["U"], v], dtype, d("tgt"), d("logq"), temperature=0.1,
+              lambda_logq=0.1), lg["c5_eff"], dtype)
+
+
+@pytest.mark.parametrize("N,V", [(1, 5), (127, 40), (128, 1000), (129, 64), (1000, 300), (4096, 3000), (5000, 100000)])
+def test_c2_sizes_vs_oracle(rs, N, V):
+    """ragged sizes around the 128-tile edge, heavy collisions (V << N) and none (V >> N)."""
+    g = torch.Generator().manual_seed(N)
+    table = F.normalize(torch.randn(V, 128, generator=g), dim=1)
+    tgt = torch.randint(0, V, (N,), generator=g)
+    U = F.normalize(torch.randn(N, 128, generator=g) + 2.0 * table[tgt], dim=1)
+    uid = torch.randint(0, max(2, N // 8), (N,), generator=g)
+    logq = torch.log(torch.rand(V, generator=g) + 1e-6)
+    u, t = U.clone().requires_grad_(True), table.clone().requires_grad_(True)
+    want = olosses.inbatch_corrected_logq_loss(u, t, tgt, uid, logq, 0.1, 1.0)
+    want.backward()
+    got = _run(rs, rs.inbatch_corrected_logq_loss, [U, table], torch.bfloat16, tgt.to(DEV), uid.to(DEV), logq.to(DEV),
+               temperature=0.1, lambda_logq=1.0)
+    _cmp(got, dict(loss=want.detach(), grads=[u.grad, t.grad]), torch.bfloat16)
+
+
+def test_rectangular_with_diag_offset(rs):
+    """[B, G*B] block of the cross-GPU negatives layout: label of row i is column i + off."""
+    g = torch.Generator().manual_seed(4)
+    B, G, r = 200, 3, 1
+    U = F.normalize(torch.randn(B, 128, generator=g), dim=1)
+    V = F.normalize(torch.randn(G * B, 128, generator=g), dim=1)
+    tgt = torch.randint(1, 50, (G * B,), generator=g)
+    uid = torch.arange(G * B)
+    logq = torch.log(torch.rand(60, generator=g) + 1e-4)
+    u, v = U.clone().requires_grad_(True), V.clone().requires_grad_(True)
+    s = u @ v.T / 0.1 - logq[tgt].view(1, -1)
+    lab = torch.arange(B) + r * B
+    same = (tgt[lab].view(-1, 1) == tgt.view(1, -1)) | (uid[lab].view(-1, 1) == uid.view(1, -1))
+    same[torch.arange(B), lab] = False
+    want = F.cross_entropy(s.masked_fill(same, float("-inf")), lab)
+    want.backward()
+    ug, vg = U.to(DEV).requires_grad_(True), V.to(DEV).requires_grad_(True)
+    got = rs.logq_infonce_rows(ug, vg[r * B:(r + 1) * B], tgt[lab].to(DEV), uid[lab].to(DEV), logq.to(DEV), 0.1, 1.0,
+                               col_rows=vg, col_target_ids=tgt.to(DEV), col_user_ids=uid.to(DEV), diag_offset=r * B)
+    got.backward()
+    _cmp((got.detach().cpu(), [ug.grad.cpu(), vg.grad.cpu()]), dict(loss=want.detach(), grads=[u.grad, v.grad]),
+         torch.bfloat16)
+
+
+def test_full_size_infonce_properties(rs):
+    """B = 8192 (BASELINE config 2): lse >= diag, lse bounded by log N + max logit, gradient rows of the
+    softmax part sum to ~0 along the label direction, loss equals log N for identical columns."""
+    g = torch.Generator().manual_seed(0)
+    N = 8192
+    U = F.normalize(torch.randn(N, 128, generator=g), dim=1).to(DEV)
+    lse, diag, _, _ = rs.losses.fused_softmax_stats(U, U, 10.0)
+    assert (lse >= diag - 1e-3).all() and (lse <= 10.0 + torch.log(torch.tensor(float(N))) + 1e-3).all()
+    torch.testing.assert_close(diag, torch.full_like(diag, 10.0), rtol=0, atol=0.1)        # <u,u> = 1 (bf16 rounding)
+    ones = F.normalize(torch.ones(N, 128), dim=1).to(DEV)
+    loss = rs.info_nce(ones, ones, 0.1)
+    torch.testing.assert_close(loss.cpu(), torch.log(torch.tensor(float(N))), rtol=1e-3, atol=1e-3)
+    # gradient w.r.t. a: sum_j softmax_ij * b_j - b_i ; for identical rows it vanishes
+    a = ones.clone().requires_grad_(True)
+    rs.info_nce(a, ones, 0.1).backward()
+    assert a.grad.abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ R1
+def test_retrieval_vs_reference(rs):
+    r = load_golden("retrieval.pt")
+    U, I = r["U"].to(DEV), r["I"].to(DEV)
+    for k in (12, 20, 100, 500):
+        sc, ids = rs.retrieve_topk(U, I, k)
+        assert torch.equal(ids.cpu(), r[f"k{k}"]["ids"]), k                 # bit-exact ids (no ties in this fixture)
+        torch.testing.assert_close(sc.cpu(), r[f"k{k}"]["scores"], rtol=0, atol=2e-6)
+    sc, ids = rs.retrieve_topk(U, I, 20, mask_index0=True)
+    assert torch.equal(ids.cpu(), r["gnn_k20"]["ids"]) and not (ids == 0).any()
+    t = r["ties_k12"]
+    sc, ids = rs.retrieve_topk(U, t["I"].to(DEV), 12)
+    assert torch.equal(ids.cpu(), oretr.canonical_ids(t["scores"], t["ids"]))    # ties: lower id first
+
+
+@pytest.mark.parametrize("nu,ni,k", [(1, 200, 5), (777, 105542, 12), (5000, 20000, 100), (33, 5000, 1000), (300, 130, 130)])
+def test_retrieval_sizes_vs_oracle(rs, nu, ni, k):
+    g = torch.Generator().manual_seed(nu + ni)
+    U = F.normalize(torch.randn(nu, 128, generator=g), dim=1)
+    I = F.normalize(torch.randn(ni, 128, generator=g), dim=1)
+    sc_w, ids_w = oretr.retrieve_topk(U, I, k)
+    sc, ids = rs.retrieve_topk(U.to(DEV), I.to(DEV), k)
+    torch.testing.assert_close(sc.cpu(), sc_w, rtol=0, atol=3e-6)
+    # ids exact wherever the k-th/k+1-th neighbouring scores are separated by more than the fp32 summation noise
+    gap_ok = (sc_w[:, :-1] - sc_w[:, 1:]).min(dim=1).values > 1e-5 if k > 1 else torch.ones(nu, dtype=torch.bool)
+    assert gap_ok.float().mean() > 0.5
+    assert torch.equal(ids.cpu()[gap_ok], ids_w[gap_ok])
+    assert (torch.sort(ids, dim=1).values[:, 1:] != torch.sort(ids, dim=1).values[:, :-1]).all()   # no duplicates
+
+
+# ------------------------------------------------------------------------------------------ F1
+@pytest.mark.parametrize("k", [4, 16, 128])
+def test_fm_vs_oracle(rs, k):
+    syn = rs.synthetic
+    vocab = [50, 7, 1000, 3, 64, 64, 20000][: (7 if k > 4 else 5)] + [64] * 32
+    F_ = len(vocab)
+    B = 1000
+    ids = syn.make_fm_batch(B, vocab, seed=1)
+    m = rs.FM(vocab, k=k, init_std=0.1)
+    emb, lin, offs = m.embedding.detach().clone(), m.linear.detach().clone(), m.offsets.clone()
+    e0, l0 = emb.clone().requires_grad_(True), lin.clone().requires_grad_(True)
+    x = ofm.field_rows(ids, e0, offs)
+    y_want = ofm.fm_second_order(x) + l0[ids + offs].squeeze(-1).sum(1)
+    cot_y, cot_c = torch.randn(B), torch.randn(B, F_ * k)
+    ((y_want * cot_y).sum() + (x.flatten(1) * cot_c).sum()).backward()
+    m = m.to(DEV)
+    y, concat = m(ids.to(DEV))
+    torch.testing.assert_close(y.detach().cpu(), y_want.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.equal(concat.detach().cpu(), x.detach().flatten(1))                      # gathered rows bit-exact
+    ((y * cot_y.to(DEV)).sum() + (concat * cot_c.to(DEV)).sum()).backward()
+    torch.testing.assert_close(m.embedding.grad.cpu(), e0.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(m.linear.grad.cpu(), l0.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_deepfm_full_size(rs):
+    """BASELINE config 3: B=65536, F=39; FM identity against the explicit pairwise sum on a slice."""
+    syn = rs.synthetic
+    vocab = syn.criteo_vocab_sizes()
+    ids = syn.make_fm_batch(65536, vocab)
+    m = rs.DeepFM(vocab, k=16, init_std=0.05).to(DEV)
+    p = m(ids.to(DEV))
+    assert p.shape == (65536,) and torch.isfinite(p).all() and (p > 0).all() and (p < 1).all()
+    y, concat = m.fm(ids.to(DEV))
+    x = concat[:512].view(512, 39, 16).double().cpu()
+    lin = m.fm.linear.detach().cpu()[ids[:512] + m.fm.offsets.cpu()].squeeze(-1).sum(1).double()
+    torch.testing.assert_close(y[:512].double().cpu(), ofm.fm_pairwise(x) + lin, rtol=1e-4, atol=1e-5)
+    F.binary_cross_entropy(p, torch.full_like(p, 0.25)).backward()
+    assert torch.isfinite(m.fm.embedding.grad).all() and m.fm.embedding.grad.abs().sum() > 0
