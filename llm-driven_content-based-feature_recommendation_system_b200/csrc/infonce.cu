@@ -162,6 +162,7 @@ struct CeParams {
   const float* lse; const float* w_lse; const float* w_diag; const float* w_pos;     // backward, by ORIGINAL row
   float* part_out;              // backward: [nsplit][M][128]
   float out_scale;
+  const float* wmax;            // backward: device scalar max|w| (coefficients are rescaled into the 16-bit range)
 };
 
 __device__ __forceinline__ void item_coords(const CeParams& p, int item, int& rb, int& sp, int& ct_lo, int& ct_hi) {
@@ -487,6 +488,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int quarter = warp & 3;
     const int rloc = quarter * 32 + lane;
     const int t128 = (warp - 2 - 4 * wg) * 32 + lane;
+    // dS entries are O(1/N) (or O(loss scale / N) under a GradScaler): multiply by a power of two that puts the
+    // largest possible coefficient near 2^13 before the 16-bit rounding (fp16 would underflow otherwise) and
+    // divide it out of the fp32 result
+    const float wm = __ldg(p.wmax);
+    int ex = 0;
+    if (wm > 0.f && wm < INFINITY) { (void)frexpf(wm, &ex); ex = 13 - ex; ex = max(-100, min(100, ex)); }
+    const float cs = ldexpf(1.0f, ex), inv_cs = ldexpf(1.0f, -ex);
     uint32_t it = 0, nuse = 0, item_n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       int rb, sp, lo, hi;
@@ -546,7 +554,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               if (edge && (diagbit & (1u << j))) c += wd;
               if (MODE == MODE_SUPCON && (posbits & (1u << j))) c += wp;
             }
-            v[j] = c;
+            v[j] = c * cs;
           }
           // 32 coefficients -> 4 x 16 B chunks of this row in the K-major SWIZZLE_128B tile
           const int box = ch >> 1;
@@ -573,6 +581,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       // ---- drain the dS@X accumulator: warpgroup wg takes columns [64*wg, 64*wg+64)
       mbar_wait(&sh.d2_full, item_n & 1);
       tc_fence_after();
+      const float osc = p.out_scale * inv_cs;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         uint32_t r[32];
@@ -584,8 +593,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(dst + j) =
-                make_float4(__uint_as_float(r[j]) * p.out_scale, __uint_as_float(r[j + 1]) * p.out_scale,
-                            __uint_as_float(r[j + 2]) * p.out_scale, __uint_as_float(r[j + 3]) * p.out_scale);
+                make_float4(__uint_as_float(r[j]) * osc, __uint_as_float(r[j + 1]) * osc,
+                            __uint_as_float(r[j + 2]) * osc, __uint_as_float(r[j + 3]) * osc);
         }
       }
       tc_fence_before();
@@ -596,6 +605,25 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+__global__ void ce_wmax_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                               int64_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    m = fmaxf(m, fabsf(a[i]));
+    if (b) m = fmaxf(m, fabsf(b[i]));
+    if (c) m = fmaxf(m, fabsf(c[i]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) *out = m;
+  }
 }
 
 __global__ void ce_bwd_reduce(const float* __restrict__ part, int nsplit, int64_t n4, float* __restrict__ out) {
@@ -696,7 +724,7 @@ extern "C" size_t rs_ce_workspace_bytes(const rs_ce_problem* p) {
   size_t m = fwd;
   if (bwd_a > m) m = bwd_a;
   if (bwd_b > m) m = bwd_b;
-  return m + 256;
+  return al256(m) + 512;        // + one scalar (max |w|) behind the partial buffers
 }
 
 static void fill_common(CeParams& k, const rs_ce_problem* p, const CePlan& pl) {
@@ -776,8 +804,11 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
   int rc = ce_validate(p);
   if (rc != RS_OK) return rc;
   if (!lse || !w_lse || !workspace || (!dA && !dB)) return RS_ERR_BAD_ARG;
-  if (workspace_bytes < rs_ce_workspace_bytes(p) - 256) return RS_ERR_WORKSPACE;
+  if (workspace_bytes < rs_ce_workspace_bytes(p)) return RS_ERR_WORKSPACE;
   const int mode = ce_mode(p);
+  float* wmax = (float*)((char*)workspace + rs_ce_workspace_bytes(p) - 512);
+  ce_wmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w_lse, w_diag, w_pos, p->M, wmax);
+  RS_LAUNCH_CHECK();
   CUtensorMap mapA, mapB;
   if ((rc = make_map(&mapA, p->a, p->M, p->ab_dtype)) != RS_OK) return rc;
   if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
@@ -794,6 +825,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.lse = lse; k.w_lse = w_lse; k.w_diag = w_diag; k.w_pos = w_pos;
     k.part_out = (float*)workspace;
     k.out_scale = p->scale;
+    k.wmax = wmax;
     if ((rc = launch_bwd_pass<false>(p, mode, k, mapA, mapB, pl.grid, st)) != RS_OK) return rc;
     const int64_t n4 = p->M * CE_K / 4;
     ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dA);
@@ -811,6 +843,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.lse = lse; k.w_lse = w_lse; k.w_diag = w_diag; k.w_pos = w_pos;
     k.part_out = (float*)workspace;
     k.out_scale = p->scale;
+    k.wmax = wmax;
     if ((rc = launch_bwd_pass<true>(p, mode, k, mapB, mapA, pl.grid, st)) != RS_OK) return rc;
     const int64_t n4 = p->N * CE_K / 4;
     ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dB);

@@ -502,7 +502,7 @@ extern "C" int rs_seq_front_bwd(const void* dx, int dx_dtype, const int64_t* con
   if (need > 8) return RS_ERR_UNSUPPORTED;
 #define LAUNCH_BWD(GD, NV)                                                                                     \
   do {                                                                                                         \
-    if (pl.smem_bytes > 48 * 1024)                                                                             \
+    if (pl.smem_bytes > 32 * 1024)                                                                             \
       cudaFuncSetAttribute(seq_front_bwd_kernel<GD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                            (int)pl.smem_bytes);                                                                \
     seq_front_bwd_kernel<GD, NV><<<pl.grid, BWD_WARPS * 32, pl.smem_bytes, st>>>(                              \
