@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--loss-scope", default="all", choices=["all", "last"])
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--minimal", action="store_true", help="only the resident-input timed loop (for ncu runs)")
     return ap.parse_args()
 
 
@@ -229,6 +230,9 @@ def run_ours(args):
         t, m, c = step(b)
         last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
 
+    if args.minimal:
+        print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)))
+        return
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
     ms_e2e = timed(args.steps, e2e_step)

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "../../include/rs_twotower.h"
 #include <cuda.h>
+#include <type_traits>
 
 namespace rs {
 
@@ -44,19 +45,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a protocol bug must fault (trap), never hang the GPU
+// bounded wait: a protocol bug must fault (trap), never hang the GPU.  try_wait carries a suspend-time hint so
+// that a waiting role (producer / MMA issuer) sleeps in hardware instead of burning issue slots that the epilogue
+// warps on the same SM sub-partition need; the clock is only consulted every 256 wake-ups.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
     if (ok) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((spin & 255u) == 255u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -128,6 +135,21 @@ __host__ __device__ inline uint32_t make_idesc(int ab_dtype, bool b_mn_major, bo
          ((uint32_t)(CE_BN >> 3) << 17) | ((uint32_t)(CE_BM >> 4) << 24);
 }
 
+// one column tile's metadata, broadcast-read by the 128 threads of an epilogue warpgroup
+struct __align__(16) ColMeta {
+  float bias[CE_BN];                       // log2 units (0 when absent)
+  uint32_t ka[CE_BN], kb[CE_BN];
+  float lse[CE_BN], wl[CE_BN], wd[CE_BN], wp[CE_BN];   // transposed backward (wl/wd/wp pre-multiplied by cs)
+  uint32_t kb_lo[4], kb_hi[4];             // per staging warp: min / max of kb over its 32 columns
+};
+#define OFF_BIAS 0
+#define OFF_KA (CE_BN * 4)
+#define OFF_KB (2 * CE_BN * 4)
+#define OFF_LSE (3 * CE_BN * 4)
+#define OFF_WL (4 * CE_BN * 4)
+#define OFF_WD (5 * CE_BN * 4)
+#define OFF_WP (6 * CE_BN * 4)
+
 struct CeShared {
   uint64_t full[CE_STAGES], empty[CE_STAGES];
   uint64_t a_full[2], a_empty[2];
@@ -135,13 +157,8 @@ struct CeShared {
   uint64_t p_full[2], p_empty[2];          // backward: dS tile in smem ready / consumed by the tensor core
   uint64_t d2_full, d2_empty;              // backward: dS@X accumulator complete / drained
   uint32_t tmem_base;
-  uint32_t pad;
-  // per epilogue warpgroup [wg][buf]: column metadata of the tile in flight (broadcast reads)
-  float col_bias[2][2][CE_BN];             // log2 units
-  uint32_t col_ka[2][2][CE_BN];
-  uint32_t col_kb[2][2][CE_BN];
-  float col_lse[2][2][CE_BN];              // backward, transposed pass (log2 units)
-  float col_wl[2][2][CE_BN], col_wd[2][2][CE_BN], col_wp[2][2][CE_BN];
+  uint32_t pad[3];
+  ColMeta meta[2][2];                      // [warpgroup][buffer]
   float xm[CE_BM], xl[CE_BM], xps[CE_BM], xpc[CE_BM];   // cross-warpgroup combine (forward)
 };
 
@@ -233,60 +250,232 @@ __device__ __forceinline__ void issue_s(const CeParams& p, CeShared& sh, uint8_t
   umma_commit(&sh.tmem_full[g]);
 }
 
-// stage the metadata of column tile `ct` for warpgroup wg into buffer buf (one column per thread)
+// stage the metadata of column tile `ct` (one column per thread of the warpgroup) + the key_b range of
+// each staging warp's 32 columns (for the range-disjointness test that lets whole tiles skip that compare)
 template <bool BWD_T>
-__device__ __forceinline__ void stage_cols(const CeParams& p, CeShared& sh, int wg, int buf, int ct, int t128) {
+__device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int ct, int t128, float cs) {
   const int64_t c = (int64_t)ct * CE_BN + t128;
   const bool ok = c < p.N;
-  sh.col_bias[wg][buf][t128] = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
-  sh.col_ka[wg][buf][t128] = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
-  sh.col_kb[wg][buf][t128] = (ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
+  cm.bias[t128] = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
+  cm.ka[t128] = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
+  const uint32_t kb = (ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
+  cm.kb[t128] = kb;
+  const uint32_t lo = __reduce_min_sync(0xffffffffu, kb), hi = __reduce_max_sync(0xffffffffu, kb);
+  if ((t128 & 31) == 0) { cm.kb_lo[t128 >> 5] = lo; cm.kb_hi[t128 >> 5] = hi; }
   if (BWD_T) {
-    sh.col_lse[wg][buf][t128] = ok ? __ldg(p.lse + c) * CE_LOG2E : 0.f;
-    sh.col_wl[wg][buf][t128] = ok ? __ldg(p.w_lse + c) : 0.f;
-    sh.col_wd[wg][buf][t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) : 0.f;
-    sh.col_wp[wg][buf][t128] = (ok && p.w_pos) ? __ldg(p.w_pos + c) : 0.f;
+    cm.lse[t128] = ok ? __ldg(p.lse + c) * CE_LOG2E : 0.f;
+    cm.wl[t128] = ok ? __ldg(p.w_lse + c) * cs : 0.f;
+    cm.wd[t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) * cs : 0.f;
+    cm.wp[t128] = (ok && p.w_pos) ? __ldg(p.w_pos + c) * cs : 0.f;
   }
 }
 
-// logits of one 32-column chunk (log2 domain), masks applied; EDGE tiles also handle the diagonal and col >= N
-template <int MODE, bool EDGE>
-__device__ __forceinline__ void logits_chunk(const uint32_t (&r)[32], float (&v)[32], unsigned& posbits,
-                                             unsigned& diagbit, const float* __restrict__ bias2,
-                                             const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
-                                             float rowbias2, uint32_t my_ka, uint32_t my_kb, const CeParams& p,
-                                             int64_t col0, int64_t jd) {
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+template <int E> __device__ __forceinline__ float f4at(const float4& v) { return E == 0 ? v.x : E == 1 ? v.y : E == 2 ? v.z : v.w; }
+template <int E> __device__ __forceinline__ uint32_t u4at(const uint4& v) { return E == 0 ? v.x : E == 1 ? v.y : E == 2 ? v.z : v.w; }
+
+// makes the compiler treat r[] as produced HERE (after tcgen05.wait::ld), so no consumer can be hoisted above the wait
+__device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                    "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                    "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                    "+r"(r[30]), "+r"(r[31]));
+}
+
+struct RowCtx {
+  uint32_t my_ka, my_kb;       // row keys (0xFFFFFFFF: never equal to a column key)
+  float nrowbias2;             // -(row bias) in log2 units (transposed backward)
+  int64_t jd;                  // this row's diagonal column
+  // forward state
+  float m, l, ps, pc;
+  // backward, non-transposed: per-row constants
+  float lse2, wlc, wdc, wpc;
+};
+
+// logits of one 32-column chunk in the log2 domain with the masks applied.
+//   EDGE   : the tile may contain the diagonal or columns >= N (slow path, a handful of tiles)
+//   USE_KB : the key_b (same-user) compare is needed (ranges of row and column keys overlap)
+//   ROWBIAS: bias comes from the row (transposed backward) instead of the column
+template <int MODE, bool EDGE, bool USE_KB, bool ROWBIAS>
+__device__ __forceinline__ void logits32(const uint32_t (&r)[32], float (&v)[32], unsigned& posbits, unsigned& diagbit,
+                                         uint32_t meta, int cbase, const RowCtx& rc, const CeParams& p, int64_t col0) {
   posbits = 0u;
   diagbit = 0u;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float a = __uint_as_float(r[j]);
-    float s;
-    bool masked = false, pos = false;
-    if (MODE == MODE_PLAIN) {
-      s = a * p.scale2;
-    } else {
-      s = fmaf(a, p.scale2, -(bias2[j] + rowbias2));
-      const bool ea = ka[j] == my_ka;
-      if (MODE == MODE_GENERAL) masked = ea | (kb[j] == my_kb);
-      else pos = ea && (my_ka != 0u);
-    }
-    if (EDGE) {
-      const int64_t col = col0 + j;
-      if (col == jd) {
-        diagbit |= 1u << j;
-        pos = false;
-        masked = (p.flags & RS_CE_DIAG_MASK) != 0;
-        if (p.flags & RS_CE_DIAG_RAW) s = a * p.scale2;
+  for (int q = 0; q < 8; ++q) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 a4 = make_uint4(0, 0, 0, 0), k4 = make_uint4(0, 0, 0, 0);
+    if (MODE != MODE_PLAIN && !ROWBIAS) b4 = lds_f4(meta + OFF_BIAS + (cbase + 4 * q) * 4);
+    if (MODE != MODE_PLAIN) a4 = lds_u4(meta + OFF_KA + (cbase + 4 * q) * 4);
+    if (MODE == MODE_GENERAL && USE_KB) k4 = lds_u4(meta + OFF_KB + (cbase + 4 * q) * 4);
+    auto one = [&](auto ec) {
+      constexpr int e = decltype(ec)::value;
+      const int j = 4 * q + e;
+      const float a = __uint_as_float(r[j]);
+      float s;
+      bool masked = false, pos = false;
+      if (MODE == MODE_PLAIN) s = a * p.scale2;
+      else if (ROWBIAS) s = fmaf(a, p.scale2, rc.nrowbias2);
+      else s = fmaf(a, p.scale2, -f4at<e>(b4));
+      if (MODE != MODE_PLAIN) {
+        const bool ea = u4at<e>(a4) == rc.my_ka;
+        if (MODE == MODE_GENERAL) masked = USE_KB ? (ea | (u4at<e>(k4) == rc.my_kb)) : ea;
+        else pos = ea;
       }
-      s = masked ? p.mask2 : s;
-      if (col >= p.N) { s = -INFINITY; pos = false; }
-    } else if (MODE == MODE_GENERAL) {
-      s = masked ? p.mask2 : s;
-    }
-    if (MODE == MODE_SUPCON && pos) posbits |= 1u << j;
-    v[j] = s;
+      if (EDGE) {
+        const int64_t col = col0 + j;
+        if (col == rc.jd) {
+          diagbit |= 1u << j;
+          pos = false;
+          masked = (p.flags & RS_CE_DIAG_MASK) != 0;
+          if (p.flags & RS_CE_DIAG_RAW) s = a * p.scale2;
+        }
+        s = masked ? p.mask2 : s;
+        if (col >= p.N) { s = -INFINITY; pos = false; }
+      } else if (MODE == MODE_GENERAL) {
+        s = masked ? p.mask2 : s;
+      }
+      if (MODE == MODE_SUPCON && pos) posbits |= 1u << j;
+      v[j] = s;
+    };
+    one(std::integral_constant<int, 0>{});
+    one(std::integral_constant<int, 1>{});
+    one(std::integral_constant<int, 2>{});
+    one(std::integral_constant<int, 3>{});
   }
+}
+
+// forward: fold one chunk into the running (max, sum) [+ SupCon sums, + the diagonal logit]
+template <int MODE, bool EDGE, bool USE_KB>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t meta, int cbase, RowCtx& rc,
+                                          const CeParams& p, int64_t col0, bool row_ok, int64_t row) {
+  float v[32];
+  unsigned posbits, diagbit;
+  logits32<MODE, EDGE, USE_KB, false>(r, v, posbits, diagbit, meta, cbase, rc, p, col0);
+  float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]);
+#pragma unroll
+  for (int j = 4; j < 32; j += 2) { c0 = fmaxf(c0, v[j]); c1 = fmaxf(c1, v[j + 1]); }
+  const float m_new = fmaxf(rc.m, fmaxf(c0, c1));
+  const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+  rc.l *= ex2(rc.m - m_use);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) { a0 += ex2(v[j] - m_use); a1 += ex2(v[j + 1] - m_use); }
+  rc.l += a0 + a1;
+  rc.m = m_new;
+  if (MODE == MODE_SUPCON) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) rc.ps += (posbits & (1u << j)) ? v[j] : 0.f;
+    rc.pc += (float)__popc(posbits);
+  }
+  if (EDGE && diagbit && row_ok) {
+    float dv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (diagbit & (1u << j)) dv = v[j];
+    p.diag_out[row] = dv * CE_LN2;
+  }
+}
+
+// backward: coefficients dS of one chunk -> 16-bit -> this row's 4 x 16 B pieces of the K-major SWIZZLE_128B tile
+template <int MODE, bool EDGE, bool USE_KB, bool TRANSPOSED>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t meta, int cbase, const RowCtx& rc,
+                                          const CeParams& p, int64_t col0, uint8_t* prow, int rloc, bool bf16) {
+  float v[32];
+  unsigned posbits, diagbit;
+  logits32<MODE, EDGE, USE_KB, TRANSPOSED>(r, v, posbits, diagbit, meta, cbase, rc, p, col0);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 l4, w4, d4, p4;
+    if (TRANSPOSED) {
+      l4 = lds_f4(meta + OFF_LSE + (cbase + 4 * q) * 4);
+      w4 = lds_f4(meta + OFF_WL + (cbase + 4 * q) * 4);
+      if (EDGE) d4 = lds_f4(meta + OFF_WD + (cbase + 4 * q) * 4);
+      if (MODE == MODE_SUPCON) p4 = lds_f4(meta + OFF_WP + (cbase + 4 * q) * 4);
+    }
+    auto one = [&](auto ec) {
+      constexpr int e = decltype(ec)::value;
+      const int j = 4 * q + e;
+      float c;
+      if (TRANSPOSED) {
+        c = f4at<e>(w4) * ex2(v[j] - f4at<e>(l4));
+        if (EDGE) c += (diagbit & (1u << j)) ? f4at<e>(d4) : 0.f;
+        if (MODE == MODE_SUPCON) c += (posbits & (1u << j)) ? f4at<e>(p4) : 0.f;
+      } else {
+        c = rc.wlc * ex2(v[j] - rc.lse2);
+        if (EDGE) c += (diagbit & (1u << j)) ? rc.wdc : 0.f;
+        if (MODE == MODE_SUPCON) c += (posbits & (1u << j)) ? rc.wpc : 0.f;
+      }
+      v[j] = c;
+    };
+    one(std::integral_constant<int, 0>{});
+    one(std::integral_constant<int, 1>{});
+    one(std::integral_constant<int, 2>{});
+    one(std::integral_constant<int, 3>{});
+  }
+  const int box = cbase >> 6;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    if (bf16) {
+      u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+      u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    } else {
+      u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
+      u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
+    }
+    const int chunk = (((cbase >> 5) & 1) * 4 + q) ^ (rloc & 7);
+    *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = u;
+  }
+}
+
+// walk the four 32-column chunks of accumulator `g` with the TMEM load of chunk c+1 in flight while chunk c
+// is processed; F(r, cbase) consumes one chunk
+template <class F>
+__device__ __forceinline__ void for_chunks(uint32_t tmem_tile, F&& f) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32(tmem_tile, ra);
+  tmem_ld_wait();
+  pin32(ra);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    tmem_ld32(tmem_tile + (uint32_t)(h * 64 + 32), rb);
+    f(ra, h * 64);
+    tmem_ld_wait();
+    pin32(rb);
+    if (h == 0) tmem_ld32(tmem_tile + 64u, ra);
+    f(rb, h * 64 + 32);
+    if (h == 0) { tmem_ld_wait(); pin32(ra); }
+  }
+}
+
+__device__ __forceinline__ void load_row_keys(const CeParams& p, int64_t row, bool row_ok, bool supcon, RowCtx& rc,
+                                              uint32_t& wkb_lo, uint32_t& wkb_hi) {
+  rc.my_ka = 0xFFFFFFFFu;
+  rc.my_kb = 0xFFFFFFFFu;
+  if (row_ok) {
+    if (p.key_a_row) rc.my_ka = (uint32_t)__ldg(p.key_a_row + row);
+    if (p.key_b_row) rc.my_kb = (uint32_t)__ldg(p.key_b_row + row);
+  }
+  if (supcon && rc.my_ka == 0u) rc.my_ka = 0xFFFFFFFFu;      // padding targets have no positives (invariant 8)
+  // key_b range of this WARP's 32 rows (rows without a key never match: keep them out of the range)
+  wkb_lo = __reduce_min_sync(0xffffffffu, rc.my_kb);
+  wkb_hi = __reduce_max_sync(0xffffffffu, rc.my_kb == 0xFFFFFFFFu ? 0u : rc.my_kb);
+}
+
+__device__ __forceinline__ bool kb_overlaps(const ColMeta& cm, uint32_t wkb_lo, uint32_t wkb_hi) {
+  const uint32_t lo = min(min(cm.kb_lo[0], cm.kb_lo[1]), min(cm.kb_lo[2], cm.kb_lo[3]));
+  const uint32_t hi = max(max(cm.kb_hi[0], cm.kb_hi[1]), max(cm.kb_hi[2], cm.kb_hi[3]));
+  return !(wkb_hi < lo || hi < wkb_lo);
 }
 
 // ================================================================================ forward kernel
@@ -333,73 +522,44 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       item_coords(p, item, rb, sp, lo, hi);
       const int64_t row = (int64_t)rb * CE_BM + rloc;
       const bool row_ok = row < p.M;
-      uint32_t my_ka = 0xFFFFFFFFu, my_kb = 0xFFFFFFFFu;
-      if (MODE != MODE_PLAIN && row_ok) {
-        if (p.key_a_row) my_ka = (uint32_t)__ldg(p.key_a_row + row);
-        if (p.key_b_row) my_kb = (uint32_t)__ldg(p.key_b_row + row);
-      }
-      const int64_t jd = row + p.diag_offset;
+      RowCtx rc;
+      uint32_t wkb_lo, wkb_hi;
+      load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi);
+      rc.nrowbias2 = 0.f;
+      rc.jd = row + p.diag_offset;
+      rc.m = -INFINITY; rc.l = 0.f; rc.ps = 0.f; rc.pc = 0.f;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;   // diag col span
-      float m = -INFINITY, l = 0.f, ps = 0.f, pc = 0.f;
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it & 1) != wg) continue;
-        const int buf = nuse & 1;
-        stage_cols<false>(p, sh, wg, buf, ct, t128);
+        ColMeta& cm = sh.meta[wg][nuse & 1];
+        stage_cols<false>(p, cm, ct, t128, 1.0f);
         named_bar_sync(1 + wg, 128);
-        mbar_wait(&sh.tmem_full[wg], nuse & 1);
-        tc_fence_after();
+        const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
         const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          float v[32];
-          unsigned posbits, diagbit;
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN + ch * 32), r);
-          tmem_ld_wait();
-          const float* b2 = &sh.col_bias[wg][buf][ch * 32];
-          const uint32_t* ka = &sh.col_ka[wg][buf][ch * 32];
-          const uint32_t* kb = &sh.col_kb[wg][buf][ch * 32];
-          if (edge) logits_chunk<MODE, true>(r, v, posbits, diagbit, b2, ka, kb, 0.f, my_ka, my_kb, p, c0 + ch * 32, jd);
-          else logits_chunk<MODE, false>(r, v, posbits, diagbit, b2, ka, kb, 0.f, my_ka, my_kb, p, c0 + ch * 32, jd);
-          float cmax = v[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
-          const float m_new = fmaxf(m, cmax);
-          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-          l *= ex2(m - m_use);
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) { acc0 += ex2(v[j] - m_use); acc1 += ex2(v[j + 1] - m_use); }
-          l += acc0 + acc1;
-          m = m_new;
-          if (MODE == MODE_SUPCON) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (posbits & (1u << j)) { ps += v[j]; pc += 1.f; }
-          }
-          if (edge && diagbit && row_ok) {
-            float dv = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (diagbit & (1u << j)) dv = v[j];
-            p.diag_out[row] = dv * CE_LN2;
-          }
-        }
+        const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
+        mbar_wait(&sh.tmem_full[wg], nuse & 1);
+        tc_fence_after();
+        const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
+        if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+        else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+        else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[wg]);
         ++nuse;
       }
       // ---- combine the two warpgroups' running (max, sum) and write this split's partial
-      if (wg == 1) { sh.xm[rloc] = m; sh.xl[rloc] = l; sh.xps[rloc] = ps; sh.xpc[rloc] = pc; }
+      if (wg == 1) { sh.xm[rloc] = rc.m; sh.xl[rloc] = rc.l; sh.xps[rloc] = rc.ps; sh.xpc[rloc] = rc.pc; }
       named_bar_sync(3, 256);
       if (wg == 0 && row_ok) {
         const float m1 = sh.xm[rloc], l1 = sh.xl[rloc];
-        const float mm = fmaxf(m, m1);
+        const float mm = fmaxf(rc.m, m1);
         const float mu = (mm == -INFINITY) ? 0.f : mm;
-        const float ll = l * ex2(m - mu) + l1 * ex2(m1 - mu);
+        const float ll = rc.l * ex2(rc.m - mu) + l1 * ex2(m1 - mu);
         const int64_t o = (int64_t)sp * p.M + row;
         p.part_m[o] = mm;
         p.part_l[o] = ll;
-        if (MODE == MODE_SUPCON) { p.part_ps[o] = ps + sh.xps[rloc]; p.part_pc[o] = pc + sh.xpc[rloc]; }
+        if (MODE == MODE_SUPCON) { p.part_ps[o] = rc.ps + sh.xps[rloc]; p.part_pc[o] = rc.pc + sh.xpc[rloc]; }
       }
       named_bar_sync(3, 256);
     }
@@ -495,83 +655,45 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     int ex = 0;
     if (wm > 0.f && wm < INFINITY) { (void)frexpf(wm, &ex); ex = 13 - ex; ex = max(-100, min(100, ex)); }
     const float cs = ldexpf(1.0f, ex), inv_cs = ldexpf(1.0f, -ex);
+    const bool bf16 = (p.idesc_s & (1u << 7)) != 0;
     uint32_t it = 0, nuse = 0, item_n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       int rb, sp, lo, hi;
       item_coords(p, item, rb, sp, lo, hi);
       const int64_t row = (int64_t)rb * CE_BM + rloc;
       const bool row_ok = row < p.M;
-      uint32_t my_ka = 0xFFFFFFFFu, my_kb = 0xFFFFFFFFu;
-      if (MODE != MODE_PLAIN && row_ok) {
-        if (p.key_a_row) my_ka = (uint32_t)__ldg(p.key_a_row + row);
-        if (p.key_b_row) my_kb = (uint32_t)__ldg(p.key_b_row + row);
-      }
-      float rowbias2 = 0.f, lse2 = 0.f, wl = 0.f, wd = 0.f, wp = 0.f;
+      RowCtx rc;
+      uint32_t wkb_lo, wkb_hi;
+      load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi);
+      rc.nrowbias2 = 0.f; rc.lse2 = 0.f; rc.wlc = 0.f; rc.wdc = 0.f; rc.wpc = 0.f;
       if (row_ok) {
-        if (TRANSPOSED) { if (p.row_bias) rowbias2 = __ldg(p.row_bias + row) * CE_LOG2E; }
+        if (TRANSPOSED) { if (p.row_bias) rc.nrowbias2 = -__ldg(p.row_bias + row) * CE_LOG2E; }
         else {
-          lse2 = __ldg(p.lse + row) * CE_LOG2E;
-          wl = __ldg(p.w_lse + row);
-          if (p.w_diag) wd = __ldg(p.w_diag + row);
-          if (p.w_pos) wp = __ldg(p.w_pos + row);
+          rc.lse2 = __ldg(p.lse + row) * CE_LOG2E;
+          rc.wlc = __ldg(p.w_lse + row) * cs;
+          if (p.w_diag) rc.wdc = __ldg(p.w_diag + row) * cs;
+          if (p.w_pos) rc.wpc = __ldg(p.w_pos + row) * cs;
         }
       }
-      const int64_t jd = row + p.diag_offset;
+      rc.jd = row + p.diag_offset;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it & 1) != wg) continue;
-        const int buf = nuse & 1;
-        stage_cols<TRANSPOSED>(p, sh, wg, buf, ct, t128);
+        ColMeta& cm = sh.meta[wg][nuse & 1];
+        stage_cols<TRANSPOSED>(p, cm, ct, t128, cs);
         named_bar_sync(1 + wg, 128);
+        const uint32_t meta = smem_u32(&cm);
+        const int64_t c0 = (int64_t)ct * CE_BN;
+        const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
+        const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
         mbar_wait(&sh.tmem_full[wg], nuse & 1);
         mbar_wait(&sh.p_empty[wg], (nuse & 1) ^ 1);     // the tensor core is done with this warpgroup's dS buffer
         tc_fence_after();
-        const int64_t c0 = (int64_t)ct * CE_BN;
-        const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
         uint8_t* prow = sP + wg * CE_TILE_BYTES + rloc * 128;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          float v[32];
-          unsigned posbits, diagbit;
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN + ch * 32), r);
-          tmem_ld_wait();
-          const float* b2 = &sh.col_bias[wg][buf][ch * 32];
-          const uint32_t* ka = &sh.col_ka[wg][buf][ch * 32];
-          const uint32_t* kb = &sh.col_kb[wg][buf][ch * 32];
-          if (edge) logits_chunk<MODE, true>(r, v, posbits, diagbit, b2, ka, kb, rowbias2, my_ka, my_kb, p, c0 + ch * 32, jd);
-          else logits_chunk<MODE, false>(r, v, posbits, diagbit, b2, ka, kb, rowbias2, my_ka, my_kb, p, c0 + ch * 32, jd);
-          // coef = w_lse * softmax + w_diag [diag] + w_pos [positive]
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float c;
-            if (TRANSPOSED) {
-              c = sh.col_wl[wg][buf][ch * 32 + j] * ex2(v[j] - sh.col_lse[wg][buf][ch * 32 + j]);
-              if (edge && (diagbit & (1u << j))) c += sh.col_wd[wg][buf][ch * 32 + j];
-              if (MODE == MODE_SUPCON && (posbits & (1u << j))) c += sh.col_wp[wg][buf][ch * 32 + j];
-            } else {
-              c = wl * ex2(v[j] - lse2);
-              if (edge && (diagbit & (1u << j))) c += wd;
-              if (MODE == MODE_SUPCON && (posbits & (1u << j))) c += wp;
-            }
-            v[j] = c * cs;
-          }
-          // 32 coefficients -> 4 x 16 B chunks of this row in the K-major SWIZZLE_128B tile
-          const int box = ch >> 1;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            if (p.idesc_s & (1u << 7)) {
-              u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-              u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-            } else {
-              u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
-              u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
-            }
-            const int chunk = ((ch & 1) * 4 + q) ^ (rloc & 7);
-            *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = u;
-          }
-        }
+        const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
+        if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, true, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
+        else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
+        else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, false, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[wg]);
         fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
@@ -588,6 +710,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int d0 = wg * 64 + h * 32;
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * CE_BN + d0), r);
         tmem_ld_wait();
+        pin32(r);
         if (row_ok) {
           float* dst = p.part_out + ((int64_t)sp * p.M + row) * CE_K + d0;
 #pragma unroll

@@ -131,6 +131,99 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) seq_front_bwd_kernel(
   }
 }
 
+// dim == 128, L <= 64 fast path.  A CTA streams whole batch rows (L consecutive positions = one contiguous
+// slab of dX); warp w owns the time steps l = w, w+8, ... so the positional sums stay in registers, and it
+// keeps up to 8 independent row loads in flight per batch row.
+#define BWD_LPW 8          // time steps per warp (L <= 8 * BWD_LPW)
+template <int GD>
+__global__ void __launch_bounds__(BWD_WARPS * 32, 2) seq_front_bwd128_kernel(
+    const void* __restrict__ dx, SeqBwdParams prm, const float* __restrict__ gates, int L, int64_t B,
+    int64_t padding_idx, float* __restrict__ pos_part, float* __restrict__ small_part,
+    float* __restrict__ gate_part) {
+  constexpr int D = 128;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int small_elems = prm.small_rows * D;
+  float* priv = smem + (size_t)wid * small_elems;
+  for (int i = lane; i < small_elems; i += 32) priv[i] = 0.f;
+  __syncwarp();
+  float g[RS_MAX_TABLES], dotacc[RS_MAX_TABLES];
+#pragma unroll
+  for (int t = 0; t < RS_MAX_TABLES; ++t) {
+    g[t] = (t < prm.n_tables) ? __ldg(gates + t) : 0.f;
+    dotacc[t] = 0.f;
+  }
+  float4 pacc[BWD_LPW];
+#pragma unroll
+  for (int i = 0; i < BWD_LPW; ++i) pacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    float4 d[BWD_LPW];
+#pragma unroll
+    for (int i = 0; i < BWD_LPW; ++i) {
+      const int l = wid + BWD_WARPS * i;
+      d[i] = (l < L) ? load4<GD>(dx, (b * L + l) * D + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < RS_MAX_TABLES; ++t) {
+      if (t >= prm.n_tables || prm.mode[t] == 0) continue;       // warp-uniform
+      int id[BWD_LPW];
+      float4 e[BWD_LPW];
+#pragma unroll
+      for (int i = 0; i < BWD_LPW; ++i) {
+        const int l = wid + BWD_WARPS * i;
+        id[i] = -1;
+        if (l < L) {
+          const int64_t x = __ldg(prm.ids[t] + b * L + l);
+          if (x >= 0 && x < prm.rows[t]) id[i] = (int)x;
+        }
+        if (id[i] >= 0) e[i] = ldg_f4(prm.tables[t] + (int64_t)id[i] * D + 4 * lane);
+      }
+#pragma unroll
+      for (int i = 0; i < BWD_LPW; ++i) {
+        if (id[i] < 0) continue;
+        dotacc[t] += dot4(e[i], d[i]);
+        if (id[i] == padding_idx) continue;
+        if (prm.mode[t] == 1) {
+          red_add_f4(prm.d_tables[t] + (int64_t)id[i] * D + 4 * lane,
+                     make_float4(g[t] * d[i].x, g[t] * d[i].y, g[t] * d[i].z, g[t] * d[i].w));
+        } else {
+          float4* q = reinterpret_cast<float4*>(priv + ((size_t)(prm.small_off[t] + id[i])) * D + 4 * lane);
+          *q = fma4(*q, d[i], g[t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BWD_LPW; ++i) {
+      pacc[i].x += d[i].x; pacc[i].y += d[i].y; pacc[i].z += d[i].z; pacc[i].w += d[i].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < BWD_LPW; ++i) {
+    const int l = wid + BWD_WARPS * i;
+    if (l < L) *reinterpret_cast<float4*>(pos_part + ((size_t)blockIdx.x * L + l) * D + 4 * lane) = pacc[i];
+  }
+  __shared__ float s_dot[BWD_WARPS][RS_MAX_TABLES];
+#pragma unroll
+  for (int t = 0; t < RS_MAX_TABLES; ++t) {
+    const float s = warp_sum(dotacc[t]);
+    if (lane == 0) s_dot[wid][t] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < small_elems; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < BWD_WARPS; ++w) s += smem[(size_t)w * small_elems + i];
+    small_part[(size_t)blockIdx.x * small_elems + i] = s;
+  }
+  if (threadIdx.x < RS_MAX_TABLES) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < BWD_WARPS; ++w) s += s_dot[w][threadIdx.x];
+    gate_part[(size_t)blockIdx.x * RS_MAX_TABLES + threadIdx.x] = s;
+  }
+}
+
 __global__ void seq_front_bwd_finalize(SeqBwdParams prm, int64_t L, int64_t dim, int nchunks, int nctas,
                                        const float* __restrict__ pos_part, const float* __restrict__ small_part,
                                        const float* __restrict__ gate_part, float* __restrict__ d_pos,
@@ -313,50 +406,63 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segment_tile_kernel(
     for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = __shfl_sync(0xffffffffu, my_key, 0);
     int seg_a = 0;
-    for (int j = 0; j <= cnt; ++j) {
-      const int k = (j < cnt) ? __shfl_sync(0xffffffffu, my_key, j) : -4;
-      if (j == cnt || k != cur) {
-        // ---- flush segment [seg_a, j) with key `cur`
-        const bool left_done = (seg_a > 0) || (prev_key != cur);
-        const bool right_done = (j < cnt) || (next_key != cur);
-        const bool valid = cur >= 0 && cur < rows;
-        if (dot_table && valid) {
+    // flush segment [seg_a, j) with key `cur`
+    auto flush = [&](int j) {
+      const bool left_done = (seg_a > 0) || (prev_key != cur);
+      const bool right_done = (j < cnt) || (next_key != cur);
+      const bool valid = cur >= 0 && cur < rows;
+      if (dot_table && valid) {
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const int v = lane + 32 * i;
-            if (v < vecs) dot_local += dot4(ldg_f4(dot_table + (int64_t)cur * dim + 4 * v), acc[i]);
-          }
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < vecs) dot_local += dot4(ldg_f4(dot_table + (int64_t)cur * dim + 4 * v), acc[i]);
         }
-        if (valid && cur != padding_idx) {
-          float* dst;
-          float s = 1.0f;
-          if (left_done && right_done) { dst = d_table + (int64_t)cur * dim; s = scale; }
-          else if (!left_done) dst = partL + tile * dim;
-          else dst = partR + tile * dim;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const int v = lane + 32 * i;
-            if (v < vecs)
-              *reinterpret_cast<float4*>(dst + 4 * v) =
-                  make_float4(acc[i].x * s, acc[i].y * s, acc[i].z * s, acc[i].w * s);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cur = k;
-        seg_a = j;
-        if (j == cnt) break;
       }
-      const int p = __shfl_sync(0xffffffffu, my_pos, j);
+      if (valid && cur != padding_idx) {
+        float* dst;
+        float sc = 1.0f;
+        if (left_done && right_done) { dst = d_table + (int64_t)cur * dim; sc = scale; }
+        else if (!left_done) dst = partL + tile * dim;
+        else dst = partR + tile * dim;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int v = lane + 32 * i;
-        if (v < vecs) {
-          const float4 g = load4<GD>(d_out, (int64_t)p * dim + 4 * v);
-          acc[i].x += g.x; acc[i].y += g.y; acc[i].z += g.z; acc[i].w += g.w;
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < vecs)
+            *reinterpret_cast<float4*>(dst + 4 * v) =
+                make_float4(acc[i].x * sc, acc[i].y * sc, acc[i].z * sc, acc[i].w * sc);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // rows are fetched SEG_G at a time (independent loads in flight), then folded in sorted order
+    constexpr int SEG_G = NV == 1 ? 8 : (NV == 2 ? 4 : 1);
+    for (int j0 = 0; j0 < cnt; j0 += SEG_G) {
+      float4 gbuf[SEG_G][NV];
+#pragma unroll
+      for (int u = 0; u < SEG_G; ++u) {
+        const int p = __shfl_sync(0xffffffffu, my_pos, (j0 + u) & 31);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + 32 * i;
+          gbuf[u][i] = (j0 + u < cnt && v < vecs) ? load4<GD>(d_out, (int64_t)p * dim + 4 * v)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < SEG_G; ++u) {
+        const int j = j0 + u;
+        const int k = __shfl_sync(0xffffffffu, my_key, j & 31);
+        if (j < cnt) {
+          if (k != cur) { flush(j); cur = k; seg_a = j; }
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            acc[i].x += gbuf[u][i].x; acc[i].y += gbuf[u][i].y; acc[i].z += gbuf[u][i].z; acc[i].w += gbuf[u][i].w;
+          }
         }
       }
     }
+    flush(cnt);
   }
   if (dot_part) {
     dot_local = warp_sum(dot_local);
@@ -409,11 +515,19 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segment_fixup_kernel(
   }
 }
 
-__global__ void dot_finalize_kernel(const float* __restrict__ dot_part, int nparts, float* __restrict__ dot_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < nparts; ++i) s += dot_part[i];
-    *dot_out += s;
+__global__ void __launch_bounds__(1024) dot_finalize_kernel(const float* __restrict__ dot_part, int nparts,
+                                                            float* __restrict__ dot_out) {
+  // fixed association order (strided partial sums, then a warp tree): deterministic
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += dot_part[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *dot_out += s;
   }
 }
 
@@ -435,7 +549,7 @@ using namespace rs;
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct SeqBwdPlan {
-  int nchunks, grid, small_rows;
+  int nchunks, grid, small_rows, fast;
   size_t pos_bytes, small_bytes, gate_bytes, smem_bytes;
 };
 static int make_seq_bwd_plan(int64_t P, int64_t L, int64_t dim, int n_tables, const int64_t* table_rows,
@@ -448,6 +562,11 @@ static int make_seq_bwd_plan(int64_t P, int64_t L, int64_t dim, int n_tables, co
   if (grid > 2 * RS_NUM_SMS) grid = 2 * RS_NUM_SMS;
   if (grid < 1) grid = 1;
   pl->grid = (int)grid;
+  pl->fast = (dim == 128 && L <= BWD_WARPS * BWD_LPW) ? 1 : 0;
+  if (pl->fast) {                      // one CTA streams whole batch rows; one positional partial per CTA
+    pl->grid = (int)(B < 2 * RS_NUM_SMS ? (B < 1 ? 1 : B) : 2 * RS_NUM_SMS);
+    pl->nchunks = pl->grid;
+  }
   pl->small_rows = 0;
   for (int t = 0; t < n_tables; ++t)
     if (big_mode[t] == 2) pl->small_rows += (int)table_rows[t];
@@ -508,7 +627,19 @@ extern "C" int rs_seq_front_bwd(const void* dx, int dx_dtype, const int64_t* con
     seq_front_bwd_kernel<GD, NV><<<pl.grid, BWD_WARPS * 32, pl.smem_bytes, st>>>(                              \
         dx, prm, gates, L, B, dim, padding_idx, pl.nchunks, pos_part, small_part, gate_part);                  \
   } while (0)
-  DISPATCH_DT(dx_dtype, GD, if (need <= 1) LAUNCH_BWD(GD, 1); else if (need <= 2) LAUNCH_BWD(GD, 2); else LAUNCH_BWD(GD, 8));
+#define LAUNCH_BWD128(GD)                                                                                       \
+  do {                                                                                                         \
+    if (pl.smem_bytes > 32 * 1024)                                                                             \
+      cudaFuncSetAttribute(seq_front_bwd128_kernel<GD>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                           (int)pl.smem_bytes);                                                                \
+    seq_front_bwd128_kernel<GD><<<pl.grid, BWD_WARPS * 32, pl.smem_bytes, st>>>(                               \
+        dx, prm, gates, (int)L, B, padding_idx, pos_part, small_part, gate_part);                              \
+  } while (0)
+  if (pl.fast) {
+    DISPATCH_DT(dx_dtype, GD, LAUNCH_BWD128(GD));
+  } else {
+    DISPATCH_DT(dx_dtype, GD, if (need <= 1) LAUNCH_BWD(GD, 1); else if (need <= 2) LAUNCH_BWD(GD, 2); else LAUNCH_BWD(GD, 8));
+  }
   RS_LAUNCH_CHECK();
   const int64_t fin = L * dim + (int64_t)pl.small_rows * dim + RS_MAX_TABLES;
   seq_front_bwd_finalize<<<(int)((fin + 255) / 256), 256, 0, st>>>(prm, L, dim, pl.nchunks, pl.grid, pos_part,
@@ -603,7 +734,7 @@ extern "C" int rs_segment_reduce_rows(const void* d_out, int d_out_dtype, const 
   DISPATCH_DT(d_out_dtype, GD, if (need <= 1) LAUNCH_SEG(GD, 1); else if (need <= 2) LAUNCH_SEG(GD, 2); else LAUNCH_SEG(GD, 8));
   RS_LAUNCH_CHECK_N(2);
   if (dot_table) {
-    dot_finalize_kernel<<<1, 32, 0, st>>>(dot_part, grid * SEG_WARPS, dot_out);
+    dot_finalize_kernel<<<1, 1024, 0, st>>>(dot_part, grid * SEG_WARPS, dot_out);
     RS_LAUNCH_CHECK();
   }
   return RS_OK;

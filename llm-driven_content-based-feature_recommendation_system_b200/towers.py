@@ -96,7 +96,11 @@ class SASRecUserTower(nn.Module):
 
     def forward(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids,
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
-                fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True):
+                fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None):
+        """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
+        When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
+        returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
+        so the other ~75 % of the [B,L] grid need not go through output_proj."""
         seq_len = item_ids.size(1)
         seq_emb = self.embed_front(pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids,
                                    section_ids)
@@ -106,7 +110,11 @@ class SASRecUserTower(nn.Module):
         static_input = self.static_front(age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids,
                                          club_status_ids, news_freq_ids, fn_ids, active_ids, cont_feats)
         user_profile_vec = self.static_mlp(static_input)
-        if training_mode:
+        if training_mode and select_index is not None:
+            rows = ops.gather_rows(output.reshape(-1, output.shape[-1]), select_index)
+            prof = ops.gather_rows(user_profile_vec, select_index // seq_len)
+            final_vec = self.output_proj(torch.cat([rows, prof.to(rows.dtype)], dim=-1))
+        elif training_mode:
             expanded = user_profile_vec.unsqueeze(1).expand(-1, seq_len, -1)
             final_vec = self.output_proj(torch.cat([output, expanded], dim=-1))
         else:

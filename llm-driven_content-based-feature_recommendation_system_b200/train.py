@@ -37,6 +37,7 @@ def add_host_index(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     batch["valid_index"] = torch.nonzero(valid.reshape(-1)).squeeze(1)
     last = (valid.sum(dim=1) - 1).clamp(min=0)
     batch["last_index"] = torch.arange(B) * L + last
+    batch["select_index"] = torch.cat([batch["valid_index"], batch["last_index"]])
     return batch
 
 
@@ -53,20 +54,23 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
         pretrained_vecs = ops.gather_rows(pretrained_lookup, item_ids)
     kw = {k: batch[k] for k in FORWARD_KEYS}
     with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
-        out1 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True)
-        out2 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True)
-        flat1 = out1.reshape(B * L, -1)
-        flat2 = out2.reshape(B * L, -1)
         tgt_flat = batch["target_ids"].reshape(-1)
         idx = batch["valid_index"] if loss_scope == "all" else batch["last_index"]
-        u = F.normalize(ops.gather_rows(flat1, idx), p=2, dim=1)                      # :794-807
+        li = batch["last_index"]
+        n_main = idx.numel()
+        # view 1 feeds the main loss (valid steps) and DuoRec (last step); view 2 only DuoRec: the late-fusion
+        # head runs on exactly those rows (same values as slicing the full [B,L,128] output)
+        sel1 = batch.get("select_index")
+        if sel1 is None:
+            sel1 = torch.cat([idx, li])
+        out1 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1)
+        out2 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=li)
+        u = F.normalize(out1[:n_main], p=2, dim=1)                                   # :794-807
         tgt = tgt_flat[idx]
         uid = idx // L                                                               # batch row = user id (:801-804)
         v = item_tower.normalized_rows(tgt)                                          # :810-811 + :833
         main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq)
-        li = batch["last_index"]                                                     # :830-842
-        cl = losses.duorec_loss_refined(ops.gather_rows(flat1, li), ops.gather_rows(flat2, li), tgt_flat[li],
-                                        lambda_sup=lambda_sup)
+        cl = losses.duorec_loss_refined(out1[n_main:], out2, tgt_flat[li], lambda_sup=lambda_sup)   # :830-842
         total = main + lambda_cl * cl
     if optimizer is not None:
         if scaler is not None:
