@@ -235,6 +235,30 @@ int rs_retrieve_topk(const float* users, int64_t n_users, const float* items, in
                      int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------- C4 / C5: hard-negative mining + sparse logits */
+
+/* Mining (no gradient) of tower_code/v1_refine_usertower.py:775-791 (:643-668, :707-719): for each row i the
+ * top-k columns j of cos_ij = <u_i, v_j> over the columns that are NOT ignored, where
+ *   ignored(i,j) = key[i] == key[j]  ||  ( <v_i, v_j> > hnm_threshold && i != j ).
+ * u, v: [n, dim] fp32, L2-normalised by the caller.  Fused: both Gram products share the item tile, the
+ * [n,n] similarity / mask matrices are never written.  out_* [n,k] sorted (score desc, id asc), padded with
+ * (-inf, -1) when a row has fewer than k candidates; avail[i] = number of non-ignored columns. */
+size_t rs_mine_workspace_bytes(int64_t n, int64_t dim, int64_t k);
+int rs_mine_hard_negatives(const float* u, const float* v, const int64_t* key, int64_t n, int64_t dim, int64_t k,
+                           float hnm_threshold, int64_t* out_ids, float* out_scores, int32_t* avail,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i,c] = scale * <a_i, b_idx[i,c]> - bias[idx[i,c]]   (-inf where idx < 0 or key_row[i] == key_col[idx]).
+ * The gathered logits of torch.gather(logits, 1, top_k_indices) (:677-678, :732-734) without the [n,n] logits.
+ * a [n,dim], b [m,dim] in ab_dtype (f32/f16/bf16); fp32 accumulation. */
+int rs_sparse_logits_fwd(const void* a, const void* b, int ab_dtype, const int64_t* idx, int64_t n, int64_t m,
+                         int64_t k, int64_t dim, float scale, const float* bias, const int64_t* key_row,
+                         const int64_t* key_col, float* out, void* stream);
+/* d_a [n,dim] fp32 overwritten; d_b [m,dim] fp32 accumulated (caller zero-fills). */
+int rs_sparse_logits_bwd(const void* a, const void* b, int ab_dtype, const int64_t* idx, int64_t n, int64_t m,
+                         int64_t k, int64_t dim, float scale, const int64_t* key_row, const int64_t* key_col,
+                         const float* g, float* d_a, float* d_b, void* stream);
+
 /* ------------------------------------------------------------- F1: FM / DeepFM */
 
 /* No reference implementation exists: follows deepctr-torch 0.2.9 FM.

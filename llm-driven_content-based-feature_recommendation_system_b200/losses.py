@@ -17,6 +17,7 @@ autocast policy (SURVEY.md 8c invariant 5).
 """
 from __future__ import annotations
 
+import math
 from typing import Optional
 
 import torch
@@ -166,3 +167,83 @@ def efficient_corrected_logq_loss(user_emb, item_emb, pos_item_ids, precomputed_
         flags = L.RS_CE_DIAG_RAW
     return info_nce(user_emb, item_emb, temperature, col_bias=bias, key_a_row=pos_item_ids, key_a_col=pos_item_ids,
                     mask_value=-30000.0 if dtype == torch.float16 else -1e9, flags=flags, dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------------- C4 / C5 (hard negatives)
+def _hnm_common(user_emb, item_tower_emb, target_ids, top_k_percent, hnm_threshold):
+    """Shared head of the hard-negative family (:775-791, :643-668, :707-719): normalise, gather, mine.
+    Mining is fused (no [N,N] cos / item-item matrices): ops.mine_hard_negatives."""
+    n = user_emb.size(0)
+    u = F.normalize(user_emb, p=2, dim=1)
+    v = F.normalize(ops.gather_rows(item_tower_emb, target_ids), p=2, dim=1)
+    k0 = max(1, int((n - 1) * top_k_percent))
+    k0 = min(k0, n)
+    scores, idx, avail = ops.mine_hard_negatives(u, v, target_ids, k0, hnm_threshold)
+    dtype = _operand_dtype(user_emb, item_tower_emb)
+    return u, v, u.to(dtype), v.to(dtype), scores, idx, avail, k0
+
+
+def _avg_sim(scores, k):
+    s = scores[:, :k]
+    fin = torch.isfinite(s)
+    return (torch.where(fin, s, torch.zeros_like(s)).sum() / fin.sum().clamp(min=1)).item()
+
+
+def full_batch_hard_emphasis_loss(user_emb, item_tower_emb, target_ids, log_q_tensor, top_k_percent=0.01,
+                                  hard_margin=0.2, hnm_threshold=0.90, temperature=0.1, lambda_logq=1.0):
+    """tower_code/v1_refine_usertower.py:762-822.  The full [N,N] softmax runs in the fused kernel; the margin
+    on the mined positions is an exact sparse correction of each row's log-sum-exp:
+        lse_i = lse0_i + log1p( (e^{m/T} - 1) * sum_{j in mined_i} exp(s_ij - lse0_i) ).
+    (When a row has fewer than k non-ignored columns the reference's topk returns arbitrary ignored positions;
+    here only real candidates are emphasised.)  Returns (loss, stats) like the reference (one host sync for
+    the stats' .item())."""
+    u, v, u16, v16, scores, idx, avail, k = _hnm_common(user_emb, item_tower_emb, target_ids, top_k_percent,
+                                                        hnm_threshold)
+    scale = 1.0 / temperature
+    bias = (log_q_tensor[target_ids] * lambda_logq) if lambda_logq > 0.0 else None
+    lse0, diag, _, _ = fused_softmax_stats(u16, v16, scale, col_bias=bias, key_a_row=target_ids,
+                                           key_a_col=target_ids, mask_value=NEG_INF, dtype=u16.dtype)
+    s_m = ops.sparse_logits(u16, v16, idx, scale, bias, target_ids, target_ids)
+    corr = torch.log1p(math.expm1(hard_margin / temperature) * torch.exp(s_m - lse0.unsqueeze(1)).sum(dim=1))
+    loss = (lse0 + corr - diag).mean()
+    return loss, {"avg_hn_similarity": _avg_sim(scores, k), "num_hard": k}
+
+
+def inbatch_hnm_corrected_loss_with_stats(user_emb, item_tower_emb, target_ids, log_q_tensor, top_k_percent=0.01,
+                                          hnm_threshold=0.90, temperature=0.1, lambda_logq=0.7, lambda_cl=0.2):
+    """tower_code/v1_refine_usertower.py:632-692: CE over [positive, top-k mined negatives]; k is capped by the
+    smallest number of non-ignored columns over the rows (:665-666, a host sync in the reference too)."""
+    n = user_emb.size(0)
+    u, v, u16, v16, scores, idx, avail, k0 = _hnm_common(user_emb, item_tower_emb, target_ids, top_k_percent,
+                                                         hnm_threshold)
+    k = max(1, min(int((n - 1) * top_k_percent), int(avail.min().item())))
+    scale = 1.0 / temperature
+    bias = (log_q_tensor[target_ids] * lambda_logq) if lambda_logq > 0.0 else None
+    cols = torch.cat([torch.arange(n, device=idx.device).unsqueeze(1), idx[:, :k]], dim=1)
+    final = ops.sparse_logits(u16, v16, cols, scale, bias)
+    loss = F.cross_entropy(final, torch.zeros(n, dtype=torch.long, device=final.device))
+    return loss, {"avg_hn_similarity": _avg_sim(scores, k), "num_active_hard_negs": k}
+
+
+def inbatch_mixed_hnm_loss_with_stats(user_emb, item_tower_emb, target_ids, log_q_tensor, top_k_percent=0.01,
+                                      random_sample_size=100, hnm_threshold=0.90, temperature=0.1, lambda_logq=0.7,
+                                      random_indices=None):
+    """tower_code/v1_refine_usertower.py:695-757: hard (top-k) + random negatives.  `random_indices` may be
+    passed for reproducibility; by default they are drawn like the reference does (:722)."""
+    n = user_emb.size(0)
+    u, v, u16, v16, scores, idx, avail, k = _hnm_common(user_emb, item_tower_emb, target_ids, top_k_percent,
+                                                        hnm_threshold)
+    if random_indices is None:
+        random_indices = torch.randint(0, n, (n, random_sample_size), device=user_emb.device)
+    scale = 1.0 / temperature
+    bias = (log_q_tensor[target_ids] * lambda_logq) if lambda_logq > 0.0 else None
+    cols = torch.cat([torch.arange(n, device=idx.device).unsqueeze(1), idx, random_indices], dim=1)
+    logits = ops.sparse_logits(u16, v16, cols, scale, bias)
+    with torch.no_grad():      # ignore mask of the random picks: same item, or item-item cosine above the threshold
+        vv = torch.ops.rs.sparse_logits(v.detach().float(), v.detach().float(), random_indices, 1.0, None, None, None)
+        rows = torch.arange(n, device=idx.device).unsqueeze(1)
+        ign = (target_ids[random_indices] == target_ids.unsqueeze(1)) | ((vv > hnm_threshold) & (random_indices != rows))
+    rnd = logits[:, 1 + k:].masked_fill(ign, -1e9)
+    final = torch.cat([logits[:, :1 + k], rnd], dim=1)
+    loss = F.cross_entropy(final, torch.zeros(n, dtype=torch.long, device=final.device))
+    return loss, {"avg_hn_similarity": _avg_sim(scores, k), "num_hard": k, "num_random": random_indices.shape[1]}

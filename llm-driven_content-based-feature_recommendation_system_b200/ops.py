@@ -413,6 +413,70 @@ def _(ids, offsets, emb, d_fm, d_concat, want_lin):
     return torch.empty_like(emb), emb.new_empty(emb.shape[0] if want_lin else 0)
 
 
+@torch.library.custom_op("rs::mine_hard_negatives", mutates_args=())
+def mine_hard_negatives_op(u: Tensor, v: Tensor, key: Tensor, k: int, hnm_threshold: float) -> List[Tensor]:
+    """[scores[n,k], ids[n,k] (-1 padded), avail[n] int32] -- no gradient (the reference mines under no_grad)."""
+    L.require_cuda(u, v, key)
+    u, v, key = _f32(u, "u"), _f32(v, "v"), _ids(key)
+    n, dim = u.shape
+    ids = torch.empty(n, k, dtype=torch.int64, device=u.device)
+    scores = torch.empty(n, k, dtype=torch.float32, device=u.device)
+    avail = torch.empty(n, dtype=torch.int32, device=u.device)
+    ws = L.workspace(_lib.rs_mine_workspace_bytes(n, dim, k), u.device)
+    L.check(_lib.rs_mine_hard_negatives(L.ptr(u), L.ptr(v), L.ptr(key), n, dim, k, hnm_threshold, L.ptr(ids),
+                                        L.ptr(scores), L.ptr(avail), L.ptr(ws), ws.numel(), L.stream()),
+            "rs_mine_hard_negatives")
+    return [scores, ids, avail]
+
+
+@mine_hard_negatives_op.register_fake
+def _(u, v, key, k, hnm_threshold):
+    n = u.shape[0]
+    return [u.new_empty(n, k), u.new_empty(n, k, dtype=torch.int64), u.new_empty(n, dtype=torch.int32)]
+
+
+@torch.library.custom_op("rs::sparse_logits", mutates_args=())
+def sparse_logits_op(a: Tensor, b: Tensor, idx: Tensor, scale: float, bias: Optional[Tensor],
+                     key_row: Optional[Tensor], key_col: Optional[Tensor]) -> Tensor:
+    L.require_cuda(a, b, idx)
+    a, b, idx = _c(a), _c(b), _ids(idx)
+    n, dim = a.shape
+    k = idx.shape[1]
+    out = torch.empty(n, k, dtype=torch.float32, device=a.device)
+    bias_ = None if bias is None else _f32(bias, "bias")
+    kr = None if key_row is None else _ids(key_row)
+    kc = None if key_col is None else _ids(key_col)
+    L.check(_lib.rs_sparse_logits_fwd(L.ptr(a), L.ptr(b), L.dt(a), L.ptr(idx), n, b.shape[0], k, dim, scale,
+                                      L.ptr(bias_), L.ptr(kr), L.ptr(kc), L.ptr(out), L.stream()),
+            "rs_sparse_logits_fwd")
+    return out
+
+
+@sparse_logits_op.register_fake
+def _(a, b, idx, scale, bias, key_row, key_col):
+    return a.new_empty(a.shape[0], idx.shape[1], dtype=torch.float32)
+
+
+@torch.library.custom_op("rs::sparse_logits_bwd", mutates_args=())
+def sparse_logits_bwd_op(a: Tensor, b: Tensor, idx: Tensor, scale: float, key_row: Optional[Tensor],
+                         key_col: Optional[Tensor], g: Tensor) -> List[Tensor]:
+    a, b, idx = _c(a), _c(b), _ids(idx)
+    n, dim = a.shape
+    d_a = torch.empty(n, dim, dtype=torch.float32, device=a.device)
+    d_b = torch.zeros(b.shape[0], dim, dtype=torch.float32, device=a.device)
+    kr = None if key_row is None else _ids(key_row)
+    kc = None if key_col is None else _ids(key_col)
+    L.check(_lib.rs_sparse_logits_bwd(L.ptr(a), L.ptr(b), L.dt(a), L.ptr(idx), n, b.shape[0], idx.shape[1], dim,
+                                      scale, L.ptr(kr), L.ptr(kc), L.ptr(_f32(g, "g")), L.ptr(d_a), L.ptr(d_b),
+                                      L.stream()), "rs_sparse_logits_bwd")
+    return [d_a, d_b]
+
+
+@sparse_logits_bwd_op.register_fake
+def _(a, b, idx, scale, key_row, key_col, g):
+    return [a.new_empty(a.shape, dtype=torch.float32), b.new_empty(b.shape, dtype=torch.float32)]
+
+
 # ---- fused in-batch softmax -------------------------------------------------------------------
 def _ce_problem(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags):
     p = L.CEProblem()
@@ -647,3 +711,31 @@ def fm_interaction(ids, offsets, emb, lin=None, want_concat=True, concat_dtype=N
 def retrieve_topk(user_emb: Tensor, item_emb: Tensor, k: int, mask_index0: bool = False):
     """R1: topk(user_emb @ item_emb.T, k) -> (scores, ids); score desc, ties by ascending id."""
     return torch.ops.rs.retrieve_topk(user_emb.float(), item_emb.float(), k, mask_index0)
+
+
+class _SparseLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, idx, scale, bias, key_row, key_col):
+        ctx.save_for_backward(a, b, idx, key_row, key_col)
+        ctx.scale = scale
+        return torch.ops.rs.sparse_logits(a, b, idx, scale, bias, key_row, key_col)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, idx, key_row, key_col = ctx.saved_tensors
+        d_a, d_b = torch.ops.rs.sparse_logits_bwd(a, b, idx, ctx.scale, key_row, key_col, g.float().contiguous())
+        return d_a.to(a.dtype), d_b.to(b.dtype), None, None, None, None, None
+
+
+def sparse_logits(a, b, idx, scale, bias=None, key_row=None, key_col=None):
+    """out[i,c] = scale*<a_i, b_idx[i,c]> - bias[idx[i,c]]  (-inf for idx < 0 or equal keys); differentiable in a, b."""
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    return _SparseLogits.apply(a, b, idx, float(scale), bias, key_row, key_col)
+
+
+def mine_hard_negatives(u, v, key, k, hnm_threshold):
+    """(scores, ids, avail): per-row top-k of <u_i, v_j> over non-ignored columns (C4/C5 mining, no gradient)."""
+    with torch.no_grad():
+        return torch.ops.rs.mine_hard_negatives(u.detach().float(), v.detach().float(), key, int(k),
+                                                float(hnm_threshold))

@@ -215,3 +215,76 @@ def test_deepfm_full_size(rs):
     torch.testing.assert_close(y[:512].double().cpu(), ofm.fm_pairwise(x) + lin, rtol=1e-4, atol=1e-5)
     F.binary_cross_entropy(p, torch.full_like(p, 0.25)).backward()
     assert torch.isfinite(m.fm.embedding.grad).all() and m.fm.embedding.grad.abs().sum() > 0
+
+
+# ------------------------------------------------------------------------------------------ C4 / C5 hard negatives
+def test_mining_vs_oracle(rs):
+    g = torch.Generator().manual_seed(12)
+    for N, V, k in ((96, 50, 4), (1000, 400, 9), (3000, 100000, 29), (700, 30, 700 // 10)):
+        table = F.normalize(torch.randn(V, 128, generator=g), dim=1)
+        table[V // 2] = F.normalize(table[V // 2 - 1] + 0.05 * torch.randn(128, generator=g), dim=0)   # a too-similar pair
+        tgt = torch.randint(0, V, (N,), generator=g)
+        U = F.normalize(torch.randn(N, 128, generator=g) + table[tgt], dim=1)
+        v = table[tgt]
+        cos = U @ v.T
+        same = tgt.view(-1, 1) == tgt.view(1, -1)
+        sim = ((v @ v.T) > 0.9) & ~torch.eye(N, dtype=torch.bool)
+        ign = same | sim
+        want_s, want_i = torch.topk(cos.masked_fill(ign, float("-inf")), k, dim=1)
+        sc, ids, avail = rs.ops.mine_hard_negatives(U.to(DEV), v.to(DEV), tgt.to(DEV), k, 0.9)
+        assert torch.equal(avail.cpu().long(), (~ign).sum(1))
+        fin = torch.isfinite(want_s)
+        torch.testing.assert_close(sc.cpu()[fin], want_s[fin], rtol=0, atol=3e-6)
+        assert (ids.cpu()[~fin] == -1).all()
+        # every returned id is a legal (non-ignored) column with the score we report
+        ii = ids.cpu().clamp(min=0)
+        assert not torch.gather(ign, 1, ii)[fin].any()
+        torch.testing.assert_close(torch.gather(cos, 1, ii)[fin], want_s[fin], rtol=0, atol=3e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_c4_c5_hnm_vs_reference(rs, lg, dtype):
+    d = lambda k: lg[k].to(DEV)
+
+    def run(fn, *a, **k):
+        old = rs.losses.COMPUTE_DTYPE
+        rs.losses.COMPUTE_DTYPE = dtype
+        try:
+            leaves = [lg["U"].to(DEV).requires_grad_(True), lg["table"].to(DEV).requires_grad_(True)]
+            loss, stats = fn(*leaves, *a, **k)
+            loss.backward()
+            return (loss.detach().cpu(), [x.grad.cpu() for x in leaves]), stats
+        finally:
+            rs.losses.COMPUTE_DTYPE = old
+
+    got, stats = run(rs.full_batch_hard_emphasis_loss, d("tgt"), d("logq"), top_k_percent=0.05, hard_margin=0.01,
+                     hnm_threshold=0.90, temperature=0.15, lambda_logq=1.0)
+    _cmp(got, lg["c4"], dtype)
+    assert stats["num_hard"] == lg["c4"]["stats"]["num_hard"]
+    assert stats["avg_hn_similarity"] == pytest.approx(lg["c4"]["stats"]["avg_hn_similarity"], abs=1e-5)
+    got, stats = run(rs.inbatch_hnm_corrected_loss_with_stats, d("tgt"), d("logq"), top_k_percent=0.05,
+                     hnm_threshold=0.90, temperature=0.1, lambda_logq=0.7)
+    _cmp(got, lg["c5_hnm"], dtype)
+    assert stats["num_active_hard_negs"] == lg["c5_hnm"]["stats"]["num_active_hard_negs"]
+    got, stats = run(rs.inbatch_mixed_hnm_loss_with_stats, d("tgt"), d("logq"), top_k_percent=0.05,
+                     random_indices=d("mixed_random_indices"))
+    _cmp(got, lg["c5_mixed"], dtype)
+
+
+def test_c4_larger_vs_oracle(rs):
+    g = torch.Generator().manual_seed(21)
+    N, V = 3000, 2000
+    table = F.normalize(torch.randn(V, 128, generator=g), dim=1)
+    tgt = torch.randint(0, V, (N,), generator=g)
+    U = F.normalize(torch.randn(N, 128, generator=g) + 1.5 * table[tgt], dim=1)
+    logq = torch.log(torch.rand(V, generator=g) + 1e-6)
+    u, t = U.clone().requires_grad_(True), table.clone().requires_grad_(True)
+    want, wstats = olosses.full_batch_hard_emphasis_loss(u, t, tgt, logq, 0.01, 0.2, 0.9, 0.1, 1.0)
+    want.backward()
+    ug, tg = U.to(DEV).requires_grad_(True), table.to(DEV).requires_grad_(True)
+    got, stats = rs.full_batch_hard_emphasis_loss(ug, tg, tgt.to(DEV), logq.to(DEV), 0.01, 0.2, 0.9, 0.1, 1.0)
+    got.backward()
+    _cmp((got.detach().cpu(), [ug.grad.cpu(), tg.grad.cpu()]), dict(loss=want.detach(), grads=[u.grad, t.grad]),
+         torch.bfloat16)
+    assert stats["num_hard"] == wstats["num_hard"]
+    assert stats["avg_hn_similarity"] == pytest.approx(wstats["avg_hn_similarity"], abs=1e-4)
