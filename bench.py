@@ -241,13 +241,13 @@ def run_ours(args):
 
     # ---- per-kernel pass (rank 0): CUDA events around every C-ABI call, on the launching stream
     kernels, roof = {}, None
+    nprof = 2
+    L.PROFILE = []                     # every rank runs these steps (they contain collectives); rank 0 reports
+    for i in range(nprof):
+        step(resident[i % pool])
+    torch.cuda.synchronize()
+    prof, L.PROFILE = L.PROFILE, None
     if rank == 0:
-        L.PROFILE = []
-        nprof = 2
-        for i in range(nprof):
-            step(resident[i % pool])
-        torch.cuda.synchronize()
-        prof, L.PROFILE = L.PROFILE, None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

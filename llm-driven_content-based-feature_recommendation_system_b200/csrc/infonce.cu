@@ -25,7 +25,8 @@ namespace rs {
 #define CE_BWD_STAGES 3
 #define CE_TILE_BYTES (CE_BN * CE_K * 2)           // 32 KB: two SWIZZLE_128B boxes of [128 rows x 64 cols]
 #define CE_BOX_BYTES (CE_TILE_BYTES / 2)
-#define CE_THREADS 320
+#define CE_NWG 3                                    // epilogue warpgroups (one TMEM accumulator each)
+#define CE_THREADS (64 + 128 * CE_NWG)
 #define CE_LOG2E 1.4426950408889634f
 #define CE_LN2 0.6931471805599453f
 
@@ -153,13 +154,13 @@ struct __align__(16) ColMeta {
 struct CeShared {
   uint64_t full[CE_STAGES], empty[CE_STAGES];
   uint64_t a_full[2], a_empty[2];
-  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t tmem_full[CE_NWG], tmem_empty[CE_NWG];
   uint64_t p_full[2], p_empty[2];          // backward: dS tile in smem ready / consumed by the tensor core
   uint64_t d2_full, d2_empty;              // backward: dS@X accumulator complete / drained
   uint32_t tmem_base;
   uint32_t pad[3];
-  ColMeta meta[2][2];                      // [warpgroup][buffer]
-  float xm[CE_BM], xl[CE_BM], xps[CE_BM], xpc[CE_BM];   // cross-warpgroup combine (forward)
+  ColMeta meta[CE_NWG][2];                 // [warpgroup][buffer]
+  float xm[CE_NWG - 1][CE_BM], xl[CE_NWG - 1][CE_BM], xps[CE_NWG - 1][CE_BM], xpc[CE_NWG - 1][CE_BM];   // combine
 };
 
 struct CeParams {
@@ -197,9 +198,9 @@ __device__ __forceinline__ void ce_setup(CeShared& sh, int warp, const CUtensorM
     for (int i = 0; i < CE_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sh.a_full[i], 1); mbar_init(&sh.a_empty[i], 1);
-      mbar_init(&sh.tmem_full[i], 1); mbar_init(&sh.tmem_empty[i], 128);
       mbar_init(&sh.p_full[i], 128); mbar_init(&sh.p_empty[i], 1);
     }
+    for (int i = 0; i < CE_NWG; ++i) { mbar_init(&sh.tmem_full[i], 1); mbar_init(&sh.tmem_empty[i], 128); }
     mbar_init(&sh.d2_full, 1);
     mbar_init(&sh.d2_empty, 256);
     fence_barrier_init();
@@ -237,7 +238,7 @@ __device__ __forceinline__ void producer_role(const CeParams& p, CeShared& sh, u
 template <int NSTAGE>
 __device__ __forceinline__ void issue_s(const CeParams& p, CeShared& sh, uint8_t* sB, uint64_t adesc,
                                         uint32_t tmem_base, uint32_t it) {
-  const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1, g = it & 1, ng = it >> 1;
+  const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1, g = it % CE_NWG, ng = it / CE_NWG;
   mbar_wait(&sh.tmem_empty[g], (ng & 1) ^ 1);
   mbar_wait(&sh.full[s], ph);
   tc_fence_after();
@@ -362,16 +363,23 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t meta
   float v[32];
   unsigned posbits, diagbit;
   logits32<MODE, EDGE, USE_KB, false>(r, v, posbits, diagbit, meta, cbase, rc, p, col0);
-  float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]);
+  // four independent chains for the max and for the sum: with only two epilogue warps per scheduler the
+  // instruction-level parallelism inside a warp is what hides the ALU / MUFU latencies
+  float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
 #pragma unroll
-  for (int j = 4; j < 32; j += 2) { c0 = fmaxf(c0, v[j]); c1 = fmaxf(c1, v[j + 1]); }
-  const float m_new = fmaxf(rc.m, fmaxf(c0, c1));
+  for (int j = 8; j < 32; j += 8) {
+    c0 = fmaxf(c0, fmaxf(v[j], v[j + 1])); c1 = fmaxf(c1, fmaxf(v[j + 2], v[j + 3]));
+    c2 = fmaxf(c2, fmaxf(v[j + 4], v[j + 5])); c3 = fmaxf(c3, fmaxf(v[j + 6], v[j + 7]));
+  }
+  const float m_new = fmaxf(rc.m, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
   const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
   rc.l *= ex2(rc.m - m_use);
-  float a0 = 0.f, a1 = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) { a0 += ex2(v[j] - m_use); a1 += ex2(v[j + 1] - m_use); }
-  rc.l += a0 + a1;
+  for (int j = 0; j < 32; j += 4) {
+    a0 += ex2(v[j] - m_use); a1 += ex2(v[j + 1] - m_use); a2 += ex2(v[j + 2] - m_use); a3 += ex2(v[j + 3] - m_use);
+  }
+  rc.l += (a0 + a1) + (a2 + a3);
   rc.m = m_new;
   if (MODE == MODE_SUPCON) {
 #pragma unroll
@@ -438,23 +446,17 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t meta
   }
 }
 
-// walk the four 32-column chunks of accumulator `g` with the TMEM load of chunk c+1 in flight while chunk c
-// is processed; F(r, cbase) consumes one chunk
+// walk the four 32-column chunks of one accumulator; F(r, cbase) consumes one chunk.  (Three epilogue warps per
+// scheduler hide the TMEM load latency; a register double buffer would push the kernel past 128 registers.)
 template <class F>
 __device__ __forceinline__ void for_chunks(uint32_t tmem_tile, F&& f) {
-  uint32_t ra[32], rb[32];
-  tmem_ld32(tmem_tile, ra);
-  tmem_ld_wait();
-  pin32(ra);
 #pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    tmem_ld32(tmem_tile + (uint32_t)(h * 64 + 32), rb);
-    f(ra, h * 64);
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t r[32];
+    tmem_ld32(tmem_tile + (uint32_t)(ch * 32), r);
     tmem_ld_wait();
-    pin32(rb);
-    if (h == 0) tmem_ld32(tmem_tile + 64u, ra);
-    f(rb, h * 64 + 32);
-    if (h == 0) { tmem_ld_wait(); pin32(ra); }
+    pin32(r);
+    f(r, ch * 32);
   }
 }
 
@@ -488,7 +490,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   uint8_t* sB = base + 2 * CE_TILE_BYTES;
   CeShared& sh = *reinterpret_cast<CeShared*>(base + (2 + CE_STAGES) * CE_TILE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ce_setup(sh, warp, &mapA, &mapB, 256);
+  ce_setup(sh, warp, &mapA, &mapB, 512);
   const uint32_t tmem_base = sh.tmem_base;
   const int n_items = p.row_blocks * p.nsplit;
 
@@ -530,7 +532,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       rc.m = -INFINITY; rc.l = 0.f; rc.ps = 0.f; rc.pc = 0.f;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;   // diag col span
       for (int ct = lo; ct < hi; ++ct, ++it) {
-        if ((int)(it & 1) != wg) continue;
+        if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
         stage_cols<false>(p, cm, ct, t128, 1.0f);
         named_bar_sync(1 + wg, 128);
@@ -549,25 +551,32 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         ++nuse;
       }
       // ---- combine the two warpgroups' running (max, sum) and write this split's partial
-      if (wg == 1) { sh.xm[rloc] = rc.m; sh.xl[rloc] = rc.l; sh.xps[rloc] = rc.ps; sh.xpc[rloc] = rc.pc; }
-      named_bar_sync(3, 256);
+      if (wg > 0) { sh.xm[wg - 1][rloc] = rc.m; sh.xl[wg - 1][rloc] = rc.l; sh.xps[wg - 1][rloc] = rc.ps; sh.xpc[wg - 1][rloc] = rc.pc; }
+      named_bar_sync(1 + CE_NWG, 128 * CE_NWG);
       if (wg == 0 && row_ok) {
-        const float m1 = sh.xm[rloc], l1 = sh.xl[rloc];
-        const float mm = fmaxf(rc.m, m1);
+        float mm = rc.m;
+#pragma unroll
+        for (int w = 0; w < CE_NWG - 1; ++w) mm = fmaxf(mm, sh.xm[w][rloc]);
         const float mu = (mm == -INFINITY) ? 0.f : mm;
-        const float ll = rc.l * ex2(rc.m - mu) + l1 * ex2(m1 - mu);
+        float ll = rc.l * ex2(rc.m - mu), ps = rc.ps, pc = rc.pc;
+#pragma unroll
+        for (int w = 0; w < CE_NWG - 1; ++w) {
+          ll += sh.xl[w][rloc] * ex2(sh.xm[w][rloc] - mu);
+          ps += sh.xps[w][rloc];
+          pc += sh.xpc[w][rloc];
+        }
         const int64_t o = (int64_t)sp * p.M + row;
         p.part_m[o] = mm;
         p.part_l[o] = ll;
-        if (MODE == MODE_SUPCON) { p.part_ps[o] = rc.ps + sh.xps[rloc]; p.part_pc[o] = rc.pc + sh.xpc[rloc]; }
+        if (MODE == MODE_SUPCON) { p.part_ps[o] = ps; p.part_pc[o] = pc; }
       }
-      named_bar_sync(3, 256);
+      named_bar_sync(1 + CE_NWG, 128 * CE_NWG);
     }
   }
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 __global__ void ce_fwd_finalize(int64_t M, int nsplit, const float* __restrict__ part_m,
@@ -621,10 +630,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         mbar_wait(&sh.d2_empty, (item_n & 1) ^ 1);      // previous item's dS@X accumulator has been drained
         tc_fence_after();
         issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, it0);
+        if (nt > 1) issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, it0 + 1);
         for (uint32_t t = it0; t < it0 + nt; ++t) {
-          // S(t+1) is issued before dS(t)@X so that the other epilogue warpgroup has work meanwhile
-          if (t + 1 < it0 + nt) issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, t + 1);
-          const uint32_t s = t % CE_BWD_STAGES, g = t & 1, ng = t >> 1;
+          // S(t+2) is issued before dS(t)@X so that the other epilogue warpgroups have work meanwhile
+          if (t + 2 < it0 + nt) issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, t + 2);
+          const uint32_t s = t % CE_BWD_STAGES, g = t & 1, ng = t >> 1;      // dS buffers alternate by tile
           mbar_wait(&sh.p_full[g], ng & 1);
           tc_fence_after();
           const uint64_t pdesc = desc_kmajor(smem_u32(sP + g * CE_TILE_BYTES));
@@ -633,7 +643,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           for (int k = 0; k < CE_BN / 16; ++k) {
             const uint64_t aoff = (uint64_t)(((k >> 2) * CE_BOX_BYTES + (k & 3) * 32) >> 4);   // 16 columns c of dS
             const uint64_t boff = (uint64_t)((k * 16 * 128) >> 4);                              // 16 rows c of X
-            umma_f16(tmem_base + 2 * CE_BN, pdesc + aoff, xdesc + boff, p.idesc_g, (t > it0 || k > 0) ? 1u : 0u);
+            umma_f16(tmem_base + CE_NWG * CE_BN, pdesc + aoff, xdesc + boff, p.idesc_g, (t > it0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&sh.p_empty[g]);
           umma_commit(&sh.empty[s]);
@@ -678,7 +688,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       rc.jd = row + p.diag_offset;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;
       for (int ct = lo; ct < hi; ++ct, ++it) {
-        if ((int)(it & 1) != wg) continue;
+        if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
         stage_cols<TRANSPOSED>(p, cm, ct, t128, cs);
         named_bar_sync(1 + wg, 128);
@@ -686,10 +696,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int64_t c0 = (int64_t)ct * CE_BN;
         const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
         const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
+        const uint32_t pb = it & 1;                     // dS buffers alternate by tile
         mbar_wait(&sh.tmem_full[wg], nuse & 1);
-        mbar_wait(&sh.p_empty[wg], (nuse & 1) ^ 1);     // the tensor core is done with this warpgroup's dS buffer
+        mbar_wait(&sh.p_empty[pb], ((it >> 1) & 1) ^ 1);   // the tensor core is done with this dS buffer
         tc_fence_after();
-        uint8_t* prow = sP + wg * CE_TILE_BYTES + rloc * 128;
+        uint8_t* prow = sP + pb * CE_TILE_BYTES + rloc * 128;
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
         if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, true, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
         else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
@@ -697,10 +708,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[wg]);
         fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
-        mbar_arrive(&sh.p_full[wg]);
+        mbar_arrive(&sh.p_full[pb]);
         ++nuse;
       }
       // ---- drain the dS@X accumulator: warpgroup wg takes columns [64*wg, 64*wg+64)
+      if (wg >= 2) continue;
       mbar_wait(&sh.d2_full, item_n & 1);
       tc_fence_after();
       const float osc = p.out_scale * inv_cs;
@@ -708,7 +720,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       for (int h = 0; h < 2; ++h) {
         uint32_t r[32];
         const int d0 = wg * 64 + h * 32;
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * CE_BN + d0), r);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(CE_NWG * CE_BN + d0), r);
         tmem_ld_wait();
         pin32(r);
         if (row_ok) {

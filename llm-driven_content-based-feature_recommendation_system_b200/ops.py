@@ -60,9 +60,12 @@ _sort_cache: "collections.OrderedDict[tuple, _SortEntry]" = collections.OrderedD
 def sorted_ids(ids: Tensor, rows: int, clamp_max: int = -1) -> Tuple[Tensor, Tensor]:
     """Stable (id, position) sort, cached per ids tensor (the two dropout views of a step and the
     forward/backward of one table share the same ids)."""
+    # keyed by storage address + version counter (custom-op dispatch hands us fresh wrappers of the same
+    # tensor, so object identity is useless); the entry keeps a reference, so the address cannot be recycled
     key = (ids.data_ptr(), ids._version, ids.numel(), rows, clamp_max)
     e = _sort_cache.get(key)
-    if e is not None and e.ids is ids:
+    if e is not None:
+        _sort_cache.move_to_end(key)
         return e.skeys, e.spos
     n = ids.numel()
     sk = torch.empty(n, dtype=torch.int32, device=ids.device)
@@ -72,7 +75,7 @@ def sorted_ids(ids: Tensor, rows: int, clamp_max: int = -1) -> Tuple[Tensor, Ten
     L.check(_lib.rs_sort_ids(L.ptr(ids), n, rows, clamp_max, L.ptr(sk), L.ptr(sp), L.ptr(ws), ws.numel(),
                              L.ptr(L.oob_flag(ids.device)), L.stream()), "rs_sort_ids")
     _sort_cache[key] = _SortEntry(ids, ids._version, rows, clamp_max, sk, sp)
-    while len(_sort_cache) > 8:
+    while len(_sort_cache) > 32:
         _sort_cache.popitem(last=False)
     return sk, sp
 
