@@ -142,66 +142,61 @@ __global__ void __launch_bounds__(256) seq_front_fwd_kernel(const void* __restri
 }
 
 // dim == 128 fast path: a warp owns 32 consecutive positions.  The ids of all 32 are fetched with ONE coalesced
-// load per live table and handed round by shuffles; rows are then fetched four positions at a time so that
-// each lane keeps 4 x (base + rows) 128-bit loads in flight (the row address depends on the id: without this
-// the kernel is bound by two serial memory latencies per position, not by bandwidth).
+// load per live table and handed round by shuffles; rows are then fetched SF_UNROLL positions at a time so that
+// each lane keeps SF_UNROLL x (base + NT rows) 128-bit loads in flight (the row address depends on the id:
+// without this the kernel is bound by two serial memory latencies per position, not by bandwidth).
+// NT = number of tables (compile time, so the per-table state is exactly sized and occupancy stays high).
 #define SF_UNROLL 4
-template <int BD, int OD>
-__global__ void __launch_bounds__(256) seq_front_fwd128_kernel(const void* __restrict__ base, SeqFrontParams prm,
-                                                               const float* __restrict__ gates,
-                                                               const float* __restrict__ pos_table, int64_t L,
-                                                               int64_t P, void* __restrict__ out,
-                                                               int* __restrict__ oob) {
+template <int BD, int OD, int NT>
+__global__ void __launch_bounds__(256, 3) seq_front_fwd128_kernel(const void* __restrict__ base, SeqFrontParams prm,
+                                                                  const float* __restrict__ gates,
+                                                                  const float* __restrict__ pos_table, int L,
+                                                                  int64_t P, void* __restrict__ out,
+                                                                  int* __restrict__ oob) {
   constexpr int D = 128;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float g[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) g[t] = __ldg(gates + t);
   for (int64_t pb = warp * 32; pb < P; pb += nwarps * 32) {
     const int64_t mine = pb + lane;
-    int myid[RS_MAX_TABLES];
-    float g[RS_MAX_TABLES];
+    int myid[NT];
 #pragma unroll
-    for (int t = 0; t < RS_MAX_TABLES; ++t) {
+    for (int t = 0; t < NT; ++t) {
       myid[t] = -1;
-      g[t] = (t < prm.n_tables) ? __ldg(gates + t) : 0.f;
-      if (t < prm.n_tables && g[t] != 0.f && mine < P) {
+      if (g[t] != 0.f && mine < P) {                 // a gate that is exactly 0 contributes exactly +0: not read
         const int64_t x = __ldg(prm.ids[t] + mine);
         if (x < 0 || x >= prm.rows[t]) { if (oob) *oob = 1; }
         else myid[t] = (int)x;
       }
     }
     const int cnt = (int)((P - pb) < 32 ? (P - pb) : 32);
+    const int l0 = (int)(pb % L);
     for (int u0 = 0; u0 < cnt; u0 += SF_UNROLL) {
-      float4 acc[SF_UNROLL], pr[SF_UNROLL];
+      float4 acc[SF_UNROLL], row[SF_UNROLL][NT];
+      int id[SF_UNROLL][NT];
 #pragma unroll
-      for (int u = 0; u < SF_UNROLL; ++u) {
+      for (int u = 0; u < SF_UNROLL; ++u) {            // every load of the group is issued before any use
         const int64_t p = pb + u0 + u;
-        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pr[u] = acc[u];
-        if (u0 + u < cnt) {
-          if (base) acc[u] = load4<BD>(base, p * D + 4 * lane);
-          if (pos_table) pr[u] = ldg_f4(pos_table + (p % L) * D + 4 * lane);
+        const bool on = u0 + u < cnt;
+        acc[u] = (on && base) ? load4<BD>(base, p * D + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          id[u][t] = __shfl_sync(0xffffffffu, myid[t], (u0 + u) & 31);
+          if (!on) id[u][t] = -1;
+          if (id[u][t] >= 0) row[u][t] = ldg_f4(prm.tables[t] + (int64_t)id[u][t] * D + 4 * lane);
         }
-      }
-#pragma unroll
-      for (int t = 0; t < RS_MAX_TABLES; ++t) {
-        if (t >= prm.n_tables || g[t] == 0.f) continue;          // warp-uniform
-        float4 row[SF_UNROLL];
-        int id[SF_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SF_UNROLL; ++u) {
-          id[u] = __shfl_sync(0xffffffffu, myid[t], (u0 + u) & 31);
-          if (u0 + u >= cnt) id[u] = -1;
-          if (id[u] >= 0) row[u] = ldg_f4(prm.tables[t] + (int64_t)id[u] * D + 4 * lane);
-        }
-#pragma unroll
-        for (int u = 0; u < SF_UNROLL; ++u)
-          if (id[u] >= 0) acc[u] = mul_add_rn(acc[u], row[u], g[t]);
       }
 #pragma unroll
       for (int u = 0; u < SF_UNROLL; ++u) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          if (id[u][t] >= 0) acc[u] = mul_add_rn(acc[u], row[u][t], g[t]);
         if (u0 + u < cnt) {
-          if (pos_table) acc[u] = add4(acc[u], pr[u]);
+          // the L position rows stay in L1: fetched at the point of use
+          if (pos_table) acc[u] = add4(acc[u], ldg_f4(pos_table + ((l0 + u0 + u) % L) * D + 4 * lane));
           store4<OD>(out, (pb + u0 + u) * D + 4 * lane, acc[u]);
         }
       }
@@ -632,10 +627,12 @@ extern "C" int rs_seq_front_fwd(const void* base, int base_dtype, const int64_t*
   const int grid = grid_for_warps((P + m.rpw - 1) / m.rpw, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (!base) base_dtype = RS_F32;
-  if (dim == 128) {
-    const int grid128 = grid_for_warps((P + 31) / 32, 8, 8);
-    DISPATCH_DT(base_dtype, BD, DISPATCH_DT(out_dtype, OD, (seq_front_fwd128_kernel<BD, OD><<<grid128, 256, 0, st>>>(
-        base, prm, gates, pos_table, L, P, out, oob_flag))));
+  if (dim == 128 && n_tables >= 1 && n_tables <= 3 && L < (1ll << 30)) {
+    const int grid128 = grid_for_warps((P + 31) / 32, 8, 3);
+#define LAUNCH_SF(NT)                                                                                        \
+  DISPATCH_DT(base_dtype, BD, DISPATCH_DT(out_dtype, OD, (seq_front_fwd128_kernel<BD, OD, NT><<<grid128, 256, 0, st>>>( \
+      base, prm, gates, pos_table, (int)L, P, out, oob_flag))))
+    if (n_tables == 1) { LAUNCH_SF(1); } else if (n_tables == 2) { LAUNCH_SF(2); } else { LAUNCH_SF(3); }
     RS_LAUNCH_CHECK();
     return RS_OK;
   }

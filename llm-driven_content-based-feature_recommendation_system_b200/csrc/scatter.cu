@@ -493,17 +493,41 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segment_fixup_kernel(
       const int v = lane + 32 * i;
       acc[i] = v < vecs ? *reinterpret_cast<const float4*>(partR + tile * dim + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int64_t u = tile + 1; u < ntiles; ++u) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int v = lane + 32 * i;
-        if (v < vecs) {
-          const float4 g = *reinterpret_cast<const float4*>(partL + u * dim + 4 * v);
-          acc[i].x += g.x; acc[i].y += g.y; acc[i].z += g.z; acc[i].w += g.w;
-        }
+    // walk the chain 32 tiles at a time: lane j tests whether the segment runs through tile u0+j, a ballot finds
+    // where it ends, then the partial rows are summed in tile order with FX_G independent loads in flight
+    // (a Zipf head item spans >1000 tiles: a one-tile-per-iteration walk is a serial chain of L2 latencies)
+    constexpr int FX_G = NV == 1 ? 8 : (NV == 2 ? 4 : 1);
+    bool more = true;
+    for (int64_t u0 = tile + 1; more && u0 < ntiles; u0 += 32) {
+      const int64_t u = u0 + lane;
+      bool through = false;                        // segment covers tile u entirely AND continues past it
+      if (u < ntiles) {
+        const int64_t u1 = (u + 1) * SEG_TILE;
+        through = (u1 < n) && skeys[u1 - 1] == k && skeys[u1] == k;
       }
-      const int64_t u1 = (u + 1) * SEG_TILE;
-      if (u1 >= n || skeys[u1 - 1] != k || skeys[u1] != k) break;   // the segment ends inside tile u
+      const unsigned bal = __ballot_sync(0xffffffffu, through);
+      const int run = (bal == 0xffffffffu) ? 32 : __ffs(~bal) - 1;   // tiles u0..u0+run-1 pass through; u0+run ends it
+      int last = run < 32 ? run : 31;              // last tile of this batch that contributes a partL piece
+      if (run < 32) more = false;
+      if (u0 + last >= ntiles) last = (int)(ntiles - 1 - u0);
+      for (int j0 = 0; j0 <= last; j0 += FX_G) {
+        float4 gb[FX_G][NV];
+#pragma unroll
+        for (int q = 0; q < FX_G; ++q)
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int v = lane + 32 * i;
+            gb[q][i] = (j0 + q <= last && v < vecs)
+                           ? *reinterpret_cast<const float4*>(partL + (u0 + j0 + q) * dim + 4 * v)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int q = 0; q < FX_G; ++q)
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            acc[i].x += gb[q][i].x; acc[i].y += gb[q][i].y; acc[i].z += gb[q][i].z; acc[i].w += gb[q][i].w;
+          }
+      }
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
