@@ -113,39 +113,43 @@ def _load_synthetic():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """One `nvidia-smi -lms 200` child for the whole timed region (no per-sample process spawn: the step is
+    launch-heavy and must not compete with a forking Python thread)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
-
-    def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._loop, daemon=True)
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.25)                      # make sure at least one sample falls after the last step
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        self.rows = [[x.strip() for x in line.split(",")] for line in out.splitlines() if line.strip()]
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        pw = [float(r[6]) for r in self.rows if len(r) > 6 and r[6].replace(".", "").isdigit()]
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    reasons=reasons, samples=len(sm), power_w_max=max(pw) if pw else None)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -203,8 +207,10 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for i in range(n):
             fn(i)
+        timed.host_ms = (time.perf_counter() - h0) * 1e3 / max(n, 1)     # time to ENQUEUE a step (launch-bound if ~= ms)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -220,6 +226,7 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         ms = timed(args.steps, lambda i: last.__setitem__("loss", step(resident[i % pool])))
     launches = lib.rs_launch_count() - launches0
+    host_ms = timed.host_ms
     total, main, cl = [float(x) for x in last["loss"]]
     assert all(map(lambda v: v == v and abs(v) < 1e6, (total, main, cl))), f"non-finite loss {total, main, cl}"
     value = world * B * args.steps / (ms * 1e-3)
@@ -305,7 +312,7 @@ def run_ours(args):
                                 loss_scope=args.loss_scope, loss_rows=n_valid if args.loss_scope == "all" else B,
                                 parallelism=f"dp{world} (replicated tables, gradients all-reduced)" if world > 1 else "1 GPU",
                                 l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
-                    e2e=e2e, gpu_launches=int(launches), clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
+                    e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
                     kernels=kernels, loss=dict(total=total, main=main, cl=cl))
         print(json.dumps(line))
     if world > 1:
