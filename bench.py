@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--seq-len", type=int, default=50)
     ap.add_argument("--loss-scope", default="all", choices=["all", "last"])
+    ap.add_argument("--columns", default="unique", choices=["unique", "catalog", "batch"],
+                    help="column enumeration of the main in-batch softmax (same loss): distinct batch items with "
+                         "multiplicities / whole catalogue / one column per row as the reference materialises it")
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="only the resident-input timed loop (for ncu runs)")
@@ -193,10 +196,13 @@ def run_ours(args):
     resident = [rs.train.prepare_batch(hb, dev) for hb in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     n_valid = int(host[0]["valid_index"].numel())
+    n_cols = {"unique": int(host[0]["col_item_ids"].numel()), "catalog": syn.N_ITEMS + 1}.get(args.columns, n_valid)
+    if args.loss_scope != "all":
+        n_cols = B if args.columns != "catalog" else n_cols
 
     def step(b):
         return rs.train.two_tower_step(model, item, b, lookup, opt, loss_scope=args.loss_scope,
-                                       amp_dtype=torch.bfloat16, grad_hook=sync_grads)
+                                       amp_dtype=torch.bfloat16, grad_hook=sync_grads, columns=args.columns)
 
     def barrier():
         if world > 1:
@@ -310,6 +316,7 @@ def run_ours(args):
                     config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B,
                                 global_batch=B * world, seq_len=SL, d_model=128, n_items=syn.N_ITEMS,
                                 loss_scope=args.loss_scope, loss_rows=n_valid if args.loss_scope == "all" else B,
+                                loss_columns=args.columns, loss_cols=n_cols,
                                 parallelism=f"dp{world} (replicated tables, gradients all-reduced)" if world > 1 else "1 GPU",
                                 l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
                     e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,

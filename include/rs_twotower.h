@@ -185,6 +185,9 @@ int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, i
  *   RS_CE_DIAG_MASK: the diagonal itself is masked (SupCon, v1_refine_usertower.py:613)
  *   RS_CE_DIAG_RAW:  the diagonal logit skips col_bias (positive recovery, mined_inference.py:774-775)
  *   RS_CE_SUPCON:    additionally pos_sum[i] = sum_j [key_a equal, key != 0, j != diag] S_ij and pos_cnt[i]
+ *   RS_CE_NO_DIAG:   no column is a label (diag_offset ignored, diag[] not written): the columns are a set of
+ *                    DISTINCT items with multiplicities folded into col_bias (bias_c - log m_c) and the row's own
+ *                    item masked through key_a; the caller adds the positive back (see losses.logq_infonce_columns)
  * Keys are compared on their low 32 bits: ids must lie in [0, 2^32) (item ids and batch-row user ids do).
  * Outputs per row: lse[i] = logsumexp_j S_ij, diag[i] = S_{i,i+diag_offset}.
  * A,B are bf16 or fp16 [M,K] / [N,K] row-major, K == 128 (tcgen05 kind::f16, fp32 accumulate in TMEM).
@@ -193,6 +196,7 @@ int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, i
 #define RS_CE_DIAG_MASK 1
 #define RS_CE_DIAG_RAW 2
 #define RS_CE_SUPCON 4
+#define RS_CE_NO_DIAG 8
 typedef struct {
   const void* a;            /* [M,K] */
   const void* b;            /* [N,K] */

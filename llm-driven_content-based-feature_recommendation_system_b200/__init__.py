@@ -14,6 +14,7 @@ from .ops import (gather_rows, seq_front, static_front, normalized_rows, masked_
 from . import losses, towers, fm, retrieval, train, sharded, synthetic     # noqa: E402
 from .losses import (simcse_loss, inbatch_corrected_logq_loss, inbatch_logq_loss_no_user, duorec_loss_refined,  # noqa
                      logq_correction_loss, efficient_corrected_logq_loss, logq_infonce_rows, info_nce,
+                     logq_infonce_columns, item_columns,
                      full_batch_hard_emphasis_loss, inbatch_hnm_corrected_loss_with_stats,
                      inbatch_mixed_hnm_loss_with_stats)
 from .towers import (SASRecUserTower, SASRecItemTower, HybridItemTower, OptimizedItemTower, SimCSEModelWrapper,  # noqa

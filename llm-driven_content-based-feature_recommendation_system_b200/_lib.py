@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librs_twotower.so")
 
 RS_F32, RS_F16, RS_BF16 = 0, 1, 2
-RS_CE_DIAG_MASK, RS_CE_DIAG_RAW, RS_CE_SUPCON = 1, 2, 4
+RS_CE_DIAG_MASK, RS_CE_DIAG_RAW, RS_CE_SUPCON, RS_CE_NO_DIAG = 1, 2, 4, 8
 RS_MAX_TABLES = 8
 
 _DT = {torch.float32: RS_F32, torch.float16: RS_F16, torch.bfloat16: RS_BF16}

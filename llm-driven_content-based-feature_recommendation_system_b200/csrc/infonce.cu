@@ -862,6 +862,11 @@ extern "C" size_t rs_ce_workspace_bytes(const rs_ce_problem* p) {
   return al256(m) + 512;        // + one scalar (max |w|) behind the partial buffers
 }
 
+// RS_CE_NO_DIAG: park the label far outside the matrix (no tile is a diagonal tile, nothing is exempt from the masks)
+static inline int64_t ce_diag_offset(const rs_ce_problem* p) {
+  return (p->flags & RS_CE_NO_DIAG) ? ((int64_t)1 << 40) : p->diag_offset;
+}
+
 static void fill_common(CeParams& k, const rs_ce_problem* p, const CePlan& pl) {
   k.scale2 = p->scale * CE_LOG2E;
   k.mask2 = p->mask_value * CE_LOG2E;
@@ -893,7 +898,7 @@ extern "C" int rs_ce_fwd(const rs_ce_problem* p, float* lse, float* diag, float*
   k.col_bias = p->col_bias;
   k.key_a_row = p->key_a_row; k.key_a_col = p->key_a_col;
   k.key_b_row = p->key_b_row; k.key_b_col = p->key_b_col;
-  k.diag_offset = p->diag_offset;
+  k.diag_offset = ce_diag_offset(p);
   char* ws = (char*)workspace;
   k.part_m = (float*)ws; k.part_l = (float*)(ws + pb); k.part_ps = (float*)(ws + 2 * pb); k.part_pc = (float*)(ws + 3 * pb);
   k.diag_out = diag;
@@ -956,7 +961,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.col_bias = p->col_bias;
     k.key_a_row = p->key_a_row; k.key_a_col = p->key_a_col;
     k.key_b_row = p->key_b_row; k.key_b_col = p->key_b_col;
-    k.diag_offset = p->diag_offset;
+    k.diag_offset = ce_diag_offset(p);
     k.lse = lse; k.w_lse = w_lse; k.w_diag = w_diag; k.w_pos = w_pos;
     k.part_out = (float*)workspace;
     k.out_scale = p->scale;
@@ -974,7 +979,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.row_bias = p->col_bias;
     k.key_a_row = p->key_a_col; k.key_a_col = p->key_a_row;
     k.key_b_row = p->key_b_col; k.key_b_col = p->key_b_row;
-    k.diag_offset = -p->diag_offset;
+    k.diag_offset = -ce_diag_offset(p);
     k.lse = lse; k.w_lse = w_lse; k.w_diag = w_diag; k.w_pos = w_pos;
     k.part_out = (float*)workspace;
     k.out_scale = p->scale;

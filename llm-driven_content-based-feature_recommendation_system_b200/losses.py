@@ -120,6 +120,52 @@ def logq_infonce_rows(user_emb: Tensor, item_rows: Tensor, target_ids: Tensor, u
                     diag_offset=diag_offset, mask_value=NEG_INF)
 
 
+def item_columns(target_ids: Tensor, num_items: Optional[int] = None):
+    """Column multiset of a batch of targets for `logq_infonce_columns` (pure index arithmetic; run it where the
+    ids live -- the loader does it on the host so that the data-dependent column count is known without a
+    device synchronisation).  Returns (col_item_ids[U], col_counts[U], pos_col[N]).
+      num_items None : the DISTINCT targets of the batch (U = number of distinct items)
+      num_items int  : every item of the catalogue (U = num_items, static; absent items get count 0)"""
+    if num_items is None:
+        ids, pos_col, counts = torch.unique(target_ids, return_inverse=True, return_counts=True)
+        return ids, counts, pos_col
+    counts = torch.bincount(target_ids, minlength=num_items)
+    return torch.arange(num_items, device=target_ids.device), counts, target_ids
+
+
+def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tensor, col_counts: Tensor,
+                         target_ids: Tensor, pos_col: Tensor, own_cols: Optional[Tensor], log_q_tensor: Tensor,
+                         temperature: float = 0.1, lambda_logq: float = 1.0) -> Tensor:
+    """C2 (tower_code/v1_refine_usertower.py:826-861) over the DISTINCT items of the batch.  In-batch columns with
+    the same target item share the item row and the logQ, hence the logit, so the reference's [N, N] softmax
+    equals an [N, U] softmax over distinct items with the batch multiplicities m_c folded into the column bias:
+
+        Z_i = e^{s_i,t_i}                                  (the label; every other copy of t_i is masked, :846)
+            + sum_{c != t_i} m_c e^{s_ic}                  (fused tensor-core pass, bias_c = lambda logq_c - log m_c)
+            - sum_{j in user(i), t_j != t_i} e^{s_i,t_j}   (same-user columns are masked too, :848; <= L per row)
+
+    U is ~5x smaller than N on an H&M-shaped batch (Zipf targets), and it is bounded by the catalogue size
+    however many ranks contribute columns.  `col_counts` may hold zeros (absent items: bias = +inf).
+    `own_cols[N, K]` = columns of the row's user's targets, -1 = none (None: no same-user mask)."""
+    dtype = _operand_dtype(user_emb, col_rows)
+    scale = 1.0 / temperature
+    u16, c16 = user_emb.to(dtype), col_rows.to(dtype)
+    lq = (log_q_tensor[col_item_ids] * lambda_logq).float() if lambda_logq > 0.0 else None
+    bias = -torch.log(col_counts.float())
+    if lq is not None:
+        bias = bias + lq
+    lse0 = fused_softmax_stats(u16, c16, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
+                               mask_value=NEG_INF, flags=L.RS_CE_NO_DIAG, dtype=dtype)[0]
+    s_pos = ops.sparse_logits(u16, c16, pos_col.view(-1, 1), scale, lq).squeeze(1)
+    mx = torch.maximum(lse0, s_pos).detach()
+    z = torch.exp(lse0 - mx) + torch.exp(s_pos - mx)
+    if own_cols is not None and own_cols.shape[1] > 0:
+        s_own = ops.sparse_logits(u16, c16, own_cols, scale, lq, target_ids, col_item_ids)
+        z = z - torch.exp(s_own - mx.unsqueeze(1)).sum(dim=1)
+    lse = mx + torch.log(z.clamp_min(1e-30))
+    return (lse - s_pos).mean()
+
+
 def inbatch_logq_loss_no_user(user_emb, item_tower_emb, target_ids, log_q_tensor, temperature=0.1, lambda_logq=1.0):
     """The shadowed first definition (tower_code/v1_refine_usertower.py:520-573): same-item mask only."""
     v = ops.gather_rows(item_tower_emb, target_ids)

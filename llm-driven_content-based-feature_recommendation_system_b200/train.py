@@ -32,8 +32,11 @@ def prepare_batch(batch: Dict[str, torch.Tensor], device, non_blocking=True) -> 
     return out
 
 
-def add_host_index(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """Add `valid_index` / `last_index` (host tensors) so that the device step needs no nonzero()."""
+def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict[str, torch.Tensor]:
+    """Add `valid_index` / `last_index` (host tensors) so that the device step needs no nonzero(), and
+    (columns=True) the distinct-item column set of the batch's targets for `losses.logq_infonce_columns`:
+    `col_item_ids[U]`, `col_counts[U]`, `pos_col[N]`, `own_grid[B, L]` (column of the target at (b, l), -1 at
+    padding).  All of it is index arithmetic on the collated batch, done where the ids live (the loader)."""
     valid = ~batch["padding_mask"]
     B, L = valid.shape
     batch = dict(batch)
@@ -41,14 +44,23 @@ def add_host_index(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     last = (valid.sum(dim=1) - 1).clamp(min=0)
     batch["last_index"] = torch.arange(B) * L + last
     batch["select_index"] = torch.cat([batch["valid_index"], batch["last_index"]])
+    if columns:
+        tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
+        ids, counts, pos_col = losses.item_columns(tgt)
+        grid = torch.full((B * L,), -1, dtype=torch.int64)
+        grid[batch["valid_index"]] = pos_col
+        batch.update(col_item_ids=ids, col_counts=counts, pos_col=pos_col, own_grid=grid.view(B, L))
     return batch
 
 
 def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1,
                    lambda_cl=0.2, loss_scope="all", amp_dtype: Optional[torch.dtype] = torch.bfloat16,
-                   scaler=None, max_norm=5.0, grad_hook=None, sdpa_efficient=True):
+                   scaler=None, max_norm=5.0, grad_hook=None, sdpa_efficient=True, columns="unique"):
     """forward x2 (two dropout views) + C2 + C3 + backward + clip + optimizer step.
-    Returns (total, main, cl) as device scalars.  `batch` comes from prepare_batch(add_host_index(...))."""
+    Returns (total, main, cl) as device scalars.  `batch` comes from prepare_batch(add_host_index(...)).
+    columns: how the in-batch softmax of the main loss enumerates its columns (same loss value, see
+    losses.logq_infonce_columns) -- "unique": the distinct target items of the batch with multiplicities
+    (default); "catalog": every item, static shape; "batch": one column per row, the reference's [N, N]."""
     item_ids = batch["item_ids"]
     B, L = item_ids.shape
     if optimizer is not None:
@@ -75,8 +87,20 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
         u = F.normalize(out1[:n_main], p=2, dim=1)                                   # :794-807
         tgt = tgt_flat[idx]
         uid = idx // L                                                               # batch row = user id (:801-804)
-        v = item_tower.normalized_rows(tgt)                                          # :810-811 + :833
-        main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq)
+        if columns == "batch" or (columns == "unique" and ("col_item_ids" not in batch or loss_scope != "all")):
+            v = item_tower.normalized_rows(tgt)                                      # :810-811 + :833
+            main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq)
+        else:
+            if columns == "unique":
+                cid, cnt, pos_col, grid = (batch[k] for k in ("col_item_ids", "col_counts", "pos_col", "own_grid"))
+                v = item_tower.normalized_rows(cid)
+            else:
+                v = F.normalize(item_tower.get_all_embeddings(), p=2, dim=1)         # :810, all rows
+                cid, cnt, pos_col = losses.item_columns(tgt, v.shape[0])
+                grid = batch["target_ids"].masked_fill(batch["padding_mask"], -1)
+            own = grid[uid] if loss_scope == "all" else None     # one row per user otherwise: nothing to mask
+            main = losses.logq_infonce_columns(u, v, cid, cnt, tgt, pos_col, own, item_tower.get_log_q(), 0.1,
+                                               lambda_logq)
         cl = losses.duorec_loss_refined(out1[n_main:], out2, tgt_flat[li], lambda_sup=lambda_sup)   # :830-842
         total = main + lambda_cl * cl
     if optimizer is not None:

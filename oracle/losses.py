@@ -53,6 +53,38 @@ def inbatch_corrected_logq_loss(user_emb, item_tower_emb, target_ids, user_ids, 
     return _diag_ce(s)
 
 
+def inbatch_corrected_logq_loss_columns(user_emb, col_rows, col_item_ids, col_counts, target_ids, pos_col,
+                                        own_cols, log_q_tensor, temperature: float = 0.1,
+                                        lambda_logq: float = 1.0) -> torch.Tensor:
+    """C2 (tower_code/v1_refine_usertower.py:826-861) restated over a MULTISET of columns: in-batch columns
+    that share a target item have the same item row and the same logQ, hence the same logit, so the [N, N]
+    softmax collapses to [N, U] over the distinct items with their batch multiplicities m_c:
+
+        Z_i = e^{s_i,t_i}                              (the diagonal; all other copies of t_i are masked, :846)
+            + sum_{c != t_i} m_c e^{s_ic}              (every in-batch column, grouped by item)
+            - sum_{j in user(i), t_j != t_i} e^{s_i,t_j}   (same-user columns are masked too, :848)
+        loss = mean_i( log Z_i - s_i,t_i )
+
+    `col_rows[U, D]` rows of the column items, `col_item_ids[U]`, `col_counts[U]` (m_c, may be 0 = absent),
+    `pos_col[N]` column of each row's own target, `own_cols[N, K]` columns of the same user's targets
+    (-1 = none).  Checked against `inbatch_corrected_logq_loss` in tests/test_oracle_golden.py."""
+    s = (user_emb @ col_rows.T) / temperature
+    if lambda_logq > 0.0:
+        s = s - log_q_tensor[col_item_ids].view(1, -1) * lambda_logq
+    n = user_emb.shape[0]
+    r = torch.arange(n)
+    s_pos = s[r, pos_col]
+    w = col_counts.to(s.dtype).view(1, -1).expand(n, -1).clone()
+    w[col_item_ids.view(1, -1) == target_ids.view(-1, 1)] = 0.0         # every copy of the row's own target
+    ok = own_cols >= 0
+    oc = own_cols.clamp(min=0)
+    ok = ok & (col_item_ids[oc] != target_ids.view(-1, 1))
+    w.scatter_add_(1, oc, -ok.to(s.dtype))                               # same-user columns
+    mx = torch.maximum(s.max(dim=1).values, s_pos).detach()
+    z = (w * torch.exp(s - mx.view(-1, 1))).sum(1) + torch.exp(s_pos - mx)
+    return (mx + torch.log(z) - s_pos).mean()
+
+
 def inbatch_logq_loss_no_user(user_emb, item_tower_emb, target_ids, log_q_tensor,
                               temperature: float = 0.1, lambda_logq: float = 1.0) -> torch.Tensor:
     """The shadowed first definition (tower_code/v1_refine_usertower.py:520-573):

@@ -97,6 +97,56 @@ def test_c2_sizes_vs_oracle(rs, N, V):
     _cmp(got, dict(loss=want.detach(), grads=[u.grad, t.grad]), torch.bfloat16)
 
 
+def _own_cols(pos_col, uid):
+    """[N, K] columns of the same user's targets (-1 padded), built the slow obvious way."""
+    n = uid.numel()
+    groups = {}
+    for i, u in enumerate(uid.tolist()):
+        groups.setdefault(u, []).append(i)
+    k = max(len(v) for v in groups.values())
+    own = torch.full((n, k), -1, dtype=torch.long)
+    for i, u in enumerate(uid.tolist()):
+        js = groups[u]
+        own[i, :len(js)] = pos_col[js]
+    return own
+
+
+def _columns_loss(rs, U, table, tgt, uid, logq, mode, temperature, lam, dtype=torch.bfloat16):
+    """C2 through the distinct-item column form (losses.logq_infonce_columns), columns built on the host."""
+    ids, counts, pos_col = rs.losses.item_columns(tgt, None if mode == "unique" else table.shape[0])
+    own = _own_cols(pos_col, uid)
+
+    def fn(u, t):
+        return rs.logq_infonce_columns(u, rs.ops.gather_rows(t, ids.to(DEV)), ids.to(DEV), counts.to(DEV), tgt.to(DEV),
+                                       pos_col.to(DEV), own.to(DEV), logq.to(DEV), temperature, lam)
+    return _run(rs, fn, [U, table], dtype)
+
+
+@pytest.mark.parametrize("mode", ["unique", "catalog"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_c2_columns_vs_reference(rs, lg, mode, dtype):
+    """the [N, U] distinct-item form equals the reference's [N, N] loss and gradients (golden fixture)."""
+    _cmp(_columns_loss(rs, lg["U"], lg["table"], lg["tgt"], lg["uid"], lg["logq"], mode, 0.1, 1.0, dtype), lg["c2"], dtype)
+    _cmp(_columns_loss(rs, lg["U"], lg["table"], lg["tgt"], lg["uid"], lg["logq"], mode, 0.07, 0.0, dtype),
+         lg["c2_nologq"], dtype)
+
+
+@pytest.mark.parametrize("N,V,mode", [(1, 5, "unique"), (127, 40, "catalog"), (129, 64, "unique"), (1000, 300, "unique"),
+                                      (4096, 3000, "catalog"), (5000, 100000, "unique")])
+def test_c2_columns_sizes_vs_oracle(rs, N, V, mode):
+    g = torch.Generator().manual_seed(N + 1)
+    table = F.normalize(torch.randn(V, 128, generator=g), dim=1)
+    tgt = torch.randint(0, V, (N,), generator=g)
+    U = F.normalize(torch.randn(N, 128, generator=g) + 2.0 * table[tgt], dim=1)
+    uid = torch.randint(0, max(2, N // 8), (N,), generator=g)
+    logq = torch.log(torch.rand(V, generator=g) + 1e-6)
+    u, t = U.clone().requires_grad_(True), table.clone().requires_grad_(True)
+    want = olosses.inbatch_corrected_logq_loss(u, t, tgt, uid, logq, 0.1, 1.0)
+    want.backward()
+    got = _columns_loss(rs, U, table, tgt, uid, logq, mode, 0.1, 1.0)
+    _cmp(got, dict(loss=want.detach(), grads=[u.grad, t.grad]), torch.bfloat16)
+
+
 def test_rectangular_with_diag_offset(rs):
     """[B, G*B] block of the cross-GPU negatives layout: label of row i is column i + off."""
     g = torch.Generator().manual_seed(4)
@@ -288,3 +338,29 @@ def test_c4_larger_vs_oracle(rs):
          torch.bfloat16)
     assert stats["num_hard"] == wstats["num_hard"]
     assert stats["avg_hn_similarity"] == pytest.approx(wstats["avg_hn_similarity"], abs=1e-4)
+
+
+def test_train_step_column_modes_agree(rs):
+    """One full train step (eval-mode towers: no dropout noise) gives the same main loss and the same
+    item-matrix / user-tower gradients whichever way the in-batch softmax enumerates its columns."""
+    syn = rs.synthetic
+    n_items, B, SL = 3000, 96, 50
+    torch.manual_seed(0)
+    model = rs.SASRecUserTower(syn.tower_args(num_items=n_items, max_len=SL)).to(DEV).eval()
+    item = rs.SASRecItemTower(n_items, 128, syn.log_q(n_items)).to(DEV)
+    lookup = syn.pretrained_table(n_items).to(DEV)
+    item.init_from_pretrained(lookup)
+    batch = rs.train.prepare_batch(rs.train.add_host_index(syn.make_batch(B, SL, n_items, seed=5)), DEV)
+    res = {}
+    for mode in ("batch", "unique", "catalog"):
+        model.zero_grad(set_to_none=True)
+        item.zero_grad(set_to_none=True)
+        opt = torch.optim.SGD(list(model.parameters()) + list(item.parameters()), lr=0.0)
+        total, main, cl = rs.train.two_tower_step(model, item, batch, lookup, opt, columns=mode)
+        res[mode] = (main.item(), cl.item(), item.item_matrix.weight.grad.clone(), model.item_id_emb.weight.grad.clone(),
+                     model.output_proj[0].weight.grad.clone())
+    for mode in ("unique", "catalog"):
+        assert abs(res[mode][0] - res["batch"][0]) < 5e-3, (mode, res[mode][0], res["batch"][0])
+        assert abs(res[mode][1] - res["batch"][1]) < 1e-5
+        for g, w in zip(res[mode][2:], res["batch"][2:]):
+            assert (g - w).abs().max() <= 2e-2 * w.abs().max() + 1e-8, (mode, (g - w).abs().max(), w.abs().max())

@@ -112,6 +112,38 @@ def test_c2(lg):
            lg["logq"], temperature=0.07, lambda_logq=0.0)
 
 
+def _columns_from_batch(tgt, uid, mode, n_items):
+    """Host-side construction of the column multiset (what the loader does; pure index arithmetic)."""
+    n = tgt.numel()
+    if mode == "unique":
+        ids, pos_col, counts = torch.unique(tgt, return_inverse=True, return_counts=True)
+    else:
+        ids = torch.arange(n_items)
+        counts = torch.bincount(tgt, minlength=n_items)
+        pos_col = tgt.clone()
+    # columns of the same user's targets, padded with -1
+    own = torch.full((n, n), -1, dtype=torch.long)
+    for i in range(n):
+        js = torch.nonzero(uid == uid[i]).squeeze(1)
+        own[i, :js.numel()] = pos_col[js]
+    k = int((own >= 0).sum(1).max())
+    return ids, counts, pos_col, own[:, :k]
+
+
+@pytest.mark.parametrize("mode", ["unique", "catalog"])
+def test_c2_column_multiset(lg, mode):
+    """The distinct-item / multiplicity form of C2 equals the reference's [N, N] form (loss and gradients)."""
+    for name, temp, lam in (("c2", 0.1, 1.0), ("c2_nologq", 0.07, 0.0)):
+        U, table = lg["U"].clone().requires_grad_(True), lg["table"].clone().requires_grad_(True)
+        ids, counts, pos_col, own = _columns_from_batch(lg["tgt"], lg["uid"], mode, table.shape[0])
+        loss = losses.inbatch_corrected_logq_loss_columns(U, table[ids], ids, counts, lg["tgt"], pos_col, own,
+                                                          lg["logq"], temp, lam)
+        torch.testing.assert_close(loss, lg[name]["loss"], rtol=1e-5, atol=1e-5)
+        loss.backward()
+        torch.testing.assert_close(U.grad, lg[name]["grads"][0], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(table.grad, lg[name]["grads"][1], rtol=1e-4, atol=1e-6)
+
+
 def test_c3(lg):
     _check(lg, "c3", losses.duorec_loss_refined, [lg["U"], lg["U2"]], lg["tgt"], temperature=0.1, lambda_sup=0.1)
     _check(lg, "c3_nosup", losses.duorec_loss_refined, [lg["U"], lg["U2"]], lg["tgt"], temperature=0.1,
