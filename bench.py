@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--columns", default="unique", choices=["unique", "catalog", "batch"],
                     help="column enumeration of the main in-batch softmax (same loss): distinct batch items with "
                          "multiplicities / whole catalogue / one column per row as the reference materialises it")
+    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "dp"],
+                    help="N>1: row-sharded item tables (all-to-all lookups) + negatives spanning the box [default], "
+                         "or plain data-parallel replicas with all-reduced gradients and rank-local negatives")
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="only the resident-input timed loop (for ncu runs)")
@@ -174,6 +177,8 @@ def run_ours(args):
     item = rs.SASRecItemTower(syn.N_ITEMS, 128, syn.log_q(syn.N_ITEMS)).to(dev)
     lookup = syn.pretrained_table(syn.N_ITEMS).to(dev)
     item.init_from_pretrained(lookup)
+    sharded = world > 1 and args.parallelism == "sharded"
+    trainer = rs.train.ShardedTwoTower(model, item) if sharded else None      # re-shards the two item tables in place
     params = list(model.parameters()) + list(item.parameters())
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True)
 
@@ -194,13 +199,23 @@ def run_ours(args):
     host = [{k: v.pin_memory() for k, v in rs.train.add_host_index(
         syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + 1000 * rank + i)).items()} for i in range(pool)]
     resident = [rs.train.prepare_batch(hb, dev) for hb in host]
+    if sharded:
+        # loader-stage routing of every batch's item ids (split sizes + the id exchange), once per batch; the host
+        # copy keeps the position order pinned (it is an input like the ids), the requested rows live on their owner
+        resident = [trainer.plan(b) for b in resident]
+        for hb, rb in zip(host, resident):
+            hb["route_order"] = rb["lookup_plan"].order.cpu().pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     n_valid = int(host[0]["valid_index"].numel())
     n_cols = {"unique": int(host[0]["col_item_ids"].numel()), "catalog": syn.N_ITEMS + 1}.get(args.columns, n_valid)
     if args.loss_scope != "all":
         n_cols = B if args.columns != "catalog" else n_cols
+    if sharded:
+        n_cols = trainer.cols.n_cols
 
     def step(b):
+        if sharded:
+            return trainer.step(b, lookup, opt, amp_dtype=torch.bfloat16)
         return rs.train.two_tower_step(model, item, b, lookup, opt, loss_scope=args.loss_scope,
                                        amp_dtype=torch.bfloat16, grad_hook=sync_grads, columns=args.columns)
 
@@ -240,6 +255,9 @@ def run_ours(args):
     # ---- end-to-end run: host batches in, losses out, every step
     def e2e_step(i):
         b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
+        if sharded:
+            pl = resident[i % pool]["lookup_plan"]
+            b["lookup_plan"] = rs.sharded.LookupPlan(b.pop("route_order"), pl.send, pl.recv, pl.req, pl.n)
         t, m, c = step(b)
         last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
 
@@ -316,8 +334,13 @@ def run_ours(args):
                     config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B,
                                 global_batch=B * world, seq_len=SL, d_model=128, n_items=syn.N_ITEMS,
                                 loss_scope=args.loss_scope, loss_rows=n_valid if args.loss_scope == "all" else B,
-                                loss_columns=args.columns, loss_cols=n_cols,
-                                parallelism=f"dp{world} (replicated tables, gradients all-reduced)" if world > 1 else "1 GPU",
+                                loss_columns="catalog" if sharded else args.columns, loss_cols=n_cols,
+                                parallelism=("1 GPU" if world == 1 else
+                                             f"{world} ranks: item_id_emb + item_matrix row-sharded (owner = row % {world}, "
+                                             f"all-to-all lookups), negatives = whole catalogue with box-wide counts, "
+                                             f"DuoRec columns all-gathered, other parameters replicated + all-reduced"
+                                             if sharded else f"dp{world} (replicated tables, gradients all-reduced, "
+                                                             f"rank-local negatives)"),
                                 l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
                     e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
                     kernels=kernels, loss=dict(total=total, main=main, cl=cl))

@@ -251,6 +251,9 @@ __device__ __forceinline__ void issue_s(const CeParams& p, CeShared& sh, uint8_t
   umma_commit(&sh.tmem_full[g]);
 }
 
+// a row whose every column is masked has lse = -inf and softmax 0 everywhere: exp2(-inf - 0) = 0, not exp2(-inf + inf)
+__device__ __forceinline__ float lse_or_zero(float lse) { return lse == -INFINITY ? 0.f : lse; }
+
 // stage the metadata of column tile `ct` (one column per thread of the warpgroup) + the key_b range of
 // each staging warp's 32 columns (for the range-disjointness test that lets whole tiles skip that compare)
 template <bool BWD_T>
@@ -264,7 +267,7 @@ __device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int c
   const uint32_t lo = __reduce_min_sync(0xffffffffu, kb), hi = __reduce_max_sync(0xffffffffu, kb);
   if ((t128 & 31) == 0) { cm.kb_lo[t128 >> 5] = lo; cm.kb_hi[t128 >> 5] = hi; }
   if (BWD_T) {
-    cm.lse[t128] = ok ? __ldg(p.lse + c) * CE_LOG2E : 0.f;
+    cm.lse[t128] = ok ? lse_or_zero(__ldg(p.lse + c)) * CE_LOG2E : 0.f;
     cm.wl[t128] = ok ? __ldg(p.w_lse + c) * cs : 0.f;
     cm.wd[t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) * cs : 0.f;
     cm.wp[t128] = (ok && p.w_pos) ? __ldg(p.w_pos + c) * cs : 0.f;
@@ -679,7 +682,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (row_ok) {
         if (TRANSPOSED) { if (p.row_bias) rc.nrowbias2 = -__ldg(p.row_bias + row) * CE_LOG2E; }
         else {
-          rc.lse2 = __ldg(p.lse + row) * CE_LOG2E;
+          rc.lse2 = lse_or_zero(__ldg(p.lse + row)) * CE_LOG2E;
           rc.wlc = __ldg(p.w_lse + row) * cs;
           if (p.w_diag) rc.wdc = __ldg(p.w_diag + row) * cs;
           if (p.w_pos) rc.wpc = __ldg(p.w_pos + row) * cs;

@@ -129,8 +129,13 @@ def item_columns(target_ids: Tensor, num_items: Optional[int] = None):
     if num_items is None:
         ids, pos_col, counts = torch.unique(target_ids, return_inverse=True, return_counts=True)
         return ids, counts, pos_col
-    counts = torch.bincount(target_ids, minlength=num_items)
-    return torch.arange(num_items, device=target_ids.device), counts, target_ids
+    return torch.arange(num_items, device=target_ids.device), count_ids(target_ids, num_items), target_ids
+
+
+def count_ids(ids: Tensor, n: int) -> Tensor:
+    """bincount(ids, minlength=n) as fp32, without torch.bincount's device->host read of max(ids)."""
+    return torch.zeros(n, dtype=torch.float32, device=ids.device).scatter_add_(
+        0, ids, torch.ones(1, dtype=torch.float32, device=ids.device).expand(ids.numel()))
 
 
 def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tensor, col_counts: Tensor,

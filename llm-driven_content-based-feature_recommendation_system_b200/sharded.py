@@ -137,3 +137,112 @@ def cross_rank_logq_infonce(user_emb, item_rows, target_ids, user_ids, log_q_ten
     fn = loss_fn or losses.logq_infonce_rows
     return fn(user_emb, item_rows, target_ids, user_ids + rank * (1 << 24), log_q_tensor, temperature, lambda_logq,
               col_rows=cols, col_target_ids=ct, col_user_ids=cu, diag_offset=rank * B)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Planned exchange: everything that depends only on the batch's ids (bucketing by owner, split sizes, the id
+# all-to-all itself) is done once per batch, where the loader prepares it -- the training step then contains
+# only the two row exchanges and no host synchronisation.
+# ----------------------------------------------------------------------------------------------------
+class LookupPlan:
+    """Routing of one id tensor against a table row-sharded as owner = id % world, local row = id // world.
+    order[n]        positions sorted by owner (stable)
+    send / recv     per-rank split sizes (host lists): rows this rank asks rank r for / is asked for by rank r
+    req[sum(recv)]  LOCAL rows the other ranks ask this rank for, grouped by requesting rank"""
+
+    def __init__(self, order, send, recv, req, n):
+        self.order, self.send, self.recv, self.req, self.n = order, send, recv, req, n
+
+    def to(self, device, non_blocking=True):
+        return LookupPlan(self.order.to(device, non_blocking=non_blocking), self.send, self.recv,
+                          self.req.to(device, non_blocking=non_blocking), self.n)
+
+
+def plan_lookup(ids: torch.Tensor, group=None) -> LookupPlan:
+    """Build the plan for `ids` (any shape; host or device tensor).  Exchanges the split sizes and the requested
+    rows with the other ranks (collective, synchronises: call it from the loader / prefetch stage)."""
+    world = dist.get_world_size(group)
+    flat = ids.reshape(-1)
+    order, counts, local_rows = route(flat, world)
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    sc, rc = counts.tolist(), recv_counts.tolist()
+    req = local_rows.new_empty(sum(rc))
+    dist.all_to_all_single(req, local_rows, rc, sc, group=group)
+    return LookupPlan(order, sc, rc, req, flat.numel())
+
+
+class _PlannedLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, shard, plan, group, gather_fn, scatter_fn, lead_rows, pad_local_row):
+        rows = gather_fn(shard, plan.req)                                            # owner-side gather (CUDA kernel)
+        back = rows.new_empty(plan.n, shard.shape[1])
+        dist.all_to_all_single(back, rows.contiguous(), plan.send, plan.recv, group=group)   # rows -> requesters
+        out = rows.new_zeros(lead_rows + plan.n, shard.shape[1]) if lead_rows else rows.new_empty(plan.n, shard.shape[1])
+        out[lead_rows:].index_copy_(0, plan.order, back)
+        ctx.plan, ctx.meta = plan, (shard.shape[0], group, scatter_fn, shard.dtype, lead_rows, pad_local_row)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan = ctx.plan
+        nrows, group, scatter_fn, sdt, lead_rows, pad_local_row = ctx.meta
+        g = g[lead_rows:].index_select(0, plan.order)
+        recv = g.new_empty(sum(plan.recv), g.shape[1])
+        dist.all_to_all_single(recv, g, plan.recv, plan.send, group=group)           # grad rows -> owners
+        return scatter_fn(recv, plan.req, nrows, pad_local_row).to(sdt), None, None, None, None, None, None
+
+
+def _scatter_pad(grad_rows, ids, rows, pad_local_row):
+    return torch.ops.rs.embedding_dense_bwd(grad_rows, ids, rows, pad_local_row, -1, True)
+
+
+def planned_lookup(shard: torch.Tensor, plan: LookupPlan, group=None, gather_fn: Optional[Callable] = None,
+                   scatter_fn: Optional[Callable] = None, lead_rows: int = 0, pad_local_row: int = -1) -> torch.Tensor:
+    """rows `full[ids]` ([lead_rows + n, D], the first `lead_rows` rows zero and without gradient) of a table
+    row-sharded as `shard = full[rank::world]`, with the routing precomputed by `plan_lookup`.  Backward: the
+    gradient rows travel back to their owners, which reduce them into their shard with the deterministic
+    sort + segment-reduce kernel (`pad_local_row`: a local row that never receives gradient -- the padding row
+    0 lives on rank 0 as local row 0; -1 elsewhere)."""
+    return _PlannedLookup.apply(shard, plan, group, gather_fn or _default_gather, scatter_fn or _scatter_pad,
+                                lead_rows, pad_local_row)
+
+
+def padded_rows(n_rows: int, world: int) -> int:
+    """Rows per shard when a table of `n_rows` is padded to a multiple of `world`."""
+    return (n_rows + world - 1) // world
+
+
+def shard_padded(full: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """`shard_rows` of the table zero-padded to world * padded_rows rows (equal shards: all-gather friendly)."""
+    R = padded_rows(full.shape[0], world)
+    out = full.new_zeros(R, *full.shape[1:])
+    mine = full[rank::world]
+    out[:mine.shape[0]] = mine
+    return out
+
+
+class CatalogColumns:
+    """Column layout of the all-gathered, row-sharded item matrix (rank-major: column r*R + j holds item
+    j*world + r) for `losses.logq_infonce_columns` with catalogue-wide negatives: every rank scores its rows
+    against ALL items, weighted by how often each item occurs as a target anywhere on the box (the reference's
+    in-batch negatives of the global batch, grouped by item).  Static shapes, no id exchange, no dedup."""
+
+    def __init__(self, n_rows: int, world: int, device):
+        self.world, self.R = world, padded_rows(n_rows, world)
+        self.n_cols = self.world * self.R
+        c = torch.arange(self.n_cols, device=device)
+        self.col_item_ids = (c % self.R) * world + c // self.R       # ids >= n_rows are padding columns (count 0)
+
+    def col_of(self, item_ids: torch.Tensor) -> torch.Tensor:
+        """column index of an item id (elementwise; negative ids stay negative)."""
+        col = (item_ids % self.world) * self.R + torch.div(item_ids, self.world, rounding_mode="floor")
+        return torch.where(item_ids < 0, item_ids, col)
+
+    def counts(self, target_ids: torch.Tensor, group=None) -> torch.Tensor:
+        """occurrences of every column's item among the targets of ALL ranks (one small all-reduce)."""
+        from .losses import count_ids
+        cnt = count_ids(self.col_of(target_ids), self.n_cols)
+        if self.world > 1:
+            dist.all_reduce(cnt, group=group)
+        return cnt

@@ -74,13 +74,20 @@ class SASRecUserTower(nn.Module):
     def get_causal_mask(self, seq_len, device):
         return torch.triu(torch.ones(seq_len, seq_len, device=device, dtype=torch.bool), diagonal=1)
 
-    def embed_front(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids):
+    def embed_front(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids,
+                    item_id_rows=None):
         """U1 (:447-456): one fused kernel instead of 6 gathers + 13 elementwise passes.  Tables whose gate
-        is hard-masked to zero (type/color/graphic/section) contribute exactly 0 and are not read."""
+        is hard-masked to zero (type/color/graphic/section) contribute exactly 0 and are not read.
+        `item_id_rows` [1 + B*L, 128]: the rows `item_id_emb.weight[item_ids]` already fetched from their owner
+        ranks (row-sharded table, sharded.py) behind one unused leading row; the kernel then reads row 1 + b*L + l
+        for position (b, l) -- same arithmetic, and the gradient of the buffer goes back through the exchange."""
         s_g = torch.sigmoid(self.seq_gate) * self._seq_gate_mask
         base = self.item_proj(pretrained_vecs)
         ids = [item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids]
         tables = [getattr(self, n).weight for n in SEQ_TABLES]
+        if item_id_rows is not None:
+            ids[0] = torch.arange(1, item_ids.numel() + 1, device=item_ids.device).view_as(item_ids)
+            tables[0] = item_id_rows
         n_live = sum(1 for m in SEQ_GATE_MASK if m != 0.0)        # live tables come first in SEQ_TABLES
         return ops.seq_front(base, ids, tables, s_g, self.pos_emb.weight, padding_idx=0, n_live=n_live)
 
@@ -96,14 +103,15 @@ class SASRecUserTower(nn.Module):
 
     def forward(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids,
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
-                fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None):
+                fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None,
+                item_id_rows=None):
         """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
         When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
         returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
         so the other ~75 % of the [B,L] grid need not go through output_proj."""
         seq_len = item_ids.size(1)
         seq_emb = self.embed_front(pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids,
-                                   section_ids)
+                                   section_ids, item_id_rows)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
         output = self.transformer_encoder(seq_emb, mask=self.get_causal_mask(seq_len, item_ids.device),
                                           src_key_padding_mask=padding_mask)

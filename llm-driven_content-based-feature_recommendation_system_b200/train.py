@@ -119,3 +119,139 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
             optimizer.step()
     return total.detach(), main.detach(), cl.detach()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# N > 1: row-sharded item tables + catalogue-wide negatives.  One process per GPU.
+# ------------------------------------------------------------------------------------------------------------
+class ShardedTwoTower:
+    """The same step on `world` ranks with
+      * `item_id_emb` (user tower) and `item_matrix` (item tower) ROW-SHARDED, owner = row % world: each rank keeps
+        [ceil(rows/world), 128] of each (parameters + AdamW state); lookups go through the planned all-to-all
+        (sharded.planned_lookup: owner-side gather kernel -> rows all-to-all; backward: gradient rows all-to-all ->
+        owner-side deterministic segment reduce);
+      * the negatives of the main loss spanning the box: every rank scores its rows against the all-gathered
+        (normalised) item matrix, each item weighted by its number of occurrences among the targets of ALL
+        ranks -- the reference's in-batch softmax over the global batch, grouped by item
+        (losses.logq_infonce_columns); the gathered matrix's gradient is reduce-scattered to the owners;
+      * DuoRec with all-gathered second views / targets (rectangular [B, world*B] blocks, diag_offset = rank*B);
+      * every other parameter replicated, gradients summed with one flat all-reduce.
+    Each rank's loss is its share of the GLOBAL mean (local sum / global row count), so that summing the
+    gradients over ranks -- which the collectives above do -- gives the gradient of the global-batch loss."""
+
+    def __init__(self, model, item_tower, group=None):
+        import torch.distributed as dist
+        from . import sharded
+        self.dist, self.sh = dist, sharded
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.model, self.item_tower = model, item_tower
+        dev = item_tower.item_matrix.weight.device
+        n_rows = item_tower.item_matrix.weight.shape[0]
+        self.n_rows = n_rows
+        self.cols = sharded.CatalogColumns(n_rows, self.world, dev)
+        for emb in (model.item_id_emb, item_tower.item_matrix):                 # keep only this rank's rows
+            full = emb.weight.data
+            emb.weight = torch.nn.Parameter(sharded.shard_padded(full, self.rank, self.world))
+        lq = item_tower.get_log_q().float()
+        lq_pad = torch.zeros(self.cols.n_cols, device=dev)
+        lq_pad[:n_rows] = lq
+        self.log_q_by_id = lq_pad                                                # indexed by item id (padded)
+        self.sharded_params = [model.item_id_emb.weight, item_tower.item_matrix.weight]
+        sp = {id(p) for p in self.sharded_params}
+        self.replicated_params = [p for p in list(model.parameters()) + list(item_tower.parameters())
+                                  if id(p) not in sp and p.requires_grad]
+        self.pad_local_row = 0 if self.rank == 0 else -1                         # global row 0 = rank 0, local row 0
+
+    def plan(self, batch):
+        """Loader-stage work for one (device) batch: routing of its item ids (collective, synchronises)."""
+        batch = dict(batch)
+        batch["lookup_plan"] = self.sh.plan_lookup(batch["item_ids"], self.group)
+        return batch
+
+    def _sync_replicated(self):
+        gs = [p.grad for p in self.replicated_params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        self.dist.all_reduce(flat, group=self.group)
+        torch._foreach_copy_(gs, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in gs]), gs)])
+
+    def _clip(self, max_norm):
+        """clip_grad_norm_ over the user tower's parameters with its sharded table counted once, globally."""
+        mp = {id(p) for p in self.model.parameters()}
+        rep = [p.grad for p in self.replicated_params if id(p) in mp and p.grad is not None]
+        sq_rep = torch.stack(torch._foreach_norm(rep)).square().sum()
+        sq_sh = self.model.item_id_emb.weight.grad.float().square().sum()
+        self.dist.all_reduce(sq_sh, group=self.group)
+        total = (sq_rep + sq_sh).sqrt()
+        coef = (max_norm / (total + 1e-6)).clamp(max=1.0)
+        torch._foreach_mul_(rep + [self.model.item_id_emb.weight.grad], coef)
+        return total
+
+    def step(self, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1, lambda_cl=0.2,
+             amp_dtype: Optional[torch.dtype] = torch.bfloat16, max_norm=5.0, sdpa_efficient=True):
+        dist, sh, model, item_tower = self.dist, self.sh, self.model, self.item_tower
+        item_ids = batch["item_ids"]
+        B, L = item_ids.shape
+        if optimizer is not None:
+            optimizer.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            pretrained_vecs = ops.gather_rows(pretrained_lookup, item_ids)
+        kw = {k: batch[k] for k in FORWARD_KEYS}
+        # one exchange serves both dropout views (their gradients add up in the buffer before travelling back)
+        id_rows = sh.planned_lookup(model.item_id_emb.weight, batch["lookup_plan"], self.group, lead_rows=1,
+                                    pad_local_row=self.pad_local_row)
+        sdpa = sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]) if sdpa_efficient else contextlib.nullcontext()
+        with sdpa, torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+            tgt_flat = batch["target_ids"].reshape(-1)
+            idx, li = batch["valid_index"], batch["last_index"]
+            n_main = idx.numel()
+            sel1 = batch.get("select_index")
+            if sel1 is None:
+                sel1 = torch.cat([idx, li])
+            out1 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1, item_id_rows=id_rows)
+            out2 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=li, item_id_rows=id_rows)
+            u = F.normalize(out1[:n_main], p=2, dim=1)
+            tgt = tgt_flat[idx]
+            uid = idx // L
+            # main loss: all items as columns, global multiplicities
+            n_glob = torch.tensor([float(n_main)], device=u.device)
+            dist.all_reduce(n_glob, group=self.group)
+            v_cols = sh.all_gather_rows(F.normalize(item_tower.item_matrix.weight, p=2, dim=1), self.group)
+            cnt = self.cols.counts(tgt, self.group)
+            grid = self.cols.col_of(batch["target_ids"].masked_fill(batch["padding_mask"], -1))
+            main_local = losses.logq_infonce_columns(u, v_cols, self.cols.col_item_ids, cnt, tgt, self.cols.col_of(tgt),
+                                                     grid[uid], self.log_q_by_id, 0.1, lambda_logq)
+            main = main_local * (n_main / n_glob.squeeze(0))
+            # DuoRec across the box
+            cl = self._duorec(out1[n_main:], out2, tgt_flat[li], lambda_sup) / self.world
+            total = main + lambda_cl * cl
+        if optimizer is not None:
+            total.backward()
+            self._sync_replicated()
+            self._clip(max_norm)
+            optimizer.step()
+        out = torch.stack([total.detach(), main.detach(), cl.detach()])
+        dist.all_reduce(out, group=self.group)                                   # global-batch losses (for logging)
+        return out[0], out[1], out[2]
+
+    def _duorec(self, e1, e2, tgt, lambda_sup, temperature=0.1):
+        """C3 (v1_refine_usertower.py:576-627) with the columns of every rank; returns this rank's mean over its
+        B rows (the caller divides by world: equal B on all ranks)."""
+        sh, rank = self.sh, self.rank
+        B = e1.shape[0]
+        z1, z2 = F.normalize(e1, dim=1), F.normalize(e2, dim=1)
+        z2_all = sh.all_gather_rows(z2, self.group)
+        loss = losses.info_nce(z1, z2_all, temperature, diag_offset=rank * B)
+        if lambda_sup > 0:
+            z1_all = sh.all_gather_rows(z1, self.group)
+            tgt_all = sh.all_gather_ids(tgt, self.group)
+            lse, _, pos_sum, pos_cnt = losses.fused_softmax_stats(
+                z1, z1_all, 1.0 / temperature, key_a_row=tgt, key_a_col=tgt_all, diag_offset=rank * B,
+                mask_value=losses.NEG_INF, flags=losses.L.RS_CE_DIAG_MASK | losses.L.RS_CE_SUPCON)
+            valid = pos_cnt > 0
+            per_row = torch.where(valid, lse - pos_sum / pos_cnt.clamp(min=1.0), torch.zeros_like(lse))
+            n_valid = valid.sum().to(per_row.dtype)
+            self.dist.all_reduce(n_valid, group=self.group)
+            # mean over the valid rows of ALL ranks; x world because the caller averages the rank means
+            loss = loss + lambda_sup * per_row.sum() / n_valid.clamp(min=1) * self.world
+        return loss

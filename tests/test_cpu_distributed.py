@@ -85,6 +85,102 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_catalog(rank, world, port, q):
+    """planned lookup (loader-stage plan, step-stage row exchange) + catalogue-wide negatives with global
+    multiplicities: the per-rank losses must add up to the reference loss of the concatenated global batch and
+    the sharded gradients must be the shards of its gradient."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = importlib.import_module(PKG)
+        from oracle import embed, losses as olosses
+        sh = rs.sharded
+        F = torch.nn.functional
+        gen = torch.Generator().manual_seed(3)
+        n_rows, D, n = 41, 16, 9                              # 41 rows: not a multiple of the world size
+        full = torch.randn(n_rows, D, generator=gen)
+        shard = sh.shard_padded(full, rank, world).clone().requires_grad_(True)
+        R = sh.padded_rows(n_rows, world)
+        ok = shard.shape[0] == R
+
+        # ---- planned lookup with a leading unused row and a padding row that takes no gradient
+        g = torch.Generator().manual_seed(50 + rank)
+        ids = torch.randint(0, n_rows, (4, 5), generator=g)
+        ids[0, 0] = 0
+        plan = sh.plan_lookup(ids)
+        gather = lambda t, i: embed.gather_rows(t, i)
+
+        def scatter(gr, i, rows, pad):
+            out = torch.zeros(rows, gr.shape[1]).index_add_(0, i, gr)
+            if pad >= 0:
+                out[pad] = 0
+            return out
+        out = sh.planned_lookup(shard, plan, None, gather, scatter, lead_rows=1, pad_local_row=0 if rank == 0 else -1)
+        ok = ok and torch.equal(out[1:].detach(), full[ids.reshape(-1)]) and bool((out[0] == 0).all())
+        w = torch.randn(ids.numel() + 1, D, generator=g)
+        (out * w).sum().backward()
+        exp = torch.zeros(n_rows, D).index_add_(0, ids.reshape(-1), w[1:])
+        dist.all_reduce(exp)
+        exp[0] = 0                                            # padding row never receives gradient
+        ok = ok and torch.allclose(shard.grad, sh.shard_padded(exp, rank, world), atol=1e-6)
+
+        # ---- catalogue-wide negatives
+        U = F.normalize(torch.randn(world * n, D, generator=gen), dim=1)
+        tgt = torch.randint(1, 12, (world * n,), generator=gen)          # heavy collisions
+        uid_loc = torch.randint(0, 3, (world * n,), generator=gen)
+        uid_glob = uid_loc + (torch.arange(world * n) // n) * 1000
+        logq = torch.log(torch.rand(n_rows, generator=gen) + 1e-3)
+        sl = slice(rank * n, (rank + 1) * n)
+        u = U[sl].clone().requires_grad_(True)
+        shard2 = sh.shard_padded(full, rank, world).clone().requires_grad_(True)
+        cols = sh.CatalogColumns(n_rows, world, "cpu")
+        ok = ok and torch.equal(torch.sort(cols.col_item_ids).values, torch.arange(world * R))
+        ok = ok and torch.equal(cols.col_item_ids[cols.col_of(tgt)], tgt)
+        v_cols = sh.all_gather_rows(F.normalize(shard2, dim=1))
+        cnt = cols.counts(tgt[sl])
+        ok = ok and torch.equal(cnt[cols.col_of(torch.arange(n_rows))], torch.bincount(tgt, minlength=n_rows).float())
+        pos = cols.col_of(tgt[sl])
+        own = torch.full((n, n), -1, dtype=torch.long)
+        for i in range(n):
+            js = torch.nonzero(uid_loc[sl] == uid_loc[sl][i]).squeeze(1)
+            own[i, :js.numel()] = pos[js]
+        lq = torch.zeros(cols.n_cols)
+        lq[:n_rows] = logq
+        loss = olosses.inbatch_corrected_logq_loss_columns(u, v_cols, cols.col_item_ids, cnt, tgt[sl], pos, own, lq,
+                                                           0.1, 1.0) * (n / (world * n))
+        loss.backward()
+        Uf, Tf = U.clone().requires_grad_(True), full.clone().requires_grad_(True)
+        ref = olosses.inbatch_corrected_logq_loss(Uf, F.normalize(Tf, dim=1), tgt, uid_glob, logq, 0.1, 1.0)
+        ref.backward()
+        tot = loss.detach().clone()
+        dist.all_reduce(tot)
+        ok = ok and torch.allclose(tot, ref.detach(), atol=1e-5)
+        ok = ok and torch.allclose(u.grad, Uf.grad[sl], atol=1e-6)
+        ok = ok and torch.allclose(shard2.grad, sh.shard_padded(Tf.grad, rank, world), atol=1e-6)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_world(worker, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    return sorted(res)
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_catalog_negatives_and_planned_lookup():
+    assert _run_world(_worker_catalog) == [(0, True), (1, True)]
+
+
 @pytest.mark.timeout(180)
 def test_two_rank_gloo():
     world = 2
