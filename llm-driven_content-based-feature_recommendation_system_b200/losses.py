@@ -154,18 +154,17 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
     `own_cols[N, K]` = columns of the row's user's targets, -1 = none (None: no same-user mask)."""
     dtype = _operand_dtype(user_emb, col_rows)
     scale = 1.0 / temperature
-    u16, c16 = user_emb.to(dtype), col_rows.to(dtype)
     lq = (log_q_tensor[col_item_ids] * lambda_logq).float() if lambda_logq > 0.0 else None
     bias = -torch.log(col_counts.float())
     if lq is not None:
         bias = bias + lq
-    lse0 = fused_softmax_stats(u16, c16, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
+    lse0 = fused_softmax_stats(user_emb, col_rows, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
                                mask_value=NEG_INF, flags=L.RS_CE_NO_DIAG, dtype=dtype)[0]
-    s_pos = ops.sparse_logits(u16, c16, pos_col.view(-1, 1), scale, lq).squeeze(1)
+    s_pos = ops.sparse_logits(user_emb, col_rows, pos_col.view(-1, 1), scale, lq, compute_dtype=dtype).squeeze(1)
     mx = torch.maximum(lse0, s_pos).detach()
     z = torch.exp(lse0 - mx) + torch.exp(s_pos - mx)
     if own_cols is not None and own_cols.shape[1] > 0:
-        s_own = ops.sparse_logits(u16, c16, own_cols, scale, lq, target_ids, col_item_ids)
+        s_own = ops.sparse_logits(user_emb, col_rows, own_cols, scale, lq, target_ids, col_item_ids, compute_dtype=dtype)
         z = z - torch.exp(s_own - mx.unsqueeze(1)).sum(dim=1)
     lse = mx + torch.log(z.clamp_min(1e-30))
     return (lse - s_pos).mean()

@@ -718,23 +718,29 @@ def retrieve_topk(user_emb: Tensor, item_emb: Tensor, k: int, mask_index0: bool 
 
 class _SparseLogits(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, idx, scale, bias, key_row, key_col):
-        ctx.save_for_backward(a, b, idx, key_row, key_col)
-        ctx.scale = scale
-        return torch.ops.rs.sparse_logits(a, b, idx, scale, bias, key_row, key_col)
+    def forward(ctx, a, b, idx, scale, bias, key_row, key_col, compute_dtype):
+        # operands are rounded to `compute_dtype` here (not by the caller) so that the gradients come back in the
+        # callers' dtype (fp32) instead of being rounded to 16 bits on their way through a cast node
+        ac = a.detach() if compute_dtype is None else a.detach().to(compute_dtype)
+        bc = b.detach() if compute_dtype is None else b.detach().to(compute_dtype)
+        ctx.save_for_backward(ac, bc, idx, key_row, key_col)
+        ctx.meta = (scale, a.dtype, b.dtype)
+        return torch.ops.rs.sparse_logits(ac, bc, idx, scale, bias, key_row, key_col)
 
     @staticmethod
     def backward(ctx, g):
         a, b, idx, key_row, key_col = ctx.saved_tensors
-        d_a, d_b = torch.ops.rs.sparse_logits_bwd(a, b, idx, ctx.scale, key_row, key_col, g.float().contiguous())
-        return d_a.to(a.dtype), d_b.to(b.dtype), None, None, None, None, None
+        scale, adt, bdt = ctx.meta
+        d_a, d_b = torch.ops.rs.sparse_logits_bwd(a, b, idx, scale, key_row, key_col, g.float().contiguous())
+        return d_a.to(adt), d_b.to(bdt), None, None, None, None, None, None
 
 
-def sparse_logits(a, b, idx, scale, bias=None, key_row=None, key_col=None):
-    """out[i,c] = scale*<a_i, b_idx[i,c]> - bias[idx[i,c]]  (-inf for idx < 0 or equal keys); differentiable in a, b."""
+def sparse_logits(a, b, idx, scale, bias=None, key_row=None, key_col=None, compute_dtype=None):
+    """out[i,c] = scale*<a_i, b_idx[i,c]> - bias[idx[i,c]]  (-inf for idx < 0 or equal keys); differentiable in a, b.
+    `compute_dtype`: round the operands to this dtype first (to match a tensor-core pass over the same operands)."""
     if bias is not None:
         bias = bias.detach().float().contiguous()
-    return _SparseLogits.apply(a, b, idx, float(scale), bias, key_row, key_col)
+    return _SparseLogits.apply(a, b, idx, float(scale), bias, key_row, key_col, compute_dtype)
 
 
 def mine_hard_negatives(u, v, key, k, hnm_threshold):

@@ -113,8 +113,14 @@ class SASRecUserTower(nn.Module):
         seq_emb = self.embed_front(pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids,
                                    section_ids, item_id_rows)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
+        # is_causal=True only tells nn.TransformerEncoder not to PROBE the mask: with is_causal=None it compares the
+        # mask with a generated causal one and reads the verdict back (`bool((mask == causal).all())`,
+        # torch/nn/modules/transformer.py:_detect_is_causal_mask) -- one device->host synchronisation per forward.
+        # The arithmetic is unchanged: with a key-padding mask present, multi_head_attention_forward merges both
+        # masks and drops the hint (torch/nn/functional.py), exactly the path the reference's call takes.
         output = self.transformer_encoder(seq_emb, mask=self.get_causal_mask(seq_len, item_ids.device),
-                                          src_key_padding_mask=padding_mask)
+                                          src_key_padding_mask=padding_mask,
+                                          is_causal=True if padding_mask is not None else None)
         static_input = self.static_front(age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids,
                                          club_status_ids, news_freq_ids, fn_ids, active_ids, cont_feats)
         user_profile_vec = self.static_mlp(static_input)
