@@ -177,6 +177,44 @@ int rs_masked_mean_fwd(const void* feats, int feats_dtype, const int64_t* mask, 
 int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, int64_t T, int64_t dim,
                        void* d_feats, int d_feats_dtype, void* stream);
 
+/* ----------------------------------- sequence encoder on packed valid tokens */
+
+/* The reference runs nn.TransformerEncoder over the padded [B, L] grid with a causal + key-padding mask
+ * (tower_code/v1_refine_usertower.py:343-352, :458-466).  Valid positions only ever attend to valid positions of
+ * their own sequence and the rest of the layer is position-wise, so the encoder runs on the PACKED valid tokens
+ * [T, 128]; cu_seqlens[n_seq+1] (int32) delimits the sequences.  The matmuls stay library GEMMs (nn.Linear in the
+ * reference as well); these entry points are everything between them.  Dropout masks come from a counter-based hash
+ * of (seed, element): nothing is stored, the backward re-derives them from the same seed.
+ *
+ * Causal attention for sequences of <= 64 tokens, head_dim == 32, straight from the packed in_proj output
+ * qkv[T, 3, H, 32] (q | k | v, heads contiguous -- nn.MultiheadAttention's layout): out[T, H*32], lse[T, H].
+ * Replaces the head transposes, the [B,H,L,L] merged-mask tensor, F.scaled_dot_product_attention and its dropout. */
+int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens,
+                       int n_heads, int head_dim, int max_len, float scale, float dropout_p, uint64_t seed,
+                       void* out, float* lse, void* stream);
+int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* lse,
+                       const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads, int head_dim,
+                       int max_len, float scale, float dropout_p, uint64_t seed, void* d_qkv, void* stream);
+/* y[r,:] = dropout(LayerNorm(x[index ? index[r] : r, :])), dim == 128, fp32 statistics (mean/rstd[n_rows] saved).
+ * `index` packs the valid rows of the padded grid on the way in (emb_ln, :458-459).  Backward: dx[index[r]] (rows
+ * that are not indexed are left untouched: pass a zeroed buffer), dw/db[128] reduced in a fixed order. */
+int rs_ln_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, int64_t dim, const float* w,
+              const float* b, float eps, float dropout_p, uint64_t seed, void* y, int y_dtype, float* mean,
+              float* rstd, void* stream);
+size_t rs_ln_bwd_workspace_bytes(int64_t n_rows);
+int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const int64_t* index, int64_t n_rows,
+              int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p, uint64_t seed,
+              void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+/* out = x + dropout(y) (n elements, n % 4 == 0); backward of the y branch: dy = mask(g) / keep */
+int rs_dropout_add_fwd(const void* x, int x_dtype, const void* y, int y_dtype, int64_t n, float dropout_p,
+                       uint64_t seed, void* out, void* stream);
+int rs_dropout_bwd(const void* g, int g_dtype, int64_t n, float dropout_p, uint64_t seed, void* dy, int dy_dtype,
+                   void* stream);
+/* out = dropout(gelu(z)), exact erf GELU (activation="gelu"); backward dz = mask(g)/keep * gelu'(z) */
+int rs_gelu_dropout_fwd(const void* z, int dtype, int64_t n, float dropout_p, uint64_t seed, void* out, void* stream);
+int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, int64_t n, float dropout_p, uint64_t seed, void* dz,
+                        void* stream);
+
 /* -------------------------------------------- C1..C5: fused in-batch softmax */
 
 /* One pass over S = scale * (A @ B^T) - col_bias, [M,N], never written to memory:

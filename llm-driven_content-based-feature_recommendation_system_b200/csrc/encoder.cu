@@ -1,0 +1,601 @@
+// Sequence-encoder body on PACKED valid tokens (U-rows' caller: tower_code/v1_refine_usertower.py:458-466).
+//
+// The reference runs nn.TransformerEncoder over the padded [B, L=50] grid with a causal + key-padding mask.  A
+// valid position only ever attends to valid positions of its own sequence, and everything else in the layer is
+// position-wise, so the valid rows of the output are a function of the valid rows alone: here the encoder runs on
+// the ~25 % of the grid that is not padding (packed, `cu_seqlens` delimits the sequences).  The matmuls stay
+// library GEMMs (stock nn.Linear in the reference as well); these kernels are the glue around them:
+//
+//   attn_fwd / attn_bwd      causal softmax(QK^T/sqrt(d))V for sequences of <= 64 tokens, head_dim 32, straight from
+//                            the packed in_proj output [T, 3, H, 32] (no head transposes, no [B,H,L,L] bias tensor,
+//                            no stored probabilities: the backward recomputes them from the saved row log-sum-exp);
+//                            attention dropout from a counter-based hash (no mask tensor)
+//   ln_fwd / ln_bwd          LayerNorm(128) with fp32 statistics, optional row gather (packing) on the way in,
+//                            optional dropout on the way out, 16-bit or fp32 output
+//   dropout_add fwd / bwd    x + dropout(y)            (residual stream stays fp32 as under the reference's autocast)
+//   gelu_dropout fwd / bwd   dropout(gelu(z))
+//
+// All of it is HBM-bound row streaming: one warp per row / per (sequence, head), 128-bit accesses.
+#include "common.cuh"
+#include "../../include/rs_twotower.h"
+
+namespace rs {
+
+#define ENC_HD 32          // head dim
+#define ENC_D 128          // model dim of the row kernels
+
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+  return h;
+}
+// 32 uniform bits for element (a, b) of the stream `seed` (two rounds of an avalanche hash: ample for dropout)
+__device__ __forceinline__ uint32_t rnd32(uint64_t seed, uint32_t a, uint32_t b) {
+  uint32_t h = mix32(a * 0x9E3779B1u + (uint32_t)seed);
+  return mix32(h ^ (b * 0x85EBCA77u + (uint32_t)(seed >> 32)));
+}
+
+template <int DT> __device__ __forceinline__ float4 ld4(const void* base, int64_t off) {
+  if constexpr (DT == RS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+  else {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off));
+    float2 a, b;
+    if constexpr (DT == RS_BF16) { a = unpack_bf16(u.x); b = unpack_bf16(u.y); }
+    else { a = unpack_f16(u.x); b = unpack_f16(u.y); }
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+template <int DT> __device__ __forceinline__ void st4(void* base, int64_t off, float4 v) {
+  if constexpr (DT == RS_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v;
+  else {
+    uint2 u;
+    if constexpr (DT == RS_BF16) { u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w); }
+    else { u.x = pack_f16(v.x, v.y); u.y = pack_f16(v.z, v.w); }
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + off) = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+struct AttnParams {
+  const int* cu;            // [n_seq + 1] token offsets
+  int64_t n_seq;
+  int H, max_len;
+  float scale;
+  uint32_t drop_thresh;     // keep iff rnd32 >= thresh   (0: no dropout)
+  float inv_keep;
+  uint64_t seed;
+};
+
+// stage `which` (0 = q, 1 = k, 2 = v) rows of one (sequence, head) into shared memory as fp32 [len][32]
+template <int DT>
+__device__ __forceinline__ void stage_rows(float* dst, const void* src, int64_t row0, int len, int64_t row_stride,
+                                           int64_t col0, int lane) {
+  const int sub = lane >> 3, d4 = (lane & 7) * 4;
+  for (int j = sub; j < len; j += 4)
+    *reinterpret_cast<float4*>(dst + j * ENC_HD + d4) = ld4<DT>(src, (row0 + j) * row_stride + col0 + d4);
+}
+
+template <int DT>
+__device__ __forceinline__ void load_row32(float (&r)[ENC_HD], const void* src, int64_t off) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = ld4<DT>(src, off + 4 * q);
+    r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+  }
+}
+__device__ __forceinline__ float dot_row32(const float (&r)[ENC_HD], const float* s) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
+    a0 = fmaf(r[4 * q], v.x, a0); a1 = fmaf(r[4 * q + 1], v.y, a1);
+    a2 = fmaf(r[4 * q + 2], v.z, a2); a3 = fmaf(r[4 * q + 3], v.w, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ void axpy_row32(float (&acc)[ENC_HD], float a, const float* s) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
+    acc[4 * q] = fmaf(a, v.x, acc[4 * q]); acc[4 * q + 1] = fmaf(a, v.y, acc[4 * q + 1]);
+    acc[4 * q + 2] = fmaf(a, v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a, v.w, acc[4 * q + 3]);
+  }
+}
+template <int DT>
+__device__ __forceinline__ void store_row32(void* dst, int64_t off, const float (&r)[ENC_HD], float s) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    st4<DT>(dst, off + 4 * q, make_float4(r[4 * q] * s, r[4 * q + 1] * s, r[4 * q + 2] * s, r[4 * q + 3] * s));
+}
+
+// one warp per (sequence, head); lane = query row (two rows per lane when the sequence is longer than 32)
+template <int DT>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const void* __restrict__ qkv, AttnParams p,
+                                                       void* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  float* sK = smem + (size_t)warp * 2 * p.max_len * ENC_HD;
+  float* sV = sK + p.max_len * ENC_HD;
+  const int64_t n_items = p.n_seq * p.H;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
+    const int64_t b = item / p.H;
+    const int h = (int)(item % p.H);
+    const int64_t t0 = __ldg(p.cu + b);
+    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    stage_rows<DT>(sK, qkv, t0, len, rs_, os_ + h * ENC_HD, lane);
+    stage_rows<DT>(sV, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, lane);
+    __syncwarp();
+    for (int r0 = 0; r0 < len; r0 += 32) {
+      const int i = r0 + lane;
+      const bool act = i < len;
+      float q[ENC_HD], acc[ENC_HD];
+      if (act) load_row32<DT>(q, qkv, (t0 + i) * rs_ + h * ENC_HD);
+#pragma unroll
+      for (int d = 0; d < ENC_HD; ++d) acc[d] = 0.f;
+      float m = -INFINITY, l = 0.f;
+      const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
+      const int jmax = min(len - 1, r0 + 31);
+      for (int j = 0; j <= jmax; ++j) {
+        if (act && j <= i) {
+          const float s = dot_row32(q, sK + j * ENC_HD) * p.scale;
+          if (s > m) {
+            const float c = __expf(m - s);
+            l *= c;
+#pragma unroll
+            for (int d = 0; d < ENC_HD; ++d) acc[d] *= c;
+            m = s;
+          }
+          const float pr = __expf(s - m);
+          l += pr;
+          float pk = pr;
+          if (p.drop_thresh) pk = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? pr * p.inv_keep : 0.f;
+          axpy_row32(acc, pk, sV + j * ENC_HD);
+        }
+      }
+      if (act) {
+        store_row32<DT>(out, (t0 + i) * os_ + h * ENC_HD, acc, 1.f / l);
+        lse[(t0 + i) * p.H + h] = m + __logf(l);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// backward: dQ with lane = query row (K, V staged), then dK / dV with lane = key row (Q, dO staged)
+template <int DT>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                                       const void* __restrict__ out, const float* __restrict__ lse,
+                                                       AttnParams p, void* __restrict__ d_qkv) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int per_warp = 2 * p.max_len * ENC_HD + 2 * p.max_len;
+  float* sA = smem + (size_t)warp * per_warp;           // K, then Q
+  float* sB = sA + p.max_len * ENC_HD;                  // V, then dO
+  float* sLse = sB + p.max_len * ENC_HD;
+  float* sDelta = sLse + p.max_len;
+  const int64_t n_items = p.n_seq * p.H;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
+    const int64_t b = item / p.H;
+    const int h = (int)(item % p.H);
+    const int64_t t0 = __ldg(p.cu + b);
+    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    // row statistics: lse_i and delta_i = <dO_i, O_i>  (8 lanes per row)
+    {
+      const int sub = lane >> 3, d4 = (lane & 7) * 4;
+      for (int j0 = 0; j0 < len; j0 += 4) {
+        const int j = j0 + sub;
+        float part = 0.f;
+        if (j < len) part = dot4(ld4<DT>(d_out, (t0 + j) * os_ + h * ENC_HD + d4), ld4<DT>(out, (t0 + j) * os_ + h * ENC_HD + d4));
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        if (j < len && (lane & 7) == 0) { sDelta[j] = part; sLse[j] = __ldg(lse + (t0 + j) * p.H + h); }
+      }
+    }
+    stage_rows<DT>(sA, qkv, t0, len, rs_, os_ + h * ENC_HD, lane);        // K
+    stage_rows<DT>(sB, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, lane);    // V
+    __syncwarp();
+    // ---- pass A: dQ_i = scale * sum_{j<=i} dS_ij K_j
+    for (int r0 = 0; r0 < len; r0 += 32) {
+      const int i = r0 + lane;
+      const bool act = i < len;
+      float q[ENC_HD], g[ENC_HD], dq[ENC_HD];
+      if (act) {
+        load_row32<DT>(q, qkv, (t0 + i) * rs_ + h * ENC_HD);
+        load_row32<DT>(g, d_out, (t0 + i) * os_ + h * ENC_HD);
+      }
+#pragma unroll
+      for (int d = 0; d < ENC_HD; ++d) dq[d] = 0.f;
+      const float li = act ? sLse[i] : 0.f, di = act ? sDelta[i] : 0.f;
+      const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
+      const int jmax = min(len - 1, r0 + 31);
+      for (int j = 0; j <= jmax; ++j) {
+        if (act && j <= i) {
+          const float pr = __expf(dot_row32(q, sA + j * ENC_HD) * p.scale - li);
+          float dp = dot_row32(g, sB + j * ENC_HD);
+          if (p.drop_thresh) dp = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? dp * p.inv_keep : 0.f;
+          axpy_row32(dq, pr * (dp - di), sA + j * ENC_HD);
+        }
+      }
+      if (act) store_row32<DT>(d_qkv, (t0 + i) * rs_ + h * ENC_HD, dq, p.scale);
+    }
+    __syncwarp();
+    stage_rows<DT>(sA, qkv, t0, len, rs_, h * ENC_HD, lane);              // Q
+    stage_rows<DT>(sB, d_out, t0, len, os_, h * ENC_HD, lane);            // dO
+    __syncwarp();
+    // ---- pass B: dK_j = scale * sum_{i>=j} dS_ij Q_i,  dV_j = sum_{i>=j} P~_ij dO_i
+    for (int r0 = 0; r0 < len; r0 += 32) {
+      const int j = r0 + lane;
+      const bool act = j < len;
+      float k[ENC_HD], v[ENC_HD], dk[ENC_HD], dv[ENC_HD];
+      if (act) {
+        load_row32<DT>(k, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD);
+        load_row32<DT>(v, qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD);
+      }
+#pragma unroll
+      for (int d = 0; d < ENC_HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+      for (int i = r0; i < len; ++i) {
+        if (act && i >= j) {
+          const float pr = __expf(dot_row32(k, sA + i * ENC_HD) * p.scale - sLse[i]);
+          float dp = dot_row32(v, sB + i * ENC_HD);
+          float pk = pr;
+          if (p.drop_thresh) {
+            const bool keep = rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh;
+            dp = keep ? dp * p.inv_keep : 0.f;
+            pk = keep ? pr * p.inv_keep : 0.f;
+          }
+          axpy_row32(dv, pk, sB + i * ENC_HD);
+          axpy_row32(dk, pr * (dp - sDelta[i]), sA + i * ENC_HD);
+        }
+      }
+      if (act) {
+        store_row32<DT>(d_qkv, (t0 + j) * rs_ + os_ + h * ENC_HD, dk, p.scale);
+        store_row32<DT>(d_qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD, dv, 1.f);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm(128)
+// y[r] = dropout(LN(x[index ? index[r] : r])) ; one warp per row, lane owns 4 consecutive features
+template <int DTI, int DTO>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, const int64_t* __restrict__ index,
+                                                     int64_t n_rows, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float eps, uint32_t drop_thresh,
+                                                     float inv_keep, uint64_t seed, void* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w4 = ldg_f4(w + 4 * lane), b4 = ldg_f4(bias + 4 * lane);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const int64_t src = index ? __ldg(index + r) : r;
+    const float4 v = ld4<DTI>(x, src * ENC_D + 4 * lane);
+    const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / ENC_D);
+    const float4 c = make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu);
+    const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / ENC_D);
+    const float rs = rsqrtf(var + eps);
+    float4 o = make_float4(c.x * rs * w4.x + b4.x, c.y * rs * w4.y + b4.y, c.z * rs * w4.z + b4.z, c.w * rs * w4.w + b4.w);
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      const uint32_t h = rnd32(seed, e, 0x5bd1e995u);
+      // four keep decisions from four byte-rotations of one hash would correlate: draw four hashes
+      o.x = (h >= drop_thresh) ? o.x * inv_keep : 0.f;
+      o.y = (rnd32(seed, e, 1u) >= drop_thresh) ? o.y * inv_keep : 0.f;
+      o.z = (rnd32(seed, e, 2u) >= drop_thresh) ? o.z * inv_keep : 0.f;
+      o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
+    }
+    st4<DTO>(y, r * ENC_D + 4 * lane, o);
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+// dx[index ? index[r] : r] = LN backward of dy[r] (dropout mask re-derived); per-CTA partial dw / db
+template <int DTI, int DTO>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+                                                     const int64_t* __restrict__ index, int64_t n_rows,
+                                                     const float* __restrict__ w, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, uint32_t drop_thresh,
+                                                     float inv_keep, uint64_t seed, void* __restrict__ dx,
+                                                     float* __restrict__ part /*[grid][2][128]*/) {
+  __shared__ float4 red[2][8][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w4 = ldg_f4(w + 4 * lane);
+  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const int64_t src = index ? __ldg(index + r) : r;
+    const float4 v = ld4<DTI>(x, src * ENC_D + 4 * lane);
+    float4 g = ld4<DTO>(dy, r * ENC_D + 4 * lane);
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      g.x = (rnd32(seed, e, 0x5bd1e995u) >= drop_thresh) ? g.x * inv_keep : 0.f;
+      g.y = (rnd32(seed, e, 1u) >= drop_thresh) ? g.y * inv_keep : 0.f;
+      g.z = (rnd32(seed, e, 2u) >= drop_thresh) ? g.z * inv_keep : 0.f;
+      g.w = (rnd32(seed, e, 3u) >= drop_thresh) ? g.w * inv_keep : 0.f;
+    }
+    const float mu = mean[r], rs = rstd[r];
+    const float4 xh = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+    dw.x += g.x * xh.x; dw.y += g.y * xh.y; dw.z += g.z * xh.z; dw.w += g.w * xh.w;
+    db.x += g.x; db.y += g.y; db.z += g.z; db.w += g.w;
+    const float4 gw = make_float4(g.x * w4.x, g.y * w4.y, g.z * w4.z, g.w * w4.w);
+    const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
+    const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
+    st4<DTI>(dx, src * ENC_D + 4 * lane,
+             make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
+                         rs * (gw.w - m1 - xh.w * m2)));
+  }
+  red[0][wib][lane] = dw;
+  red[1][wib][lane] = db;
+  __syncthreads();
+  if (wib < 2) {                                   // warp 0 folds dw, warp 1 folds db, in a fixed order
+    float4 s = red[wib][0][lane];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      const float4 t = red[wib][k][lane];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * ENC_D + 4 * lane) = s;
+  }
+}
+
+// out[k][c] = sum_b part[b][k][c]   (fixed order: deterministic)
+__global__ void colsum_finalize_kernel(const float* __restrict__ part, int n_blocks, int n_cols, float* __restrict__ out0,
+                                       float* __restrict__ out1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * n_cols) return;
+  float s = 0.f;
+  for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * 2 * n_cols + c];
+  if (c < n_cols) out0[c] = s; else if (out1) out1[c - n_cols] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+// out = x + dropout(y)     x, out fp32 (or DTX), y DTY
+template <int DTX, int DTY>
+__global__ void __launch_bounds__(256) dropout_add_fwd_kernel(const void* __restrict__ x, const void* __restrict__ y,
+                                                              int64_t n4, uint32_t drop_thresh, float inv_keep,
+                                                              uint64_t seed, void* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = ld4<DTX>(x, 4 * i);
+    float4 b = ld4<DTY>(y, 4 * i);
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)i;
+      b.x = (rnd32(seed, e, 0u) >= drop_thresh) ? b.x * inv_keep : 0.f;
+      b.y = (rnd32(seed, e, 1u) >= drop_thresh) ? b.y * inv_keep : 0.f;
+      b.z = (rnd32(seed, e, 2u) >= drop_thresh) ? b.z * inv_keep : 0.f;
+      b.w = (rnd32(seed, e, 3u) >= drop_thresh) ? b.w * inv_keep : 0.f;
+    }
+    st4<DTX>(out, 4 * i, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+  }
+}
+// dy = dropout_mask(g)     g DTX (fp32), dy DTY
+template <int DTX, int DTY>
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const void* __restrict__ g, int64_t n4, uint32_t drop_thresh,
+                                                          float inv_keep, uint64_t seed, void* __restrict__ dy) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 b = ld4<DTX>(g, 4 * i);
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)i;
+      b.x = (rnd32(seed, e, 0u) >= drop_thresh) ? b.x * inv_keep : 0.f;
+      b.y = (rnd32(seed, e, 1u) >= drop_thresh) ? b.y * inv_keep : 0.f;
+      b.z = (rnd32(seed, e, 2u) >= drop_thresh) ? b.z * inv_keep : 0.f;
+      b.w = (rnd32(seed, e, 3u) >= drop_thresh) ? b.w * inv_keep : 0.f;
+    }
+    st4<DTY>(dy, 4 * i, b);
+  }
+}
+
+template <int DT> __device__ __forceinline__ float round_dt(float x) {
+  if constexpr (DT == RS_BF16) return __bfloat162float(__float2bfloat16_rn(x));
+  else if constexpr (DT == RS_F16) return __half2float(__float2half_rn(x));
+  else return x;
+}
+
+// exact (erf) GELU, as nn.TransformerEncoderLayer(activation="gelu") -> F.gelu(approximate="none")
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float z) {
+  return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+}
+// out = dropout(gelu(z)) ; BWD: dz = dropout_mask(g) * gelu'(z)
+template <int DT, bool BWD>
+__global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restrict__ z, const void* __restrict__ g,
+                                                           int64_t n4, uint32_t drop_thresh, float inv_keep,
+                                                           uint64_t seed, void* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = ld4<DT>(z, 4 * i);
+    float4 o;
+    if (BWD) {
+      const float4 gg = ld4<DT>(g, 4 * i);
+      o = make_float4(gg.x * gelu_grad_f(a.x), gg.y * gelu_grad_f(a.y), gg.z * gelu_grad_f(a.z), gg.w * gelu_grad_f(a.w));
+    } else {
+      // the reference's gelu output is rounded to the activation dtype BEFORE its dropout scales it: do the same
+      o = make_float4(round_dt<DT>(gelu_f(a.x)), round_dt<DT>(gelu_f(a.y)), round_dt<DT>(gelu_f(a.z)),
+                      round_dt<DT>(gelu_f(a.w)));
+    }
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)i;
+      o.x = (rnd32(seed, e, 0u) >= drop_thresh) ? o.x * inv_keep : 0.f;
+      o.y = (rnd32(seed, e, 1u) >= drop_thresh) ? o.y * inv_keep : 0.f;
+      o.z = (rnd32(seed, e, 2u) >= drop_thresh) ? o.z * inv_keep : 0.f;
+      o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
+    }
+    st4<DT>(out, 4 * i, o);
+  }
+}
+
+static inline void drop_consts(float p, uint32_t& thresh, float& inv_keep) {
+  if (p <= 0.f) { thresh = 0u; inv_keep = 1.f; return; }
+  double t = (double)p * 4294967296.0;
+  if (t < 1.0) t = 1.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  thresh = (uint32_t)t;
+  inv_keep = 1.f / (1.f - p);
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+#define ENC_DISPATCH1(dt, NAME, ...)                                    \
+  switch (dt) {                                                         \
+    case RS_F32: { constexpr int NAME = RS_F32; __VA_ARGS__; break; }   \
+    case RS_F16: { constexpr int NAME = RS_F16; __VA_ARGS__; break; }   \
+    case RS_BF16: { constexpr int NAME = RS_BF16; __VA_ARGS__; break; } \
+    default: return RS_ERR_BAD_ARG;                                     \
+  }
+
+static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, float p) {
+  if (n_seq <= 0 || total < 0 || H <= 0 || max_len <= 0) return RS_ERR_BAD_ARG;
+  if (hd != ENC_HD || max_len > 64) return RS_ERR_UNSUPPORTED;
+  if (p < 0.f || p >= 1.f) return RS_ERR_BAD_ARG;
+  if (total * H >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;      // dropout stream index is 32 bits
+  return RS_OK;
+}
+
+extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int64_t n_seq,
+                                  int64_t total_tokens, int n_heads, int head_dim, int max_len, float scale,
+                                  float dropout_p, uint64_t seed, void* out, float* lse, void* stream) {
+  int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p);
+  if (rc != RS_OK) return rc;
+  if (total_tokens == 0) return RS_OK;
+  if (!qkv || !cu_seqlens || !out || !lse) return RS_ERR_BAD_ARG;
+  AttnParams p;
+  p.cu = cu_seqlens; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
+  drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
+  const size_t smem = (size_t)4 * 2 * max_len * ENC_HD * sizeof(float);
+  const int grid = grid_for_warps(n_seq * n_heads, 4, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  ENC_DISPATCH1(dtype, DT, {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_fwd_kernel<DT><<<grid, 128, smem, st>>>(qkv, p, out, lse);
+  });
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* lse,
+                                  const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads,
+                                  int head_dim, int max_len, float scale, float dropout_p, uint64_t seed, void* d_qkv,
+                                  void* stream) {
+  int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p);
+  if (rc != RS_OK) return rc;
+  if (total_tokens == 0) return RS_OK;
+  if (!qkv || !d_out || !out || !lse || !cu_seqlens || !d_qkv) return RS_ERR_BAD_ARG;
+  AttnParams p;
+  p.cu = cu_seqlens; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
+  drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
+  const size_t smem = (size_t)4 * (2 * max_len * ENC_HD + 2 * max_len) * sizeof(float);
+  const int grid = grid_for_warps(n_seq * n_heads, 4, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  ENC_DISPATCH1(dtype, DT, {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_bwd_kernel<DT><<<grid, 128, smem, st>>>(qkv, d_out, out, lse, p, d_qkv);
+  });
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+#define LN_GRID_CAP (RS_NUM_SMS * 8)
+static int ln_grid(int64_t n_rows) { return grid_for_warps(n_rows, 8, 8); }
+
+extern "C" size_t rs_ln_bwd_workspace_bytes(int64_t n_rows) { return (size_t)ln_grid(n_rows) * 2 * ENC_D * sizeof(float); }
+
+extern "C" int rs_ln_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, int64_t dim, const float* w,
+                         const float* b, float eps, float dropout_p, uint64_t seed, void* y, int y_dtype, float* mean,
+                         float* rstd, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!x || !w || !b || !y || !mean || !rstd || n_rows < 0) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (n_rows * (ENC_D / 4) >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(y_dtype, DTO, (ln_fwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
+      x, index, n_rows, w, b, eps, th, ik, seed, y, mean, rstd))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const int64_t* index, int64_t n_rows,
+                         int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p,
+                         uint64_t seed, void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || !workspace) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_ln_bwd_workspace_bytes(n_rows)) return RS_ERR_WORKSPACE;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  float* part = (float*)workspace;
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dy_dtype, DTO, (ln_bwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
+      dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, part))));
+  RS_LAUNCH_CHECK();
+  colsum_finalize_kernel<<<1, 2 * ENC_D, 0, st>>>(part, grid, ENC_D, dw, db);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+static int ew_grid(int64_t n4) {
+  int64_t g = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)RS_NUM_SMS * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int rs_dropout_add_fwd(const void* x, int x_dtype, const void* y, int y_dtype, int64_t n, float dropout_p,
+                                  uint64_t seed, void* out, void* stream) {
+  if (n == 0) return RS_OK;
+  if (!x || !y || !out || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  if (n / 4 >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  ENC_DISPATCH1(x_dtype, DTX, ENC_DISPATCH1(y_dtype, DTY, (dropout_add_fwd_kernel<DTX, DTY><<<ew_grid(n / 4), 256, 0, st>>>(
+      x, y, n / 4, th, ik, seed, out))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_dropout_bwd(const void* g, int g_dtype, int64_t n, float dropout_p, uint64_t seed, void* dy,
+                              int dy_dtype, void* stream) {
+  if (n == 0) return RS_OK;
+  if (!g || !dy || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  ENC_DISPATCH1(g_dtype, DTX, ENC_DISPATCH1(dy_dtype, DTY, (dropout_bwd_kernel<DTX, DTY><<<ew_grid(n / 4), 256, 0, st>>>(
+      g, n / 4, th, ik, seed, dy))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_gelu_dropout_fwd(const void* z, int dtype, int64_t n, float dropout_p, uint64_t seed, void* out,
+                                   void* stream) {
+  if (n == 0) return RS_OK;
+  if (!z || !out || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  if (n / 4 >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, false><<<ew_grid(n / 4), 256, 0, st>>>(z, nullptr, n / 4, th, ik, seed, out)));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, int64_t n, float dropout_p, uint64_t seed,
+                                   void* dz, void* stream) {
+  if (n == 0) return RS_OK;
+  if (!z || !g || !dz || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, true><<<ew_grid(n / 4), 256, 0, st>>>(z, g, n / 4, th, ik, seed, dz)));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}

@@ -1,0 +1,289 @@
+"""The sequence-encoder body of SASRecUserTower on PACKED valid tokens.
+
+Reference: `nn.TransformerEncoder(nn.TransformerEncoderLayer(d_model=128, nhead=4, dim_feedforward=256,
+dropout=0.2, activation="gelu", norm_first=True, batch_first=True), num_layers=2)` called with a causal mask and
+`src_key_padding_mask` over the left-padded [B, L=50] grid (tower_code/v1_refine_usertower.py:343-352, :458-466).
+
+A valid position attends only to valid positions of its own sequence and the rest of the layer is position-wise, so
+the valid rows of the output depend on the valid rows alone.  `packed_encoder` therefore runs the SAME layers (same
+parameters -- the nn.TransformerEncoder module stays the owner, state-dict names unchanged) on the packed valid
+tokens [T, 128] (T ~ 25 % of B*L on H&M-shaped batches), delimited by `cu_seqlens`:
+
+    h   = LN1(x)                                    rs::ln            (fp32 stats, activation-dtype output)
+    qkv = in_proj(h)                                library GEMM (nn.Linear in the reference as well)
+    o   = causal softmax(q k^T / sqrt(32)) v        rs::attn_varlen   (short-sequence kernel, dropout inside)
+    x   = x + dropout(out_proj(o))                  GEMM + rs::dropout_add   (residual stream stays fp32)
+    f   = dropout(gelu(linear1(LN2(x))))            rs::ln, GEMM, rs::gelu_dropout
+    x   = x + dropout(linear2(f))                   GEMM + rs::dropout_add
+
+Values at valid positions equal the reference's in eval mode (tests/test_gpu_encoder.py); in train mode the dropout
+masks come from a counter-based hash instead of Philox (same Bernoulli(1-p)/(1-p) law, different stream).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+
+_lib = L.load()
+
+
+def _seed() -> int:
+    """A fresh 62-bit seed from torch's CPU generator (host-side: no device synchronisation; reproducible under
+    torch.manual_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+# ------------------------------------------------------------------------------------------------ custom ops
+@torch.library.custom_op("rs::attn_varlen", mutates_args=())
+def attn_varlen_op(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, scale: float, dropout_p: float,
+                   seed: int) -> List[Tensor]:
+    L.require_cuda(qkv, cu_seqlens)
+    qkv = qkv.contiguous()
+    T = qkv.shape[0]
+    hd = qkv.shape[1] // (3 * n_heads)
+    out = torch.empty(T, n_heads * hd, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(T, n_heads, dtype=torch.float32, device=qkv.device)
+    L.check(_lib.rs_attn_varlen_fwd(L.ptr(qkv), L.dt(qkv), L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T, n_heads, hd,
+                                    max_len, scale, dropout_p, seed, L.ptr(out), L.ptr(lse), L.stream()),
+            "rs_attn_varlen_fwd")
+    return [out, lse]
+
+
+@attn_varlen_op.register_fake
+def _(qkv, cu_seqlens, n_heads, max_len, scale, dropout_p, seed):
+    return [qkv.new_empty(qkv.shape[0], qkv.shape[1] // 3), qkv.new_empty(qkv.shape[0], n_heads, dtype=torch.float32)]
+
+
+@torch.library.custom_op("rs::attn_varlen_bwd", mutates_args=())
+def attn_varlen_bwd_op(qkv: Tensor, d_out: Tensor, out: Tensor, lse: Tensor, cu_seqlens: Tensor, n_heads: int,
+                       max_len: int, scale: float, dropout_p: float, seed: int) -> Tensor:
+    d_out = d_out.to(qkv.dtype).contiguous()
+    T = qkv.shape[0]
+    hd = qkv.shape[1] // (3 * n_heads)
+    d_qkv = torch.empty_like(qkv)
+    L.check(_lib.rs_attn_varlen_bwd(L.ptr(qkv), L.ptr(d_out), L.ptr(out), L.dt(qkv), L.ptr(lse), L.ptr(cu_seqlens),
+                                    cu_seqlens.numel() - 1, T, n_heads, hd, max_len, scale, dropout_p, seed,
+                                    L.ptr(d_qkv), L.stream()), "rs_attn_varlen_bwd")
+    return d_qkv
+
+
+@attn_varlen_bwd_op.register_fake
+def _(qkv, d_out, out, lse, cu_seqlens, n_heads, max_len, scale, dropout_p, seed):
+    return torch.empty_like(qkv)
+
+
+@torch.library.custom_op("rs::ln", mutates_args=())
+def ln_op(x: Tensor, index: Optional[Tensor], w: Tensor, b: Tensor, eps: float, dropout_p: float, seed: int,
+          out_dtype: int) -> List[Tensor]:
+    L.require_cuda(x, w, b)
+    x = x.contiguous()
+    n = x.shape[0] if index is None else index.numel()
+    y = torch.empty(n, x.shape[1], dtype=L.torch_dtype(out_dtype), device=x.device)
+    mean = torch.empty(n, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+    L.check(_lib.rs_ln_fwd(L.ptr(x), L.dt(x), L.ptr(index), n, x.shape[1], L.ptr(w), L.ptr(b), eps, dropout_p, seed,
+                           L.ptr(y), out_dtype, L.ptr(mean), L.ptr(rstd), L.stream()), "rs_ln_fwd")
+    return [y, mean, rstd]
+
+
+@ln_op.register_fake
+def _(x, index, w, b, eps, dropout_p, seed, out_dtype):
+    n = x.shape[0] if index is None else index.numel()
+    return [x.new_empty(n, x.shape[1], dtype=L.torch_dtype(out_dtype)), x.new_empty(n, dtype=torch.float32),
+            x.new_empty(n, dtype=torch.float32)]
+
+
+@torch.library.custom_op("rs::ln_bwd", mutates_args=())
+def ln_bwd_op(dy: Tensor, x: Tensor, index: Optional[Tensor], w: Tensor, mean: Tensor, rstd: Tensor, dropout_p: float,
+              seed: int) -> List[Tensor]:
+    dy = dy.contiguous()
+    n = dy.shape[0]
+    dx = torch.empty_like(x) if index is None else torch.zeros_like(x)
+    dw = torch.empty_like(w)
+    db = torch.empty_like(w)
+    ws = L.workspace(_lib.rs_ln_bwd_workspace_bytes(n), x.device)
+    L.check(_lib.rs_ln_bwd(L.ptr(dy), L.dt(dy), L.ptr(x), L.dt(x), L.ptr(index), n, x.shape[1], L.ptr(w), L.ptr(mean),
+                           L.ptr(rstd), dropout_p, seed, L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(),
+                           L.stream()), "rs_ln_bwd")
+    return [dx, dw, db]
+
+
+@ln_bwd_op.register_fake
+def _(dy, x, index, w, mean, rstd, dropout_p, seed):
+    return [torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)]
+
+
+@torch.library.custom_op("rs::dropout_add", mutates_args=())
+def dropout_add_op(x: Tensor, y: Tensor, dropout_p: float, seed: int) -> Tensor:
+    L.require_cuda(x, y)
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty_like(x)
+    L.check(_lib.rs_dropout_add_fwd(L.ptr(x), L.dt(x), L.ptr(y), L.dt(y), x.numel(), dropout_p, seed, L.ptr(out),
+                                    L.stream()), "rs_dropout_add_fwd")
+    return out
+
+
+@dropout_add_op.register_fake
+def _(x, y, dropout_p, seed):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("rs::dropout_bwd", mutates_args=())
+def dropout_bwd_op(g: Tensor, dropout_p: float, seed: int, out_dtype: int) -> Tensor:
+    g = g.contiguous()
+    dy = torch.empty(g.shape, dtype=L.torch_dtype(out_dtype), device=g.device)
+    L.check(_lib.rs_dropout_bwd(L.ptr(g), L.dt(g), g.numel(), dropout_p, seed, L.ptr(dy), out_dtype, L.stream()),
+            "rs_dropout_bwd")
+    return dy
+
+
+@dropout_bwd_op.register_fake
+def _(g, dropout_p, seed, out_dtype):
+    return g.new_empty(g.shape, dtype=L.torch_dtype(out_dtype))
+
+
+@torch.library.custom_op("rs::gelu_dropout", mutates_args=())
+def gelu_dropout_op(z: Tensor, dropout_p: float, seed: int) -> Tensor:
+    L.require_cuda(z)
+    z = z.contiguous()
+    out = torch.empty_like(z)
+    L.check(_lib.rs_gelu_dropout_fwd(L.ptr(z), L.dt(z), z.numel(), dropout_p, seed, L.ptr(out), L.stream()),
+            "rs_gelu_dropout_fwd")
+    return out
+
+
+@gelu_dropout_op.register_fake
+def _(z, dropout_p, seed):
+    return torch.empty_like(z)
+
+
+@torch.library.custom_op("rs::gelu_dropout_bwd", mutates_args=())
+def gelu_dropout_bwd_op(z: Tensor, g: Tensor, dropout_p: float, seed: int) -> Tensor:
+    g = g.to(z.dtype).contiguous()
+    dz = torch.empty_like(z)
+    L.check(_lib.rs_gelu_dropout_bwd(L.ptr(z), L.ptr(g), L.dt(z), z.numel(), dropout_p, seed, L.ptr(dz), L.stream()),
+            "rs_gelu_dropout_bwd")
+    return dz
+
+
+@gelu_dropout_bwd_op.register_fake
+def _(z, g, dropout_p, seed):
+    return torch.empty_like(z)
+
+
+# ------------------------------------------------------------------------------------------------ autograd
+class _AttnVarlen(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, cu_seqlens, n_heads, max_len, scale, dropout_p, seed):
+        out, lse = torch.ops.rs.attn_varlen(qkv, cu_seqlens, n_heads, max_len, scale, dropout_p, seed)
+        ctx.save_for_backward(qkv, out, lse, cu_seqlens)
+        ctx.meta = (n_heads, max_len, scale, dropout_p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, out, lse, cu = ctx.saved_tensors
+        return (torch.ops.rs.attn_varlen_bwd(qkv, g, out, lse, cu, *ctx.meta),) + (None,) * 6
+
+
+def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dropout_p: float = 0.0,
+                scale: Optional[float] = None) -> Tensor:
+    """Causal self-attention over packed sequences: qkv [T, 3*H*32] (in_proj output) -> [T, H*32]."""
+    hd = qkv.shape[1] // (3 * n_heads)
+    scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    return _AttnVarlen.apply(qkv, cu_seqlens, n_heads, max_len, float(scale), float(dropout_p),
+                             _seed() if dropout_p > 0 else 0)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, index, w, b, eps, dropout_p, seed, out_dtype):
+        y, mean, rstd = torch.ops.rs.ln(x, index, w, b, eps, dropout_p, seed, out_dtype)
+        ctx.save_for_backward(x, index, w, mean, rstd)
+        ctx.meta = (dropout_p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, index, w, mean, rstd = ctx.saved_tensors
+        dx, dw, db = torch.ops.rs.ln_bwd(g, x, index, w, mean, rstd, *ctx.meta)
+        return dx, None, dw, db, None, None, None, None
+
+
+def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, index: Optional[Tensor] = None,
+               dropout_p: float = 0.0, out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """dropout(LayerNorm(x[index])) for 128-wide rows; `index` (int64) packs rows on the way in."""
+    od = L.dt(out_dtype) if out_dtype is not None else L.dt(x)
+    return _LayerNorm.apply(x, index, weight, bias, float(eps), float(dropout_p), _seed() if dropout_p > 0 else 0, od)
+
+
+class _DropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, dropout_p, seed):
+        ctx.meta = (dropout_p, seed, L.dt(y))
+        return torch.ops.rs.dropout_add(x, y, dropout_p, seed)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, seed, ydt = ctx.meta
+        return g, torch.ops.rs.dropout_bwd(g, p, seed, ydt), None, None
+
+
+def dropout_add(x: Tensor, y: Tensor, dropout_p: float = 0.0) -> Tensor:
+    """x + dropout(y) in x's dtype (the fp32 residual stream)."""
+    return _DropoutAdd.apply(x, y, float(dropout_p), _seed() if dropout_p > 0 else 0)
+
+
+class _GeluDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, dropout_p, seed):
+        ctx.save_for_backward(z)
+        ctx.meta = (dropout_p, seed)
+        return torch.ops.rs.gelu_dropout(z, dropout_p, seed)
+
+    @staticmethod
+    def backward(ctx, g):
+        (z,) = ctx.saved_tensors
+        return torch.ops.rs.gelu_dropout_bwd(z, g, *ctx.meta), None, None
+
+
+def gelu_dropout(z: Tensor, dropout_p: float = 0.0) -> Tensor:
+    return _GeluDropout.apply(z, float(dropout_p), _seed() if dropout_p > 0 else 0)
+
+
+# ------------------------------------------------------------------------------------------------ composition
+def _act_dtype(x: Tensor) -> torch.dtype:
+    if torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
+    return x.dtype
+
+
+def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int) -> Tensor:
+    if not layer.norm_first or layer.activation_relu_or_gelu != 2:
+        raise NotImplementedError("packed encoder: pre-norm GELU layers only (the reference's configuration)")
+    tr = layer.training
+    attn = layer.self_attn
+    ad = _act_dtype(x)
+    h = layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, out_dtype=ad)
+    qkv = F.linear(h, attn.in_proj_weight, attn.in_proj_bias)
+    o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0)
+    x = dropout_add(x, F.linear(o, attn.out_proj.weight, attn.out_proj.bias), layer.dropout1.p if tr else 0.0)
+    h = layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, out_dtype=ad)
+    f = gelu_dropout(F.linear(h, layer.linear1.weight, layer.linear1.bias), layer.dropout.p if tr else 0.0)
+    return dropout_add(x, F.linear(f, layer.linear2.weight, layer.linear2.bias), layer.dropout2.p if tr else 0.0)
+
+
+def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int) -> Tensor:
+    """x: [T, 128] fp32 residual stream of the packed valid tokens -> same shape."""
+    for layer in encoder.layers:
+        x = packed_encoder_layer(layer, x, cu_seqlens, max_len)
+    if encoder.norm is not None:
+        x = encoder.norm(x)
+    return x

@@ -44,6 +44,15 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
     last = (valid.sum(dim=1) - 1).clamp(min=0)
     batch["last_index"] = torch.arange(B) * L + last
     batch["select_index"] = torch.cat([batch["valid_index"], batch["last_index"]])
+    # packed-token view of the same batch (encoder.py): sequence offsets and the last valid step of every sequence
+    lens = valid.sum(dim=1)
+    if bool((lens > 0).all()):
+        cu = torch.zeros(B + 1, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens, 0)
+        T = int(cu[-1])
+        batch["cu_seqlens"] = cu
+        batch["last_packed"] = cu[1:].to(torch.int64) - 1
+        batch["select_packed"] = torch.cat([torch.arange(T), batch["last_packed"]])
     if columns:
         tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
         ids, counts, pos_col = losses.item_columns(tgt)
@@ -53,14 +62,34 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
     return batch
 
 
+def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
+    """The two dropout views (v1_usertower_train.py:788-792).  View 1 feeds the main loss (valid steps, or the last
+    step) and DuoRec (last step); view 2 only DuoRec: the late-fusion head runs on exactly those rows (same values
+    as slicing the full [B, L, 128] output).  Returns ([n_main + B, 128], [B, 128])."""
+    if packed and "cu_seqlens" in batch:
+        lp = batch["last_packed"]
+        sel1 = batch["select_packed"] if loss_scope == "all" else torch.cat([lp, lp])
+        pk = dict(packed_index=batch["valid_index"], cu_seqlens=batch["cu_seqlens"])
+        return (model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1, **pk, **extra),
+                model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=lp, **pk, **extra))
+    li = batch["last_index"]
+    sel1 = batch.get("select_index") if loss_scope == "all" else torch.cat([li, li])
+    if sel1 is None:
+        sel1 = torch.cat([batch["valid_index"], li])
+    return (model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1, **extra),
+            model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=li, **extra))
+
+
 def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1,
                    lambda_cl=0.2, loss_scope="all", amp_dtype: Optional[torch.dtype] = torch.bfloat16,
-                   scaler=None, max_norm=5.0, grad_hook=None, sdpa_efficient=True, columns="unique"):
+                   scaler=None, max_norm=5.0, grad_hook=None, sdpa_efficient=True, columns="unique", packed=True):
     """forward x2 (two dropout views) + C2 + C3 + backward + clip + optimizer step.
     Returns (total, main, cl) as device scalars.  `batch` comes from prepare_batch(add_host_index(...)).
     columns: how the in-batch softmax of the main loss enumerates its columns (same loss value, see
     losses.logq_infonce_columns) -- "unique": the distinct target items of the batch with multiplicities
-    (default); "catalog": every item, static shape; "batch": one column per row, the reference's [N, N]."""
+    (default); "catalog": every item, static shape; "batch": one column per row, the reference's [N, N].
+    packed: run the sequence encoder on the packed valid tokens (encoder.py) instead of the padded [B, L] grid
+    (needs the batch's `cu_seqlens`, i.e. no empty sequence); same values at the positions the losses read."""
     item_ids = batch["item_ids"]
     B, L = item_ids.shape
     if optimizer is not None:
@@ -79,11 +108,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
         n_main = idx.numel()
         # view 1 feeds the main loss (valid steps) and DuoRec (last step); view 2 only DuoRec: the late-fusion
         # head runs on exactly those rows (same values as slicing the full [B,L,128] output)
-        sel1 = batch.get("select_index")
-        if sel1 is None:
-            sel1 = torch.cat([idx, li])
-        out1 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1)
-        out2 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=li)
+        out1, out2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
         u = F.normalize(out1[:n_main], p=2, dim=1)                                   # :794-807
         tgt = tgt_flat[idx]
         uid = idx // L                                                               # batch row = user id (:801-804)
@@ -188,7 +213,7 @@ class ShardedTwoTower:
         return total
 
     def step(self, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1, lambda_cl=0.2,
-             amp_dtype: Optional[torch.dtype] = torch.bfloat16, max_norm=5.0, sdpa_efficient=True):
+             amp_dtype: Optional[torch.dtype] = torch.bfloat16, max_norm=5.0, sdpa_efficient=True, packed=True):
         dist, sh, model, item_tower = self.dist, self.sh, self.model, self.item_tower
         item_ids = batch["item_ids"]
         B, L = item_ids.shape
@@ -205,11 +230,7 @@ class ShardedTwoTower:
             tgt_flat = batch["target_ids"].reshape(-1)
             idx, li = batch["valid_index"], batch["last_index"]
             n_main = idx.numel()
-            sel1 = batch.get("select_index")
-            if sel1 is None:
-                sel1 = torch.cat([idx, li])
-            out1 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1, item_id_rows=id_rows)
-            out2 = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=li, item_id_rows=id_rows)
+            out1, out2 = _two_views(model, batch, pretrained_vecs, kw, "all", packed, item_id_rows=id_rows)
             u = F.normalize(out1[:n_main], p=2, dim=1)
             tgt = tgt_flat[idx]
             uid = idx // L

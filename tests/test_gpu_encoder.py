@@ -1,0 +1,196 @@
+"""GPU parity of the packed sequence encoder (encoder.py / csrc/encoder.cu) against stock PyTorch and against the
+reference-generated user-tower fixture.  fp32 cases: 1e-4 / 1e-3 (different summation order); bf16: stated per test."""
+import math
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cu(lens):
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    return cu
+
+
+def _ref_attention(qkv, lens, H):
+    """dense causal attention per sequence, fp32"""
+    outs, t0 = [], 0
+    for n in lens:
+        x = qkv[t0:t0 + n].view(n, 3, H, -1)
+        q, k, v = x[:, 0].transpose(0, 1), x[:, 1].transpose(0, 1), x[:, 2].transpose(0, 1)      # [H, n, hd]
+        s = q @ k.transpose(1, 2) / math.sqrt(q.shape[-1])
+        s = s.masked_fill(torch.triu(torch.ones(n, n, dtype=torch.bool, device=s.device), 1), float("-inf"))
+        outs.append((torch.softmax(s, -1) @ v).transpose(0, 1).reshape(n, -1))
+        t0 += n
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("lens", [[1], [1, 2, 3], [50, 7, 33, 32, 64, 1, 17], [13] * 40])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attn_varlen_vs_dense(rs, lens, dtype):
+    H, hd = 4, 32
+    g = torch.Generator().manual_seed(sum(lens))
+    T = sum(lens)
+    qkv32 = torch.randn(T, 3 * H * hd, generator=g)
+    w = torch.randn(T, H * hd, generator=g)
+    a = qkv32.to(dtype).float().to(DEV).requires_grad_(True)               # same rounded operands on both sides
+    want = _ref_attention(a, lens, H)
+    (want * w.to(DEV)).sum().backward()
+    b = qkv32.to(dtype).to(DEV).requires_grad_(True)
+    got = rs.encoder.attn_varlen(b, _cu(lens).to(DEV), H, max(lens))
+    (got.float() * w.to(DEV)).sum().backward()
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(got.float(), want.detach(), **tol)
+    torch.testing.assert_close(b.grad.float(), a.grad, **(tol if dtype == torch.float32 else dict(rtol=3e-2, atol=6e-2)))
+
+
+def test_attn_dropout_forward_backward_share_the_mask(rs):
+    """with an explicit seed the op is a deterministic function: its analytic gradient must match central differences
+    of the SAME seeded forward (fp32), i.e. forward, dQ pass and dK/dV pass all draw the same keep mask."""
+    H, hd, lens = 2, 32, [5, 37, 2]
+    g = torch.Generator().manual_seed(0)
+    T = sum(lens)
+    qkv = (0.5 * torch.randn(T, 3 * H * hd, generator=g)).to(DEV)
+    w = torch.randn(T, H * hd, generator=g).to(DEV)
+    cu, seed, p, scale = _cu(lens).to(DEV), 1234567, 0.3, 1 / math.sqrt(hd)
+    out, lse = torch.ops.rs.attn_varlen(qkv, cu, H, 64, scale, p, seed)
+    out0, _ = torch.ops.rs.attn_varlen(qkv, cu, H, 64, scale, 0.0, 0)
+    assert not torch.allclose(out, out0)                                   # dropout did something
+    out_again, _ = torch.ops.rs.attn_varlen(qkv, cu, H, 64, scale, p, seed)
+    assert torch.equal(out, out_again)
+    dq = torch.ops.rs.attn_varlen_bwd(qkv, w, out, lse, cu, H, 64, scale, p, seed)
+    idx = torch.randint(0, qkv.numel(), (40,), generator=g)
+    eps = 1e-2
+    for flat in idx.tolist():
+        d = torch.zeros_like(qkv).view(-1)
+        d[flat] = eps
+        fp, _ = torch.ops.rs.attn_varlen(qkv + d.view_as(qkv), cu, H, 64, scale, p, seed)
+        fm, _ = torch.ops.rs.attn_varlen(qkv - d.view_as(qkv), cu, H, 64, scale, p, seed)
+        num = ((fp - fm) * w).sum().item() / (2 * eps)
+        assert abs(num - dq.view(-1)[flat].item()) < 2e-2 * max(1.0, abs(num)), (flat, num, dq.view(-1)[flat].item())
+
+
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.float32)])
+def test_layer_norm_vs_torch(rs, xdt, ydt):
+    g = torch.Generator().manual_seed(1)
+    n_in, n = 700, 333
+    x = (torch.randn(n_in, 128, generator=g) * 2 + 0.5).to(xdt)
+    w, b = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    index = torch.randperm(n_in, generator=g)[:n]
+    cot = torch.randn(n, 128, generator=g)
+    xr, wr, br = x.float().to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    want = F.layer_norm(xr[index.to(DEV)], (128,), wr, br, 1e-5)
+    (want * cot.to(DEV)).sum().backward()
+    xp, wp, bp = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    got = rs.encoder.layer_norm(xp, wp, bp, 1e-5, index=index.to(DEV), out_dtype=ydt)
+    assert got.dtype == ydt
+    (got.float() * cot.to(DEV)).sum().backward()
+    lo = xdt != torch.float32 or ydt != torch.float32
+    tol = dict(rtol=2e-2, atol=3e-2) if lo else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got.float(), want.detach(), **tol)
+    torch.testing.assert_close(xp.grad.float(), xr.grad, **tol)
+    torch.testing.assert_close(wp.grad, wr.grad, **(dict(rtol=2e-2, atol=0.3) if lo else dict(rtol=1e-4, atol=1e-3)))
+    torch.testing.assert_close(bp.grad, br.grad, **(dict(rtol=2e-2, atol=0.3) if lo else dict(rtol=1e-4, atol=1e-3)))
+    assert (xp.grad.float()[torch.ones(n_in, dtype=torch.bool).index_fill_(0, index, False)] == 0).all()
+
+
+def test_elementwise_ops_vs_torch_and_dropout_law(rs):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1000, 128, generator=g).to(DEV).requires_grad_(True)
+    y = torch.randn(1000, 128, generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    out = rs.encoder.dropout_add(x, y, 0.0)
+    torch.testing.assert_close(out, x.detach() + y.detach().float())
+    z = torch.randn(1000, 256, generator=g).to(DEV).requires_grad_(True)
+    f = rs.encoder.gelu_dropout(z, 0.0)
+    torch.testing.assert_close(f, F.gelu(z.detach()), rtol=1e-5, atol=1e-6)
+    f.sum().backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    F.gelu(z2).sum().backward()
+    torch.testing.assert_close(z.grad, z2.grad, rtol=1e-4, atol=1e-5)
+    # dropout: Bernoulli(1-p)/(1-p), the same mask in forward and backward
+    p = 0.2
+    torch.manual_seed(7)
+    out = rs.encoder.dropout_add(x, y, p)
+    out.sum().backward()
+    kept = (out.detach() - x.detach()).abs() > 0
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    torch.testing.assert_close(y.grad.float(), kept.float() / (1 - p), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close((out.detach() - x.detach())[kept], (y.detach().float() / (1 - p))[kept], rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(x.grad, torch.ones_like(x))
+    # two calls draw different masks; column-wise keep rates are unbiased too
+    out2 = rs.encoder.dropout_add(x, y, p)
+    assert not torch.equal(out2, out)
+    assert (kept.float().mean(0) - (1 - p)).abs().max() < 0.06
+
+
+def _tower(rs, ut):
+    m = rs.SASRecUserTower(SimpleNamespace(**ut["args"]))
+    m.load_state_dict(ut["state"], strict=True)
+    return m.to(DEV).eval()
+
+
+def _packing(pad):
+    valid = ~pad
+    B, Lq = valid.shape
+    idx = torch.nonzero(valid.reshape(-1)).squeeze(1)
+    return idx, _cu(valid.sum(1).tolist())
+
+
+def test_packed_tower_vs_reference_fixture(rs):
+    """the packed encoder reproduces the reference's outputs at every valid position (train-mode signature, eval-mode
+    layers) and its last-step output, and the parameter gradients for a cotangent supported on the valid steps."""
+    ut = load_golden("user_tower.pt")
+    m = _tower(rs, ut)
+    inp = {k: v.to(DEV) for k, v in ut["inputs"].items()}
+    pad = ut["inputs"]["padding_mask"]
+    if not bool(((~pad).sum(1) > 0).all()):
+        pytest.skip("fixture has an empty sequence")
+    idx, cu = _packing(pad)
+    out = m(**inp, training_mode=True, packed_index=idx.to(DEV), cu_seqlens=cu.to(DEV))
+    want = ut["out_train"].reshape(-1, 128)[idx]
+    torch.testing.assert_close(out.detach().cpu(), want, rtol=1e-3, atol=1e-4)
+    ev = m(**inp, training_mode=False, packed_index=idx.to(DEV), cu_seqlens=cu.to(DEV))
+    torch.testing.assert_close(ev.detach().cpu(), ut["out_eval"], rtol=1e-3, atol=1e-4)
+    # gradients: dense path vs packed path with the same (valid-only) cotangent
+    cot = ut["cotangent"].reshape(-1, 128)[idx].to(DEV)
+    (out * cot).sum().backward()
+    got = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    dense = m(**inp, training_mode=True)
+    (dense.reshape(-1, 128)[idx.to(DEV)] * cot).sum().backward()
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        torch.testing.assert_close(got[k], p.grad, rtol=2e-3, atol=2e-4, msg=k)
+
+
+def test_packed_step_matches_dense_step_bf16(rs):
+    """full train step, eval-mode towers (no dropout), bf16 autocast: packed vs padded-grid encoder."""
+    syn = rs.synthetic
+    n_items, B, SL = 3000, 64, 50
+    torch.manual_seed(0)
+    model = rs.SASRecUserTower(syn.tower_args(num_items=n_items, max_len=SL)).to(DEV).eval()
+    item = rs.SASRecItemTower(n_items, 128, syn.log_q(n_items)).to(DEV)
+    lookup = syn.pretrained_table(n_items).to(DEV)
+    item.init_from_pretrained(lookup)
+    batch = rs.train.prepare_batch(rs.train.add_host_index(syn.make_batch(B, SL, n_items, seed=9)), DEV)
+    res = {}
+    for packed in (False, True):
+        model.zero_grad(set_to_none=True)
+        item.zero_grad(set_to_none=True)
+        opt = torch.optim.SGD(list(model.parameters()) + list(item.parameters()), lr=0.0)
+        t, mn, c = rs.train.two_tower_step(model, item, batch, lookup, opt, packed=packed)
+        res[packed] = (mn.item(), c.item(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert abs(res[True][0] - res[False][0]) < 2e-2 and abs(res[True][1] - res[False][1]) < 2e-2, (res[True][:2], res[False][:2])
+    for k, gref in res[False][2].items():
+        g = res[True][2][k]
+        assert (g - gref).abs().max() <= 0.1 * gref.abs().max() + 1e-6, (k, (g - gref).abs().max(), gref.abs().max())
