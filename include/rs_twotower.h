@@ -188,13 +188,19 @@ int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, i
  *
  * Causal attention for sequences of <= 64 tokens, head_dim == 32, straight from the packed in_proj output
  * qkv[T, 3, H, 32] (q | k | v, heads contiguous -- nn.MultiheadAttention's layout): out[T, H*32], lse[T, H].
- * Replaces the head transposes, the [B,H,L,L] merged-mask tensor, F.scaled_dot_product_attention and its dropout. */
+ * Replaces the head transposes, the [B,H,L,L] merged-mask tensor, F.scaled_dot_product_attention and its dropout.
+ * zero_tail: the last `zero_tail` sequences are queries at PADDED positions -- in the reference's padded grid every
+ * key of such a query is masked and the attention output is 0 (fully-masked softmax row); they get out = 0 and no
+ * gradient.  The reference reads such rows: `last_indices = valid_mask.sum(1) - 1` (v1_usertower_train.py:830)
+ * addresses its LEFT-padded grid from the left, i.e. a padded position whenever a sequence fills less than half
+ * of the window; the packed encoder carries those positions as extra one-token sequences to reproduce it. */
 int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens,
-                       int n_heads, int head_dim, int max_len, float scale, float dropout_p, uint64_t seed,
-                       void* out, float* lse, void* stream);
+                       int n_heads, int head_dim, int max_len, int64_t zero_tail, float scale, float dropout_p,
+                       uint64_t seed, void* out, float* lse, void* stream);
 int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* lse,
                        const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads, int head_dim,
-                       int max_len, float scale, float dropout_p, uint64_t seed, void* d_qkv, void* stream);
+                       int max_len, int64_t zero_tail, float scale, float dropout_p, uint64_t seed, void* d_qkv,
+                       void* stream);
 /* y[r,:] = dropout(LayerNorm(x[index ? index[r] : r, :])), dim == 128, fp32 statistics (mean/rstd[n_rows] saved).
  * `index` packs the valid rows of the padded grid on the way in (emb_ln, :458-459).  Backward: dx[index[r]] (rows
  * that are not indexed are left untouched: pass a zeroed buffer), dw/db[128] reduced in a fixed order. */

@@ -54,11 +54,18 @@ template <int DT> __device__ __forceinline__ void st4(void* base, int64_t off, f
   }
 }
 
+// element type as stored (only used to write zeros)
+template <int DT> struct DTStoreT { typedef float type; };
+template <> struct DTStoreT<RS_F16> { typedef __half type; };
+template <> struct DTStoreT<RS_BF16> { typedef __nv_bfloat16 type; };
+template <int DT> using DTStore = typename DTStoreT<DT>::type;
+
 // ------------------------------------------------------------------------------------------------ attention
 struct AttnParams {
   const int* cu;            // [n_seq + 1] token offsets
   int64_t n_seq;
   int H, max_len;
+  int64_t zero_from;        // sequences b >= zero_from are fully masked queries: output 0, no gradient
   float scale;
   uint32_t drop_thresh;     // keep iff rnd32 >= thresh   (0: no dropout)
   float inv_keep;
@@ -122,6 +129,13 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const void* __restrict__ 
     const int h = (int)(item % p.H);
     const int64_t t0 = __ldg(p.cu + b);
     const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (b >= p.zero_from) {                             // a query whose every key is masked (see rs_twotower.h)
+      for (int i = 0; i < len; ++i) {
+        reinterpret_cast<DTStore<DT>*>(out)[(t0 + i) * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
+        if (lane == 0) lse[(t0 + i) * p.H + h] = 0.f;
+      }
+      continue;
+    }
     stage_rows<DT>(sK, qkv, t0, len, rs_, os_ + h * ENC_HD, lane);
     stage_rows<DT>(sV, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, lane);
     __syncwarp();
@@ -180,6 +194,12 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ 
     const int h = (int)(item % p.H);
     const int64_t t0 = __ldg(p.cu + b);
     const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (b >= p.zero_from) {
+      for (int i = 0; i < len; ++i)
+        for (int c = 0; c < 3; ++c)
+          reinterpret_cast<DTStore<DT>*>(d_qkv)[(t0 + i) * rs_ + c * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
+      continue;
+    }
     // row statistics: lse_i and delta_i = <dO_i, O_i>  (8 lanes per row)
     {
       const int sub = lane >> 3, d4 = (lane & 7) * 4;
@@ -446,8 +466,8 @@ using namespace rs;
     default: return RS_ERR_BAD_ARG;                                     \
   }
 
-static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, float p) {
-  if (n_seq <= 0 || total < 0 || H <= 0 || max_len <= 0) return RS_ERR_BAD_ARG;
+static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, float p, int64_t zero_tail) {
+  if (n_seq <= 0 || total < 0 || H <= 0 || max_len <= 0 || zero_tail < 0 || zero_tail > n_seq) return RS_ERR_BAD_ARG;
   if (hd != ENC_HD || max_len > 64) return RS_ERR_UNSUPPORTED;
   if (p < 0.f || p >= 1.f) return RS_ERR_BAD_ARG;
   if (total * H >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;      // dropout stream index is 32 bits
@@ -455,14 +475,16 @@ static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, 
 }
 
 extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int64_t n_seq,
-                                  int64_t total_tokens, int n_heads, int head_dim, int max_len, float scale,
-                                  float dropout_p, uint64_t seed, void* out, float* lse, void* stream) {
-  int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p);
+                                  int64_t total_tokens, int n_heads, int head_dim, int max_len, int64_t zero_tail,
+                                  float scale, float dropout_p, uint64_t seed, void* out, float* lse, void* stream) {
+  int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p, zero_tail);
   if (rc != RS_OK) return rc;
   if (total_tokens == 0) return RS_OK;
   if (!qkv || !cu_seqlens || !out || !lse) return RS_ERR_BAD_ARG;
   AttnParams p;
+  max_len = (max_len + 3) & ~3;      // keeps every per-warp shared-memory region 16-byte aligned
   p.cu = cu_seqlens; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
+  p.zero_from = n_seq - zero_tail;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const size_t smem = (size_t)4 * 2 * max_len * ENC_HD * sizeof(float);
   const int grid = grid_for_warps(n_seq * n_heads, 4, 8);
@@ -478,14 +500,16 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_
 
 extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* lse,
                                   const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads,
-                                  int head_dim, int max_len, float scale, float dropout_p, uint64_t seed, void* d_qkv,
-                                  void* stream) {
-  int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p);
+                                  int head_dim, int max_len, int64_t zero_tail, float scale, float dropout_p,
+                                  uint64_t seed, void* d_qkv, void* stream) {
+  int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p, zero_tail);
   if (rc != RS_OK) return rc;
   if (total_tokens == 0) return RS_OK;
   if (!qkv || !d_out || !out || !lse || !cu_seqlens || !d_qkv) return RS_ERR_BAD_ARG;
   AttnParams p;
+  max_len = (max_len + 3) & ~3;      // keeps every per-warp shared-memory region 16-byte aligned
   p.cu = cu_seqlens; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
+  p.zero_from = n_seq - zero_tail;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const size_t smem = (size_t)4 * (2 * max_len * ENC_HD + 2 * max_len) * sizeof(float);
   const int grid = grid_for_warps(n_seq * n_heads, 4, 8);

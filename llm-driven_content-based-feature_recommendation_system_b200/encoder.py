@@ -42,8 +42,8 @@ def _seed() -> int:
 
 # ------------------------------------------------------------------------------------------------ custom ops
 @torch.library.custom_op("rs::attn_varlen", mutates_args=())
-def attn_varlen_op(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, scale: float, dropout_p: float,
-                   seed: int) -> List[Tensor]:
+def attn_varlen_op(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, zero_tail: int, scale: float,
+                   dropout_p: float, seed: int) -> List[Tensor]:
     L.require_cuda(qkv, cu_seqlens)
     qkv = qkv.contiguous()
     T = qkv.shape[0]
@@ -51,31 +51,31 @@ def attn_varlen_op(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, 
     out = torch.empty(T, n_heads * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(T, n_heads, dtype=torch.float32, device=qkv.device)
     L.check(_lib.rs_attn_varlen_fwd(L.ptr(qkv), L.dt(qkv), L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T, n_heads, hd,
-                                    max_len, scale, dropout_p, seed, L.ptr(out), L.ptr(lse), L.stream()),
+                                    max_len, zero_tail, scale, dropout_p, seed, L.ptr(out), L.ptr(lse), L.stream()),
             "rs_attn_varlen_fwd")
     return [out, lse]
 
 
 @attn_varlen_op.register_fake
-def _(qkv, cu_seqlens, n_heads, max_len, scale, dropout_p, seed):
+def _(qkv, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
     return [qkv.new_empty(qkv.shape[0], qkv.shape[1] // 3), qkv.new_empty(qkv.shape[0], n_heads, dtype=torch.float32)]
 
 
 @torch.library.custom_op("rs::attn_varlen_bwd", mutates_args=())
 def attn_varlen_bwd_op(qkv: Tensor, d_out: Tensor, out: Tensor, lse: Tensor, cu_seqlens: Tensor, n_heads: int,
-                       max_len: int, scale: float, dropout_p: float, seed: int) -> Tensor:
+                       max_len: int, zero_tail: int, scale: float, dropout_p: float, seed: int) -> Tensor:
     d_out = d_out.to(qkv.dtype).contiguous()
     T = qkv.shape[0]
     hd = qkv.shape[1] // (3 * n_heads)
     d_qkv = torch.empty_like(qkv)
     L.check(_lib.rs_attn_varlen_bwd(L.ptr(qkv), L.ptr(d_out), L.ptr(out), L.dt(qkv), L.ptr(lse), L.ptr(cu_seqlens),
-                                    cu_seqlens.numel() - 1, T, n_heads, hd, max_len, scale, dropout_p, seed,
+                                    cu_seqlens.numel() - 1, T, n_heads, hd, max_len, zero_tail, scale, dropout_p, seed,
                                     L.ptr(d_qkv), L.stream()), "rs_attn_varlen_bwd")
     return d_qkv
 
 
 @attn_varlen_bwd_op.register_fake
-def _(qkv, d_out, out, lse, cu_seqlens, n_heads, max_len, scale, dropout_p, seed):
+def _(qkv, d_out, out, lse, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
     return torch.empty_like(qkv)
 
 
@@ -181,24 +181,25 @@ def _(z, g, dropout_p, seed):
 # ------------------------------------------------------------------------------------------------ autograd
 class _AttnVarlen(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, cu_seqlens, n_heads, max_len, scale, dropout_p, seed):
-        out, lse = torch.ops.rs.attn_varlen(qkv, cu_seqlens, n_heads, max_len, scale, dropout_p, seed)
+    def forward(ctx, qkv, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
+        out, lse = torch.ops.rs.attn_varlen(qkv, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed)
         ctx.save_for_backward(qkv, out, lse, cu_seqlens)
-        ctx.meta = (n_heads, max_len, scale, dropout_p, seed)
+        ctx.meta = (n_heads, max_len, zero_tail, scale, dropout_p, seed)
         return out
 
     @staticmethod
     def backward(ctx, g):
         qkv, out, lse, cu = ctx.saved_tensors
-        return (torch.ops.rs.attn_varlen_bwd(qkv, g, out, lse, cu, *ctx.meta),) + (None,) * 6
+        return (torch.ops.rs.attn_varlen_bwd(qkv, g, out, lse, cu, *ctx.meta),) + (None,) * 7
 
 
 def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dropout_p: float = 0.0,
-                scale: Optional[float] = None) -> Tensor:
-    """Causal self-attention over packed sequences: qkv [T, 3*H*32] (in_proj output) -> [T, H*32]."""
+                scale: Optional[float] = None, zero_tail: int = 0) -> Tensor:
+    """Causal self-attention over packed sequences: qkv [T, 3*H*32] (in_proj output) -> [T, H*32].  The last
+    `zero_tail` sequences are queries at padded positions (every key masked): output 0, no gradient."""
     hd = qkv.shape[1] // (3 * n_heads)
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
-    return _AttnVarlen.apply(qkv, cu_seqlens, n_heads, max_len, float(scale), float(dropout_p),
+    return _AttnVarlen.apply(qkv, cu_seqlens, n_heads, max_len, int(zero_tail), float(scale), float(dropout_p),
                              _seed() if dropout_p > 0 else 0)
 
 
@@ -265,7 +266,8 @@ def _act_dtype(x: Tensor) -> torch.dtype:
     return x.dtype
 
 
-def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int) -> Tensor:
+def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int,
+                         zero_tail: int = 0) -> Tensor:
     if not layer.norm_first or layer.activation_relu_or_gelu != 2:
         raise NotImplementedError("packed encoder: pre-norm GELU layers only (the reference's configuration)")
     tr = layer.training
@@ -273,17 +275,18 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     ad = _act_dtype(x)
     h = layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, out_dtype=ad)
     qkv = F.linear(h, attn.in_proj_weight, attn.in_proj_bias)
-    o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0)
+    o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail)
     x = dropout_add(x, F.linear(o, attn.out_proj.weight, attn.out_proj.bias), layer.dropout1.p if tr else 0.0)
     h = layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, out_dtype=ad)
     f = gelu_dropout(F.linear(h, layer.linear1.weight, layer.linear1.bias), layer.dropout.p if tr else 0.0)
     return dropout_add(x, F.linear(f, layer.linear2.weight, layer.linear2.bias), layer.dropout2.p if tr else 0.0)
 
 
-def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int) -> Tensor:
+def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,
+                   zero_tail: int = 0) -> Tensor:
     """x: [T, 128] fp32 residual stream of the packed valid tokens -> same shape."""
     for layer in encoder.layers:
-        x = packed_encoder_layer(layer, x, cu_seqlens, max_len)
+        x = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail)
     if encoder.norm is not None:
         x = encoder.norm(x)
     return x

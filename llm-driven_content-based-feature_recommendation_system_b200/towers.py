@@ -105,7 +105,7 @@ class SASRecUserTower(nn.Module):
     def forward(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids,
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
                 fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None,
-                item_id_rows=None, packed_index=None, cu_seqlens=None):
+                item_id_rows=None, packed_index=None, cu_seqlens=None, packed_zero_tail=0):
         """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
         When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
         returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
@@ -118,7 +118,7 @@ class SASRecUserTower(nn.Module):
         user_profile_vec = self.static_mlp(static_input)
         if packed_index is not None:
             return self._forward_packed(seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index,
-                                        cu_seqlens)
+                                        cu_seqlens, packed_zero_tail)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
         # is_causal=True only tells nn.TransformerEncoder not to PROBE the mask: with is_causal=None it compares the
         # mask with a generated causal one and reads the verdict back (`bool((mask == causal).all())`,
@@ -139,19 +139,21 @@ class SASRecUserTower(nn.Module):
             final_vec = self.output_proj(torch.cat([output[:, -1, :], user_profile_vec], dim=-1))
         return F.normalize(final_vec, p=2, dim=-1)
 
-    def _forward_packed(self, seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index, cu_seqlens):
+    def _forward_packed(self, seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index, cu_seqlens,
+                        zero_tail=0):
         """The encoder on the packed valid tokens (encoder.py): `packed_index` [T] = flat b*L+l positions of the
-        valid time steps in batch-major order, `cu_seqlens` [B+1] int32 their per-sequence offsets (every sequence
-        non-empty).  `select_index` then indexes PACKED rows; returns [len(select_index), 128] (all T valid rows when
+        valid time steps in batch-major order, `cu_seqlens` int32 their per-sequence offsets (every sequence
+        non-empty).  `select_index` then indexes PACKED rows; returns [len(select_index), 128] (all T rows when
         None) in training mode, the last valid step of every sequence [B, 128] otherwise -- the values the reference
-        computes at those positions of its padded grid."""
+        computes at those positions of its padded grid.  The last `zero_tail` entries of `cu_seqlens` may be
+        one-token pseudo-sequences at PADDED positions (attention output 0 there, train.add_host_index)."""
         tr = self.training
         x = enc.layer_norm(seq_emb.reshape(-1, seq_emb.shape[-1]), self.emb_ln.weight, self.emb_ln.bias, self.emb_ln.eps,
                            index=packed_index, dropout_p=self.emb_dropout.p if tr else 0.0, out_dtype=torch.float32)
-        output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len)
+        output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
         users = packed_index // seq_len
         if not training_mode:
-            select_index = cu_seqlens[1:].to(torch.int64) - 1
+            select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1
         if select_index is not None:
             output = ops.gather_rows(output, select_index)
             users = users[select_index]

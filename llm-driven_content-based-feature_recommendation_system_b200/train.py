@@ -44,15 +44,27 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
     last = (valid.sum(dim=1) - 1).clamp(min=0)
     batch["last_index"] = torch.arange(B) * L + last
     batch["select_index"] = torch.cat([batch["valid_index"], batch["last_index"]])
-    # packed-token view of the same batch (encoder.py): sequence offsets and the last valid step of every sequence
+    # packed-token view of the same batch (encoder.py): the valid time steps in batch-major order, their sequence
+    # offsets, and the row DuoRec reads for every user.  The reference takes `last_indices = valid.sum(1) - 1`
+    # (v1_usertower_train.py:830) on its LEFT-padded grid, i.e. column len-1 counted from the left: a padded
+    # position whenever the sequence fills less than half of the window.  To stay a drop-in those positions are
+    # carried as extra one-token pseudo-sequences behind the valid tokens (`packed_zero_tail` of them: every key of
+    # such a query is masked in the reference, attention output 0).
     lens = valid.sum(dim=1)
     if bool((lens > 0).all()):
-        cu = torch.zeros(B + 1, dtype=torch.int32)
-        cu[1:] = torch.cumsum(lens, 0)
-        T = int(cu[-1])
+        T = int(lens.sum())
+        pos2packed = torch.full((B * L,), -1, dtype=torch.int64)
+        pos2packed[batch["valid_index"]] = torch.arange(T)
+        lp = pos2packed[batch["last_index"]]
+        extra = torch.nonzero(lp < 0).squeeze(1)                       # users whose "last" position is padding
+        lp[extra] = T + torch.arange(extra.numel())
+        cu = torch.zeros(B + 1 + extra.numel(), dtype=torch.int32)
+        cu[1:B + 1] = torch.cumsum(lens, 0)
+        cu[B + 1:] = T + 1 + torch.arange(extra.numel(), dtype=torch.int32)
+        batch["packed_index"] = torch.cat([batch["valid_index"], batch["last_index"][extra]])
         batch["cu_seqlens"] = cu
-        batch["last_packed"] = cu[1:].to(torch.int64) - 1
-        batch["select_packed"] = torch.cat([torch.arange(T), batch["last_packed"]])
+        batch["last_packed"] = lp
+        batch["select_packed"] = torch.cat([torch.arange(T), lp])
     if columns:
         tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
         ids, counts, pos_col = losses.item_columns(tgt)
@@ -69,7 +81,8 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
     if packed and "cu_seqlens" in batch:
         lp = batch["last_packed"]
         sel1 = batch["select_packed"] if loss_scope == "all" else torch.cat([lp, lp])
-        pk = dict(packed_index=batch["valid_index"], cu_seqlens=batch["cu_seqlens"])
+        pk = dict(packed_index=batch["packed_index"], cu_seqlens=batch["cu_seqlens"],
+                  packed_zero_tail=batch["cu_seqlens"].numel() - 1 - batch["item_ids"].shape[0])
         return (model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1, **pk, **extra),
                 model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=lp, **pk, **extra))
     li = batch["last_index"]
