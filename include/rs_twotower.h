@@ -194,10 +194,12 @@ int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, i
  * gradient.  The reference reads such rows: `last_indices = valid_mask.sum(1) - 1` (v1_usertower_train.py:830)
  * addresses its LEFT-padded grid from the left, i.e. a padded position whenever a sequence fills less than half
  * of the window; the packed encoder carries those positions as extra one-token sequences to reproduce it. */
-int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens,
+int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias /*[3*H*32] in_proj bias added on load, or NULL*/,
+                       const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens,
                        int n_heads, int head_dim, int max_len, int64_t zero_tail, float scale, float dropout_p,
                        uint64_t seed, void* out, float* lse, void* stream);
-int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* lse,
+int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* bias,
+                       const float* lse,
                        const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads, int head_dim,
                        int max_len, int64_t zero_tail, float scale, float dropout_p, uint64_t seed, void* d_qkv,
                        void* stream);
@@ -211,15 +213,23 @@ size_t rs_ln_bwd_workspace_bytes(int64_t n_rows);
 int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const int64_t* index, int64_t n_rows,
               int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p, uint64_t seed,
               void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
-/* out = x + dropout(y) (n elements, n % 4 == 0); backward of the y branch: dy = mask(g) / keep */
-int rs_dropout_add_fwd(const void* x, int x_dtype, const void* y, int y_dtype, int64_t n, float dropout_p,
-                       uint64_t seed, void* out, void* stream);
+/* The biases of the four Linear layers of an encoder layer are folded into the kernel that consumes the GEMM output
+ * (`bias` fp32 [n_cols] or NULL), so the GEMMs are plain matmuls and the bias gradients are column sums of tensors
+ * these kernels produce (rs_colsum) instead of separate reductions behind each GEMM.
+ * out = x + dropout(y + bias) (n elements = rows * n_cols); backward of the y branch: dy = mask(g) / keep */
+int rs_dropout_add_fwd(const void* x, int x_dtype, const void* y, int y_dtype, const float* bias, int64_t n_cols,
+                       int64_t n, float dropout_p, uint64_t seed, void* out, void* stream);
 int rs_dropout_bwd(const void* g, int g_dtype, int64_t n, float dropout_p, uint64_t seed, void* dy, int dy_dtype,
                    void* stream);
-/* out = dropout(gelu(z)), exact erf GELU (activation="gelu"); backward dz = mask(g)/keep * gelu'(z) */
-int rs_gelu_dropout_fwd(const void* z, int dtype, int64_t n, float dropout_p, uint64_t seed, void* out, void* stream);
-int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, int64_t n, float dropout_p, uint64_t seed, void* dz,
-                        void* stream);
+/* out = dropout(gelu(z + bias)), exact erf GELU (activation="gelu"); backward dz = mask(g)/keep * gelu'(z + bias) */
+int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, int64_t n_cols, int64_t n, float dropout_p,
+                        uint64_t seed, void* out, void* stream);
+int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
+                        float dropout_p, uint64_t seed, void* dz, void* stream);
+/* out[c] = sum_r x[r, c], fp32, fixed summation order (n_cols % 4 == 0, <= 1024) */
+size_t rs_colsum_workspace_bytes(int64_t n_rows, int64_t n_cols);
+int rs_colsum(const void* x, int dtype, int64_t n_rows, int64_t n_cols, float* out, void* workspace,
+              size_t workspace_bytes, void* stream);
 
 /* -------------------------------------------- C1..C5: fused in-batch softmax */
 
@@ -270,6 +280,21 @@ int rs_ce_fwd(const rs_ce_problem* p /*host*/, float* lse /*[M]*/, float* diag /
 int rs_ce_bwd(const rs_ce_problem* p /*host*/, const float* lse, const float* w_lse /*[M]*/,
               const float* w_diag /*[M] or NULL*/, const float* w_pos /*[M] or NULL*/, float* dA, float* dB,
               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same-user block of the distinct-item softmax (losses.logq_infonce_columns; the same-user mask of
+ * tower_code/v1_refine_usertower.py:848).  Rows are grouped by user (row_cu[n_users+1], <= 64 rows per user);
+ * pos_col[i] is the column (distinct item) of row i's target.  Per user, over its own rows i, j:
+ *   s_ij = scale*<u_i, cols[pos_col_j]> - col_bias[pos_col_j];  s_pos[i] = s_ii;
+ *   own_lse[i] = log sum_{j: pos_col_j != pos_col_i} exp(s_ij)   (-inf if none)
+ * Backward: d_u[n_rows,128] (overwritten), d_cols[n_cols,128] (ACCUMULATED: pass zeros), fp32, one row added per
+ * (user, item) instead of one per (row, item) pair.  u / cols: fp32, fp16 or bf16 [., 128]. */
+int rs_user_block_logits_fwd(const void* u, const void* cols, int dtype, const int64_t* pos_col, const int32_t* row_cu,
+                             int64_t n_users, int64_t n_cols, int64_t dim, int max_len, float scale,
+                             const float* col_bias, float* s_pos, float* own_lse, void* stream);
+int rs_user_block_logits_bwd(const void* u, const void* cols, int dtype, const int64_t* pos_col, const int32_t* row_cu,
+                             int64_t n_users, int64_t n_cols, int64_t dim, int max_len, float scale,
+                             const float* col_bias, const float* own_lse, const float* g_pos, const float* g_own,
+                             float* d_u, float* d_cols, void* stream);
 
 /* ------------------------------------------------------- R1: top-k retrieval */
 

@@ -55,15 +55,17 @@ PROTOTYPES = {
     "rs_bert_embed_fwd": (i32, [vp, i64, vp, vp, vp, vp, f32, vp, i64, i64, i64, f32, u64, vp, i32, vp, vp]),
     "rs_masked_mean_fwd": (i32, [vp, i32, vp, i64, i64, i64, vp, vp]),
     "rs_masked_mean_bwd": (i32, [vp, vp, i64, i64, i64, vp, i32, vp]),
-    "rs_attn_varlen_fwd": (i32, [vp, i32, vp, i64, i64, i32, i32, i32, i64, f32, f32, u64, vp, vp, vp]),
-    "rs_attn_varlen_bwd": (i32, [vp, vp, vp, i32, vp, vp, i64, i64, i32, i32, i32, i64, f32, f32, u64, vp, vp]),
+    "rs_attn_varlen_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, i32, i64, f32, f32, u64, vp, vp, vp]),
+    "rs_attn_varlen_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i64, i64, i32, i32, i32, i64, f32, f32, u64, vp, vp]),
+    "rs_colsum_workspace_bytes": (sz, [i64, i64]),
+    "rs_colsum": (i32, [vp, i32, i64, i64, vp, vp, sz, vp]),
     "rs_ln_fwd": (i32, [vp, i32, vp, i64, i64, vp, vp, f32, f32, u64, vp, i32, vp, vp, vp]),
     "rs_ln_bwd_workspace_bytes": (sz, [i64]),
     "rs_ln_bwd": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, vp, vp, f32, u64, vp, vp, vp, vp, sz, vp]),
-    "rs_dropout_add_fwd": (i32, [vp, i32, vp, i32, i64, f32, u64, vp, vp]),
+    "rs_dropout_add_fwd": (i32, [vp, i32, vp, i32, vp, i64, i64, f32, u64, vp, vp]),
     "rs_dropout_bwd": (i32, [vp, i32, i64, f32, u64, vp, i32, vp]),
-    "rs_gelu_dropout_fwd": (i32, [vp, i32, i64, f32, u64, vp, vp]),
-    "rs_gelu_dropout_bwd": (i32, [vp, vp, i32, i64, f32, u64, vp, vp]),
+    "rs_gelu_dropout_fwd": (i32, [vp, i32, vp, i64, i64, f32, u64, vp, vp]),
+    "rs_gelu_dropout_bwd": (i32, [vp, vp, i32, vp, i64, i64, f32, u64, vp, vp]),
     "rs_ce_workspace_bytes": (sz, [C.POINTER(CEProblem)]),
     "rs_ce_fwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_bwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, sz, vp]),
@@ -73,6 +75,8 @@ PROTOTYPES = {
     "rs_mine_hard_negatives": (i32, [vp, vp, vp, i64, i64, i64, f32, vp, vp, vp, vp, sz, vp]),
     "rs_sparse_logits_fwd": (i32, [vp, vp, i32, vp, i64, i64, i64, i64, f32, vp, vp, vp, vp, vp]),
     "rs_sparse_logits_bwd": (i32, [vp, vp, i32, vp, i64, i64, i64, i64, f32, vp, vp, vp, vp, vp, vp]),
+    "rs_user_block_logits_fwd": (i32, [vp, vp, i32, vp, vp, i64, i64, i64, i32, f32, vp, vp, vp, vp]),
+    "rs_user_block_logits_bwd": (i32, [vp, vp, i32, vp, vp, i64, i64, i64, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "rs_fm_fwd": (i32, [vp, vp, i64, i64, vp, i64, vp, i64, vp, vp, i32, vp, vp]),
     "rs_fm_bwd": (i32, [vp, vp, i64, i64, vp, i64, vp, vp, i32, i64, vp, vp, vp]),
 }

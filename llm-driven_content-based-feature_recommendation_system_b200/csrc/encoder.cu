@@ -63,6 +63,7 @@ template <int DT> using DTStore = typename DTStoreT<DT>::type;
 // ------------------------------------------------------------------------------------------------ attention
 struct AttnParams {
   const int* cu;            // [n_seq + 1] token offsets
+  const float* bias;        // [3*H*32] in_proj bias, added on load (NULL: none)
   int64_t n_seq;
   int H, max_len;
   int64_t zero_from;        // sequences b >= zero_from are fully masked queries: output 0, no gradient
@@ -72,49 +73,103 @@ struct AttnParams {
   uint64_t seed;
 };
 
-// stage `which` (0 = q, 1 = k, 2 = v) rows of one (sequence, head) into shared memory as fp32 [len][32]
+// stage rows [row0, row0+len) x 32 columns starting at col0 (+ bias) into shared memory as fp32 [len][32]
 template <int DT>
 __device__ __forceinline__ void stage_rows(float* dst, const void* src, int64_t row0, int len, int64_t row_stride,
-                                           int64_t col0, int lane) {
+                                           int64_t col0, const float* bias, int lane) {
   const int sub = lane >> 3, d4 = (lane & 7) * 4;
-  for (int j = sub; j < len; j += 4)
-    *reinterpret_cast<float4*>(dst + j * ENC_HD + d4) = ld4<DT>(src, (row0 + j) * row_stride + col0 + d4);
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b4 = ldg_f4(bias + col0 + d4);
+  for (int j = sub; j < len; j += 4) {
+    const float4 v = ld4<DT>(src, (row0 + j) * row_stride + col0 + d4);
+    *reinterpret_cast<float4*>(dst + j * ENC_HD + d4) = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+  }
 }
 
-template <int DT>
-__device__ __forceinline__ void load_row32(float (&r)[ENC_HD], const void* src, int64_t off) {
+// a lane's slice of a row: N consecutive values (N = 4, 8 or 16)
+template <int DT, int N>
+__device__ __forceinline__ void load_slice(float (&r)[N], const void* src, int64_t off, const float* bias, int64_t boff) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 v = ld4<DT>(src, off + 4 * q);
+  for (int q = 0; q < N / 4; ++q) {
+    float4 v = ld4<DT>(src, off + 4 * q);
+    if (bias) { const float4 b4 = ldg_f4(bias + boff + 4 * q); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
     r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
   }
 }
-__device__ __forceinline__ float dot_row32(const float (&r)[ENC_HD], const float* s) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+template <int N> __device__ __forceinline__ float dot_slice(const float (&r)[N], const float* s) {
+  float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < N / 4; ++q) {
     const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
     a0 = fmaf(r[4 * q], v.x, a0); a1 = fmaf(r[4 * q + 1], v.y, a1);
-    a2 = fmaf(r[4 * q + 2], v.z, a2); a3 = fmaf(r[4 * q + 3], v.w, a3);
+    a0 = fmaf(r[4 * q + 2], v.z, a0); a1 = fmaf(r[4 * q + 3], v.w, a1);
   }
-  return (a0 + a1) + (a2 + a3);
+  return a0 + a1;
 }
-__device__ __forceinline__ void axpy_row32(float (&acc)[ENC_HD], float a, const float* s) {
+template <int N> __device__ __forceinline__ void axpy_slice(float (&acc)[N], float a, const float* s) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < N / 4; ++q) {
     const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
     acc[4 * q] = fmaf(a, v.x, acc[4 * q]); acc[4 * q + 1] = fmaf(a, v.y, acc[4 * q + 1]);
     acc[4 * q + 2] = fmaf(a, v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a, v.w, acc[4 * q + 3]);
   }
 }
-template <int DT>
-__device__ __forceinline__ void store_row32(void* dst, int64_t off, const float (&r)[ENC_HD], float s) {
+template <int DT, int N>
+__device__ __forceinline__ void store_slice(void* dst, int64_t off, const float (&r)[N], float s) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q)
+  for (int q = 0; q < N / 4; ++q)
     st4<DT>(dst, off + 4 * q, make_float4(r[4 * q] * s, r[4 * q + 1] * s, r[4 * q + 2] * s, r[4 * q + 3] * s));
 }
+// sum over the R consecutive lanes that share a row
+template <int R> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = R / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-// one warp per (sequence, head); lane = query row (two rows per lane when the sequence is longer than 32)
+// One (sequence, head) with R lanes per query row (each lane owns 32/R of the 32 dims) and 32/R rows per pass:
+// short sequences -- the common case, mean length ~13 -- keep all 32 lanes busy instead of one lane per row.
+template <int DT, int R>
+__device__ __forceinline__ void attn_fwd_item(const void* __restrict__ qkv, const AttnParams& p, const float* sK,
+                                              const float* sV, int64_t t0, int len, int h, int lane,
+                                              void* __restrict__ out, float* __restrict__ lse) {
+  constexpr int N = ENC_HD / R, RPP = 32 / R;
+  const int sub = lane % R, rl = lane / R, d0 = sub * N;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int r0 = 0; r0 < len; r0 += RPP) {
+    const int i = r0 + rl;
+    const bool act = i < len;
+    float q[N], acc[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) { q[d] = 0.f; acc[d] = 0.f; }
+    if (act) load_slice<DT, N>(q, qkv, (t0 + i) * rs_ + h * ENC_HD + d0, p.bias, h * ENC_HD + d0);
+    float m = -INFINITY, l = 0.f;
+    const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
+    const int jmax = min(len - 1, r0 + RPP - 1);
+    for (int j = 0; j <= jmax; ++j) {
+      const float s = group_sum<R>(dot_slice<N>(q, sK + j * ENC_HD + d0)) * p.scale;
+      if (act && j <= i) {
+        if (s > m) {
+          const float c = __expf(m - s);
+          l *= c;
+#pragma unroll
+          for (int d = 0; d < N; ++d) acc[d] *= c;
+          m = s;
+        }
+        const float pr = __expf(s - m);
+        l += pr;
+        float pk = pr;
+        if (p.drop_thresh) pk = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? pr * p.inv_keep : 0.f;
+        axpy_slice<N>(acc, pk, sV + j * ENC_HD + d0);
+      }
+    }
+    if (act) {
+      store_slice<DT, N>(out, (t0 + i) * os_ + h * ENC_HD + d0, acc, 1.f / l);
+      if (sub == 0) lse[(t0 + i) * p.H + h] = m + __logf(l);
+    }
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const void* __restrict__ qkv, AttnParams p,
                                                        void* __restrict__ out, float* __restrict__ lse) {
@@ -136,46 +191,91 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const void* __restrict__ 
       }
       continue;
     }
-    stage_rows<DT>(sK, qkv, t0, len, rs_, os_ + h * ENC_HD, lane);
-    stage_rows<DT>(sV, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, lane);
+    stage_rows<DT>(sK, qkv, t0, len, rs_, os_ + h * ENC_HD, p.bias, lane);
+    stage_rows<DT>(sV, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);
     __syncwarp();
-    for (int r0 = 0; r0 < len; r0 += 32) {
-      const int i = r0 + lane;
-      const bool act = i < len;
-      float q[ENC_HD], acc[ENC_HD];
-      if (act) load_row32<DT>(q, qkv, (t0 + i) * rs_ + h * ENC_HD);
-#pragma unroll
-      for (int d = 0; d < ENC_HD; ++d) acc[d] = 0.f;
-      float m = -INFINITY, l = 0.f;
-      const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
-      const int jmax = min(len - 1, r0 + 31);
-      for (int j = 0; j <= jmax; ++j) {
-        if (act && j <= i) {
-          const float s = dot_row32(q, sK + j * ENC_HD) * p.scale;
-          if (s > m) {
-            const float c = __expf(m - s);
-            l *= c;
-#pragma unroll
-            for (int d = 0; d < ENC_HD; ++d) acc[d] *= c;
-            m = s;
-          }
-          const float pr = __expf(s - m);
-          l += pr;
-          float pk = pr;
-          if (p.drop_thresh) pk = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? pr * p.inv_keep : 0.f;
-          axpy_row32(acc, pk, sV + j * ENC_HD);
-        }
-      }
-      if (act) {
-        store_row32<DT>(out, (t0 + i) * os_ + h * ENC_HD, acc, 1.f / l);
-        lse[(t0 + i) * p.H + h] = m + __logf(l);
-      }
-    }
+    if (len <= 4) attn_fwd_item<DT, 8>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
+    else if (len <= 8) attn_fwd_item<DT, 4>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
+    else attn_fwd_item<DT, 2>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
     __syncwarp();
   }
 }
 
-// backward: dQ with lane = query row (K, V staged), then dK / dV with lane = key row (Q, dO staged)
+// dQ_i = scale * sum_{j<=i} dS_ij K_j          (sA = K, sB = V staged; lane group = query row)
+template <int DT, int R>
+__device__ __forceinline__ void attn_bwd_q(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                           const AttnParams& p, const float* sA, const float* sB, const float* sLse,
+                                           const float* sDelta, int64_t t0, int len, int h, int lane,
+                                           void* __restrict__ d_qkv) {
+  constexpr int N = ENC_HD / R, RPP = 32 / R;
+  const int sub = lane % R, rl = lane / R, d0 = sub * N;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int r0 = 0; r0 < len; r0 += RPP) {
+    const int i = r0 + rl;
+    const bool act = i < len;
+    float q[N], g[N], dq[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) { q[d] = 0.f; g[d] = 0.f; dq[d] = 0.f; }
+    if (act) {
+      load_slice<DT, N>(q, qkv, (t0 + i) * rs_ + h * ENC_HD + d0, p.bias, h * ENC_HD + d0);
+      load_slice<DT, N>(g, d_out, (t0 + i) * os_ + h * ENC_HD + d0, nullptr, 0);
+    }
+    const float li = act ? sLse[i] : 0.f, di = act ? sDelta[i] : 0.f;
+    const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
+    const int jmax = min(len - 1, r0 + RPP - 1);
+    for (int j = 0; j <= jmax; ++j) {
+      const float s = group_sum<R>(dot_slice<N>(q, sA + j * ENC_HD + d0));
+      float dp = group_sum<R>(dot_slice<N>(g, sB + j * ENC_HD + d0));
+      if (act && j <= i) {
+        const float pr = __expf(s * p.scale - li);
+        if (p.drop_thresh) dp = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? dp * p.inv_keep : 0.f;
+        axpy_slice<N>(dq, pr * (dp - di), sA + j * ENC_HD + d0);
+      }
+    }
+    if (act) store_slice<DT, N>(d_qkv, (t0 + i) * rs_ + h * ENC_HD + d0, dq, p.scale);
+  }
+}
+
+// dK_j = scale * sum_{i>=j} dS_ij Q_i,  dV_j = sum_{i>=j} P~_ij dO_i     (sA = Q, sB = dO staged; lane group = key row)
+template <int DT, int R>
+__device__ __forceinline__ void attn_bwd_kv(const void* __restrict__ qkv, const AttnParams& p, const float* sA,
+                                            const float* sB, const float* sLse, const float* sDelta, int64_t t0,
+                                            int len, int h, int lane, void* __restrict__ d_qkv) {
+  constexpr int N = ENC_HD / R, RPP = 32 / R;
+  const int sub = lane % R, rl = lane / R, d0 = sub * N;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int r0 = 0; r0 < len; r0 += RPP) {
+    const int j = r0 + rl;
+    const bool act = j < len;
+    float k[N], v[N], dk[N], dv[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) { k[d] = 0.f; v[d] = 0.f; dk[d] = 0.f; dv[d] = 0.f; }
+    if (act) {
+      load_slice<DT, N>(k, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + d0, p.bias, os_ + h * ENC_HD + d0);
+      load_slice<DT, N>(v, qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + d0, p.bias, 2 * os_ + h * ENC_HD + d0);
+    }
+    for (int i = r0; i < len; ++i) {
+      const float s = group_sum<R>(dot_slice<N>(k, sA + i * ENC_HD + d0));
+      float dp = group_sum<R>(dot_slice<N>(v, sB + i * ENC_HD + d0));
+      if (act && i >= j) {
+        const float pr = __expf(s * p.scale - sLse[i]);
+        float pk = pr;
+        if (p.drop_thresh) {
+          const bool keep = rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh;
+          dp = keep ? dp * p.inv_keep : 0.f;
+          pk = keep ? pr * p.inv_keep : 0.f;
+        }
+        axpy_slice<N>(dv, pk, sB + i * ENC_HD + d0);
+        axpy_slice<N>(dk, pr * (dp - sDelta[i]), sA + i * ENC_HD + d0);
+      }
+    }
+    if (act) {
+      store_slice<DT, N>(d_qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + d0, dk, p.scale);
+      store_slice<DT, N>(d_qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + d0, dv, 1.f);
+    }
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ qkv, const void* __restrict__ d_out,
                                                        const void* __restrict__ out, const float* __restrict__ lse,
@@ -213,69 +313,54 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ 
         if (j < len && (lane & 7) == 0) { sDelta[j] = part; sLse[j] = __ldg(lse + (t0 + j) * p.H + h); }
       }
     }
-    stage_rows<DT>(sA, qkv, t0, len, rs_, os_ + h * ENC_HD, lane);        // K
-    stage_rows<DT>(sB, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, lane);    // V
+    stage_rows<DT>(sA, qkv, t0, len, rs_, os_ + h * ENC_HD, p.bias, lane);        // K
+    stage_rows<DT>(sB, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);    // V
     __syncwarp();
-    // ---- pass A: dQ_i = scale * sum_{j<=i} dS_ij K_j
-    for (int r0 = 0; r0 < len; r0 += 32) {
-      const int i = r0 + lane;
-      const bool act = i < len;
-      float q[ENC_HD], g[ENC_HD], dq[ENC_HD];
-      if (act) {
-        load_row32<DT>(q, qkv, (t0 + i) * rs_ + h * ENC_HD);
-        load_row32<DT>(g, d_out, (t0 + i) * os_ + h * ENC_HD);
-      }
-#pragma unroll
-      for (int d = 0; d < ENC_HD; ++d) dq[d] = 0.f;
-      const float li = act ? sLse[i] : 0.f, di = act ? sDelta[i] : 0.f;
-      const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
-      const int jmax = min(len - 1, r0 + 31);
-      for (int j = 0; j <= jmax; ++j) {
-        if (act && j <= i) {
-          const float pr = __expf(dot_row32(q, sA + j * ENC_HD) * p.scale - li);
-          float dp = dot_row32(g, sB + j * ENC_HD);
-          if (p.drop_thresh) dp = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? dp * p.inv_keep : 0.f;
-          axpy_row32(dq, pr * (dp - di), sA + j * ENC_HD);
-        }
-      }
-      if (act) store_row32<DT>(d_qkv, (t0 + i) * rs_ + h * ENC_HD, dq, p.scale);
-    }
+    if (len <= 4) attn_bwd_q<DT, 8>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+    else if (len <= 8) attn_bwd_q<DT, 4>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+    else attn_bwd_q<DT, 2>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
     __syncwarp();
-    stage_rows<DT>(sA, qkv, t0, len, rs_, h * ENC_HD, lane);              // Q
-    stage_rows<DT>(sB, d_out, t0, len, os_, h * ENC_HD, lane);            // dO
+    stage_rows<DT>(sA, qkv, t0, len, rs_, h * ENC_HD, p.bias, lane);              // Q
+    stage_rows<DT>(sB, d_out, t0, len, os_, h * ENC_HD, nullptr, lane);           // dO
     __syncwarp();
-    // ---- pass B: dK_j = scale * sum_{i>=j} dS_ij Q_i,  dV_j = sum_{i>=j} P~_ij dO_i
-    for (int r0 = 0; r0 < len; r0 += 32) {
-      const int j = r0 + lane;
-      const bool act = j < len;
-      float k[ENC_HD], v[ENC_HD], dk[ENC_HD], dv[ENC_HD];
-      if (act) {
-        load_row32<DT>(k, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD);
-        load_row32<DT>(v, qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD);
-      }
-#pragma unroll
-      for (int d = 0; d < ENC_HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
-      for (int i = r0; i < len; ++i) {
-        if (act && i >= j) {
-          const float pr = __expf(dot_row32(k, sA + i * ENC_HD) * p.scale - sLse[i]);
-          float dp = dot_row32(v, sB + i * ENC_HD);
-          float pk = pr;
-          if (p.drop_thresh) {
-            const bool keep = rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh;
-            dp = keep ? dp * p.inv_keep : 0.f;
-            pk = keep ? pr * p.inv_keep : 0.f;
-          }
-          axpy_row32(dv, pk, sB + i * ENC_HD);
-          axpy_row32(dk, pr * (dp - sDelta[i]), sA + i * ENC_HD);
-        }
-      }
-      if (act) {
-        store_row32<DT>(d_qkv, (t0 + j) * rs_ + os_ + h * ENC_HD, dk, p.scale);
-        store_row32<DT>(d_qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD, dv, 1.f);
-      }
-    }
+    if (len <= 4) attn_bwd_kv<DT, 8>(qkv, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+    else if (len <= 8) attn_bwd_kv<DT, 4>(qkv, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+    else attn_bwd_kv<DT, 2>(qkv, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
     __syncwarp();
   }
+}
+
+// out[c] = sum_r x[r, c]  -- column sums of a [n_rows, n_cols] matrix (bias gradients), two deterministic stages:
+// thread t of a CTA owns column group (t % (n_cols/4)) and walks rows t / (n_cols/4), + row-groups ...; per-CTA partials
+template <int DT>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ x, int64_t n_rows, int n_cols,
+                                                             float* __restrict__ part /*[grid][n_cols]*/) {
+  extern __shared__ float4 cred[];                 // [rows_per_iter][n_cols/4]
+  const int c4n = n_cols >> 2;
+  const int rpi = blockDim.x / c4n;                // rows handled per iteration by this CTA
+  const int c4 = threadIdx.x % c4n, rr = threadIdx.x / c4n;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rr < rpi)
+    for (int64_t r = (int64_t)blockIdx.x * rpi + rr; r < n_rows; r += (int64_t)gridDim.x * rpi) {
+      const float4 v = ld4<DT>(x, r * n_cols + 4 * c4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  if (rr < rpi) cred[rr * c4n + c4] = s;
+  __syncthreads();
+  if (rr == 0) {
+    for (int k = 1; k < rpi; ++k) {
+      const float4 t = cred[k * c4n + c4];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * n_cols + 4 * c4) = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int n_blocks, int n_cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  float s = 0.f;
+  for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * n_cols + c];
+  out[c] = s;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm(128)
@@ -372,14 +457,19 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ part, int n_blo
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise
-// out = x + dropout(y)     x, out fp32 (or DTX), y DTY
+// out = x + dropout(y + bias)     x, out fp32 (or DTX), y DTY, bias fp32 [4*c4n] or NULL
 template <int DTX, int DTY>
 __global__ void __launch_bounds__(256) dropout_add_fwd_kernel(const void* __restrict__ x, const void* __restrict__ y,
-                                                              int64_t n4, uint32_t drop_thresh, float inv_keep,
-                                                              uint64_t seed, void* __restrict__ out) {
+                                                              const float* __restrict__ bias, int c4n, int64_t n4,
+                                                              uint32_t drop_thresh, float inv_keep, uint64_t seed,
+                                                              void* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = ld4<DTX>(x, 4 * i);
     float4 b = ld4<DTY>(y, 4 * i);
+    if (bias) {
+      const float4 b4 = ldg_f4(bias + 4 * (int)(i % c4n));
+      b.x += b4.x; b.y += b4.y; b.z += b4.z; b.w += b4.w;
+    }
     if (drop_thresh) {
       const uint32_t e = (uint32_t)i;
       b.x = (rnd32(seed, e, 0u) >= drop_thresh) ? b.x * inv_keep : 0.f;
@@ -418,13 +508,19 @@ __device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.f + erff
 __device__ __forceinline__ float gelu_grad_f(float z) {
   return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
 }
-// out = dropout(gelu(z)) ; BWD: dz = dropout_mask(g) * gelu'(z)
+// out = dropout(gelu(z + bias)) ; BWD: dz = dropout_mask(g) * gelu'(z + bias)
 template <int DT, bool BWD>
 __global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restrict__ z, const void* __restrict__ g,
-                                                           int64_t n4, uint32_t drop_thresh, float inv_keep,
-                                                           uint64_t seed, void* __restrict__ out) {
+                                                           const float* __restrict__ bias, int c4n, int64_t n4,
+                                                           uint32_t drop_thresh, float inv_keep, uint64_t seed,
+                                                           void* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 a = ld4<DT>(z, 4 * i);
+    float4 a = ld4<DT>(z, 4 * i);
+    if (bias) {
+      const float4 b4 = ldg_f4(bias + 4 * (int)(i % c4n));
+      // the reference's Linear rounds z + b to the activation dtype before the GELU
+      a = make_float4(round_dt<DT>(a.x + b4.x), round_dt<DT>(a.y + b4.y), round_dt<DT>(a.z + b4.z), round_dt<DT>(a.w + b4.w));
+    }
     float4 o;
     if (BWD) {
       const float4 gg = ld4<DT>(g, 4 * i);
@@ -474,7 +570,7 @@ static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, 
   return RS_OK;
 }
 
-extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_seqlens, int64_t n_seq,
+extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias, const int32_t* cu_seqlens, int64_t n_seq,
                                   int64_t total_tokens, int n_heads, int head_dim, int max_len, int64_t zero_tail,
                                   float scale, float dropout_p, uint64_t seed, void* out, float* lse, void* stream) {
   int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p, zero_tail);
@@ -483,7 +579,7 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_
   if (!qkv || !cu_seqlens || !out || !lse) return RS_ERR_BAD_ARG;
   AttnParams p;
   max_len = (max_len + 3) & ~3;      // keeps every per-warp shared-memory region 16-byte aligned
-  p.cu = cu_seqlens; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
+  p.cu = cu_seqlens; p.bias = bias; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
   p.zero_from = n_seq - zero_tail;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const size_t smem = (size_t)4 * 2 * max_len * ENC_HD * sizeof(float);
@@ -498,7 +594,8 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const int32_t* cu_
   return RS_OK;
 }
 
-extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* lse,
+extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* bias,
+                                  const float* lse,
                                   const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads,
                                   int head_dim, int max_len, int64_t zero_tail, float scale, float dropout_p,
                                   uint64_t seed, void* d_qkv, void* stream) {
@@ -508,7 +605,7 @@ extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void
   if (!qkv || !d_out || !out || !lse || !cu_seqlens || !d_qkv) return RS_ERR_BAD_ARG;
   AttnParams p;
   max_len = (max_len + 3) & ~3;      // keeps every per-warp shared-memory region 16-byte aligned
-  p.cu = cu_seqlens; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
+  p.cu = cu_seqlens; p.bias = bias; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
   p.zero_from = n_seq - zero_tail;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const size_t smem = (size_t)4 * (2 * max_len * ENC_HD + 2 * max_len) * sizeof(float);
@@ -519,6 +616,30 @@ extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void
     if (e != cudaSuccess) return (int)e;
     attn_bwd_kernel<DT><<<grid, 128, smem, st>>>(qkv, d_out, out, lse, p, d_qkv);
   });
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+static int colsum_grid(int64_t n_rows, int rpi) {
+  int64_t g = (n_rows + rpi * 8 - 1) / (rpi * 8);
+  const int64_t cap = RS_NUM_SMS * 4;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+extern "C" size_t rs_colsum_workspace_bytes(int64_t n_rows, int64_t n_cols) {
+  return (size_t)RS_NUM_SMS * 4 * (size_t)n_cols * sizeof(float);
+}
+extern "C" int rs_colsum(const void* x, int dtype, int64_t n_rows, int64_t n_cols, float* out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!x || !out || !workspace || n_rows < 0 || n_cols <= 0 || (n_cols & 3) || n_cols > 1024) return RS_ERR_BAD_ARG;
+  if (workspace_bytes < rs_colsum_workspace_bytes(n_rows, n_cols)) return RS_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c4n = (int)(n_cols / 4), rpi = 256 / c4n;
+  const int grid = colsum_grid(n_rows, rpi);
+  const size_t smem = (size_t)rpi * c4n * sizeof(float4);
+  float* part = (float*)workspace;
+  ENC_DISPATCH1(dtype, DT, (colsum_partial_kernel<DT><<<grid, 256, smem, st>>>(x, n_rows, (int)n_cols, part)));
+  RS_LAUNCH_CHECK();
+  colsum_final_kernel<<<(int)((n_cols + 127) / 128), 128, 0, st>>>(part, grid, (int)n_cols, out);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -572,16 +693,16 @@ static int ew_grid(int64_t n4) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-extern "C" int rs_dropout_add_fwd(const void* x, int x_dtype, const void* y, int y_dtype, int64_t n, float dropout_p,
-                                  uint64_t seed, void* out, void* stream) {
+extern "C" int rs_dropout_add_fwd(const void* x, int x_dtype, const void* y, int y_dtype, const float* bias,
+                                  int64_t n_cols, int64_t n, float dropout_p, uint64_t seed, void* out, void* stream) {
   if (n == 0) return RS_OK;
-  if (!x || !y || !out || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  if (!x || !y || !out || n < 0 || (n & 3) || n_cols <= 0 || (n_cols & 3) || n % n_cols) return RS_ERR_BAD_ARG;
   if (n / 4 >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
   uint32_t th; float ik;
   drop_consts(dropout_p, th, ik);
   cudaStream_t st = (cudaStream_t)stream;
   ENC_DISPATCH1(x_dtype, DTX, ENC_DISPATCH1(y_dtype, DTY, (dropout_add_fwd_kernel<DTX, DTY><<<ew_grid(n / 4), 256, 0, st>>>(
-      x, y, n / 4, th, ik, seed, out))));
+      x, y, bias, (int)(n_cols / 4), n / 4, th, ik, seed, out))));
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -599,27 +720,27 @@ extern "C" int rs_dropout_bwd(const void* g, int g_dtype, int64_t n, float dropo
   return RS_OK;
 }
 
-extern "C" int rs_gelu_dropout_fwd(const void* z, int dtype, int64_t n, float dropout_p, uint64_t seed, void* out,
-                                   void* stream) {
+extern "C" int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, int64_t n_cols, int64_t n,
+                                   float dropout_p, uint64_t seed, void* out, void* stream) {
   if (n == 0) return RS_OK;
-  if (!z || !out || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  if (!z || !out || n < 0 || (n & 3) || n_cols <= 0 || (n_cols & 3) || n % n_cols) return RS_ERR_BAD_ARG;
   if (n / 4 >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
   uint32_t th; float ik;
   drop_consts(dropout_p, th, ik);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, false><<<ew_grid(n / 4), 256, 0, st>>>(z, nullptr, n / 4, th, ik, seed, out)));
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, false><<<ew_grid(n / 4), 256, 0, st>>>(z, nullptr, bias, (int)(n_cols / 4), n / 4, th, ik, seed, out)));
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
 
-extern "C" int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, int64_t n, float dropout_p, uint64_t seed,
-                                   void* dz, void* stream) {
+extern "C" int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
+                                   float dropout_p, uint64_t seed, void* dz, void* stream) {
   if (n == 0) return RS_OK;
-  if (!z || !g || !dz || n < 0 || (n & 3)) return RS_ERR_BAD_ARG;
+  if (!z || !g || !dz || n < 0 || (n & 3) || n_cols <= 0 || (n_cols & 3) || n % n_cols) return RS_ERR_BAD_ARG;
   uint32_t th; float ik;
   drop_consts(dropout_p, th, ik);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, true><<<ew_grid(n / 4), 256, 0, st>>>(z, g, n / 4, th, ik, seed, dz)));
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, true><<<ew_grid(n / 4), 256, 0, st>>>(z, g, bias, (int)(n_cols / 4), n / 4, th, ik, seed, dz)));
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

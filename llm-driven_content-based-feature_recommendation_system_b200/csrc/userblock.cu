@@ -1,0 +1,229 @@
+// Same-user correction of the distinct-item in-batch softmax (losses.logq_infonce_columns, C2 of SURVEY.md 8a).
+//
+// The fused tensor-core pass scores every row against the DISTINCT items of the batch with their multiplicities.
+// The reference also masks the columns that belong to the row's own user (tower_code/v1_refine_usertower.py:848):
+// those are at most L per row and they all live in the row's own user block, so they are handled here as one small
+// dense block per user: rows i of user b  x  the target items of the same rows,
+//
+//     s_ij    = scale * <u_i, c[pos_col_j]> - bias[pos_col_j]          i, j in the user's rows
+//     s_pos_i = s_ii                                                   (the label logit)
+//     own_lse_i = log sum_{j : pos_col_j != pos_col_i} exp(s_ij)       (-inf when the user has no other item)
+//
+// which the host combines with the dense pass: Z_i = e^{lse0_i} + e^{s_pos_i} - e^{own_lse_i}.
+// One CTA per user; the user's u rows and item rows are staged in shared memory once (fp32, padded stride), the
+// l x l logits live in shared memory, and the backward adds ONE gradient row per (user, item) into d_cols instead
+// of one per (row, item) pair.
+#include "common.cuh"
+#include "../../include/rs_twotower.h"
+
+namespace rs {
+
+#define UB_D 128
+#define UB_STRIDE 132          // padded row stride (floats): 128-bit reads of 32 different rows hit all banks evenly
+#define UB_THREADS 128
+
+struct UbParams {
+  const void* u; const void* cols;
+  const int64_t* pos_col;     // [n_rows]
+  const int* row_cu;          // [n_users + 1] row offsets of the users
+  const float* col_bias;      // [n_cols] or NULL
+  int64_t n_users, n_cols;
+  int max_len;
+  float scale;
+};
+
+template <int DT>
+__device__ __forceinline__ float4 ub_ld4(const void* base, int64_t off) {
+  if constexpr (DT == RS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+  else {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off));
+    float2 a, b;
+    if constexpr (DT == RS_BF16) { a = unpack_bf16(w.x); b = unpack_bf16(w.y); }
+    else { a = unpack_f16(w.x); b = unpack_f16(w.y); }
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+// stage the user's rows: sU[i][:] = u[r0 + i], sC[i][:] = cols[pos_col[r0 + i]]; sCol[i] = pos_col (int), sBias[i]
+template <int DT>
+__device__ __forceinline__ void ub_stage(const UbParams& p, int64_t r0, int len, float* sU, float* sC, int* sCol,
+                                         float* sBias) {
+  for (int i = threadIdx.x; i < len; i += UB_THREADS) {
+    const int64_t c = __ldg(p.pos_col + r0 + i);
+    const bool ok = c >= 0 && c < p.n_cols;
+    sCol[i] = ok ? (int)c : -1;
+    sBias[i] = (ok && p.col_bias) ? __ldg(p.col_bias + c) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = w; i < len; i += UB_THREADS / 32) {
+    *reinterpret_cast<float4*>(sU + i * UB_STRIDE + 4 * lane) = ub_ld4<DT>(p.u, (r0 + i) * UB_D + 4 * lane);
+    const int c = sCol[i];
+    *reinterpret_cast<float4*>(sC + i * UB_STRIDE + 4 * lane) =
+        c >= 0 ? ub_ld4<DT>(p.cols, (int64_t)c * UB_D + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+}
+
+// sS[i][j] = scale * <u_i, c_j> - bias_j for all (i, j) of the block
+__device__ __forceinline__ void ub_logits(const UbParams& p, int len, const float* sU, const float* sC,
+                                          const float* sBias, float* sS) {
+  for (int pr = threadIdx.x; pr < len * len; pr += UB_THREADS) {
+    const int i = pr / len, j = pr - i * len;
+    const float* a = sU + i * UB_STRIDE;
+    const float* b = sC + j * UB_STRIDE;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < UB_D; k += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(a + k), y = *reinterpret_cast<const float4*>(b + k);
+      a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1); a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
+    }
+    sS[i * p.max_len + j] = ((a0 + a1) + (a2 + a3)) * p.scale - sBias[j];
+  }
+  __syncthreads();
+}
+
+template <int DT>
+__global__ void __launch_bounds__(UB_THREADS) ub_fwd_kernel(UbParams p, float* __restrict__ s_pos,
+                                                            float* __restrict__ own_lse) {
+  extern __shared__ float smem[];
+  float* sU = smem;
+  float* sC = sU + p.max_len * UB_STRIDE;
+  float* sS = sC + p.max_len * UB_STRIDE;
+  float* sBias = sS + p.max_len * p.max_len;
+  int* sCol = reinterpret_cast<int*>(sBias + p.max_len);
+  for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
+    const int64_t r0 = __ldg(p.row_cu + b);
+    const int len = min((int)(__ldg(p.row_cu + b + 1) - r0), p.max_len);
+    __syncthreads();
+    ub_stage<DT>(p, r0, len, sU, sC, sCol, sBias);
+    ub_logits(p, len, sU, sC, sBias, sS);
+    for (int i = threadIdx.x; i < len; i += UB_THREADS) {
+      const int ci = sCol[i];
+      float m = -INFINITY;
+      for (int j = 0; j < len; ++j)
+        if (sCol[j] != ci && sCol[j] >= 0) m = fmaxf(m, sS[i * p.max_len + j]);
+      float l = 0.f;
+      if (m > -INFINITY)
+        for (int j = 0; j < len; ++j)
+          if (sCol[j] != ci && sCol[j] >= 0) l += __expf(sS[i * p.max_len + j] - m);
+      s_pos[r0 + i] = ci >= 0 ? sS[i * p.max_len + i] : -INFINITY;
+      own_lse[r0 + i] = m > -INFINITY ? m + __logf(l) : -INFINITY;
+    }
+  }
+}
+
+// d_u[i] = scale * sum_j dS_ij c_j ;  d_cols[pos_col_j] += scale * sum_i dS_ij u_i
+//   dS_ij = g_own_i * exp(s_ij - own_lse_i) for pos_col_j != pos_col_i,  dS_ii = g_pos_i
+template <int DT>
+__global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const float* __restrict__ own_lse,
+                                                            const float* __restrict__ g_pos,
+                                                            const float* __restrict__ g_own, float* __restrict__ d_u,
+                                                            float* __restrict__ d_cols) {
+  extern __shared__ float smem[];
+  float* sU = smem;
+  float* sC = sU + p.max_len * UB_STRIDE;
+  float* sS = sC + p.max_len * UB_STRIDE;
+  float* sBias = sS + p.max_len * p.max_len;
+  int* sCol = reinterpret_cast<int*>(sBias + p.max_len);
+  for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
+    const int64_t r0 = __ldg(p.row_cu + b);
+    const int len = min((int)(__ldg(p.row_cu + b + 1) - r0), p.max_len);
+    __syncthreads();
+    ub_stage<DT>(p, r0, len, sU, sC, sCol, sBias);
+    ub_logits(p, len, sU, sC, sBias, sS);
+    // logits -> coefficients, in place
+    for (int pr = threadIdx.x; pr < len * len; pr += UB_THREADS) {
+      const int i = pr / len, j = pr - i * len;
+      const int ci = sCol[i], cj = sCol[j];
+      float c = 0.f;
+      if (cj >= 0 && ci >= 0) {
+        if (i == j) c = __ldg(g_pos + r0 + i);
+        else if (cj != ci) {
+          const float ol = __ldg(own_lse + r0 + i);
+          c = ol > -INFINITY ? __ldg(g_own + r0 + i) * __expf(sS[pr / len * p.max_len + j] - ol) : 0.f;
+        }
+      }
+      sS[i * p.max_len + j] = c * p.scale;
+    }
+    __syncthreads();
+    // thread k owns feature k of every row
+    const int k = threadIdx.x;
+    for (int i = 0; i < len; ++i) {
+      float acc = 0.f;
+      for (int j = 0; j < len; ++j) acc = fmaf(sS[i * p.max_len + j], sC[j * UB_STRIDE + k], acc);
+      d_u[(r0 + i) * UB_D + k] = acc;
+    }
+    for (int j = 0; j < len; ++j) {
+      const int cj = sCol[j];
+      if (cj < 0) continue;
+      float acc = 0.f;
+      for (int i = 0; i < len; ++i) acc = fmaf(sS[i * p.max_len + j], sU[i * UB_STRIDE + k], acc);
+      atomicAdd(d_cols + (int64_t)cj * UB_D + k, acc);
+    }
+  }
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+static size_t ub_smem(int max_len) {
+  return ((size_t)2 * max_len * UB_STRIDE + (size_t)max_len * max_len + 2 * (size_t)max_len) * sizeof(float);
+}
+
+#define UB_DISPATCH(dt, NAME, ...)                                      \
+  switch (dt) {                                                         \
+    case RS_F32: { constexpr int NAME = RS_F32; __VA_ARGS__; break; }   \
+    case RS_F16: { constexpr int NAME = RS_F16; __VA_ARGS__; break; }   \
+    case RS_BF16: { constexpr int NAME = RS_BF16; __VA_ARGS__; break; } \
+    default: return RS_ERR_BAD_ARG;                                     \
+  }
+
+static int ub_check(const void* u, const void* cols, const int64_t* pos_col, const int32_t* row_cu, int64_t n_users,
+                    int64_t n_cols, int64_t dim, int max_len) {
+  if (!u || !cols || !pos_col || !row_cu || n_users <= 0 || n_cols <= 0 || max_len <= 0) return RS_ERR_BAD_ARG;
+  if (dim != UB_D || max_len > 64) return RS_ERR_UNSUPPORTED;
+  return RS_OK;
+}
+
+extern "C" int rs_user_block_logits_fwd(const void* u, const void* cols, int dtype, const int64_t* pos_col,
+                                        const int32_t* row_cu, int64_t n_users, int64_t n_cols, int64_t dim, int max_len,
+                                        float scale, const float* col_bias, float* s_pos, float* own_lse, void* stream) {
+  int rc = ub_check(u, cols, pos_col, row_cu, n_users, n_cols, dim, max_len);
+  if (rc != RS_OK) return rc;
+  if (!s_pos || !own_lse) return RS_ERR_BAD_ARG;
+  max_len = (max_len + 3) & ~3;
+  UbParams p = {u, cols, pos_col, row_cu, col_bias, n_users, n_cols, max_len, scale};
+  const size_t smem = ub_smem(max_len);
+  const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 8 ? n_users : (int64_t)RS_NUM_SMS * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  UB_DISPATCH(dtype, DT, {
+    cudaError_t e = cudaFuncSetAttribute(ub_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ub_fwd_kernel<DT><<<grid, UB_THREADS, smem, st>>>(p, s_pos, own_lse);
+  });
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_user_block_logits_bwd(const void* u, const void* cols, int dtype, const int64_t* pos_col,
+                                        const int32_t* row_cu, int64_t n_users, int64_t n_cols, int64_t dim, int max_len,
+                                        float scale, const float* col_bias, const float* own_lse, const float* g_pos,
+                                        const float* g_own, float* d_u, float* d_cols, void* stream) {
+  int rc = ub_check(u, cols, pos_col, row_cu, n_users, n_cols, dim, max_len);
+  if (rc != RS_OK) return rc;
+  if (!own_lse || !g_pos || !g_own || !d_u || !d_cols) return RS_ERR_BAD_ARG;
+  max_len = (max_len + 3) & ~3;
+  UbParams p = {u, cols, pos_col, row_cu, col_bias, n_users, n_cols, max_len, scale};
+  const size_t smem = ub_smem(max_len);
+  const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 8 ? n_users : (int64_t)RS_NUM_SMS * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  UB_DISPATCH(dtype, DT, {
+    cudaError_t e = cudaFuncSetAttribute(ub_bwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ub_bwd_kernel<DT><<<grid, UB_THREADS, smem, st>>>(p, own_lse, g_pos, g_own, d_u, d_cols);
+  });
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}

@@ -13,6 +13,7 @@ tokens [T, 128] (T ~ 25 % of B*L on H&M-shaped batches), delimited by `cu_seqlen
     qkv = in_proj(h)                                library GEMM (nn.Linear in the reference as well)
     o   = causal softmax(q k^T / sqrt(32)) v        rs::attn_varlen   (short-sequence kernel, dropout inside)
     x   = x + dropout(out_proj(o))                  GEMM + rs::dropout_add   (residual stream stays fp32)
+    (the Linear biases are added inside the consuming kernel; their gradients are rs::colsum of its backward)
     f   = dropout(gelu(linear1(LN2(x))))            rs::ln, GEMM, rs::gelu_dropout
     x   = x + dropout(linear2(f))                   GEMM + rs::dropout_add
 
@@ -41,42 +42,67 @@ def _seed() -> int:
 
 
 # ------------------------------------------------------------------------------------------------ custom ops
+def _colsum(x: Tensor) -> Tensor:
+    x = x.contiguous()
+    n_cols = x.shape[-1]
+    n_rows = x.numel() // n_cols
+    out = torch.empty(n_cols, dtype=torch.float32, device=x.device)
+    ws = L.workspace(_lib.rs_colsum_workspace_bytes(n_rows, n_cols), x.device)
+    L.check(_lib.rs_colsum(L.ptr(x), L.dt(x), n_rows, n_cols, L.ptr(out), L.ptr(ws), ws.numel(), L.stream()), "rs_colsum")
+    return out
+
+
+@torch.library.custom_op("rs::colsum", mutates_args=())
+def colsum_op(x: Tensor) -> Tensor:
+    """fp32 column sums of a [rows, cols] matrix in a fixed order (bias gradients)."""
+    L.require_cuda(x)
+    return _colsum(x)
+
+
+@colsum_op.register_fake
+def _(x):
+    return x.new_empty(x.shape[-1], dtype=torch.float32)
+
+
 @torch.library.custom_op("rs::attn_varlen", mutates_args=())
-def attn_varlen_op(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, zero_tail: int, scale: float,
-                   dropout_p: float, seed: int) -> List[Tensor]:
+def attn_varlen_op(qkv: Tensor, bias: Optional[Tensor], cu_seqlens: Tensor, n_heads: int, max_len: int, zero_tail: int,
+                   scale: float, dropout_p: float, seed: int) -> List[Tensor]:
     L.require_cuda(qkv, cu_seqlens)
     qkv = qkv.contiguous()
     T = qkv.shape[0]
     hd = qkv.shape[1] // (3 * n_heads)
     out = torch.empty(T, n_heads * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(T, n_heads, dtype=torch.float32, device=qkv.device)
-    L.check(_lib.rs_attn_varlen_fwd(L.ptr(qkv), L.dt(qkv), L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T, n_heads, hd,
-                                    max_len, zero_tail, scale, dropout_p, seed, L.ptr(out), L.ptr(lse), L.stream()),
-            "rs_attn_varlen_fwd")
+    L.check(_lib.rs_attn_varlen_fwd(L.ptr(qkv), L.dt(qkv), L.ptr(bias), L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T,
+                                    n_heads, hd, max_len, zero_tail, scale, dropout_p, seed, L.ptr(out), L.ptr(lse),
+                                    L.stream()), "rs_attn_varlen_fwd")
     return [out, lse]
 
 
 @attn_varlen_op.register_fake
-def _(qkv, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
+def _(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
     return [qkv.new_empty(qkv.shape[0], qkv.shape[1] // 3), qkv.new_empty(qkv.shape[0], n_heads, dtype=torch.float32)]
 
 
 @torch.library.custom_op("rs::attn_varlen_bwd", mutates_args=())
-def attn_varlen_bwd_op(qkv: Tensor, d_out: Tensor, out: Tensor, lse: Tensor, cu_seqlens: Tensor, n_heads: int,
-                       max_len: int, zero_tail: int, scale: float, dropout_p: float, seed: int) -> Tensor:
+def attn_varlen_bwd_op(qkv: Tensor, bias: Optional[Tensor], d_out: Tensor, out: Tensor, lse: Tensor, cu_seqlens: Tensor,
+                       n_heads: int, max_len: int, zero_tail: int, scale: float, dropout_p: float,
+                       seed: int) -> List[Tensor]:
+    """[d_qkv, d_bias] (d_bias empty when there is no bias)."""
     d_out = d_out.to(qkv.dtype).contiguous()
     T = qkv.shape[0]
     hd = qkv.shape[1] // (3 * n_heads)
     d_qkv = torch.empty_like(qkv)
-    L.check(_lib.rs_attn_varlen_bwd(L.ptr(qkv), L.ptr(d_out), L.ptr(out), L.dt(qkv), L.ptr(lse), L.ptr(cu_seqlens),
-                                    cu_seqlens.numel() - 1, T, n_heads, hd, max_len, zero_tail, scale, dropout_p, seed,
-                                    L.ptr(d_qkv), L.stream()), "rs_attn_varlen_bwd")
-    return d_qkv
+    L.check(_lib.rs_attn_varlen_bwd(L.ptr(qkv), L.ptr(d_out), L.ptr(out), L.dt(qkv), L.ptr(bias), L.ptr(lse),
+                                    L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T, n_heads, hd, max_len, zero_tail,
+                                    scale, dropout_p, seed, L.ptr(d_qkv), L.stream()), "rs_attn_varlen_bwd")
+    d_bias = _colsum(d_qkv) if bias is not None else qkv.new_empty(0, dtype=torch.float32)
+    return [d_qkv, d_bias]
 
 
 @attn_varlen_bwd_op.register_fake
-def _(qkv, d_out, out, lse, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
-    return torch.empty_like(qkv)
+def _(qkv, bias, d_out, out, lse, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
+    return [torch.empty_like(qkv), qkv.new_empty(qkv.shape[1] if bias is not None else 0, dtype=torch.float32)]
 
 
 @torch.library.custom_op("rs::ln", mutates_args=())
@@ -121,85 +147,89 @@ def _(dy, x, index, w, mean, rstd, dropout_p, seed):
 
 
 @torch.library.custom_op("rs::dropout_add", mutates_args=())
-def dropout_add_op(x: Tensor, y: Tensor, dropout_p: float, seed: int) -> Tensor:
+def dropout_add_op(x: Tensor, y: Tensor, bias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:
     L.require_cuda(x, y)
     x, y = x.contiguous(), y.contiguous()
     out = torch.empty_like(x)
-    L.check(_lib.rs_dropout_add_fwd(L.ptr(x), L.dt(x), L.ptr(y), L.dt(y), x.numel(), dropout_p, seed, L.ptr(out),
-                                    L.stream()), "rs_dropout_add_fwd")
+    L.check(_lib.rs_dropout_add_fwd(L.ptr(x), L.dt(x), L.ptr(y), L.dt(y), L.ptr(bias), x.shape[-1], x.numel(),
+                                    dropout_p, seed, L.ptr(out), L.stream()), "rs_dropout_add_fwd")
     return out
 
 
 @dropout_add_op.register_fake
-def _(x, y, dropout_p, seed):
+def _(x, y, bias, dropout_p, seed):
     return torch.empty_like(x)
 
 
 @torch.library.custom_op("rs::dropout_bwd", mutates_args=())
-def dropout_bwd_op(g: Tensor, dropout_p: float, seed: int, out_dtype: int) -> Tensor:
+def dropout_bwd_op(g: Tensor, dropout_p: float, seed: int, out_dtype: int, want_colsum: bool) -> List[Tensor]:
+    """[dy, colsum(dy)] -- the gradient of the dropped branch and (optionally) of the bias folded into it."""
     g = g.contiguous()
     dy = torch.empty(g.shape, dtype=L.torch_dtype(out_dtype), device=g.device)
     L.check(_lib.rs_dropout_bwd(L.ptr(g), L.dt(g), g.numel(), dropout_p, seed, L.ptr(dy), out_dtype, L.stream()),
             "rs_dropout_bwd")
-    return dy
+    return [dy, _colsum(dy) if want_colsum else g.new_empty(0, dtype=torch.float32)]
 
 
 @dropout_bwd_op.register_fake
-def _(g, dropout_p, seed, out_dtype):
-    return g.new_empty(g.shape, dtype=L.torch_dtype(out_dtype))
+def _(g, dropout_p, seed, out_dtype, want_colsum):
+    return [g.new_empty(g.shape, dtype=L.torch_dtype(out_dtype)),
+            g.new_empty(g.shape[-1] if want_colsum else 0, dtype=torch.float32)]
 
 
 @torch.library.custom_op("rs::gelu_dropout", mutates_args=())
-def gelu_dropout_op(z: Tensor, dropout_p: float, seed: int) -> Tensor:
+def gelu_dropout_op(z: Tensor, bias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:
     L.require_cuda(z)
     z = z.contiguous()
     out = torch.empty_like(z)
-    L.check(_lib.rs_gelu_dropout_fwd(L.ptr(z), L.dt(z), z.numel(), dropout_p, seed, L.ptr(out), L.stream()),
-            "rs_gelu_dropout_fwd")
+    L.check(_lib.rs_gelu_dropout_fwd(L.ptr(z), L.dt(z), L.ptr(bias), z.shape[-1], z.numel(), dropout_p, seed,
+                                     L.ptr(out), L.stream()), "rs_gelu_dropout_fwd")
     return out
 
 
 @gelu_dropout_op.register_fake
-def _(z, dropout_p, seed):
+def _(z, bias, dropout_p, seed):
     return torch.empty_like(z)
 
 
 @torch.library.custom_op("rs::gelu_dropout_bwd", mutates_args=())
-def gelu_dropout_bwd_op(z: Tensor, g: Tensor, dropout_p: float, seed: int) -> Tensor:
+def gelu_dropout_bwd_op(z: Tensor, bias: Optional[Tensor], g: Tensor, dropout_p: float, seed: int) -> List[Tensor]:
     g = g.to(z.dtype).contiguous()
     dz = torch.empty_like(z)
-    L.check(_lib.rs_gelu_dropout_bwd(L.ptr(z), L.ptr(g), L.dt(z), z.numel(), dropout_p, seed, L.ptr(dz), L.stream()),
-            "rs_gelu_dropout_bwd")
-    return dz
+    L.check(_lib.rs_gelu_dropout_bwd(L.ptr(z), L.ptr(g), L.dt(z), L.ptr(bias), z.shape[-1], z.numel(), dropout_p, seed,
+                                     L.ptr(dz), L.stream()), "rs_gelu_dropout_bwd")
+    return [dz, _colsum(dz) if bias is not None else z.new_empty(0, dtype=torch.float32)]
 
 
 @gelu_dropout_bwd_op.register_fake
-def _(z, g, dropout_p, seed):
-    return torch.empty_like(z)
+def _(z, bias, g, dropout_p, seed):
+    return [torch.empty_like(z), z.new_empty(z.shape[-1] if bias is not None else 0, dtype=torch.float32)]
 
 
 # ------------------------------------------------------------------------------------------------ autograd
 class _AttnVarlen(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
-        out, lse = torch.ops.rs.attn_varlen(qkv, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed)
-        ctx.save_for_backward(qkv, out, lse, cu_seqlens)
+    def forward(ctx, qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
+        out, lse = torch.ops.rs.attn_varlen(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed)
+        ctx.save_for_backward(qkv, bias, out, lse, cu_seqlens)
         ctx.meta = (n_heads, max_len, zero_tail, scale, dropout_p, seed)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        qkv, out, lse, cu = ctx.saved_tensors
-        return (torch.ops.rs.attn_varlen_bwd(qkv, g, out, lse, cu, *ctx.meta),) + (None,) * 7
+        qkv, bias, out, lse, cu = ctx.saved_tensors
+        d_qkv, d_bias = torch.ops.rs.attn_varlen_bwd(qkv, bias, g, out, lse, cu, *ctx.meta)
+        return (d_qkv, d_bias if bias is not None else None) + (None,) * 7
 
 
 def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dropout_p: float = 0.0,
-                scale: Optional[float] = None, zero_tail: int = 0) -> Tensor:
-    """Causal self-attention over packed sequences: qkv [T, 3*H*32] (in_proj output) -> [T, H*32].  The last
-    `zero_tail` sequences are queries at padded positions (every key masked): output 0, no gradient."""
+                scale: Optional[float] = None, zero_tail: int = 0, bias: Optional[Tensor] = None) -> Tensor:
+    """Causal self-attention over packed sequences: qkv [T, 3*H*32] (in_proj output; its `bias` [3*H*32] may be
+    passed separately and is added on load) -> [T, H*32].  The last `zero_tail` sequences are queries at padded
+    positions (every key masked): output 0, no gradient."""
     hd = qkv.shape[1] // (3 * n_heads)
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
-    return _AttnVarlen.apply(qkv, cu_seqlens, n_heads, max_len, int(zero_tail), float(scale), float(dropout_p),
+    return _AttnVarlen.apply(qkv, bias, cu_seqlens, n_heads, max_len, int(zero_tail), float(scale), float(dropout_p),
                              _seed() if dropout_p > 0 else 0)
 
 
@@ -227,36 +257,39 @@ def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, index
 
 class _DropoutAdd(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, dropout_p, seed):
-        ctx.meta = (dropout_p, seed, L.dt(y))
-        return torch.ops.rs.dropout_add(x, y, dropout_p, seed)
+    def forward(ctx, x, y, bias, dropout_p, seed):
+        ctx.meta = (dropout_p, seed, L.dt(y), bias is not None)
+        return torch.ops.rs.dropout_add(x, y, bias, dropout_p, seed)
 
     @staticmethod
     def backward(ctx, g):
-        p, seed, ydt = ctx.meta
-        return g, torch.ops.rs.dropout_bwd(g, p, seed, ydt), None, None
+        p, seed, ydt, has_bias = ctx.meta
+        dy, db = torch.ops.rs.dropout_bwd(g, p, seed, ydt, has_bias)
+        return g, dy, (db if has_bias else None), None, None
 
 
-def dropout_add(x: Tensor, y: Tensor, dropout_p: float = 0.0) -> Tensor:
-    """x + dropout(y) in x's dtype (the fp32 residual stream)."""
-    return _DropoutAdd.apply(x, y, float(dropout_p), _seed() if dropout_p > 0 else 0)
+def dropout_add(x: Tensor, y: Tensor, dropout_p: float = 0.0, bias: Optional[Tensor] = None) -> Tensor:
+    """x + dropout(y + bias) in x's dtype (the fp32 residual stream)."""
+    return _DropoutAdd.apply(x, y, bias, float(dropout_p), _seed() if dropout_p > 0 else 0)
 
 
 class _GeluDropout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, dropout_p, seed):
-        ctx.save_for_backward(z)
+    def forward(ctx, z, bias, dropout_p, seed):
+        ctx.save_for_backward(z, bias)
         ctx.meta = (dropout_p, seed)
-        return torch.ops.rs.gelu_dropout(z, dropout_p, seed)
+        return torch.ops.rs.gelu_dropout(z, bias, dropout_p, seed)
 
     @staticmethod
     def backward(ctx, g):
-        (z,) = ctx.saved_tensors
-        return torch.ops.rs.gelu_dropout_bwd(z, g, *ctx.meta), None, None
+        z, bias = ctx.saved_tensors
+        dz, db = torch.ops.rs.gelu_dropout_bwd(z, bias, g, *ctx.meta)
+        return dz, (db if bias is not None else None), None, None
 
 
-def gelu_dropout(z: Tensor, dropout_p: float = 0.0) -> Tensor:
-    return _GeluDropout.apply(z, float(dropout_p), _seed() if dropout_p > 0 else 0)
+def gelu_dropout(z: Tensor, dropout_p: float = 0.0, bias: Optional[Tensor] = None) -> Tensor:
+    """dropout(gelu(z + bias))"""
+    return _GeluDropout.apply(z, bias, float(dropout_p), _seed() if dropout_p > 0 else 0)
 
 
 # ------------------------------------------------------------------------------------------------ composition
@@ -274,12 +307,15 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     attn = layer.self_attn
     ad = _act_dtype(x)
     h = layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, out_dtype=ad)
-    qkv = F.linear(h, attn.in_proj_weight, attn.in_proj_bias)
-    o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail)
-    x = dropout_add(x, F.linear(o, attn.out_proj.weight, attn.out_proj.bias), layer.dropout1.p if tr else 0.0)
+    # the four biases are folded into the kernels that consume the GEMM outputs: plain matmuls, and the bias
+    # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
+    qkv = F.linear(h, attn.in_proj_weight)
+    o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail,
+                    bias=attn.in_proj_bias)
+    x = dropout_add(x, F.linear(o, attn.out_proj.weight), layer.dropout1.p if tr else 0.0, bias=attn.out_proj.bias)
     h = layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, out_dtype=ad)
-    f = gelu_dropout(F.linear(h, layer.linear1.weight, layer.linear1.bias), layer.dropout.p if tr else 0.0)
-    return dropout_add(x, F.linear(f, layer.linear2.weight, layer.linear2.bias), layer.dropout2.p if tr else 0.0)
+    f = gelu_dropout(F.linear(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
+    return dropout_add(x, F.linear(f, layer.linear2.weight), layer.dropout2.p if tr else 0.0, bias=layer.linear2.bias)
 
 
 def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,

@@ -140,7 +140,8 @@ def count_ids(ids: Tensor, n: int) -> Tensor:
 
 def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tensor, col_counts: Tensor,
                          target_ids: Tensor, pos_col: Tensor, own_cols: Optional[Tensor], log_q_tensor: Tensor,
-                         temperature: float = 0.1, lambda_logq: float = 1.0) -> Tensor:
+                         temperature: float = 0.1, lambda_logq: float = 1.0, row_cu: Optional[Tensor] = None,
+                         max_rows_per_user: int = 0) -> Tensor:
     """C2 (tower_code/v1_refine_usertower.py:826-861) over the DISTINCT items of the batch.  In-batch columns with
     the same target item share the item row and the logQ, hence the logit, so the reference's [N, N] softmax
     equals an [N, U] softmax over distinct items with the batch multiplicities m_c folded into the column bias:
@@ -151,7 +152,9 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
 
     U is ~5x smaller than N on an H&M-shaped batch (Zipf targets), and it is bounded by the catalogue size
     however many ranks contribute columns.  `col_counts` may hold zeros (absent items: bias = +inf).
-    `own_cols[N, K]` = columns of the row's user's targets, -1 = none (None: no same-user mask)."""
+    The same-user term: either `row_cu` (int32 [n_users+1], rows grouped by user, at most `max_rows_per_user` <= 64
+    each -> one small dense block per user, ops.user_block_logits) or `own_cols[N, K]` = columns of the row's
+    user's targets, -1 = none (generic sparse path); both None: no same-user mask."""
     dtype = _operand_dtype(user_emb, col_rows)
     scale = 1.0 / temperature
     lq = (log_q_tensor[col_item_ids] * lambda_logq).float() if lambda_logq > 0.0 else None
@@ -160,12 +163,19 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
         bias = bias + lq
     lse0 = fused_softmax_stats(user_emb, col_rows, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
                                mask_value=NEG_INF, flags=L.RS_CE_NO_DIAG, dtype=dtype)[0]
-    s_pos = ops.sparse_logits(user_emb, col_rows, pos_col.view(-1, 1), scale, lq, compute_dtype=dtype).squeeze(1)
-    mx = torch.maximum(lse0, s_pos).detach()
-    z = torch.exp(lse0 - mx) + torch.exp(s_pos - mx)
-    if own_cols is not None and own_cols.shape[1] > 0:
-        s_own = ops.sparse_logits(user_emb, col_rows, own_cols, scale, lq, target_ids, col_item_ids, compute_dtype=dtype)
-        z = z - torch.exp(s_own - mx.unsqueeze(1)).sum(dim=1)
+    if row_cu is not None:
+        s_pos, own_lse = ops.user_block_logits(user_emb, col_rows, pos_col, row_cu, max_rows_per_user, scale, lq,
+                                               compute_dtype=dtype)
+        mx = torch.maximum(lse0, s_pos).detach()
+        z = torch.exp(lse0 - mx) + torch.exp(s_pos - mx) - torch.exp(own_lse - mx)
+    else:
+        s_pos = ops.sparse_logits(user_emb, col_rows, pos_col.view(-1, 1), scale, lq, compute_dtype=dtype).squeeze(1)
+        mx = torch.maximum(lse0, s_pos).detach()
+        z = torch.exp(lse0 - mx) + torch.exp(s_pos - mx)
+        if own_cols is not None and own_cols.shape[1] > 0:
+            s_own = ops.sparse_logits(user_emb, col_rows, own_cols, scale, lq, target_ids, col_item_ids,
+                                      compute_dtype=dtype)
+            z = z - torch.exp(s_own - mx.unsqueeze(1)).sum(dim=1)
     lse = mx + torch.log(z.clamp_min(1e-30))
     return (lse - s_pos).mean()
 

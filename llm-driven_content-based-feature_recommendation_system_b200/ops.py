@@ -743,6 +743,71 @@ def sparse_logits(a, b, idx, scale, bias=None, key_row=None, key_col=None, compu
     return _SparseLogits.apply(a, b, idx, float(scale), bias, key_row, key_col, compute_dtype)
 
 
+@torch.library.custom_op("rs::user_block_logits", mutates_args=())
+def user_block_logits_op(u: Tensor, cols: Tensor, pos_col: Tensor, row_cu: Tensor, max_len: int, scale: float,
+                         bias: Optional[Tensor]) -> List[Tensor]:
+    """[s_pos[n], own_lse[n]] of the per-user blocks (see rs_user_block_logits_fwd)."""
+    L.require_cuda(u, cols, pos_col, row_cu)
+    u, cols, pos_col = _c(u), _c(cols), _ids(pos_col)
+    n = u.shape[0]
+    s_pos = torch.empty(n, dtype=torch.float32, device=u.device)
+    own = torch.empty(n, dtype=torch.float32, device=u.device)
+    L.check(_lib.rs_user_block_logits_fwd(L.ptr(u), L.ptr(cols), L.dt(u), L.ptr(pos_col), L.ptr(row_cu),
+                                          row_cu.numel() - 1, cols.shape[0], u.shape[1], max_len, scale, L.ptr(bias),
+                                          L.ptr(s_pos), L.ptr(own), L.stream()), "rs_user_block_logits_fwd")
+    return [s_pos, own]
+
+
+@user_block_logits_op.register_fake
+def _(u, cols, pos_col, row_cu, max_len, scale, bias):
+    return [u.new_empty(u.shape[0], dtype=torch.float32), u.new_empty(u.shape[0], dtype=torch.float32)]
+
+
+@torch.library.custom_op("rs::user_block_logits_bwd", mutates_args=())
+def user_block_logits_bwd_op(u: Tensor, cols: Tensor, pos_col: Tensor, row_cu: Tensor, max_len: int, scale: float,
+                             bias: Optional[Tensor], own_lse: Tensor, g_pos: Tensor, g_own: Tensor) -> List[Tensor]:
+    u, cols, pos_col = _c(u), _c(cols), _ids(pos_col)
+    d_u = torch.zeros(u.shape, dtype=torch.float32, device=u.device)
+    d_c = torch.zeros(cols.shape, dtype=torch.float32, device=u.device)
+    L.check(_lib.rs_user_block_logits_bwd(L.ptr(u), L.ptr(cols), L.dt(u), L.ptr(pos_col), L.ptr(row_cu),
+                                          row_cu.numel() - 1, cols.shape[0], u.shape[1], max_len, scale, L.ptr(bias),
+                                          L.ptr(own_lse), L.ptr(_f32(g_pos, "g_pos")), L.ptr(_f32(g_own, "g_own")),
+                                          L.ptr(d_u), L.ptr(d_c), L.stream()), "rs_user_block_logits_bwd")
+    return [d_u, d_c]
+
+
+@user_block_logits_bwd_op.register_fake
+def _(u, cols, pos_col, row_cu, max_len, scale, bias, own_lse, g_pos, g_own):
+    return [u.new_empty(u.shape, dtype=torch.float32), cols.new_empty(cols.shape, dtype=torch.float32)]
+
+
+class _UserBlockLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, cols, pos_col, row_cu, max_len, scale, bias, compute_dtype):
+        uc = u.detach() if compute_dtype is None else u.detach().to(compute_dtype)
+        cc = cols.detach() if compute_dtype is None else cols.detach().to(compute_dtype)
+        s_pos, own = torch.ops.rs.user_block_logits(uc, cc, pos_col, row_cu, max_len, scale, bias)
+        ctx.save_for_backward(uc, cc, pos_col, row_cu, bias, own)
+        ctx.meta = (max_len, scale, u.dtype, cols.dtype)
+        return s_pos, own
+
+    @staticmethod
+    def backward(ctx, g_pos, g_own):
+        uc, cc, pos_col, row_cu, bias, own = ctx.saved_tensors
+        max_len, scale, udt, cdt = ctx.meta
+        d_u, d_c = torch.ops.rs.user_block_logits_bwd(uc, cc, pos_col, row_cu, max_len, scale, bias, own,
+                                                      g_pos.float().contiguous(), g_own.float().contiguous())
+        return d_u.to(udt), d_c.to(cdt), None, None, None, None, None, None
+
+
+def user_block_logits(u, cols, pos_col, row_cu, max_len, scale, bias=None, compute_dtype=None):
+    """(s_pos[n], own_lse[n]): the label logit of every row and the log-sum-exp of its logits against the OTHER
+    target items of the same user (rows grouped by user, `row_cu` offsets); differentiable in u and cols."""
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    return _UserBlockLogits.apply(u, cols, pos_col, row_cu, int(max_len), float(scale), bias, compute_dtype)
+
+
 def mine_hard_negatives(u, v, key, k, hnm_threshold):
     """(scores, ids, avail): per-row top-k of <u_i, v_j> over non-ignored columns (C4/C5 mining, no gradient)."""
     with torch.no_grad():

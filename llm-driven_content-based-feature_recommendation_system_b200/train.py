@@ -136,9 +136,14 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
                 v = F.normalize(item_tower.get_all_embeddings(), p=2, dim=1)         # :810, all rows
                 cid, cnt, pos_col = losses.item_columns(tgt, v.shape[0])
                 grid = batch["target_ids"].masked_fill(batch["padding_mask"], -1)
-            own = grid[uid] if loss_scope == "all" else None     # one row per user otherwise: nothing to mask
+            # same-user mask: the rows are grouped by user (batch-major valid steps) -> one dense block per user
+            blk = {}
+            if loss_scope == "all" and "cu_seqlens" in batch and L <= 64:
+                blk, own = dict(row_cu=batch["cu_seqlens"][:B + 1], max_rows_per_user=L), None
+            else:
+                own = grid[uid] if loss_scope == "all" else None     # one row per user otherwise: nothing to mask
             main = losses.logq_infonce_columns(u, v, cid, cnt, tgt, pos_col, own, item_tower.get_log_q(), 0.1,
-                                               lambda_logq)
+                                               lambda_logq, **blk)
         cl = losses.duorec_loss_refined(out1[n_main:], out2, tgt_flat[li], lambda_sup=lambda_sup)   # :830-842
         total = main + lambda_cl * cl
     if optimizer is not None:
@@ -252,9 +257,12 @@ class ShardedTwoTower:
             dist.all_reduce(n_glob, group=self.group)
             v_cols = sh.all_gather_rows(F.normalize(item_tower.item_matrix.weight, p=2, dim=1), self.group)
             cnt = self.cols.counts(tgt, self.group)
-            grid = self.cols.col_of(batch["target_ids"].masked_fill(batch["padding_mask"], -1))
+            if "cu_seqlens" in batch and L <= 64:
+                blk, own = dict(row_cu=batch["cu_seqlens"][:B + 1], max_rows_per_user=L), None
+            else:
+                blk, own = {}, self.cols.col_of(batch["target_ids"].masked_fill(batch["padding_mask"], -1))[uid]
             main_local = losses.logq_infonce_columns(u, v_cols, self.cols.col_item_ids, cnt, tgt, self.cols.col_of(tgt),
-                                                     grid[uid], self.log_q_by_id, 0.1, lambda_logq)
+                                                     own, self.log_q_by_id, 0.1, lambda_logq, **blk)
             main = main_local * (n_main / n_glob.squeeze(0))
             # DuoRec across the box
             cl = self._duorec(out1[n_main:], out2, tgt_flat[li], lambda_sup) / self.world

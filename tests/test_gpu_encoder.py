@@ -51,6 +51,57 @@ def test_attn_varlen_vs_dense(rs, lens, dtype):
     torch.testing.assert_close(b.grad.float(), a.grad, **(tol if dtype == torch.float32 else dict(rtol=3e-2, atol=6e-2)))
 
 
+def test_folded_biases_and_colsum(rs):
+    """biases folded into attention / dropout_add / gelu_dropout: values and bias gradients vs torch."""
+    H, hd, lens = 4, 32, [7, 20, 3, 41]
+    g = torch.Generator().manual_seed(5)
+    T = sum(lens)
+    qkv = torch.randn(T, 3 * H * hd, generator=g).to(DEV)
+    bias = torch.randn(3 * H * hd, generator=g).to(DEV)
+    w = torch.randn(T, H * hd, generator=g).to(DEV)
+    a, ba = qkv.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    (_ref_attention(a + ba, lens, H) * w).sum().backward()
+    b, bb = qkv.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    got = rs.encoder.attn_varlen(b, _cu(lens).to(DEV), H, max(lens), bias=bb)
+    (got * w).sum().backward()
+    torch.testing.assert_close(got.detach(), _ref_attention(qkv + bias, lens, H), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(b.grad, a.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(bb.grad, ba.grad, rtol=1e-4, atol=1e-3)
+    for n_rows, n_cols in ((1, 128), (1000, 256), (70001, 384)):
+        x = torch.randn(n_rows, n_cols, generator=g).to(DEV)
+        torch.testing.assert_close(torch.ops.rs.colsum(x), x.sum(0), rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(torch.ops.rs.colsum(x.bfloat16()), x.bfloat16().float().sum(0), rtol=1e-4, atol=1e-3)
+    x = torch.randn(500, 128, generator=g).to(DEV).requires_grad_(True)
+    y = torch.randn(500, 128, generator=g).to(DEV).requires_grad_(True)
+    b1 = torch.randn(128, generator=g).to(DEV).requires_grad_(True)
+    out = rs.encoder.dropout_add(x, y, 0.0, bias=b1)
+    torch.testing.assert_close(out.detach(), (x + y + b1).detach())
+    (out * w[:500]).sum().backward()
+    torch.testing.assert_close(b1.grad, w[:500].sum(0), rtol=1e-4, atol=1e-3)
+    z = torch.randn(500, 256, generator=g).to(DEV).requires_grad_(True)
+    b2 = torch.randn(256, generator=g).to(DEV).requires_grad_(True)
+    f = rs.encoder.gelu_dropout(z, 0.0, bias=b2)
+    torch.testing.assert_close(f.detach(), F.gelu((z + b2).detach()), rtol=1e-5, atol=1e-6)
+    f.sum().backward()
+    z2, b3 = z.detach().clone().requires_grad_(True), b2.detach().clone().requires_grad_(True)
+    F.gelu(z2 + b3).sum().backward()
+    torch.testing.assert_close(z.grad, z2.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(b2.grad, b3.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_attn_zero_tail_sequences(rs):
+    """pseudo-sequences at padded positions: output 0, gradient 0, the others untouched."""
+    H, hd, lens = 4, 32, [5, 9, 1, 1]
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(sum(lens), 3 * H * hd, generator=g).to(DEV).requires_grad_(True)
+    out = rs.encoder.attn_varlen(qkv, _cu(lens).to(DEV), H, 16, zero_tail=2)
+    ref = _ref_attention(qkv.detach(), lens[:2], H)
+    torch.testing.assert_close(out[:14].detach(), ref, rtol=1e-4, atol=1e-4)
+    assert (out[14:] == 0).all()
+    out.sum().backward()
+    assert (qkv.grad[14:] == 0).all() and qkv.grad[:14].abs().sum() > 0
+
+
 def test_attn_dropout_forward_backward_share_the_mask(rs):
     """with an explicit seed the op is a deterministic function: its analytic gradient must match central differences
     of the SAME seeded forward (fp32), i.e. forward, dQ pass and dK/dV pass all draw the same keep mask."""
@@ -60,19 +111,19 @@ def test_attn_dropout_forward_backward_share_the_mask(rs):
     qkv = (0.5 * torch.randn(T, 3 * H * hd, generator=g)).to(DEV)
     w = torch.randn(T, H * hd, generator=g).to(DEV)
     cu, seed, p, scale = _cu(lens).to(DEV), 1234567, 0.3, 1 / math.sqrt(hd)
-    out, lse = torch.ops.rs.attn_varlen(qkv, cu, H, 64, scale, p, seed)
-    out0, _ = torch.ops.rs.attn_varlen(qkv, cu, H, 64, scale, 0.0, 0)
+    out, lse = torch.ops.rs.attn_varlen(qkv, None, cu, H, 64, 0, scale, p, seed)
+    out0, _ = torch.ops.rs.attn_varlen(qkv, None, cu, H, 64, 0, scale, 0.0, 0)
     assert not torch.allclose(out, out0)                                   # dropout did something
-    out_again, _ = torch.ops.rs.attn_varlen(qkv, cu, H, 64, scale, p, seed)
+    out_again, _ = torch.ops.rs.attn_varlen(qkv, None, cu, H, 64, 0, scale, p, seed)
     assert torch.equal(out, out_again)
-    dq = torch.ops.rs.attn_varlen_bwd(qkv, w, out, lse, cu, H, 64, scale, p, seed)
+    dq, _ = torch.ops.rs.attn_varlen_bwd(qkv, None, w, out, lse, cu, H, 64, 0, scale, p, seed)
     idx = torch.randint(0, qkv.numel(), (40,), generator=g)
     eps = 1e-2
     for flat in idx.tolist():
         d = torch.zeros_like(qkv).view(-1)
         d[flat] = eps
-        fp, _ = torch.ops.rs.attn_varlen(qkv + d.view_as(qkv), cu, H, 64, scale, p, seed)
-        fm, _ = torch.ops.rs.attn_varlen(qkv - d.view_as(qkv), cu, H, 64, scale, p, seed)
+        fp, _ = torch.ops.rs.attn_varlen(qkv + d.view_as(qkv), None, cu, H, 64, 0, scale, p, seed)
+        fm, _ = torch.ops.rs.attn_varlen(qkv - d.view_as(qkv), None, cu, H, 64, 0, scale, p, seed)
         num = ((fp - fm) * w).sum().item() / (2 * eps)
         assert abs(num - dq.view(-1)[flat].item()) < 2e-2 * max(1.0, abs(num)), (flat, num, dq.view(-1)[flat].item())
 

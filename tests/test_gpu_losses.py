@@ -364,3 +364,40 @@ def test_train_step_column_modes_agree(rs):
         assert abs(res[mode][1] - res["batch"][1]) < 1e-5
         for g, w in zip(res[mode][2:], res["batch"][2:]):
             assert (g - w).abs().max() <= 2e-2 * w.abs().max() + 1e-8, (mode, (g - w).abs().max(), w.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_user_block_logits_vs_torch(rs, dtype):
+    """per-user dense blocks: label logit, log-sum-exp over the user's OTHER items, and both gradients."""
+    g = torch.Generator().manual_seed(11)
+    lens = [1, 5, 50, 2, 17, 33, 1, 8]
+    n, n_cols = sum(lens), 40
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    U = F.normalize(torch.randn(n, 128, generator=g), dim=1).to(dtype).float()
+    C = F.normalize(torch.randn(n_cols, 128, generator=g), dim=1).to(dtype).float()
+    pos = torch.randint(0, n_cols, (n,), generator=g)
+    bias = torch.randn(n_cols, generator=g)
+    wp, wo = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    u0, c0 = U.clone().requires_grad_(True), C.clone().requires_grad_(True)
+    s = u0 @ c0.T / 0.1 - bias.view(1, -1)
+    s_pos0 = s[torch.arange(n), pos]
+    own0 = []
+    for b in range(len(lens)):
+        r = torch.arange(cu[b], cu[b + 1])
+        blk = s[r][:, pos[r]]                                          # [len, len]
+        blk = blk.masked_fill(pos[r].view(-1, 1) == pos[r].view(1, -1), float("-inf"))
+        own0.append(torch.logsumexp(blk, dim=1))
+    own0 = torch.cat(own0)
+    fin = torch.isfinite(own0)
+    (s_pos0 * wp).sum().backward(retain_graph=True)
+    (torch.where(fin, own0, torch.zeros_like(own0)) * wo).sum().backward()
+    u1, c1 = U.to(DEV).requires_grad_(True), C.to(DEV).requires_grad_(True)
+    s_pos, own = rs.ops.user_block_logits(u1, c1, pos.to(DEV), cu.to(DEV), 50, 10.0, bias.to(DEV), compute_dtype=dtype)
+    tol = dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(s_pos.detach().cpu(), s_pos0.detach(), **tol)
+    assert torch.equal(torch.isfinite(own.detach().cpu()), fin)
+    torch.testing.assert_close(own.detach().cpu()[fin], own0.detach()[fin], **tol)
+    ((s_pos * wp.to(DEV)).sum() + (torch.where(fin.to(DEV), own, torch.zeros_like(own)) * wo.to(DEV)).sum()).backward()
+    torch.testing.assert_close(u1.grad.cpu(), u0.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(c1.grad.cpu(), c0.grad, rtol=1e-3, atol=1e-3)
