@@ -204,8 +204,9 @@ int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int 
                        int max_len, int64_t zero_tail, float scale, float dropout_p, uint64_t seed, void* d_qkv,
                        void* stream);
 /* y[r,:] = dropout(LayerNorm(x[index ? index[r] : r, :])), dim == 128, fp32 statistics (mean/rstd[n_rows] saved).
- * `index` packs the valid rows of the padded grid on the way in (emb_ln, :458-459).  Backward: dx[index[r]] (rows
- * that are not indexed are left untouched: pass a zeroed buffer), dw/db[128] reduced in a fixed order. */
+ * `index` packs the valid rows of the padded grid on the way in (emb_ln, :458-459) and may repeat a row (one copy per
+ * dropout view).  Backward: dx[r] = gradient w.r.t. the row that was normalised for output r ([n_rows,128], packed
+ * like dy: the caller scatter-adds it by `index`), dw/db[128] reduced in a fixed order. */
 int rs_ln_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, int64_t dim, const float* w,
               const float* b, float eps, float dropout_p, uint64_t seed, void* y, int y_dtype, float* mean,
               float* rstd, void* stream);

@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
   }
 }
 
-// dx[index ? index[r] : r] = LN backward of dy[r] (dropout mask re-derived); per-CTA partial dw / db
+// dx[r] = LN backward of dy[r] w.r.t. the row it normalised, x[index ? index[r] : r] (PACKED like dy: an index may
+// name the same source row several times -- two dropout views -- so the caller scatter-adds); per-CTA partial dw / db
 template <int DTI, int DTO>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                      const int64_t* __restrict__ index, int64_t n_rows,
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
     const float4 gw = make_float4(g.x * w4.x, g.y * w4.y, g.z * w4.z, g.w * w4.w);
     const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
     const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
-    st4<DTI>(dx, src * ENC_D + 4 * lane,
+    st4<DTI>(dx, r * ENC_D + 4 * lane,
              make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
                          rs * (gw.w - m1 - xh.w * m2)));
   }

@@ -131,7 +131,7 @@ def ln_bwd_op(dy: Tensor, x: Tensor, index: Optional[Tensor], w: Tensor, mean: T
               seed: int) -> List[Tensor]:
     dy = dy.contiguous()
     n = dy.shape[0]
-    dx = torch.empty_like(x) if index is None else torch.zeros_like(x)
+    dx = torch.empty(n, x.shape[1], dtype=x.dtype, device=x.device)       # packed like dy
     dw = torch.empty_like(w)
     db = torch.empty_like(w)
     ws = L.workspace(_lib.rs_ln_bwd_workspace_bytes(n), x.device)
@@ -143,7 +143,7 @@ def ln_bwd_op(dy: Tensor, x: Tensor, index: Optional[Tensor], w: Tensor, mean: T
 
 @ln_bwd_op.register_fake
 def _(dy, x, index, w, mean, rstd, dropout_p, seed):
-    return [torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)]
+    return [x.new_empty(dy.shape[0], x.shape[1]), torch.empty_like(w), torch.empty_like(w)]
 
 
 @torch.library.custom_op("rs::dropout_add", mutates_args=())
@@ -245,6 +245,8 @@ class _LayerNorm(torch.autograd.Function):
     def backward(ctx, g):
         x, index, w, mean, rstd = ctx.saved_tensors
         dx, dw, db = torch.ops.rs.ln_bwd(g, x, index, w, mean, rstd, *ctx.meta)
+        if index is not None:          # an index may repeat rows (one copy per dropout view): scatter-ADD
+            dx = torch.zeros_like(x).index_add_(0, index, dx)
         return dx, None, dw, db, None, None, None, None
 
 

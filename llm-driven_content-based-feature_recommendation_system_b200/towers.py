@@ -105,7 +105,8 @@ class SASRecUserTower(nn.Module):
     def forward(self, pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids,
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
                 fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None,
-                item_id_rows=None, packed_index=None, cu_seqlens=None, packed_zero_tail=0):
+                item_id_rows=None, packed_index=None, cu_seqlens=None, packed_zero_tail=0, views=1,
+                select_users=None):
         """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
         When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
         returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
@@ -115,10 +116,13 @@ class SASRecUserTower(nn.Module):
                                    section_ids, item_id_rows)
         static_input = self.static_front(age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids,
                                          club_status_ids, news_freq_ids, fn_ids, active_ids, cont_feats)
-        user_profile_vec = self.static_mlp(static_input)
         if packed_index is not None:
+            # `views` dropout views in ONE pass: the deterministic fronts are computed once, the index / offsets carry
+            # every token `views` times (train.add_host_index), and each copy draws its own dropout masks
+            user_profile_vec = self.static_mlp(static_input if views == 1 else static_input.repeat(views, 1))
             return self._forward_packed(seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index,
-                                        cu_seqlens, packed_zero_tail)
+                                        cu_seqlens, packed_zero_tail, select_users)
+        user_profile_vec = self.static_mlp(static_input)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
         # is_causal=True only tells nn.TransformerEncoder not to PROBE the mask: with is_causal=None it compares the
         # mask with a generated causal one and reads the verdict back (`bool((mask == causal).all())`,
@@ -140,23 +144,28 @@ class SASRecUserTower(nn.Module):
         return F.normalize(final_vec, p=2, dim=-1)
 
     def _forward_packed(self, seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index, cu_seqlens,
-                        zero_tail=0):
+                        zero_tail=0, select_users=None):
         """The encoder on the packed valid tokens (encoder.py): `packed_index` [T] = flat b*L+l positions of the
         valid time steps in batch-major order, `cu_seqlens` int32 their per-sequence offsets (every sequence
         non-empty).  `select_index` then indexes PACKED rows; returns [len(select_index), 128] (all T rows when
         None) in training mode, the last valid step of every sequence [B, 128] otherwise -- the values the reference
         computes at those positions of its padded grid.  The last `zero_tail` entries of `cu_seqlens` may be
-        one-token pseudo-sequences at PADDED positions (attention output 0 there, train.add_host_index)."""
+        one-token pseudo-sequences at PADDED positions (attention output 0 there, train.add_host_index).
+        `select_users` [len(select_index)]: the row of `user_profile_vec` that goes with every selected row (needed
+        when several dropout views share the pass; default: the token's own batch row)."""
         tr = self.training
         x = enc.layer_norm(seq_emb.reshape(-1, seq_emb.shape[-1]), self.emb_ln.weight, self.emb_ln.bias, self.emb_ln.eps,
                            index=packed_index, dropout_p=self.emb_dropout.p if tr else 0.0, out_dtype=torch.float32)
         output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
-        users = packed_index // seq_len
         if not training_mode:
             select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1
+        users = select_users
+        if users is None:
+            users = packed_index // seq_len
+            if select_index is not None:
+                users = users[select_index]
         if select_index is not None:
             output = ops.gather_rows(output, select_index)
-            users = users[select_index]
         prof = ops.gather_rows(user_profile_vec, users)
         final_vec = self.output_proj(torch.cat([output, prof.to(output.dtype)], dim=-1))
         return F.normalize(final_vec, p=2, dim=-1)

@@ -65,6 +65,23 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
         batch["cu_seqlens"] = cu
         batch["last_packed"] = lp
         batch["select_packed"] = torch.cat([torch.arange(T), lp])
+        # both dropout views in one pass: tokens [view-1 valid | view-2 valid | view-1 extras | view-2 extras]
+        E = extra.numel()
+        ext_pos = batch["last_index"][extra]
+        batch["packed_index_2v"] = torch.cat([batch["valid_index"], batch["valid_index"], ext_pos, ext_pos])
+        cu2 = torch.zeros(2 * B + 1 + 2 * E, dtype=torch.int32)
+        cs = torch.cumsum(lens, 0).to(torch.int32)
+        cu2[1:B + 1] = cs
+        cu2[B + 1:2 * B + 1] = T + cs
+        cu2[2 * B + 1:] = 2 * T + 1 + torch.arange(2 * E, dtype=torch.int32)
+        batch["cu_seqlens_2v"] = cu2
+        lp1 = torch.where(lp < T, lp, lp + T)                     # extras of view 1 start at 2T
+        lp2 = torch.where(lp < T, lp + T, lp + T + E)             # view-2 valid tokens at T.., its extras at 2T+E..
+        ar = torch.arange(B)
+        batch["select_2v_all"] = torch.cat([torch.arange(T), lp1, lp2])       # main rows + DuoRec rows of both views
+        batch["select_2v_last"] = torch.cat([lp1, lp1, lp2])                   # loss_scope == "last"
+        batch["users_2v_all"] = torch.cat([batch["valid_index"] // L, ar, B + ar])
+        batch["users_2v_last"] = torch.cat([ar, ar, B + ar])
     if columns:
         tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
         ids, counts, pos_col = losses.item_columns(tgt)
@@ -78,13 +95,14 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
     """The two dropout views (v1_usertower_train.py:788-792).  View 1 feeds the main loss (valid steps, or the last
     step) and DuoRec (last step); view 2 only DuoRec: the late-fusion head runs on exactly those rows (same values
     as slicing the full [B, L, 128] output).  Returns ([n_main + B, 128], [B, 128])."""
-    if packed and "cu_seqlens" in batch:
-        lp = batch["last_packed"]
-        sel1 = batch["select_packed"] if loss_scope == "all" else torch.cat([lp, lp])
-        pk = dict(packed_index=batch["packed_index"], cu_seqlens=batch["cu_seqlens"],
-                  packed_zero_tail=batch["cu_seqlens"].numel() - 1 - batch["item_ids"].shape[0])
-        return (model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=sel1, **pk, **extra),
-                model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=lp, **pk, **extra))
+    if packed and "cu_seqlens_2v" in batch:
+        B = batch["item_ids"].shape[0]
+        k = "all" if loss_scope == "all" else "last"
+        cu2 = batch["cu_seqlens_2v"]
+        out = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=batch["select_2v_" + k],
+                    select_users=batch["users_2v_" + k], packed_index=batch["packed_index_2v"], cu_seqlens=cu2,
+                    packed_zero_tail=cu2.numel() - 1 - 2 * B, views=2, **extra)
+        return out[:-B], out[-B:]
     li = batch["last_index"]
     sel1 = batch.get("select_index") if loss_scope == "all" else torch.cat([li, li])
     if sel1 is None:
