@@ -202,16 +202,15 @@ def run_ours(args):
     if sharded:
         # loader-stage routing of every batch's item ids (split sizes + the id exchange), once per batch; the host
         # copy keeps the position order pinned (it is an input like the ids), the requested rows live on their owner
-        resident = [trainer.plan(b) for b in resident]
-        for hb, rb in zip(host, resident):
-            hb["route_order"] = rb["lookup_plan"].order.cpu().pin_memory()
+        resident = [trainer.plan(b, "catalog" if args.columns == "catalog" else "unique") for b in resident]
+        plan_keys = [k for k in ("lookup_plan", "col_plan", "col_item_ids", "col_counts", "pos_col") if k in resident[0]]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     n_valid = int(host[0]["valid_index"].numel())
     n_cols = {"unique": int(host[0]["col_item_ids"].numel()), "catalog": syn.N_ITEMS + 1}.get(args.columns, n_valid)
     if args.loss_scope != "all":
         n_cols = B if args.columns != "catalog" else n_cols
     if sharded:
-        n_cols = trainer.cols.n_cols
+        n_cols = int(resident[0]["col_item_ids"].numel()) if "col_plan" in resident[0] else trainer.cols.n_cols
 
     def step(b):
         if sharded:
@@ -255,9 +254,8 @@ def run_ours(args):
     # ---- end-to-end run: host batches in, losses out, every step
     def e2e_step(i):
         b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
-        if sharded:
-            pl = resident[i % pool]["lookup_plan"]
-            b["lookup_plan"] = rs.sharded.LookupPlan(b.pop("route_order"), pl.send, pl.recv, pl.req, pl.n)
+        if sharded:          # the loader-stage products (made with collectives, they live on the device) ride along
+            b.update({k: resident[i % pool][k] for k in plan_keys})
         t, m, c = step(b)
         last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
 
@@ -334,10 +332,11 @@ def run_ours(args):
                     config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B,
                                 global_batch=B * world, seq_len=SL, d_model=128, n_items=syn.N_ITEMS,
                                 loss_scope=args.loss_scope, loss_rows=n_valid if args.loss_scope == "all" else B,
-                                loss_columns="catalog" if sharded else args.columns, loss_cols=n_cols,
+                                loss_columns=("catalog" if args.columns == "catalog" else "unique (box-wide)") if sharded else args.columns,
+                                loss_cols=n_cols,
                                 parallelism=("1 GPU" if world == 1 else
                                              f"{world} ranks: item_id_emb + item_matrix row-sharded (owner = row % {world}, "
-                                             f"all-to-all lookups), negatives = whole catalogue with box-wide counts, "
+                                             f"all-to-all lookups), negatives = distinct targets of all ranks with box-wide counts, "
                                              f"DuoRec columns all-gathered, other parameters replicated + all-reduced"
                                              if sharded else f"dp{world} (replicated tables, gradients all-reduced, "
                                                              f"rank-local negatives)"),

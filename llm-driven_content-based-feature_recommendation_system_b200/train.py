@@ -191,10 +191,11 @@ class ShardedTwoTower:
         [ceil(rows/world), 128] of each (parameters + AdamW state); lookups go through the planned all-to-all
         (sharded.planned_lookup: owner-side gather kernel -> rows all-to-all; backward: gradient rows all-to-all ->
         owner-side deterministic segment reduce);
-      * the negatives of the main loss spanning the box: every rank scores its rows against the all-gathered
-        (normalised) item matrix, each item weighted by its number of occurrences among the targets of ALL
-        ranks -- the reference's in-batch softmax over the global batch, grouped by item
-        (losses.logq_infonce_columns); the gathered matrix's gradient is reduce-scattered to the owners;
+      * the negatives of the main loss spanning the box: every rank scores its rows against the DISTINCT target
+        items of all ranks (their rows fetched from the owners by all-to-all; or, columns="catalog", against the
+        all-gathered item matrix), each item weighted by its number of occurrences among the targets of ALL ranks
+        -- the reference's in-batch softmax over the global batch, grouped by item (losses.logq_infonce_columns);
+        the gradient of the fetched rows travels back to the owners (all-to-all / reduce-scatter);
       * DuoRec with all-gathered second views / targets (rectangular [B, world*B] blocks, diag_offset = rank*B);
       * every other parameter replicated, gradients summed with one flat all-reduce.
     Each rank's loss is its share of the GLOBAL mean (local sum / global row count), so that summing the
@@ -224,10 +225,33 @@ class ShardedTwoTower:
                                   if id(p) not in sp and p.requires_grad]
         self.pad_local_row = 0 if self.rank == 0 else -1                         # global row 0 = rank 0, local row 0
 
-    def plan(self, batch):
-        """Loader-stage work for one (device) batch: routing of its item ids (collective, synchronises)."""
+    def plan(self, batch, columns="unique"):
+        """Loader-stage work for one (device) batch -- everything that depends only on its ids, done with
+        collectives and host reads BEFORE the step so that the step itself never synchronises:
+          * routing of the item ids against the row-sharded `item_id_emb` (sharded.plan_lookup);
+          * columns="unique": the distinct target items of ALL ranks (sorted), their box-wide counts, the routing of
+            that list against the row-sharded `item_matrix`, and the column of every local target;
+            columns="catalog": nothing (every item is a column, static; counts are all-reduced inside the step)."""
+        dist, sh = self.dist, self.sh
         batch = dict(batch)
-        batch["lookup_plan"] = self.sh.plan_lookup(batch["item_ids"], self.group)
+        batch["lookup_plan"] = sh.plan_lookup(batch["item_ids"], self.group)
+        if columns == "unique":
+            tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
+            mine = torch.unique(tgt)
+            n = torch.tensor([mine.numel()], device=tgt.device)
+            sizes = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(sizes, n, group=self.group)
+            cap = int(max(int(x) for x in sizes))
+            padded = torch.full((cap,), -1, dtype=mine.dtype, device=tgt.device)
+            padded[:mine.numel()] = mine
+            allv = torch.empty(self.world * cap, dtype=mine.dtype, device=tgt.device)
+            dist.all_gather_into_tensor(allv, padded, group=self.group)
+            gq = torch.unique(allv[allv >= 0])                               # sorted, identical on every rank
+            pos_col = torch.searchsorted(gq, tgt)
+            cnt = losses.count_ids(pos_col, gq.numel())
+            dist.all_reduce(cnt, group=self.group)
+            batch.update(col_item_ids=gq, col_counts=cnt, pos_col=pos_col,
+                         col_plan=sh.plan_lookup(gq, self.group))
         return batch
 
     def _sync_replicated(self):
@@ -273,14 +297,24 @@ class ShardedTwoTower:
             # main loss: all items as columns, global multiplicities
             n_glob = torch.tensor([float(n_main)], device=u.device)
             dist.all_reduce(n_glob, group=self.group)
-            v_cols = sh.all_gather_rows(F.normalize(item_tower.item_matrix.weight, p=2, dim=1), self.group)
-            cnt = self.cols.counts(tgt, self.group)
+            if "col_plan" in batch:
+                # columns = the distinct targets of the whole box: fetch their rows from the owners (all-to-all), normalise
+                rows = sh.planned_lookup(item_tower.item_matrix.weight, batch["col_plan"], self.group)
+                v_cols = F.normalize(rows, p=2, dim=1)
+                cid, cnt, pos_col = batch["col_item_ids"], batch["col_counts"], batch["pos_col"]
+            else:
+                # columns = every item: all-gather the normalised shards (reduce-scatter backward), static shapes
+                v_cols = sh.all_gather_rows(F.normalize(item_tower.item_matrix.weight, p=2, dim=1), self.group)
+                cid, cnt, pos_col = self.cols.col_item_ids, self.cols.counts(tgt, self.group), self.cols.col_of(tgt)
             if "cu_seqlens" in batch and L <= 64:
                 blk, own = dict(row_cu=batch["cu_seqlens"][:B + 1], max_rows_per_user=L), None
+            elif "col_plan" in batch:
+                g_ = torch.full((B * L,), -1, dtype=torch.int64, device=u.device).index_copy_(0, idx, pos_col)
+                blk, own = {}, g_.view(B, L)[uid]
             else:
                 blk, own = {}, self.cols.col_of(batch["target_ids"].masked_fill(batch["padding_mask"], -1))[uid]
-            main_local = losses.logq_infonce_columns(u, v_cols, self.cols.col_item_ids, cnt, tgt, self.cols.col_of(tgt),
-                                                     own, self.log_q_by_id, 0.1, lambda_logq, **blk)
+            main_local = losses.logq_infonce_columns(u, v_cols, cid, cnt, tgt, pos_col, own, self.log_q_by_id, 0.1,
+                                                     lambda_logq, **blk)
             main = main_local * (n_main / n_glob.squeeze(0))
             # DuoRec across the box
             cl = self._duorec(out1[n_main:], out2, tgt_flat[li], lambda_sup) / self.world

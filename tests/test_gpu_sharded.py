@@ -55,7 +55,7 @@ def _worker(rank, world, port, q):
         model, item, lookup = build()
         tr = rs.train.ShardedTwoTower(model, item)
         opt = torch.optim.SGD(list(model.parameters()) + list(item.parameters()), lr=0.0)
-        lb = tr.plan(rs.train.prepare_batch(rs.train.add_host_index(parts[rank]), dev))
+        lb = tr.plan(rs.train.prepare_batch(rs.train.add_host_index(parts[rank]), dev), "unique")
         t1, m1, c1 = tr.step(lb, lookup, opt)
         ok = True
         msgs = []
@@ -74,6 +74,12 @@ def _worker(rank, world, port, q):
         close("output_proj", model.output_proj[0].weight.grad, ref["op"], 3e-2)
         close("time_emb", model.time_emb.weight.grad, ref["te"], 3e-2)
         close("seq_gate", model.seq_gate.grad, ref["sg"], 3e-2)
+        # same step with every item as a column (static shapes, all-gathered item matrix)
+        opt.zero_grad(set_to_none=True)
+        lb2 = tr.plan(rs.train.prepare_batch(rs.train.add_host_index(parts[rank]), dev), "catalog")
+        t2, m2, c2 = tr.step(lb2, lookup, opt)
+        close("main(catalog)", m2, m0, 2e-3)
+        close("item_matrix(catalog)", item.item_matrix.weight.grad, sh.shard_padded(ref["im"], rank, world), 3e-2)
         q.put((rank, ok, msgs))
     finally:
         dist.destroy_process_group()
