@@ -355,14 +355,6 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restr
     *reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * n_cols + 4 * c4) = s;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int n_blocks, int n_cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cols) return;
-  float s = 0.f;
-  for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * n_cols + c];
-  out[c] = s;
-}
-
 // ------------------------------------------------------------------------------------------------ LayerNorm(128)
 // y[r] = dropout(LN(x[index ? index[r] : r])) ; one warp per row, lane owns 4 consecutive features
 template <int DTI, int DTO>
@@ -447,14 +439,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
   }
 }
 
-// out[k][c] = sum_b part[b][k][c]   (fixed order: deterministic)
-__global__ void colsum_finalize_kernel(const float* __restrict__ part, int n_blocks, int n_cols, float* __restrict__ out0,
-                                       float* __restrict__ out1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * n_cols) return;
-  float s = 0.f;
-  for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * 2 * n_cols + c];
-  if (c < n_cols) out0[c] = s; else if (out1) out1[c - n_cols] = s;
+// out[c] = sum_b part[b][c] over n_blocks partial rows of n_cols_total columns, fixed order (deterministic).
+// One CTA per 32 columns; warp w adds partial rows w, w+8, ... (coalesced 128 B reads), then the 8 warps are folded.
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, int n_blocks, int n_cols_total,
+                                                          float* __restrict__ out0, float* __restrict__ out1, int split) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < n_cols_total) {
+    int b = w;
+    for (; b + 8 < n_blocks; b += 16) {
+      s0 += part[(int64_t)b * n_cols_total + c];
+      s1 += part[(int64_t)(b + 8) * n_cols_total + c];
+    }
+    if (b < n_blocks) s0 += part[(int64_t)b * n_cols_total + c];
+  }
+  red[w][lane] = s0 + s1;
+  __syncthreads();
+  if (w == 0 && c < n_cols_total) {
+    float s = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][lane];
+    if (c < split) out0[c] = s; else if (out1) out1[c - split] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise
@@ -640,7 +648,7 @@ extern "C" int rs_colsum(const void* x, int dtype, int64_t n_rows, int64_t n_col
   float* part = (float*)workspace;
   ENC_DISPATCH1(dtype, DT, (colsum_partial_kernel<DT><<<grid, 256, smem, st>>>(x, n_rows, (int)n_cols, part)));
   RS_LAUNCH_CHECK();
-  colsum_final_kernel<<<(int)((n_cols + 127) / 128), 128, 0, st>>>(part, grid, (int)n_cols, out);
+  partial_sum_kernel<<<(int)((n_cols + 31) / 32), 256, 0, st>>>(part, grid, (int)n_cols, out, nullptr, (int)n_cols);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -683,7 +691,7 @@ extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtyp
   ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dy_dtype, DTO, (ln_bwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
       dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, part))));
   RS_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<1, 2 * ENC_D, 0, st>>>(part, grid, ENC_D, dw, db);
+  partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
