@@ -26,6 +26,19 @@ STATIC_TABLES = ("age_emb", "price_emb", "cnt_emb", "recency_emb", "channel_emb"
                  "news_freq_emb", "fn_emb", "active_emb")
 
 
+class _ZeroGradTables(torch.autograd.Function):
+    """identity on x; the listed tables get explicit all-zero gradients (they take part with a gate of exactly 0)."""
+
+    @staticmethod
+    def forward(ctx, x, *tables):
+        ctx.save_for_backward(*tables)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g,) + tuple(torch.zeros_like(t) for t in ctx.saved_tensors)
+
+
 class SASRecUserTower(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -92,6 +105,25 @@ class SASRecUserTower(nn.Module):
         n_live = sum(1 for m in SEQ_GATE_MASK if m != 0.0)        # live tables come first in SEQ_TABLES
         return ops.seq_front(base, ids, tables, s_g, self.pos_emb.weight, padding_idx=0, n_live=n_live)
 
+    def embed_front_packed(self, pretrained_vecs, item_ids, time_bucket_ids, pos_ids, item_id_rows=None):
+        """U1 on PACKED tokens: the same kernel and the same order of additions, with the position embedding passed
+        as a third gathered table (gate 1.0, ids = l + 1 behind a zero row so that the padding convention of the
+        other tables -- id 0 never receives gradient -- leaves position 0 alone).  `item_ids` / `time_bucket_ids` /
+        `pos_ids` are [R, 64] grids holding the batch's valid tokens (train.add_host_index), zero-padded at the end."""
+        s_g = torch.sigmoid(self.seq_gate) * self._seq_gate_mask
+        base = self.item_proj(pretrained_vecs)
+        w = self.pos_emb.weight
+        pos_ext = torch.cat([w.new_zeros(1, w.shape[1]), w])
+        gates = torch.cat([s_g[:2], s_g.new_ones(1)])
+        ids = [item_ids, time_bucket_ids, pos_ids]
+        tables = [self.item_id_emb.weight, self.time_emb.weight, pos_ext]
+        if item_id_rows is not None:
+            ids[0] = torch.arange(1, item_ids.numel() + 1, device=item_ids.device).view_as(item_ids)
+            tables[0] = item_id_rows
+        out = ops.seq_front(base, ids, tables, gates, None, padding_idx=0, n_live=3)
+        # the hard-masked tables contribute exactly 0 and receive exactly-0 gradients in the reference (invariant 2)
+        return _ZeroGradTables.apply(out, *[getattr(self, n).weight for n in SEQ_TABLES[2:]])
+
     def static_front(self, age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids,
                      news_freq_ids, fn_ids, active_ids, cont_feats):
         """U2 (:472-491): one kernel instead of ~25."""
@@ -106,14 +138,18 @@ class SASRecUserTower(nn.Module):
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
                 fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None,
                 item_id_rows=None, packed_index=None, cu_seqlens=None, packed_zero_tail=0, views=1,
-                select_users=None):
+                select_users=None, packed_inputs=None):
         """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
         When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
         returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
         so the other ~75 % of the [B,L] grid need not go through output_proj."""
         seq_len = item_ids.size(1)
-        seq_emb = self.embed_front(pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids,
-                                   section_ids, item_id_rows)
+        if packed_inputs is not None:      # U1 on the packed tokens too (pretrained_vecs is gathered for that grid)
+            seq_emb = self.embed_front_packed(pretrained_vecs, packed_inputs["item_ids"],
+                                              packed_inputs["time_bucket_ids"], packed_inputs["pos_ids"], item_id_rows)
+        else:
+            seq_emb = self.embed_front(pretrained_vecs, item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids,
+                                       section_ids, item_id_rows)
         static_input = self.static_front(age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids,
                                          club_status_ids, news_freq_ids, fn_ids, active_ids, cont_feats)
         if packed_index is not None:

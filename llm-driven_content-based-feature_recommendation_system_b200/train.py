@@ -82,6 +82,21 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
         batch["select_2v_last"] = torch.cat([lp1, lp1, lp2])                   # loss_scope == "last"
         batch["users_2v_all"] = torch.cat([batch["valid_index"] // L, ar, B + ar])
         batch["users_2v_last"] = torch.cat([ar, ar, B + ar])
+        # U1 on packed tokens as well: [R, 64] grids holding the T valid tokens, then the E extras, zero-padded
+        PK = 64
+        R = (T + E + PK - 1) // PK
+        flat = torch.cat([batch["valid_index"], ext_pos])
+
+        def grid_of(x):
+            g_ = torch.zeros(R * PK, dtype=torch.int64)
+            g_[:T + E] = x
+            return g_.view(R, PK)
+        batch["pk_item_ids"] = grid_of(batch["item_ids"].reshape(-1)[flat])
+        batch["pk_time_ids"] = grid_of(batch["time_bucket_ids"].reshape(-1)[flat])
+        batch["pk_pos_ids"] = grid_of(flat % L + 1)
+        tok = torch.arange(T)
+        ext = T + torch.arange(E)
+        batch["pk_index_2v"] = torch.cat([tok, tok, ext, ext])
     if columns:
         tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
         ids, counts, pos_col = losses.item_columns(tgt)
@@ -89,6 +104,11 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
         grid[batch["valid_index"]] = pos_col
         batch.update(col_item_ids=ids, col_counts=counts, pos_col=pos_col, own_grid=grid.view(B, L))
     return batch
+
+
+def _front_item_ids(batch, packed):
+    """the item-id grid U1 runs on: the packed [R, 64] grid when the batch carries it, else the padded [B, L] one."""
+    return batch["pk_item_ids"] if (packed and "pk_item_ids" in batch and "cu_seqlens_2v" in batch) else batch["item_ids"]
 
 
 def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
@@ -99,9 +119,16 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
         B = batch["item_ids"].shape[0]
         k = "all" if loss_scope == "all" else "last"
         cu2 = batch["cu_seqlens_2v"]
+        pk = {}
+        if "pk_item_ids" in batch:
+            pk = dict(packed_index=batch["pk_index_2v"],
+                      packed_inputs=dict(item_ids=batch["pk_item_ids"], time_bucket_ids=batch["pk_time_ids"],
+                                         pos_ids=batch["pk_pos_ids"]))
+        else:
+            pk = dict(packed_index=batch["packed_index_2v"])
         out = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=batch["select_2v_" + k],
-                    select_users=batch["users_2v_" + k], packed_index=batch["packed_index_2v"], cu_seqlens=cu2,
-                    packed_zero_tail=cu2.numel() - 1 - 2 * B, views=2, **extra)
+                    select_users=batch["users_2v_" + k], cu_seqlens=cu2,
+                    packed_zero_tail=cu2.numel() - 1 - 2 * B, views=2, **pk, **extra)
         return out[:-B], out[-B:]
     li = batch["last_index"]
     sel1 = batch.get("select_index") if loss_scope == "all" else torch.cat([li, li])
@@ -126,7 +153,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
     with torch.no_grad():
-        pretrained_vecs = ops.gather_rows(pretrained_lookup, item_ids)
+        pretrained_vecs = ops.gather_rows(pretrained_lookup, _front_item_ids(batch, packed))
     kw = {k: batch[k] for k in FORWARD_KEYS}
     # The encoder is stock nn.TransformerEncoder (as in the reference).  For its shape (L=50, 4 heads x 32, explicit
     # causal + padding mask) PyTorch's default pick on sm_100, the cuDNN flash kernel with 128-wide tiles, is 28 %
@@ -234,7 +261,7 @@ class ShardedTwoTower:
             columns="catalog": nothing (every item is a column, static; counts are all-reduced inside the step)."""
         dist, sh = self.dist, self.sh
         batch = dict(batch)
-        batch["lookup_plan"] = sh.plan_lookup(batch["item_ids"], self.group)
+        batch["lookup_plan"] = sh.plan_lookup(_front_item_ids(batch, True), self.group)
         if columns == "unique":
             tgt = batch["target_ids"].reshape(-1)[batch["valid_index"]]
             mine = torch.unique(tgt)
@@ -280,7 +307,7 @@ class ShardedTwoTower:
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
-            pretrained_vecs = ops.gather_rows(pretrained_lookup, item_ids)
+            pretrained_vecs = ops.gather_rows(pretrained_lookup, _front_item_ids(batch, packed))
         kw = {k: batch[k] for k in FORWARD_KEYS}
         # one exchange serves both dropout views (their gradients add up in the buffer before travelling back)
         id_rows = sh.planned_lookup(model.item_id_emb.weight, batch["lookup_plan"], self.group, lead_rows=1,
