@@ -266,6 +266,10 @@ typedef struct {
   int64_t diag_offset;      /* label of row i is column i + diag_offset */
   float mask_value;
   int flags;
+  float logit_bound;        /* > 0: the caller vouches that |<a_i, b_j>| <= logit_bound for all i, j (e.g. 1.0 for
+                               unit-norm rows).  With a bounded exponent range the forward then sums 2^(s - C)
+                               against a fixed offset C instead of tracking a running maximum, and the backward
+                               factors per-row / per-column constants out of the exponent.  0: unknown (general path) */
 } rs_ce_problem;
 size_t rs_ce_workspace_bytes(const rs_ce_problem* p);
 int rs_ce_fwd(const rs_ce_problem* p /*host*/, float* lse /*[M]*/, float* diag /*[M]*/,

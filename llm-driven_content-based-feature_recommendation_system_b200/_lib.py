@@ -28,7 +28,7 @@ class CEProblem(C.Structure):
     """Mirror of rs_ce_problem."""
     _fields_ = [("a", vp), ("b", vp), ("ab_dtype", i32), ("M", i64), ("N", i64), ("K", i64), ("scale", f32),
                 ("col_bias", vp), ("key_a_row", vp), ("key_a_col", vp), ("key_b_row", vp), ("key_b_col", vp),
-                ("diag_offset", i64), ("mask_value", f32), ("flags", i32)]
+                ("diag_offset", i64), ("mask_value", f32), ("flags", i32), ("logit_bound", f32)]
 
 
 # name -> (restype, argtypes); must list every function of include/rs_twotower.h

@@ -181,6 +181,12 @@ struct CeParams {
   float* part_out;              // backward: [nsplit][M][128]
   float out_scale;
   const float* wmax;            // backward: device scalar max|w| (coefficients are rescaled into the 16-bit range)
+  // device scalars written by ce_prep_kernel / ce_wmax_kernel (tail of the workspace):
+  //   tune[0] = C   fixed softmax offset in log2 units: an upper bound of every logit of this launch
+  //   tune[1] != 0  -> the bound is trustworthy and the exponent range is small: no running max in the forward,
+  //                    bias factored out of the exponent in the backward
+  //   tune[2] != 0  -> every w_lse >= 0 (needed to move the weight into the exponent)
+  const float* tune;
 };
 
 __device__ __forceinline__ void item_coords(const CeParams& p, int item, int& rb, int& sp, int& ct_lo, int& ct_hi) {
@@ -257,18 +263,25 @@ __device__ __forceinline__ float lse_or_zero(float lse) { return lse == -INFINIT
 // stage the metadata of column tile `ct` (one column per thread of the warpgroup) + the key_b range of
 // each staging warp's 32 columns (for the range-disjointness test that lets whole tiles skip that compare)
 template <bool BWD_T>
-__device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int ct, int t128, float cs) {
+__device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int ct, int t128, float cs, float c_off,
+                                           bool fold) {
   const int64_t c = (int64_t)ct * CE_BN + t128;
   const bool ok = c < p.N;
-  cm.bias[t128] = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
+  const float b2 = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
+  cm.bias[t128] = b2 + c_off;
   cm.ka[t128] = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
   const uint32_t kb = (ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
   cm.kb[t128] = kb;
   const uint32_t lo = __reduce_min_sync(0xffffffffu, kb), hi = __reduce_max_sync(0xffffffffu, kb);
   if ((t128 & 31) == 0) { cm.kb_lo[t128 >> 5] = lo; cm.kb_hi[t128 >> 5] = hi; }
+  if (!BWD_T && fold) cm.wl[t128] = ex2(-b2);          // pass A folded: the column's bias as a factor 2^-bias
   if (BWD_T) {
-    cm.lse[t128] = ok ? lse_or_zero(__ldg(p.lse + c)) * CE_LOG2E : 0.f;
-    cm.wl[t128] = ok ? __ldg(p.w_lse + c) * cs : 0.f;
+    const float l2 = ok ? lse_or_zero(__ldg(p.lse + c)) * CE_LOG2E : 0.f;
+    const float wl = ok ? __ldg(p.w_lse + c) * cs : 0.f;
+    // pass B folded: -lse2 + log2(w*cs) of the column, in the (otherwise unused) bias slot; w == 0 -> coefficient 0
+    if (fold) cm.bias[t128] = wl > 0.f ? __log2f(wl) - l2 : -INFINITY;
+    cm.lse[t128] = l2;
+    cm.wl[t128] = wl;
     cm.wd[t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) * cs : 0.f;
     cm.wp[t128] = (ok && p.w_pos) ? __ldg(p.w_pos + c) * cs : 0.f;
   }
@@ -304,6 +317,8 @@ struct RowCtx {
   float m, l, ps, pc;
   // backward, non-transposed: per-row constants
   float lse2, wlc, wdc, wpc;
+  float c_off, mask2c;         // forward fixed-offset mode: logits are produced as s - C (0 / mask2 otherwise)
+  float nl, eb;                // backward folded mode: -lse2 + log2(w*cs) of the row (pass A), 2^-rowbias2 (pass B)
 };
 
 // logits of one 32-column chunk in the log2 domain with the masks applied.
@@ -328,7 +343,7 @@ __device__ __forceinline__ void logits32(const uint32_t (&r)[32], float (&v)[32]
       const float a = __uint_as_float(r[j]);
       float s;
       bool masked = false, pos = false;
-      if (MODE == MODE_PLAIN) s = a * p.scale2;
+      if (MODE == MODE_PLAIN) s = fmaf(a, p.scale2, -rc.c_off);
       else if (ROWBIAS) s = fmaf(a, p.scale2, rc.nrowbias2);
       else s = fmaf(a, p.scale2, -f4at<e>(b4));
       if (MODE != MODE_PLAIN) {
@@ -342,12 +357,12 @@ __device__ __forceinline__ void logits32(const uint32_t (&r)[32], float (&v)[32]
           diagbit |= 1u << j;
           pos = false;
           masked = (p.flags & RS_CE_DIAG_MASK) != 0;
-          if (p.flags & RS_CE_DIAG_RAW) s = a * p.scale2;
+          if (p.flags & RS_CE_DIAG_RAW) s = fmaf(a, p.scale2, -rc.c_off);
         }
-        s = masked ? p.mask2 : s;
+        s = masked ? rc.mask2c : s;
         if (col >= p.N) { s = -INFINITY; pos = false; }
       } else if (MODE == MODE_GENERAL) {
-        s = masked ? p.mask2 : s;
+        s = masked ? rc.mask2c : s;
       }
       if (MODE == MODE_SUPCON && pos) posbits |= 1u << j;
       v[j] = s;
@@ -360,12 +375,19 @@ __device__ __forceinline__ void logits32(const uint32_t (&r)[32], float (&v)[32]
 }
 
 // forward: fold one chunk into the running (max, sum) [+ SupCon sums, + the diagonal logit]
-template <int MODE, bool EDGE, bool USE_KB>
+template <int MODE, bool EDGE, bool USE_KB, bool FIXED>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t meta, int cbase, RowCtx& rc,
                                           const CeParams& p, int64_t col0, bool row_ok, int64_t row) {
   float v[32];
   unsigned posbits, diagbit;
   logits32<MODE, EDGE, USE_KB, false>(r, v, posbits, diagbit, meta, cbase, rc, p, col0);
+  if (FIXED) {
+    // every logit is already s - C with C >= max possible logit: 2^(s-C) <= 1, no running max, no rescale
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) { a0 += ex2(v[j]); a1 += ex2(v[j + 1]); a2 += ex2(v[j + 2]); a3 += ex2(v[j + 3]); }
+    rc.l += (a0 + a1) + (a2 + a3);
+  } else {
   // four independent chains for the max and for the sum: with only two epilogue warps per scheduler the
   // instruction-level parallelism inside a warp is what hides the ALU / MUFU latencies
   float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
@@ -384,6 +406,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t meta
   }
   rc.l += (a0 + a1) + (a2 + a3);
   rc.m = m_new;
+  }
   if (MODE == MODE_SUPCON) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) rc.ps += (posbits & (1u << j)) ? v[j] : 0.f;
@@ -393,7 +416,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t meta
     float dv = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) if (diagbit & (1u << j)) dv = v[j];
-    p.diag_out[row] = dv * CE_LN2;
+    p.diag_out[row] = (dv + rc.c_off) * CE_LN2;
   }
 }
 
@@ -425,6 +448,57 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t meta
         c = rc.wlc * ex2(v[j] - rc.lse2);
         if (EDGE) c += (diagbit & (1u << j)) ? rc.wdc : 0.f;
         if (MODE == MODE_SUPCON) c += (posbits & (1u << j)) ? rc.wpc : 0.f;
+      }
+      v[j] = c;
+    };
+    one(std::integral_constant<int, 0>{});
+    one(std::integral_constant<int, 1>{});
+    one(std::integral_constant<int, 2>{});
+    one(std::integral_constant<int, 3>{});
+  }
+  const int box = cbase >> 6;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    if (bf16) {
+      u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+      u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+    } else {
+      u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
+      u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
+    }
+    const int chunk = (((cbase >> 5) & 1) * 4 + q) ^ (rloc & 7);
+    *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = u;
+  }
+}
+
+// backward fast path (no edge, weights >= 0, small exponent range): everything that is constant along the row or the
+// column leaves the per-element work.  Non-transposed: c = 2^(a*scale2 + nl_i) * eb_j with nl_i = -lse2_i + log2(w_i*cs)
+// and eb_j = 2^-bias2_j; transposed: c = 2^(a*scale2 + nl_j) * eb_i.  Per element: FFMA, EX2, FMUL, compare, select.
+template <int MODE, bool USE_KB, bool TRANSPOSED>
+__device__ __forceinline__ void bwd_chunk_fold(const uint32_t (&r)[32], uint32_t meta, int cbase, const RowCtx& rc,
+                                               const CeParams& p, uint8_t* prow, int rloc, bool bf16) {
+  float v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 f4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    uint4 a4 = make_uint4(0, 0, 0, 0), k4 = make_uint4(0, 0, 0, 0);
+    if (TRANSPOSED) f4 = lds_f4(meta + OFF_BIAS + (cbase + 4 * q) * 4);           // nl_j
+    else if (MODE != MODE_PLAIN) f4 = lds_f4(meta + OFF_WL + (cbase + 4 * q) * 4);  // eb_j
+    if (MODE != MODE_PLAIN) a4 = lds_u4(meta + OFF_KA + (cbase + 4 * q) * 4);
+    if (MODE == MODE_GENERAL && USE_KB) k4 = lds_u4(meta + OFF_KB + (cbase + 4 * q) * 4);
+    auto one = [&](auto ec) {
+      constexpr int e = decltype(ec)::value;
+      const int j = 4 * q + e;
+      const float a = __uint_as_float(r[j]);
+      float c;
+      if (TRANSPOSED) c = ex2(fmaf(a, p.scale2, f4at<e>(f4))) * rc.eb;
+      else if (MODE != MODE_PLAIN) c = ex2(fmaf(a, p.scale2, rc.nl)) * f4at<e>(f4);
+      else c = ex2(fmaf(a, p.scale2, rc.nl));
+      if (MODE == MODE_GENERAL) {
+        bool masked = u4at<e>(a4) == rc.my_ka;
+        if (USE_KB) masked |= (u4at<e>(k4) == rc.my_kb);
+        c = masked ? 0.f : c;
       }
       v[j] = c;
     };
@@ -522,6 +596,8 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int rloc = quarter * 32 + lane;
     const int t128 = (warp - 2 - 4 * wg) * 32 + lane;   // 0..127 within the warpgroup (staging index)
     uint32_t it = 0, nuse = 0;                          // nuse: tiles this warpgroup has consumed
+    const bool fixed = __ldg(p.tune + 1) != 0.f;        // warp-uniform (device scalar)
+    const float c_off = fixed ? __ldg(p.tune) : 0.f;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int rb, sp, lo, hi;
       item_coords(p, item, rb, sp, lo, hi);
@@ -532,12 +608,13 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi);
       rc.nrowbias2 = 0.f;
       rc.jd = row + p.diag_offset;
-      rc.m = -INFINITY; rc.l = 0.f; rc.ps = 0.f; rc.pc = 0.f;
+      rc.c_off = c_off; rc.mask2c = p.mask2 - c_off;
+      rc.m = fixed ? c_off : -INFINITY; rc.l = 0.f; rc.ps = 0.f; rc.pc = 0.f;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;   // diag col span
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
-        stage_cols<false>(p, cm, ct, t128, 1.0f);
+        stage_cols<false>(p, cm, ct, t128, 1.0f, c_off, false);
         named_bar_sync(1 + wg, 128);
         const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
@@ -546,9 +623,15 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         mbar_wait(&sh.tmem_full[wg], nuse & 1);
         tc_fence_after();
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
-        if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
-        else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
-        else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+        if (fixed) {
+          if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+        } else {
+          if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+        }
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[wg]);
         ++nuse;
@@ -571,7 +654,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int64_t o = (int64_t)sp * p.M + row;
         p.part_m[o] = mm;
         p.part_l[o] = ll;
-        if (MODE == MODE_SUPCON) { p.part_ps[o] = ps; p.part_pc[o] = pc; }
+        if (MODE == MODE_SUPCON) { p.part_ps[o] = ps + c_off * pc; p.part_pc[o] = pc; }
       }
       named_bar_sync(1 + CE_NWG, 128 * CE_NWG);
     }
@@ -669,6 +752,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (wm > 0.f && wm < INFINITY) { (void)frexpf(wm, &ex); ex = 13 - ex; ex = max(-100, min(100, ex)); }
     const float cs = ldexpf(1.0f, ex), inv_cs = ldexpf(1.0f, -ex);
     const bool bf16 = (p.idesc_s & (1u << 7)) != 0;
+    // folded fast path: bounded exponent range (tune[1]), non-negative weights (tune[2]), finite mask value would
+    // need the masked entries' softmax mass: only -inf masks (coefficient exactly 0) qualify
+    const bool fold = MODE != MODE_SUPCON && __ldg(p.tune + 1) != 0.f && __ldg(p.tune + 2) != 0.f &&
+                      (MODE == MODE_PLAIN || p.mask2 == -INFINITY);
     uint32_t it = 0, nuse = 0, item_n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       int rb, sp, lo, hi;
@@ -679,13 +766,17 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       uint32_t wkb_lo, wkb_hi;
       load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi);
       rc.nrowbias2 = 0.f; rc.lse2 = 0.f; rc.wlc = 0.f; rc.wdc = 0.f; rc.wpc = 0.f;
+      rc.c_off = 0.f; rc.mask2c = p.mask2; rc.nl = -INFINITY; rc.eb = 0.f;
       if (row_ok) {
-        if (TRANSPOSED) { if (p.row_bias) rc.nrowbias2 = -__ldg(p.row_bias + row) * CE_LOG2E; }
-        else {
+        if (TRANSPOSED) {
+          if (p.row_bias) rc.nrowbias2 = -__ldg(p.row_bias + row) * CE_LOG2E;
+          rc.eb = ex2(rc.nrowbias2);
+        } else {
           rc.lse2 = lse_or_zero(__ldg(p.lse + row)) * CE_LOG2E;
           rc.wlc = __ldg(p.w_lse + row) * cs;
           if (p.w_diag) rc.wdc = __ldg(p.w_diag + row) * cs;
           if (p.w_pos) rc.wpc = __ldg(p.w_pos + row) * cs;
+          rc.nl = rc.wlc > 0.f ? __log2f(rc.wlc) - rc.lse2 : -INFINITY;
         }
       }
       rc.jd = row + p.diag_offset;
@@ -693,7 +784,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
-        stage_cols<TRANSPOSED>(p, cm, ct, t128, cs);
+        stage_cols<TRANSPOSED>(p, cm, ct, t128, cs, 0.f, fold);
         named_bar_sync(1 + wg, 128);
         const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
@@ -705,6 +796,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tc_fence_after();
         uint8_t* prow = sP + pb * CE_TILE_BYTES + rloc * 128;
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
+        if (!edge && fold) {
+          if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, true, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16); });
+        } else
         if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, true, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
         else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
         else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, false, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
@@ -745,22 +840,58 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// out[0] = max |w| ; out[6] = 1 iff every w_lse >= 0 (tune[2])
 __global__ void ce_wmax_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                int64_t n, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ int neg;
+  if (threadIdx.x == 0) neg = 0;
+  __syncthreads();
   float m = 0.f;
+  bool any_neg = false;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    any_neg |= !(a[i] >= 0.f);
     m = fmaxf(m, fabsf(a[i]));
     if (b) m = fmaxf(m, fabsf(b[i]));
     if (c) m = fmaxf(m, fabsf(c[i]));
   }
+  if (any_neg) neg = 1;
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x < 32) {
     m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     m = warp_max(m);
-    if (threadIdx.x == 0) *out = m;
+    if (threadIdx.x == 0) { out[0] = m; out[6] = neg ? 0.f : 1.f; }
+  }
+}
+
+// tune[0] = C = scale2*bound - min(0, min finite bias2): an upper bound of every logit (log2 units) of the launch;
+// tune[1] = 1 iff the caller vouched for |A.B^T| <= bound and the whole exponent range is small (no under/overflow
+// when the running max is replaced by C and when 2^-bias is factored out of the exponent)
+__global__ void ce_prep_kernel(const float* __restrict__ bias, int64_t n, float scale2, float bound,
+                               float* __restrict__ tune) {
+  __shared__ float rmin[32], rmax[32];
+  float lo = INFINITY, hi = -INFINITY;
+  if (bias)
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const float b = bias[i] * CE_LOG2E;
+      if (fabsf(b) < INFINITY) { lo = fminf(lo, b); hi = fmaxf(hi, b); }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { rmin[threadIdx.x >> 5] = lo; rmax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { lo = fminf(lo, rmin[k]); hi = fmaxf(hi, rmax[k]); }
+    if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }                 // no (finite) bias at all
+    const float top = fabsf(scale2) * bound;
+    tune[0] = top - fminf(lo, 0.f);
+    const float range = 2.f * top + (hi - lo) + fabsf(fminf(lo, 0.f));
+    tune[1] = (bound > 0.f && range < 100.f && fabsf(lo) < 100.f && fabsf(hi) < 100.f) ? 1.f : 0.f;
   }
 }
 
@@ -891,7 +1022,7 @@ extern "C" int rs_ce_fwd(const rs_ce_problem* p, float* lse, float* diag, float*
   if (mode == MODE_SUPCON && (!pos_sum || !pos_cnt)) return RS_ERR_BAD_ARG;
   const CePlan pl = ce_plan(p->M, p->N, CE_FWD_ITEMS_PER_SM);
   const size_t pb = al256((size_t)pl.nsplit * p->M * sizeof(float));
-  if (workspace_bytes < 4 * pb) return RS_ERR_WORKSPACE;
+  if (workspace_bytes < rs_ce_workspace_bytes(p)) return RS_ERR_WORKSPACE;
   CUtensorMap mapA, mapB;
   if ((rc = make_map(&mapA, p->a, p->M, p->ab_dtype)) != RS_OK) return rc;
   if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
@@ -906,6 +1037,10 @@ extern "C" int rs_ce_fwd(const rs_ce_problem* p, float* lse, float* diag, float*
   k.part_m = (float*)ws; k.part_l = (float*)(ws + pb); k.part_ps = (float*)(ws + 2 * pb); k.part_pc = (float*)(ws + 3 * pb);
   k.diag_out = diag;
   cudaStream_t st = (cudaStream_t)stream;
+  float* tail = (float*)((char*)workspace + rs_ce_workspace_bytes(p) - 512);
+  k.tune = tail + 4;
+  ce_prep_kernel<<<1, 1024, 0, st>>>(p->col_bias, p->N, p->scale * CE_LOG2E, p->logit_bound, tail + 4);
+  RS_LAUNCH_CHECK();
   const size_t smem = ce_smem_bytes(false);
 #define LAUNCH_FWD(MODE)                                                                                 \
   do {                                                                                                   \
@@ -952,6 +1087,8 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
   float* wmax = (float*)((char*)workspace + rs_ce_workspace_bytes(p) - 512);
   ce_wmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w_lse, w_diag, w_pos, p->M, wmax);
   RS_LAUNCH_CHECK();
+  ce_prep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->col_bias, p->N, p->scale * CE_LOG2E, p->logit_bound, wmax + 4);
+  RS_LAUNCH_CHECK();
   CUtensorMap mapA, mapB;
   if ((rc = make_map(&mapA, p->a, p->M, p->ab_dtype)) != RS_OK) return rc;
   if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
@@ -969,6 +1106,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.part_out = (float*)workspace;
     k.out_scale = p->scale;
     k.wmax = wmax;
+    k.tune = wmax + 4;
     if ((rc = launch_bwd_pass<false>(p, mode, k, mapA, mapB, pl.grid, st)) != RS_OK) return rc;
     const int64_t n4 = p->M * CE_K / 4;
     ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dA);
@@ -987,6 +1125,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.part_out = (float*)workspace;
     k.out_scale = p->scale;
     k.wmax = wmax;
+    k.tune = wmax + 4;
     if ((rc = launch_bwd_pass<true>(p, mode, k, mapB, mapA, pl.grid, st)) != RS_OK) return rc;
     const int64_t n4 = p->N * CE_K / 4;
     ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dB);

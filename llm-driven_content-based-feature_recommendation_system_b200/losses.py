@@ -28,6 +28,7 @@ from . import _lib as L
 from . import ops
 
 COMPUTE_DTYPE = torch.bfloat16
+UNIT_NORM_BOUND = 1.0 + 2.0 ** -6        # |<a, b>| of 16-bit-rounded unit rows
 NEG_INF = float("-inf")
 
 
@@ -47,19 +48,19 @@ class _FusedSoftmax(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value,
-                flags, dtype):
+                flags, dtype, logit_bound):
         a16, b16 = a.detach().to(dtype).contiguous(), b.detach().to(dtype).contiguous()
         lse, diag, pos_sum, pos_cnt = torch.ops.rs.ce_fwd(a16, b16, scale, col_bias, key_a_row, key_a_col, key_b_row,
-                                                          key_b_col, diag_offset, mask_value, flags)
+                                                          key_b_col, diag_offset, mask_value, flags, logit_bound)
         ctx.save_for_backward(a16, b16, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, lse)
-        ctx.meta = (scale, diag_offset, mask_value, flags, a.dtype, b.dtype)
+        ctx.meta = (scale, diag_offset, mask_value, flags, a.dtype, b.dtype, logit_bound)
         ctx.mark_non_differentiable(pos_cnt)
         return lse, diag, pos_sum, pos_cnt
 
     @staticmethod
     def backward(ctx, g_lse, g_diag, g_pos, _g_cnt):
         a16, b16, col_bias, kar, kac, kbr, kbc, lse = ctx.saved_tensors
-        scale, diag_offset, mask_value, flags, adt, bdt = ctx.meta
+        scale, diag_offset, mask_value, flags, adt, bdt, logit_bound = ctx.meta
         M = a16.shape[0]
         zeros = None
         if g_lse is None:
@@ -68,20 +69,22 @@ class _FusedSoftmax(torch.autograd.Function):
         w_pos = g_pos.float().contiguous() if (g_pos is not None and flags & L.RS_CE_SUPCON) else None
         w_diag = None if g_diag is None else g_diag.float().contiguous()
         dA, dB = torch.ops.rs.ce_bwd(a16, b16, scale, col_bias, kar, kac, kbr, kbc, diag_offset, mask_value, flags,
-                                     lse, g_lse.float().contiguous(), w_diag, w_pos)
-        return (dA.to(adt), dB.to(bdt)) + (None,) * 10
+                                     lse, g_lse.float().contiguous(), w_diag, w_pos, logit_bound)
+        return (dA.to(adt), dB.to(bdt)) + (None,) * 11
 
 
 def fused_softmax_stats(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor] = None,
                         key_a_row: Optional[Tensor] = None, key_a_col: Optional[Tensor] = None,
                         key_b_row: Optional[Tensor] = None, key_b_col: Optional[Tensor] = None,
                         diag_offset: int = 0, mask_value: float = NEG_INF, flags: int = 0,
-                        dtype: Optional[torch.dtype] = None):
+                        dtype: Optional[torch.dtype] = None, unit_norm: bool = False):
+    """`unit_norm`: the caller vouches that the rows of a and b have norm <= 1 (|logit| <= scale + bias range): the
+    kernels then use a fixed softmax offset instead of a running maximum (rs_ce_problem.logit_bound)."""
     dtype = dtype or _operand_dtype(a, b)
     if col_bias is not None:
         col_bias = col_bias.detach().float().contiguous()
     return _FusedSoftmax.apply(a, b, float(scale), col_bias, key_a_row, key_a_col, key_b_row, key_b_col,
-                               int(diag_offset), float(mask_value), int(flags), dtype)
+                               int(diag_offset), float(mask_value), int(flags), dtype, UNIT_NORM_BOUND if unit_norm else 0.0)
 
 
 def info_nce(a: Tensor, b: Tensor, temperature: float, **kw) -> Tensor:
@@ -108,7 +111,7 @@ def inbatch_corrected_logq_loss(user_emb: Tensor, item_tower_emb: Tensor, target
 def logq_infonce_rows(user_emb: Tensor, item_rows: Tensor, target_ids: Tensor, user_ids: Optional[Tensor],
                       log_q_tensor: Tensor, temperature: float = 0.1, lambda_logq: float = 1.0,
                       col_rows: Optional[Tensor] = None, col_target_ids: Optional[Tensor] = None,
-                      col_user_ids: Optional[Tensor] = None, diag_offset: int = 0) -> Tensor:
+                      col_user_ids: Optional[Tensor] = None, diag_offset: int = 0, unit_norm: bool = False) -> Tensor:
     """C2 on already-gathered item rows.  With `col_*` given the columns are a larger (all-gathered)
     set of negatives and `diag_offset` locates this rank's positives inside it."""
     cols = item_rows if col_rows is None else col_rows
@@ -117,7 +120,7 @@ def logq_infonce_rows(user_emb: Tensor, item_rows: Tensor, target_ids: Tensor, u
     bias = (log_q_tensor[ct] * lambda_logq) if lambda_logq > 0.0 else None
     return info_nce(user_emb, cols, temperature, col_bias=bias, key_a_row=target_ids, key_a_col=ct,
                     key_b_row=user_ids, key_b_col=cu if user_ids is not None else None,
-                    diag_offset=diag_offset, mask_value=NEG_INF)
+                    diag_offset=diag_offset, mask_value=NEG_INF, unit_norm=unit_norm)
 
 
 def item_columns(target_ids: Tensor, num_items: Optional[int] = None):
@@ -141,7 +144,7 @@ def count_ids(ids: Tensor, n: int) -> Tensor:
 def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tensor, col_counts: Tensor,
                          target_ids: Tensor, pos_col: Tensor, own_cols: Optional[Tensor], log_q_tensor: Tensor,
                          temperature: float = 0.1, lambda_logq: float = 1.0, row_cu: Optional[Tensor] = None,
-                         max_rows_per_user: int = 0) -> Tensor:
+                         max_rows_per_user: int = 0, unit_norm: bool = False) -> Tensor:
     """C2 (tower_code/v1_refine_usertower.py:826-861) over the DISTINCT items of the batch.  In-batch columns with
     the same target item share the item row and the logQ, hence the logit, so the reference's [N, N] softmax
     equals an [N, U] softmax over distinct items with the batch multiplicities m_c folded into the column bias:
@@ -162,7 +165,7 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
     if lq is not None:
         bias = bias + lq
     lse0 = fused_softmax_stats(user_emb, col_rows, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
-                               mask_value=NEG_INF, flags=L.RS_CE_NO_DIAG, dtype=dtype)[0]
+                               mask_value=NEG_INF, flags=L.RS_CE_NO_DIAG, dtype=dtype, unit_norm=unit_norm)[0]
     if row_cu is not None:
         s_pos, own_lse = ops.user_block_logits(user_emb, col_rows, pos_col, row_cu, max_rows_per_user, scale, lq,
                                                compute_dtype=dtype)
@@ -194,11 +197,11 @@ def duorec_loss_refined(user_emb_1: Tensor, user_emb_2: Tensor, target_ids: Tens
     become arithmetic on device scalars."""
     z1 = F.normalize(user_emb_1, dim=1)
     z2 = F.normalize(user_emb_2, dim=1)
-    loss = info_nce(z1, z2, temperature)
+    loss = info_nce(z1, z2, temperature, unit_norm=True)
     if lambda_sup > 0:
         lse, _, pos_sum, pos_cnt = fused_softmax_stats(z1, z1, 1.0 / temperature, key_a_row=target_ids,
                                                        key_a_col=target_ids, mask_value=NEG_INF,
-                                                       flags=L.RS_CE_DIAG_MASK | L.RS_CE_SUPCON)
+                                                       flags=L.RS_CE_DIAG_MASK | L.RS_CE_SUPCON, unit_norm=True)
         valid = pos_cnt > 0
         per_row = torch.where(valid, lse - pos_sum / pos_cnt.clamp(min=1.0), torch.zeros_like(lse))
         sup = per_row.sum() / valid.sum().clamp(min=1).to(per_row.dtype)

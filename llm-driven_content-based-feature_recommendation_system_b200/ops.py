@@ -481,7 +481,8 @@ def _(a, b, idx, scale, key_row, key_col, g):
 
 
 # ---- fused in-batch softmax -------------------------------------------------------------------
-def _ce_problem(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags):
+def _ce_problem(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags,
+                logit_bound=0.0):
     p = L.CEProblem()
     p.a, p.b = a.data_ptr(), b.data_ptr()
     p.ab_dtype = L.dt(a)
@@ -493,6 +494,7 @@ def _ce_problem(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_co
     p.key_b_row = key_b_row.data_ptr() if key_b_row is not None else None
     p.key_b_col = key_b_col.data_ptr() if key_b_col is not None else None
     p.diag_offset, p.mask_value, p.flags = diag_offset, mask_value, flags
+    p.logit_bound = logit_bound
     return p
 
 
@@ -508,7 +510,7 @@ def _ce_prepare(a, b, col_bias, keys):
 @torch.library.custom_op("rs::ce_fwd", mutates_args=())
 def ce_fwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], key_a_row: Optional[Tensor],
               key_a_col: Optional[Tensor], key_b_row: Optional[Tensor], key_b_col: Optional[Tensor],
-              diag_offset: int, mask_value: float, flags: int) -> List[Tensor]:
+              diag_offset: int, mask_value: float, flags: int, logit_bound: float = 0.0) -> List[Tensor]:
     """Returns [lse[M], diag[M], pos_sum[M], pos_cnt[M]] (the last two only meaningful with RS_CE_SUPCON)."""
     L.require_cuda(a, b)
     a, b, col_bias, keys = _ce_prepare(a, b, col_bias, [key_a_row, key_a_col, key_b_row, key_b_col])
@@ -518,7 +520,7 @@ def ce_fwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], ke
     sup = bool(flags & L.RS_CE_SUPCON)
     pos_sum = torch.empty(M if sup else 0, dtype=torch.float32, device=dev)
     pos_cnt = torch.empty(M if sup else 0, dtype=torch.float32, device=dev)
-    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags)
+    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags, logit_bound)
     ws = L.workspace(_lib.rs_ce_workspace_bytes(p), dev)
     L.check(_lib.rs_ce_fwd(p, L.ptr(lse), L.ptr(diag), L.ptr(pos_sum) if sup else None,
                            L.ptr(pos_cnt) if sup else None, L.ptr(ws), ws.numel(), L.stream()), "rs_ce_fwd")
@@ -526,7 +528,7 @@ def ce_fwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], ke
 
 
 @ce_fwd_op.register_fake
-def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags):
+def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags, logit_bound=0.0):
     M = a.shape[0]
     n = M if flags & L.RS_CE_SUPCON else 0
     f = lambda k: a.new_empty(k, dtype=torch.float32)
@@ -537,13 +539,13 @@ def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_of
 def ce_bwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], key_a_row: Optional[Tensor],
               key_a_col: Optional[Tensor], key_b_row: Optional[Tensor], key_b_col: Optional[Tensor],
               diag_offset: int, mask_value: float, flags: int, lse: Tensor, w_lse: Tensor,
-              w_diag: Optional[Tensor], w_pos: Optional[Tensor]) -> List[Tensor]:
+              w_diag: Optional[Tensor], w_pos: Optional[Tensor], logit_bound: float = 0.0) -> List[Tensor]:
     """Returns [dA[M,K], dB[N,K]] in fp32 for dS = w_lse*softmax + w_diag*[diag] + w_pos*[positive]."""
     a, b, col_bias, keys = _ce_prepare(a, b, col_bias, [key_a_row, key_a_col, key_b_row, key_b_col])
     dev = a.device
     dA = torch.empty(a.shape, dtype=torch.float32, device=dev)
     dB = torch.empty(b.shape, dtype=torch.float32, device=dev)
-    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags)
+    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags, logit_bound)
     ws = L.workspace(_lib.rs_ce_workspace_bytes(p), dev)
     w_diag_ = None if w_diag is None else _f32(w_diag, "w_diag")
     w_pos_ = None if w_pos is None else _f32(w_pos, "w_pos")
@@ -554,7 +556,7 @@ def ce_bwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], ke
 
 @ce_bwd_op.register_fake
 def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags, lse, w_lse,
-      w_diag, w_pos):
+      w_diag, w_pos, logit_bound=0.0):
     return [a.new_empty(a.shape, dtype=torch.float32), b.new_empty(b.shape, dtype=torch.float32)]
 
 

@@ -172,7 +172,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
         uid = idx // L                                                               # batch row = user id (:801-804)
         if columns == "batch" or (columns == "unique" and ("col_item_ids" not in batch or loss_scope != "all")):
             v = item_tower.normalized_rows(tgt)                                      # :810-811 + :833
-            main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq)
+            main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq, unit_norm=True)
         else:
             if columns == "unique":
                 cid, cnt, pos_col, grid = (batch[k] for k in ("col_item_ids", "col_counts", "pos_col", "own_grid"))
@@ -188,7 +188,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
             else:
                 own = grid[uid] if loss_scope == "all" else None     # one row per user otherwise: nothing to mask
             main = losses.logq_infonce_columns(u, v, cid, cnt, tgt, pos_col, own, item_tower.get_log_q(), 0.1,
-                                               lambda_logq, **blk)
+                                               lambda_logq, unit_norm=True, **blk)     # u and v are F.normalize'd
         cl = losses.duorec_loss_refined(out1[n_main:], out2, tgt_flat[li], lambda_sup=lambda_sup)   # :830-842
         total = main + lambda_cl * cl
     if optimizer is not None:
@@ -341,7 +341,7 @@ class ShardedTwoTower:
             else:
                 blk, own = {}, self.cols.col_of(batch["target_ids"].masked_fill(batch["padding_mask"], -1))[uid]
             main_local = losses.logq_infonce_columns(u, v_cols, cid, cnt, tgt, pos_col, own, self.log_q_by_id, 0.1,
-                                                     lambda_logq, **blk)
+                                                     lambda_logq, unit_norm=True, **blk)
             main = main_local * (n_main / n_glob.squeeze(0))
             # DuoRec across the box
             cl = self._duorec(out1[n_main:], out2, tgt_flat[li], lambda_sup) / self.world
@@ -362,13 +362,13 @@ class ShardedTwoTower:
         B = e1.shape[0]
         z1, z2 = F.normalize(e1, dim=1), F.normalize(e2, dim=1)
         z2_all = sh.all_gather_rows(z2, self.group)
-        loss = losses.info_nce(z1, z2_all, temperature, diag_offset=rank * B)
+        loss = losses.info_nce(z1, z2_all, temperature, diag_offset=rank * B, unit_norm=True)
         if lambda_sup > 0:
             z1_all = sh.all_gather_rows(z1, self.group)
             tgt_all = sh.all_gather_ids(tgt, self.group)
             lse, _, pos_sum, pos_cnt = losses.fused_softmax_stats(
                 z1, z1_all, 1.0 / temperature, key_a_row=tgt, key_a_col=tgt_all, diag_offset=rank * B,
-                mask_value=losses.NEG_INF, flags=losses.L.RS_CE_DIAG_MASK | losses.L.RS_CE_SUPCON)
+                mask_value=losses.NEG_INF, flags=losses.L.RS_CE_DIAG_MASK | losses.L.RS_CE_SUPCON, unit_norm=True)
             valid = pos_cnt > 0
             per_row = torch.where(valid, lse - pos_sum / pos_cnt.clamp(min=1.0), torch.zeros_like(lse))
             n_valid = valid.sum().to(per_row.dtype)

@@ -111,14 +111,14 @@ def _own_cols(pos_col, uid):
     return own
 
 
-def _columns_loss(rs, U, table, tgt, uid, logq, mode, temperature, lam, dtype=torch.bfloat16):
+def _columns_loss(rs, U, table, tgt, uid, logq, mode, temperature, lam, dtype=torch.bfloat16, unit_norm=False):
     """C2 through the distinct-item column form (losses.logq_infonce_columns), columns built on the host."""
     ids, counts, pos_col = rs.losses.item_columns(tgt, None if mode == "unique" else table.shape[0])
     own = _own_cols(pos_col, uid)
 
     def fn(u, t):
         return rs.logq_infonce_columns(u, rs.ops.gather_rows(t, ids.to(DEV)), ids.to(DEV), counts.to(DEV), tgt.to(DEV),
-                                       pos_col.to(DEV), own.to(DEV), logq.to(DEV), temperature, lam)
+                                       pos_col.to(DEV), own.to(DEV), logq.to(DEV), temperature, lam, unit_norm=unit_norm)
     return _run(rs, fn, [U, table], dtype)
 
 
@@ -401,3 +401,32 @@ def test_user_block_logits_vs_torch(rs, dtype):
     ((s_pos * wp.to(DEV)).sum() + (torch.where(fin.to(DEV), own, torch.zeros_like(own)) * wo.to(DEV)).sum()).backward()
     torch.testing.assert_close(u1.grad.cpu(), u0.grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(c1.grad.cpu(), c0.grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("N,V", [(129, 64), (1000, 300), (4096, 3000), (5000, 100000)])
+def test_fixed_offset_and_folded_paths_vs_oracle(rs, N, V):
+    """unit-norm operands -> fixed softmax offset in the forward, folded exponent in the backward (logit_bound > 0):
+    same tolerance as the general path, for the [N, N] form, the distinct-item form and a finite-mask (C5) case."""
+    g = torch.Generator().manual_seed(N + 7)
+    table = F.normalize(torch.randn(V, 128, generator=g), dim=1)
+    tgt = torch.randint(0, V, (N,), generator=g)
+    U = F.normalize(torch.randn(N, 128, generator=g) + 2.0 * table[tgt], dim=1)
+    uid = torch.randint(0, max(2, N // 8), (N,), generator=g)
+    logq = torch.log(torch.rand(V, generator=g) + 1e-6)
+    u, t = U.clone().requires_grad_(True), table.clone().requires_grad_(True)
+    want = olosses.inbatch_corrected_logq_loss(u, t, tgt, uid, logq, 0.1, 1.0)
+    want.backward()
+    ref = dict(loss=want.detach(), grads=[u.grad, t.grad])
+
+    def rows_fn(uu, tt):
+        return rs.logq_infonce_rows(uu, rs.ops.gather_rows(tt, tgt.to(DEV)), tgt.to(DEV), uid.to(DEV), logq.to(DEV), 0.1,
+                                    1.0, unit_norm=True)
+    _cmp(_run(rs, rows_fn, [U, table], torch.bfloat16), ref, torch.bfloat16)
+    _cmp(_columns_loss(rs, U, table, tgt, uid, logq, "unique", 0.1, 1.0, unit_norm=True), ref, torch.bfloat16)
+    # the two kernel paths agree with each other much more tightly than with the fp32 oracle
+    a = _run(rs, rows_fn, [U, table], torch.bfloat16)
+    b = _run(rs, lambda uu, tt: rs.logq_infonce_rows(uu, rs.ops.gather_rows(tt, tgt.to(DEV)), tgt.to(DEV), uid.to(DEV),
+                                                      logq.to(DEV), 0.1, 1.0), [U, table], torch.bfloat16)
+    assert abs(a[0].item() - b[0].item()) < 1e-4
+    for x, y in zip(a[1], b[1]):
+        assert (x - y).abs().max() <= 1e-2 * y.abs().max() + 1e-8
