@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--parallelism", default="sharded", choices=["sharded", "dp"],
                     help="N>1: row-sharded item tables (all-to-all lookups) + negatives spanning the box [default], "
                          "or plain data-parallel replicas with all-reduced gradients and rank-local negatives")
+    ap.add_argument("--cuda-graph", type=int, default=1,
+                    help="1: capture the whole step in one CUDA graph per pooled batch and replay it (default, 1 GPU); "
+                         "0: eager launches")
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="only the resident-input timed loop (for ncu runs)")
@@ -184,7 +187,8 @@ def run_ours(args):
     sharded = world > 1 and args.parallelism == "sharded"
     trainer = rs.train.ShardedTwoTower(model, item) if sharded else None      # re-shards the two item tables in place
     params = list(model.parameters()) + list(item.parameters())
-    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True)
+    use_graph = bool(args.cuda_graph) and world == 1
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
 
     def sync_grads():
         if world == 1:
@@ -244,12 +248,20 @@ def run_ours(args):
 
     # ---- resident-input run: the headline `value`
     last = {}
+    graphs = None
+    if use_graph:
+        # one captured graph per pooled batch (shapes are data dependent); counting our launches at capture time
+        graphs = [rs.train.GraphedStep(step, rb) for rb in resident]
+        per_step_launches = max(g_.launches for g_ in graphs)                     # counted while capturing
+        run = lambda i: graphs[i % pool].replay()
+    else:
+        run = lambda i: step(resident[i % pool])
     for i in range(args.warmup):
-        last["loss"] = step(resident[i % pool])
+        last["loss"] = run(i)
     launches0 = lib.rs_launch_count()
     with ClockSampler(local) as clk:
-        ms = timed(args.steps, lambda i: last.__setitem__("loss", step(resident[i % pool])))
-    launches = lib.rs_launch_count() - launches0
+        ms = timed(args.steps, lambda i: last.__setitem__("loss", run(i)))
+    launches = (per_step_launches * args.steps) if use_graph else (lib.rs_launch_count() - launches0)
     host_ms = timed.host_ms
     total, main, cl = [float(x) for x in last["loss"]]
     assert all(map(lambda v: v == v and abs(v) < 1e6, (total, main, cl))), f"non-finite loss {total, main, cl}"
@@ -257,10 +269,15 @@ def run_ours(args):
 
     # ---- end-to-end run: host batches in, losses out, every step
     def e2e_step(i):
-        b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
-        if sharded:          # the loader-stage products (made with collectives, they live on the device) ride along
-            b.update({k: resident[i % pool][k] for k in plan_keys})
-        t, m, c = step(b)
+        if use_graph:        # H2D into the graph's static inputs, replay, read the losses back
+            g_ = graphs[i % pool]
+            g_.load(host[i % pool])
+            t, m, c = g_.replay()
+        else:
+            b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
+            if sharded:      # the loader-stage products (made with collectives, they live on the device) ride along
+                b.update({k: resident[i % pool][k] for k in plan_keys})
+            t, m, c = step(b)
         last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
 
     if args.minimal:
@@ -344,6 +361,8 @@ def run_ours(args):
                                              f"DuoRec columns all-gathered, other parameters replicated + all-reduced"
                                              if sharded else f"dp{world} (replicated tables, gradients all-reduced, "
                                                              f"rank-local negatives)"),
+                                cuda_graph=("one captured graph per pooled batch (per-batch shapes), replayed" if use_graph
+                                            else "off (eager launches)"),
                                 l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
                     e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
                     kernels=kernels, loss=dict(total=total, main=main, cl=cl))

@@ -227,6 +227,9 @@ int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, int64_t n_c
                         uint64_t seed, void* out, void* stream);
 int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
                         float dropout_p, uint64_t seed, void* dz, void* stream);
+/* Advance the device-side dropout epoch that every kernel above mixes into its (by-value) seed.  Stream-ordered: call
+ * it once at the start of a train step.  Inside a captured CUDA graph it is what makes every REPLAY draw new masks. */
+int rs_rng_advance(void* stream);
 /* out[c] = sum_r x[r, c], fp32, fixed summation order (n_cols % 4 == 0, <= 1024) */
 size_t rs_colsum_workspace_bytes(int64_t n_rows, int64_t n_cols);
 int rs_colsum(const void* x, int dtype, int64_t n_rows, int64_t n_cols, float* out, void* workspace,

@@ -28,6 +28,15 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
   return h;
 }
+// Dropout epoch: one device-side counter mixed into every seed.  rs_rng_advance() increments it from the stream, so a
+// CUDA graph that captured a train step (seeds are by-value kernel arguments, frozen at capture) still draws fresh
+// masks on every replay, while the forward and backward kernels of one step see the same value.
+__device__ unsigned long long g_rng_epoch = 0ull;
+__global__ void rng_advance_kernel() { g_rng_epoch += 1ull; }
+__device__ __forceinline__ uint64_t epoch_seed(uint64_t seed) {
+  return seed ^ (*reinterpret_cast<volatile unsigned long long*>(&g_rng_epoch) * 0x9E3779B97F4A7C15ull);
+}
+
 // 32 uniform bits for element (a, b) of the stream `seed` (two rounds of an avalanche hash: ample for dropout)
 __device__ __forceinline__ uint32_t rnd32(uint64_t seed, uint32_t a, uint32_t b) {
   uint32_t h = mix32(a * 0x9E3779B1u + (uint32_t)seed);
@@ -174,6 +183,7 @@ template <int DT>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const void* __restrict__ qkv, AttnParams p,
                                                        void* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ float smem[];
+  p.seed = epoch_seed(p.seed);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   float* sK = smem + (size_t)warp * 2 * p.max_len * ENC_HD;
   float* sV = sK + p.max_len * ENC_HD;
@@ -281,6 +291,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ 
                                                        const void* __restrict__ out, const float* __restrict__ lse,
                                                        AttnParams p, void* __restrict__ d_qkv) {
   extern __shared__ float smem[];
+  p.seed = epoch_seed(p.seed);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int per_warp = 2 * p.max_len * ENC_HD + 2 * p.max_len;
   float* sA = smem + (size_t)warp * per_warp;           // K, then Q
@@ -363,6 +374,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
                                                      const float* __restrict__ bias, float eps, uint32_t drop_thresh,
                                                      float inv_keep, uint64_t seed, void* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  seed = epoch_seed(seed);
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -399,6 +411,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      float inv_keep, uint64_t seed, void* __restrict__ dx,
                                                      float* __restrict__ part /*[grid][2][128]*/) {
   __shared__ float4 red[2][8][32];
+  seed = epoch_seed(seed);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -472,6 +485,7 @@ __global__ void __launch_bounds__(256) dropout_add_fwd_kernel(const void* __rest
                                                               const float* __restrict__ bias, int c4n, int64_t n4,
                                                               uint32_t drop_thresh, float inv_keep, uint64_t seed,
                                                               void* __restrict__ out) {
+  seed = epoch_seed(seed);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = ld4<DTX>(x, 4 * i);
     float4 b = ld4<DTY>(y, 4 * i);
@@ -493,6 +507,7 @@ __global__ void __launch_bounds__(256) dropout_add_fwd_kernel(const void* __rest
 template <int DTX, int DTY>
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const void* __restrict__ g, int64_t n4, uint32_t drop_thresh,
                                                           float inv_keep, uint64_t seed, void* __restrict__ dy) {
+  seed = epoch_seed(seed);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 b = ld4<DTX>(g, 4 * i);
     if (drop_thresh) {
@@ -523,6 +538,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restric
                                                            const float* __restrict__ bias, int c4n, int64_t n4,
                                                            uint32_t drop_thresh, float inv_keep, uint64_t seed,
                                                            void* __restrict__ out) {
+  seed = epoch_seed(seed);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = ld4<DT>(z, 4 * i);
     if (bias) {
@@ -570,6 +586,12 @@ using namespace rs;
     case RS_BF16: { constexpr int NAME = RS_BF16; __VA_ARGS__; break; } \
     default: return RS_ERR_BAD_ARG;                                     \
   }
+
+extern "C" int rs_rng_advance(void* stream) {
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>();
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
 
 static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, float p, int64_t zero_tail) {
   if (n_seq <= 0 || total < 0 || H <= 0 || max_len <= 0 || zero_tail < 0 || zero_tail > n_seq) return RS_ERR_BAD_ARG;

@@ -41,6 +41,11 @@ def _seed() -> int:
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
+def rng_advance() -> None:
+    """Advance the device-side dropout epoch (stream-ordered; call once per train step)."""
+    L.check(_lib.rs_rng_advance(L.stream()), "rs_rng_advance")
+
+
 # ------------------------------------------------------------------------------------------------ custom ops
 def _colsum(x: Tensor) -> Tensor:
     x = x.contiguous()

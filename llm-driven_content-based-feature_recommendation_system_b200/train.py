@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 from torch.nn.attention import SDPBackend, sdpa_kernel
 
-from . import losses, ops
+from . import encoder, losses, ops
 from .synthetic import FORWARD_KEYS
 
 
@@ -150,6 +150,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
     (needs the batch's `cu_seqlens`, i.e. no empty sequence); same values at the positions the losses read."""
     item_ids = batch["item_ids"]
     B, L = item_ids.shape
+    encoder.rng_advance()            # new dropout epoch (also what makes a captured graph draw new masks per replay)
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
     with torch.no_grad():
@@ -304,6 +305,7 @@ class ShardedTwoTower:
         dist, sh, model, item_tower = self.dist, self.sh, self.model, self.item_tower
         item_ids = batch["item_ids"]
         B, L = item_ids.shape
+        encoder.rng_advance()
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
@@ -376,3 +378,48 @@ class ShardedTwoTower:
             # mean over the valid rows of ALL ranks; x world because the caller averages the rank means
             loss = loss + lambda_sup * per_row.sum() / n_valid.clamp(min=1) * self.world
         return loss
+
+
+class GraphedStep:
+    """One train step captured in a CUDA graph (whole step: forward, losses, backward, clip, optimizer), replayed with
+    a single launch.  The step is ~600 small kernels; eager Python enqueues them about as fast as the GPU retires
+    them, so one graph launch per step takes the host off the critical path.
+
+    Shapes inside the step depend on the batch (valid tokens, distinct items), so a graph belongs to ONE static batch
+    (a dict of device tensors): refill those tensors in place (`load`) and `replay`.  A loader that buckets batches by
+    shape keeps one GraphedStep per bucket.  Dropout: the kernels' seeds are frozen at capture, the device-side epoch
+    advanced inside the step (rs_rng_advance) makes every replay draw new masks; torch's own dropout is graph-safe.
+    The optimizer must be capturable (`torch.optim.AdamW(..., fused=True, capturable=True)`)."""
+
+    def __init__(self, step_fn, static_batch, warmup: int = 3):
+        self.batch = static_batch
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                  # allocator, workspaces, sort caches, autotuned GEMMs: all warm
+                step_fn(static_batch)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        # the (id, position) sorts of the sparse backward are cached per ids tensor: drop the warm-up's entries so that
+        # the sorts are captured INSIDE the graph (a replay after `load` must sort the new ids), and drop the captured
+        # entries afterwards (they live in the graph's private pool)
+        ops._sort_cache.clear()
+        lib = ops._lib
+        c0 = lib.rs_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = step_fn(static_batch)
+        self.launches = int(lib.rs_launch_count() - c0)      # this library's kernel nodes in the graph
+        ops._sort_cache.clear()
+
+    def load(self, host_batch, non_blocking=True):
+        """copy a host batch with the SAME shapes into the static inputs (H2D, stream-ordered before the replay)"""
+        for k, v in host_batch.items():
+            dst = self.batch.get(k)
+            if isinstance(dst, torch.Tensor) and isinstance(v, torch.Tensor):
+                dst.copy_(v, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out

@@ -246,3 +246,61 @@ def test_packed_step_matches_dense_step_bf16(rs):
     for k, gref in res[False][2].items():
         g = res[True][2][k]
         assert (g - gref).abs().max() <= 0.1 * gref.abs().max() + 1e-6, (k, (g - gref).abs().max(), gref.abs().max())
+
+
+def test_graphed_step_matches_eager_and_resorts_after_load(rs):
+    """train.GraphedStep: the whole step replayed from one CUDA graph gives the eager step's losses and gradients,
+    also after `load` refilled the static batch with DIFFERENT ids of the same shapes (the users of the batch in
+    another order: same token / distinct-item counts) -- the sparse backward's sorts must be inside the graph."""
+    syn = rs.synthetic
+    n_items, B, SL = 3000, 64, 50
+    torch.manual_seed(0)
+    model = rs.SASRecUserTower(syn.tower_args(num_items=n_items, max_len=SL)).to(DEV).eval()      # no dropout
+    item = rs.SASRecItemTower(n_items, 128, syn.log_q(n_items)).to(DEV)
+    lookup = syn.pretrained_table(n_items).to(DEV)
+    item.init_from_pretrained(lookup)
+    host = syn.make_batch(B, SL, n_items, seed=9)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    host_b = {k: v[perm].clone() for k, v in host.items()}
+    ha, hb = rs.train.add_host_index(host), rs.train.add_host_index(host_b)
+    assert all(ha[k].shape == hb[k].shape for k in ha)
+    params = list(model.parameters()) + list(item.parameters())
+    opt = torch.optim.AdamW(params, lr=0.0, fused=True, capturable=True)
+    step = lambda b: rs.train.two_tower_step(model, item, b, lookup, opt)
+
+    def grads():
+        return {k: p.grad.clone() for k, p in list(model.named_parameters()) + list(item.named_parameters())
+                if p.grad is not None}
+
+    want = {}
+    for name, h in (("a", ha), ("b", hb)):
+        out = step(rs.train.prepare_batch(h, DEV))
+        want[name] = ([x.item() for x in out], grads())
+    g = rs.train.GraphedStep(step, rs.train.prepare_batch(ha, DEV))
+    for name, h in (("a", ha), ("b", hb), ("a", ha)):
+        g.load(h)
+        out = g.replay()
+        got = ([x.item() for x in out], grads())
+        for x, y in zip(got[0], want[name][0]):
+            assert abs(x - y) <= 1e-4 * max(1.0, abs(y)), (name, got[0], want[name][0])
+        for k, gref in want[name][1].items():
+            torch.testing.assert_close(got[1][k], gref, rtol=1e-3, atol=1e-5 + 1e-3 * gref.abs().max().item(), msg=k)
+
+
+def test_graphed_step_draws_new_dropout_masks_per_replay(rs):
+    """seeds are by-value kernel arguments frozen at capture; the device-side epoch (rs_rng_advance, inside the step)
+    makes every replay an independent draw: consecutive replays of the same batch give different losses (train mode,
+    lr = 0 so that nothing else changes)."""
+    syn = rs.synthetic
+    n_items, B, SL = 3000, 64, 50
+    torch.manual_seed(0)
+    model = rs.SASRecUserTower(syn.tower_args(num_items=n_items, max_len=SL)).to(DEV).train()
+    item = rs.SASRecItemTower(n_items, 128, syn.log_q(n_items)).to(DEV)
+    lookup = syn.pretrained_table(n_items).to(DEV)
+    item.init_from_pretrained(lookup)
+    batch = rs.train.prepare_batch(rs.train.add_host_index(syn.make_batch(B, SL, n_items, seed=9)), DEV)
+    opt = torch.optim.AdamW(list(model.parameters()) + list(item.parameters()), lr=0.0, fused=True, capturable=True)
+    g = rs.train.GraphedStep(lambda b: rs.train.two_tower_step(model, item, b, lookup, opt), batch)
+    vals = [g.replay()[1].item() for _ in range(4)]
+    assert len(set(vals)) == 4, vals
+    assert max(vals) - min(vals) < 0.5, vals                   # same loss up to the dropout noise
