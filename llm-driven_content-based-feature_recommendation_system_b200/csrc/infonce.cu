@@ -119,6 +119,41 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: two fp32 lanes per issue slot)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2_t pk2u(uint32_t a, uint32_t b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t fmul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t fadd2(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// 2^x for a pair.  POLY = false: two MUFU.EX2.  POLY = true: on the FMA pipe -- n = round(x) by the magic-number add,
+// f = x - n in [-0.5, 0.5], degree-3 minimax polynomial (relative error 7.5e-5, far below the 16-bit rounding of the
+// operands), exponent added as an integer.  Needs -125 <= x <= 125 (the callers' bounded-exponent modes guarantee it).
+// The MUFU unit retires 16 ex2 per clock and SM, exactly as long as the tensor core needs for the same tile: moving a
+// share of the exponentials to the (packed) FMA pipe takes the special-function unit off the critical path.
+template <bool POLY>
+__device__ __forceinline__ f2_t exp2_pair(f2_t x) {
+  if (!POLY) {
+    float a, b;
+    upk2(x, a, b);
+    return pk2(ex2(a), ex2(b));
+  }
+  const f2_t t = fadd2(x, pk2(12582912.f, 12582912.f));
+  const f2_t n = fadd2(t, pk2(-12582912.f, -12582912.f));
+  const f2_t f = ffma2(n, pk2(-1.f, -1.f), x);
+  f2_t q = ffma2(pk2(0.055175911635160446f, 0.055175911635160446f), f, pk2(0.24261151254177094f, 0.24261151254177094f));
+  q = ffma2(q, f, pk2(0.6932601928710938f, 0.6932601928710938f));
+  q = ffma2(q, f, pk2(0.9999279975891113f, 0.9999279975891113f));
+  float q0, q1, t0, t1;
+  upk2(q, q0, q1);
+  upk2(t, t0, t1);
+  return pk2(__int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23)),
+             __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23)));
+}
+// of the 16 pairs of a 32-column chunk, NPOLY (spread evenly) take the polynomial
+template <int NPOLY> __host__ __device__ constexpr bool pair_is_poly(int pi) { return ((pi + 1) * NPOLY) / 16 != (pi * NPOLY) / 16; }
+
 // smem matrix descriptors (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
 //   K-major  (rows = M/N index, 128 B of K per row): LBO field 1, SBO = 1024 B (8-row group pitch)
 //   MN-major (rows = K index, 128 B of MN per row, two 16 KB boxes along MN): LBO = 16 KB, SBO = 1024 B
@@ -142,6 +177,7 @@ struct __align__(16) ColMeta {
   uint32_t ka[CE_BN], kb[CE_BN];
   float lse[CE_BN], wl[CE_BN], wd[CE_BN], wp[CE_BN];   // transposed backward (wl/wd/wp pre-multiplied by cs)
   uint32_t kb_lo[4], kb_hi[4];             // per staging warp: min / max of kb over its 32 columns
+  uint32_t ka_lo[4], ka_hi[4];             // ditto for ka: chunks whose key range misses a warp's rows skip the compare
 };
 #define OFF_BIAS 0
 #define OFF_KA (CE_BN * 4)
@@ -186,6 +222,7 @@ struct CeParams {
   //   tune[1] != 0  -> the bound is trustworthy and the exponent range is small: no running max in the forward,
   //                    bias factored out of the exponent in the backward
   //   tune[2] != 0  -> every w_lse >= 0 (needed to move the weight into the exponent)
+  //   tune[3] = scale2 * bound: |a.b * scale2| <= tune[3] when tune[1] != 0
   const float* tune;
 };
 
@@ -264,22 +301,31 @@ __device__ __forceinline__ float lse_or_zero(float lse) { return lse == -INFINIT
 // each staging warp's 32 columns (for the range-disjointness test that lets whole tiles skip that compare)
 template <bool BWD_T>
 __device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int ct, int t128, float cs, float c_off,
-                                           bool fold) {
+                                           bool fold, float top) {
   const int64_t c = (int64_t)ct * CE_BN + t128;
   const bool ok = c < p.N;
   const float b2 = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
   cm.bias[t128] = b2 + c_off;
-  cm.ka[t128] = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
+  const uint32_t ka = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
+  cm.ka[t128] = ka;
   const uint32_t kb = (ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
   cm.kb[t128] = kb;
   const uint32_t lo = __reduce_min_sync(0xffffffffu, kb), hi = __reduce_max_sync(0xffffffffu, kb);
-  if ((t128 & 31) == 0) { cm.kb_lo[t128 >> 5] = lo; cm.kb_hi[t128 >> 5] = hi; }
-  if (!BWD_T && fold) cm.wl[t128] = ex2(-b2);          // pass A folded: the column's bias as a factor 2^-bias
+  const uint32_t alo = __reduce_min_sync(0xffffffffu, ka), ahi = __reduce_max_sync(0xffffffffu, ka);
+  if ((t128 & 31) == 0) {
+    cm.kb_lo[t128 >> 5] = lo; cm.kb_hi[t128 >> 5] = hi;
+    cm.ka_lo[t128 >> 5] = alo; cm.ka_hi[t128 >> 5] = ahi;
+  }
+  // the column's bias as a factor: 2^-bias (backward pass A, folded) / 2^(top - C - bias) in (0, 1] (forward, fixed
+  // offset; the logit offset C = c_off splits into the uniform part `top` and the bias part); +inf bias -> exactly 0
+  if (!BWD_T && fold) cm.wl[t128] = ex2(c_off == 0.f ? -b2 : top - c_off - b2);
   if (BWD_T) {
     const float l2 = ok ? lse_or_zero(__ldg(p.lse + c)) * CE_LOG2E : 0.f;
     const float wl = ok ? __ldg(p.w_lse + c) * cs : 0.f;
-    // pass B folded: -lse2 + log2(w*cs) of the column, in the (otherwise unused) bias slot; w == 0 -> coefficient 0
-    if (fold) cm.bias[t128] = wl > 0.f ? __log2f(wl) - l2 : -INFINITY;
+    // pass B folded: -lse2 + log2(w*cs) of the column, in the (otherwise unused) bias slot; w == 0 -> coefficient
+    // 2^(top - 125 + a*scale2) <= 2^(2 top - 125): nothing in 16 bits next to coefficients of order 2^13, and finite,
+    // which the polynomial exponential needs
+    if (fold) cm.bias[t128] = fmaxf(wl > 0.f ? __log2f(wl) - l2 : -INFINITY, top - 125.f);
     cm.lse[t128] = l2;
     cm.wl[t128] = wl;
     cm.wd[t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) * cs : 0.f;
@@ -523,6 +569,78 @@ __device__ __forceinline__ void bwd_chunk_fold(const uint32_t (&r)[32], uint32_t
   }
 }
 
+// ---- fast paths: no edge, no key hit in this chunk, bounded exponents.  Packed fp32 pairs throughout; NPOLY of the
+// 16 pairs take the polynomial exponential.  Per element: 1/2 FFMA2 + (MUFU | ~4 FMA-pipe) + 1/2 FFMA2|FMUL2 (+ cvt).
+#define CE_FWD_NPOLY 8
+#define CE_BWD_NPOLY 6
+// forward: l += sum_j 2^(a*scale2 - top) * f_j,  f_j = 2^(top - C - bias_j) staged per column (PLAIN: top == C, f = 1)
+template <int MODE, int NPOLY>
+__device__ __forceinline__ void fwd_chunk_fast(const uint32_t (&r)[32], uint32_t meta, int cbase, RowCtx& rc,
+                                               const CeParams& p, float ntop) {
+  const f2_t s2 = pk2(p.scale2, p.scale2), nt2 = pk2(ntop, ntop);
+  f2_t acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const f2_t x0 = ffma2(pk2u(r[4 * q], r[4 * q + 1]), s2, nt2);
+    const f2_t x1 = ffma2(pk2u(r[4 * q + 2], r[4 * q + 3]), s2, nt2);
+    const f2_t e0 = pair_is_poly<NPOLY>(2 * q) ? exp2_pair<true>(x0) : exp2_pair<false>(x0);
+    const f2_t e1 = pair_is_poly<NPOLY>(2 * q + 1) ? exp2_pair<true>(x1) : exp2_pair<false>(x1);
+    if (MODE != MODE_PLAIN) {
+      const float4 f4 = lds_f4(meta + OFF_WL + (cbase + 4 * q) * 4);
+      acc0 = ffma2(e0, pk2(f4.x, f4.y), acc0);
+      acc1 = ffma2(e1, pk2(f4.z, f4.w), acc1);
+    } else {
+      acc0 = fadd2(acc0, e0);
+      acc1 = fadd2(acc1, e1);
+    }
+  }
+  float a, b, c, d;
+  upk2(acc0, a, b);
+  upk2(acc1, c, d);
+  rc.l += (a + b) + (c + d);
+}
+
+// backward: c = 2^(a*scale2 + nl) * f with (nl, f) = (row, column) constants in pass A and (column, row) in pass B
+template <int MODE, bool TRANSPOSED, int NPOLY, bool BF16>
+__device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&r)[32], uint32_t meta, int cbase, const RowCtx& rc,
+                                               const CeParams& p, uint8_t* prow, int rloc) {
+  const f2_t s2 = pk2(p.scale2, p.scale2), nl2 = pk2(rc.nl, rc.nl), eb2 = pk2(rc.eb, rc.eb);
+  uint32_t w[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 f4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (TRANSPOSED) f4 = lds_f4(meta + OFF_BIAS + (cbase + 4 * q) * 4);             // nl_j
+    else if (MODE != MODE_PLAIN) f4 = lds_f4(meta + OFF_WL + (cbase + 4 * q) * 4);   // 2^-bias_j
+    const f2_t x0 = ffma2(pk2u(r[4 * q], r[4 * q + 1]), s2, TRANSPOSED ? pk2(f4.x, f4.y) : nl2);
+    const f2_t x1 = ffma2(pk2u(r[4 * q + 2], r[4 * q + 3]), s2, TRANSPOSED ? pk2(f4.z, f4.w) : nl2);
+    f2_t e0 = pair_is_poly<NPOLY>(2 * q) ? exp2_pair<true>(x0) : exp2_pair<false>(x0);
+    f2_t e1 = pair_is_poly<NPOLY>(2 * q + 1) ? exp2_pair<true>(x1) : exp2_pair<false>(x1);
+    if (MODE != MODE_PLAIN) {
+      e0 = fmul2(e0, TRANSPOSED ? eb2 : pk2(f4.x, f4.y));
+      e1 = fmul2(e1, TRANSPOSED ? eb2 : pk2(f4.z, f4.w));
+    }
+    float a, b, c, d;
+    upk2(e0, a, b);
+    upk2(e1, c, d);
+    w[2 * q] = BF16 ? pack_bf16(a, b) : pack_f16(a, b);
+    w[2 * q + 1] = BF16 ? pack_bf16(c, d) : pack_f16(c, d);
+  }
+  const int box = cbase >> 6;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = (((cbase >> 5) & 1) * 4 + q) ^ (rloc & 7);
+    *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
+}
+
+// does any row of this warp carry a key_a inside the key range of chunk `ch` of the staged column tile?
+__device__ __forceinline__ bool ka_hits(uint32_t meta, int ch, uint32_t my_ka) {
+  uint32_t lo, hi;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(meta + (uint32_t)offsetof(ColMeta, ka_lo) + ch * 4));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(meta + (uint32_t)offsetof(ColMeta, ka_hi) + ch * 4));
+  return __any_sync(0xffffffffu, my_ka >= lo && my_ka <= hi);
+}
+
 // walk the four 32-column chunks of one accumulator; F(r, cbase) consumes one chunk.  (Three epilogue warps per
 // scheduler hide the TMEM load latency; a register double buffer would push the kernel past 128 registers.)
 template <class F>
@@ -598,6 +716,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint32_t it = 0, nuse = 0;                          // nuse: tiles this warpgroup has consumed
     const bool fixed = __ldg(p.tune + 1) != 0.f;        // warp-uniform (device scalar)
     const float c_off = fixed ? __ldg(p.tune) : 0.f;
+    const float top = __ldg(p.tune + 3);                // scale2 * bound: |a.b * scale2| <= top
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int rb, sp, lo, hi;
       item_coords(p, item, rb, sp, lo, hi);
@@ -614,7 +733,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
-        stage_cols<false>(p, cm, ct, t128, 1.0f, c_off, false);
+        stage_cols<false>(p, cm, ct, t128, 1.0f, c_off, fixed, top);
         named_bar_sync(1 + wg, 128);
         const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
@@ -626,7 +745,11 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (fixed) {
           if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
           else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
-          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else if (MODE == MODE_SUPCON) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) {
+            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka)) fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row);
+            else fwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, CE_FWD_NPOLY>(r, meta, cb, rc, p, -top);
+          });
         } else {
           if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
           else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
@@ -756,6 +879,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     // need the masked entries' softmax mass: only -inf masks (coefficient exactly 0) qualify
     const bool fold = MODE != MODE_SUPCON && __ldg(p.tune + 1) != 0.f && __ldg(p.tune + 2) != 0.f &&
                       (MODE == MODE_PLAIN || p.mask2 == -INFINITY);
+    const float top = __ldg(p.tune + 3);
     uint32_t it = 0, nuse = 0, item_n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       int rb, sp, lo, hi;
@@ -779,12 +903,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           rc.nl = rc.wlc > 0.f ? __log2f(rc.wlc) - rc.lse2 : -INFINITY;
         }
       }
+      if (fold && !TRANSPOSED) rc.nl = fmaxf(rc.nl, top - 125.f);      // finite (see stage_cols): rows >= M / w == 0
       rc.jd = row + p.diag_offset;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
-        stage_cols<TRANSPOSED>(p, cm, ct, t128, cs, 0.f, fold);
+        stage_cols<TRANSPOSED>(p, cm, ct, t128, cs, 0.f, fold, top);
         named_bar_sync(1 + wg, 128);
         const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
@@ -798,7 +923,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
         if (!edge && fold) {
           if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, true, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16); });
-          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) {
+            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka)) bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16);
+            else if (bf16) bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, true>(r, meta, cb, rc, p, prow, rloc);
+            else bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, false>(r, meta, cb, rc, p, prow, rloc);
+          });
         } else
         if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, true, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
         else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
@@ -890,6 +1019,7 @@ __global__ void ce_prep_kernel(const float* __restrict__ bias, int64_t n, float 
     if (!(lo <= hi)) { lo = 0.f; hi = 0.f; }                 // no (finite) bias at all
     const float top = fabsf(scale2) * bound;
     tune[0] = top - fminf(lo, 0.f);
+    tune[3] = top;
     const float range = 2.f * top + (hi - lo) + fabsf(fminf(lo, 0.f));
     tune[1] = (bound > 0.f && range < 100.f && fabsf(lo) < 100.f && fabsf(hi) < 100.f) ? 1.f : 0.f;
   }
@@ -945,22 +1075,39 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dtype) 
 }
 
 struct CePlan { int row_blocks, col_tiles, tiles_per_item, nsplit, grid; };
-static CePlan ce_plan(int64_t rows, int64_t cols, int target_items_per_sm) {
+// Work items = (row block, column range).  The column tiles of a row block are cut into `nsplit` EQUAL ranges, nsplit
+// chosen to minimise  rounds x (tiles per item + per-item overhead) + split cost,  rounds = ceil(items / SMs): the
+// persistent CTAs take items round-robin, so what matters is how full the last round is (813 row blocks unsplit are
+// 5.5 rounds = 6; split in two they are 10.99 = 11 half-size rounds) and that all items cost the same.
+static CePlan ce_plan(int64_t rows, int64_t cols, float item_overhead_tiles, float split_cost_tiles) {
   CePlan pl;
   pl.row_blocks = (int)((rows + CE_BM - 1) / CE_BM);
   pl.col_tiles = (int)((cols + CE_BN - 1) / CE_BN);
-  const int64_t pairs = (int64_t)pl.row_blocks * pl.col_tiles;
-  int64_t tpi = pairs / ((int64_t)RS_NUM_SMS * target_items_per_sm);
-  if (tpi < 1) tpi = 1;
-  if (tpi > pl.col_tiles) tpi = pl.col_tiles;
-  pl.tiles_per_item = (int)tpi;
-  pl.nsplit = (pl.col_tiles + pl.tiles_per_item - 1) / pl.tiles_per_item;
+  float best = 0.f;
+  pl.nsplit = 1;
+  pl.tiles_per_item = pl.col_tiles;
+  int max_split = pl.col_tiles < 16 ? pl.col_tiles : 16;
+  if (split_cost_tiles >= 1.f) {      // backward: [nsplit][rows][128] fp32 partials, keep them under 256 MB
+    const int64_t cap = ((int64_t)256 << 20) / (rows * CE_K * 4 + 1);
+    if (cap < max_split) max_split = cap < 1 ? 1 : (int)cap;
+  }
+  for (int ns = 1; ns <= max_split; ++ns) {
+    const int tpi = (pl.col_tiles + ns - 1) / ns;
+    const int ns_eff = (pl.col_tiles + tpi - 1) / tpi;
+    const int64_t items = (int64_t)pl.row_blocks * ns_eff;
+    const int64_t rounds = (items + RS_NUM_SMS - 1) / RS_NUM_SMS;
+    const float cost = (float)rounds * ((float)tpi + item_overhead_tiles) +
+                       split_cost_tiles * (float)ns_eff * (float)pl.row_blocks / (float)RS_NUM_SMS;
+    if (ns == 1 || cost < best) { best = cost; pl.nsplit = ns_eff; pl.tiles_per_item = tpi; }
+  }
   const int64_t items = (int64_t)pl.row_blocks * pl.nsplit;
   pl.grid = (int)(items < RS_NUM_SMS ? items : RS_NUM_SMS);
   return pl;
 }
-#define CE_FWD_ITEMS_PER_SM 8
-#define CE_BWD_ITEMS_PER_SM 3
+// forward: an item costs ~1 tile of fill/combine; a split costs M floats of partials (nothing).  backward: ~3 tiles
+// (pipeline fill, accumulator drain), a split writes and re-reads a [128, 128] fp32 block per row block (~2 tiles).
+#define CE_FWD_PLAN(rows, cols) ce_plan(rows, cols, 1.0f, 0.05f)
+#define CE_BWD_PLAN(rows, cols) ce_plan(rows, cols, 3.0f, 2.0f)
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t ce_smem_bytes(bool bwd) {
@@ -984,10 +1131,10 @@ static int ce_mode(const rs_ce_problem* p) {
 
 extern "C" size_t rs_ce_workspace_bytes(const rs_ce_problem* p) {
   if (ce_validate(p) != RS_OK) return 256;
-  const CePlan f = ce_plan(p->M, p->N, CE_FWD_ITEMS_PER_SM);
+  const CePlan f = CE_FWD_PLAN(p->M, p->N);
   const size_t fwd = 4 * al256((size_t)f.nsplit * p->M * sizeof(float));
-  const CePlan ba = ce_plan(p->M, p->N, CE_BWD_ITEMS_PER_SM);
-  const CePlan bb = ce_plan(p->N, p->M, CE_BWD_ITEMS_PER_SM);
+  const CePlan ba = CE_BWD_PLAN(p->M, p->N);
+  const CePlan bb = CE_BWD_PLAN(p->N, p->M);
   const size_t bwd_a = (size_t)ba.nsplit * p->M * CE_K * sizeof(float);
   const size_t bwd_b = (size_t)bb.nsplit * p->N * CE_K * sizeof(float);
   size_t m = fwd;
@@ -1020,7 +1167,7 @@ extern "C" int rs_ce_fwd(const rs_ce_problem* p, float* lse, float* diag, float*
   if (!lse || !diag || !workspace) return RS_ERR_BAD_ARG;
   const int mode = ce_mode(p);
   if (mode == MODE_SUPCON && (!pos_sum || !pos_cnt)) return RS_ERR_BAD_ARG;
-  const CePlan pl = ce_plan(p->M, p->N, CE_FWD_ITEMS_PER_SM);
+  const CePlan pl = CE_FWD_PLAN(p->M, p->N);
   const size_t pb = al256((size_t)pl.nsplit * p->M * sizeof(float));
   if (workspace_bytes < rs_ce_workspace_bytes(p)) return RS_ERR_WORKSPACE;
   CUtensorMap mapA, mapB;
@@ -1094,7 +1241,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
   if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dA) {      // pass A: rows = A, cols = B
-    const CePlan pl = ce_plan(p->M, p->N, CE_BWD_ITEMS_PER_SM);
+    const CePlan pl = CE_BWD_PLAN(p->M, p->N);
     CeParams k = {};
     fill_common(k, p, pl);
     k.M = p->M; k.N = p->N;
@@ -1113,7 +1260,7 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     RS_LAUNCH_CHECK();
   }
   if (dB) {      // pass B: rows = B, cols = A (transposed roles)
-    const CePlan pl = ce_plan(p->N, p->M, CE_BWD_ITEMS_PER_SM);
+    const CePlan pl = CE_BWD_PLAN(p->N, p->M);
     CeParams k = {};
     fill_common(k, p, pl);
     k.M = p->N; k.N = p->M;
