@@ -22,7 +22,8 @@ namespace rs {
 #define CE_BN 128
 #define CE_K 128
 #define CE_STAGES 4
-#define CE_BWD_STAGES 3
+#define CE_BWD_STAGES 5
+#define CE_MAX_STAGES (CE_STAGES > CE_BWD_STAGES ? CE_STAGES : CE_BWD_STAGES)
 #define CE_TILE_BYTES (CE_BN * CE_K * 2)           // 32 KB: two SWIZZLE_128B boxes of [128 rows x 64 cols]
 #define CE_BOX_BYTES (CE_TILE_BYTES / 2)
 #define CE_NWG 3                                    // epilogue warpgroups (one TMEM accumulator each)
@@ -109,6 +110,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&w)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+        "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from TMEM (16-bit elements, two K values per 32-bit column, one M row per lane), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -188,10 +203,10 @@ struct __align__(16) ColMeta {
 #define OFF_WP (6 * CE_BN * 4)
 
 struct CeShared {
-  uint64_t full[CE_STAGES], empty[CE_STAGES];
+  uint64_t full[CE_MAX_STAGES], empty[CE_MAX_STAGES];
   uint64_t a_full[2], a_empty[2];
   uint64_t tmem_full[CE_NWG], tmem_empty[CE_NWG];
-  uint64_t p_full[2], p_empty[2];          // backward: dS tile in smem ready / consumed by the tensor core
+  uint64_t p_full[CE_NWG];                 // backward: dS tile (16-bit, in TMEM, over its own S accumulator) ready
   uint64_t d2_full, d2_empty;              // backward: dS@X accumulator complete / drained
   uint32_t tmem_base;
   uint32_t pad[3];
@@ -238,12 +253,13 @@ __device__ __forceinline__ void ce_setup(CeShared& sh, int warp, const CUtensorM
   if (warp == 0 && (threadIdx.x & 31) == 0) {
     prefetch_tmap(mapA);
     prefetch_tmap(mapB);
-    for (int i = 0; i < CE_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < CE_MAX_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sh.a_full[i], 1); mbar_init(&sh.a_empty[i], 1);
-      mbar_init(&sh.p_full[i], 128); mbar_init(&sh.p_empty[i], 1);
     }
-    for (int i = 0; i < CE_NWG; ++i) { mbar_init(&sh.tmem_full[i], 1); mbar_init(&sh.tmem_empty[i], 128); }
+    for (int i = 0; i < CE_NWG; ++i) {
+      mbar_init(&sh.tmem_full[i], 1); mbar_init(&sh.tmem_empty[i], 128); mbar_init(&sh.p_full[i], 128);
+    }
     mbar_init(&sh.d2_full, 1);
     mbar_init(&sh.d2_empty, 256);
     fence_barrier_init();
@@ -278,11 +294,13 @@ __device__ __forceinline__ void producer_role(const CeParams& p, CeShared& sh, u
 }
 
 // S(tile) = A_block @ B_tile^T into TMEM accumulator g = it & 1
-template <int NSTAGE>
+template <int NSTAGE, bool WAIT_EMPTY>
 __device__ __forceinline__ void issue_s(const CeParams& p, CeShared& sh, uint8_t* sB, uint64_t adesc,
                                         uint32_t tmem_base, uint32_t it) {
   const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1, g = it % CE_NWG, ng = it / CE_NWG;
-  mbar_wait(&sh.tmem_empty[g], (ng & 1) ^ 1);
+  // backward: the accumulator's previous tenant (dS of tile it-3) is read by the tensor core itself (dS @ X, issued
+  // earlier by this same thread): tcgen05.mma instructions execute in issue order, no barrier needed
+  if (WAIT_EMPTY) mbar_wait(&sh.tmem_empty[g], (ng & 1) ^ 1);
   mbar_wait(&sh.full[s], ph);
   tc_fence_after();
   const uint64_t bdesc = desc_kmajor(smem_u32(sB + s * CE_TILE_BYTES));
@@ -469,7 +487,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], uint32_t meta
 // backward: coefficients dS of one chunk -> 16-bit -> this row's 4 x 16 B pieces of the K-major SWIZZLE_128B tile
 template <int MODE, bool EDGE, bool USE_KB, bool TRANSPOSED>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t meta, int cbase, const RowCtx& rc,
-                                          const CeParams& p, int64_t col0, uint8_t* prow, int rloc, bool bf16) {
+                                          const CeParams& p, int64_t col0, uint32_t ptaddr, bool bf16) {
   float v[32];
   unsigned posbits, diagbit;
   logits32<MODE, EDGE, USE_KB, TRANSPOSED>(r, v, posbits, diagbit, meta, cbase, rc, p, col0);
@@ -502,20 +520,10 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t meta
     one(std::integral_constant<int, 2>{});
     one(std::integral_constant<int, 3>{});
   }
-  const int box = cbase >> 6;
+  uint32_t w[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    if (bf16) {
-      u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-      u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-    } else {
-      u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
-      u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
-    }
-    const int chunk = (((cbase >> 5) & 1) * 4 + q) ^ (rloc & 7);
-    *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = u;
-  }
+  for (int q = 0; q < 16; ++q) w[q] = bf16 ? pack_bf16(v[2 * q], v[2 * q + 1]) : pack_f16(v[2 * q], v[2 * q + 1]);
+  tmem_st16(ptaddr, w);
 }
 
 // backward fast path (no edge, weights >= 0, small exponent range): everything that is constant along the row or the
@@ -523,7 +531,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t meta
 // and eb_j = 2^-bias2_j; transposed: c = 2^(a*scale2 + nl_j) * eb_i.  Per element: FFMA, EX2, FMUL, compare, select.
 template <int MODE, bool USE_KB, bool TRANSPOSED>
 __device__ __forceinline__ void bwd_chunk_fold(const uint32_t (&r)[32], uint32_t meta, int cbase, const RowCtx& rc,
-                                               const CeParams& p, uint8_t* prow, int rloc, bool bf16) {
+                                               const CeParams& p, uint32_t ptaddr, bool bf16) {
   float v[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -553,20 +561,10 @@ __device__ __forceinline__ void bwd_chunk_fold(const uint32_t (&r)[32], uint32_t
     one(std::integral_constant<int, 2>{});
     one(std::integral_constant<int, 3>{});
   }
-  const int box = cbase >> 6;
+  uint32_t w[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    if (bf16) {
-      u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-      u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-    } else {
-      u.x = pack_f16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_f16(v[8 * q + 2], v[8 * q + 3]);
-      u.z = pack_f16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_f16(v[8 * q + 6], v[8 * q + 7]);
-    }
-    const int chunk = (((cbase >> 5) & 1) * 4 + q) ^ (rloc & 7);
-    *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = u;
-  }
+  for (int q = 0; q < 16; ++q) w[q] = bf16 ? pack_bf16(v[2 * q], v[2 * q + 1]) : pack_f16(v[2 * q], v[2 * q + 1]);
+  tmem_st16(ptaddr, w);
 }
 
 // ---- fast paths: no edge, no key hit in this chunk, bounded exponents.  Packed fp32 pairs throughout; NPOLY of the
@@ -603,7 +601,7 @@ __device__ __forceinline__ void fwd_chunk_fast(const uint32_t (&r)[32], uint32_t
 // backward: c = 2^(a*scale2 + nl) * f with (nl, f) = (row, column) constants in pass A and (column, row) in pass B
 template <int MODE, bool TRANSPOSED, int NPOLY, bool BF16>
 __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&r)[32], uint32_t meta, int cbase, const RowCtx& rc,
-                                               const CeParams& p, uint8_t* prow, int rloc) {
+                                               const CeParams& p, uint32_t ptaddr) {
   const f2_t s2 = pk2(p.scale2, p.scale2), nl2 = pk2(rc.nl, rc.nl), eb2 = pk2(rc.eb, rc.eb);
   uint32_t w[16];
 #pragma unroll
@@ -625,12 +623,7 @@ __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&r)[32], uint32_t
     w[2 * q] = BF16 ? pack_bf16(a, b) : pack_f16(a, b);
     w[2 * q + 1] = BF16 ? pack_bf16(c, d) : pack_f16(c, d);
   }
-  const int box = cbase >> 6;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int chunk = (((cbase >> 5) & 1) * 4 + q) ^ (rloc & 7);
-    *reinterpret_cast<uint4*>(prow + box * CE_BOX_BYTES + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-  }
+  tmem_st16(ptaddr, w);
 }
 
 // does any row of this warp carry a key_a inside the key range of chunk `ch` of the staged column tile?
@@ -701,7 +694,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         mbar_wait(&sh.a_full[ab], (item_n >> 1) & 1);
         const uint64_t adesc = desc_kmajor(smem_u32(sA + ab * CE_TILE_BYTES));
         for (int ct = lo; ct < hi; ++ct, ++it) {
-          issue_s<CE_STAGES>(p, sh, sB, adesc, tmem_base, it);
+          issue_s<CE_STAGES, true>(p, sh, sB, adesc, tmem_base, it);
           umma_commit(&sh.empty[it % CE_STAGES]);
         }
         umma_commit(&sh.a_empty[ab]);
@@ -817,8 +810,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                                       // 1 x 32 KB (row-side operand of the item)
   uint8_t* sB = base + CE_TILE_BYTES;                       // CE_BWD_STAGES x 32 KB (column-side tiles X)
-  uint8_t* sP = base + (1 + CE_BWD_STAGES) * CE_TILE_BYTES; // 2 x 32 KB (dS tiles, 16-bit, K-major SWIZZLE_128B)
-  CeShared& sh = *reinterpret_cast<CeShared*>(base + (3 + CE_BWD_STAGES) * CE_TILE_BYTES);
+  CeShared& sh = *reinterpret_cast<CeShared*>(base + (1 + CE_BWD_STAGES) * CE_TILE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ce_setup(sh, warp, &mapA, &mapB, 512);
   const uint32_t tmem_base = sh.tmem_base;
@@ -838,23 +830,21 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const uint64_t adesc = desc_kmajor(smem_u32(sA + ab * CE_TILE_BYTES));
         mbar_wait(&sh.d2_empty, (item_n & 1) ^ 1);      // previous item's dS@X accumulator has been drained
         tc_fence_after();
-        issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, it0);
-        if (nt > 1) issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, it0 + 1);
+        issue_s<CE_BWD_STAGES, false>(p, sh, sB, adesc, tmem_base, it0);
+        if (nt > 1) issue_s<CE_BWD_STAGES, false>(p, sh, sB, adesc, tmem_base, it0 + 1);
         for (uint32_t t = it0; t < it0 + nt; ++t) {
           // S(t+2) is issued before dS(t)@X so that the other epilogue warpgroups have work meanwhile
-          if (t + 2 < it0 + nt) issue_s<CE_BWD_STAGES>(p, sh, sB, adesc, tmem_base, t + 2);
-          const uint32_t s = t % CE_BWD_STAGES, g = t & 1, ng = t >> 1;      // dS buffers alternate by tile
-          mbar_wait(&sh.p_full[g], ng & 1);
+          if (t + 2 < it0 + nt) issue_s<CE_BWD_STAGES, false>(p, sh, sB, adesc, tmem_base, t + 2);
+          const uint32_t s = t % CE_BWD_STAGES, g = t % CE_NWG, ng = t / CE_NWG;
+          mbar_wait(&sh.p_full[g], ng & 1);                 // dS(t) sits in TMEM, over the first 64 columns of S(t)
           tc_fence_after();
-          const uint64_t pdesc = desc_kmajor(smem_u32(sP + g * CE_TILE_BYTES));
           const uint64_t xdesc = desc_mnmajor(smem_u32(sB + s * CE_TILE_BYTES));
 #pragma unroll
           for (int k = 0; k < CE_BN / 16; ++k) {
-            const uint64_t aoff = (uint64_t)(((k >> 2) * CE_BOX_BYTES + (k & 3) * 32) >> 4);   // 16 columns c of dS
             const uint64_t boff = (uint64_t)((k * 16 * 128) >> 4);                              // 16 rows c of X
-            umma_f16(tmem_base + CE_NWG * CE_BN, pdesc + aoff, xdesc + boff, p.idesc_g, (t > it0 || k > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_base + CE_NWG * CE_BN, tmem_base + g * CE_BN + k * 8, xdesc + boff, p.idesc_g,
+                        (t > it0 || k > 0) ? 1u : 0u);      // 16 columns c of dS = 8 TMEM columns
           }
-          umma_commit(&sh.p_empty[g]);
           umma_commit(&sh.empty[s]);
         }
         it = it0 + nt;
@@ -915,27 +905,25 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int64_t c0 = (int64_t)ct * CE_BN;
         const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
         const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
-        const uint32_t pb = it & 1;                     // dS buffers alternate by tile
         mbar_wait(&sh.tmem_full[wg], nuse & 1);
-        mbar_wait(&sh.p_empty[pb], ((it >> 1) & 1) ^ 1);   // the tensor core is done with this dS buffer
         tc_fence_after();
-        uint8_t* prow = sP + pb * CE_TILE_BYTES + rloc * 128;
+        // dS (16-bit pairs) goes back into TMEM over the S columns this thread has already consumed: chunk ch
+        // (S columns 32ch..32ch+31) -> columns 16ch..16ch+15; the second GEMM takes it from there as its A operand
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
         if (!edge && fold) {
-          if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, true, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16); });
+          if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, true, TRANSPOSED>(r, meta, cb, rc, p, tt + (cb >> 1), bf16); });
           else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) {
-            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka)) bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, prow, rloc, bf16);
-            else if (bf16) bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, true>(r, meta, cb, rc, p, prow, rloc);
-            else bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, false>(r, meta, cb, rc, p, prow, rloc);
+            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka)) bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, tt + (cb >> 1), bf16);
+            else if (bf16) bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, true>(r, meta, cb, rc, p, tt + (cb >> 1));
+            else bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, false>(r, meta, cb, rc, p, tt + (cb >> 1));
           });
         } else
-        if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, true, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
-        else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
-        else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, false, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, prow, rloc, bf16); });
+        if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, true, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, tt + (cb >> 1), bf16); });
+        else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, true, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, tt + (cb >> 1), bf16); });
+        else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk<MODE, false, false, TRANSPOSED>(r, meta, cb, rc, p, c0 + cb, tt + (cb >> 1), bf16); });
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&sh.tmem_empty[wg]);
-        fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
-        mbar_arrive(&sh.p_full[pb]);
+        mbar_arrive(&sh.p_full[wg]);
         ++nuse;
       }
       // ---- drain the dS@X accumulator: warpgroup wg takes columns [64*wg, 64*wg+64)
@@ -1111,7 +1099,7 @@ static CePlan ce_plan(int64_t rows, int64_t cols, float item_overhead_tiles, flo
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t ce_smem_bytes(bool bwd) {
-  return (size_t)(bwd ? (3 + CE_BWD_STAGES) : (2 + CE_STAGES)) * CE_TILE_BYTES + sizeof(CeShared) + 1024;
+  return (size_t)(bwd ? (1 + CE_BWD_STAGES) : (2 + CE_STAGES)) * CE_TILE_BYTES + sizeof(CeShared) + 1024;
 }
 
 static int ce_validate(const rs_ce_problem* p) {
