@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librs_twotower.so")
+LIB_PATH = os.environ.get("RS_TWOTOWER_LIB") or os.path.join(_HERE, "librs_twotower.so")   # override: kernel-variant experiments only
 
 RS_F32, RS_F16, RS_BF16 = 0, 1, 2
 RS_CE_DIAG_MASK, RS_CE_DIAG_RAW, RS_CE_SUPCON, RS_CE_NO_DIAG = 1, 2, 4, 8

@@ -317,19 +317,35 @@ __device__ __forceinline__ float lse_or_zero(float lse) { return lse == -INFINIT
 
 // stage the metadata of column tile `ct` (one column per thread of the warpgroup) + the key_b range of
 // each staging warp's 32 columns (for the range-disjointness test that lets whole tiles skip that compare)
+// Column metadata of one tile, one column per thread of the warpgroup.  Split in two so that the global loads of the
+// warpgroup's NEXT tile are in flight while it waits for the current accumulator (cols_load), and land in the other
+// metadata buffer right after that wait (cols_store): their latency never sits between two tiles.
+struct ColRegs { float b, lse, wl, wd, wp; uint32_t ka, kb; bool ok; };
 template <bool BWD_T>
-__device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int ct, int t128, float cs, float c_off,
-                                           bool fold, float top) {
+__device__ __forceinline__ ColRegs cols_load(const CeParams& p, int ct, int t128) {
+  ColRegs r;
   const int64_t c = (int64_t)ct * CE_BN + t128;
-  const bool ok = c < p.N;
-  const float b2 = (ok && p.col_bias) ? __ldg(p.col_bias + c) * CE_LOG2E : 0.f;
+  r.ok = c < p.N;
+  r.b = (r.ok && p.col_bias) ? __ldg(p.col_bias + c) : 0.f;
+  r.ka = (r.ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
+  r.kb = (r.ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
+  r.lse = 0.f; r.wl = 0.f; r.wd = 0.f; r.wp = 0.f;
+  if (BWD_T) {
+    if (r.ok) { r.lse = __ldg(p.lse + c); r.wl = __ldg(p.w_lse + c); }
+    if (r.ok && p.w_diag) r.wd = __ldg(p.w_diag + c);
+    if (r.ok && p.w_pos) r.wp = __ldg(p.w_pos + c);
+  }
+  return r;
+}
+template <bool BWD_T>
+__device__ __forceinline__ void cols_store(const ColRegs& r, ColMeta& cm, int t128, float cs, float c_off, bool fold,
+                                           float top) {
+  const float b2 = r.b * CE_LOG2E;
   cm.bias[t128] = b2 + c_off;
-  const uint32_t ka = (ok && p.key_a_col) ? (uint32_t)__ldg(p.key_a_col + c) : 0xFFFFFFFEu;
-  cm.ka[t128] = ka;
-  const uint32_t kb = (ok && p.key_b_col) ? (uint32_t)__ldg(p.key_b_col + c) : 0xFFFFFFFEu;
-  cm.kb[t128] = kb;
-  const uint32_t lo = __reduce_min_sync(0xffffffffu, kb), hi = __reduce_max_sync(0xffffffffu, kb);
-  const uint32_t alo = __reduce_min_sync(0xffffffffu, ka), ahi = __reduce_max_sync(0xffffffffu, ka);
+  cm.ka[t128] = r.ka;
+  cm.kb[t128] = r.kb;
+  const uint32_t lo = __reduce_min_sync(0xffffffffu, r.kb), hi = __reduce_max_sync(0xffffffffu, r.kb);
+  const uint32_t alo = __reduce_min_sync(0xffffffffu, r.ka), ahi = __reduce_max_sync(0xffffffffu, r.ka);
   if ((t128 & 31) == 0) {
     cm.kb_lo[t128 >> 5] = lo; cm.kb_hi[t128 >> 5] = hi;
     cm.ka_lo[t128 >> 5] = alo; cm.ka_hi[t128 >> 5] = ahi;
@@ -338,16 +354,16 @@ __device__ __forceinline__ void stage_cols(const CeParams& p, ColMeta& cm, int c
   // offset; the logit offset C = c_off splits into the uniform part `top` and the bias part); +inf bias -> exactly 0
   if (!BWD_T && fold) cm.wl[t128] = ex2(c_off == 0.f ? -b2 : top - c_off - b2);
   if (BWD_T) {
-    const float l2 = ok ? lse_or_zero(__ldg(p.lse + c)) * CE_LOG2E : 0.f;
-    const float wl = ok ? __ldg(p.w_lse + c) * cs : 0.f;
+    const float l2 = r.ok ? lse_or_zero(r.lse) * CE_LOG2E : 0.f;
+    const float wl = r.wl * cs;
     // pass B folded: -lse2 + log2(w*cs) of the column, in the (otherwise unused) bias slot; w == 0 -> coefficient
     // 2^(top - 125 + a*scale2) <= 2^(2 top - 125): nothing in 16 bits next to coefficients of order 2^13, and finite,
     // which the polynomial exponential needs
     if (fold) cm.bias[t128] = fmaxf(wl > 0.f ? __log2f(wl) - l2 : -INFINITY, top - 125.f);
     cm.lse[t128] = l2;
     cm.wl[t128] = wl;
-    cm.wd[t128] = (ok && p.w_diag) ? __ldg(p.w_diag + c) * cs : 0.f;
-    cm.wp[t128] = (ok && p.w_pos) ? __ldg(p.w_pos + c) * cs : 0.f;
+    cm.wd[t128] = r.wd * cs;
+    cm.wp[t128] = r.wp * cs;
   }
 }
 
@@ -569,8 +585,12 @@ __device__ __forceinline__ void bwd_chunk_fold(const uint32_t (&r)[32], uint32_t
 
 // ---- fast paths: no edge, no key hit in this chunk, bounded exponents.  Packed fp32 pairs throughout; NPOLY of the
 // 16 pairs take the polynomial exponential.  Per element: 1/2 FFMA2 + (MUFU | ~4 FMA-pipe) + 1/2 FFMA2|FMUL2 (+ cvt).
-#define CE_FWD_NPOLY 8
-#define CE_BWD_NPOLY 6
+#ifndef CE_FWD_NPOLY
+#define CE_FWD_NPOLY 6
+#endif
+#ifndef CE_BWD_NPOLY
+#define CE_BWD_NPOLY 4
+#endif
 // forward: l += sum_j 2^(a*scale2 - top) * f_j,  f_j = 2^(top - C - bias_j) staged per column (PLAIN: top == C, f = 1)
 template <int MODE, int NPOLY>
 __device__ __forceinline__ void fwd_chunk_fast(const uint32_t (&r)[32], uint32_t meta, int cbase, RowCtx& rc,
@@ -723,17 +743,24 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       rc.c_off = c_off; rc.mask2c = p.mask2 - c_off;
       rc.m = fixed ? c_off : -INFINITY; rc.l = 0.f; rc.ps = 0.f; rc.pc = 0.f;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;   // diag col span
+      // first tile of this warpgroup in the item: its column metadata is staged here, every later one is loaded
+      // while the warpgroup waits for the current accumulator (see cols_load)
+      const int first = lo + (int)((wg + CE_NWG - it % CE_NWG) % CE_NWG);
+      if (first < hi) cols_store<false>(cols_load<false>(p, first, t128), sh.meta[wg][nuse & 1], t128, 1.0f, c_off, fixed, top);
+      named_bar_sync(1 + wg, 128);
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
-        stage_cols<false>(p, cm, ct, t128, 1.0f, c_off, fixed, top);
-        named_bar_sync(1 + wg, 128);
+        const bool has_next = ct + CE_NWG < hi;
+        ColRegs nxt;
+        if (has_next) nxt = cols_load<false>(p, ct + CE_NWG, t128);
         const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
         const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
         const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
         mbar_wait(&sh.tmem_full[wg], nuse & 1);
         tc_fence_after();
+        if (has_next) cols_store<false>(nxt, sh.meta[wg][(nuse + 1) & 1], t128, 1.0f, c_off, fixed, top);
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
         if (fixed) {
           if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
@@ -751,6 +778,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[wg]);
         ++nuse;
+        named_bar_sync(1 + wg, 128);                     // the next tile's metadata is complete (and this one's is free)
       }
       // ---- combine the two warpgroups' running (max, sum) and write this split's partial
       if (wg > 0) { sh.xm[wg - 1][rloc] = rc.m; sh.xl[wg - 1][rloc] = rc.l; sh.xps[wg - 1][rloc] = rc.ps; sh.xpc[wg - 1][rloc] = rc.pc; }
@@ -896,17 +924,22 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (fold && !TRANSPOSED) rc.nl = fmaxf(rc.nl, top - 125.f);      // finite (see stage_cols): rows >= M / w == 0
       rc.jd = row + p.diag_offset;
       const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;
+      const int first = lo + (int)((wg + CE_NWG - it % CE_NWG) % CE_NWG);
+      if (first < hi) cols_store<TRANSPOSED>(cols_load<TRANSPOSED>(p, first, t128), sh.meta[wg][nuse & 1], t128, cs, 0.f, fold, top);
+      named_bar_sync(1 + wg, 128);
       for (int ct = lo; ct < hi; ++ct, ++it) {
         if ((int)(it % CE_NWG) != wg) continue;
         ColMeta& cm = sh.meta[wg][nuse & 1];
-        stage_cols<TRANSPOSED>(p, cm, ct, t128, cs, 0.f, fold, top);
-        named_bar_sync(1 + wg, 128);
+        const bool has_next = ct + CE_NWG < hi;
+        ColRegs nxt;
+        if (has_next) nxt = cols_load<TRANSPOSED>(p, ct + CE_NWG, t128);
         const uint32_t meta = smem_u32(&cm);
         const int64_t c0 = (int64_t)ct * CE_BN;
         const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
         const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
         mbar_wait(&sh.tmem_full[wg], nuse & 1);
         tc_fence_after();
+        if (has_next) cols_store<TRANSPOSED>(nxt, sh.meta[wg][(nuse + 1) & 1], t128, cs, 0.f, fold, top);
         // dS (16-bit pairs) goes back into TMEM over the S columns this thread has already consumed: chunk ch
         // (S columns 32ch..32ch+31) -> columns 16ch..16ch+15; the second GEMM takes it from there as its A operand
         const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
@@ -925,6 +958,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(&sh.p_full[wg]);
         ++nuse;
+        named_bar_sync(1 + wg, 128);                     // the next tile's metadata is complete (and this one's is free)
       }
       // ---- drain the dS@X accumulator: warpgroup wg takes columns [64*wg, 64*wg+64)
       if (wg >= 2) continue;
