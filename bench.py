@@ -187,7 +187,7 @@ def run_ours(args):
     sharded = world > 1 and args.parallelism == "sharded"
     trainer = rs.train.ShardedTwoTower(model, item) if sharded else None      # re-shards the two item tables in place
     params = list(model.parameters()) + list(item.parameters())
-    use_graph = bool(args.cuda_graph) and world == 1
+    use_graph = bool(args.cuda_graph) and world == 1      # N > 1: eager (capturing the NCCL exchanges hung in a 2-GPU trial)
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
 
     def sync_grads():

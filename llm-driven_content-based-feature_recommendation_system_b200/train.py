@@ -324,7 +324,7 @@ class ShardedTwoTower:
             tgt = tgt_flat[idx]
             uid = idx // L
             # main loss: all items as columns, global multiplicities
-            n_glob = torch.tensor([float(n_main)], device=u.device)
+            n_glob = torch.full((1,), float(n_main), device=u.device)          # (a fill kernel: graph-capturable)
             dist.all_reduce(n_glob, group=self.group)
             if "col_plan" in batch:
                 # columns = the distinct targets of the whole box: fetch their rows from the owners (all-to-all), normalise
@@ -408,7 +408,10 @@ class GraphedStep:
         lib = ops._lib
         c0 = lib.rs_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # collectives inside the step (N > 1) are captured too; NCCL's watchdog thread polls events meanwhile, which a
+        # "global" capture would reject
+        mode = "thread_local" if (torch.distributed.is_available() and torch.distributed.is_initialized()) else "global"
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
             self.out = step_fn(static_batch)
         self.launches = int(lib.rs_launch_count() - c0)      # this library's kernel nodes in the graph
         ops._sort_cache.clear()
