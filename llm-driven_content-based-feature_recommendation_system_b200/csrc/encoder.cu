@@ -341,6 +341,325 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ 
   }
 }
 
+// ================================================================================================ attention, v2
+// Same arithmetic as above, restructured for occupancy and instruction-level parallelism:
+//   * keys (forward, dQ phase) / queries (dK-dV phase) are staged in blocks of 16 rows: 4 KB of shared memory per warp
+//     whatever the sequence length (was 2 x max_len rows: 13 KB per warp, 16 resident warps per SM), online softmax
+//     across blocks;
+//   * two keys (queries) per iteration -- independent dot/exp chains -- and a branch-free running-max update;
+//   * packed fp32 pairs (FFMA2) for every dot product and accumulation.
+#define ATT_BLK 16
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t fmul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t fadd2(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// stage `n` rows (<= 16) as fp32 [16][32]; the row after the last one is zero-filled when n is odd (pairs are processed)
+template <int DT>
+__device__ __forceinline__ void stage_block(float* dst, const void* src, int64_t row0, int n, int64_t row_stride,
+                                            int64_t col0, const float* bias, int lane) {
+  const int sub = lane >> 3, d4 = (lane & 7) * 4;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b4 = ldg_f4(bias + col0 + d4);
+  const int n2 = (n + 1) & ~1;
+#pragma unroll
+  for (int j0 = 0; j0 < ATT_BLK; j0 += 4) {
+    const int j = j0 + sub;
+    if (j < n) {
+      const float4 v = ld4<DT>(src, (row0 + j) * row_stride + col0 + d4);
+      *reinterpret_cast<float4*>(dst + j * ENC_HD + d4) = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+    } else if (j < n2) {
+      *reinterpret_cast<float4*>(dst + j * ENC_HD + d4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+template <int N> __device__ __forceinline__ void load_pairs(f2_t (&r)[N / 2], const float* s) {
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
+    r[2 * q] = pk2(v.x, v.y); r[2 * q + 1] = pk2(v.z, v.w);
+  }
+}
+template <int N> __device__ __forceinline__ float dot_pairs(const f2_t (&a)[N / 2], const f2_t (&b)[N / 2]) {
+  f2_t s0 = fmul2(a[0], b[0]), s1 = fmul2(a[1], b[1]);
+#pragma unroll
+  for (int q = 2; q < N / 2; q += 2) { s0 = ffma2(a[q], b[q], s0); s1 = ffma2(a[q + 1], b[q + 1], s1); }
+  float x, y;
+  upk2(fadd2(s0, s1), x, y);
+  return x + y;
+}
+template <int N> __device__ __forceinline__ float dot_smem(const f2_t (&a)[N / 2], const float* s) {
+  f2_t b[N / 2];
+  load_pairs<N>(b, s);
+  return dot_pairs<N>(a, b);
+}
+template <int N> __device__ __forceinline__ void pack_slice(f2_t (&r)[N / 2], const float (&x)[N], float scale) {
+#pragma unroll
+  for (int q = 0; q < N / 2; ++q) r[q] = pk2(x[2 * q] * scale, x[2 * q + 1] * scale);
+}
+template <int DT, int N>
+__device__ __forceinline__ void store_pairs(void* dst, int64_t off, const f2_t (&r)[N / 2], float s) {
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    float a, b, c, d;
+    upk2(r[2 * q], a, b);
+    upk2(r[2 * q + 1], c, d);
+    st4<DT>(dst, off + 4 * q, make_float4(a * s, b * s, c * s, d * s));
+  }
+}
+
+template <int DT, int R>
+__device__ __forceinline__ void attn2_fwd_item(const void* __restrict__ qkv, const AttnParams& p, float* sK, float* sV,
+                                               int64_t t0, int len, int h, int lane, void* __restrict__ out,
+                                               float* __restrict__ lse) {
+  constexpr int N = ENC_HD / R, RPP = 32 / R, NP = N / 2;
+  const int sub = lane % R, rl = lane / R, d0 = sub * N;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int r0 = 0; r0 < len; r0 += RPP) {
+    const int i = r0 + rl;
+    const bool act = i < len;
+    f2_t q[NP], acc[NP];
+    {
+      float qf[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) qf[d] = 0.f;
+      if (act) load_slice<DT, N>(qf, qkv, (t0 + i) * rs_ + h * ENC_HD + d0, p.bias, h * ENC_HD + d0);
+      pack_slice<N>(q, qf, p.scale);
+    }
+#pragma unroll
+    for (int d = 0; d < NP; ++d) acc[d] = 0ull;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
+    const int jend = min(len, r0 + RPP);
+    for (int kb = 0; kb < jend; kb += ATT_BLK) {
+      const int nk = min(ATT_BLK, jend - kb);
+      __syncwarp();
+      stage_block<DT>(sK, qkv, t0 + kb, nk, rs_, os_ + h * ENC_HD, p.bias, lane);
+      stage_block<DT>(sV, qkv, t0 + kb, nk, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);
+      __syncwarp();
+      for (int jj = 0; jj < nk; jj += 2) {
+        const int j0 = kb + jj;
+        float s0 = group_sum<R>(dot_smem<N>(q, sK + jj * ENC_HD + d0));
+        float s1 = group_sum<R>(dot_smem<N>(q, sK + (jj + 1) * ENC_HD + d0));
+        const bool ok0 = act && j0 <= i, ok1 = act && (jj + 1 < nk) && (j0 + 1 <= i);
+        s0 = ok0 ? s0 : -INFINITY;
+        s1 = ok1 ? s1 : -INFINITY;
+        const float mn = fmaxf(m, fmaxf(s0, s1));
+        const float mu = (mn == -INFINITY) ? 0.f : mn;
+        const float c = __expf(m - mu), p0 = __expf(s0 - mu), p1 = __expf(s1 - mu);
+        l = fmaf(l, c, p0 + p1);
+        m = mn;
+        float k0 = p0, k1 = p1;
+        if (p.drop_thresh) {
+          k0 = (rnd32(p.seed, rid, (uint32_t)j0) >= p.drop_thresh) ? p0 * p.inv_keep : 0.f;
+          k1 = (rnd32(p.seed, rid, (uint32_t)(j0 + 1)) >= p.drop_thresh) ? p1 * p.inv_keep : 0.f;
+        }
+        const f2_t c2 = pk2(c, c), a0 = pk2(k0, k0), a1 = pk2(k1, k1);
+        f2_t v0[NP], v1[NP];
+        load_pairs<N>(v0, sV + jj * ENC_HD + d0);
+        load_pairs<N>(v1, sV + (jj + 1) * ENC_HD + d0);
+#pragma unroll
+        for (int d = 0; d < NP; ++d) acc[d] = ffma2(a1, v1[d], ffma2(a0, v0[d], fmul2(acc[d], c2)));
+      }
+    }
+    if (act) {
+      store_pairs<DT, N>(out, (t0 + i) * os_ + h * ENC_HD + d0, acc, 1.f / l);
+      if (sub == 0) lse[(t0 + i) * p.H + h] = m + __logf(l);
+    }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256, 3) attn2_fwd_kernel(const void* __restrict__ qkv, AttnParams p,
+                                                        void* __restrict__ out, float* __restrict__ lse) {
+  __shared__ __align__(16) float smem[8 * 2 * ATT_BLK * ENC_HD];
+  p.seed = epoch_seed(p.seed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  float* sK = smem + warp * 2 * ATT_BLK * ENC_HD;
+  float* sV = sK + ATT_BLK * ENC_HD;
+  const int64_t n_items = p.n_seq * p.H;
+  const int64_t os_ = (int64_t)p.H * ENC_HD;
+  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
+    const int64_t b = item / p.H;
+    const int h = (int)(item % p.H);
+    const int64_t t0 = __ldg(p.cu + b);
+    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (b >= p.zero_from) {                             // a query whose every key is masked (see rs_twotower.h)
+      for (int i = 0; i < len; ++i) {
+        reinterpret_cast<DTStore<DT>*>(out)[(t0 + i) * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
+        if (lane == 0) lse[(t0 + i) * p.H + h] = 0.f;
+      }
+      continue;
+    }
+    if (len <= 8) attn2_fwd_item<DT, 4>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
+    else attn2_fwd_item<DT, 2>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
+  }
+}
+
+// dQ phase: rows = queries; also leaves lse_i and delta_i = <dO_i, O_i> of every row in shared memory for the dK/dV phase
+template <int DT, int R>
+__device__ __forceinline__ void attn2_bwd_q(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                            const void* __restrict__ out, const float* __restrict__ lse,
+                                            const AttnParams& p, float* sA, float* sB, float* sLse, float* sDelta,
+                                            int64_t t0, int len, int h, int lane, void* __restrict__ d_qkv) {
+  constexpr int N = ENC_HD / R, RPP = 32 / R, NP = N / 2;
+  const int sub = lane % R, rl = lane / R, d0 = sub * N;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int r0 = 0; r0 < len; r0 += RPP) {
+    const int i = r0 + rl;
+    const bool act = i < len;
+    f2_t q[NP], g[NP], dq[NP];
+    float di, li = 0.f;
+    {
+      float qf[N], gf[N], of[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) { qf[d] = 0.f; gf[d] = 0.f; of[d] = 0.f; }
+      if (act) {
+        load_slice<DT, N>(qf, qkv, (t0 + i) * rs_ + h * ENC_HD + d0, p.bias, h * ENC_HD + d0);
+        load_slice<DT, N>(gf, d_out, (t0 + i) * os_ + h * ENC_HD + d0, nullptr, 0);
+        load_slice<DT, N>(of, out, (t0 + i) * os_ + h * ENC_HD + d0, nullptr, 0);
+        li = __ldg(lse + (t0 + i) * p.H + h);
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int d = 0; d < N; ++d) part = fmaf(gf[d], of[d], part);
+      di = group_sum<R>(part);
+      pack_slice<N>(q, qf, p.scale);
+      pack_slice<N>(g, gf, 1.f);
+    }
+    if (act && sub == 0) { sLse[i] = li; sDelta[i] = di; }
+#pragma unroll
+    for (int d = 0; d < NP; ++d) dq[d] = 0ull;
+    const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
+    const int jend = min(len, r0 + RPP);
+    for (int kb = 0; kb < jend; kb += ATT_BLK) {
+      const int nk = min(ATT_BLK, jend - kb);
+      __syncwarp();
+      stage_block<DT>(sA, qkv, t0 + kb, nk, rs_, os_ + h * ENC_HD, p.bias, lane);        // K
+      stage_block<DT>(sB, qkv, t0 + kb, nk, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);    // V
+      __syncwarp();
+      for (int jj = 0; jj < nk; jj += 2) {
+        const int j0 = kb + jj;
+        f2_t k0[NP], k1[NP];
+        load_pairs<N>(k0, sA + jj * ENC_HD + d0);
+        load_pairs<N>(k1, sA + (jj + 1) * ENC_HD + d0);
+        const float s0 = group_sum<R>(dot_pairs<N>(q, k0)), s1 = group_sum<R>(dot_pairs<N>(q, k1));
+        float dp0 = group_sum<R>(dot_smem<N>(g, sB + jj * ENC_HD + d0));
+        float dp1 = group_sum<R>(dot_smem<N>(g, sB + (jj + 1) * ENC_HD + d0));
+        const bool ok0 = act && j0 <= i, ok1 = act && (jj + 1 < nk) && (j0 + 1 <= i);
+        const float pr0 = ok0 ? __expf(s0 - li) : 0.f, pr1 = ok1 ? __expf(s1 - li) : 0.f;
+        if (p.drop_thresh) {
+          dp0 = (rnd32(p.seed, rid, (uint32_t)j0) >= p.drop_thresh) ? dp0 * p.inv_keep : 0.f;
+          dp1 = (rnd32(p.seed, rid, (uint32_t)(j0 + 1)) >= p.drop_thresh) ? dp1 * p.inv_keep : 0.f;
+        }
+        const float e0 = pr0 * (dp0 - di), e1 = pr1 * (dp1 - di);
+        const f2_t a0 = pk2(e0, e0), a1 = pk2(e1, e1);
+#pragma unroll
+        for (int d = 0; d < NP; ++d) dq[d] = ffma2(a1, k1[d], ffma2(a0, k0[d], dq[d]));
+      }
+    }
+    if (act) store_pairs<DT, N>(d_qkv, (t0 + i) * rs_ + h * ENC_HD + d0, dq, p.scale);
+  }
+}
+
+// dK / dV phase: rows = keys, query blocks staged (Q in sA, dO in sB)
+template <int DT, int R>
+__device__ __forceinline__ void attn2_bwd_kv(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                             const AttnParams& p, float* sA, float* sB, const float* sLse,
+                                             const float* sDelta, int64_t t0, int len, int h, int lane,
+                                             void* __restrict__ d_qkv) {
+  constexpr int N = ENC_HD / R, RPP = 32 / R, NP = N / 2;
+  const int sub = lane % R, rl = lane / R, d0 = sub * N;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int r0 = 0; r0 < len; r0 += RPP) {
+    const int j = r0 + rl;
+    const bool act = j < len;
+    f2_t k[NP], v[NP], dk[NP], dv[NP];
+    {
+      float kf[N], vf[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) { kf[d] = 0.f; vf[d] = 0.f; }
+      if (act) {
+        load_slice<DT, N>(kf, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + d0, p.bias, os_ + h * ENC_HD + d0);
+        load_slice<DT, N>(vf, qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + d0, p.bias, 2 * os_ + h * ENC_HD + d0);
+      }
+      pack_slice<N>(k, kf, p.scale);
+      pack_slice<N>(v, vf, 1.f);
+    }
+#pragma unroll
+    for (int d = 0; d < NP; ++d) { dk[d] = 0ull; dv[d] = 0ull; }
+    for (int ib = (r0 / ATT_BLK) * ATT_BLK; ib < len; ib += ATT_BLK) {
+      const int nq = min(ATT_BLK, len - ib);
+      __syncwarp();
+      stage_block<DT>(sA, qkv, t0 + ib, nq, rs_, h * ENC_HD, p.bias, lane);              // Q
+      stage_block<DT>(sB, d_out, t0 + ib, nq, os_, h * ENC_HD, nullptr, lane);           // dO
+      __syncwarp();
+#pragma unroll 2
+      for (int ii = 0; ii < nq; ++ii) {
+        const int i = ib + ii;
+        f2_t qr[NP], gr[NP];
+        load_pairs<N>(qr, sA + ii * ENC_HD + d0);
+        load_pairs<N>(gr, sB + ii * ENC_HD + d0);
+        const float s = group_sum<R>(dot_pairs<N>(k, qr));
+        float dp = group_sum<R>(dot_pairs<N>(v, gr));
+        const bool ok = act && i >= j;
+        const float pr = ok ? __expf(s - sLse[i]) : 0.f;
+        float pk = pr;
+        if (p.drop_thresh) {
+          const bool keep = rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh;
+          dp = keep ? dp * p.inv_keep : 0.f;
+          pk = keep ? pr * p.inv_keep : 0.f;
+        }
+        const float e = pr * (dp - sDelta[i]);
+        const f2_t a = pk2(pk, pk), b = pk2(e, e);
+#pragma unroll
+        for (int d = 0; d < NP; ++d) { dv[d] = ffma2(a, gr[d], dv[d]); dk[d] = ffma2(b, qr[d], dk[d]); }
+      }
+    }
+    if (act) {
+      store_pairs<DT, N>(d_qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + d0, dk, p.scale);
+      store_pairs<DT, N>(d_qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + d0, dv, 1.f);
+    }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256, 2) attn2_bwd_kernel(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                                        const void* __restrict__ out, const float* __restrict__ lse,
+                                                        AttnParams p, void* __restrict__ d_qkv) {
+  __shared__ __align__(16) float smem[8 * (2 * ATT_BLK * ENC_HD + 128)];
+  p.seed = epoch_seed(p.seed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  float* sA = smem + warp * (2 * ATT_BLK * ENC_HD + 128);
+  float* sB = sA + ATT_BLK * ENC_HD;
+  float* sLse = sB + ATT_BLK * ENC_HD;
+  float* sDelta = sLse + 64;
+  const int64_t n_items = p.n_seq * p.H;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
+    const int64_t b = item / p.H;
+    const int h = (int)(item % p.H);
+    const int64_t t0 = __ldg(p.cu + b);
+    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (b >= p.zero_from) {
+      for (int i = 0; i < len; ++i)
+        for (int c = 0; c < 3; ++c)
+          reinterpret_cast<DTStore<DT>*>(d_qkv)[(t0 + i) * rs_ + c * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
+      continue;
+    }
+    __syncwarp();                                       // the previous item's lse / delta are no longer read
+    if (len <= 8) {
+      attn2_bwd_q<DT, 4>(qkv, d_out, out, lse, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+      attn2_bwd_kv<DT, 4>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+    } else {
+      attn2_bwd_q<DT, 2>(qkv, d_out, out, lse, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+      attn2_bwd_kv<DT, 2>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
+    }
+  }
+}
+
 // out[c] = sum_r x[r, c]  -- column sums of a [n_rows, n_cols] matrix (bias gradients), two deterministic stages:
 // thread t of a CTA owns column group (t % (n_cols/4)) and walks rows t / (n_cols/4), + row-groups ...; per-CTA partials
 template <int DT>
@@ -613,14 +932,9 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias,
   p.cu = cu_seqlens; p.bias = bias; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
   p.zero_from = n_seq - zero_tail;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
-  const size_t smem = (size_t)4 * 2 * max_len * ENC_HD * sizeof(float);
-  const int grid = grid_for_warps(n_seq * n_heads, 4, 8);
+  const int grid = grid_for_warps(n_seq * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attn_fwd_kernel<DT><<<grid, 128, smem, st>>>(qkv, p, out, lse);
-  });
+  ENC_DISPATCH1(dtype, DT, { attn2_fwd_kernel<DT><<<grid, 256, 0, st>>>(qkv, p, out, lse); });
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -639,14 +953,9 @@ extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void
   p.cu = cu_seqlens; p.bias = bias; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
   p.zero_from = n_seq - zero_tail;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
-  const size_t smem = (size_t)4 * (2 * max_len * ENC_HD + 2 * max_len) * sizeof(float);
-  const int grid = grid_for_warps(n_seq * n_heads, 4, 8);
+  const int grid = grid_for_warps(n_seq * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attn_bwd_kernel<DT><<<grid, 128, smem, st>>>(qkv, d_out, out, lse, p, d_qkv);
-  });
+  ENC_DISPATCH1(dtype, DT, { attn2_bwd_kernel<DT><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv); });
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
