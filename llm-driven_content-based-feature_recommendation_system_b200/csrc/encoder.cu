@@ -136,216 +136,10 @@ template <int R> __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-// One (sequence, head) with R lanes per query row (each lane owns 32/R of the 32 dims) and 32/R rows per pass:
-// short sequences -- the common case, mean length ~13 -- keep all 32 lanes busy instead of one lane per row.
-template <int DT, int R>
-__device__ __forceinline__ void attn_fwd_item(const void* __restrict__ qkv, const AttnParams& p, const float* sK,
-                                              const float* sV, int64_t t0, int len, int h, int lane,
-                                              void* __restrict__ out, float* __restrict__ lse) {
-  constexpr int N = ENC_HD / R, RPP = 32 / R;
-  const int sub = lane % R, rl = lane / R, d0 = sub * N;
-  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
-  for (int r0 = 0; r0 < len; r0 += RPP) {
-    const int i = r0 + rl;
-    const bool act = i < len;
-    float q[N], acc[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) { q[d] = 0.f; acc[d] = 0.f; }
-    if (act) load_slice<DT, N>(q, qkv, (t0 + i) * rs_ + h * ENC_HD + d0, p.bias, h * ENC_HD + d0);
-    float m = -INFINITY, l = 0.f;
-    const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
-    const int jmax = min(len - 1, r0 + RPP - 1);
-    for (int j = 0; j <= jmax; ++j) {
-      const float s = group_sum<R>(dot_slice<N>(q, sK + j * ENC_HD + d0)) * p.scale;
-      if (act && j <= i) {
-        if (s > m) {
-          const float c = __expf(m - s);
-          l *= c;
-#pragma unroll
-          for (int d = 0; d < N; ++d) acc[d] *= c;
-          m = s;
-        }
-        const float pr = __expf(s - m);
-        l += pr;
-        float pk = pr;
-        if (p.drop_thresh) pk = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? pr * p.inv_keep : 0.f;
-        axpy_slice<N>(acc, pk, sV + j * ENC_HD + d0);
-      }
-    }
-    if (act) {
-      store_slice<DT, N>(out, (t0 + i) * os_ + h * ENC_HD + d0, acc, 1.f / l);
-      if (sub == 0) lse[(t0 + i) * p.H + h] = m + __logf(l);
-    }
-  }
-}
-
-template <int DT>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const void* __restrict__ qkv, AttnParams p,
-                                                       void* __restrict__ out, float* __restrict__ lse) {
-  extern __shared__ float smem[];
-  p.seed = epoch_seed(p.seed);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-  float* sK = smem + (size_t)warp * 2 * p.max_len * ENC_HD;
-  float* sV = sK + p.max_len * ENC_HD;
-  const int64_t n_items = p.n_seq * p.H;
-  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
-  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
-    const int64_t b = item / p.H;
-    const int h = (int)(item % p.H);
-    const int64_t t0 = __ldg(p.cu + b);
-    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
-    if (b >= p.zero_from) {                             // a query whose every key is masked (see rs_twotower.h)
-      for (int i = 0; i < len; ++i) {
-        reinterpret_cast<DTStore<DT>*>(out)[(t0 + i) * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
-        if (lane == 0) lse[(t0 + i) * p.H + h] = 0.f;
-      }
-      continue;
-    }
-    stage_rows<DT>(sK, qkv, t0, len, rs_, os_ + h * ENC_HD, p.bias, lane);
-    stage_rows<DT>(sV, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);
-    __syncwarp();
-    if (len <= 4) attn_fwd_item<DT, 8>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
-    else if (len <= 8) attn_fwd_item<DT, 4>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
-    else attn_fwd_item<DT, 2>(qkv, p, sK, sV, t0, len, h, lane, out, lse);
-    __syncwarp();
-  }
-}
-
-// dQ_i = scale * sum_{j<=i} dS_ij K_j          (sA = K, sB = V staged; lane group = query row)
-template <int DT, int R>
-__device__ __forceinline__ void attn_bwd_q(const void* __restrict__ qkv, const void* __restrict__ d_out,
-                                           const AttnParams& p, const float* sA, const float* sB, const float* sLse,
-                                           const float* sDelta, int64_t t0, int len, int h, int lane,
-                                           void* __restrict__ d_qkv) {
-  constexpr int N = ENC_HD / R, RPP = 32 / R;
-  const int sub = lane % R, rl = lane / R, d0 = sub * N;
-  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
-  for (int r0 = 0; r0 < len; r0 += RPP) {
-    const int i = r0 + rl;
-    const bool act = i < len;
-    float q[N], g[N], dq[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) { q[d] = 0.f; g[d] = 0.f; dq[d] = 0.f; }
-    if (act) {
-      load_slice<DT, N>(q, qkv, (t0 + i) * rs_ + h * ENC_HD + d0, p.bias, h * ENC_HD + d0);
-      load_slice<DT, N>(g, d_out, (t0 + i) * os_ + h * ENC_HD + d0, nullptr, 0);
-    }
-    const float li = act ? sLse[i] : 0.f, di = act ? sDelta[i] : 0.f;
-    const uint32_t rid = (uint32_t)((t0 + i) * p.H + h);
-    const int jmax = min(len - 1, r0 + RPP - 1);
-    for (int j = 0; j <= jmax; ++j) {
-      const float s = group_sum<R>(dot_slice<N>(q, sA + j * ENC_HD + d0));
-      float dp = group_sum<R>(dot_slice<N>(g, sB + j * ENC_HD + d0));
-      if (act && j <= i) {
-        const float pr = __expf(s * p.scale - li);
-        if (p.drop_thresh) dp = (rnd32(p.seed, rid, (uint32_t)j) >= p.drop_thresh) ? dp * p.inv_keep : 0.f;
-        axpy_slice<N>(dq, pr * (dp - di), sA + j * ENC_HD + d0);
-      }
-    }
-    if (act) store_slice<DT, N>(d_qkv, (t0 + i) * rs_ + h * ENC_HD + d0, dq, p.scale);
-  }
-}
-
-// dK_j = scale * sum_{i>=j} dS_ij Q_i,  dV_j = sum_{i>=j} P~_ij dO_i     (sA = Q, sB = dO staged; lane group = key row)
-template <int DT, int R>
-__device__ __forceinline__ void attn_bwd_kv(const void* __restrict__ qkv, const AttnParams& p, const float* sA,
-                                            const float* sB, const float* sLse, const float* sDelta, int64_t t0,
-                                            int len, int h, int lane, void* __restrict__ d_qkv) {
-  constexpr int N = ENC_HD / R, RPP = 32 / R;
-  const int sub = lane % R, rl = lane / R, d0 = sub * N;
-  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
-  for (int r0 = 0; r0 < len; r0 += RPP) {
-    const int j = r0 + rl;
-    const bool act = j < len;
-    float k[N], v[N], dk[N], dv[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) { k[d] = 0.f; v[d] = 0.f; dk[d] = 0.f; dv[d] = 0.f; }
-    if (act) {
-      load_slice<DT, N>(k, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + d0, p.bias, os_ + h * ENC_HD + d0);
-      load_slice<DT, N>(v, qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + d0, p.bias, 2 * os_ + h * ENC_HD + d0);
-    }
-    for (int i = r0; i < len; ++i) {
-      const float s = group_sum<R>(dot_slice<N>(k, sA + i * ENC_HD + d0));
-      float dp = group_sum<R>(dot_slice<N>(v, sB + i * ENC_HD + d0));
-      if (act && i >= j) {
-        const float pr = __expf(s * p.scale - sLse[i]);
-        float pk = pr;
-        if (p.drop_thresh) {
-          const bool keep = rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh;
-          dp = keep ? dp * p.inv_keep : 0.f;
-          pk = keep ? pr * p.inv_keep : 0.f;
-        }
-        axpy_slice<N>(dv, pk, sB + i * ENC_HD + d0);
-        axpy_slice<N>(dk, pr * (dp - sDelta[i]), sA + i * ENC_HD + d0);
-      }
-    }
-    if (act) {
-      store_slice<DT, N>(d_qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + d0, dk, p.scale);
-      store_slice<DT, N>(d_qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + d0, dv, 1.f);
-    }
-  }
-}
-
-template <int DT>
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const void* __restrict__ qkv, const void* __restrict__ d_out,
-                                                       const void* __restrict__ out, const float* __restrict__ lse,
-                                                       AttnParams p, void* __restrict__ d_qkv) {
-  extern __shared__ float smem[];
-  p.seed = epoch_seed(p.seed);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-  const int per_warp = 2 * p.max_len * ENC_HD + 2 * p.max_len;
-  float* sA = smem + (size_t)warp * per_warp;           // K, then Q
-  float* sB = sA + p.max_len * ENC_HD;                  // V, then dO
-  float* sLse = sB + p.max_len * ENC_HD;
-  float* sDelta = sLse + p.max_len;
-  const int64_t n_items = p.n_seq * p.H;
-  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
-  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
-    const int64_t b = item / p.H;
-    const int h = (int)(item % p.H);
-    const int64_t t0 = __ldg(p.cu + b);
-    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
-    if (b >= p.zero_from) {
-      for (int i = 0; i < len; ++i)
-        for (int c = 0; c < 3; ++c)
-          reinterpret_cast<DTStore<DT>*>(d_qkv)[(t0 + i) * rs_ + c * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
-      continue;
-    }
-    // row statistics: lse_i and delta_i = <dO_i, O_i>  (8 lanes per row)
-    {
-      const int sub = lane >> 3, d4 = (lane & 7) * 4;
-      for (int j0 = 0; j0 < len; j0 += 4) {
-        const int j = j0 + sub;
-        float part = 0.f;
-        if (j < len) part = dot4(ld4<DT>(d_out, (t0 + j) * os_ + h * ENC_HD + d4), ld4<DT>(out, (t0 + j) * os_ + h * ENC_HD + d4));
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 4);
-        if (j < len && (lane & 7) == 0) { sDelta[j] = part; sLse[j] = __ldg(lse + (t0 + j) * p.H + h); }
-      }
-    }
-    stage_rows<DT>(sA, qkv, t0, len, rs_, os_ + h * ENC_HD, p.bias, lane);        // K
-    stage_rows<DT>(sB, qkv, t0, len, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);    // V
-    __syncwarp();
-    if (len <= 4) attn_bwd_q<DT, 8>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
-    else if (len <= 8) attn_bwd_q<DT, 4>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
-    else attn_bwd_q<DT, 2>(qkv, d_out, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
-    __syncwarp();
-    stage_rows<DT>(sA, qkv, t0, len, rs_, h * ENC_HD, p.bias, lane);              // Q
-    stage_rows<DT>(sB, d_out, t0, len, os_, h * ENC_HD, nullptr, lane);           // dO
-    __syncwarp();
-    if (len <= 4) attn_bwd_kv<DT, 8>(qkv, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
-    else if (len <= 8) attn_bwd_kv<DT, 4>(qkv, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
-    else attn_bwd_kv<DT, 2>(qkv, p, sA, sB, sLse, sDelta, t0, len, h, lane, d_qkv);
-    __syncwarp();
-  }
-}
-
-// ================================================================================================ attention, v2
-// Same arithmetic as above, restructured for occupancy and instruction-level parallelism:
+// ================================================================================================ attention, SIMT (fp32 operands)
+// One warp per (sequence, head), R lanes per query row (each lane owns 32/R of the 32 dims):
 //   * keys (forward, dQ phase) / queries (dK-dV phase) are staged in blocks of 16 rows: 4 KB of shared memory per warp
-//     whatever the sequence length (was 2 x max_len rows: 13 KB per warp, 16 resident warps per SM), online softmax
-//     across blocks;
+//     whatever the sequence length, online softmax across blocks;
 //   * two keys (queries) per iteration -- independent dot/exp chains -- and a branch-free running-max update;
 //   * packed fp32 pairs (FFMA2) for every dot product and accumulation.
 #define ATT_BLK 16
@@ -660,6 +454,8 @@ __global__ void __launch_bounds__(256, 2) attn2_bwd_kernel(const void* __restric
   }
 }
 
+#include "attn_mma.cuh"
+
 // out[c] = sum_r x[r, c]  -- column sums of a [n_rows, n_cols] matrix (bias gradients), two deterministic stages:
 // thread t of a CTA owns column group (t % (n_cols/4)) and walks rows t / (n_cols/4), + row-groups ...; per-CTA partials
 template <int DT>
@@ -934,7 +730,11 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias,
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const int grid = grid_for_warps(n_seq * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, { attn2_fwd_kernel<DT><<<grid, 256, 0, st>>>(qkv, p, out, lse); });
+  // 16-bit operands: tensor-core tiles (attn_mma.cuh); fp32: the SIMT kernel
+  if (dtype == RS_BF16) attn3_fwd_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, p, out, lse);
+  else if (dtype == RS_F16) attn3_fwd_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, p, out, lse);
+  else if (dtype == RS_F32) attn2_fwd_kernel<RS_F32><<<grid, 256, 0, st>>>(qkv, p, out, lse);
+  else return RS_ERR_BAD_ARG;
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -955,7 +755,10 @@ extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const int grid = grid_for_warps(n_seq * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, { attn2_bwd_kernel<DT><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv); });
+  if (dtype == RS_BF16) attn3_bwd_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+  else if (dtype == RS_F16) attn3_bwd_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+  else if (dtype == RS_F32) attn2_bwd_kernel<RS_F32><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+  else return RS_ERR_BAD_ARG;
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

@@ -304,3 +304,29 @@ def test_graphed_step_draws_new_dropout_masks_per_replay(rs):
     vals = [g.replay()[1].item() for _ in range(4)]
     assert len(set(vals)) == 4, vals
     assert max(vals) - min(vals) < 0.5, vals                   # same loss up to the dropout noise
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_attn_tensor_core_path_matches_simt_path(rs, dtype):
+    """16-bit operands run on the m16n8k16 tiles (attn_mma.cuh), fp32 on the SIMT kernel: same in_proj bias handling,
+    same zero-tail rule and -- with a seed -- the SAME dropout mask (both hash (row id, key)), forward and backward.
+    Tolerance: 16-bit rounding of the biased operands, of P / dS before the second product and of the outputs."""
+    H, hd, lens = 4, 32, [5, 37, 2, 16, 17, 50, 33, 1, 1]
+    g = torch.Generator().manual_seed(11)
+    T = sum(lens)
+    qkv = (0.7 * torch.randn(T, 3 * H * hd, generator=g)).to(dtype).to(DEV)
+    bias = (0.3 * torch.randn(3 * H * hd, generator=g)).to(DEV)
+    w = torch.randn(T, H * hd, generator=g).to(dtype).to(DEV)
+    cu, scale = _cu(lens).to(DEV), 1 / math.sqrt(hd)
+    for p, seed in ((0.0, 0), (0.25, 987654321)):
+        args = (cu, H, 64, 2, scale, p, seed)
+        out16, lse16 = torch.ops.rs.attn_varlen(qkv, bias, *args)
+        out32, lse32 = torch.ops.rs.attn_varlen(qkv.float(), bias, *args)
+        torch.testing.assert_close(out16.float(), out32, rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(lse16, lse32, rtol=1e-2, atol=2e-2)
+        assert (out16[-2:] == 0).all()
+        d16, _ = torch.ops.rs.attn_varlen_bwd(qkv, bias, w, out16, lse16, *args)
+        d32, _ = torch.ops.rs.attn_varlen_bwd(qkv.float(), bias, w.float(), out32, lse32, *args)
+        assert (d16[-2:] == 0).all()
+        err = (d16.float() - d32).abs().max().item()
+        assert err <= 3e-2 * d32.abs().max().item() + 1e-3, (p, err, d32.abs().max().item())
