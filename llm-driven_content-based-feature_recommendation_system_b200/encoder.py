@@ -306,6 +306,47 @@ def _act_dtype(x: Tensor) -> torch.dtype:
     return x.dtype
 
 
+class _LinearColsumBias(torch.autograd.Function):
+    """y = x W^T + b as nn.Linear computes it (one library GEMM with the bias in its epilogue; under autocast in the
+    autocast dtype); the only difference is the bias gradient: rs::colsum of the incoming gradient (fixed order, one
+    pass) instead of the generic reduction autograd launches behind every Linear."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = F.linear(x, weight, bias)                # (autocast, if active, applies here as for nn.Linear)
+        ctx.save_for_backward(x, weight)
+        ctx.bias_dtype = bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1]).to(g2.dtype)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = (g2 @ weight.to(g2.dtype)).view(x.shape).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            dw = (g2.t() @ x2).to(weight.dtype)
+        db = _colsum(g2).to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear(module: torch.nn.Linear, x: Tensor) -> Tensor:
+    """`module(x)` for a stock nn.Linear, bias gradient by rs::colsum (CUDA, training); plain call otherwise."""
+    if module.bias is None or not x.is_cuda or not torch.is_grad_enabled() or x.shape[-1] % 4 or module.out_features % 4 \
+            or module.out_features > 1024:
+        return module(x)
+    return _LinearColsumBias.apply(x, module.weight, module.bias)
+
+
+def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
+    """`seq(x)` with its nn.Linear members routed through `linear` (same modules, same parameters)."""
+    for m in seq:
+        x = linear(m, x) if isinstance(m, torch.nn.Linear) else m(x)
+    return x
+
+
 def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int,
                          zero_tail: int = 0) -> Tensor:
     if not layer.norm_first or layer.activation_relu_or_gelu != 2:

@@ -96,7 +96,7 @@ class SASRecUserTower(nn.Module):
         ranks (row-sharded table, sharded.py) behind one unused leading row; the kernel then reads row 1 + b*L + l
         for position (b, l) -- same arithmetic, and the gradient of the buffer goes back through the exchange."""
         s_g = torch.sigmoid(self.seq_gate) * self._seq_gate_mask
-        base = self.item_proj(pretrained_vecs)
+        base = enc.linear(self.item_proj, pretrained_vecs)
         ids = [item_ids, time_bucket_ids, type_ids, color_ids, graphic_ids, section_ids]
         tables = [getattr(self, n).weight for n in SEQ_TABLES]
         if item_id_rows is not None:
@@ -111,7 +111,7 @@ class SASRecUserTower(nn.Module):
         other tables -- id 0 never receives gradient -- leaves position 0 alone).  `item_ids` / `time_bucket_ids` /
         `pos_ids` are [R, 64] grids holding the batch's valid tokens (train.add_host_index), zero-padded at the end."""
         s_g = torch.sigmoid(self.seq_gate) * self._seq_gate_mask
-        base = self.item_proj(pretrained_vecs)
+        base = enc.linear(self.item_proj, pretrained_vecs)
         w = self.pos_emb.weight
         pos_ext = torch.cat([w.new_zeros(1, w.shape[1]), w])
         gates = torch.cat([s_g[:2], s_g.new_ones(1)])
@@ -155,7 +155,7 @@ class SASRecUserTower(nn.Module):
         if packed_index is not None:
             # `views` dropout views in ONE pass: the deterministic fronts are computed once, the index / offsets carry
             # every token `views` times (train.add_host_index), and each copy draws its own dropout masks
-            user_profile_vec = self.static_mlp(static_input if views == 1 else static_input.repeat(views, 1))
+            user_profile_vec = enc.sequential(self.static_mlp, static_input if views == 1 else static_input.repeat(views, 1))
             return self._forward_packed(seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index,
                                         cu_seqlens, packed_zero_tail, select_users)
         user_profile_vec = self.static_mlp(static_input)
@@ -203,7 +203,7 @@ class SASRecUserTower(nn.Module):
         if select_index is not None:
             output = ops.gather_rows(output, select_index)
         prof = ops.gather_rows(user_profile_vec, users)
-        final_vec = self.output_proj(torch.cat([output, prof.to(output.dtype)], dim=-1))
+        final_vec = enc.sequential(self.output_proj, torch.cat([output, prof.to(output.dtype)], dim=-1))
         return F.normalize(final_vec, p=2, dim=-1)
 
 
