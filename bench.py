@@ -259,7 +259,7 @@ def run_ours(args):
     # eager mode (N > 1): every pooled batch has its own shapes, the caching allocator and the per-shape library
     # heuristics settle after each has been seen a few times (host enqueue 29 -> 17 ms/step on 2 GPUs): warm up at
     # least 3 rounds over the pool.  Graph mode warmed each batch up while capturing.
-    for i in range(args.warmup if use_graph else max(args.warmup, 3 * pool)):
+    for i in range(max(args.warmup, 3 * pool) if world > 1 else args.warmup):
         last["loss"] = run(i)
     launches0 = lib.rs_launch_count()
     with ClockSampler(local) as clk:
@@ -314,7 +314,8 @@ def run_ours(args):
             a["ms"] += s.elapsed_time(e)
             a["calls"] += 1
             a["work"] += extra
-        P = B * SL
+        # U1 runs on the packed [R, 64] token grid when the batch carries it (train.add_host_index), else on [B, L]
+        P = int(resident[0]["pk_item_ids"].numel()) if "pk_item_ids" in resident[0] else B * SL
         D = 128
         for name, a in agg.items():
             per_step_ms = a["ms"] / nprof
@@ -323,8 +324,9 @@ def run_ours(args):
                 k.update(bound="tensor", unit="TFLOP/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e12,
                          peak=tf_peak)
             elif name == "rs_seq_front_fwd":
-                # per position: base bf16 + 2 live table rows fp32 + out bf16 + 2 ids (pos rows are L2 resident)
-                by = P * (D * 2 + 2 * D * 4 + D * 2 + 2 * 8) * a["calls"] / nprof
+                # per position: base bf16 + the item-id row fp32 + out bf16 + 3 ids (time / position rows: 12- and
+                # 51-row tables, cache resident, not counted)
+                by = P * (D * 2 + D * 4 + D * 2 + 3 * 8) * a["calls"] / nprof
                 k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
             elif name == "rs_seq_front_bwd":
                 by = P * (D * 2 + 8) * a["calls"] / nprof          # one pass over dX (bf16) + time ids

@@ -343,7 +343,15 @@ def linear(module: torch.nn.Linear, x: Tensor) -> Tensor:
 def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
     """`seq(x)` with its nn.Linear members routed through `linear` (same modules, same parameters)."""
     for m in seq:
-        x = linear(m, x) if isinstance(m, torch.nn.Linear) else m(x)
+        if isinstance(m, torch.nn.Linear):
+            x = linear(m, x)
+        elif (isinstance(m, torch.nn.LayerNorm) and x.is_cuda and tuple(m.normalized_shape) == (128,) and m.elementwise_affine
+              and m.bias is not None and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+            # LayerNorm(128): the row kernel (fp32 statistics and fp32 output, as torch's layer_norm under autocast;
+            # its backward folds d_gamma / d_beta into the same pass)
+            x = layer_norm(x.reshape(-1, 128), m.weight, m.bias, m.eps, out_dtype=torch.float32).view(*x.shape)
+        else:
+            x = m(x)
     return x
 
 
