@@ -271,11 +271,30 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end-to-end run: host batches in, losses out, every step
-    def e2e_step(i):
-        if use_graph:        # H2D into the graph's static inputs, replay, read the losses back
-            g_ = graphs[i % pool]
+    copy_stream = torch.cuda.Stream() if use_graph else None
+    staged, replayed = {}, {}
+
+    def stage(i):            # H2D of step i's inputs into ITS graph's static buffers, on the copy stream
+        g_ = graphs[i % pool]
+        if i % pool in replayed:
+            copy_stream.wait_event(replayed[i % pool])            # that graph's previous replay has finished
+        with torch.cuda.stream(copy_stream):
             g_.load(host[i % pool])
-            t, m, c = g_.replay()
+            staged[i] = torch.cuda.Event()
+            staged[i].record(copy_stream)
+
+    def e2e_step(i):
+        if use_graph:
+            # every step: H2D of its inputs (pinned host -> the graph's static buffers), replay, D2H of the losses.
+            # The copy of step i+1 is issued before step i's result is read back, so it overlaps step i's compute
+            # (a prefetching loader); pool >= 2 graphs means it never writes buffers a running replay reads.
+            if i not in staged:
+                stage(i)
+            torch.cuda.current_stream().wait_event(staged.pop(i))
+            t, m, c = graphs[i % pool].replay()
+            replayed[i % pool] = torch.cuda.Event()
+            replayed[i % pool].record()
+            stage(i + 1)
         else:
             b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
             if sharded:      # the loader-stage products (made with collectives, they live on the device) ride along

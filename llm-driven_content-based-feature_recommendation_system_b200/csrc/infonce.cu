@@ -646,12 +646,17 @@ __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&r)[32], uint32_t
   tmem_st16(ptaddr, w);
 }
 
-// does any row of this warp carry a key_a inside the key range of chunk `ch` of the staged column tile?
-__device__ __forceinline__ bool ka_hits(uint32_t meta, int ch, uint32_t my_ka) {
+// Can any (row of this warp, column of chunk `ch`) pair have equal key_a?  Two range tests, both necessary for a match:
+// some row key inside the chunk's column-key range (decisive when the COLUMNS are sorted: forward, pass A), and some
+// column key inside the warp's row-key range [wlo, whi] (decisive when the ROWS are sorted: transposed pass B).
+__device__ __forceinline__ bool ka_hits(uint32_t meta, int ch, uint32_t my_ka, uint32_t wlo, uint32_t whi, int lane) {
   uint32_t lo, hi;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(meta + (uint32_t)offsetof(ColMeta, ka_lo) + ch * 4));
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(meta + (uint32_t)offsetof(ColMeta, ka_hi) + ch * 4));
-  return __any_sync(0xffffffffu, my_ka >= lo && my_ka <= hi);
+  if (!__any_sync(0xffffffffu, my_ka >= lo && my_ka <= hi)) return false;
+  uint32_t ck;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ck) : "r"(meta + (uint32_t)OFF_KA + (uint32_t)(ch * 32 + lane) * 4));
+  return __any_sync(0xffffffffu, ck >= wlo && ck <= whi);
 }
 
 // walk the four 32-column chunks of one accumulator; F(r, cbase) consumes one chunk.  (Three epilogue warps per
@@ -669,7 +674,7 @@ __device__ __forceinline__ void for_chunks(uint32_t tmem_tile, F&& f) {
 }
 
 __device__ __forceinline__ void load_row_keys(const CeParams& p, int64_t row, bool row_ok, bool supcon, RowCtx& rc,
-                                              uint32_t& wkb_lo, uint32_t& wkb_hi) {
+                                              uint32_t& wkb_lo, uint32_t& wkb_hi, uint32_t& wka_lo, uint32_t& wka_hi) {
   rc.my_ka = 0xFFFFFFFFu;
   rc.my_kb = 0xFFFFFFFFu;
   if (row_ok) {
@@ -680,6 +685,8 @@ __device__ __forceinline__ void load_row_keys(const CeParams& p, int64_t row, bo
   // key_b range of this WARP's 32 rows (rows without a key never match: keep them out of the range)
   wkb_lo = __reduce_min_sync(0xffffffffu, rc.my_kb);
   wkb_hi = __reduce_max_sync(0xffffffffu, rc.my_kb == 0xFFFFFFFFu ? 0u : rc.my_kb);
+  wka_lo = __reduce_min_sync(0xffffffffu, rc.my_ka);
+  wka_hi = __reduce_max_sync(0xffffffffu, rc.my_ka == 0xFFFFFFFFu ? 0u : rc.my_ka);
 }
 
 __device__ __forceinline__ bool kb_overlaps(const ColMeta& cm, uint32_t wkb_lo, uint32_t wkb_hi) {
@@ -736,8 +743,8 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int64_t row = (int64_t)rb * CE_BM + rloc;
       const bool row_ok = row < p.M;
       RowCtx rc;
-      uint32_t wkb_lo, wkb_hi;
-      load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi);
+      uint32_t wkb_lo, wkb_hi, wka_lo, wka_hi;
+      load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi, wka_lo, wka_hi);
       rc.nrowbias2 = 0.f;
       rc.jd = row + p.diag_offset;
       rc.c_off = c_off; rc.mask2c = p.mask2 - c_off;
@@ -767,7 +774,7 @@ ce_fwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
           else if (MODE == MODE_SUPCON) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
           else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) {
-            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka)) fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row);
+            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka, wka_lo, wka_hi, lane)) fwd_chunk<MODE, false, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row);
             else fwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, CE_FWD_NPOLY>(r, meta, cb, rc, p, -top);
           });
         } else {
@@ -905,8 +912,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int64_t row = (int64_t)rb * CE_BM + rloc;
       const bool row_ok = row < p.M;
       RowCtx rc;
-      uint32_t wkb_lo, wkb_hi;
-      load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi);
+      uint32_t wkb_lo, wkb_hi, wka_lo, wka_hi;
+      load_row_keys(p, row, row_ok, MODE == MODE_SUPCON, rc, wkb_lo, wkb_hi, wka_lo, wka_hi);
       rc.nrowbias2 = 0.f; rc.lse2 = 0.f; rc.wlc = 0.f; rc.wdc = 0.f; rc.wpc = 0.f;
       rc.c_off = 0.f; rc.mask2c = p.mask2; rc.nl = -INFINITY; rc.eb = 0.f;
       if (row_ok) {
@@ -946,7 +953,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (!edge && fold) {
           if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { bwd_chunk_fold<MODE, true, TRANSPOSED>(r, meta, cb, rc, p, tt + (cb >> 1), bf16); });
           else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) {
-            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka)) bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, tt + (cb >> 1), bf16);
+            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka, wka_lo, wka_hi, lane)) bwd_chunk_fold<MODE, false, TRANSPOSED>(r, meta, cb, rc, p, tt + (cb >> 1), bf16);
             else if (bf16) bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, true>(r, meta, cb, rc, p, tt + (cb >> 1));
             else bwd_chunk_fast<MODE == MODE_SUPCON ? MODE_GENERAL : MODE, TRANSPOSED, CE_BWD_NPOLY, false>(r, meta, cb, rc, p, tt + (cb >> 1));
           });
