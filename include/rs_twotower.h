@@ -230,6 +230,13 @@ int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bi
 /* Advance the device-side dropout epoch that every kernel above mixes into its (by-value) seed.  Stream-ordered: call
  * it once at the start of a train step.  Inside a captured CUDA graph it is what makes every REPLAY draw new masks. */
 int rs_rng_advance(void* stream);
+/* y = x / max(||x||_2, eps) per 128-wide row == F.normalize(x, p=2, dim=-1) (v1_refine_usertower.py:510, the loop's
+ * v1_usertower_train.py:807); inv_norm[n_rows] is saved for the backward (negative where the clamp was active).
+ * bwd: dx = (g - y <g, y>) * inv_norm; y must be the fp32 output of the forward. */
+int rs_l2_normalize_fwd(const void* x, int x_dtype, int64_t n_rows, int64_t dim, float eps, void* y, int y_dtype,
+                        float* inv_norm, void* stream);
+int rs_l2_normalize_bwd(const void* g, int g_dtype, const void* y, int y_dtype, const float* inv_norm, int64_t n_rows,
+                        int64_t dim, void* dx, int dx_dtype, void* stream);
 /* out[c] = sum_r x[r, c], fp32, fixed summation order (n_cols % 4 == 0, <= 1024) */
 size_t rs_colsum_workspace_bytes(int64_t n_rows, int64_t n_cols);
 int rs_colsum(const void* x, int dtype, int64_t n_rows, int64_t n_cols, float* out, void* workspace,

@@ -690,6 +690,42 @@ static inline void drop_consts(float p, uint32_t& thresh, float& inv_keep) {
   inv_keep = 1.f / (1.f - p);
 }
 
+// ------------------------------------------------------------------------------------------------ L2 normalise (128)
+// y = x / max(||x||_2, eps)  (F.normalize(p=2, dim=-1), v1_refine_usertower.py:510 and the loop's :807): one warp per
+// row, one pass.  inv[r] = 1 / max(||x||, eps), NEGATED when the clamp was active (the backward then has no projection).
+template <int DTI, int DTO>
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const void* __restrict__ x, int64_t n_rows, float eps,
+                                                         void* __restrict__ y, float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const float4 v = ld4<DTI>(x, r * ENC_D + 4 * lane);
+    const float nrm = sqrtf(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w));
+    const float iv = 1.f / fmaxf(nrm, eps);
+    st4<DTO>(y, r * ENC_D + 4 * lane, make_float4(v.x * iv, v.y * iv, v.z * iv, v.w * iv));
+    if (lane == 0) inv[r] = nrm > eps ? iv : -iv;
+  }
+}
+// dx = (g - y <g, y>) * inv   (clamped rows: dx = g * |inv|)
+template <int DTG, int DTY, int DTX>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const void* __restrict__ g, const void* __restrict__ y,
+                                                         const float* __restrict__ inv, int64_t n_rows,
+                                                         void* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const float4 gv = ld4<DTG>(g, r * ENC_D + 4 * lane), yv = ld4<DTY>(y, r * ENC_D + 4 * lane);
+    const float iv = __ldg(inv + r);
+    float d = warp_sum(gv.x * yv.x + gv.y * yv.y + gv.z * yv.z + gv.w * yv.w);
+    if (iv < 0.f) d = 0.f;
+    const float a = fabsf(iv);
+    st4<DTX>(dx, r * ENC_D + 4 * lane,
+             make_float4((gv.x - yv.x * d) * a, (gv.y - yv.y * d) * a, (gv.z - yv.z * d) * a, (gv.w - yv.w * d) * a));
+  }
+}
+
 }  // namespace rs
 
 using namespace rs;
@@ -826,6 +862,33 @@ extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtyp
       dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, part))));
   RS_LAUNCH_CHECK();
   partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_l2_normalize_fwd(const void* x, int x_dtype, int64_t n_rows, int64_t dim, float eps, void* y,
+                                   int y_dtype, float* inv_norm, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!x || !y || !inv_norm || n_rows < 0) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(y_dtype, DTO, (l2norm_fwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
+      x, n_rows, eps, y, inv_norm))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_l2_normalize_bwd(const void* g, int g_dtype, const void* y, int y_dtype, const float* inv_norm,
+                                   int64_t n_rows, int64_t dim, void* dx, int dx_dtype, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!g || !y || !inv_norm || !dx || n_rows < 0) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (y_dtype != RS_F32) return RS_ERR_UNSUPPORTED;          // the normalised rows are kept in fp32 (as under autocast)
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  ENC_DISPATCH1(g_dtype, DTG, ENC_DISPATCH1(dx_dtype, DTX, (l2norm_bwd_kernel<DTG, RS_F32, DTX><<<grid, 256, 0, st>>>(
+      g, y, inv_norm, n_rows, dx))));
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

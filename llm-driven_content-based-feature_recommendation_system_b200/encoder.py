@@ -306,6 +306,60 @@ def _act_dtype(x: Tensor) -> torch.dtype:
     return x.dtype
 
 
+@torch.library.custom_op("rs::l2_normalize", mutates_args=())
+def l2_normalize_op(x: Tensor, eps: float) -> List[Tensor]:
+    """[y fp32, inv_norm] for 128-wide rows."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    n = x.numel() // 128
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    inv = torch.empty(n, dtype=torch.float32, device=x.device)
+    L.check(_lib.rs_l2_normalize_fwd(L.ptr(x), L.dt(x), n, 128, eps, L.ptr(y), L.RS_F32, L.ptr(inv), L.stream()),
+            "rs_l2_normalize_fwd")
+    return [y, inv]
+
+
+@l2_normalize_op.register_fake
+def _(x, eps):
+    return [x.new_empty(x.shape, dtype=torch.float32), x.new_empty(x.numel() // 128, dtype=torch.float32)]
+
+
+@torch.library.custom_op("rs::l2_normalize_bwd", mutates_args=())
+def l2_normalize_bwd_op(g: Tensor, y: Tensor, inv: Tensor, dx_dtype: int) -> Tensor:
+    g = g.contiguous()
+    dx = torch.empty(y.shape, dtype=L.torch_dtype(dx_dtype), device=y.device)
+    L.check(_lib.rs_l2_normalize_bwd(L.ptr(g), L.dt(g), L.ptr(y), L.RS_F32, L.ptr(inv), inv.numel(), 128, L.ptr(dx),
+                                     dx_dtype, L.stream()), "rs_l2_normalize_bwd")
+    return dx
+
+
+@l2_normalize_bwd_op.register_fake
+def _(g, y, inv, dx_dtype):
+    return y.new_empty(y.shape, dtype=L.torch_dtype(dx_dtype))
+
+
+class _L2Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        y, inv = torch.ops.rs.l2_normalize(x, eps)
+        ctx.save_for_backward(y, inv)
+        ctx.xdt = L.dt(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, inv = ctx.saved_tensors
+        return torch.ops.rs.l2_normalize_bwd(g, y, inv, ctx.xdt), None
+
+
+def l2_normalize(x: Tensor, eps: float = 1e-12) -> Tensor:
+    """F.normalize(x, p=2, dim=-1) for 128-wide CUDA rows in one pass each way (fp32 output, as under autocast where
+    the norm runs in fp32); anything else goes to F.normalize."""
+    if not x.is_cuda or x.shape[-1] != 128 or x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        return F.normalize(x, p=2, dim=-1, eps=eps)
+    return _L2Normalize.apply(x, float(eps))
+
+
 class _LinearColsumBias(torch.autograd.Function):
     """y = x W^T + b as nn.Linear computes it (one library GEMM with the bias in its epilogue; under autocast in the
     autocast dtype); the only difference is the bias gradient: rs::colsum of the incoming gradient (fixed order, one

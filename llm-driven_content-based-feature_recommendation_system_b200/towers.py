@@ -204,7 +204,7 @@ class SASRecUserTower(nn.Module):
             output = ops.gather_rows(output, select_index)
         prof = ops.gather_rows(user_profile_vec, users)
         final_vec = enc.sequential(self.output_proj, torch.cat([output, prof.to(output.dtype)], dim=-1))
-        return F.normalize(final_vec, p=2, dim=-1)
+        return enc.l2_normalize(final_vec)
 
 
 class SASRecItemTower(nn.Module):

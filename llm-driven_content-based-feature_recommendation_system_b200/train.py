@@ -168,7 +168,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
         # view 1 feeds the main loss (valid steps) and DuoRec (last step); view 2 only DuoRec: the late-fusion
         # head runs on exactly those rows (same values as slicing the full [B,L,128] output)
         out1, out2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
-        u = F.normalize(out1[:n_main], p=2, dim=1)                                   # :794-807
+        u = encoder.l2_normalize(out1[:n_main])                                      # :794-807
         tgt = tgt_flat[idx]
         uid = idx // L                                                               # batch row = user id (:801-804)
         if columns == "batch" or (columns == "unique" and ("col_item_ids" not in batch or loss_scope != "all")):
@@ -320,7 +320,7 @@ class ShardedTwoTower:
             idx, li = batch["valid_index"], batch["last_index"]
             n_main = idx.numel()
             out1, out2 = _two_views(model, batch, pretrained_vecs, kw, "all", packed, item_id_rows=id_rows)
-            u = F.normalize(out1[:n_main], p=2, dim=1)
+            u = encoder.l2_normalize(out1[:n_main])
             tgt = tgt_flat[idx]
             uid = idx // L
             # main loss: all items as columns, global multiplicities

@@ -330,3 +330,26 @@ def test_attn_tensor_core_path_matches_simt_path(rs, dtype):
         assert (d16[-2:] == 0).all()
         err = (d16.float() - d32).abs().max().item()
         assert err <= 3e-2 * d32.abs().max().item() + 1e-3, (p, err, d32.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_l2_normalize_vs_torch(rs, dtype):
+    """rs::l2_normalize == F.normalize(x.float(), p=2, dim=-1) forward and backward, zero rows included (clamp active:
+    output 0, gradient g / eps)."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1001, 128, generator=g).to(dtype)
+    x[17] = 0
+    w = torch.randn(1001, 128, generator=g)
+    a = x.float().to(DEV).requires_grad_(True)
+    want = F.normalize(a, p=2, dim=-1)
+    (want * w.to(DEV)).sum().backward()
+    b = x.to(DEV).requires_grad_(True)
+    got = rs.encoder.l2_normalize(b)
+    assert got.dtype == torch.float32
+    (got * w.to(DEV)).sum().backward()
+    torch.testing.assert_close(got, want.detach(), rtol=1e-6, atol=1e-6)
+    assert (got[17] == 0).all()
+    rows = torch.arange(1001) != 17
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(b.grad.float()[rows], a.grad[rows], **tol)
+    assert torch.isfinite(b.grad.float()).all()
