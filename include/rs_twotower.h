@@ -213,7 +213,9 @@ int rs_ln_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, 
 size_t rs_ln_bwd_workspace_bytes(int64_t n_rows);
 int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const int64_t* index, int64_t n_rows,
               int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p, uint64_t seed,
-              void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+              void* dx, const float* residual_grad /* nullable [n_rows,128] fp32, added to dx: the gradient that
+              reaches the LayerNorm's input through the residual connection around it */,
+              float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 /* The biases of the four Linear layers of an encoder layer are folded into the kernel that consumes the GEMM output
  * (`bias` fp32 [n_cols] or NULL), so the GEMMs are plain matmuls and the bias gradients are column sums of tensors
  * these kernels produce (rs_colsum) instead of separate reductions behind each GEMM.

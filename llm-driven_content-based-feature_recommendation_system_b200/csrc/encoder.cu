@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      const float* __restrict__ w, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, uint32_t drop_thresh,
                                                      float inv_keep, uint64_t seed, void* __restrict__ dx,
+                                                     const float* __restrict__ res /*nullable: added to dx*/,
                                                      float* __restrict__ part /*[grid][2][128]*/) {
   __shared__ float4 red[2][8][32];
   seed = epoch_seed(seed);
@@ -550,9 +551,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
     const float4 gw = make_float4(g.x * w4.x, g.y * w4.y, g.z * w4.z, g.w * w4.w);
     const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
     const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
-    st4<DTI>(dx, r * ENC_D + 4 * lane,
-             make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
-                         rs * (gw.w - m1 - xh.w * m2)));
+    float4 o = make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
+                           rs * (gw.w - m1 - xh.w * m2));
+    if (res) {                                      // the gradient arriving through the residual connection around the LN
+      const float4 rg = ldg_f4(res + r * ENC_D + 4 * lane);
+      o.x += rg.x; o.y += rg.y; o.z += rg.z; o.w += rg.w;
+    }
+    st4<DTI>(dx, r * ENC_D + 4 * lane, o);
   }
   red[0][wib][lane] = dw;
   red[1][wib][lane] = db;
@@ -847,8 +852,8 @@ extern "C" int rs_ln_fwd(const void* x, int x_dtype, const int64_t* index, int64
 
 extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const int64_t* index, int64_t n_rows,
                          int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p,
-                         uint64_t seed, void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+                         uint64_t seed, void* dx, const float* residual_grad, float* dw, float* db, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   if (n_rows == 0) return RS_OK;
   if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || !workspace) return RS_ERR_BAD_ARG;
   if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
@@ -859,7 +864,7 @@ extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtyp
   const int grid = ln_grid(n_rows);
   float* part = (float*)workspace;
   ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dy_dtype, DTO, (ln_bwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
-      dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, part))));
+      dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, residual_grad, part))));
   RS_LAUNCH_CHECK();
   partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
   RS_LAUNCH_CHECK();

@@ -133,21 +133,24 @@ def _(x, index, w, b, eps, dropout_p, seed, out_dtype):
 
 @torch.library.custom_op("rs::ln_bwd", mutates_args=())
 def ln_bwd_op(dy: Tensor, x: Tensor, index: Optional[Tensor], w: Tensor, mean: Tensor, rstd: Tensor, dropout_p: float,
-              seed: int) -> List[Tensor]:
+              seed: int, res: Optional[Tensor] = None) -> List[Tensor]:
+    """`res` (fp32, shaped like the packed dx): gradient reaching the LN input through the residual path, added in."""
     dy = dy.contiguous()
+    if res is not None:
+        res = res.float().contiguous()
     n = dy.shape[0]
     dx = torch.empty(n, x.shape[1], dtype=x.dtype, device=x.device)       # packed like dy
     dw = torch.empty_like(w)
     db = torch.empty_like(w)
     ws = L.workspace(_lib.rs_ln_bwd_workspace_bytes(n), x.device)
     L.check(_lib.rs_ln_bwd(L.ptr(dy), L.dt(dy), L.ptr(x), L.dt(x), L.ptr(index), n, x.shape[1], L.ptr(w), L.ptr(mean),
-                           L.ptr(rstd), dropout_p, seed, L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(),
+                           L.ptr(rstd), dropout_p, seed, L.ptr(dx), L.ptr(res), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(),
                            L.stream()), "rs_ln_bwd")
     return [dx, dw, db]
 
 
 @ln_bwd_op.register_fake
-def _(dy, x, index, w, mean, rstd, dropout_p, seed):
+def _(dy, x, index, w, mean, rstd, dropout_p, seed, res=None):
     return [x.new_empty(dy.shape[0], x.shape[1]), torch.empty_like(w), torch.empty_like(w)]
 
 
@@ -240,26 +243,68 @@ def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dro
 
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, index, w, b, eps, dropout_p, seed, out_dtype):
+    def forward(ctx, x, index, w, b, eps, dropout_p, seed, out_dtype, fold=None):
         y, mean, rstd = torch.ops.rs.ln(x, index, w, b, eps, dropout_p, seed, out_dtype)
         ctx.save_for_backward(x, index, w, mean, rstd)
         ctx.meta = (dropout_p, seed)
+        ctx.fold = fold
         return y
 
     @staticmethod
     def backward(ctx, g):
         x, index, w, mean, rstd = ctx.saved_tensors
         dx, dw, db = torch.ops.rs.ln_bwd(g, x, index, w, mean, rstd, *ctx.meta)
-        if index is not None:          # an index may repeat rows (one copy per dropout view): scatter-ADD
+        if index is not None and ctx.fold is not None:
+            # index == [0..T) twice, then [T..T+E) twice (two dropout views of the same packed rows): the scatter-add
+            # is two elementwise sums (deterministic, no atomics)
+            T, E = ctx.fold
+            full = torch.empty_like(x)
+            torch.add(dx[:T], dx[T:2 * T], out=full[:T])
+            if E:
+                torch.add(dx[2 * T:2 * T + E], dx[2 * T + E:2 * T + 2 * E], out=full[T:T + E])
+            full[T + E:].zero_()
+            dx = full
+        elif index is not None:        # an index may repeat rows (one copy per dropout view): scatter-ADD
             dx = torch.zeros_like(x).index_add_(0, index, dx)
-        return dx, None, dw, db, None, None, None, None
+        return dx, None, dw, db, None, None, None, None, None
 
 
 def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, index: Optional[Tensor] = None,
-               dropout_p: float = 0.0, out_dtype: Optional[torch.dtype] = None) -> Tensor:
-    """dropout(LayerNorm(x[index])) for 128-wide rows; `index` (int64) packs rows on the way in."""
+               dropout_p: float = 0.0, out_dtype: Optional[torch.dtype] = None, index_fold=None) -> Tensor:
+    """dropout(LayerNorm(x[index])) for 128-wide rows; `index` (int64) packs rows on the way in.  `index_fold` = (T, E):
+    the caller vouches that index == cat(arange(T), arange(T), T + arange(E), T + arange(E)) (train.add_host_index's
+    two-view layout), which turns the backward's scatter-add into two elementwise sums."""
     od = L.dt(out_dtype) if out_dtype is not None else L.dt(x)
-    return _LayerNorm.apply(x, index, weight, bias, float(eps), float(dropout_p), _seed() if dropout_p > 0 else 0, od)
+    if index_fold is not None:
+        T, E = index_fold
+        assert index is not None and index.numel() == 2 * (T + E) and x.shape[0] >= T + E
+    return _LayerNorm.apply(x, index, weight, bias, float(eps), float(dropout_p), _seed() if dropout_p > 0 else 0, od,
+                            index_fold)
+
+
+class _ResidualLN(torch.autograd.Function):
+    """(x, LN(x)) for a pre-norm residual block: x is handed through so that the gradient arriving on the residual path
+    and the gradient of the LN branch meet in ONE backward kernel (ln_bwd adds the former to its dx) instead of an
+    autograd accumulation pass over the [T, 128] fp32 stream."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, out_dtype):
+        y, mean, rstd = torch.ops.rs.ln(x, None, w, b, eps, 0.0, 0, out_dtype)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, gx, gy):
+        x, w, mean, rstd = ctx.saved_tensors
+        if gy is None:
+            return gx, None, None, None, None
+        dx, dw, db = torch.ops.rs.ln_bwd(gy, x, None, w, mean, rstd, 0.0, 0, gx)
+        return dx, dw, db, None, None
+
+
+def residual_layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, out_dtype: torch.dtype):
+    """returns (x, LayerNorm(x)); use the returned x for the residual add (see _ResidualLN)."""
+    return _ResidualLN.apply(x, weight, bias, float(eps), L.dt(out_dtype))
 
 
 class _DropoutAdd(torch.autograd.Function):
@@ -416,14 +461,14 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     tr = layer.training
     attn = layer.self_attn
     ad = _act_dtype(x)
-    h = layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, out_dtype=ad)
+    x, h = residual_layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ad)
     # the four biases are folded into the kernels that consume the GEMM outputs: plain matmuls, and the bias
     # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
     qkv = F.linear(h, attn.in_proj_weight)
     o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail,
                     bias=attn.in_proj_bias)
     x = dropout_add(x, F.linear(o, attn.out_proj.weight), layer.dropout1.p if tr else 0.0, bias=attn.out_proj.bias)
-    h = layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, out_dtype=ad)
+    x, h = residual_layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, ad)
     f = gelu_dropout(F.linear(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
     return dropout_add(x, F.linear(f, layer.linear2.weight), layer.dropout2.p if tr else 0.0, bias=layer.linear2.bias)
 

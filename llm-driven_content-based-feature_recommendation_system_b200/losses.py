@@ -195,8 +195,9 @@ def duorec_loss_refined(user_emb_1: Tensor, user_emb_2: Tensor, target_ids: Tens
     """tower_code/v1_refine_usertower.py:576-627: InfoNCE(z1, z2) + lambda_sup * SupCon(z1; same target).
     No host synchronisation: the reference's `if mask.sum() > 0` / `valid_rows.sum() > 0` tests (:608,:623)
     become arithmetic on device scalars."""
-    z1 = F.normalize(user_emb_1, dim=1)
-    z2 = F.normalize(user_emb_2, dim=1)
+    from . import encoder                      # (late: encoder imports ops, which this module shares)
+    z1 = encoder.l2_normalize(user_emb_1)
+    z2 = encoder.l2_normalize(user_emb_2)
     loss = info_nce(z1, z2, temperature, unit_norm=True)
     if lambda_sup > 0:
         lse, _, pos_sum, pos_cnt = fused_softmax_stats(z1, z1, 1.0 / temperature, key_a_row=target_ids,

@@ -121,7 +121,8 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
         cu2 = batch["cu_seqlens_2v"]
         pk = {}
         if "pk_item_ids" in batch:
-            pk = dict(packed_index=batch["pk_index_2v"],
+            T_ = batch["valid_index"].numel()
+            pk = dict(packed_index=batch["pk_index_2v"], packed_fold=(T_, (batch["pk_index_2v"].numel() - 2 * T_) // 2),
                       packed_inputs=dict(item_ids=batch["pk_item_ids"], time_bucket_ids=batch["pk_time_ids"],
                                          pos_ids=batch["pk_pos_ids"]))
         else:
@@ -329,7 +330,7 @@ class ShardedTwoTower:
             if "col_plan" in batch:
                 # columns = the distinct targets of the whole box: fetch their rows from the owners (all-to-all), normalise
                 rows = sh.planned_lookup(item_tower.item_matrix.weight, batch["col_plan"], self.group)
-                v_cols = F.normalize(rows, p=2, dim=1)
+                v_cols = encoder.l2_normalize(rows)
                 cid, cnt, pos_col = batch["col_item_ids"], batch["col_counts"], batch["pos_col"]
             else:
                 # columns = every item: all-gather the normalised shards (reduce-scatter backward), static shapes
@@ -362,7 +363,7 @@ class ShardedTwoTower:
         B rows (the caller divides by world: equal B on all ranks)."""
         sh, rank = self.sh, self.rank
         B = e1.shape[0]
-        z1, z2 = F.normalize(e1, dim=1), F.normalize(e2, dim=1)
+        z1, z2 = encoder.l2_normalize(e1), encoder.l2_normalize(e2)
         z2_all = sh.all_gather_rows(z2, self.group)
         loss = losses.info_nce(z1, z2_all, temperature, diag_offset=rank * B, unit_norm=True)
         if lambda_sup > 0:
