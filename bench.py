@@ -187,7 +187,8 @@ def run_ours(args):
     sharded = world > 1 and args.parallelism == "sharded"
     trainer = rs.train.ShardedTwoTower(model, item) if sharded else None      # re-shards the two item tables in place
     params = list(model.parameters()) + list(item.parameters())
-    use_graph = bool(args.cuda_graph) and world == 1      # N > 1: eager (capturing the NCCL exchanges hung in a 2-GPU trial)
+    use_graph = bool(args.cuda_graph) and world == 1      # N > 1: eager (two 2-GPU trials with the NCCL exchanges captured hung;
+                                                          # tools/nccl_graph_probe.py: plain collectives do capture and replay)
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
 
     def sync_grads():
@@ -303,7 +304,7 @@ def run_ours(args):
         last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
 
     if args.minimal:
-        print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)))
+        print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)), flush=True)
         return
     for i in range(max(args.warmup, 3 * pool)):      # every pooled batch (each has its own shapes) seen 3x: allocator warm
         e2e_step(i)
@@ -390,7 +391,7 @@ def run_ours(args):
                                 l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
                     e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
                     kernels=kernels, loss=dict(total=total, main=main, cl=cl))
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
