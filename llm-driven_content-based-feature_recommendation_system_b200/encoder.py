@@ -218,7 +218,7 @@ def _(z, bias, g, dropout_p, seed):
 class _AttnVarlen(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
-        out, lse = torch.ops.rs.attn_varlen(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed)
+        out, lse = L.direct.attn_varlen(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed)
         ctx.save_for_backward(qkv, bias, out, lse, cu_seqlens)
         ctx.meta = (n_heads, max_len, zero_tail, scale, dropout_p, seed)
         return out
@@ -226,7 +226,7 @@ class _AttnVarlen(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         qkv, bias, out, lse, cu = ctx.saved_tensors
-        d_qkv, d_bias = torch.ops.rs.attn_varlen_bwd(qkv, bias, g, out, lse, cu, *ctx.meta)
+        d_qkv, d_bias = L.direct.attn_varlen_bwd(qkv, bias, g, out, lse, cu, *ctx.meta)
         return (d_qkv, d_bias if bias is not None else None) + (None,) * 7
 
 
@@ -244,7 +244,7 @@ def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dro
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, index, w, b, eps, dropout_p, seed, out_dtype, fold=None):
-        y, mean, rstd = torch.ops.rs.ln(x, index, w, b, eps, dropout_p, seed, out_dtype)
+        y, mean, rstd = L.direct.ln(x, index, w, b, eps, dropout_p, seed, out_dtype)
         ctx.save_for_backward(x, index, w, mean, rstd)
         ctx.meta = (dropout_p, seed)
         ctx.fold = fold
@@ -253,7 +253,7 @@ class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, index, w, mean, rstd = ctx.saved_tensors
-        dx, dw, db = torch.ops.rs.ln_bwd(g, x, index, w, mean, rstd, *ctx.meta)
+        dx, dw, db = L.direct.ln_bwd(g, x, index, w, mean, rstd, *ctx.meta)
         if index is not None and ctx.fold is not None:
             # index == [0..T) twice, then [T..T+E) twice (two dropout views of the same packed rows): the scatter-add
             # is two elementwise sums (deterministic, no atomics)
@@ -289,7 +289,7 @@ class _ResidualLN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, eps, out_dtype):
-        y, mean, rstd = torch.ops.rs.ln(x, None, w, b, eps, 0.0, 0, out_dtype)
+        y, mean, rstd = L.direct.ln(x, None, w, b, eps, 0.0, 0, out_dtype)
         ctx.save_for_backward(x, w, mean, rstd)
         return x.view_as(x), y
 
@@ -298,7 +298,7 @@ class _ResidualLN(torch.autograd.Function):
         x, w, mean, rstd = ctx.saved_tensors
         if gy is None:
             return gx, None, None, None, None
-        dx, dw, db = torch.ops.rs.ln_bwd(gy, x, None, w, mean, rstd, 0.0, 0, gx)
+        dx, dw, db = L.direct.ln_bwd(gy, x, None, w, mean, rstd, 0.0, 0, gx)
         return dx, dw, db, None, None
 
 
@@ -311,12 +311,12 @@ class _DropoutAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, bias, dropout_p, seed):
         ctx.meta = (dropout_p, seed, L.dt(y), bias is not None)
-        return torch.ops.rs.dropout_add(x, y, bias, dropout_p, seed)
+        return L.direct.dropout_add(x, y, bias, dropout_p, seed)
 
     @staticmethod
     def backward(ctx, g):
         p, seed, ydt, has_bias = ctx.meta
-        dy, db = torch.ops.rs.dropout_bwd(g, p, seed, ydt, has_bias)
+        dy, db = L.direct.dropout_bwd(g, p, seed, ydt, has_bias)
         return g, dy, (db if has_bias else None), None, None
 
 
@@ -330,12 +330,12 @@ class _GeluDropout(torch.autograd.Function):
     def forward(ctx, z, bias, dropout_p, seed):
         ctx.save_for_backward(z, bias)
         ctx.meta = (dropout_p, seed)
-        return torch.ops.rs.gelu_dropout(z, bias, dropout_p, seed)
+        return L.direct.gelu_dropout(z, bias, dropout_p, seed)
 
     @staticmethod
     def backward(ctx, g):
         z, bias = ctx.saved_tensors
-        dz, db = torch.ops.rs.gelu_dropout_bwd(z, bias, g, *ctx.meta)
+        dz, db = L.direct.gelu_dropout_bwd(z, bias, g, *ctx.meta)
         return dz, (db if bias is not None else None), None, None
 
 
@@ -386,7 +386,7 @@ def _(g, y, inv, dx_dtype):
 class _L2Normalize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eps):
-        y, inv = torch.ops.rs.l2_normalize(x, eps)
+        y, inv = L.direct.l2_normalize(x, eps)
         ctx.save_for_backward(y, inv)
         ctx.xdt = L.dt(x)
         return y
@@ -394,7 +394,7 @@ class _L2Normalize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         y, inv = ctx.saved_tensors
-        return torch.ops.rs.l2_normalize_bwd(g, y, inv, ctx.xdt), None
+        return L.direct.l2_normalize_bwd(g, y, inv, ctx.xdt), None
 
 
 def l2_normalize(x: Tensor, eps: float = 1e-12) -> Tensor:

@@ -50,7 +50,7 @@ class _FusedSoftmax(torch.autograd.Function):
     def forward(ctx, a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value,
                 flags, dtype, logit_bound):
         a16, b16 = a.detach().to(dtype).contiguous(), b.detach().to(dtype).contiguous()
-        lse, diag, pos_sum, pos_cnt = torch.ops.rs.ce_fwd(a16, b16, scale, col_bias, key_a_row, key_a_col, key_b_row,
+        lse, diag, pos_sum, pos_cnt = L.direct.ce_fwd(a16, b16, scale, col_bias, key_a_row, key_a_col, key_b_row,
                                                           key_b_col, diag_offset, mask_value, flags, logit_bound)
         ctx.save_for_backward(a16, b16, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, lse)
         ctx.meta = (scale, diag_offset, mask_value, flags, a.dtype, b.dtype, logit_bound)
@@ -68,7 +68,7 @@ class _FusedSoftmax(torch.autograd.Function):
             g_lse = zeros
         w_pos = g_pos.float().contiguous() if (g_pos is not None and flags & L.RS_CE_SUPCON) else None
         w_diag = None if g_diag is None else g_diag.float().contiguous()
-        dA, dB = torch.ops.rs.ce_bwd(a16, b16, scale, col_bias, kar, kac, kbr, kbc, diag_offset, mask_value, flags,
+        dA, dB = L.direct.ce_bwd(a16, b16, scale, col_bias, kar, kac, kbr, kbc, diag_offset, mask_value, flags,
                                      lse, g_lse.float().contiguous(), w_diag, w_pos, logit_bound)
         return (dA.to(adt), dB.to(bdt)) + (None,) * 11
 
@@ -304,7 +304,7 @@ def inbatch_mixed_hnm_loss_with_stats(user_emb, item_tower_emb, target_ids, log_
     cols = torch.cat([torch.arange(n, device=idx.device).unsqueeze(1), idx, random_indices], dim=1)
     logits = ops.sparse_logits(u16, v16, cols, scale, bias)
     with torch.no_grad():      # ignore mask of the random picks: same item, or item-item cosine above the threshold
-        vv = torch.ops.rs.sparse_logits(v.detach().float(), v.detach().float(), random_indices, 1.0, None, None, None)
+        vv = L.direct.sparse_logits(v.detach().float(), v.detach().float(), random_indices, 1.0, None, None, None)
         rows = torch.arange(n, device=idx.device).unsqueeze(1)
         ign = (target_ids[random_indices] == target_ids.unsqueeze(1)) | ((vv > hnm_threshold) & (random_indices != rows))
     rnd = logits[:, 1 + k:].masked_fill(ign, -1e9)

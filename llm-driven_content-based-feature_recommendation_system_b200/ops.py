@@ -578,13 +578,13 @@ class _GatherRows(torch.autograd.Function):
     def forward(ctx, table, ids, padding_idx, clamp_max, out_dtype):
         ctx.save_for_backward(ids)
         ctx.meta = (table.shape[0], padding_idx, clamp_max, table.dtype)
-        return torch.ops.rs.gather_rows(table, ids, clamp_max, out_dtype)
+        return L.direct.gather_rows(table, ids, clamp_max, out_dtype)
 
     @staticmethod
     def backward(ctx, g):
         (ids,) = ctx.saved_tensors
         rows, padding_idx, clamp_max, tdt = ctx.meta
-        d = torch.ops.rs.embedding_dense_bwd(g, ids, rows, padding_idx, clamp_max, DETERMINISTIC)
+        d = L.direct.embedding_dense_bwd(g, ids, rows, padding_idx, clamp_max, DETERMINISTIC)
         return d.to(tdt), None, None, None, None
 
 
@@ -603,7 +603,7 @@ class _SeqFront(torch.autograd.Function):
         n = len(rest) // 2
         ids, tables = list(rest[:n]), list(rest[n:])
         L_ = ids[0].shape[-1]
-        out = torch.ops.rs.seq_front(base, ids[:n_live], tables[:n_live], gates[:n_live].contiguous(), pos_table, L_,
+        out = L.direct.seq_front(base, ids[:n_live], tables[:n_live], gates[:n_live].contiguous(), pos_table, L_,
                                      out_dtype)
         ctx.save_for_backward(gates, *ids[:n_live], *tables)
         ctx.meta = (n, n_live, L_, padding_idx, None if base is None else base.dtype, pos_table is not None)
@@ -615,7 +615,7 @@ class _SeqFront(torch.autograd.Function):
         gates = ctx.saved_tensors[0]
         ids = list(ctx.saved_tensors[1:1 + n_live])
         tables = list(ctx.saved_tensors[1 + n_live:])
-        res = torch.ops.rs.seq_front_bwd(dx, ids, tables[:n_live], gates[:n_live].contiguous(), L_, padding_idx,
+        res = L.direct.seq_front_bwd(dx, ids, tables[:n_live], gates[:n_live].contiguous(), L_, padding_idx,
                                          DETERMINISTIC)
         d_tables = list(res[:n_live]) + [torch.zeros_like(t) for t in tables[n_live:]]
         d_gates = torch.zeros_like(gates)
@@ -638,13 +638,13 @@ class _StaticFront(torch.autograd.Function):
         ids, tables = list(rest[:9]), list(rest[9:])
         ctx.save_for_backward(cont, cont_w, cont_b, gates, *ids, *tables)
         ctx.padding_idx = padding_idx
-        return torch.ops.rs.static_front(ids, tables, cont, cont_w, cont_b, gates)
+        return L.direct.static_front(ids, tables, cont, cont_w, cont_b, gates)
 
     @staticmethod
     def backward(ctx, g):
         cont, cont_w, cont_b, gates = ctx.saved_tensors[:4]
         ids, tables = list(ctx.saved_tensors[4:13]), list(ctx.saved_tensors[13:])
-        res = torch.ops.rs.static_front_bwd(g.float().contiguous(), ids, tables, cont, cont_w, cont_b, gates,
+        res = L.direct.static_front_bwd(g.float().contiguous(), ids, tables, cont, cont_w, cont_b, gates,
                                             ctx.padding_idx)
         return (None, res[10], res[11], res[9], None, *([None] * 9), *res[:9])
 
@@ -659,12 +659,12 @@ class _NormalizedRows(torch.autograd.Function):
     def forward(ctx, table, ids, eps, out_dtype):
         ctx.save_for_backward(table, ids)
         ctx.eps = eps
-        return torch.ops.rs.normalized_rows(table, ids, eps, out_dtype)
+        return L.direct.normalized_rows(table, ids, eps, out_dtype)
 
     @staticmethod
     def backward(ctx, g):
         table, ids = ctx.saved_tensors
-        return torch.ops.rs.normalized_rows_bwd(g, table, ids, ctx.eps), None, None, None
+        return L.direct.normalized_rows_bwd(g, table, ids, ctx.eps), None, None, None
 
 
 def normalized_rows(table, ids, eps: float = 1e-12, out_dtype=None):
@@ -678,12 +678,12 @@ class _MaskedMean(torch.autograd.Function):
     def forward(ctx, feats, mask):
         ctx.save_for_backward(mask)
         ctx.dt = L.dt(feats)
-        return torch.ops.rs.masked_mean(feats, mask)
+        return L.direct.masked_mean(feats, mask)
 
     @staticmethod
     def backward(ctx, g):
         (mask,) = ctx.saved_tensors
-        return torch.ops.rs.masked_mean_bwd(g.float().contiguous(), mask, ctx.dt), None
+        return L.direct.masked_mean_bwd(g.float().contiguous(), mask, ctx.dt), None
 
 
 def masked_mean(feats, mask):
@@ -694,7 +694,7 @@ def masked_mean(feats, mask):
 class _FM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, offsets, emb, lin, want_concat, concat_dtype):
-        fm, concat = torch.ops.rs.fm_fwd(ids, offsets, emb, lin, want_concat, concat_dtype)
+        fm, concat = L.direct.fm_fwd(ids, offsets, emb, lin, want_concat, concat_dtype)
         ctx.save_for_backward(ids, offsets, emb)
         ctx.meta = (lin is not None, want_concat, None if lin is None else lin.shape)
         return fm, concat
@@ -703,7 +703,7 @@ class _FM(torch.autograd.Function):
     def backward(ctx, d_fm, d_concat):
         ids, offsets, emb = ctx.saved_tensors
         has_lin, want_concat, lin_shape = ctx.meta
-        d_emb, d_lin = torch.ops.rs.fm_bwd(ids, offsets, emb, d_fm, d_concat if want_concat else None, has_lin)
+        d_emb, d_lin = L.direct.fm_bwd(ids, offsets, emb, d_fm, d_concat if want_concat else None, has_lin)
         return None, None, d_emb, (d_lin.reshape(lin_shape) if has_lin else None), None, None
 
 
@@ -715,7 +715,7 @@ def fm_interaction(ids, offsets, emb, lin=None, want_concat=True, concat_dtype=N
 
 def retrieve_topk(user_emb: Tensor, item_emb: Tensor, k: int, mask_index0: bool = False):
     """R1: topk(user_emb @ item_emb.T, k) -> (scores, ids); score desc, ties by ascending id."""
-    return torch.ops.rs.retrieve_topk(user_emb.float(), item_emb.float(), k, mask_index0)
+    return L.direct.retrieve_topk(user_emb.float(), item_emb.float(), k, mask_index0)
 
 
 class _SparseLogits(torch.autograd.Function):
@@ -727,13 +727,13 @@ class _SparseLogits(torch.autograd.Function):
         bc = b.detach() if compute_dtype is None else b.detach().to(compute_dtype)
         ctx.save_for_backward(ac, bc, idx, key_row, key_col)
         ctx.meta = (scale, a.dtype, b.dtype)
-        return torch.ops.rs.sparse_logits(ac, bc, idx, scale, bias, key_row, key_col)
+        return L.direct.sparse_logits(ac, bc, idx, scale, bias, key_row, key_col)
 
     @staticmethod
     def backward(ctx, g):
         a, b, idx, key_row, key_col = ctx.saved_tensors
         scale, adt, bdt = ctx.meta
-        d_a, d_b = torch.ops.rs.sparse_logits_bwd(a, b, idx, scale, key_row, key_col, g.float().contiguous())
+        d_a, d_b = L.direct.sparse_logits_bwd(a, b, idx, scale, key_row, key_col, g.float().contiguous())
         return d_a.to(adt), d_b.to(bdt), None, None, None, None, None, None
 
 
@@ -788,7 +788,7 @@ class _UserBlockLogits(torch.autograd.Function):
     def forward(ctx, u, cols, pos_col, row_cu, max_len, scale, bias, compute_dtype):
         uc = u.detach() if compute_dtype is None else u.detach().to(compute_dtype)
         cc = cols.detach() if compute_dtype is None else cols.detach().to(compute_dtype)
-        s_pos, own = torch.ops.rs.user_block_logits(uc, cc, pos_col, row_cu, max_len, scale, bias)
+        s_pos, own = L.direct.user_block_logits(uc, cc, pos_col, row_cu, max_len, scale, bias)
         ctx.save_for_backward(uc, cc, pos_col, row_cu, bias, own)
         ctx.meta = (max_len, scale, u.dtype, cols.dtype)
         return s_pos, own
@@ -797,7 +797,7 @@ class _UserBlockLogits(torch.autograd.Function):
     def backward(ctx, g_pos, g_own):
         uc, cc, pos_col, row_cu, bias, own = ctx.saved_tensors
         max_len, scale, udt, cdt = ctx.meta
-        d_u, d_c = torch.ops.rs.user_block_logits_bwd(uc, cc, pos_col, row_cu, max_len, scale, bias, own,
+        d_u, d_c = L.direct.user_block_logits_bwd(uc, cc, pos_col, row_cu, max_len, scale, bias, own,
                                                       g_pos.float().contiguous(), g_own.float().contiguous())
         return d_u.to(udt), d_c.to(cdt), None, None, None, None, None, None
 
@@ -813,5 +813,5 @@ def user_block_logits(u, cols, pos_col, row_cu, max_len, scale, bias=None, compu
 def mine_hard_negatives(u, v, key, k, hnm_threshold):
     """(scores, ids, avail): per-row top-k of <u_i, v_j> over non-ignored columns (C4/C5 mining, no gradient)."""
     with torch.no_grad():
-        return torch.ops.rs.mine_hard_negatives(u.detach().float(), v.detach().float(), key, int(k),
+        return L.direct.mine_hard_negatives(u.detach().float(), v.detach().float(), key, int(k),
                                                 float(hnm_threshold))

@@ -17,14 +17,16 @@ from typing import Callable, Optional
 import torch
 import torch.distributed as dist
 
+from . import _lib as _L
+
 
 def _default_gather(table, ids):
-    from . import ops
-    return torch.ops.rs.gather_rows(table, ids, -1, ops.L.dt(table))
+    from . import ops  # noqa: F401  (registers the ops)
+    return _L.direct.gather_rows(table, ids, -1, _L.dt(table))
 
 
 def _default_scatter(grad_rows, ids, rows):
-    return torch.ops.rs.embedding_dense_bwd(grad_rows, ids, rows, -1, -1, True)
+    return _L.direct.embedding_dense_bwd(grad_rows, ids, rows, -1, -1, True)
 
 
 def shard_rows(full: torch.Tensor, rank: int, world: int) -> torch.Tensor:
@@ -194,7 +196,7 @@ class _PlannedLookup(torch.autograd.Function):
 
 
 def _scatter_pad(grad_rows, ids, rows, pad_local_row):
-    return torch.ops.rs.embedding_dense_bwd(grad_rows, ids, rows, pad_local_row, -1, True)
+    return _L.direct.embedding_dense_bwd(grad_rows, ids, rows, pad_local_row, -1, True)
 
 
 def planned_lookup(shard: torch.Tensor, plan: LookupPlan, group=None, gather_fn: Optional[Callable] = None,
