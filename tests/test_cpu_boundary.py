@@ -108,3 +108,47 @@ def test_synthetic_batch_shapes(rs):
     assert (b["item_ids"][pad] == 0).all() and (b["item_ids"][~pad] > 0).all()
     assert (pad[:, 1:] <= pad[:, :-1]).all()              # left padding
     assert syn.log_q(1000)[0] == -20.0
+
+
+def test_two_view_index_layout_is_what_the_ln_backward_fold_assumes(rs):
+    """train.add_host_index lays the two dropout views out as [tokens | tokens | extras | extras]; the LayerNorm backward
+    (encoder.layer_norm(index_fold=(T, E))) turns its scatter-add into two elementwise sums on that promise."""
+    syn = rs.synthetic
+    for seed, B in ((3, 64), (4, 257)):
+        hb = rs.train.add_host_index(syn.make_batch(B, 50, 3000, seed=seed))
+        T = hb["valid_index"].numel()
+        idx = hb["pk_index_2v"]
+        E = (idx.numel() - 2 * T) // 2
+        assert idx.numel() == 2 * (T + E) and E >= 0
+        tok, ext = torch.arange(T), T + torch.arange(E)
+        assert torch.equal(idx, torch.cat([tok, tok, ext, ext]))
+        assert hb["pk_item_ids"].numel() >= T + E
+        # the packed grids hold exactly the valid tokens, then the literal-DuoRec positions, then zeros
+        flat = hb["pk_item_ids"].reshape(-1)
+        assert torch.equal(flat[:T], hb["item_ids"].reshape(-1)[hb["valid_index"]])
+        assert (flat[T + E:] == 0).all()
+        cu = hb["cu_seqlens_2v"]
+        assert cu[0] == 0 and cu[-1] == 2 * (T + E) and (cu[1:] > cu[:-1]).all()
+
+
+def test_direct_entry_points_cover_every_registered_op(rs):
+    """_lib.direct.NAME is the Python implementation behind torch.ops.rs.NAME (no silent fallback to the dispatcher)."""
+    from torch._library.custom_ops import OPDEFS
+    names = sorted(k.split("::")[1] for k in OPDEFS if k.startswith("rs::"))
+    assert len(names) >= 30
+    for n in names:
+        fn = getattr(rs._lib.direct, n)
+        assert callable(fn) and fn is OPDEFS["rs::" + n]._init_fn, n
+        assert hasattr(torch.ops.rs, n)
+
+
+def test_host_wrappers_fall_back_to_torch_off_device(rs):
+    """encoder.linear / sequential / l2_normalize are drop-ins for the stock modules: on CPU tensors (no kernels) they
+    must be the stock computation."""
+    g = torch.Generator().manual_seed(0)
+    seq = torch.nn.Sequential(torch.nn.Linear(100, 128), torch.nn.LayerNorm(128), torch.nn.GELU(), torch.nn.Linear(128, 128))
+    x = torch.randn(7, 100, generator=g)
+    torch.testing.assert_close(rs.encoder.sequential(seq, x), seq(x))
+    torch.testing.assert_close(rs.encoder.linear(seq[0], x), seq[0](x))
+    y = torch.randn(5, 128, generator=g)
+    torch.testing.assert_close(rs.encoder.l2_normalize(y), torch.nn.functional.normalize(y, p=2, dim=-1))
