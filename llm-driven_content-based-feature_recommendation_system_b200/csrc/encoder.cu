@@ -82,18 +82,6 @@ struct AttnParams {
   uint64_t seed;
 };
 
-// stage rows [row0, row0+len) x 32 columns starting at col0 (+ bias) into shared memory as fp32 [len][32]
-template <int DT>
-__device__ __forceinline__ void stage_rows(float* dst, const void* src, int64_t row0, int len, int64_t row_stride,
-                                           int64_t col0, const float* bias, int lane) {
-  const int sub = lane >> 3, d4 = (lane & 7) * 4;
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias) b4 = ldg_f4(bias + col0 + d4);
-  for (int j = sub; j < len; j += 4) {
-    const float4 v = ld4<DT>(src, (row0 + j) * row_stride + col0 + d4);
-    *reinterpret_cast<float4*>(dst + j * ENC_HD + d4) = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
-  }
-}
 
 // a lane's slice of a row: N consecutive values (N = 4, 8 or 16)
 template <int DT, int N>
@@ -104,30 +92,6 @@ __device__ __forceinline__ void load_slice(float (&r)[N], const void* src, int64
     if (bias) { const float4 b4 = ldg_f4(bias + boff + 4 * q); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
     r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
   }
-}
-template <int N> __device__ __forceinline__ float dot_slice(const float (&r)[N], const float* s) {
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (int q = 0; q < N / 4; ++q) {
-    const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
-    a0 = fmaf(r[4 * q], v.x, a0); a1 = fmaf(r[4 * q + 1], v.y, a1);
-    a0 = fmaf(r[4 * q + 2], v.z, a0); a1 = fmaf(r[4 * q + 3], v.w, a1);
-  }
-  return a0 + a1;
-}
-template <int N> __device__ __forceinline__ void axpy_slice(float (&acc)[N], float a, const float* s) {
-#pragma unroll
-  for (int q = 0; q < N / 4; ++q) {
-    const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
-    acc[4 * q] = fmaf(a, v.x, acc[4 * q]); acc[4 * q + 1] = fmaf(a, v.y, acc[4 * q + 1]);
-    acc[4 * q + 2] = fmaf(a, v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a, v.w, acc[4 * q + 3]);
-  }
-}
-template <int DT, int N>
-__device__ __forceinline__ void store_slice(void* dst, int64_t off, const float (&r)[N], float s) {
-#pragma unroll
-  for (int q = 0; q < N / 4; ++q)
-    st4<DT>(dst, off + 4 * q, make_float4(r[4 * q] * s, r[4 * q + 1] * s, r[4 * q + 2] * s, r[4 * q + 3] * s));
 }
 // sum over the R consecutive lanes that share a row
 template <int R> __device__ __forceinline__ float group_sum(float v) {

@@ -3,14 +3,16 @@
 //   S = scale * (A @ B^T) - col_bias  (+ id masks)      [M, N], K = 128
 //
 // forward  : per-row logsumexp / diagonal logit / SupCon sums, S never leaves the SM
-// backward : S recomputed, dS -> bf16 tile in shared memory -> second tcgen05.mma (dS @ B), ditto
+// backward : S recomputed, dS -> 16-bit, written back into TMEM over the S columns just consumed -> second
+//            tcgen05.mma with dS as its A operand FROM TMEM and the resident X tile MN-major from shared memory
 //
 // Structure (one CTA per SM, persistent over (row block, column range) work items):
-//   warp 0     TMA producer      cp.async.bulk.tensor (SWIZZLE_128B) -> smem ring, mbarrier complete_tx
-//   warp 1     MMA issuer        one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM
-//   warps 2-9  two epilogue warpgroups, alternating tiles: tcgen05.ld TMEM -> registers, one thread per
-//              row (no shuffles), online logsumexp in the log2 domain
-// TMEM: two 128-column S accumulators (+ one 128-column dS@X accumulator in the backward).
+//   warp 0      TMA producer      cp.async.bulk.tensor (SWIZZLE_128B) -> smem ring (4 stages fwd, 5 bwd), mbarriers
+//   warp 1      MMA issuer        one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM
+//   warps 2-13  three epilogue warpgroups, alternating tiles: tcgen05.ld TMEM -> registers, one thread per
+//               row (no shuffles), log2 domain, packed f32x2 math, a share of the 2^x on the FMA pipe
+// TMEM: three 128-column S accumulators (+ one 128-column dS@X accumulator in the backward) = 512 columns.
+// DESIGN.md section 5 has the reasoning and the measurements behind each of these choices.
 #include "common.cuh"
 #include "../../include/rs_twotower.h"
 #include <cuda.h>
