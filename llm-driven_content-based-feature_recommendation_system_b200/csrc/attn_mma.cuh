@@ -120,28 +120,37 @@ __device__ __forceinline__ void mma_abt(float (&c)[2][4], const uint32_t (&a)[2]
     for (int ks = 0; ks < 2; ++ks) mma16816<DT>(c[nt], a[ks], b[nt][ks][0], b[nt][ks][1]);
   }
 }
-// stage rows [row0, row0 + 16) x 32 columns (+ bias) as a 16-bit [16][AT3_LD] tile; rows >= limit are zero
+// stage rows [row0, row0 + 16) x 32 columns (+ bias) as a 16-bit [16][AT3_LD] tile; rows >= limit are zero.  Split in two
+// so that the global loads are issued at the top of a tile iteration and their latency hides behind the fragment loads,
+// the first product and the elementwise work; the tile is only written (and read back by ldmatrix) at the end.
+struct TileRegs { uint4 v0, v1; };
 template <int DT>
-__device__ __forceinline__ void stage_tile16(uint16_t* dst, const void* src, int64_t tok0, int row0, int limit,
-                                             int64_t row_stride, int64_t col0, const float* bias, int lane) {
+__device__ __forceinline__ TileRegs tile_load(const void* src, int64_t tok0, int row0, int limit, int64_t row_stride,
+                                              int64_t col0, const float* bias, int lane) {
   const int row = lane >> 1, c0 = (lane & 1) * 16;
-  uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+  TileRegs t;
+  t.v0 = make_uint4(0, 0, 0, 0);
+  t.v1 = t.v0;
   if (row0 + row < limit) {
     const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + (tok0 + row0 + row) * row_stride +
                                                     col0 + c0);
-    v0 = __ldg(s);
-    v1 = __ldg(s + 1);
+    t.v0 = __ldg(s);
+    t.v1 = __ldg(s + 1);
     if (bias) {
       const float4 b0 = ldg_f4(bias + col0 + c0), b1 = ldg_f4(bias + col0 + c0 + 4), b2 = ldg_f4(bias + col0 + c0 + 8),
                    b3 = ldg_f4(bias + col0 + c0 + 12);
-      v0.x = add16x2<DT>(v0.x, pack16<DT>(b0.x, b0.y)); v0.y = add16x2<DT>(v0.y, pack16<DT>(b0.z, b0.w));
-      v0.z = add16x2<DT>(v0.z, pack16<DT>(b1.x, b1.y)); v0.w = add16x2<DT>(v0.w, pack16<DT>(b1.z, b1.w));
-      v1.x = add16x2<DT>(v1.x, pack16<DT>(b2.x, b2.y)); v1.y = add16x2<DT>(v1.y, pack16<DT>(b2.z, b2.w));
-      v1.z = add16x2<DT>(v1.z, pack16<DT>(b3.x, b3.y)); v1.w = add16x2<DT>(v1.w, pack16<DT>(b3.z, b3.w));
+      t.v0.x = add16x2<DT>(t.v0.x, pack16<DT>(b0.x, b0.y)); t.v0.y = add16x2<DT>(t.v0.y, pack16<DT>(b0.z, b0.w));
+      t.v0.z = add16x2<DT>(t.v0.z, pack16<DT>(b1.x, b1.y)); t.v0.w = add16x2<DT>(t.v0.w, pack16<DT>(b1.z, b1.w));
+      t.v1.x = add16x2<DT>(t.v1.x, pack16<DT>(b2.x, b2.y)); t.v1.y = add16x2<DT>(t.v1.y, pack16<DT>(b2.z, b2.w));
+      t.v1.z = add16x2<DT>(t.v1.z, pack16<DT>(b3.x, b3.y)); t.v1.w = add16x2<DT>(t.v1.w, pack16<DT>(b3.z, b3.w));
     }
   }
-  *reinterpret_cast<uint4*>(dst + row * AT3_LD + c0) = v0;
-  *reinterpret_cast<uint4*>(dst + row * AT3_LD + c0 + 8) = v1;
+  return t;
+}
+__device__ __forceinline__ void tile_store(uint16_t* dst, const TileRegs& t, int lane) {
+  const int row = lane >> 1, c0 = (lane & 1) * 16;
+  *reinterpret_cast<uint4*>(dst + row * AT3_LD + c0) = t.v0;
+  *reinterpret_cast<uint4*>(dst + row * AT3_LD + c0 + 8) = t.v1;
 }
 // acc[4 n-tiles of 8 dims][4] += A[16 x 16 tokens] . T[16 tokens x 32 dims], T staged in shared memory
 template <int DT>
@@ -219,13 +228,11 @@ __global__ void __launch_bounds__(256, 3) attn3_fwd_kernel(const void* __restric
       const uint32_t shi = (uint32_t)(p.seed >> 32);
       const uint32_t hr[2] = {rnd_row(p.seed, (uint32_t)((t0 + i0) * p.H + h)), rnd_row(p.seed, (uint32_t)((t0 + i0 + 8) * p.H + h))};
       for (int kt = 0; kt <= qt; ++kt) {
+        const TileRegs vt = tile_load<DT>(qkv, t0, kt * 16, len, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);    // V
         uint32_t kb[2][2][2];
         load_b<DT>(kb, qkv, t0, kt * 16, len, rs_, os_ + h * ENC_HD, bk, hb, g, t);
         float s[2][4];
         mma_abt<DT>(s, qa, kb);
-        __syncwarp();
-        stage_tile16<DT>(sT, qkv, t0, kt * 16, len, rs_, 2 * os_ + h * ENC_HD, p.bias, lane);      // V
-        __syncwarp();
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
@@ -262,6 +269,9 @@ __global__ void __launch_bounds__(256, 3) attn3_fwd_kernel(const void* __restric
         for (int n = 0; n < 4; ++n) { o[n][0] *= c[0]; o[n][1] *= c[0]; o[n][2] *= c[1]; o[n][3] *= c[1]; }
         uint32_t pa[4];
         c_to_a<DT>(pa, s);
+        __syncwarp();                                   // the previous tile's ldmatrix reads are done
+        tile_store(sT, vt, lane);
+        __syncwarp();
         mma_a_tile<DT>(o, pa, sT, lane);
       }
 #pragma unroll
@@ -355,15 +365,13 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_kernel(const void* __restric
       const uint32_t shi = (uint32_t)(p.seed >> 32);
       const uint32_t hr[2] = {rnd_row(p.seed, (uint32_t)((t0 + i0) * p.H + h)), rnd_row(p.seed, (uint32_t)((t0 + i0 + 8) * p.H + h))};
       for (int kt = 0; kt <= qt; ++kt) {
+        const TileRegs kt_ = tile_load<DT>(qkv, t0, kt * 16, len, rs_, os_ + h * ENC_HD, p.bias, lane);       // K
         uint32_t kb[2][2][2], vb[2][2][2];
         load_b<DT>(kb, qkv, t0, kt * 16, len, rs_, os_ + h * ENC_HD, bk, hb, g, t);
         load_b<DT>(vb, qkv, t0, kt * 16, len, rs_, 2 * os_ + h * ENC_HD, bv, hb, g, t);
         float s[2][4], dp[2][4];
         mma_abt<DT>(s, qa, kb);
         mma_abt<DT>(dp, ga, vb);
-        __syncwarp();
-        stage_tile16<DT>(sT0, qkv, t0, kt * 16, len, rs_, os_ + h * ENC_HD, p.bias, lane);          // K
-        __syncwarp();
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -378,6 +386,9 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_kernel(const void* __restric
           }
         uint32_t da[4];
         c_to_a<DT>(da, s);
+        __syncwarp();
+        tile_store(sT0, kt_, lane);
+        __syncwarp();
         mma_a_tile<DT>(dq, da, sT0, lane);
       }
 #pragma unroll
@@ -403,16 +414,14 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_kernel(const void* __restric
 #pragma unroll
         for (int e = 0; e < 4; ++e) { dk[n][e] = 0.f; dv[n][e] = 0.f; }
       for (int qt = kt; qt * 16 < len; ++qt) {
+        const TileRegs qt_ = tile_load<DT>(qkv, t0, qt * 16, len, rs_, h * ENC_HD, p.bias, lane);             // Q
+        const TileRegs gt_ = tile_load<DT>(d_out, t0, qt * 16, len, os_, h * ENC_HD, nullptr, lane);          // dO
         uint32_t qb[2][2][2], gb[2][2][2];
         load_b<DT>(qb, qkv, t0, qt * 16, len, rs_, h * ENC_HD, bq, hb, g, t);
         load_b<DT>(gb, d_out, t0, qt * 16, len, os_, h * ENC_HD, nob, false, g, t);
         float s[2][4], dp[2][4];
         mma_abt<DT>(s, ka, qb);
         mma_abt<DT>(dp, va, gb);
-        __syncwarp();
-        stage_tile16<DT>(sT0, qkv, t0, qt * 16, len, rs_, h * ENC_HD, p.bias, lane);                // Q
-        stage_tile16<DT>(sT1, d_out, t0, qt * 16, len, os_, h * ENC_HD, nullptr, lane);             // dO
-        __syncwarp();
         float pk[2][4];
         const uint32_t shi = (uint32_t)(p.seed >> 32);
         uint32_t hq[2][2];
@@ -439,6 +448,10 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_kernel(const void* __restric
         uint32_t pa[4], da[4];
         c_to_a<DT>(pa, pk);
         c_to_a<DT>(da, s);
+        __syncwarp();
+        tile_store(sT0, qt_, lane);
+        tile_store(sT1, gt_, lane);
+        __syncwarp();
         mma_a_tile<DT>(dv, pa, sT1, lane);
         mma_a_tile<DT>(dk, da, sT0, lane);
       }
