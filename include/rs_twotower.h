@@ -298,6 +298,26 @@ int rs_ce_bwd(const rs_ce_problem* p /*host*/, const float* lse, const float* w_
               const float* w_diag /*[M] or NULL*/, const float* w_pos /*[M] or NULL*/, float* dA, float* dB,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Forward that also accumulates the row side of the backward ("flash" form of the same loss; same reference lines as
+ * rs_ce_fwd / rs_ce_bwd).  With a bounded logit range (logit_bound > 0 and a moderate bias range, decided on the
+ * device) every exponential e_ij = 2^(S_ij - C) is final when it is formed, and dS_ij = (w_i / l_i) e_ij is a per-row
+ * scalar times e_ij: the pass that sums l_i also accumulates G_i = sum_j bf16(e_ij) B_j on the tensor cores (second
+ * tcgen05.mma, P from TMEM), and the backward's dA is a row scaling of G.  Per loss the tensor cores then execute
+ * S, P@B (here) and S, dS^T@A (rs_ce_bwd_from_grad, the dB side): 4 contractions instead of 5.
+ *   g_parts : caller-owned [rs_ce_fwd_grad_bytes(p)] bytes, kept until the backward (split partials of G, fp32)
+ *   g_info  : caller-owned float[8], kept until the backward: [0] = C (log2 units), [1] != 0 iff G is valid (else the
+ *             backward falls back to its own row-side pass, stream-ordered, no host decision), [3] = scale2*bound
+ * bf16 operands only; no RS_CE_SUPCON; masks must be -inf (a masked entry must carry no softmax mass).
+ * lse / diag exactly as rs_ce_fwd. */
+size_t rs_ce_fwd_grad_bytes(const rs_ce_problem* p);
+int rs_ce_fwd_grad(const rs_ce_problem* p /*host*/, float* lse /*[M]*/, float* diag /*[M]*/, float* g_parts,
+                   float* g_info, void* workspace, size_t workspace_bytes, void* stream);
+/* rs_ce_bwd with the row side taken from rs_ce_fwd_grad's outputs: dA = scale * (w_lse/l) * G + scale * w_diag * B[label]
+ * (one pass over G), dB by the transposed tensor-core pass as in rs_ce_bwd.  dA or dB may be NULL. */
+int rs_ce_bwd_from_grad(const rs_ce_problem* p /*host*/, const float* lse, const float* w_lse /*[M]*/,
+                        const float* w_diag /*[M] or NULL*/, const float* g_parts, const float* g_info,
+                        float* dA, float* dB, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same-user block of the distinct-item softmax (losses.logq_infonce_columns; the same-user mask of
  * tower_code/v1_refine_usertower.py:848).  Rows are grouped by user (row_cu[n_users+1], <= 64 rows per user);
  * pos_col[i] is the column (distinct item) of row i's target.  Per user, over its own rows i, j:

@@ -72,6 +72,9 @@ PROTOTYPES = {
     "rs_ce_workspace_bytes": (sz, [C.POINTER(CEProblem)]),
     "rs_ce_fwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_bwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "rs_ce_fwd_grad_bytes": (sz, [C.POINTER(CEProblem)]),
+    "rs_ce_fwd_grad": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
+    "rs_ce_bwd_from_grad": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "rs_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),
     "rs_retrieve_topk": (i32, [vp, i64, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
     "rs_mine_workspace_bytes": (sz, [i64, i64, i64]),
@@ -97,6 +100,12 @@ def _algorithmic_work(name, args):
         p = args[0]
         sides = (args[5] is not None) + (args[6] is not None)
         return 2.0 * p.M * p.N * p.K * 2 * sides
+    if name == "rs_ce_fwd_grad":                # S + P@B
+        p = args[0]
+        return 2.0 * p.M * p.N * p.K * 2
+    if name == "rs_ce_bwd_from_grad":           # the dB side only (S recompute + dS^T@A); dA is a row scaling of G
+        p = args[0]
+        return 2.0 * p.M * p.N * p.K * 2 * (args[7] is not None)
     if name == "rs_segment_reduce_rows":        # one read of the gradient rows + the sorted (id, pos) pairs
         n, dim, esz = args[4], args[5], (4 if args[1] == RS_F32 else 2)
         return float(n) * (dim * esz + 8)

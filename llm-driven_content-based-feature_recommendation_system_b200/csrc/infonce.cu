@@ -241,6 +241,8 @@ struct CeParams {
   //   tune[2] != 0  -> every w_lse >= 0 (needed to move the weight into the exponent)
   //   tune[3] = scale2 * bound: |a.b * scale2| <= tune[3] when tune[1] != 0
   const float* tune;
+  const float* skip_if;         // backward pass A: device scalar; != 0 -> the forward already produced G (rs_ce_fwd_grad),
+                                // this launch has nothing to do and returns at once
 };
 
 __device__ __forceinline__ void item_coords(const CeParams& p, int item, int& rb, int& sp, int& ct_lo, int& ct_hi) {
@@ -648,6 +650,72 @@ __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&r)[32], uint32_t
   tmem_st16(ptaddr, w);
 }
 
+// ---- forward that also feeds the row-side gradient ("flash" form).  With the fixed softmax offset C every exponential
+// e_ij = 2^(s_ij - C) is final when it is formed (no running max, no rescale), and
+//     dS_ij = w_i * softmax_ij = (w_i / l_i) * e_ij        (l_i = sum_j e_ij, known only after the whole row)
+// is a per-ROW scalar times e_ij.  So G_i = sum_j bf16(e_ij) B_j can be accumulated on the tensor cores in the same pass
+// that sums l_i, and the backward's row side is dA_i = scale * (w_i / l_i) * G_i: a row scaling.  One S contraction and
+// one P@B contraction replace the forward's S + the backward's S recompute + dS@B.
+#ifndef CE_FWDG_NPOLY
+#define CE_FWDG_NPOLY 5
+#endif
+template <int MODE, bool EDGE, bool USE_KB>
+__device__ __forceinline__ void fwdg_chunk(const uint32_t (&r)[32], uint32_t meta, int cbase, RowCtx& rc,
+                                           const CeParams& p, int64_t col0, bool row_ok, int64_t row, uint32_t ptaddr) {
+  float v[32];
+  unsigned posbits, diagbit;
+  logits32<MODE, EDGE, USE_KB, false>(r, v, posbits, diagbit, meta, cbase, rc, p, col0);
+  if (EDGE && diagbit && row_ok) {
+    float dv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (diagbit & (1u << j)) dv = v[j];
+    p.diag_out[row] = (dv + rc.c_off) * CE_LN2;
+  }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    v[j] = ex2(v[j]); v[j + 1] = ex2(v[j + 1]); v[j + 2] = ex2(v[j + 2]); v[j + 3] = ex2(v[j + 3]);
+    a0 += v[j]; a1 += v[j + 1]; a2 += v[j + 2]; a3 += v[j + 3];
+  }
+  rc.l += (a0 + a1) + (a2 + a3);
+  uint32_t w[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) w[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+  tmem_st16(ptaddr, w);
+}
+// fast path (no edge, no key hit in this chunk): e = 2^(a*scale2 - top) * f_j, packed pairs, NPOLY polynomial pairs
+template <int MODE, int NPOLY>
+__device__ __forceinline__ void fwdg_chunk_fast(const uint32_t (&r)[32], uint32_t meta, int cbase, RowCtx& rc,
+                                                const CeParams& p, float ntop, uint32_t ptaddr) {
+  const f2_t s2 = pk2(p.scale2, p.scale2), nt2 = pk2(ntop, ntop);
+  f2_t acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
+  uint32_t w[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const f2_t x0 = ffma2(pk2u(r[4 * q], r[4 * q + 1]), s2, nt2);
+    const f2_t x1 = ffma2(pk2u(r[4 * q + 2], r[4 * q + 3]), s2, nt2);
+    f2_t e0 = pair_is_poly<NPOLY>(2 * q) ? exp2_pair<true>(x0) : exp2_pair<false>(x0);
+    f2_t e1 = pair_is_poly<NPOLY>(2 * q + 1) ? exp2_pair<true>(x1) : exp2_pair<false>(x1);
+    if (MODE != MODE_PLAIN) {
+      const float4 f4 = lds_f4(meta + OFF_WL + (cbase + 4 * q) * 4);
+      e0 = fmul2(e0, pk2(f4.x, f4.y));
+      e1 = fmul2(e1, pk2(f4.z, f4.w));
+    }
+    acc0 = fadd2(acc0, e0);
+    acc1 = fadd2(acc1, e1);
+    float a, b, c, d;
+    upk2(e0, a, b);
+    upk2(e1, c, d);
+    w[2 * q] = pack_bf16(a, b);
+    w[2 * q + 1] = pack_bf16(c, d);
+  }
+  float a, b, c, d;
+  upk2(acc0, a, b);
+  upk2(acc1, c, d);
+  rc.l += (a + b) + (c + d);
+  tmem_st16(ptaddr, w);
+}
+
 // Can any (row of this warp, column of chunk `ch`) pair have equal key_a?  Two range tests, both necessary for a match:
 // some row key inside the chunk's column-key range (decisive when the COLUMNS are sorted: forward, pass A), and some
 // column key inside the warp's row-key range [wlo, whi] (decisive when the ROWS are sorted: transposed pass B).
@@ -836,6 +904,199 @@ __global__ void ce_fwd_finalize(int64_t M, int nsplit, const float* __restrict__
   if (pos_sum) { pos_sum[r] = ps * CE_LN2; pos_cnt[r] = pc; }
 }
 
+// ================================================================================ forward + row-side gradient
+// Same pipeline as the backward kernel below (S into one of three TMEM accumulators, a 16-bit tile written back over
+// the S columns just consumed, second tcgen05.mma with that tile as its A operand from TMEM and the resident column
+// tile MN-major, fourth TMEM region accumulating over the item's column range) with the forward's epilogue: the tile
+// written back is P = 2^(S - C) itself, its row sums go to the log-sum-exp partials.  Output per (split, row):
+// part_m / part_l (as the forward) and part_out[sp][row][0..128) = sum_c P[row, c] * B[c, :] (unscaled).
+// When the fixed-offset precondition does not hold (tune[1] == 0) the kernel still returns the correct log-sum-exp
+// (running-max path) and the G partials are meaningless: the backward then runs its own pass A (CeParams.skip_if).
+template <int MODE>
+__global__ void __launch_bounds__(CE_THREADS, 1)
+ce_fwdg_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const CeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                                       // 1 x 32 KB (row block of A)
+  uint8_t* sB = base + CE_TILE_BYTES;                       // CE_BWD_STAGES x 32 KB (column tiles of B)
+  CeShared& sh = *reinterpret_cast<CeShared*>(base + (1 + CE_BWD_STAGES) * CE_TILE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ce_setup(sh, warp, &mapA, &mapB, 512);
+  const uint32_t tmem_base = sh.tmem_base;
+  const int n_items = p.row_blocks * p.nsplit;
+
+  if (warp == 0) {
+    if (lane == 0) producer_role<CE_BWD_STAGES, 1>(p, sh, sA, sB, &mapA, &mapB);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, item_n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        int rb, sp, lo, hi;
+        item_coords(p, item, rb, sp, lo, hi);
+        const uint32_t nt = (uint32_t)(hi - lo), it0 = it;
+        mbar_wait(&sh.a_full[0], item_n & 1);
+        const uint64_t adesc = desc_kmajor(smem_u32(sA));
+        mbar_wait(&sh.d2_empty, (item_n & 1) ^ 1);      // previous item's P@B accumulator has been drained
+        tc_fence_after();
+        issue_s<CE_BWD_STAGES, false>(p, sh, sB, adesc, tmem_base, it0);
+        if (nt > 1) issue_s<CE_BWD_STAGES, false>(p, sh, sB, adesc, tmem_base, it0 + 1);
+        for (uint32_t t = it0; t < it0 + nt; ++t) {
+          if (t + 2 < it0 + nt) issue_s<CE_BWD_STAGES, false>(p, sh, sB, adesc, tmem_base, t + 2);
+          const uint32_t s = t % CE_BWD_STAGES, g = t % CE_NWG, ng = t / CE_NWG;
+          mbar_wait(&sh.p_full[g], ng & 1);                 // P(t) sits in TMEM, over the first 64 columns of S(t)
+          tc_fence_after();
+          const uint64_t xdesc = desc_mnmajor(smem_u32(sB + s * CE_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < CE_BN / 16; ++k) {
+            const uint64_t boff = (uint64_t)((k * 16 * 128) >> 4);
+            umma_f16_ts(tmem_base + CE_NWG * CE_BN, tmem_base + g * CE_BN + k * 8, xdesc + boff, p.idesc_g,
+                        (t > it0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&sh.empty[s]);
+        }
+        it = it0 + nt;
+        umma_commit(&sh.d2_full);
+        umma_commit(&sh.a_empty[0]);
+      }
+    }
+  } else {
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int rloc = quarter * 32 + lane;
+    const int t128 = (warp - 2 - 4 * wg) * 32 + lane;
+    uint32_t it = 0, nuse = 0, item_n = 0;
+    const bool fixed = __ldg(p.tune + 1) != 0.f;
+    const float c_off = fixed ? __ldg(p.tune) : 0.f;
+    const float top = __ldg(p.tune + 3);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+      int rb, sp, lo, hi;
+      item_coords(p, item, rb, sp, lo, hi);
+      const int64_t row = (int64_t)rb * CE_BM + rloc;
+      const bool row_ok = row < p.M;
+      RowCtx rc;
+      uint32_t wkb_lo, wkb_hi, wka_lo, wka_hi;
+      load_row_keys(p, row, row_ok, false, rc, wkb_lo, wkb_hi, wka_lo, wka_hi);
+      rc.nrowbias2 = 0.f;
+      rc.jd = row + p.diag_offset;
+      rc.c_off = c_off; rc.mask2c = p.mask2 - c_off;
+      rc.m = fixed ? c_off : -INFINITY; rc.l = 0.f; rc.ps = 0.f; rc.pc = 0.f;
+      const int64_t blk_d_lo = (int64_t)rb * CE_BM + p.diag_offset, blk_d_hi = blk_d_lo + CE_BM;
+      const int first = lo + (int)((wg + CE_NWG - it % CE_NWG) % CE_NWG);
+      if (first < hi) cols_store<false>(cols_load<false>(p, first, t128), sh.meta[wg][nuse & 1], t128, 1.0f, c_off, fixed, top);
+      named_bar_sync(1 + wg, 128);
+      for (int ct = lo; ct < hi; ++ct, ++it) {
+        if ((int)(it % CE_NWG) != wg) continue;
+        ColMeta& cm = sh.meta[wg][nuse & 1];
+        const bool has_next = ct + CE_NWG < hi;
+        ColRegs nxt;
+        if (has_next) nxt = cols_load<false>(p, ct + CE_NWG, t128);
+        const uint32_t meta = smem_u32(&cm);
+        const int64_t c0 = (int64_t)ct * CE_BN;
+        const bool edge = (c0 + CE_BN > p.N) || (c0 < blk_d_hi && c0 + CE_BN > blk_d_lo);
+        const bool use_kb = (MODE == MODE_GENERAL) && kb_overlaps(cm, wkb_lo, wkb_hi);
+        mbar_wait(&sh.tmem_full[wg], nuse & 1);
+        tc_fence_after();
+        if (has_next) cols_store<false>(nxt, sh.meta[wg][(nuse + 1) & 1], t128, 1.0f, c_off, fixed, top);
+        const uint32_t tt = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * CE_BN);
+        if (fixed) {
+          // P chunk ch (S columns 32ch..32ch+31) -> 16-bit pairs in columns 16ch..16ch+15 of the same accumulator
+          if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwdg_chunk<MODE, true, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row, tt + (cb >> 1)); });
+          else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwdg_chunk<MODE, false, true>(r, meta, cb, rc, p, c0 + cb, row_ok, row, tt + (cb >> 1)); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) {
+            if (MODE == MODE_GENERAL && ka_hits(meta, cb >> 5, rc.my_ka, wka_lo, wka_hi, lane)) fwdg_chunk<MODE, false, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row, tt + (cb >> 1));
+            else fwdg_chunk_fast<MODE, CE_FWDG_NPOLY>(r, meta, cb, rc, p, -top, tt + (cb >> 1));
+          });
+          tmem_st_wait();
+        } else {
+          if (edge) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, true, true, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else if (use_kb) for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, true, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+          else for_chunks(tt, [&](const uint32_t (&r)[32], int cb) { fwd_chunk<MODE, false, false, false>(r, meta, cb, rc, p, c0 + cb, row_ok, row); });
+        }
+        tc_fence_before();
+        mbar_arrive(&sh.p_full[wg]);
+        ++nuse;
+        named_bar_sync(1 + wg, 128);
+      }
+      // ---- combine the warpgroups' (max, sum) and write this split's log-sum-exp partial (as the forward kernel)
+      if (wg > 0) { sh.xm[wg - 1][rloc] = rc.m; sh.xl[wg - 1][rloc] = rc.l; }
+      named_bar_sync(1 + CE_NWG, 128 * CE_NWG);
+      if (wg == 0 && row_ok) {
+        float mm = rc.m;
+#pragma unroll
+        for (int w = 0; w < CE_NWG - 1; ++w) mm = fmaxf(mm, sh.xm[w][rloc]);
+        const float mu = (mm == -INFINITY) ? 0.f : mm;
+        float ll = rc.l * ex2(rc.m - mu);
+#pragma unroll
+        for (int w = 0; w < CE_NWG - 1; ++w) ll += sh.xl[w][rloc] * ex2(sh.xm[w][rloc] - mu);
+        const int64_t o = (int64_t)sp * p.M + row;
+        p.part_m[o] = mm;
+        p.part_l[o] = ll;
+      }
+      named_bar_sync(1 + CE_NWG, 128 * CE_NWG);
+      // ---- drain the P@B accumulator: warpgroup wg takes columns [64*wg, 64*wg+64)
+      if (wg >= 2) continue;
+      mbar_wait(&sh.d2_full, item_n & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        const int d0 = wg * 64 + h * 32;
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(CE_NWG * CE_BN + d0), r);
+        tmem_ld_wait();
+        pin32(r);
+        if (row_ok) {
+          float* dst = p.part_out + ((int64_t)sp * p.M + row) * CE_K + d0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                            __uint_as_float(r[j + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh.d2_empty);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// dA[r,:] = scale * ( w_lse[r] * 2^(C - lse2[r]) * sum_s G[s][r,:]  +  w_diag[r] * B[r + diag_offset,:] ): the backward's
+// row side when the forward produced G (see ce_fwdg_kernel).  One warp per row, 128-bit accesses.
+__global__ void ce_ga_kernel(const float* __restrict__ g_parts, int nsplit, int64_t M, int64_t N,
+                             const float* __restrict__ g_info, const float* __restrict__ lse,
+                             const float* __restrict__ w_lse, const float* __restrict__ w_diag,
+                             const uint16_t* __restrict__ B, int64_t diag_offset, float scale, float* __restrict__ dA) {
+  if (__ldg(g_info + 1) == 0.f) return;            // G not valid: pass A of the backward kernel ran instead
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float C = __ldg(g_info);
+  for (int64_t r = warp0; r < M; r += nwarps) {
+    const float l = __ldg(lse + r);
+    const float w = __ldg(w_lse + r);
+    const float coef = (l == -INFINITY || w == 0.f) ? 0.f : w * exp2f(C - l * CE_LOG2E) * scale;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < nsplit; ++s) {
+      const float4 v = ld_stream_f4(g_parts + ((int64_t)s * M + r) * CE_K + lane * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4 o = make_float4(acc.x * coef, acc.y * coef, acc.z * coef, acc.w * coef);
+    if (w_diag) {
+      const int64_t jd = r + diag_offset;
+      const float wd = __ldg(w_diag + r) * scale;
+      if (jd >= 0 && jd < N && wd != 0.f) {
+        const uint2 u = ld_stream_u2(B + jd * CE_K + lane * 4);
+        const float2 x = unpack_bf16(u.x), y = unpack_bf16(u.y);
+        o.x = fmaf(wd, x.x, o.x); o.y = fmaf(wd, x.y, o.y); o.z = fmaf(wd, y.x, o.z); o.w = fmaf(wd, y.y, o.w);
+      }
+    }
+    *reinterpret_cast<float4*>(dA + r * CE_K + lane * 4) = o;
+  }
+}
+
 // ================================================================================ backward kernel
 // One pass computes out[r,:] = out_scale * sum_c coef(r,c) * X[c,:] for the rows r of the row side.
 //   pass A (TRANSPOSED = false): rows = A rows i, cols = B rows j, coef = dS_ij, lse/w per ROW  -> dA
@@ -843,6 +1104,7 @@ __global__ void ce_fwd_finalize(int64_t M, int nsplit, const float* __restrict__
 template <int MODE, bool TRANSPOSED>
 __global__ void __launch_bounds__(CE_THREADS, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const CeParams p) {
+  if (p.skip_if && __ldg(p.skip_if) != 0.f) return;      // (uniform) the forward already produced this side: ce_ga_kernel
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                                       // 1 x 32 KB (row-side operand of the item)
@@ -1056,9 +1318,10 @@ __global__ void ce_prep_kernel(const float* __restrict__ bias, int64_t n, float 
   }
 }
 
-__global__ void ce_bwd_reduce(const float* __restrict__ part, int nsplit, int64_t n4, float* __restrict__ out) {
+__global__ void ce_bwd_reduce(const float* __restrict__ part, int nsplit, int64_t n4, float* __restrict__ out,
+                              const float* __restrict__ skip_if) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
+  if (i >= n4 || (skip_if && __ldg(skip_if) != 0.f)) return;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < nsplit; ++k) {
     const float4 v = *reinterpret_cast<const float4*>(part + ((int64_t)k * n4 + i) * 4);
@@ -1254,12 +1517,14 @@ static int launch_bwd_pass(const rs_ce_problem* p, int mode, const CeParams& k, 
   return RS_OK;
 }
 
-extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* w_lse, const float* w_diag,
-                         const float* w_pos, float* dA, float* dB, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+static int ce_bwd_impl(const rs_ce_problem* p, const float* lse, const float* w_lse, const float* w_diag,
+                       const float* w_pos, const float* g_parts, const float* g_info, float* dA, float* dB,
+                       void* workspace, size_t workspace_bytes, void* stream) {
   int rc = ce_validate(p);
   if (rc != RS_OK) return rc;
   if (!lse || !w_lse || !workspace || (!dA && !dB)) return RS_ERR_BAD_ARG;
+  if ((g_parts != nullptr) != (g_info != nullptr)) return RS_ERR_BAD_ARG;
+  if (g_parts && ((p->flags & RS_CE_SUPCON) || p->ab_dtype != RS_BF16)) return RS_ERR_UNSUPPORTED;
   if (workspace_bytes < rs_ce_workspace_bytes(p)) return RS_ERR_WORKSPACE;
   const int mode = ce_mode(p);
   float* wmax = (float*)((char*)workspace + rs_ce_workspace_bytes(p) - 512);
@@ -1285,10 +1550,18 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.out_scale = p->scale;
     k.wmax = wmax;
     k.tune = wmax + 4;
+    k.skip_if = g_info ? g_info + 1 : nullptr;      // G valid -> this pass and its reduction return at once
     if ((rc = launch_bwd_pass<false>(p, mode, k, mapA, mapB, pl.grid, st)) != RS_OK) return rc;
     const int64_t n4 = p->M * CE_K / 4;
-    ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dA);
+    ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dA, k.skip_if);
     RS_LAUNCH_CHECK();
+    if (g_parts) {
+      // row side from the forward's G: dA = scale * (w / l) * G  (+ the label term); same split layout as pass A
+      const int64_t warps = p->M < (int64_t)RS_NUM_SMS * 64 ? p->M : (int64_t)RS_NUM_SMS * 64;
+      ce_ga_kernel<<<(int)((warps + 7) / 8), 256, 0, st>>>(g_parts, pl.nsplit, p->M, p->N, g_info, lse, w_lse, w_diag,
+                                                           (const uint16_t*)p->b, ce_diag_offset(p), p->scale, dA);
+      RS_LAUNCH_CHECK();
+    }
   }
   if (dB) {      // pass B: rows = B, cols = A (transposed roles)
     const CePlan pl = CE_BWD_PLAN(p->N, p->M);
@@ -1306,8 +1579,74 @@ extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* 
     k.tune = wmax + 4;
     if ((rc = launch_bwd_pass<true>(p, mode, k, mapB, mapA, pl.grid, st)) != RS_OK) return rc;
     const int64_t n4 = p->N * CE_K / 4;
-    ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dB);
+    ce_bwd_reduce<<<(int)((n4 + 255) / 256), 256, 0, st>>>(k.part_out, pl.nsplit, n4, dB, nullptr);
     RS_LAUNCH_CHECK();
   }
+  return RS_OK;
+}
+
+extern "C" int rs_ce_bwd(const rs_ce_problem* p, const float* lse, const float* w_lse, const float* w_diag,
+                         const float* w_pos, float* dA, float* dB, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return ce_bwd_impl(p, lse, w_lse, w_diag, w_pos, nullptr, nullptr, dA, dB, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rs_ce_bwd_from_grad(const rs_ce_problem* p, const float* lse, const float* w_lse, const float* w_diag,
+                                   const float* g_parts, const float* g_info, float* dA, float* dB, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!g_parts || !g_info) return RS_ERR_BAD_ARG;
+  return ce_bwd_impl(p, lse, w_lse, w_diag, nullptr, g_parts, g_info, dA, dB, workspace, workspace_bytes, stream);
+}
+
+// ---- forward that also accumulates the unnormalised row-side gradient (ce_fwdg_kernel)
+extern "C" size_t rs_ce_fwd_grad_bytes(const rs_ce_problem* p) {
+  if (ce_validate(p) != RS_OK) return 0;
+  const CePlan pl = CE_BWD_PLAN(p->M, p->N);
+  return (size_t)pl.nsplit * p->M * CE_K * sizeof(float);
+}
+
+extern "C" int rs_ce_fwd_grad(const rs_ce_problem* p, float* lse, float* diag, float* g_parts, float* g_info,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ce_validate(p);
+  if (rc != RS_OK) return rc;
+  if (!lse || !diag || !g_parts || !g_info || !workspace) return RS_ERR_BAD_ARG;
+  const int mode = ce_mode(p);
+  if (mode == MODE_SUPCON || p->ab_dtype != RS_BF16) return RS_ERR_UNSUPPORTED;
+  // masked entries must carry exactly zero softmax mass (masked_fill gives them no gradient): -inf masks only
+  if ((p->key_a_row || p->key_b_row || (p->flags & RS_CE_DIAG_MASK)) && p->mask_value != -INFINITY) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_ce_workspace_bytes(p)) return RS_ERR_WORKSPACE;
+  const CePlan pl = CE_BWD_PLAN(p->M, p->N);
+  const size_t pb = al256((size_t)pl.nsplit * p->M * sizeof(float));      // 2 * pb <= the pass-A partial area
+  CUtensorMap mapA, mapB;
+  if ((rc = make_map(&mapA, p->a, p->M, p->ab_dtype)) != RS_OK) return rc;
+  if ((rc = make_map(&mapB, p->b, p->N, p->ab_dtype)) != RS_OK) return rc;
+  CeParams k = {};
+  fill_common(k, p, pl);
+  k.M = p->M; k.N = p->N;
+  k.col_bias = p->col_bias;
+  k.key_a_row = p->key_a_row; k.key_a_col = p->key_a_col;
+  k.key_b_row = p->key_b_row; k.key_b_col = p->key_b_col;
+  k.diag_offset = ce_diag_offset(p);
+  char* ws = (char*)workspace;
+  k.part_m = (float*)ws; k.part_l = (float*)(ws + pb);
+  k.diag_out = diag;
+  k.part_out = g_parts;
+  k.tune = g_info;              // [0] = C, [1] = fixed-offset mode held (G valid), [3] = scale2 * bound
+  cudaStream_t st = (cudaStream_t)stream;
+  ce_prep_kernel<<<1, 1024, 0, st>>>(p->col_bias, p->N, p->scale * CE_LOG2E, p->logit_bound, g_info);
+  RS_LAUNCH_CHECK();
+  const size_t smem = ce_smem_bytes(true);
+#define LAUNCH_FWDG(MODE)                                                                                 \
+  do {                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(ce_fwdg_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                                  \
+    ce_fwdg_kernel<MODE><<<pl.grid, CE_THREADS, smem, st>>>(mapA, mapB, k);                               \
+  } while (0)
+  if (mode == MODE_PLAIN) LAUNCH_FWDG(MODE_PLAIN);
+  else LAUNCH_FWDG(MODE_GENERAL);
+  RS_LAUNCH_CHECK();
+  ce_fwd_finalize<<<(int)((p->M + 255) / 256), 256, 0, st>>>(p->M, pl.nsplit, k.part_m, k.part_l, nullptr, nullptr, lse,
+                                                             nullptr, nullptr);
+  RS_LAUNCH_CHECK();
   return RS_OK;
 }

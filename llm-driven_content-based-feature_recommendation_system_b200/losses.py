@@ -30,6 +30,9 @@ from . import ops
 COMPUTE_DTYPE = torch.bfloat16
 UNIT_NORM_BOUND = 1.0 + 2.0 ** -6        # |<a, b>| of 16-bit-rounded unit rows
 NEG_INF = float("-inf")
+# True: when the row operand needs a gradient the forward pass also accumulates its unnormalised gradient on the tensor
+# cores (ops.ce_fwd_grad, "flash" form) and the backward runs one tensor-core pass (dB side) instead of two.
+FUSE_ROW_GRAD = True
 
 
 def _operand_dtype(*ts) -> torch.dtype:
@@ -50,16 +53,25 @@ class _FusedSoftmax(torch.autograd.Function):
     def forward(ctx, a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value,
                 flags, dtype, logit_bound):
         a16, b16 = a.detach().to(dtype).contiguous(), b.detach().to(dtype).contiguous()
-        lse, diag, pos_sum, pos_cnt = L.direct.ce_fwd(a16, b16, scale, col_bias, key_a_row, key_a_col, key_b_row,
+        g_parts = g_info = None
+        if FUSE_ROW_GRAD and ctx.needs_input_grad[0] and ops.ce_fwd_grad_supported(
+                a16, flags, mask_value, logit_bound, key_a_row is not None or key_b_row is not None):
+            # the forward also accumulates G = sum_j e_ij b_j: the backward's dA is then a row scaling (rs_ce_fwd_grad)
+            lse, diag, g_parts, g_info = L.direct.ce_fwd_grad(a16, b16, scale, col_bias, key_a_row, key_a_col,
+                                                              key_b_row, key_b_col, diag_offset, mask_value, flags,
+                                                              logit_bound)
+            pos_sum, pos_cnt = lse.new_empty(0), lse.new_empty(0)
+        else:
+            lse, diag, pos_sum, pos_cnt = L.direct.ce_fwd(a16, b16, scale, col_bias, key_a_row, key_a_col, key_b_row,
                                                           key_b_col, diag_offset, mask_value, flags, logit_bound)
-        ctx.save_for_backward(a16, b16, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, lse)
+        ctx.save_for_backward(a16, b16, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, lse, g_parts, g_info)
         ctx.meta = (scale, diag_offset, mask_value, flags, a.dtype, b.dtype, logit_bound)
         ctx.mark_non_differentiable(pos_cnt)
         return lse, diag, pos_sum, pos_cnt
 
     @staticmethod
     def backward(ctx, g_lse, g_diag, g_pos, _g_cnt):
-        a16, b16, col_bias, kar, kac, kbr, kbc, lse = ctx.saved_tensors
+        a16, b16, col_bias, kar, kac, kbr, kbc, lse, g_parts, g_info = ctx.saved_tensors
         scale, diag_offset, mask_value, flags, adt, bdt, logit_bound = ctx.meta
         M = a16.shape[0]
         zeros = None
@@ -69,7 +81,7 @@ class _FusedSoftmax(torch.autograd.Function):
         w_pos = g_pos.float().contiguous() if (g_pos is not None and flags & L.RS_CE_SUPCON) else None
         w_diag = None if g_diag is None else g_diag.float().contiguous()
         dA, dB = L.direct.ce_bwd(a16, b16, scale, col_bias, kar, kac, kbr, kbc, diag_offset, mask_value, flags,
-                                     lse, g_lse.float().contiguous(), w_diag, w_pos, logit_bound)
+                                     lse, g_lse.float().contiguous(), w_diag, w_pos, logit_bound, g_parts, g_info)
         return (dA.to(adt), dB.to(bdt)) + (None,) * 11
 
 

@@ -535,12 +535,49 @@ def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_of
     return [f(M), f(M), f(n), f(n)]
 
 
+@torch.library.custom_op("rs::ce_fwd_grad", mutates_args=())
+def ce_fwd_grad_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], key_a_row: Optional[Tensor],
+                   key_a_col: Optional[Tensor], key_b_row: Optional[Tensor], key_b_col: Optional[Tensor],
+                   diag_offset: int, mask_value: float, flags: int, logit_bound: float) -> List[Tensor]:
+    """Forward that also accumulates the row side of the backward (rs_ce_fwd_grad): [lse[M], diag[M], g_parts, g_info].
+    `g_parts` / `g_info` go to ce_bwd unchanged."""
+    L.require_cuda(a, b)
+    a, b, col_bias, keys = _ce_prepare(a, b, col_bias, [key_a_row, key_a_col, key_b_row, key_b_col])
+    M, dev = a.shape[0], a.device
+    lse = torch.empty(M, dtype=torch.float32, device=dev)
+    diag = torch.empty(M, dtype=torch.float32, device=dev)
+    p = _ce_problem(a, b, scale, col_bias, *keys, diag_offset, mask_value, flags, logit_bound)
+    g_parts = torch.empty(_lib.rs_ce_fwd_grad_bytes(p) // 4, dtype=torch.float32, device=dev)
+    g_info = torch.empty(8, dtype=torch.float32, device=dev)
+    ws = L.workspace(_lib.rs_ce_workspace_bytes(p), dev)
+    L.check(_lib.rs_ce_fwd_grad(p, L.ptr(lse), L.ptr(diag), L.ptr(g_parts), L.ptr(g_info), L.ptr(ws), ws.numel(),
+                                L.stream()), "rs_ce_fwd_grad")
+    return [lse, diag, g_parts, g_info]
+
+
+@ce_fwd_grad_op.register_fake
+def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags, logit_bound):
+    M = a.shape[0]
+    f = lambda k: a.new_empty(k, dtype=torch.float32)
+    return [f(M), f(M), f(M * a.shape[1]), f(8)]
+
+
+def ce_fwd_grad_supported(a: Tensor, flags: int, mask_value: float, logit_bound: float, has_keys: bool) -> bool:
+    """Host-side preconditions of rs_ce_fwd_grad (the device decides the rest, see g_info[1])."""
+    if a.dtype != torch.bfloat16 or logit_bound <= 0.0 or (flags & L.RS_CE_SUPCON):
+        return False
+    return mask_value == float("-inf") or not (has_keys or (flags & L.RS_CE_DIAG_MASK))
+
+
 @torch.library.custom_op("rs::ce_bwd", mutates_args=())
 def ce_bwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], key_a_row: Optional[Tensor],
               key_a_col: Optional[Tensor], key_b_row: Optional[Tensor], key_b_col: Optional[Tensor],
               diag_offset: int, mask_value: float, flags: int, lse: Tensor, w_lse: Tensor,
-              w_diag: Optional[Tensor], w_pos: Optional[Tensor], logit_bound: float = 0.0) -> List[Tensor]:
-    """Returns [dA[M,K], dB[N,K]] in fp32 for dS = w_lse*softmax + w_diag*[diag] + w_pos*[positive]."""
+              w_diag: Optional[Tensor], w_pos: Optional[Tensor], logit_bound: float = 0.0,
+              g_parts: Optional[Tensor] = None, g_info: Optional[Tensor] = None) -> List[Tensor]:
+    """Returns [dA[M,K], dB[N,K]] in fp32 for dS = w_lse*softmax + w_diag*[diag] + w_pos*[positive].
+    With `g_parts` / `g_info` (outputs of ce_fwd_grad for the same problem) dA is a row scaling of the forward's G and
+    only the dB side runs on the tensor cores (rs_ce_bwd_from_grad)."""
     a, b, col_bias, keys = _ce_prepare(a, b, col_bias, [key_a_row, key_a_col, key_b_row, key_b_col])
     dev = a.device
     dA = torch.empty(a.shape, dtype=torch.float32, device=dev)
@@ -549,6 +586,11 @@ def ce_bwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], ke
     ws = L.workspace(_lib.rs_ce_workspace_bytes(p), dev)
     w_diag_ = None if w_diag is None else _f32(w_diag, "w_diag")
     w_pos_ = None if w_pos is None else _f32(w_pos, "w_pos")
+    if g_parts is not None:
+        L.check(_lib.rs_ce_bwd_from_grad(p, L.ptr(_f32(lse, "lse")), L.ptr(_f32(w_lse, "w_lse")), L.ptr(w_diag_),
+                                         L.ptr(g_parts), L.ptr(g_info), L.ptr(dA), L.ptr(dB), L.ptr(ws), ws.numel(),
+                                         L.stream()), "rs_ce_bwd_from_grad")
+        return [dA, dB]
     L.check(_lib.rs_ce_bwd(p, L.ptr(_f32(lse, "lse")), L.ptr(_f32(w_lse, "w_lse")), L.ptr(w_diag_), L.ptr(w_pos_),
                            L.ptr(dA), L.ptr(dB), L.ptr(ws), ws.numel(), L.stream()), "rs_ce_bwd")
     return [dA, dB]
@@ -556,7 +598,7 @@ def ce_bwd_op(a: Tensor, b: Tensor, scale: float, col_bias: Optional[Tensor], ke
 
 @ce_bwd_op.register_fake
 def _(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags, lse, w_lse,
-      w_diag, w_pos, logit_bound=0.0):
+      w_diag, w_pos, logit_bound=0.0, g_parts=None, g_info=None):
     return [a.new_empty(a.shape, dtype=torch.float32), b.new_empty(b.shape, dtype=torch.float32)]
 
 

@@ -16,6 +16,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 LOSS_TOL = {torch.bfloat16: 2e-2, torch.float16: 3e-3}
 GRAD_TOL = {torch.bfloat16: 3e-2, torch.float16: 5e-3}
+# relative Frobenius norm of the gradient error (a max-norm bound alone would hide a systematic error in the many
+# small-magnitude rows).  The fixtures are fp32 end to end; rounding the unit-norm operands to 16 bits perturbs every
+# logit by ~ 2^-9 * 10 (bf16) and hence every softmax weight by ~ 2 % (bf16) / 0.25 % (fp16), independently per entry.
+FRO_TOL = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
 
 
 @pytest.fixture(scope="module")
@@ -42,6 +46,7 @@ def _cmp(got, want, dtype):
     for g, w in zip(grads, want["grads"]):
         assert torch.isfinite(g).all()
         assert (g - w).abs().max() <= GRAD_TOL[dtype] * w.abs().max() + 1e-7, ((g - w).abs().max(), w.abs().max())
+        assert (g - w).norm() <= FRO_TOL[dtype] * w.norm() + 1e-7, ((g - w).norm(), w.norm())
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
