@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="only the resident-input timed loop (for ncu runs)")
+    ap.add_argument("--tok-bucket", type=int, default=2048, help="shape bucket of the main-loss rows (1 GPU)")
+    ap.add_argument("--col-bucket", type=int, default=512, help="shape bucket of the distinct-target columns (1 GPU)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs' kernel-level numbers")
     return ap.parse_args()
 
 
@@ -199,6 +202,286 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return pk.get("hbm_gbs", 6650.0), pk.get("bf16_tflops_sustained", 1400.0), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+def _kernel_table(prof, nprof, P, D, step_ms):
+    """per-C-ABI-call CUDA-event times of `nprof` eager steps -> {name: {...}}, plus the fused-softmax aggregate.
+    Algorithmic work: SURVEY.md 8(d) -- 2*M*N*128 flops per contraction, FOUR contractions per loss (S forward, one S
+    recompute, dU, dV); the fused forward executes two of them (S, P@B), the backward the other two (S, dS^T@A)."""
+    hbm_peak, tf_peak, peak_src = _peaks()
+    agg = {}
+    for name, s, e, extra in prof:
+        a = agg.setdefault(name, dict(ms=0.0, calls=0, work=0.0))
+        a["ms"] += s.elapsed_time(e)
+        a["calls"] += 1
+        a["work"] += extra
+    kernels = {}
+    ce = dict(ms=0.0, flops=0.0)
+    for name, a in agg.items():
+        per_step_ms = a["ms"] / nprof
+        k = dict(ms_per_step=round(per_step_ms, 4), calls_per_step=a["calls"] / nprof)
+        if name in ("rs_ce_fwd", "rs_ce_bwd", "rs_ce_fwd_grad", "rs_ce_bwd_from_grad"):
+            k.update(bound="tensor", unit="TFLOP/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e12, peak=tf_peak)
+            ce["ms"] += per_step_ms
+            ce["flops"] += a["work"] / nprof
+        elif name == "rs_seq_front_fwd":
+            # per position: base bf16 + the item-id row fp32 + out bf16 + 3 ids (time / position rows: 12- and
+            # 51-row tables, cache resident, not counted)
+            by = P * (D * 2 + D * 4 + D * 2 + 3 * 8) * a["calls"] / nprof
+            k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
+        elif name == "rs_seq_front_bwd":
+            by = P * (D * 2 + 8) * a["calls"] / nprof          # one pass over dX (bf16) + time ids
+            k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
+        elif name == "rs_segment_reduce_rows":
+            k.update(bound="hbm", unit="GB/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
+        if "achieved" in k:
+            k["frac"] = k["achieved"] / k["peak"]
+        kernels[name] = k
+    roof = None
+    if ce["ms"] > 0:
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("fused_softmax")
+        except Exception:
+            pass
+        ach = ce["flops"] / (ce["ms"] * 1e-3) / 1e12
+        roof = dict(kernel="fused softmax (ce_fwdg_kernel + ce_bwd_kernel + ce_fwd_kernel: all rs_ce_* calls of a step)",
+                    bound="tensor", achieved=ach, peak=tf_peak, unit="TFLOP/s", frac=ach / tf_peak, traffic=traffic,
+                    peak_source=peak_src, ms_per_step=round(ce["ms"], 4), share_of_step=ce["ms"] / step_ms,
+                    accounting="4 contractions of 2*M*N*128 flops per loss (SURVEY 8d); executed = algorithmic")
+    return kernels, roof
+
+
+def _cuda_timed(n, fn, barrier, dev, world):
+    import torch.distributed as dist
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h0 = time.perf_counter()
+    for i in range(n):
+        fn(i)
+    host_ms = (time.perf_counter() - h0) * 1e3 / max(n, 1)       # time to ENQUEUE a step (launch-bound if ~= ms)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), host_ms
+
+
+def run_single(args, rs, dev):
+    """N = 1: device-indexed batches, one captured graph per shape bucket, every timed step on a batch no replay has
+    seen before."""
+    syn, L, tr = rs.synthetic, rs._lib, rs.train
+    lib = L.load()
+    torch.manual_seed(42)
+    B, SL = args.batch, args.seq_len
+    n_rows = syn.N_ITEMS + 1
+    model = rs.SASRecUserTower(syn.tower_args(max_len=SL)).to(dev).train()
+    item = rs.SASRecItemTower(syn.N_ITEMS, 128, syn.log_q(syn.N_ITEMS)).to(dev)
+    lookup = syn.pretrained_table(syn.N_ITEMS).to(dev)
+    item.init_from_pretrained(lookup)
+    params = list(model.parameters()) + list(item.parameters())
+    use_graph = bool(args.cuda_graph)
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
+
+    def step(b):
+        return tr.two_tower_step(model, item, b, lookup, opt, loss_scope="all", amp_dtype=torch.bfloat16, columns="unique")
+
+    bs = tr.BucketedStep(step, B, SL, n_rows, dev, use_graph=use_graph, tok_q=args.tok_bucket, col_q=args.col_bucket)
+
+    # ---- the batches: all distinct (seed 42 + i).  value run: warm-up + steps; e2e run: warm-up + steps more.
+    W = max(args.warmup, 3)
+    n_val, n_e2e = W + args.steps, (0 if args.minimal else W + args.steps)
+    n_all = n_val + n_e2e
+    t0 = time.perf_counter()
+    host = [tr.FlatBatch(B, SL, pin=True).fill(syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + i)) for i in range(n_all)]
+    gen_s = time.perf_counter() - t0
+    resident = [tr.FlatBatch(B, SL, device=dev).copy_(host[i]) for i in range(n_val)]
+    # loader metadata of the resident batches: their shape bucket (device pre-pass, read back before the timed region)
+    metas = torch.stack([bs.counts(fb) for fb in resident]).cpu()
+    keys = [bs.bucket(int(m[0]), int(m[2])) for m in metas]
+    # capture every bucket the VALUE run needs on a batch that no timed step uses: extra batches (seeds beyond n_all)
+    # are drawn until each needed bucket has been met (or 48 tries)
+    # (the e2e run's batches stay on the host until their step; their buckets are computed here on the host only to
+    # capture the graphs up front -- a long run has met each of its few buckets within its first steps -- the timed
+    # pipeline itself picks the bucket from the device counts)
+    def host_key(fb):
+        valid = ~fb.views["padding_mask"]
+        return bs.bucket(int(valid.sum()), int(torch.unique(fb.views["target_ids"][valid]).numel()))
+    e2e_keys = [host_key(host[n_val + j]) for j in range(n_e2e)]
+    need, tries, captured_on_timed = set(keys) | set(e2e_keys), 0, 0
+    stage_fb = tr.FlatBatch(B, SL, pin=True)
+    while need - set(bs.graphs) and use_graph and tries < 48:
+        stage_fb.fill(syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + n_all + tries))
+        tries += 1
+        bs.raw.copy_(stage_fb, non_blocking=False)
+        m = bs.counts(bs.raw).cpu()
+        k = bs.bucket(int(m[0]), int(m[2]))
+        if k in need and k not in bs.graphs:
+            bs.ensure(k)
+    for i, k in enumerate(keys):                     # buckets no extra batch fell into: capture on the batch itself
+        if use_graph and k not in bs.graphs:
+            bs.raw.copy_(resident[i])
+            bs.ensure(k)
+            captured_on_timed += i >= W
+    for j, k in enumerate(e2e_keys):
+        if use_graph and k not in bs.graphs:
+            bs.raw.copy_(host[n_val + j], non_blocking=False)
+            bs.ensure(k)
+            captured_on_timed += j >= W
+    per_step_launches = max((g_.launches for g_ in bs.graphs.values()), default=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    last = {}
+
+    def run_resident(i):
+        bs.raw.copy_(resident[i])                    # device -> the graphs' static inputs (one 41 MB copy)
+        last["loss"] = bs.run(keys[i])
+
+    for i in range(W):
+        run_resident(i)
+    launches0 = lib.rs_launch_count()
+    with ClockSampler(dev.index or 0) as clk:
+        ms, host_ms = _cuda_timed(args.steps, lambda i: run_resident(W + i), barrier, dev, 1)
+    launches = (per_step_launches * args.steps) if use_graph else (lib.rs_launch_count() - launches0)
+    total, main, cl = [float(x) for x in last["loss"]]
+    assert all(map(lambda v: v == v and abs(v) < 1e6, (total, main, cl))), f"non-finite loss {total, main, cl}"
+    chk = tr.check_index(bs.index[keys[W + args.steps - 1]])          # overflow / malformed-batch flags of the last step
+    value = B * args.steps / (ms * 1e-3)
+    if args.minimal:
+        print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)), flush=True)
+        return
+
+    # ---- end to end: pinned host batch -> device (one copy, on a copy stream, one step ahead) -> bucket choice from the
+    # device counts -> replay -> losses read back, EVERY step, each on a batch nothing has seen before
+    copy_stream = torch.cuda.Stream()
+    staging = [tr.FlatBatch(B, SL, device=dev) for _ in range(2)]
+    meta_dev = [torch.zeros(8, dtype=torch.int32, device=dev) for _ in range(2)]
+    meta_host = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+    staged, consumed = {}, {}
+    late_captures = []
+
+    def stage(j):                 # H2D of batch j + its counts, on the copy stream
+        slot = j % 2
+        if slot in consumed:
+            copy_stream.wait_event(consumed[slot])               # the step that read this staging slot has copied it out
+        with torch.cuda.stream(copy_stream):
+            staging[slot].copy_(host[n_val + j])
+            bs.counts(staging[slot], meta_dev[slot])
+            meta_host[slot].copy_(meta_dev[slot], non_blocking=True)
+            staged[j] = torch.cuda.Event()
+            staged[j].record(copy_stream)
+
+    def e2e_step(j):
+        if j not in staged:
+            stage(j)
+        ev = staged.pop(j)
+        ev.synchronize()                                         # issued one step ago: complete in steady state
+        slot = j % 2
+        key = bs.bucket(int(meta_host[slot][0]), int(meta_host[slot][2]))
+        torch.cuda.current_stream().wait_event(ev)
+        bs.raw.copy_(staging[slot])
+        consumed[slot] = torch.cuda.Event()
+        consumed[slot].record()
+        if use_graph and key not in bs.graphs:                   # a bucket met for the first time: capture (then replay)
+            late_captures.append(j)
+            bs.ensure(key)
+        t, m, c = bs.run(key)
+        if j + 1 < n_e2e:
+            stage(j + 1)
+        last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
+
+    for j in range(W):
+        e2e_step(j)
+    n_late_warm = len(late_captures)
+    ms_e2e, _ = _cuda_timed(args.steps, lambda i: e2e_step(W + i), barrier, dev, 1)
+    h2d_bytes = host[0].nbytes
+    e2e = dict(value=B * args.steps / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d_bytes,
+               d2h_bytes_per_step=12 + 32, ms_per_step=ms_e2e / args.steps,
+               graph_captures_inside_timed_region=len(late_captures) - n_late_warm)
+
+    # ---- loader-stage cost on the device, per batch: counts pre-pass and the index build (the latter runs INSIDE every
+    # timed step); and the same index on the host (torch nonzero / unique / cumsum: what round 1 did outside the timed region)
+    def ev_time(fn, n=10):
+        fn()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / n
+    k0 = keys[0]
+    bs.raw.copy_(resident[0])
+    idx0 = rs.ops.batch_index_alloc(B, SL, k0[0], k0[1], dev)
+    counts_ms = ev_time(lambda: bs.counts(bs.raw))
+    build_ms = ev_time(lambda: tr.device_index(bs.raw.views, n_rows, k0[0], k0[1], out=idx0))
+    th = time.perf_counter()
+    tr.add_host_index({k: v for k, v in host[0].views.items()})
+    host_index_ms = (time.perf_counter() - th) * 1e3
+    loader = dict(device_counts_ms_per_batch=round(counts_ms, 4), device_index_build_ms_per_batch=round(build_ms, 4),
+                  host_index_ms_per_batch_for_comparison=round(host_index_ms, 2),
+                  note="index build is inside every timed step (value and e2e); counts pre-pass is inside e2e")
+
+    # ---- per-kernel pass: CUDA events around every C-ABI call of two EAGER steps, on the launching stream
+    L.PROFILE = []
+    nprof = 2
+    for i in range(nprof):
+        bs.raw.copy_(resident[i])
+        bs._run_eager(keys[i])
+    torch.cuda.synchronize()
+    prof, L.PROFILE = L.PROFILE, None
+    grid_cap = int(bs.index[keys[0]]["fold_inv1"].numel())
+    kernels, roof = _kernel_table(prof, nprof, grid_cap, 128, ms / args.steps)
+
+    extra = None if args.no_extra else bench_extra(rs, dev)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_step_rate(args, 2, 1, syn)
+
+    buckets = {}
+    for k in keys[W:]:
+        buckets[f"{k[0]}x{k[1]}"] = buckets.get(f"{k[0]}x{k[1]}", 0) + 1
+    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic",
+                config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B, global_batch=B,
+                            seq_len=SL, d_model=128, n_items=syn.N_ITEMS, loss_scope="all",
+                            loss_rows=chk["tokens"], loss_cols=chk["columns"], loss_columns="unique",
+                            parallelism="1 GPU",
+                            batches=f"every step (value and e2e) consumes a batch no earlier step or capture has seen "
+                                    f"({n_all} distinct synthetic batches, seeds 42..{41 + n_all}; "
+                                    f"{captured_on_timed} timed batches doubled as capture batches)",
+                            index="built on the device inside every step (rs_batch_index_build); host sends the collated "
+                                  "[B, L] tensors only",
+                            cuda_graph=(f"one captured graph per shape bucket (rows % {args.tok_bucket}, columns % "
+                                        f"{args.col_bucket}): {len(bs.graphs)} graphs, buckets of the timed steps {buckets}"
+                                        if use_graph else "off (eager launches)"),
+                            l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), fresh batch per step"),
+                e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(),
+                roofline=roof, cpu_baseline=cpu, loader=loader, kernels=kernels, extra=extra,
+                loss=dict(total=total, main=main, cl=cl), host_batch_generation_s=round(gen_s, 1))
+    if extra:
+        line["gather_frac"] = extra.get("gather_frac")
+        line["scatter_frac"] = extra.get("scatter_frac")
+    print(json.dumps(line), flush=True)
+
+
+def bench_extra(rs, dev):
+    """Driver-visible numbers for the other BASELINE configs (filled in below)."""
+    return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,6 +491,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rs = importlib.import_module(PKG)          # raises if librs_twotower.so is missing: no fallback
+    if world == 1 and args.loss_scope == "all" and args.columns == "unique":
+        return run_single(args, rs, dev)
+    return run_multi(args, rs, dev, rank, world, local)
+
+
+def run_multi(args, rs, dev, rank, world, local):
+    import torch.distributed as dist
     syn, L = rs.synthetic, rs._lib
     lib = L.load()
     torch.manual_seed(42)
@@ -220,8 +510,7 @@ def run_ours(args):
     sharded = world > 1 and args.parallelism == "sharded"
     trainer = rs.train.ShardedTwoTower(model, item) if sharded else None      # re-shards the two item tables in place
     params = list(model.parameters()) + list(item.parameters())
-    use_graph = bool(args.cuda_graph) and world == 1      # N > 1: eager (two 2-GPU trials with the NCCL exchanges captured hung;
-                                                          # tools/nccl_graph_probe.py: plain collectives do capture and replay)
+    use_graph = bool(args.cuda_graph) and world == 1
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
 
     def sync_grads():
@@ -242,8 +531,6 @@ def run_ours(args):
         syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + 1000 * rank + i)).items()} for i in range(pool)]
     resident = [rs.train.prepare_batch(hb, dev) for hb in host]
     if sharded:
-        # loader-stage routing of every batch's item ids (split sizes + the id exchange), once per batch; the host
-        # copy keeps the position order pinned (it is an input like the ids), the requested rows live on their owner
         resident = [trainer.plan(b, "catalog" if args.columns == "catalog" else "unique") for b in resident]
         plan_keys = [k for k in ("lookup_plan", "col_plan", "col_item_ids", "col_counts", "pos_col") if k in resident[0]]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -265,53 +552,31 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, fn):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        h0 = time.perf_counter()
-        for i in range(n):
-            fn(i)
-        timed.host_ms = (time.perf_counter() - h0) * 1e3 / max(n, 1)     # time to ENQUEUE a step (launch-bound if ~= ms)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    # ---- resident-input run: the headline `value`
     last = {}
     graphs = None
     if use_graph:
-        # one captured graph per pooled batch (shapes are data dependent); counting our launches at capture time
         graphs = [rs.train.GraphedStep(step, rb) for rb in resident]
-        per_step_launches = max(g_.launches for g_ in graphs)                     # counted while capturing
+        per_step_launches = max(g_.launches for g_ in graphs)
         run = lambda i: graphs[i % pool].replay()
     else:
         run = lambda i: step(resident[i % pool])
-    # eager mode (N > 1): every pooled batch has its own shapes, the caching allocator and the per-shape library
-    # heuristics settle after each has been seen a few times (host enqueue 29 -> 17 ms/step on 2 GPUs): warm up at
-    # least 3 rounds over the pool.  Graph mode warmed each batch up while capturing.
     for i in range(max(args.warmup, 3 * pool) if world > 1 else args.warmup):
         last["loss"] = run(i)
     launches0 = lib.rs_launch_count()
     with ClockSampler(local) as clk:
-        ms = timed(args.steps, lambda i: last.__setitem__("loss", run(i)))
+        ms, host_ms = _cuda_timed(args.steps, lambda i: last.__setitem__("loss", run(i)), barrier, dev, world)
     launches = (per_step_launches * args.steps) if use_graph else (lib.rs_launch_count() - launches0)
-    host_ms = timed.host_ms
     total, main, cl = [float(x) for x in last["loss"]]
     assert all(map(lambda v: v == v and abs(v) < 1e6, (total, main, cl))), f"non-finite loss {total, main, cl}"
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end run: host batches in, losses out, every step
     copy_stream = torch.cuda.Stream() if use_graph else None
     staged, replayed = {}, {}
 
-    def stage(i):            # H2D of step i's inputs into ITS graph's static buffers, on the copy stream
+    def stage(i):
         g_ = graphs[i % pool]
         if i % pool in replayed:
-            copy_stream.wait_event(replayed[i % pool])            # that graph's previous replay has finished
+            copy_stream.wait_event(replayed[i % pool])
         with torch.cuda.stream(copy_stream):
             g_.load(host[i % pool])
             staged[i] = torch.cuda.Event()
@@ -319,9 +584,6 @@ def run_ours(args):
 
     def e2e_step(i):
         if use_graph:
-            # every step: H2D of its inputs (pinned host -> the graph's static buffers), replay, D2H of the losses.
-            # The copy of step i+1 is issued before step i's result is read back, so it overlaps step i's compute
-            # (a prefetching loader); pool >= 2 graphs means it never writes buffers a running replay reads.
             if i not in staged:
                 stage(i)
             torch.cuda.current_stream().wait_event(staged.pop(i))
@@ -331,78 +593,33 @@ def run_ours(args):
             stage(i + 1)
         else:
             b = rs.train.prepare_batch(host[i % pool], dev, non_blocking=True)
-            if sharded:      # the loader-stage products (made with collectives, they live on the device) ride along
+            if sharded:
                 b.update({k: resident[i % pool][k] for k in plan_keys})
             t, m, c = step(b)
-        last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
+        last["host_loss"] = (t.item(), m.item(), c.item())
 
     if args.minimal:
-        print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)), flush=True)
+        if rank == 0:
+            print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
-    for i in range(max(args.warmup, 3 * pool)):      # every pooled batch (each has its own shapes) seen 3x: allocator warm
+    for i in range(max(args.warmup, 3 * pool)):
         e2e_step(i)
-    ms_e2e = timed(args.steps, e2e_step)
+    ms_e2e, _ = _cuda_timed(args.steps, e2e_step, barrier, dev, world)
     e2e = dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d_bytes,
                d2h_bytes_per_step=12, ms_per_step=ms_e2e / args.steps)
 
-    # ---- per-kernel pass (rank 0): CUDA events around every C-ABI call, on the launching stream
     kernels, roof = {}, None
     nprof = 2
-    L.PROFILE = []                     # every rank runs these steps (they contain collectives); rank 0 reports
+    L.PROFILE = []
     for i in range(nprof):
         step(resident[i % pool])
     torch.cuda.synchronize()
     prof, L.PROFILE = L.PROFILE, None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak, tf_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured" if peaks else "fallback"
-        agg = {}
-        for name, s, e, extra in prof:
-            a = agg.setdefault(name, dict(ms=0.0, calls=0, work=0.0))
-            a["ms"] += s.elapsed_time(e)
-            a["calls"] += 1
-            a["work"] += extra
-        # U1 runs on the packed [R, 64] token grid when the batch carries it (train.add_host_index), else on [B, L]
         P = int(resident[0]["pk_item_ids"].numel()) if "pk_item_ids" in resident[0] else B * SL
-        D = 128
-        for name, a in agg.items():
-            per_step_ms = a["ms"] / nprof
-            k = dict(ms_per_step=round(per_step_ms, 4), calls_per_step=a["calls"] / nprof)
-            if name in ("rs_ce_fwd", "rs_ce_bwd"):
-                k.update(bound="tensor", unit="TFLOP/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e12,
-                         peak=tf_peak)
-            elif name == "rs_seq_front_fwd":
-                # per position: base bf16 + the item-id row fp32 + out bf16 + 3 ids (time / position rows: 12- and
-                # 51-row tables, cache resident, not counted)
-                by = P * (D * 2 + D * 4 + D * 2 + 3 * 8) * a["calls"] / nprof
-                k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
-            elif name == "rs_seq_front_bwd":
-                by = P * (D * 2 + 8) * a["calls"] / nprof          # one pass over dX (bf16) + time ids
-                k.update(bound="hbm", unit="GB/s", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
-            elif name == "rs_segment_reduce_rows":
-                k.update(bound="hbm", unit="GB/s", achieved=a["work"] / nprof / (per_step_ms * 1e-3) / 1e9, peak=hbm_peak)
-            if "achieved" in k:
-                k["frac"] = k["achieved"] / k["peak"]
-            kernels[name] = k
-        top = max((n for n in kernels if "achieved" in kernels[n]), key=lambda n: kernels[n]["ms_per_step"])
-        t = kernels[top]
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
-        except Exception:
-            pass
-        roof = dict(kernel=top, bound=t["bound"], achieved=t["achieved"], peak=t["peak"], unit=t["unit"],
-                    frac=t["frac"], traffic=traffic, peak_source=peak_src, ms_per_step=t["ms_per_step"],
-                    share_of_step=t["ms_per_step"] / (ms / args.steps))
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference_step_rate(args, 2, 1, syn)
+        kernels, roof = _kernel_table(prof, nprof, P, 128, ms / args.steps)
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -422,8 +639,8 @@ def run_ours(args):
                                 cuda_graph=("one captured graph per pooled batch (per-batch shapes), replayed" if use_graph
                                             else "off (eager launches)"),
                                 l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), 3 rotating batches"),
-                    e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof, cpu_baseline=cpu,
-                    kernels=kernels, loss=dict(total=total, main=main, cl=cl))
+                    e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(), roofline=roof,
+                    cpu_baseline=None, kernels=kernels, loss=dict(total=total, main=main, cl=cl))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

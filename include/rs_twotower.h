@@ -333,6 +333,58 @@ int rs_user_block_logits_bwd(const void* u, const void* cols, int dtype, const i
                              const float* col_bias, const float* own_lse, const float* g_pos, const float* g_own,
                              float* d_u, float* d_cols, void* stream);
 
+/* ------------------------------------------- N1: on-device batch assembly for the train step */
+
+/* The reference derives the step's index sets from the collated [B, L] batch inside the step with boolean indexing
+ * (`output_1[valid_mask]`, `target_ids[valid_mask]`, tower_code/v1_usertower_train.py:794-804; the dataset side is
+ * tower_code/v1_refine_usertower.py:204-306): nonzero + host synchronisation, data-dependent shapes.  This call builds
+ * every index the packed step consumes on the device, stream-ordered, into arrays of STATIC capacity (shape buckets):
+ * true counts in meta[], rows / columns beyond them are inert padding (row_weight 0, col_counts 0).
+ *   packed order     t = (valid time steps, batch-major);  T = meta[0]
+ *   U1 grid          [T valid | E positions `len-1` that are padding (v1_usertower_train.py:830 on a left-padded grid) | pad]
+ *   encoder tokens   [view-1 valid | view-2 valid | view-1 extras | view-2 extras | pad]  (2 * grid_cap slots; everything
+ *                    behind 2T is ONE zero-tail pseudo-sequence: cu_seqlens_2v has 2B + 2 entries, n_seq = 2B + 1)
+ *   columns          distinct valid targets in ascending id order, col_counts = multiplicity;  U = meta[2]
+ * meta[8] (int32): [0] T, [1] E, [2] U, [3] flags: 1 = a capacity was too small (outputs truncated, do not use),
+ *                  2 = an empty sequence, 4 = a target id outside [0, n_item_rows).
+ * padding_mask: [B, L] bytes, 1 = padding (torch.bool).  L <= 64.  grid_cap % 64 == 0, grid_cap >= tok_cap. */
+typedef struct {
+  const uint8_t* padding_mask;
+  const int64_t* item_ids;       /* [B, L] */
+  const int64_t* time_ids;       /* [B, L] */
+  const int64_t* target_ids;     /* [B, L] */
+  int64_t B, L, n_item_rows;
+  int64_t tok_cap;               /* capacity of the main-loss row arrays   (>= T) */
+  int64_t col_cap;               /* capacity of the column arrays          (>= U) */
+  int64_t grid_cap;              /* capacity of the U1 token grid          (>= T + E) */
+  int64_t* pk_item_ids;          /* [grid_cap] */
+  int64_t* pk_time_ids;          /* [grid_cap] */
+  int64_t* pk_pos_ids;           /* [grid_cap]  l + 1 (0 = padding slot) */
+  int64_t* pk_index_2v;          /* [2*grid_cap] U1 row of every encoder token */
+  int64_t* fold_inv1;            /* [grid_cap]  encoder slot of the view-1 copy of every U1 row */
+  int64_t* fold_inv2;            /* [grid_cap]  ... of the view-2 copy */
+  int32_t* cu_seqlens_2v;        /* [2B + 2] */
+  int32_t* row_cu;               /* [B + 1]  rows of every user among the main-loss rows */
+  int64_t* select_2v;            /* [tok_cap + 2B] encoder slots of: the main rows | DuoRec rows view 1 | view 2 */
+  int64_t* users_2v;             /* [tok_cap + 2B] row of the (2B-row, two-view) profile matrix for each of those */
+  int64_t* main_tgt;             /* [tok_cap] target item of every main row */
+  int64_t* last_tgt;             /* [B] target at the DuoRec position */
+  float* row_weight;             /* [tok_cap] 1/T for real rows, 0 for padding */
+  int64_t* col_item_ids;         /* [col_cap] */
+  float* col_counts;             /* [col_cap] */
+  int64_t* pos_col;              /* [tok_cap] column of every main row's target */
+  int32_t* meta;                 /* [8] */
+} rs_batch_index;
+size_t rs_batch_index_workspace_bytes(int64_t B, int64_t L, int64_t n_item_rows);
+int rs_batch_index_build(const rs_batch_index* d /*host*/, void* workspace, size_t workspace_bytes, void* stream);
+/* only the counts (meta[0..2] = T, E, U): what a loader needs to pick the shape bucket of a batch */
+int rs_batch_index_counts(const uint8_t* padding_mask, const int64_t* target_ids, int64_t B, int64_t L,
+                          int64_t n_item_rows, int32_t* meta, void* workspace, size_t workspace_bytes, void* stream);
+/* out[u,:] = x[i1[u],:] + x[i2[u],:]  (x, out in `dtype`; an index outside [0, n_src) contributes 0): folds the
+ * gradients of the two dropout views of a U1 row (fold_inv1 / fold_inv2) without a scatter. */
+int rs_gather_add2(const void* x, int dtype, const int64_t* i1, const int64_t* i2, int64_t n, int64_t n_src, int64_t dim,
+                   void* out, void* stream);
+
 /* ------------------------------------------------------- R1: top-k retrieval */
 
 /* ids/scores[b, 0..k) = top-k over items of <users[b,:], items[j,:]>, fp32, sorted by

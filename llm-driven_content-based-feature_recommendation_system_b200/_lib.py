@@ -24,11 +24,24 @@ _DT_INV = {v: k for k, v in _DT.items()}
 vp, i64, i32, f32, u64, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_size_t
 
 
+# output arrays of rs_batch_index, in struct order
+BATCH_INDEX_OUTPUTS = ("pk_item_ids", "pk_time_ids", "pk_pos_ids", "pk_index_2v", "fold_inv1", "fold_inv2", "cu_seqlens_2v",
+                       "row_cu", "select_2v", "users_2v", "main_tgt", "last_tgt", "row_weight", "col_item_ids", "col_counts",
+                       "pos_col", "meta")
+
+
 class CEProblem(C.Structure):
     """Mirror of rs_ce_problem."""
     _fields_ = [("a", vp), ("b", vp), ("ab_dtype", i32), ("M", i64), ("N", i64), ("K", i64), ("scale", f32),
                 ("col_bias", vp), ("key_a_row", vp), ("key_a_col", vp), ("key_b_row", vp), ("key_b_col", vp),
                 ("diag_offset", i64), ("mask_value", f32), ("flags", i32), ("logit_bound", f32)]
+
+
+class BatchIndex(C.Structure):
+    """Mirror of rs_batch_index."""
+    _fields_ = ([("padding_mask", vp), ("item_ids", vp), ("time_ids", vp), ("target_ids", vp), ("B", i64), ("L", i64),
+                 ("n_item_rows", i64), ("tok_cap", i64), ("col_cap", i64), ("grid_cap", i64)] +
+                [(n, vp) for n in BATCH_INDEX_OUTPUTS])
 
 
 # name -> (restype, argtypes); must list every function of include/rs_twotower.h
@@ -75,6 +88,10 @@ PROTOTYPES = {
     "rs_ce_fwd_grad_bytes": (sz, [C.POINTER(CEProblem)]),
     "rs_ce_fwd_grad": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_bwd_from_grad": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "rs_batch_index_workspace_bytes": (sz, [i64, i64, i64]),
+    "rs_batch_index_build": (i32, [C.POINTER(BatchIndex), vp, sz, vp]),
+    "rs_batch_index_counts": (i32, [vp, vp, i64, i64, i64, vp, vp, sz, vp]),
+    "rs_gather_add2": (i32, [vp, i32, vp, vp, i64, i64, i64, vp, vp]),
     "rs_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),
     "rs_retrieve_topk": (i32, [vp, i64, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
     "rs_mine_workspace_bytes": (sz, [i64, i64, i64]),

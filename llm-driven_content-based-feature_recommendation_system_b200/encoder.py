@@ -243,18 +243,22 @@ def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dro
 
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, index, w, b, eps, dropout_p, seed, out_dtype, fold=None):
+    def forward(ctx, x, index, w, b, eps, dropout_p, seed, out_dtype, fold=None, inv1=None, inv2=None):
         y, mean, rstd = L.direct.ln(x, index, w, b, eps, dropout_p, seed, out_dtype)
-        ctx.save_for_backward(x, index, w, mean, rstd)
+        ctx.save_for_backward(x, index, w, mean, rstd, inv1, inv2)
         ctx.meta = (dropout_p, seed)
         ctx.fold = fold
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, index, w, mean, rstd = ctx.saved_tensors
+        x, index, w, mean, rstd, inv1, inv2 = ctx.saved_tensors
         dx, dw, db = L.direct.ln_bwd(g, x, index, w, mean, rstd, *ctx.meta)
-        if index is not None and ctx.fold is not None:
+        if index is not None and inv1 is not None:
+            # every row of x is read by exactly two packed rows (inv1 / inv2: the two dropout views): the scatter-add
+            # is a gather of two rows (static shapes, deterministic)
+            dx = L.direct.gather_add2(dx, inv1, inv2)
+        elif index is not None and ctx.fold is not None:
             # index == [0..T) twice, then [T..T+E) twice (two dropout views of the same packed rows): the scatter-add
             # is two elementwise sums (deterministic, no atomics)
             T, E = ctx.fold
@@ -266,20 +270,26 @@ class _LayerNorm(torch.autograd.Function):
             dx = full
         elif index is not None:        # an index may repeat rows (one copy per dropout view): scatter-ADD
             dx = torch.zeros_like(x).index_add_(0, index, dx)
-        return dx, None, dw, db, None, None, None, None, None
+        return dx, None, dw, db, None, None, None, None, None, None, None
 
 
 def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, index: Optional[Tensor] = None,
-               dropout_p: float = 0.0, out_dtype: Optional[torch.dtype] = None, index_fold=None) -> Tensor:
+               dropout_p: float = 0.0, out_dtype: Optional[torch.dtype] = None, index_fold=None,
+               index_inv=None) -> Tensor:
     """dropout(LayerNorm(x[index])) for 128-wide rows; `index` (int64) packs rows on the way in.  `index_fold` = (T, E):
     the caller vouches that index == cat(arange(T), arange(T), T + arange(E), T + arange(E)) (train.add_host_index's
-    two-view layout), which turns the backward's scatter-add into two elementwise sums."""
+    two-view layout), which turns the backward's scatter-add into two elementwise sums.  `index_inv` = (inv1, inv2)
+    [len(x)] each: the caller vouches that row r of x is read by exactly the packed rows inv1[r] and inv2[r]
+    (ops.batch_index_build's fold_inv1 / fold_inv2): the scatter-add becomes a two-row gather, shapes static."""
     od = L.dt(out_dtype) if out_dtype is not None else L.dt(x)
     if index_fold is not None:
         T, E = index_fold
         assert index is not None and index.numel() == 2 * (T + E) and x.shape[0] >= T + E
+    inv1, inv2 = index_inv if index_inv is not None else (None, None)
+    if inv1 is not None:
+        assert index is not None and index.numel() == 2 * x.shape[0] and inv1.numel() == x.shape[0] == inv2.numel()
     return _LayerNorm.apply(x, index, weight, bias, float(eps), float(dropout_p), _seed() if dropout_p > 0 else 0, od,
-                            index_fold)
+                            index_fold, inv1, inv2)
 
 
 class _ResidualLN(torch.autograd.Function):

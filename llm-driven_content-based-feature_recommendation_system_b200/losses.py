@@ -156,7 +156,8 @@ def count_ids(ids: Tensor, n: int) -> Tensor:
 def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tensor, col_counts: Tensor,
                          target_ids: Tensor, pos_col: Tensor, own_cols: Optional[Tensor], log_q_tensor: Tensor,
                          temperature: float = 0.1, lambda_logq: float = 1.0, row_cu: Optional[Tensor] = None,
-                         max_rows_per_user: int = 0, unit_norm: bool = False) -> Tensor:
+                         max_rows_per_user: int = 0, unit_norm: bool = False,
+                         row_weight: Optional[Tensor] = None) -> Tensor:
     """C2 (tower_code/v1_refine_usertower.py:826-861) over the DISTINCT items of the batch.  In-batch columns with
     the same target item share the item row and the logQ, hence the logit, so the reference's [N, N] softmax
     equals an [N, U] softmax over distinct items with the batch multiplicities m_c folded into the column bias:
@@ -169,7 +170,10 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
     however many ranks contribute columns.  `col_counts` may hold zeros (absent items: bias = +inf).
     The same-user term: either `row_cu` (int32 [n_users+1], rows grouped by user, at most `max_rows_per_user` <= 64
     each -> one small dense block per user, ops.user_block_logits) or `own_cols[N, K]` = columns of the row's
-    user's targets, -1 = none (generic sparse path); both None: no same-user mask."""
+    user's targets, -1 = none (generic sparse path); both None: no same-user mask.
+    `row_weight` [N] (fp32): the loss is sum_i row_weight_i * loss_i instead of the mean -- the bucketed, device-built
+    batch index (ops.batch_index_build) pads rows and columns to static capacities: padding rows carry weight 0 (real
+    rows 1/N_true) and padding columns count 0 (bias +inf: no softmax mass)."""
     dtype = _operand_dtype(user_emb, col_rows)
     scale = 1.0 / temperature
     lq = (log_q_tensor[col_item_ids] * lambda_logq).float() if lambda_logq > 0.0 else None
@@ -192,6 +196,8 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
                                       compute_dtype=dtype)
             z = z - torch.exp(s_own - mx.unsqueeze(1)).sum(dim=1)
     lse = mx + torch.log(z.clamp_min(1e-30))
+    if row_weight is not None:
+        return ((lse - s_pos) * row_weight).sum()
     return (lse - s_pos).mean()
 
 

@@ -480,6 +480,77 @@ def _(a, b, idx, scale, key_row, key_col, g):
     return [a.new_empty(a.shape, dtype=torch.float32), b.new_empty(b.shape, dtype=torch.float32)]
 
 
+# ---- N1: on-device batch assembly ---------------------------------------------------------------
+def round_up(n: int, q: int) -> int:
+    return (int(n) + q - 1) // q * q
+
+
+def batch_index_counts(padding_mask: Tensor, target_ids: Tensor, n_item_rows: int, meta: Optional[Tensor] = None) -> Tensor:
+    """int32[8] device tensor: [0] valid time steps T, [1] extras E, [2] distinct valid targets U (rs_batch_index_counts):
+    what the loader needs to pick the shape bucket of a batch.  Stream-ordered, no synchronisation."""
+    L.require_cuda(padding_mask, target_ids)
+    if padding_mask.dtype != torch.bool:
+        raise TypeError("padding_mask must be a bool tensor (True = padding)")
+    pm, tg = padding_mask.contiguous(), _ids(target_ids)
+    B, SL = pm.shape
+    meta = torch.empty(8, dtype=torch.int32, device=pm.device) if meta is None else meta
+    ws = L.workspace(_lib.rs_batch_index_workspace_bytes(B, SL, n_item_rows), pm.device)
+    L.check(_lib.rs_batch_index_counts(L.ptr(pm), L.ptr(tg), B, SL, n_item_rows, L.ptr(meta), L.ptr(ws), ws.numel(),
+                                       L.stream()), "rs_batch_index_counts")
+    return meta
+
+
+def batch_index_alloc(B: int, SL: int, tok_cap: int, col_cap: int, device) -> dict:
+    """Static-shape output arrays of rs_batch_index_build for one shape bucket (tok_cap main rows, col_cap columns)."""
+    grid_cap = round_up(tok_cap + B, 64)                 # E <= B extras behind the T <= tok_cap valid tokens
+    i64 = lambda *s: torch.empty(*s, dtype=torch.int64, device=device)
+    return dict(pk_item_ids=i64(grid_cap // 64, 64), pk_time_ids=i64(grid_cap // 64, 64), pk_pos_ids=i64(grid_cap // 64, 64),
+                pk_index_2v=i64(2 * grid_cap), fold_inv1=i64(grid_cap), fold_inv2=i64(grid_cap),
+                cu_seqlens_2v=torch.empty(2 * B + 2, dtype=torch.int32, device=device),
+                row_cu=torch.empty(B + 1, dtype=torch.int32, device=device),
+                select_2v=i64(tok_cap + 2 * B), users_2v=i64(tok_cap + 2 * B), main_tgt=i64(tok_cap), last_tgt=i64(B),
+                row_weight=torch.empty(tok_cap, dtype=torch.float32, device=device), col_item_ids=i64(col_cap),
+                col_counts=torch.empty(col_cap, dtype=torch.float32, device=device), pos_col=i64(tok_cap),
+                meta=torch.empty(8, dtype=torch.int32, device=device))
+
+
+def batch_index_build(padding_mask: Tensor, item_ids: Tensor, time_ids: Tensor, target_ids: Tensor, n_item_rows: int,
+                      out: dict) -> dict:
+    """Fill `out` (from batch_index_alloc) for one collated batch: every index the packed two-view step consumes
+    (rs_batch_index_build; layout in include/rs_twotower.h).  Stream-ordered, static shapes: graph-capturable.
+    `out["meta"]` carries the true counts and the overflow flag."""
+    L.require_cuda(padding_mask, item_ids, time_ids, target_ids)
+    if padding_mask.dtype != torch.bool:
+        raise TypeError("padding_mask must be a bool tensor (True = padding)")
+    pm, it, tm, tg = padding_mask.contiguous(), _ids(item_ids), _ids(time_ids), _ids(target_ids)
+    B, SL = pm.shape
+    d = L.BatchIndex()
+    d.padding_mask, d.item_ids, d.time_ids, d.target_ids = pm.data_ptr(), it.data_ptr(), tm.data_ptr(), tg.data_ptr()
+    d.B, d.L, d.n_item_rows = B, SL, n_item_rows
+    d.tok_cap, d.col_cap, d.grid_cap = out["main_tgt"].numel(), out["col_item_ids"].numel(), out["fold_inv1"].numel()
+    for name in L.BATCH_INDEX_OUTPUTS:
+        setattr(d, name, out[name].data_ptr())
+    ws = L.workspace(_lib.rs_batch_index_workspace_bytes(B, SL, n_item_rows), pm.device)
+    L.check(_lib.rs_batch_index_build(d, L.ptr(ws), ws.numel(), L.stream()), "rs_batch_index_build")
+    return out
+
+
+@torch.library.custom_op("rs::gather_add2", mutates_args=())
+def gather_add2_op(x: Tensor, i1: Tensor, i2: Tensor) -> Tensor:
+    """out[u] = x[i1[u]] + x[i2[u]] (rows; an index outside [0, len(x)) contributes 0)."""
+    L.require_cuda(x, i1, i2)
+    x, i1, i2 = x.contiguous(), _ids(i1), _ids(i2)
+    out = torch.empty(i1.numel(), x.shape[1], dtype=x.dtype, device=x.device)
+    L.check(_lib.rs_gather_add2(L.ptr(x), L.dt(x), L.ptr(i1), L.ptr(i2), i1.numel(), x.shape[0], x.shape[1], L.ptr(out),
+                                L.stream()), "rs_gather_add2")
+    return out
+
+
+@gather_add2_op.register_fake
+def _(x, i1, i2):
+    return x.new_empty(i1.numel(), x.shape[1])
+
+
 # ---- fused in-batch softmax -------------------------------------------------------------------
 def _ce_problem(a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value, flags,
                 logit_bound=0.0):
@@ -794,8 +865,11 @@ def user_block_logits_op(u: Tensor, cols: Tensor, pos_col: Tensor, row_cu: Tenso
     L.require_cuda(u, cols, pos_col, row_cu)
     u, cols, pos_col = _c(u), _c(cols), _ids(pos_col)
     n = u.shape[0]
-    s_pos = torch.empty(n, dtype=torch.float32, device=u.device)
-    own = torch.empty(n, dtype=torch.float32, device=u.device)
+    if row_cu.dtype != torch.int32 or not row_cu.is_contiguous():
+        raise TypeError("row_cu must be a contiguous int32 tensor")
+    # rows that belong to no user block (bucket padding behind row_cu[-1]) keep 0 instead of uninitialised memory
+    s_pos = torch.zeros(n, dtype=torch.float32, device=u.device)
+    own = torch.zeros(n, dtype=torch.float32, device=u.device)
     L.check(_lib.rs_user_block_logits_fwd(L.ptr(u), L.ptr(cols), L.dt(u), L.ptr(pos_col), L.ptr(row_cu),
                                           row_cu.numel() - 1, cols.shape[0], u.shape[1], max_len, scale, L.ptr(bias),
                                           L.ptr(s_pos), L.ptr(own), L.stream()), "rs_user_block_logits_fwd")

@@ -138,7 +138,7 @@ class SASRecUserTower(nn.Module):
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
                 fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None,
                 item_id_rows=None, packed_index=None, cu_seqlens=None, packed_zero_tail=0, views=1, packed_fold=None,
-                select_users=None, packed_inputs=None):
+                select_users=None, packed_inputs=None, packed_fold_inv=None):
         """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
         When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
         returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
@@ -157,7 +157,7 @@ class SASRecUserTower(nn.Module):
             # every token `views` times (train.add_host_index), and each copy draws its own dropout masks
             user_profile_vec = enc.sequential(self.static_mlp, static_input if views == 1 else static_input.repeat(views, 1))
             return self._forward_packed(seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index,
-                                        cu_seqlens, packed_zero_tail, select_users, packed_fold)
+                                        cu_seqlens, packed_zero_tail, select_users, packed_fold, packed_fold_inv)
         user_profile_vec = self.static_mlp(static_input)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
         # is_causal=True only tells nn.TransformerEncoder not to PROBE the mask: with is_causal=None it compares the
@@ -180,7 +180,7 @@ class SASRecUserTower(nn.Module):
         return F.normalize(final_vec, p=2, dim=-1)
 
     def _forward_packed(self, seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index, cu_seqlens,
-                        zero_tail=0, select_users=None, packed_fold=None):
+                        zero_tail=0, select_users=None, packed_fold=None, packed_fold_inv=None):
         """The encoder on the packed valid tokens (encoder.py): `packed_index` [T] = flat b*L+l positions of the
         valid time steps in batch-major order, `cu_seqlens` int32 their per-sequence offsets (every sequence
         non-empty).  `select_index` then indexes PACKED rows; returns [len(select_index), 128] (all T rows when
@@ -192,7 +192,7 @@ class SASRecUserTower(nn.Module):
         tr = self.training
         x = enc.layer_norm(seq_emb.reshape(-1, seq_emb.shape[-1]), self.emb_ln.weight, self.emb_ln.bias, self.emb_ln.eps,
                            index=packed_index, dropout_p=self.emb_dropout.p if tr else 0.0, out_dtype=torch.float32,
-                           index_fold=packed_fold)
+                           index_fold=packed_fold, index_inv=packed_fold_inv)
         output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
         if not training_mode:
             select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1

@@ -106,15 +106,67 @@ def add_host_index(batch: Dict[str, torch.Tensor], columns: bool = True) -> Dict
     return batch
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Device-built, bucketed batch index: the collated [B, L] tensors go to the device as they are and
+# one stream-ordered call (ops.batch_index_build -> rs_batch_index_build) derives every index the packed two-view step
+# consumes, into arrays whose shapes depend only on the bucket (tok_cap, col_cap).  Padding rows carry loss weight 0,
+# padding columns count 0, padding tokens sit in the attention kernel's zero tail -- so ONE captured graph serves
+# every batch of a bucket, and nothing of the reference's per-step `nonzero` / `unique` work stays on the host.
+# ------------------------------------------------------------------------------------------------------------
+TOK_BUCKET = 2048          # main-loss rows (valid time steps) are padded to a multiple of this
+COL_BUCKET = 512           # distinct-target columns are padded to a multiple of this
+
+
+def bucket_of(n_tokens: int, n_cols: int, tok_q: int = TOK_BUCKET, col_q: int = COL_BUCKET):
+    """(tok_cap, col_cap) of the shape bucket that holds a batch with `n_tokens` valid steps and `n_cols` distinct
+    targets."""
+    return ops.round_up(max(n_tokens, 1), tok_q), ops.round_up(max(n_cols, 1), col_q)
+
+
+def device_index(batch: Dict[str, torch.Tensor], n_item_rows: int, tok_cap: int, col_cap: int,
+                 out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """`batch` (device tensors of one collated batch) + its device-built index for the bucket (tok_cap, col_cap).
+    `out`: preallocated index arrays (ops.batch_index_alloc) to fill in place -- the static buffers of a graph."""
+    B, L = batch["item_ids"].shape
+    if out is None:
+        out = ops.batch_index_alloc(B, L, tok_cap, col_cap, batch["item_ids"].device)
+    ops.batch_index_build(batch["padding_mask"], batch["item_ids"], batch["time_bucket_ids"], batch["target_ids"],
+                          n_item_rows, out)
+    merged = dict(batch)
+    merged.update(out)
+    return merged
+
+
+def check_index(batch: Dict[str, torch.Tensor]) -> Dict[str, int]:
+    """Read the index's counters back (synchronises) and raise if a capacity was too small / the batch is malformed."""
+    t, e, u, flags = (int(x) for x in batch["meta"][:4].tolist())
+    if flags & 1:
+        raise RuntimeError(f"batch index overflow: T={t}, E={e}, U={u} do not fit tok_cap={batch['main_tgt'].numel()}, "
+                           f"col_cap={batch['col_item_ids'].numel()}")
+    if flags & 2:
+        raise ValueError("batch index: a user has an empty sequence")
+    if flags & 4:
+        raise IndexError("batch index: a target id lies outside the item table")
+    return dict(tokens=t, extras=e, columns=u)
+
+
 def _front_item_ids(batch, packed):
     """the item-id grid U1 runs on: the packed [R, 64] grid when the batch carries it, else the padded [B, L] one."""
-    return batch["pk_item_ids"] if (packed and "pk_item_ids" in batch and "cu_seqlens_2v" in batch) else batch["item_ids"]
+    return batch["pk_item_ids"] if (packed and "pk_item_ids" in batch and ("cu_seqlens_2v" in batch)) else batch["item_ids"]
 
 
 def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
     """The two dropout views (v1_usertower_train.py:788-792).  View 1 feeds the main loss (valid steps, or the last
     step) and DuoRec (last step); view 2 only DuoRec: the late-fusion head runs on exactly those rows (same values
     as slicing the full [B, L, 128] output).  Returns ([n_main + B, 128], [B, 128])."""
+    if packed and "row_weight" in batch:          # device-built, bucketed index (device_index)
+        out = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=batch["select_2v"],
+                    select_users=batch["users_2v"], cu_seqlens=batch["cu_seqlens_2v"], packed_zero_tail=1, views=2,
+                    packed_index=batch["pk_index_2v"], packed_fold_inv=(batch["fold_inv1"], batch["fold_inv2"]),
+                    packed_inputs=dict(item_ids=batch["pk_item_ids"], time_bucket_ids=batch["pk_time_ids"],
+                                       pos_ids=batch["pk_pos_ids"]), **extra)
+        B = batch["item_ids"].shape[0]
+        return out[:-B], out[-B:]
     if packed and "cu_seqlens_2v" in batch:
         B = batch["item_ids"].shape[0]
         k = "all" if loss_scope == "all" else "last"
@@ -139,6 +191,61 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
             model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=li, **extra))
 
 
+def _losses_device_index(model, item_tower, batch, pretrained_vecs, kw, loss_scope, packed, columns, lambda_logq,
+                         lambda_sup):
+    """main (C2, all valid steps, distinct-item columns) + DuoRec on a batch indexed by `device_index`: static shapes --
+    tok_cap main rows (weight 0 beyond the true count), col_cap columns (count 0 beyond it)."""
+    L = batch["item_ids"].shape[1]
+    tgt = batch["main_tgt"]
+    n_main = tgt.numel()
+    out1, out2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
+    u = encoder.l2_normalize(out1[:n_main])                                          # :794-807
+    cid = batch["col_item_ids"]
+    v = item_tower.normalized_rows(cid)                                              # :810-811 + :833
+    main = losses.logq_infonce_columns(u, v, cid, batch["col_counts"], tgt, batch["pos_col"], None,
+                                       item_tower.get_log_q(), 0.1, lambda_logq, unit_norm=True,
+                                       row_cu=batch["row_cu"], max_rows_per_user=L, row_weight=batch["row_weight"])
+    cl = losses.duorec_loss_refined(out1[n_main:], out2, batch["last_tgt"], lambda_sup=lambda_sup)   # :830-842
+    return main, cl
+
+
+def _losses_host_index(model, item_tower, batch, pretrained_vecs, kw, loss_scope, packed, columns, lambda_logq,
+                       lambda_sup):
+    """the same two losses on a batch indexed on the host (add_host_index): exact, data-dependent shapes."""
+    B, L = batch["item_ids"].shape
+    tgt_flat = batch["target_ids"].reshape(-1)
+    idx = batch["valid_index"] if loss_scope == "all" else batch["last_index"]
+    li = batch["last_index"]
+    n_main = idx.numel()
+    # view 1 feeds the main loss (valid steps) and DuoRec (last step); view 2 only DuoRec: the late-fusion
+    # head runs on exactly those rows (same values as slicing the full [B,L,128] output)
+    out1, out2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
+    u = encoder.l2_normalize(out1[:n_main])                                      # :794-807
+    tgt = tgt_flat[idx]
+    uid = idx // L                                                               # batch row = user id (:801-804)
+    if columns == "batch" or (columns == "unique" and ("col_item_ids" not in batch or loss_scope != "all")):
+        v = item_tower.normalized_rows(tgt)                                      # :810-811 + :833
+        main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq, unit_norm=True)
+    else:
+        if columns == "unique":
+            cid, cnt, pos_col, grid = (batch[k] for k in ("col_item_ids", "col_counts", "pos_col", "own_grid"))
+            v = item_tower.normalized_rows(cid)
+        else:
+            v = F.normalize(item_tower.get_all_embeddings(), p=2, dim=1)         # :810, all rows
+            cid, cnt, pos_col = losses.item_columns(tgt, v.shape[0])
+            grid = batch["target_ids"].masked_fill(batch["padding_mask"], -1)
+        # same-user mask: the rows are grouped by user (batch-major valid steps) -> one dense block per user
+        blk = {}
+        if loss_scope == "all" and "cu_seqlens" in batch and L <= 64:
+            blk, own = dict(row_cu=batch["cu_seqlens"][:B + 1], max_rows_per_user=L), None
+        else:
+            own = grid[uid] if loss_scope == "all" else None     # one row per user otherwise: nothing to mask
+        main = losses.logq_infonce_columns(u, v, cid, cnt, tgt, pos_col, own, item_tower.get_log_q(), 0.1,
+                                           lambda_logq, unit_norm=True, **blk)     # u and v are F.normalize'd
+    cl = losses.duorec_loss_refined(out1[n_main:], out2, tgt_flat[li], lambda_sup=lambda_sup)   # :830-842
+    return main, cl
+
+
 def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1,
                    lambda_cl=0.2, loss_scope="all", amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                    scaler=None, max_norm=5.0, grad_hook=None, sdpa_efficient=True, columns="unique", packed=True):
@@ -161,37 +268,12 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
     # causal + padding mask) PyTorch's default pick on sm_100, the cuDNN flash kernel with 128-wide tiles, is 28 %
     # slower than the memory-efficient backend (tools/sdpa_probe.py: 28.4 vs 22.2 ms per view, fwd+bwd): select it.
     sdpa = sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]) if sdpa_efficient else contextlib.nullcontext()
+    bucketed = packed and "row_weight" in batch
+    if bucketed and (loss_scope != "all" or columns != "unique"):
+        raise ValueError("the device-built batch index serves loss_scope='all' with columns='unique'")
     with sdpa, torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
-        tgt_flat = batch["target_ids"].reshape(-1)
-        idx = batch["valid_index"] if loss_scope == "all" else batch["last_index"]
-        li = batch["last_index"]
-        n_main = idx.numel()
-        # view 1 feeds the main loss (valid steps) and DuoRec (last step); view 2 only DuoRec: the late-fusion
-        # head runs on exactly those rows (same values as slicing the full [B,L,128] output)
-        out1, out2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
-        u = encoder.l2_normalize(out1[:n_main])                                      # :794-807
-        tgt = tgt_flat[idx]
-        uid = idx // L                                                               # batch row = user id (:801-804)
-        if columns == "batch" or (columns == "unique" and ("col_item_ids" not in batch or loss_scope != "all")):
-            v = item_tower.normalized_rows(tgt)                                      # :810-811 + :833
-            main = losses.logq_infonce_rows(u, v, tgt, uid, item_tower.get_log_q(), 0.1, lambda_logq, unit_norm=True)
-        else:
-            if columns == "unique":
-                cid, cnt, pos_col, grid = (batch[k] for k in ("col_item_ids", "col_counts", "pos_col", "own_grid"))
-                v = item_tower.normalized_rows(cid)
-            else:
-                v = F.normalize(item_tower.get_all_embeddings(), p=2, dim=1)         # :810, all rows
-                cid, cnt, pos_col = losses.item_columns(tgt, v.shape[0])
-                grid = batch["target_ids"].masked_fill(batch["padding_mask"], -1)
-            # same-user mask: the rows are grouped by user (batch-major valid steps) -> one dense block per user
-            blk = {}
-            if loss_scope == "all" and "cu_seqlens" in batch and L <= 64:
-                blk, own = dict(row_cu=batch["cu_seqlens"][:B + 1], max_rows_per_user=L), None
-            else:
-                own = grid[uid] if loss_scope == "all" else None     # one row per user otherwise: nothing to mask
-            main = losses.logq_infonce_columns(u, v, cid, cnt, tgt, pos_col, own, item_tower.get_log_q(), 0.1,
-                                               lambda_logq, unit_norm=True, **blk)     # u and v are F.normalize'd
-        cl = losses.duorec_loss_refined(out1[n_main:], out2, tgt_flat[li], lambda_sup=lambda_sup)   # :830-842
+        fn = _losses_device_index if bucketed else _losses_host_index
+        main, cl = fn(model, item_tower, batch, pretrained_vecs, kw, loss_scope, packed, columns, lambda_logq, lambda_sup)
         total = main + lambda_cl * cl
     if optimizer is not None:
         if scaler is not None:
@@ -381,6 +463,99 @@ class ShardedTwoTower:
         return loss
 
 
+# the tensors of one collated batch (SASRecDataset's default collate, tower_code/v1_refine_usertower.py:204-306)
+_GRID_I64 = ("item_ids", "target_ids", "time_bucket_ids", "type_ids", "color_ids", "graphic_ids", "section_ids")
+_USER_I64 = ("age_bucket", "price_bucket", "cnt_bucket", "recency_bucket", "channel_ids", "club_status_ids",
+             "news_freq_ids", "fn_ids", "active_ids")
+
+
+class FlatBatch:
+    """One collated batch as views of ONE byte buffer (pinned host memory or device memory): a batch crosses PCIe, or
+    moves between a staging buffer and a graph's static inputs, with a single copy."""
+
+    def __init__(self, B: int, L: int, device=None, pin: bool = False):
+        spec = [(k, (B, L), torch.int64) for k in _GRID_I64] + [(k, (B,), torch.int64) for k in _USER_I64]
+        spec += [("cont_feats", (B, 4), torch.float32), ("padding_mask", (B, L), torch.bool)]
+        offs, o = [], 0
+        for _, shape, dt in spec:
+            offs.append(o)
+            n = torch.tensor([], dtype=dt).element_size()
+            for d in shape:
+                n *= d
+            o += (n + 255) // 256 * 256
+        self.B, self.L, self.nbytes = B, L, o
+        self.buf = torch.empty(o, dtype=torch.uint8, device=device if device is not None else "cpu",
+                               pin_memory=bool(pin and device is None))
+        self.views: Dict[str, torch.Tensor] = {}
+        for (k, shape, dt), off in zip(spec, offs):
+            n = torch.tensor([], dtype=dt).element_size()
+            for d in shape:
+                n *= d
+            self.views[k] = self.buf[off:off + n].view(dt).view(*shape)
+
+    def fill(self, batch: Dict[str, torch.Tensor]) -> "FlatBatch":
+        for k, v in self.views.items():
+            v.copy_(batch[k])
+        return self
+
+    def copy_(self, other: "FlatBatch", non_blocking: bool = True) -> "FlatBatch":
+        self.buf.copy_(other.buf, non_blocking=non_blocking)
+        return self
+
+
+class BucketedStep:
+    """The train step on device-indexed batches, one captured CUDA graph per SHAPE BUCKET (tok_cap, col_cap).
+
+    Every graph reads the same static raw-batch buffer (`self.raw`, a FlatBatch on the device), builds the batch index
+    inside the graph (ops.batch_index_build: static output shapes) and runs forward, losses, backward, clip and the
+    optimizer.  A loader only needs two numbers per batch to pick the graph -- valid time steps T and distinct targets
+    U (`counts`, computed on the device while the previous step runs).  step_fn(indexed_batch) -> (total, main, cl)."""
+
+    def __init__(self, step_fn, B: int, L: int, n_item_rows: int, device, use_graph: bool = True,
+                 tok_q: int = TOK_BUCKET, col_q: int = COL_BUCKET):
+        self.step_fn, self.B, self.L, self.n_item_rows, self.device = step_fn, B, L, n_item_rows, device
+        self.use_graph, self.tok_q, self.col_q = use_graph, tok_q, col_q
+        self.raw = FlatBatch(B, L, device=device)
+        self.index: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.graphs: Dict[tuple, "GraphedStep"] = {}
+        self.pool = None
+
+    def counts(self, fb: FlatBatch, meta: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int32[8] device tensor (T, E, U, ...) of the batch in `fb` -- stream-ordered, no synchronisation."""
+        return ops.batch_index_counts(fb.views["padding_mask"], fb.views["target_ids"], self.n_item_rows, meta)
+
+    def bucket(self, n_tokens: int, n_cols: int):
+        return bucket_of(n_tokens, n_cols, self.tok_q, self.col_q)
+
+    def _run_eager(self, key):
+        idx = self.index.get(key)
+        if idx is None:
+            idx = self.index[key] = ops.batch_index_alloc(self.B, self.L, key[0], key[1], self.device)
+        return self.step_fn(device_index(self.raw.views, self.n_item_rows, key[0], key[1], out=idx))
+
+    def ensure(self, key) -> bool:
+        """Capture the graph of bucket `key` if it does not exist yet; `self.raw` must hold a batch of that bucket.
+        Returns True when a capture happened."""
+        if not self.use_graph or key in self.graphs:
+            return False
+        g = GraphedStep(lambda _views: self._run_eager(key), self.raw.views, pool=self.pool)
+        if self.pool is None:
+            self.pool = g.graph.pool()         # later graphs share this one's memory pool (they never run concurrently)
+        self.graphs[key] = g
+        return True
+
+    def run(self, key):
+        """One step on the batch in `self.raw` (which must belong to bucket `key`)."""
+        if not self.use_graph:
+            return self._run_eager(key)
+        self.ensure(key)
+        return self.graphs[key].replay()
+
+    def meta_of(self, key) -> torch.Tensor:
+        """the index's counters / overflow flags of the last step run in bucket `key` (device int32[8])"""
+        return self.index[key]["meta"]
+
+
 class GraphedStep:
     """One train step captured in a CUDA graph (whole step: forward, losses, backward, clip, optimizer), replayed with
     a single launch.  The step is ~600 small kernels; eager Python enqueues them about as fast as the GPU retires
@@ -392,7 +567,7 @@ class GraphedStep:
     advanced inside the step (rs_rng_advance) makes every replay draw new masks; torch's own dropout is graph-safe.
     The optimizer must be capturable (`torch.optim.AdamW(..., fused=True, capturable=True)`)."""
 
-    def __init__(self, step_fn, static_batch, warmup: int = 3):
+    def __init__(self, step_fn, static_batch, warmup: int = 3, pool=None):
         self.batch = static_batch
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -409,10 +584,10 @@ class GraphedStep:
         lib = ops._lib
         c0 = lib.rs_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        # collectives inside the step (N > 1) are captured too; NCCL's watchdog thread polls events meanwhile, which a
-        # "global" capture would reject
+        # with torch.distributed initialised NCCL's watchdog thread polls events meanwhile, which a "global" capture
+        # would reject (capturing the N > 1 step itself is not supported: see DESIGN.md 7)
         mode = "thread_local" if (torch.distributed.is_available() and torch.distributed.is_initialized()) else "global"
-        with torch.cuda.graph(self.graph, capture_error_mode=mode):
+        with torch.cuda.graph(self.graph, pool=pool, capture_error_mode=mode):
             self.out = step_fn(static_batch)
         self.launches = int(lib.rs_launch_count() - c0)      # this library's kernel nodes in the graph
         ops._sort_cache.clear()
@@ -422,7 +597,13 @@ class GraphedStep:
         for k, v in host_batch.items():
             dst = self.batch.get(k)
             if isinstance(dst, torch.Tensor) and isinstance(v, torch.Tensor):
+                if dst.shape != v.shape:
+                    raise ValueError(f"GraphedStep.load: '{k}' has shape {tuple(v.shape)}, the graph was captured with "
+                                     f"{tuple(dst.shape)}")
                 dst.copy_(v, non_blocking=non_blocking)
+            elif dst is not None and not isinstance(dst, torch.Tensor):
+                raise TypeError(f"GraphedStep.load: '{k}' is not a tensor (routing plans of the sharded step hold host "
+                                f"split sizes that a captured graph has frozen)")
 
     def replay(self):
         self.graph.replay()
