@@ -94,7 +94,14 @@ __global__ void __launch_bounds__(UB_THREADS) ub_fwd_kernel(UbParams p, float* _
   int* sCol = reinterpret_cast<int*>(sBias + p.max_len);
   for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
     const int64_t r0 = __ldg(p.row_cu + b);
-    const int len = min((int)(__ldg(p.row_cu + b + 1) - r0), p.max_len);
+    const int true_len = (int)(__ldg(p.row_cu + b + 1) - r0);
+    const int len = min(true_len, p.max_len);
+    // a user with more rows than the block holds cannot be represented: poison the rows that do not fit so that the
+    // loss turns NaN (loud) instead of carrying silently wrong values
+    for (int i = len + threadIdx.x; i < true_len; i += UB_THREADS) {
+      s_pos[r0 + i] = __int_as_float(0x7fc00000);
+      own_lse[r0 + i] = __int_as_float(0x7fc00000);
+    }
     __syncthreads();
     ub_stage<DT>(p, r0, len, sU, sC, sCol, sBias);
     ub_logits(p, len, sU, sC, sBias, sS);

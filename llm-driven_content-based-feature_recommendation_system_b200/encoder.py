@@ -408,9 +408,11 @@ class _L2Normalize(torch.autograd.Function):
 
 
 def l2_normalize(x: Tensor, eps: float = 1e-12) -> Tensor:
-    """F.normalize(x, p=2, dim=-1) for 128-wide CUDA rows in one pass each way (fp32 output, as under autocast where
-    the norm runs in fp32); anything else goes to F.normalize."""
-    if not x.is_cuda or x.shape[-1] != 128 or x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+    """F.normalize(x, p=2, dim=-1) for 128-wide rows in one pass each way (fp32 output, as under autocast where the
+    norm runs in fp32).  Other widths / dtypes are not on the path: the stock op serves them (on the device).  CPU tensors
+    are rejected like by every other entry point of this package (no CPU path)."""
+    L.require_cuda(x)
+    if x.shape[-1] != 128 or x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         return F.normalize(x, p=2, dim=-1, eps=eps)
     return _L2Normalize.apply(x, float(eps))
 
@@ -442,19 +444,22 @@ class _LinearColsumBias(torch.autograd.Function):
 
 
 def linear(module: torch.nn.Linear, x: Tensor) -> Tensor:
-    """`module(x)` for a stock nn.Linear, bias gradient by rs::colsum (CUDA, training); plain call otherwise."""
-    if module.bias is None or not x.is_cuda or not torch.is_grad_enabled() or x.shape[-1] % 4 or module.out_features % 4 \
+    """`module(x)` for a stock nn.Linear with its bias gradient by rs::colsum (training); the plain module call when
+    there is no bias gradient to take or the shape is outside rs::colsum's range.  CUDA tensors only."""
+    L.require_cuda(x)
+    if module.bias is None or not torch.is_grad_enabled() or x.shape[-1] % 4 or module.out_features % 4 \
             or module.out_features > 1024:
         return module(x)
     return _LinearColsumBias.apply(x, module.weight, module.bias)
 
 
 def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
-    """`seq(x)` with its nn.Linear members routed through `linear` (same modules, same parameters)."""
+    """`seq(x)` with its nn.Linear members routed through `linear` (same modules, same parameters).  CUDA tensors only."""
+    L.require_cuda(x)
     for m in seq:
         if isinstance(m, torch.nn.Linear):
             x = linear(m, x)
-        elif (isinstance(m, torch.nn.LayerNorm) and x.is_cuda and tuple(m.normalized_shape) == (128,) and m.elementwise_affine
+        elif (isinstance(m, torch.nn.LayerNorm) and tuple(m.normalized_shape) == (128,) and m.elementwise_affine
               and m.bias is not None and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
             # LayerNorm(128): the row kernel (fp32 statistics and fp32 output, as torch's layer_norm under autocast;
             # its backward folds d_gamma / d_beta into the same pass)

@@ -260,6 +260,11 @@ def _hnm_common(user_emb, item_tower_emb, target_ids, top_k_percent, hnm_thresho
     v = F.normalize(ops.gather_rows(item_tower_emb, target_ids), p=2, dim=1)
     k0 = max(1, int((n - 1) * top_k_percent))
     k0 = min(k0, n)
+    if k0 > 1024:
+        raise NotImplementedError(
+            f"hard-negative mining keeps at most 1024 candidates per row (rs_mine_hard_negatives); N = {n} rows with "
+            f"top_k_percent = {top_k_percent} asks for k = {k0}.  Lower top_k_percent below {1024.0 / max(n - 1, 1):.4f} "
+            f"or split the batch (the reference runs torch.topk over the materialised [N, N] matrix at this size).")
     scores, idx, avail = ops.mine_hard_negatives(u, v, target_ids, k0, hnm_threshold)
     dtype = _operand_dtype(user_emb, item_tower_emb)
     return u, v, u.to(dtype), v.to(dtype), scores, idx, avail, k0

@@ -120,6 +120,10 @@ def seq_front_op(base: Optional[Tensor], ids: Sequence[Tensor], tables: Sequence
     tables = [_f32(t, "embedding table") for t in tables]
     base = _c(base)
     pos_table = None if pos_table is None else _f32(pos_table, "pos table")
+    if pos_table is not None and pos_table.shape[0] < seq_len:
+        # the reference's pos_emb(arange(seq_len)) raises here too (the C ABI carries no row count for this table)
+        raise IndexError(f"index out of range in self: sequence length {seq_len} exceeds the {pos_table.shape[0]} rows "
+                         f"of the position table")
     dim = tables[0].shape[1] if n else (base.shape[-1] if base is not None else pos_table.shape[1])
     shape = ids[0].shape if n else base.shape[:-1]
     P = 1
@@ -719,12 +723,13 @@ class _SeqFront(torch.autograd.Function):
         out = L.direct.seq_front(base, ids[:n_live], tables[:n_live], gates[:n_live].contiguous(), pos_table, L_,
                                      out_dtype)
         ctx.save_for_backward(gates, *ids[:n_live], *tables)
-        ctx.meta = (n, n_live, L_, padding_idx, None if base is None else base.dtype, pos_table is not None)
+        ctx.meta = (n, n_live, L_, padding_idx, None if base is None else base.dtype,
+                    None if pos_table is None else pos_table.shape[0])
         return out
 
     @staticmethod
     def backward(ctx, dx):
-        n, n_live, L_, padding_idx, base_dtype, has_pos = ctx.meta
+        n, n_live, L_, padding_idx, base_dtype, pos_rows = ctx.meta
         gates = ctx.saved_tensors[0]
         ids = list(ctx.saved_tensors[1:1 + n_live])
         tables = list(ctx.saved_tensors[1 + n_live:])
@@ -733,7 +738,11 @@ class _SeqFront(torch.autograd.Function):
         d_tables = list(res[:n_live]) + [torch.zeros_like(t) for t in tables[n_live:]]
         d_gates = torch.zeros_like(gates)
         d_gates[:n_live] = res[n_live][:n_live]
-        d_pos = res[n_live + 1] if has_pos else None
+        d_pos = None
+        if pos_rows is not None:
+            d_pos = res[n_live + 1]                  # [seq_len, dim]: rows arange(seq_len) of the position table
+            if pos_rows > L_:                        # shorter batch than max_len: the other rows got no gradient
+                d_pos = torch.cat([d_pos, d_pos.new_zeros(pos_rows - L_, d_pos.shape[1])])
         d_base = None if base_dtype is None else dx.to(base_dtype)
         return (d_base, d_gates, d_pos, None, None, None, *([None] * n), *d_tables)
 

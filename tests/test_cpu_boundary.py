@@ -142,13 +142,13 @@ def test_direct_entry_points_cover_every_registered_op(rs):
         assert hasattr(torch.ops.rs, n)
 
 
-def test_host_wrappers_fall_back_to_torch_off_device(rs):
-    """encoder.linear / sequential / l2_normalize are drop-ins for the stock modules: on CPU tensors (no kernels) they
-    must be the stock computation."""
+def test_host_wrappers_reject_cpu_tensors(rs):
+    """encoder.linear / sequential / l2_normalize wrap stock modules around the row kernels; like every other entry point
+    they have no CPU path (the CPU implementation of this package is the oracle, which the product never imports)."""
     g = torch.Generator().manual_seed(0)
     seq = torch.nn.Sequential(torch.nn.Linear(100, 128), torch.nn.LayerNorm(128), torch.nn.GELU(), torch.nn.Linear(128, 128))
     x = torch.randn(7, 100, generator=g)
-    torch.testing.assert_close(rs.encoder.sequential(seq, x), seq(x))
-    torch.testing.assert_close(rs.encoder.linear(seq[0], x), seq[0](x))
-    y = torch.randn(5, 128, generator=g)
-    torch.testing.assert_close(rs.encoder.l2_normalize(y), torch.nn.functional.normalize(y, p=2, dim=-1))
+    for call in (lambda: rs.encoder.sequential(seq, x), lambda: rs.encoder.linear(seq[0], x),
+                 lambda: rs.encoder.l2_normalize(torch.randn(5, 128, generator=g))):
+        with pytest.raises(RuntimeError, match="CUDA tensors only"):
+            call()

@@ -128,6 +128,32 @@ def test_seq_front_bit_exact_vs_reference(rs, ut):
     assert torch.equal(got.cpu(), want)
 
 
+def test_seq_front_sequence_shorter_or_longer_than_the_position_table(rs):
+    """pos_emb has max_len rows; a batch with seq_len < max_len trains fine in the reference (rows arange(seq_len) get
+    gradient, the others none), seq_len > max_len raises IndexError."""
+    g = torch.Generator().manual_seed(3)
+    B, L, D, max_len = 8, 20, 128, 50
+    table = (torch.randn(300, D, generator=g) * 0.02)
+    pos = (torch.randn(max_len, D, generator=g) * 0.02)
+    ids = torch.randint(0, 300, (B, L), generator=g)
+    base = torch.randn(B, L, D, generator=g)
+    gates = torch.tensor([0.6])
+    cot = torch.randn(B, L, D, generator=g)
+    t0, p0 = table.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    want = embed.seq_front(base, [ids], [t0], gates, p0)
+    (want * cot).sum().backward()
+    t1, p1 = table.to(DEV).requires_grad_(True), pos.to(DEV).requires_grad_(True)
+    got = rs.seq_front(base.to(DEV), [ids.to(DEV)], [t1], gates.to(DEV), p1, out_dtype=torch.float32)
+    assert torch.equal(got.detach().cpu(), want.detach())
+    (got * cot.to(DEV)).sum().backward()
+    assert p1.grad.shape == pos.shape
+    torch.testing.assert_close(p1.grad.cpu(), p0.grad, rtol=1e-4, atol=1e-5)
+    assert (p1.grad[L:] == 0).all()
+    torch.testing.assert_close(t1.grad.cpu(), t0.grad, rtol=1e-4, atol=1e-5)
+    with pytest.raises(IndexError):
+        rs.seq_front(base.to(DEV), [ids.to(DEV)], [t1], gates.to(DEV), p1[:L - 1])
+
+
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_seq_front_backward_vs_oracle(rs, deterministic):
     g = torch.Generator().manual_seed(9)
