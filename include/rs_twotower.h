@@ -397,6 +397,21 @@ int rs_retrieve_topk(const float* users, int64_t n_users, const float* items, in
                      int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------- N4: ensemble merge of two retrieval lists */
+
+/* tower_code/mined_inference.py:1110-1189 (min-max weighted sum) and :1337-1411 (weighted reciprocal-rank fusion).
+ * cand_ids [n_users, P]: the two models' top-M lists side by side (P = 2M <= 2048; an item both models rank appears
+ * twice); s1, s2 [n_users, P]: both models' re-scored candidates (fp32).  Per user and per blend weight alpha[a]:
+ *   mode 0: n = (s - min) / (max - min + 1e-9) per model;   mode 1: n = 1 / (k_rrf + rank + 1), rank by descending s
+ *   final = alpha * n1 + (1 - alpha) * n2;  the k_sel (= max_k + 20 in the reference) best in (final desc, id asc)
+ *   order;  duplicates dropped, order kept (the reference does this per user with np.unique on the host, :1182-1183).
+ * out_ids [n_alpha, n_users, k_sel] int64, -1 padded behind out_cnt [n_alpha, n_users] distinct ids.
+ * out_n1 / out_n2 (optional, [n_users, P]): the normalised scores / reciprocal ranks.  alphas: HOST doubles.
+ * ids are compared and returned on their low 32 bits. */
+int rs_ensemble_merge(const int64_t* cand_ids, const float* s1, const float* s2, int64_t n_users, int64_t P,
+                      int mode, float k_rrf, const double* alphas /*host*/, int n_alpha, int64_t k_sel,
+                      int64_t* out_ids, int32_t* out_cnt, float* out_n1, float* out_n2, void* stream);
+
 /* ------------------------------------------- C4 / C5: hard-negative mining + sparse logits */
 
 /* Mining (no gradient) of tower_code/v1_refine_usertower.py:775-791 (:643-668, :707-719): for each row i the

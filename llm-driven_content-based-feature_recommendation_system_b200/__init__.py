@@ -12,6 +12,7 @@ _lib.load()
 from . import ops                                               # noqa: E402  (registers torch.ops.rs.*)
 from .ops import (gather_rows, seq_front, static_front, normalized_rows, masked_mean, fm_interaction)  # noqa: E402
 from . import encoder, losses, towers, fm, retrieval, train, sharded, synthetic     # noqa: E402
+from . import alignment, ensemble, lightgcl                                        # noqa: E402
 from .losses import (simcse_loss, inbatch_corrected_logq_loss, inbatch_logq_loss_no_user, duorec_loss_refined,  # noqa
                      logq_correction_loss, efficient_corrected_logq_loss, logq_infonce_rows, info_nce,
                      logq_infonce_columns, item_columns,

@@ -308,6 +308,129 @@ def make_hybrid_user(mi):
                                 gathered=cap, grads=grads, out=out.detach()))
 
 
+def make_alignment(ut):
+    """N2: the on-disk contract (utils/inference_utils.py:84-85,200-202: `pretrained_item_matrix.pt` = [N, 128] fp32,
+    `item_ids.pt` = list[str]) read back by load_aligned_pretrained_embeddings (v1_usertower_train.py:131-160)."""
+    import tempfile
+    g = torch.Generator().manual_seed(17)
+    n_pre, n_cur, D = 700, 900, 128
+    pre = F.normalize(torch.randn(n_pre, D, generator=g), dim=1)
+    # exported ids: zero-padded numeric strings (H&M article ids), sorted by str as the exporter does; one id twice
+    # (the reference's dict keeps the LAST occurrence)
+    pool = [f"{int(x):010d}" for x in torch.randperm(5000, generator=g)[:1200] + 108775000]
+    pre_ids = sorted(pool[:n_pre - 1]) + [pool[3]]
+    # the processor's catalogue: overlaps the export partly, in its own order
+    perm = torch.randperm(1200, generator=g).tolist()
+    cur_ids = [pool[i] for i in perm[:n_cur]]
+    out = dict(pretrained=pre, pretrained_ids=pre_ids, item_ids=cur_ids, dim=D, seed=123)
+    with tempfile.TemporaryDirectory() as d:
+        torch.save(pre, os.path.join(d, "pretrained_item_matrix.pt"))
+        torch.save(pre_ids, os.path.join(d, "item_ids.pt"))
+        proc = SimpleNamespace(num_items=n_cur, item_ids=cur_ids)
+        torch.manual_seed(123)
+        out["aligned"] = ut.load_aligned_pretrained_embeddings(proc, d, D)
+        # dict-wrapped tensor + tensor ids (both accepted by the reference, :141-146)
+        torch.save({"weight": pre}, os.path.join(d, "pretrained_item_matrix.pt"))
+        int_ids = torch.tensor([int(x) for x in pre_ids])
+        torch.save(int_ids, os.path.join(d, "item_ids.pt"))
+        proc2 = SimpleNamespace(num_items=n_cur, item_ids=[str(int(x)) for x in cur_ids])
+        torch.manual_seed(123)
+        out["aligned_int_ids"] = ut.load_aligned_pretrained_embeddings(proc2, d, D)
+        out["pretrained_int_ids"] = int_ids
+        # missing files -> random init only (:157-158)
+        torch.manual_seed(123)
+        out["aligned_missing"] = ut.load_aligned_pretrained_embeddings(proc, os.path.join(d, "nope"), D)
+    save("alignment.pt", out)
+
+
+def make_ensemble():
+    """N4: the candidate-union ensembles of mined_inference.py -- min-max weighted sum (:1103-1183) and weighted RRF
+    (:1347-1407) -- by exec()-ing the reference's own lines on synthetic normalised vectors."""
+    import numpy as np
+    g = torch.Generator().manual_seed(23)
+    b, n, d1, d2, pool_k, max_k = 24, 1500, 64, 128, 100, 50
+    ug = F.normalize(torch.randn(b, d1, generator=g), dim=1)
+    ig = F.normalize(torch.randn(n, d1, generator=g), dim=1)
+    us = F.normalize(torch.randn(b, d2, generator=g), dim=1)
+    it_ = F.normalize(torch.randn(n, d2, generator=g) + 0.0, dim=1)
+    alphas = [0.0, 0.3, 0.5, 0.7, 1.0]
+    out = dict(user_gnn=ug, items_gnn=ig, user_seq=us, items_seq=it_, pool_k=pool_k, max_k=max_k, alphas=alphas, k_rrf=60)
+    ns = dict(torch=torch, F=F, np=np, user_gnn_vecs=ug, all_gnn_item_vecs=ig, user_seq_vecs=us, all_seq_item_vecs=it_,
+              pool_k=pool_k, current_batch_size=b, max_k=max_k, device="cpu", k_rrf=60)
+    exec(ref_lines("tower_code/mined_inference.py", 1103, 1108), ns)        # two global top-M
+    exec(ref_lines("tower_code/mined_inference.py", 1115, 1115), ns)        # union
+    exec(ref_lines("tower_code/mined_inference.py", 1124, 1133), ns)        # gather + re-score
+    exec(ref_lines("tower_code/mined_inference.py", 1139, 1145), ns)        # min-max
+    out["combined_indices"] = ns["combined_indices"]
+    out["s_gnn"], out["s_seq"] = ns["s_gnn"], ns["s_seq"]
+    cic = ns["combined_indices"].cpu().numpy()
+
+    def dedup(local_topk):
+        rows = []
+        for i in range(b):
+            env = dict(np=np, pred_global_ids=cic[i][local_topk[i]])
+            exec(ref_lines("tower_code/mined_inference.py", 1182, 1183), env)
+            rows.append(torch.from_numpy(env["pred_unique"].copy()))
+        return rows
+    mm = {}
+    for alpha in alphas:
+        ns["alpha"] = alpha
+        exec(ref_lines("tower_code/mined_inference.py", 1162, 1162), ns)    # weighted sum
+        exec(ref_lines("tower_code/mined_inference.py", 1170, 1171), ns)    # topk(max_k + 20) -> numpy
+        mm[alpha] = dict(final_scores=ns["final_scores"].clone(), pred_unique=dedup(ns["local_topk_indices"]))
+    out["minmax"] = mm
+    # RRF
+    exec(ref_lines("tower_code/mined_inference.py", 1347, 1348), ns)        # raw scores
+    exec(ref_lines("tower_code/mined_inference.py", 1358, 1371), ns)        # ranks by double sort + scatter
+    exec(ref_lines("tower_code/mined_inference.py", 1379, 1380), ns)        # rrf scores
+    out["rank_gnn"], out["rank_seq"] = ns["rank_gnn"], ns["rank_seq"]
+    rr = {}
+    for alpha in alphas:
+        ns["alpha"] = alpha
+        exec(ref_lines("tower_code/mined_inference.py", 1393, 1393), ns)
+        exec(ref_lines("tower_code/mined_inference.py", 1396, 1397), ns)
+        rr[alpha] = dict(final_scores=ns["final_rrf_scores"].clone(), pred_unique=dedup(ns["local_topk_indices"]))
+    out["rrf"] = rr
+    save("ensemble.pt", out)
+
+
+def make_lightgcl():
+    """N3: LightGCL's BPR / InfoNCE / L2 terms (gnn_model/v1_lightgcl.py:188-222) and its retrieval lines
+    (gnn_model/v1_evaluate_lightgcl.py:312-318), called on the reference class with a stand-in `self`."""
+    sys.path.insert(0, os.path.join(REF, "gnn_model"))
+    import v1_lightgcl as lg
+    g = torch.Generator().manual_seed(31)
+    n_users, n_items, D, B = 300, 500, 64, 256
+    n = n_users + n_items
+    local = (torch.randn(n, D, generator=g) * 0.3).requires_grad_(True)
+    glob = (torch.randn(n, D, generator=g) * 0.3).requires_grad_(True)
+    users = torch.randint(0, n_users, (B,), generator=g)
+    pos = torch.randint(n_users, n, (B,), generator=g)
+    neg = torch.randint(n_users, n, (B,), generator=g)
+    me = SimpleNamespace(temp=0.2)
+    bpr = lg.LightGCL.calc_bpr_loss(me, local, users, pos, neg)
+    g_bpr, = torch.autograd.grad(bpr, local)
+    ssl = lg.LightGCL.calc_ssl_loss(me, local, glob, users, pos)
+    g_ssl = torch.autograd.grad(ssl, [local, glob])
+    emb_u = torch.nn.Embedding(n_users, D)
+    emb_i = torch.nn.Embedding(n_items, D)
+    me2 = SimpleNamespace(embedding_user=emb_u, embedding_item=emb_i)
+    reg = lg.LightGCL.get_l2_reg(me2, users, pos - n_users, neg - n_users)
+    g_reg = torch.autograd.grad(reg, [emb_u.weight, emb_i.weight])
+    out = dict(local=local.detach(), glob=glob.detach(), users=users, pos=pos, neg=neg, temp=0.2, n_users=n_users,
+               bpr=dict(loss=bpr.detach(), grad=g_bpr), ssl=dict(loss=ssl.detach(), grads=[x for x in g_ssl]),
+               reg=dict(loss=reg.detach(), grads=[x for x in g_reg], user_w=emb_u.weight.detach(),
+                        item_w=emb_i.weight.detach()))
+    # retrieval: pure dot product, item 0 masked (v1_evaluate_lightgcl.py:312-318)
+    all_items = torch.randn(n_items, D, generator=g)
+    user_emb = torch.randn(40, D, generator=g)
+    ns = dict(torch=torch, user_emb=user_emb, all_items=all_items, max_k=20)
+    exec(ref_lines("gnn_model/v1_evaluate_lightgcl.py", 312, 318), ns)
+    out["retrieval"] = dict(user_emb=user_emb, all_items=all_items, ids=ns["topk_indices"],
+                            scores=torch.topk(ns["scores"], k=20, dim=1).values)
+    save("lightgcl.pt", out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     ru, ut, mi = import_tower_code()
@@ -317,3 +440,6 @@ if __name__ == "__main__":
     make_retrieval()
     make_item_front(it)
     make_hybrid_user(mi)
+    make_alignment(ut)
+    make_ensemble()
+    make_lightgcl()
