@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="1: capture the whole step in one CUDA graph per pooled batch and replay it (default, 1 GPU); "
                          "0: eager launches")
+    ap.add_argument("--cuda-graph-multi", type=int, default=1,
+                    help="N > 1: capture the sharded step (NCCL collectives included) per shape bucket [1], or launch eagerly [0]")
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="only the resident-input timed loop (for ncu runs)")
@@ -275,58 +277,142 @@ def _cuda_timed(n, fn, barrier, dev, world):
     return ms.item(), host_ms
 
 
-def run_single(args, rs, dev):
-    """N = 1: device-indexed batches, one captured graph per shape bucket, every timed step on a batch no replay has
-    seen before."""
+def sharded_parity_check(rs, dev, rank, world):
+    """Small sharded-vs-single-process check, run by every `bench.py --gpus N` (the pytest for it needs 2 GPUs and is
+    skipped on 1-GPU boxes): the row-sharded step on `world` ranks against the single-process step on the concatenated
+    batch -- losses and gradients (eval-mode towers: no dropout; lr 0).  Returns a short verdict string."""
+    import torch.distributed as dist
+    syn, tr = rs.synthetic, rs.train
+    n_items, B, SL = 3000, 64, 50
+    n_rows = n_items + 1
+
+    def towers():
+        torch.manual_seed(7)
+        m = rs.SASRecUserTower(syn.tower_args(num_items=n_items, max_len=SL)).to(dev).eval()
+        it = rs.SASRecItemTower(n_items, 128, syn.log_q(n_items)).to(dev)
+        lk = syn.pretrained_table(n_items).to(dev)
+        it.init_from_pretrained(lk)
+        return m, it, lk
+    hbs = [syn.make_batch(B, SL, n_items, seed=500 + r) for r in range(world)]
+    # single process, concatenated batch
+    m0, it0, lk = towers()
+    cat = {k: torch.cat([hb[k] for hb in hbs]).to(dev) for k in hbs[0]}
+    full = tr.device_index(cat, n_rows, *tr.bucket_of(int((~cat["padding_mask"]).sum()), 4096, 256, 4096))
+    opt0 = torch.optim.SGD(list(m0.parameters()) + list(it0.parameters()), lr=0.0)
+    want = tr.two_tower_step(m0, it0, full, lk, opt0)
+    # sharded
+    m1, it1, _ = towers()
+    trainer = tr.ShardedDeviceStep(m1, it1)
+    mine = {k: v.to(dev) for k, v in hbs[rank].items()}
+    t_cap = rs.ops.round_up(int((~mine["padding_mask"]).sum()), 256)
+    idx = tr.device_index(mine, n_rows, t_cap, t_cap)
+    trainer.calibrate([idx], q=64)
+    opt1 = torch.optim.SGD(list(m1.parameters()) + list(it1.parameters()), lr=0.0)
+    got = trainer.step(idx, lk, opt1)
+    trainer.check()
+    worst = 0.0
+    for a, b in zip(got, want):
+        worst = max(worst, abs(a.item() - b.item()) / max(1.0, abs(b.item())))
+    sd = tr.gathered_state_dicts(trainer)          # (also exercises the gather-to-full state_dict hook)
+    assert sd["user_tower"]["item_id_emb.weight"].shape == m0.item_id_emb.weight.shape
+    assert torch.equal(sd["user_tower"]["item_id_emb.weight"], m0.item_id_emb.weight.detach())
+    g_rel = 0.0
+    ref = dict(m0.named_parameters())
+    for k, p in m1.named_parameters():
+        if p.grad is None or k == "item_id_emb.weight":
+            continue
+        g0 = ref[k].grad
+        g_rel = max(g_rel, ((p.grad - g0).norm() / g0.norm().clamp_min(1e-12)).item())
+    for shard_p, full_p in ((m1.item_id_emb.weight, m0.item_id_emb.weight), (it1.item_matrix.weight, it0.item_matrix.weight)):
+        parts = [torch.empty_like(shard_p.grad) for _ in range(world)]
+        dist.all_gather(parts, shard_p.grad.contiguous())
+        g1 = rs.sharded.unshard_rows(parts)[:full_p.shape[0]]
+        g_rel = max(g_rel, ((g1 - full_p.grad).norm() / full_p.grad.norm().clamp_min(1e-12)).item())
+    t = torch.tensor([worst, g_rel], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst, g_rel = t.tolist()
+    ok = worst < 2e-3 and g_rel < 3e-2
+    return f"{'ok' if ok else 'MISMATCH'} (loss rel err {worst:.1e}, gradient rel-Frobenius err {g_rel:.1e}; {world} ranks x B={B} vs one process)"
+
+
+def run_bucketed(args, rs, dev, rank, world):
+    """Device-indexed batches, one captured graph per shape bucket, every timed step on a batch no replay has seen
+    before.  N = 1: the plain step.  N > 1: the row-sharded step (train.ShardedDeviceStep) -- every rank runs the same
+    bucket per step (the largest row count over the ranks picks it) so that captures and replays stay in lockstep."""
+    import torch.distributed as dist
     syn, L, tr = rs.synthetic, rs._lib, rs.train
     lib = L.load()
-    torch.manual_seed(42)
     B, SL = args.batch, args.seq_len
     n_rows = syn.N_ITEMS + 1
+    parity = sharded_parity_check(rs, dev, rank, world) if world > 1 else None
+    torch.manual_seed(42)
     model = rs.SASRecUserTower(syn.tower_args(max_len=SL)).to(dev).train()
     item = rs.SASRecItemTower(syn.N_ITEMS, 128, syn.log_q(syn.N_ITEMS)).to(dev)
     lookup = syn.pretrained_table(syn.N_ITEMS).to(dev)
     item.init_from_pretrained(lookup)
+    trainer = tr.ShardedDeviceStep(model, item) if world > 1 else None      # re-shards the two item tables in place
     params = list(model.parameters()) + list(item.parameters())
-    use_graph = bool(args.cuda_graph)
+    use_graph = bool(args.cuda_graph) if world == 1 else bool(args.cuda_graph_multi)
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
+    meta_group = dist.new_group() if world > 1 else None      # own communicator for the loader-stage row-count exchange
 
     def step(b):
+        if trainer is not None:
+            return trainer.step(b, lookup, opt, amp_dtype=torch.bfloat16)
         return tr.two_tower_step(model, item, b, lookup, opt, loss_scope="all", amp_dtype=torch.bfloat16, columns="unique")
 
     bs = tr.BucketedStep(step, B, SL, n_rows, dev, use_graph=use_graph, tok_q=args.tok_bucket, col_q=args.col_bucket)
 
-    # ---- the batches: all distinct (seed 42 + i).  value run: warm-up + steps; e2e run: warm-up + steps more.
+    def key_of(t_, u_):
+        return bs.bucket(t_, u_ if world == 1 else None)
+
+    # ---- the batches: all distinct (seed 42 + 1000 * rank + i).  value run: warm-up + steps; e2e run: as many again.
     W = max(args.warmup, 3)
     n_val, n_e2e = W + args.steps, (0 if args.minimal else W + args.steps)
     n_all = n_val + n_e2e
     t0 = time.perf_counter()
-    host = [tr.FlatBatch(B, SL, pin=True).fill(syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + i)) for i in range(n_all)]
+    seed0 = 42 + 1000 * rank
+    host = [tr.FlatBatch(B, SL, pin=True).fill(syn.make_batch(B, SL, syn.N_ITEMS, seed=seed0 + i)) for i in range(n_all)]
     gen_s = time.perf_counter() - t0
     resident = [tr.FlatBatch(B, SL, device=dev).copy_(host[i]) for i in range(n_val)]
     # loader metadata of the resident batches: their shape bucket (device pre-pass, read back before the timed region)
-    metas = torch.stack([bs.counts(fb) for fb in resident]).cpu()
-    keys = [bs.bucket(int(m[0]), int(m[2])) for m in metas]
-    # capture every bucket the VALUE run needs on a batch that no timed step uses: extra batches (seeds beyond n_all)
-    # are drawn until each needed bucket has been met (or 48 tries)
+    metas = torch.stack([bs.counts(fb) for fb in resident])
+    if world > 1:
+        dist.all_reduce(metas, op=dist.ReduceOp.MAX)
+    metas = metas.cpu()
+    keys = [key_of(int(m[0]), int(m[2])) for m in metas]
+
     # (the e2e run's batches stay on the host until their step; their buckets are computed here on the host only to
     # capture the graphs up front -- a long run has met each of its few buckets within its first steps -- the timed
     # pipeline itself picks the bucket from the device counts)
-    def host_key(fb):
+    def host_counts(fb):
         valid = ~fb.views["padding_mask"]
-        return bs.bucket(int(valid.sum()), int(torch.unique(fb.views["target_ids"][valid]).numel()))
-    e2e_keys = [host_key(host[n_val + j]) for j in range(n_e2e)]
+        return [int(valid.sum()), 0, int(torch.unique(fb.views["target_ids"][valid]).numel()) if world == 1 else 0]
+    e2e_meta = torch.tensor([host_counts(host[n_val + j]) for j in range(n_e2e)], device=dev).reshape(-1, 3)
+    if world > 1 and n_e2e:
+        dist.all_reduce(e2e_meta, op=dist.ReduceOp.MAX)
+    e2e_keys = [key_of(int(m[0]), int(m[2])) for m in e2e_meta.cpu()]
+
+    if trainer is not None:           # per-owner capacities of the two exchanges, from the first resident batches
+        cal = []
+        for i in range(min(3, n_val)):
+            cal.append(tr.device_index(resident[i].views, n_rows, keys[i][0], keys[i][1]))
+        caps = trainer.calibrate(cal)
+        del cal
+
+    # capture every bucket the run needs.  N = 1: on batches that no timed step uses (extra seeds are drawn until each
+    # needed bucket has been met, or 48 tries).  N > 1: in lockstep on the first batch of each bucket.
     need, tries, captured_on_timed = set(keys) | set(e2e_keys), 0, 0
     stage_fb = tr.FlatBatch(B, SL, pin=True)
-    while need - set(bs.graphs) and use_graph and tries < 48:
-        stage_fb.fill(syn.make_batch(B, SL, syn.N_ITEMS, seed=42 + n_all + tries))
+    while world == 1 and need - set(bs.graphs) and use_graph and tries < 48:
+        stage_fb.fill(syn.make_batch(B, SL, syn.N_ITEMS, seed=seed0 + n_all + tries))
         tries += 1
         bs.raw.copy_(stage_fb, non_blocking=False)
         m = bs.counts(bs.raw).cpu()
-        k = bs.bucket(int(m[0]), int(m[2]))
+        k = key_of(int(m[0]), int(m[2]))
         if k in need and k not in bs.graphs:
             bs.ensure(k)
-    for i, k in enumerate(keys):                     # buckets no extra batch fell into: capture on the batch itself
+    for i, k in enumerate(keys):
         if use_graph and k not in bs.graphs:
             bs.raw.copy_(resident[i])
             bs.ensure(k)
@@ -339,30 +425,36 @@ def run_single(args, rs, dev):
     per_step_launches = max((g_.launches for g_ in bs.graphs.values()), default=0)
 
     def barrier():
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
 
     last = {}
 
     def run_resident(i):
-        bs.raw.copy_(resident[i])                    # device -> the graphs' static inputs (one 41 MB copy)
+        bs.raw.copy_(resident[i])                    # device -> the graphs' static inputs (one copy of the batch)
         last["loss"] = bs.run(keys[i])
 
     for i in range(W):
         run_resident(i)
     launches0 = lib.rs_launch_count()
     with ClockSampler(dev.index or 0) as clk:
-        ms, host_ms = _cuda_timed(args.steps, lambda i: run_resident(W + i), barrier, dev, 1)
+        ms, host_ms = _cuda_timed(args.steps, lambda i: run_resident(W + i), barrier, dev, world)
     launches = (per_step_launches * args.steps) if use_graph else (lib.rs_launch_count() - launches0)
     total, main, cl = [float(x) for x in last["loss"]]
     assert all(map(lambda v: v == v and abs(v) < 1e6, (total, main, cl))), f"non-finite loss {total, main, cl}"
     chk = tr.check_index(bs.index[keys[W + args.steps - 1]])          # overflow / malformed-batch flags of the last step
-    value = B * args.steps / (ms * 1e-3)
+    if trainer is not None:
+        trainer.check()
+    value = world * B * args.steps / (ms * 1e-3)
     if args.minimal:
-        print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)), flush=True)
+        if rank == 0:
+            print(json.dumps(dict(metric=METRIC, value=value, ms_per_step=ms / args.steps, minimal=True)), flush=True)
         return
 
     # ---- end to end: pinned host batch -> device (one copy, on a copy stream, one step ahead) -> bucket choice from the
-    # device counts -> replay -> losses read back, EVERY step, each on a batch nothing has seen before
+    # device counts (N > 1: largest row count over the ranks, exchanged on the copy stream) -> replay -> losses read
+    # back, EVERY step, each on a batch nothing has seen before
     copy_stream = torch.cuda.Stream()
     staging = [tr.FlatBatch(B, SL, device=dev) for _ in range(2)]
     meta_dev = [torch.zeros(8, dtype=torch.int32, device=dev) for _ in range(2)]
@@ -377,6 +469,8 @@ def run_single(args, rs, dev):
         with torch.cuda.stream(copy_stream):
             staging[slot].copy_(host[n_val + j])
             bs.counts(staging[slot], meta_dev[slot])
+            if world > 1:
+                dist.all_reduce(meta_dev[slot], op=dist.ReduceOp.MAX, group=meta_group)
             meta_host[slot].copy_(meta_dev[slot], non_blocking=True)
             staged[j] = torch.cuda.Event()
             staged[j].record(copy_stream)
@@ -387,7 +481,7 @@ def run_single(args, rs, dev):
         ev = staged.pop(j)
         ev.synchronize()                                         # issued one step ago: complete in steady state
         slot = j % 2
-        key = bs.bucket(int(meta_host[slot][0]), int(meta_host[slot][2]))
+        key = key_of(int(meta_host[slot][0]), int(meta_host[slot][2]))
         torch.cuda.current_stream().wait_event(ev)
         bs.raw.copy_(staging[slot])
         consumed[slot] = torch.cuda.Event()
@@ -403,9 +497,11 @@ def run_single(args, rs, dev):
     for j in range(W):
         e2e_step(j)
     n_late_warm = len(late_captures)
-    ms_e2e, _ = _cuda_timed(args.steps, lambda i: e2e_step(W + i), barrier, dev, 1)
+    ms_e2e, _ = _cuda_timed(args.steps, lambda i: e2e_step(W + i), barrier, dev, world)
+    if trainer is not None:
+        trainer.check()
     h2d_bytes = host[0].nbytes
-    e2e = dict(value=B * args.steps / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d_bytes,
+    e2e = dict(value=world * B * args.steps / (ms_e2e * 1e-3), unit="samples/s", h2d_bytes_per_step=h2d_bytes,
                d2h_bytes_per_step=12 + 32, ms_per_step=ms_e2e / args.steps,
                graph_captures_inside_timed_region=len(late_captures) - n_late_warm)
 
@@ -444,33 +540,47 @@ def run_single(args, rs, dev):
     grid_cap = int(bs.index[keys[0]]["fold_inv1"].numel())
     kernels, roof = _kernel_table(prof, nprof, grid_cap, 128, ms / args.steps)
 
-    extra = None if args.no_extra else bench_extra(rs, dev)
+    extra = None if (args.no_extra or world > 1) else bench_extra(rs, dev)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cpu, _ = cpu_reference_step_rate(args, 2, 1, syn)
-
+    if rank != 0:
+        return
     buckets = {}
     for k in keys[W:]:
         buckets[f"{k[0]}x{k[1]}"] = buckets.get(f"{k[0]}x{k[1]}", 0) + 1
-    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+    if world == 1:
+        par = "1 GPU"
+        n_cols = chk["columns"]
+    else:
+        n_cols = world * caps[1]
+        par = (f"{world} ranks: item_id_emb + item_matrix row-sharded (owner = row % {world}); U1 rows by a de-duplicated "
+               f"equal-split exchange built on the device ({caps[0]} request slots per owner), negatives = distinct targets "
+               f"of ALL ranks from the all-reduced target histogram ({caps[1]} column slots per owner, all-gathered "
+               f"segments), DuoRec columns all-gathered, other parameters replicated + all-reduced; the id exchange, "
+               f"the routing and the index build are inside every timed step")
+    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B, global_batch=B,
-                            seq_len=SL, d_model=128, n_items=syn.N_ITEMS, loss_scope="all",
-                            loss_rows=chk["tokens"], loss_cols=chk["columns"], loss_columns="unique",
-                            parallelism="1 GPU",
-                            batches=f"every step (value and e2e) consumes a batch no earlier step or capture has seen "
-                                    f"({n_all} distinct synthetic batches, seeds 42..{41 + n_all}; "
-                                    f"{captured_on_timed} timed batches doubled as capture batches)",
+                config=dict(workload="two_tower_infonce_train_step (BASELINE configs[1])", batch_per_gpu=B,
+                            global_batch=B * world, seq_len=SL, d_model=128, n_items=syn.N_ITEMS, loss_scope="all",
+                            loss_rows=chk["tokens"], loss_cols=n_cols,
+                            loss_columns="unique" if world == 1 else "unique (box-wide, capacity-padded)", parallelism=par,
+                            batches=f"every step (value and e2e) consumes a batch no earlier step has seen "
+                                    f"({n_all} distinct synthetic batches per rank, seeds {seed0}..{seed0 + n_all - 1}; "
+                                    f"{captured_on_timed} timed batches doubled as graph-capture batches)",
                             index="built on the device inside every step (rs_batch_index_build); host sends the collated "
                                   "[B, L] tensors only",
-                            cuda_graph=(f"one captured graph per shape bucket (rows % {args.tok_bucket}, columns % "
-                                        f"{args.col_bucket}): {len(bs.graphs)} graphs, buckets of the timed steps {buckets}"
+                            cuda_graph=(f"one captured graph per shape bucket (rows % {args.tok_bucket}"
+                                        f"{', columns % ' + str(args.col_bucket) if world == 1 else ''}): {len(bs.graphs)} "
+                                        f"graphs, buckets of the timed steps {buckets}"
                                         if use_graph else "off (eager launches)"),
                             l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), fresh batch per step"),
                 e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(),
                 roofline=roof, cpu_baseline=cpu, loader=loader, kernels=kernels, extra=extra,
                 loss=dict(total=total, main=main, cl=cl), host_batch_generation_s=round(gen_s, 1))
+    if parity is not None:
+        line["sharded_parity"] = parity
     if extra:
         line["gather_frac"] = extra.get("gather_frac")
         line["scatter_frac"] = extra.get("scatter_frac")
@@ -491,8 +601,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rs = importlib.import_module(PKG)          # raises if librs_twotower.so is missing: no fallback
-    if world == 1 and args.loss_scope == "all" and args.columns == "unique":
-        return run_single(args, rs, dev)
+    if args.loss_scope == "all" and args.columns == "unique" and (world == 1 or args.parallelism == "sharded"):
+        run_bucketed(args, rs, dev, rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     return run_multi(args, rs, dev, rank, world, local)
 
 

@@ -397,6 +397,29 @@ int rs_retrieve_topk(const float* users, int64_t n_users, const float* items, in
                      int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------- row-sharded tables: device-side routing */
+
+/* The reference is single-process; these serve the N > 1 step's `owner = id % world` row sharding.
+ * Conventions: an id of -1 is the NULL id everywhere in this library (rs_gather_rows / rs_normalized_rows_fwd read
+ * zeros, rs_sort_ids / the scatters skip it, no oob flag).
+ *
+ * cnt[id] = number of i < min(n, *n_valid_dev) with ids[i] == id (cnt is cleared first; n_valid_dev may be NULL);
+ * force_bin0: count id 0 once more (the padding id must always own slot 0 of rank 0's list). */
+int rs_id_histogram(const int64_t* ids, int64_t n, const int32_t* n_valid_dev, int64_t n_bins, int force_bin0,
+                    int32_t* cnt, int* oob_flag, void* stream);
+/* Owner-major compaction of the present ids (cnt > 0) of a catalogue of n_ids ids sharded as owner = id % world,
+ * local row = id / world (rows_per_owner = ceil(n_ids / world)): owner by owner, ascending local row, at most `cap`
+ * per owner.  Slot o = owner * cap + s holds
+ *   out_rows[o] = local row (-1: empty)    -- the request list of an equal-split all-to-all
+ *   out_ids[o]  = global id (0: empty), out_cnt[o] = cnt as fp32 (0: empty)          (both optional)
+ * and slot_of[id] = o for present ids, -1 otherwise ([n_ids] int32).
+ * meta (int32[4]): [0] largest per-owner count, [1] 1 iff it exceeds cap (outputs truncated), [2] present ids. */
+int rs_owner_compact(const int32_t* cnt, int world, int64_t rows_per_owner, int64_t n_ids, int64_t cap,
+                     int64_t* out_rows, int64_t* out_ids, float* out_cnt, int32_t* slot_of, int32_t* meta, void* stream);
+/* out[i] = table[ids[i]] widened to int64; `fill` where the id is outside [0, n_table) or the entry is negative */
+int rs_lookup_i32(const int32_t* table, int64_t n_table, const int64_t* ids, int64_t n, int64_t fill, int64_t* out,
+                  void* stream);
+
 /* ------------------------------------------------------- N4: ensemble merge of two retrieval lists */
 
 /* tower_code/mined_inference.py:1110-1189 (min-max weighted sum) and :1337-1411 (weighted reciprocal-rank fusion).

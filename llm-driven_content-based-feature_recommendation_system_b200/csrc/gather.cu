@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const void* __restrict
     int64_t id = __ldg(ids + r);
     if (clamp_max >= 0 && id > clamp_max) id = clamp_max;
     const bool ok = (id >= 0) && (id < rows);
-    if (!ok && oob && gl == 0) *oob = 1;
+    if (!ok && id != -1 && oob && gl == 0) *oob = 1;      // id -1 is the null id: reads as zeros, never flagged
     for (int v = gl; v < m.vecs; v += m.lpr) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) normalized_rows_fwd_kernel(const float* _
     const bool live = r < n;
     int64_t id = live ? __ldg(ids + r) : 0;
     bool ok = live && id >= 0 && id < rows;
-    if (live && !ok && oob && gl == 0) *oob = 1;
+    if (live && !ok && id != -1 && oob && gl == 0) *oob = 1;      // (-1: null id, zeros)
     float ss = 0.f;
     for (int v = gl; v < m.vecs; v += m.lpr) {
       if (ok) { float4 x = ldg_f4(table + id * dim + 4 * v); ss += dot4(x, x); }

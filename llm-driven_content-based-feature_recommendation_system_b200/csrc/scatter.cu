@@ -269,7 +269,7 @@ __device__ __forceinline__ int sort_key_first(const int64_t* ids, int64_t i, int
                                               int* oob) {
   int64_t x = __ldg(ids + i);
   if (clamp_max >= 0 && x > clamp_max) x = clamp_max;
-  if (x < 0 || x >= rows) { if (oob) *oob = 1; x = rows; }   // out-of-range ids sort last (key == rows)
+  if (x < 0 || x >= rows) { if (oob && x != -1) *oob = 1; x = rows; }   // out-of-range ids sort last (key == rows); -1 = null id
   return (int)x;
 }
 

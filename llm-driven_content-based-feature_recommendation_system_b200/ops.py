@@ -539,6 +539,43 @@ def batch_index_build(padding_mask: Tensor, item_ids: Tensor, time_ids: Tensor, 
     return out
 
 
+# ---- row-sharded tables: device-side routing ------------------------------------------------------
+def id_histogram(ids: Tensor, n_bins: int, n_valid: Optional[Tensor] = None, force_bin0: bool = False) -> Tensor:
+    """int32 [n_bins] occurrences of every id among the first `n_valid` (device int32 scalar; default all) entries."""
+    L.require_cuda(ids)
+    ids = _ids(ids).reshape(-1)
+    cnt = torch.empty(n_bins, dtype=torch.int32, device=ids.device)
+    L.check(_lib.rs_id_histogram(L.ptr(ids), ids.numel(), L.ptr(n_valid), n_bins, int(force_bin0), L.ptr(cnt),
+                                 L.ptr(L.oob_flag(ids.device)), L.stream()), "rs_id_histogram")
+    return cnt
+
+
+def owner_compact(cnt: Tensor, world: int, rows_per_owner: int, cap: int, want_ids: bool = False):
+    """Owner-major compaction of the present ids of a histogram (rs_owner_compact):
+    (rows [world*cap] int64 local rows / -1, ids [world*cap] int64 | None, counts [world*cap] fp32 | None,
+     slot_of [n_ids] int32, meta int32[4] = (largest per-owner count, overflow flag, present ids, -))."""
+    L.require_cuda(cnt)
+    dev, n_ids = cnt.device, cnt.numel()
+    rows = torch.empty(world * cap, dtype=torch.int64, device=dev)
+    ids = torch.empty(world * cap, dtype=torch.int64, device=dev) if want_ids else None
+    cf = torch.empty(world * cap, dtype=torch.float32, device=dev) if want_ids else None
+    slot_of = torch.empty(n_ids, dtype=torch.int32, device=dev)
+    meta = torch.empty(4, dtype=torch.int32, device=dev)
+    L.check(_lib.rs_owner_compact(L.ptr(cnt), world, rows_per_owner, n_ids, cap, L.ptr(rows), L.ptr(ids), L.ptr(cf),
+                                  L.ptr(slot_of), L.ptr(meta), L.stream()), "rs_owner_compact")
+    return rows, ids, cf, slot_of, meta
+
+
+def lookup_i32(table: Tensor, ids: Tensor, fill: int = 0) -> Tensor:
+    """table[ids] (int32 table) as int64, `fill` for ids outside the table or negative entries."""
+    L.require_cuda(table, ids)
+    ids = _ids(ids)
+    out = torch.empty(ids.shape, dtype=torch.int64, device=ids.device)
+    L.check(_lib.rs_lookup_i32(L.ptr(table), table.numel(), L.ptr(ids), ids.numel(), fill, L.ptr(out), L.stream()),
+            "rs_lookup_i32")
+    return out
+
+
 @torch.library.custom_op("rs::gather_add2", mutates_args=())
 def gather_add2_op(x: Tensor, i1: Tensor, i2: Tensor) -> Tensor:
     """out[u] = x[i1[u]] + x[i2[u]] (rows; an index outside [0, len(x)) contributes 0)."""

@@ -210,6 +210,45 @@ def planned_lookup(shard: torch.Tensor, plan: LookupPlan, group=None, gather_fn:
                                 lead_rows, pad_local_row)
 
 
+# ----------------------------------------------------------------------------------------------------
+# De-duplicated, equal-split exchange: a rank asks every owner for the DISTINCT rows it needs, through a request list of
+# static capacity per owner built on the device (ops.owner_compact): no host-side split sizes, no synchronisation, the
+# id exchange itself is part of the step.  -1 = empty request slot (the owner answers zeros, the gradient is dropped).
+# ----------------------------------------------------------------------------------------------------
+def _all_to_all_equal(x: torch.Tensor, group) -> torch.Tensor:
+    out = torch.empty_like(x)
+    dist.all_to_all_single(out, x.contiguous(), group=group)
+    return out
+
+
+class _DedupLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, shard, req_rows, group, gather_fn, scatter_fn, pad_local_row):
+        got = _all_to_all_equal(req_rows, group)                       # ids -> owners   ([world * cap] each way)
+        rows = gather_fn(shard, got)                                   # owner-side gather (CUDA kernel; -1 -> zeros)
+        buf = _all_to_all_equal(rows, group)                           # rows -> requesters: slot o = owner * cap + s
+        ctx.save_for_backward(got)
+        ctx.meta = (shard.shape[0], group, scatter_fn, shard.dtype, pad_local_row)
+        return buf
+
+    @staticmethod
+    def backward(ctx, g):
+        (got,) = ctx.saved_tensors
+        nrows, group, scatter_fn, sdt, pad_local_row = ctx.meta
+        recv = _all_to_all_equal(g.contiguous(), group)                # gradient rows -> owners
+        return scatter_fn(recv, got, nrows, pad_local_row).to(sdt), None, None, None, None, None
+
+
+def dedup_lookup(shard: torch.Tensor, req_rows: torch.Tensor, group=None, gather_fn: Optional[Callable] = None,
+                 scatter_fn: Optional[Callable] = None, pad_local_row: int = -1) -> torch.Tensor:
+    """[world * cap, D] buffer whose slot o = owner * cap + s holds row `req_rows[o]` of owner's shard (zeros for -1).
+    Backward: the buffer's gradient travels back slot by slot; every owner reduces what it receives into its shard
+    with the deterministic sort + segment-reduce kernel (rows requested by several ranks add up; -1 slots and
+    `pad_local_row` are skipped)."""
+    return _DedupLookup.apply(shard, req_rows, group, gather_fn or _default_gather, scatter_fn or _scatter_pad,
+                              pad_local_row)
+
+
 def padded_rows(n_rows: int, world: int) -> int:
     """Rows per shard when a table of `n_rows` is padded to a multiple of `world`."""
     return (n_rows + world - 1) // world

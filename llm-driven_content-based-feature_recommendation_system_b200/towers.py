@@ -117,7 +117,12 @@ class SASRecUserTower(nn.Module):
         gates = torch.cat([s_g[:2], s_g.new_ones(1)])
         ids = [item_ids, time_bucket_ids, pos_ids]
         tables = [self.item_id_emb.weight, self.time_emb.weight, pos_ext]
-        if item_id_rows is not None:
+        if isinstance(item_id_rows, (tuple, list)):
+            # (buffer, slots): the DISTINCT item rows of the batch fetched from their owners (sharded.dedup_lookup) and
+            # the buffer slot of every token; slot 0 is the padding id's row (train.ShardedDeviceStep forces it there), so
+            # the kernels' "id 0 never receives gradient" rule keeps its meaning
+            tables[0], ids[0] = item_id_rows[0], item_id_rows[1].view_as(item_ids)
+        elif item_id_rows is not None:
             ids[0] = torch.arange(1, item_ids.numel() + 1, device=item_ids.device).view_as(item_ids)
             tables[0] = item_id_rows
         out = ops.seq_front(base, ids, tables, gates, None, padding_idx=0, n_live=3)

@@ -463,6 +463,130 @@ class ShardedTwoTower:
         return loss
 
 
+class ShardedDeviceStep(ShardedTwoTower):
+    """The N > 1 step on device-indexed batches (device_index): same sharding and the same loss as ShardedTwoTower, but
+    every routing decision is made on the device inside the step, with static shapes:
+
+      * U1's item rows: histogram of the batch's item ids -> owner-major request list of `front_cap` slots per owner
+        (ops.owner_compact) -> DE-DUPLICATED equal-split exchange (sharded.dedup_lookup: ids all-to-all, owner-side
+        gather kernel, rows all-to-all) -> the front kernel reads row `slot` of the arrival buffer for every token.
+        ~20 k distinct rows travel instead of ~110 k token rows; the backward reduces token gradients into the
+        buffer locally (the front's own sparse backward), then ONE gradient row per (rank, item) travels back;
+      * negatives spanning the box: the ranks' target histograms are all-reduced (int32 [n_items], 0.4 MB), every rank
+        derives the identical owner-major list of distinct targets (`col_cap` per owner) from it, normalises ITS OWN
+        segment's rows from its shard and all-gathers the segments (reduce-scatter backward): no id lists exchanged,
+        no unique / searchsorted, no host read;
+      * capacities are fixed at start-up from a few batches (`calibrate`), overflow raises a device flag (`check`).
+    Nothing in the step synchronises with the host, and all collective sizes are static."""
+
+    def __init__(self, model, item_tower, group=None):
+        super().__init__(model, item_tower, group)
+        self.R = self.sh.padded_rows(self.n_rows, self.world)
+        self.front_cap = self.col_cap = None
+        self.flags = []
+
+    # -- routing (device, stream-ordered)
+    def _front_route(self, batch, cap):
+        cnt = ops.id_histogram(batch["pk_item_ids"], self.n_rows, force_bin0=True)
+        req, _, _, slot_of, meta = ops.owner_compact(cnt, self.world, self.R, cap)
+        return req, ops.lookup_i32(slot_of, batch["pk_item_ids"], 0), meta
+
+    def _col_route(self, batch, cap):
+        cnt = ops.id_histogram(batch["main_tgt"], self.n_rows, n_valid=batch["meta"][0:1])
+        if self.world > 1:
+            self.dist.all_reduce(cnt, group=self.group)                  # occurrences among the targets of ALL ranks
+        rows, ids, counts, slot_of, meta = ops.owner_compact(cnt, self.world, self.R, cap, want_ids=True)
+        return rows, ids, counts, ops.lookup_i32(slot_of, batch["main_tgt"], 0), meta
+
+    def calibrate(self, batches, margin: float = 1.15, q: int = 128):
+        """Fix the per-owner capacities from a few (device-indexed) batches of every rank: largest list seen anywhere,
+        plus a margin.  Collective + host read: start-up only."""
+        mf = mc = 0
+        for b in batches:
+            mf = max(mf, int(self._front_route(b, self.R)[2][0]))
+            mc = max(mc, int(self._col_route(b, self.R)[4][0]))
+        t = torch.tensor([mf, mc], device=batches[0]["main_tgt"].device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        mf, mc = (int(x) for x in t.tolist())
+        self.front_cap = min(self.R, ops.round_up(int(mf * margin) + 1, q))
+        self.col_cap = min(self.R, ops.round_up(int(mc * margin) + 1, q))
+        return self.front_cap, self.col_cap
+
+    def check(self):
+        """Raise if a request list overflowed its capacity in any step since the last check (synchronises)."""
+        bad = [int(m[1]) for m in self.flags]
+        self.flags = []
+        if any(bad):
+            raise RuntimeError("sharded step: a per-owner request list exceeded its capacity; re-run calibrate()")
+
+    def step(self, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1, lambda_cl=0.2,
+             amp_dtype: Optional[torch.dtype] = torch.bfloat16, max_norm=5.0, sdpa_efficient=True, packed=True):
+        if "row_weight" not in batch:
+            raise ValueError("ShardedDeviceStep.step needs a device-indexed batch (train.device_index)")
+        if self.front_cap is None:
+            raise RuntimeError("call calibrate() first")
+        dist, sh, model, item_tower = self.dist, self.sh, self.model, self.item_tower
+        B, L = batch["item_ids"].shape
+        encoder.rng_advance()
+        if optimizer is not None:
+            optimizer.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            pretrained_vecs = ops.gather_rows(pretrained_lookup, batch["pk_item_ids"])
+        kw = {k: batch[k] for k in FORWARD_KEYS}
+        # one de-duplicated exchange serves every token of both dropout views
+        req, slots, meta_f = self._front_route(batch, self.front_cap)
+        buf = sh.dedup_lookup(model.item_id_emb.weight, req, self.group, pad_local_row=self.pad_local_row)
+        sdpa = sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]) if sdpa_efficient else contextlib.nullcontext()
+        with sdpa, torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+            tgt = batch["main_tgt"]
+            n_main = tgt.numel()
+            out1, out2 = _two_views(model, batch, pretrained_vecs, kw, "all", packed, item_id_rows=(buf, slots))
+            u = encoder.l2_normalize(out1[:n_main])
+            # columns: the distinct targets of the whole box, owner-major; this rank contributes its own segment
+            rows, cid, cnt, pos_col, meta_c = self._col_route(batch, self.col_cap)
+            own = rows[self.rank * self.col_cap:(self.rank + 1) * self.col_cap]
+            v_cols = sh.all_gather_rows(ops.normalized_rows(item_tower.item_matrix.weight, own), self.group)
+            t_loc = batch["meta"][0:1].to(torch.float32)
+            t_glob = t_loc.clone()
+            dist.all_reduce(t_glob, group=self.group)
+            rw = batch["row_weight"] * (t_loc / t_glob)                           # 1 / (valid rows of ALL ranks)
+            main = losses.logq_infonce_columns(u, v_cols, cid, cnt, tgt, pos_col, None, self.log_q_by_id, 0.1,
+                                               lambda_logq, unit_norm=True, row_cu=batch["row_cu"],
+                                               max_rows_per_user=L, row_weight=rw)
+            cl = self._duorec(out1[n_main:], out2, batch["last_tgt"], lambda_sup) / self.world
+            total = main + lambda_cl * cl
+        self.flags.append(torch.maximum(meta_f, meta_c))
+        if optimizer is not None:
+            total.backward()
+            self._sync_replicated()
+            self._clip(max_norm)
+            optimizer.step()
+        out = torch.stack([total.detach(), main.detach(), cl.detach()])
+        dist.all_reduce(out, group=self.group)                                   # global-batch losses (for logging)
+        return out[0], out[1], out[2]
+
+    def full_state_dict(self):
+        """`state_dict()` of both towers with the row-sharded tables gathered back to full size, under the reference's
+        parameter names (checkpoints are saved / loaded by name,
+        tower_code/v1_usertower_train.py:1020-1021,1079-1083).  Collective: call it on every rank."""
+        return gathered_state_dicts(self)
+
+
+def gathered_state_dicts(trainer) -> Dict[str, Dict[str, torch.Tensor]]:
+    """{'user_tower': ..., 'item_tower': ...}: full-size state dicts of a (row-sharded) trainer, every rank gets them."""
+    dist, sh = trainer.dist, trainer.sh
+    out = {}
+    for name, mod, key in (("user_tower", trainer.model, "item_id_emb.weight"), ("item_tower", trainer.item_tower, "item_matrix.weight")):
+        sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+        shard = sd[key].contiguous()
+        parts = [torch.empty_like(shard) for _ in range(trainer.world)]
+        dist.all_gather(parts, shard, group=trainer.group)
+        sd[key] = sh.unshard_rows(parts)[:trainer.n_rows].contiguous()        # drop the equal-shard padding rows
+        out[name] = sd
+    return out
+
+
 # the tensors of one collated batch (SASRecDataset's default collate, tower_code/v1_refine_usertower.py:204-306)
 _GRID_I64 = ("item_ids", "target_ids", "time_bucket_ids", "type_ids", "color_ids", "graphic_ids", "section_ids")
 _USER_I64 = ("age_bucket", "price_bucket", "cnt_bucket", "recency_bucket", "channel_ids", "club_status_ids",
@@ -525,6 +649,11 @@ class BucketedStep:
         return ops.batch_index_counts(fb.views["padding_mask"], fb.views["target_ids"], self.n_item_rows, meta)
 
     def bucket(self, n_tokens: int, n_cols: int):
+        """`n_cols` None: the step does not use the index's LOCAL column list (the sharded step derives box-wide
+        columns itself): give it the capacity that can never overflow."""
+        if n_cols is None:
+            t = ops.round_up(max(n_tokens, 1), self.tok_q)
+            return t, t
         return bucket_of(n_tokens, n_cols, self.tok_q, self.col_q)
 
     def _run_eager(self, key):

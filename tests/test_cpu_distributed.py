@@ -194,3 +194,74 @@ def test_two_rank_gloo():
     for p in procs:
         p.join(30)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def owner_compact_ref(cnt, world, R, cap):
+    """torch restatement of rs_owner_compact (csrc/shard_route.cu) for the CPU tests: owner by owner, ascending local
+    row, `cap` slots per owner.  Returns (rows [world*cap], ids, counts, slot_of [n_ids])."""
+    n_ids = cnt.numel()
+    rows = torch.full((world * cap,), -1, dtype=torch.int64)
+    ids = torch.zeros(world * cap, dtype=torch.int64)
+    counts = torch.zeros(world * cap)
+    slot_of = torch.full((n_ids,), -1, dtype=torch.int32)
+    for r in range(world):
+        present = [i for i in range(r, n_ids, world) if cnt[i] > 0][:cap]
+        for s, i in enumerate(present):
+            o = r * cap + s
+            rows[o], ids[o], counts[o], slot_of[i] = i // world, i, float(cnt[i]), o
+    return rows, ids, counts, slot_of
+
+
+def _worker_dedup(rank, world, port, q):
+    """sharded.dedup_lookup: de-duplicated equal-split exchange (forward rows, backward gradient rows) on gloo."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = importlib.import_module(PKG)
+        sh = rs.sharded
+        torch.manual_seed(0)
+        n_ids, D, cap = 41, 8, 24
+        R = sh.padded_rows(n_ids, world)
+        full = torch.randn(n_ids, D)
+        shard = sh.shard_padded(full, rank, world).clone().requires_grad_(True)
+        g = torch.Generator().manual_seed(200 + rank)
+        tok_ids = torch.randint(0, n_ids, (60,), generator=g)            # many repeats: 60 tokens over <= 41 ids
+        cnt = torch.bincount(tok_ids, minlength=n_ids)
+        cnt[0] += 1                                                      # the padding id always owns slot 0
+        req, _, _, slot_of = owner_compact_ref(cnt, world, R, cap)
+        slots = slot_of[tok_ids].long()
+
+        def gather(t, i):                                                # -1 = empty request slot -> zeros
+            out = t[i.clamp(min=0)].clone()
+            out[i < 0] = 0
+            return out
+
+        def scatter(gr, i, rows, pad):
+            keep = (i >= 0) & (i != pad)
+            return torch.zeros(rows, gr.shape[1]).index_add_(0, i[keep], gr[keep])
+        buf = sh.dedup_lookup(shard, req, None, gather, scatter, pad_local_row=0 if rank == 0 else -1)
+        ok = slot_of[0] == 0 and torch.equal(buf.detach()[slots], full[tok_ids])
+        w = torch.randn(60, D, generator=g)
+        (buf[slots] * w).sum().backward()
+        # reference: dense gradient of the full table from ALL ranks' tokens, row 0 (padding) excluded
+        ws, ts = [torch.zeros(60, D) for _ in range(world)], [torch.zeros(60, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(ws, w)
+        dist.all_gather(ts, tok_ids)
+        want = torch.zeros(n_ids, D)
+        for w_r, t_r in zip(ws, ts):
+            want.index_add_(0, t_r, w_r)
+        want[0] = 0
+        ok = ok and torch.allclose(shard.grad, sh.shard_padded(want, rank, world), atol=1e-6)
+        # gather-to-full of the shards (state_dict hook)
+        parts = [torch.empty_like(shard.data) for _ in range(world)]
+        dist.all_gather(parts, shard.data)
+        ok = ok and torch.equal(sh.unshard_rows(parts)[:n_ids], full)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_dedup_exchange():
+    assert _run_world(_worker_dedup) == [(0, True), (1, True)]

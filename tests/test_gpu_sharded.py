@@ -103,3 +103,39 @@ def test_sharded_step_matches_single_process():
     for rank, ok, msgs in sorted(res):
         print(rank, msgs)
     assert all(ok for _, ok, _ in res), res
+
+
+def _worker_device(rank, world, port, q):
+    """the device-routed sharded step (train.ShardedDeviceStep) through bench.py's own parity check"""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        rs = importlib.import_module(PKG)
+        import bench
+        q.put((rank, bench.sharded_parity_check(rs, dev, rank, world)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_device_routed_sharded_step_matches_single_process():
+    """de-duplicated equal-split exchange + box-wide columns from the all-reduced target histogram vs the single-process
+    step on the concatenated batch (losses, all gradients, gather-to-full state_dict)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_device, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert all(v.startswith("ok") for _, v in res), res

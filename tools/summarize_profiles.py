@@ -10,6 +10,11 @@ import sys
 def launches(path, steps, out_md):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
+    if steps < 0:
+        # keep only the last -steps train steps: a step starts with the dropout-epoch kernel (rs_rng_advance)
+        starts = [i for i, r in enumerate(rows) if "rng_advance" in r["Kernel Name"]]
+        steps = -steps
+        rows = rows[starts[-steps]:]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows:
         v = float(r["Metric Value"].replace(",", ""))
