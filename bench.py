@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--seq-len", type=int, default=50)
     ap.add_argument("--loss-scope", default="all", choices=["all", "last"])
@@ -101,6 +101,60 @@ def cpu_reference_step_rate(args, steps, warmup, syn):
     return dict(value=Bc / dt, unit="samples/s", cores=nthreads, kind="port",
                 sample=f"B={Bc} users of the B={args.batch} synthetic batch, all-timestep loss, fp32, "
                        f"{len(times)} timed steps after {warmup} warm-up, {dt * 1e3:.0f} ms/step"), dt
+
+
+def gpu_eager_step_rate(syn, dev, B, SL, steps=3, warmup=2):
+    """Stock PyTorch eager on the same B200 (the bar SURVEY.md section 2 names: the reference ships no kernels of its
+    own): the oracle-port nn.Modules on `cuda`, bf16 autocast, the unfused [N, N] loss as the reference materialises it,
+    per-step host-side pretrained lookup as the reference does it (v1_usertower_train.py:760), stock AdamW.
+    Baseline leg only -- nothing of the product runs here."""
+    from oracle import towers as otowers
+    torch.manual_seed(42)
+    model = otowers.UserTowerOracle(syn.tower_args(max_len=SL)).to(dev).train()
+    item = otowers.ItemMatrixOracle(syn.N_ITEMS, 128, syn.log_q(syn.N_ITEMS)).to(dev)
+    lookup = syn.pretrained_table(syn.N_ITEMS)
+    with torch.no_grad():
+        item.item_matrix.weight.copy_(lookup)
+    opt = torch.optim.AdamW(list(model.parameters()) + list(item.parameters()), lr=5e-4, weight_decay=1e-4)
+    batches = [syn.make_batch(B, SL, syn.N_ITEMS, seed=900 + i) for i in range(warmup + steps)]
+    ts, n_rows = [], 0
+    for i, hb in enumerate(batches):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b = {k: hb[k].to(dev) for k in syn.FORWARD_KEYS}
+        b["pretrained_vecs"] = lookup[hb["item_ids"]].to(dev)                       # :760
+        b["target_ids"] = hb["target_ids"].to(dev)
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            total, _, _ = otowers.all_timestep_step_loss(model, item, b)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=5.0)
+        opt.step()
+        total.item()                                                                # the loop's .item() reads (:857-859)
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+        n_rows = int((~hb["padding_mask"]).sum())
+    dt = sum(ts) / len(ts)
+    return dict(value=B / dt, unit="samples/s", batch=B, loss_rows=n_rows, ms_per_step=dt * 1e3,
+                what="stock PyTorch eager on this GPU: oracle-port modules, bf16 autocast, unfused [N, N] loss, end to end "
+                     "from host batches")
+
+
+def run_torch_gpu(args):
+    """`--impl torch_gpu`: the stock-PyTorch-eager arm alone, at the reference's batch (768) and at the largest batch
+    whose unfused [N, N] logits fit comfortably (2048: N ~ 26k rows)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    syn = _load_synthetic()
+    dev = torch.device("cuda", 0)
+    rows = [gpu_eager_step_rate(syn, dev, b, args.seq_len) for b in (768, 2048)]
+    best = max(rows, key=lambda r: r["value"])
+    print(json.dumps(dict(metric=METRIC, value=best["value"], unit="samples/s", n_gpus=1, steps=3, warmup=2,
+                          ms_per_step=best["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                          dtype="bf16", data="synthetic", impl="torch_gpu",
+                          config=dict(workload="two_tower_infonce_train_step, stock PyTorch eager", seq_len=args.seq_len,
+                                      batches=[r["batch"] for r in rows]), gpu_eager_baseline=rows)))
 
 
 def run_reference(args):
@@ -541,9 +595,19 @@ def run_bucketed(args, rs, dev, rank, world):
     kernels, roof = _kernel_table(prof, nprof, grid_cap, 128, ms / args.steps)
 
     extra = None if (args.no_extra or world > 1) else bench_extra(rs, dev)
-    cpu = None
+    cpu = gpu_eager = None
+    n_graphs = len(bs.graphs)
     if not args.no_cpu_baseline and world == 1:
         cpu, _ = cpu_reference_step_rate(args, 2, 1, syn)
+        n_graphs = len(bs.graphs)
+        bs.graphs.clear()                                      # free the graphs' pool before the unfused [N, N] baseline
+        bs.index.clear()
+        resident.clear()
+        torch.cuda.empty_cache()
+        try:
+            gpu_eager = [gpu_eager_step_rate(syn, dev, b_, SL) for b_ in (768, 2048)]
+        except Exception as ex:          # noqa: BLE001 -- a baseline leg must not take the bench line down
+            gpu_eager = dict(error=repr(ex)[:200])
     if rank != 0:
         return
     buckets = {}
@@ -572,12 +636,12 @@ def run_bucketed(args, rs, dev, rank, world):
                             index="built on the device inside every step (rs_batch_index_build); host sends the collated "
                                   "[B, L] tensors only",
                             cuda_graph=(f"one captured graph per shape bucket (rows % {args.tok_bucket}"
-                                        f"{', columns % ' + str(args.col_bucket) if world == 1 else ''}): {len(bs.graphs)} "
+                                        f"{', columns % ' + str(args.col_bucket) if world == 1 else ''}): {n_graphs} "
                                         f"graphs, buckets of the timed steps {buckets}"
                                         if use_graph else "off (eager launches)"),
                             l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), fresh batch per step"),
                 e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(),
-                roofline=roof, cpu_baseline=cpu, loader=loader, kernels=kernels, extra=extra,
+                roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=gpu_eager, loader=loader, kernels=kernels, extra=extra,
                 loss=dict(total=total, main=main, cl=cl), host_batch_generation_s=round(gen_s, 1))
     if parity is not None:
         line["sharded_parity"] = parity
@@ -588,8 +652,117 @@ def run_bucketed(args, rs, dev, rank, world):
 
 
 def bench_extra(rs, dev):
-    """Driver-visible numbers for the other BASELINE configs (filled in below)."""
-    return None
+    """Driver-visible kernel-level numbers for the BASELINE configs that are not the train step, each against its
+    roofline (MEASURED_PEAKS.json), CUDA events, L2 flushed between iterations, median of n:
+      fronts     config 2's U1 gather-sum / U3 scatter at the FULL [B=8192, L=50] grid and the plain row gathers (the
+                 metric's "gather GB/s vs HBM peak"; inside the step these kernels run on the 4x smaller packed grid)
+      fm         config 3: DeepFM front, B=65536, F=39, k=16
+      retrieval  config 5: 105,542 items, top-12, a 65,536-user sample of the 1.37 M users (ids checked against a
+                 chunked fp32 torch matmul+topk on the GPU for the first 4096 users)
+      ensemble   N4: union of two top-1000 lists + blend + de-duplicated top-520 for 4096 users x 11 alphas"""
+    syn = rs.synthetic
+    hbm, _, src = _peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, n=7):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    def hb(what, ms, nbytes):
+        a = nbytes / (ms * 1e-3) / 1e9
+        return dict(what=what, ms=round(ms, 4), bound="hbm", achieved=round(a, 1), unit="GB/s", peak=hbm, frac=round(a / hbm, 3),
+                    algorithmic_bytes=int(nbytes))
+    out = dict(peak_source=src)
+    g = torch.Generator().manual_seed(0)
+    B, SL, D, NI = 8192, 50, 128, syn.N_ITEMS
+    P = B * SL
+    b = syn.make_batch(B, SL, NI)
+    item_tab = (torch.randn(NI + 1, D, generator=g) * 0.02).to(dev)
+    time_tab = (torch.randn(12, D, generator=g) * 0.02).to(dev)
+    pos = (torch.randn(SL, D, generator=g) * 0.02).to(dev)
+    ids = [b["item_ids"].to(dev), b["time_bucket_ids"].to(dev)]
+    gates = torch.tensor([0.7, 0.4], device=dev)
+    base = torch.randn(B, SL, D, generator=g).to(dev).bfloat16()
+    cot = torch.randn(B, SL, D, generator=g).to(dev).bfloat16()
+    fr = {}
+    # U1: per position base bf16 + item row fp32 + out bf16 + 2 ids (time / position rows are cache resident)
+    fr["seq_front_fwd"] = hb("U1 gather-sum, 409,600 positions, bf16 in/out", timeit(
+        lambda: torch.ops.rs.seq_front(base, ids, [item_tab, time_tab], gates, pos, SL, 2)), P * (256 + 512 + 256 + 16))
+    fr["gather_rows_item"] = hb("gather 409,600 (Zipf ids) rows of [105543, 128] fp32", timeit(
+        lambda: torch.ops.rs.gather_rows(item_tab, ids[0], -1, 0)), P * (512 + 512 + 8))
+    big = torch.randn(syn.N_CUSTOMERS + 1, 64, generator=g).to(dev)
+    uidx = torch.randint(0, syn.N_CUSTOMERS, (1 << 20,), generator=g).to(dev)
+    fr["gather_rows_customers"] = hb("gather 1,048,576 rows of the [1.37M, 64] fp32 customer table", timeit(
+        lambda: torch.ops.rs.gather_rows(big, uidx, -1, 0)), (1 << 20) * (256 + 256 + 8))
+    word = torch.randn(30522, 768, generator=g).to(dev)
+    tok = torch.randint(0, 30522, (512 * 9 * 32,), generator=g).to(dev)
+    fr["gather_rows_bert"] = hb("I2: gather 147,456 rows of [30522, 768] fp32", timeit(
+        lambda: torch.ops.rs.gather_rows(word, tok, -1, 0)), 147456 * (768 * 4 * 2 + 8))
+    # U3: one read of dX (bf16) + ids, RMW of the rows that are hit (unique rows x 512 B x 2) + the dense table's clear
+    uniq = int(torch.unique(ids[0]).numel())
+    sc_bytes = P * (256 + 8) + 2 * uniq * 512 + (NI + 1) * 512
+    rs.ops._sort_cache.clear()
+    fr["scatter_sorted"] = hb("U3 deterministic: sort + segment reduce into the dense [105543, 128] grad (incl. its clear)", timeit(
+        lambda: (rs.ops._sort_cache.clear(), torch.ops.rs.embedding_dense_bwd(cot.view(-1, D), ids[0].view(-1), NI + 1, 0, -1, True))),
+        sc_bytes)
+    fr["scatter_atomic"] = hb("U3 red.global.add.v4.f32 variant, same", timeit(
+        lambda: torch.ops.rs.embedding_dense_bwd(cot.view(-1, D), ids[0].view(-1), NI + 1, 0, -1, False)), sc_bytes)
+    out["fronts"] = fr
+    out["gather_frac"] = max(fr["seq_front_fwd"]["frac"], fr["gather_rows_item"]["frac"])
+    out["scatter_frac"] = max(fr["scatter_sorted"]["frac"], fr["scatter_atomic"]["frac"])
+    del big, word, base, cot
+    # ---- config 3
+    vocab = syn.criteo_vocab_sizes()
+    Bf, F_, k = 65536, len(vocab), 16
+    fids = syn.make_fm_batch(Bf, vocab, seed=1).to(dev)
+    fm = rs.FM(vocab, k=k, init_std=0.01).to(dev)
+    fwd_bytes = Bf * F_ * (k * 4 + 4 + 8) + Bf * 4 + Bf * F_ * k * 2
+    d_fm, d_cat = torch.randn(Bf, device=dev), torch.randn(Bf, F_ * k, device=dev).bfloat16()
+    bwd_bytes = Bf * F_ * (k * 4 + 8) + Bf * 4 + Bf * F_ * k * 2 + 2 * Bf * F_ * (k + 1) * 4
+    out["fm"] = dict(
+        fwd=hb(f"fm_fwd B={Bf} F={F_} k={k}: gather + FM + bf16 concat for the DNN", timeit(
+            lambda: torch.ops.rs.fm_fwd(fids, fm.offsets, fm.embedding, fm.linear.reshape(-1), True, 2)), fwd_bytes),
+        bwd=hb("fm_bwd: atomic scatter into the concatenated table (incl. its clear)", timeit(
+            lambda: torch.ops.rs.fm_bwd(fids, fm.offsets, fm.embedding, d_fm, d_cat, True)), bwd_bytes))
+    # ---- config 5
+    nu, kk = 65536, 12
+    I = torch.nn.functional.normalize(torch.randn(NI, D, generator=g), dim=1).to(dev)
+    U = torch.nn.functional.normalize(torch.randn(nu, D, generator=g), dim=1).to(dev)
+    ms = timeit(lambda: rs.retrieve_topk(U, I, kk), n=3)
+    sc, ix = rs.retrieve_topk(U[:4096], I, kk)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sc0, ix0 = torch.topk(U[:4096] @ I.T, kk + 1, dim=1)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    gap = (sc0[:, :-1] - sc0[:, 1:]).min(dim=1).values > 1e-5          # rows whose top-13 are separated beyond fp32 noise
+    exact = bool(torch.equal(ix[gap], ix0[gap][:, :kk]))
+    flops = 2.0 * nu * NI * D
+    out["retrieval"] = dict(what=f"retrieve_topk {nu} users x {NI} items, k={kk}, fp32 accumulate (exact ids)", ms=round(ms, 2),
+                            achieved=round(flops / ms / 1e9, 1), unit="TFLOP/s fp32", users_per_s=round(nu / ms * 1e3),
+                            full_1p37M_users_s=round(syn.N_CUSTOMERS / (nu / ms * 1e3), 2),
+                            ids_exact_vs_fp32_torch=f"{exact} on {int(gap.sum())}/4096 rows with a top-13 gap > 1e-5")
+    # ---- N4
+    ua = torch.nn.functional.normalize(torch.randn(4096, 64, generator=g), dim=1).to(dev)
+    ia = torch.nn.functional.normalize(torch.randn(NI, 64, generator=g), dim=1).to(dev)
+    alphas = [i / 10 for i in range(11)]
+    comb, sa, sb = rs.ensemble.candidate_union(ua, ia, U[:4096], I, 1000)
+    ms_m = timeit(lambda: rs.ensemble.merge(comb, sa, sb, alphas, 520, "minmax"), n=3)
+    ms_all = timeit(lambda: rs.ensemble.weighted_score_ensemble(ua, ia, U[:4096], I, alphas, 1000, 500), n=3)
+    out["ensemble"] = dict(what="4096 users: two top-1000 retrievals over 105,542 items, re-score, min-max blend for 11 alphas, "
+                                "de-duplicated top-520 each", merge_kernel_ms=round(ms_m, 3), whole_batch_ms=round(ms_all, 2),
+                           users_per_s=round(4096 / ms_all * 1e3))
+    return out
 
 
 def run_ours(args):
@@ -764,5 +937,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch_gpu":
+        run_torch_gpu(a)
     else:
         run_ours(a)

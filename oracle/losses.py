@@ -72,7 +72,7 @@ def inbatch_corrected_logq_loss_columns(user_emb, col_rows, col_item_ids, col_co
     if lambda_logq > 0.0:
         s = s - log_q_tensor[col_item_ids].view(1, -1) * lambda_logq
     n = user_emb.shape[0]
-    r = torch.arange(n)
+    r = torch.arange(n, device=s.device)
     s_pos = s[r, pos_col]
     w = col_counts.to(s.dtype).view(1, -1).expand(n, -1).clone()
     w[col_item_ids.view(1, -1) == target_ids.view(-1, 1)] = 0.0         # every copy of the row's own target
@@ -92,7 +92,7 @@ def inbatch_logq_loss_no_user(user_emb, item_tower_emb, target_ids, log_q_tensor
     (v1_usertower_train.py:479) was written against it."""
     n = user_emb.shape[0]
     return inbatch_corrected_logq_loss(user_emb, item_tower_emb, target_ids,
-                                       torch.arange(n), log_q_tensor, temperature, lambda_logq)
+                                       torch.arange(n, device=user_emb.device), log_q_tensor, temperature, lambda_logq)
 
 
 def duorec_loss_refined(user_emb_1, user_emb_2, target_ids,
@@ -112,14 +112,14 @@ def duorec_loss_refined(user_emb_1, user_emb_2, target_ids,
     z1 = F.normalize(user_emb_1, dim=1)
     z2 = F.normalize(user_emb_2, dim=1)
     unsup = _diag_ce(z1 @ z2.T / temperature)
-    sup = torch.zeros((), dtype=unsup.dtype)
+    sup = torch.zeros((), dtype=unsup.dtype, device=unsup.device)
     if lambda_sup > 0:
         t = target_ids.view(-1, 1)
         pos = (t == t.T) & (t != 0)
         pos = _offdiag(pos).to(z1.dtype)
         if pos.sum() > 0:
             n = z1.shape[0]
-            eye = torch.eye(n, dtype=torch.bool)
+            eye = torch.eye(n, dtype=torch.bool, device=z1.device)
             s = (z1 @ z1.T / temperature).masked_fill(eye, NEG_INF)
             logp = F.log_softmax(s, dim=1).masked_fill(eye, 0.0)
             cnt = pos.sum(1)

@@ -55,7 +55,7 @@ class UserTowerOracle(nn.Module):
         self.output_proj = nn.Sequential(nn.Linear(2 * d, d), nn.LayerNorm(d), nn.GELU(), nn.Linear(d, d))
 
     def seq_gates(self):
-        return torch.sigmoid(self.seq_gate) * torch.tensor(SEQ_GATE_MASK)
+        return torch.sigmoid(self.seq_gate) * torch.tensor(SEQ_GATE_MASK, device=self.seq_gate.device)
 
     def embed_front(self, pretrained_vecs, **seq_ids):
         """Pre-LayerNorm sequence embedding (v1_refine_usertower.py:447-456)."""
@@ -79,7 +79,7 @@ class UserTowerOracle(nn.Module):
                              type_ids=type_ids, color_ids=color_ids, graphic_ids=graphic_ids,
                              section_ids=section_ids)
         x = self.emb_dropout(self.emb_ln(x))                                   # :458-459
-        causal = torch.triu(torch.ones(L, L, dtype=torch.bool), diagonal=1)    # :413-415
+        causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device=item_ids.device), diagonal=1)    # :413-415
         h = self.transformer_encoder(x, mask=causal, src_key_padding_mask=padding_mask)
         prof = self.static_mlp(self.static_front(
             cont_feats, age_bucket=age_bucket, price_bucket=price_bucket, cnt_bucket=cnt_bucket,
@@ -119,13 +119,13 @@ def all_timestep_step_loss(user_tower, item_tower, batch, lambda_logq=1.0, lambd
     out2 = user_tower(**kw, training_mode=True)
     valid = ~batch["padding_mask"]
     B, L = batch["item_ids"].shape
-    rows = torch.arange(B).unsqueeze(1).expand(-1, L)
+    rows = torch.arange(B, device=valid.device).unsqueeze(1).expand(-1, L)
     u = F.normalize(out1[valid], p=2, dim=1)
     v_all = F.normalize(item_tower.get_all_embeddings(), p=2, dim=1)
     main = losses.inbatch_corrected_logq_loss(u, v_all, batch["target_ids"][valid], rows[valid],
                                               item_tower.get_log_q(), 0.1, lambda_logq)
     last = (valid.sum(dim=1) - 1).clamp(min=0)
-    br = torch.arange(B)
+    br = torch.arange(B, device=valid.device)
     cl = losses.duorec_loss_refined(out1[br, last], out2[br, last], batch["target_ids"][br, last],
                                     lambda_sup=lambda_sup)
     return main + lambda_cl * cl, main, cl
