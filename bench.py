@@ -935,6 +935,9 @@ def run_multi(args, rs, dev, rank, world, local):
 
 if __name__ == "__main__":
     a = parse()
+    if os.environ.get("RS_BENCH_FAULT_DUMP"):      # debugging aid: dump every thread's Python stack after N seconds and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["RS_BENCH_FAULT_DUMP"]), exit=True)
     if a.impl == "reference":
         run_reference(a)
     elif a.impl == "torch_gpu":

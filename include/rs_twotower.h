@@ -414,8 +414,10 @@ int rs_id_histogram(const int64_t* ids, int64_t n, const int32_t* n_valid_dev, i
  *   out_ids[o]  = global id (0: empty), out_cnt[o] = cnt as fp32 (0: empty)          (both optional)
  * and slot_of[id] = o for present ids, -1 otherwise ([n_ids] int32).
  * meta (int32[4]): [0] largest per-owner count, [1] 1 iff it exceeds cap (outputs truncated), [2] present ids. */
+size_t rs_owner_compact_workspace_bytes(int world, int64_t rows_per_owner);
 int rs_owner_compact(const int32_t* cnt, int world, int64_t rows_per_owner, int64_t n_ids, int64_t cap,
-                     int64_t* out_rows, int64_t* out_ids, float* out_cnt, int32_t* slot_of, int32_t* meta, void* stream);
+                     int64_t* out_rows /*nullable*/, int64_t* out_ids, float* out_cnt, int32_t* slot_of, int32_t* meta,
+                     void* workspace, size_t workspace_bytes, void* stream);
 /* out[i] = table[ids[i]] widened to int64; `fill` where the id is outside [0, n_table) or the entry is negative */
 int rs_lookup_i32(const int32_t* table, int64_t n_table, const int64_t* ids, int64_t n, int64_t fill, int64_t* out,
                   void* stream);

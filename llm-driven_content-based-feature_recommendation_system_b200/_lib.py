@@ -93,7 +93,8 @@ PROTOTYPES = {
     "rs_batch_index_counts": (i32, [vp, vp, i64, i64, i64, vp, vp, sz, vp]),
     "rs_gather_add2": (i32, [vp, i32, vp, vp, i64, i64, i64, vp, vp]),
     "rs_id_histogram": (i32, [vp, i64, vp, i64, i32, vp, vp, vp]),
-    "rs_owner_compact": (i32, [vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
+    "rs_owner_compact_workspace_bytes": (sz, [i32, i64]),
+    "rs_owner_compact": (i32, [vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, sz, vp]),
     "rs_lookup_i32": (i32, [vp, i64, vp, i64, i64, vp, vp]),
     "rs_ensemble_merge": (i32, [vp, vp, vp, i64, i64, i32, f32, vp, i32, i64, vp, vp, vp, vp, vp]),
     "rs_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),

@@ -29,6 +29,8 @@ struct BiWs {
   int* eoff;      // [B]   exclusive scan of ex
   int* cnt;       // [n_item_rows] occurrences of every item among the valid targets
   int* colidx;    // [n_item_rows] column of every present item
+  int* cmeta;     // [4] meta of the column compaction (largest list, overflow, distinct targets)
+  void* oc_ws;    // workspace of rs_owner_compact
 };
 
 __device__ __forceinline__ void user_masks(const uint8_t* pad, int64_t b, int64_t L, int lane, unsigned& m0, unsigned& m1) {
@@ -108,12 +110,13 @@ struct BiOut {
   int32_t* meta;
 };
 
-// block 0: scans over the users (sequence offsets, extras); block 1: scan over the catalogue (columns)
+// one CTA: scans over the users (sequence offsets, extras).  The column list (distinct targets, ascending id, with
+// multiplicities) is the owner-major compaction of shard_route.cu with a single owner (rs_owner_compact, world = 1).
 __global__ void __launch_bounds__(BI_SCAN_THREADS) bi_scan_kernel(int64_t B, int64_t n_item_rows, int64_t tok_cap,
                                                                    int64_t col_cap, int64_t grid_cap, BiWs ws, BiOut o,
                                                                    int counts_only) {
   const int tid = threadIdx.x;
-  if (blockIdx.x == 0) {
+  {
     const int per = (int)((B + BI_SCAN_THREADS - 1) / BI_SCAN_THREADS);
     const int64_t b0 = (int64_t)tid * per, b1 = b0 + per < B ? b0 + per : B;
     int sl = 0, se = 0;
@@ -139,27 +142,6 @@ __global__ void __launch_bounds__(BI_SCAN_THREADS) bi_scan_kernel(int64_t B, int
       o.cu_seqlens_2v[2 * B] = 2 * T;
       o.cu_seqlens_2v[2 * B + 1] = (int)(2 * grid_cap);     // the zero tail: extras of both views + padding
     }
-  } else {
-    const int per = (int)((n_item_rows + BI_SCAN_THREADS - 1) / BI_SCAN_THREADS);
-    const int64_t i0 = (int64_t)tid * per, i1 = i0 + per < n_item_rows ? i0 + per : n_item_rows;
-    int s = 0;
-    for (int64_t i = i0; i < i1; ++i) s += ws.cnt[i] > 0;
-    int U;
-    int c = block_excl_scan(s, &U);
-    if (tid == 0) {
-      o.meta[2] = U;
-      if (!counts_only && U > col_cap) atomicOr(o.meta + 3, 1);
-    }
-    if (counts_only) return;
-    for (int64_t i = i0; i < i1; ++i) {
-      const int n = ws.cnt[i];
-      ws.colidx[i] = c;
-      if (n > 0) {
-        if (c < col_cap) { o.col_item_ids[c] = i; o.col_counts[c] = (float)n; }
-        ++c;
-      }
-    }
-    for (int64_t k = U + tid; k < col_cap; k += BI_SCAN_THREADS) { o.col_item_ids[k] = 0; o.col_counts[k] = 0.f; }
   }
 }
 
@@ -173,6 +155,10 @@ __global__ void __launch_bounds__(BI_THREADS) bi_fill_kernel(const uint8_t* __re
   const int lane = threadIdx.x & 31;
   const int64_t T = o.meta[0], E = o.meta[1];
   const float w = T > 0 ? 1.0f / (float)T : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                 // the column compaction's counters into the index's meta
+    o.meta[2] = ws.cmeta[2];
+    if (ws.cmeta[1]) atomicOr(o.meta + 3, 1);
+  }
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t b = warp0; b < B; b += nwarps) {
@@ -267,15 +253,23 @@ __global__ void __launch_bounds__(256) gather_add2_kernel(const void* __restrict
   }
 }
 
+__global__ void bi_merge_counts_kernel(int32_t* meta, const int32_t* cmeta) { meta[2] = cmeta[2]; }
+
 }  // namespace rs
 
 using namespace rs;
+
+extern "C" size_t rs_owner_compact_workspace_bytes(int world, int64_t rows_per_owner);
+extern "C" int rs_owner_compact(const int32_t* cnt, int world, int64_t rows_per_owner, int64_t n_ids, int64_t cap,
+                                int64_t* out_rows, int64_t* out_ids, float* out_cnt, int32_t* slot_of, int32_t* meta,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 static inline size_t bi_al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t rs_batch_index_workspace_bytes(int64_t B, int64_t L, int64_t n_item_rows) {
   (void)L;
-  return 4 * bi_al((size_t)(B + 1) * 4) + 2 * bi_al((size_t)n_item_rows * 4);
+  return 4 * bi_al((size_t)(B + 1) * 4) + 2 * bi_al((size_t)n_item_rows * 4) + 256 +
+         bi_al(rs_owner_compact_workspace_bytes(1, n_item_rows));
 }
 
 static BiWs bi_carve(void* workspace, int64_t B, int64_t n_item_rows) {
@@ -286,7 +280,9 @@ static BiWs bi_carve(void* workspace, int64_t B, int64_t n_item_rows) {
   ws.cu = (int*)p; p += bi_al((size_t)(B + 1) * 4);
   ws.eoff = (int*)p; p += bi_al((size_t)(B + 1) * 4);
   ws.cnt = (int*)p; p += bi_al((size_t)n_item_rows * 4);
-  ws.colidx = (int*)p;
+  ws.colidx = (int*)p; p += bi_al((size_t)n_item_rows * 4);
+  ws.cmeta = (int*)p; p += 256;
+  ws.oc_ws = p;
   return ws;
 }
 
@@ -306,7 +302,13 @@ extern "C" int rs_batch_index_counts(const uint8_t* padding_mask, const int64_t*
   RS_LAUNCH_CHECK();
   BiOut o = {};
   o.meta = meta;
-  bi_scan_kernel<<<2, BI_SCAN_THREADS, 0, st>>>(B, n_item_rows, 0, 0, 0, ws, o, 1);
+  bi_scan_kernel<<<1, BI_SCAN_THREADS, 0, st>>>(B, n_item_rows, 0, 0, 0, ws, o, 1);
+  RS_LAUNCH_CHECK();
+  // distinct valid targets = present bins of the histogram (capacity = all: nothing is truncated, outputs unused)
+  int rc = rs_owner_compact(ws.cnt, 1, n_item_rows, n_item_rows, n_item_rows, nullptr, (int64_t*)nullptr, nullptr, ws.colidx,
+                            ws.cmeta, ws.oc_ws, rs_owner_compact_workspace_bytes(1, n_item_rows), stream);
+  (void)rc;
+  bi_merge_counts_kernel<<<1, 1, 0, st>>>(meta, ws.cmeta);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -337,8 +339,12 @@ extern "C" int rs_batch_index_build(const rs_batch_index* d, void* workspace, si
   const int ugrid = (int)((d->B * 32 + BI_THREADS - 1) / BI_THREADS);
   bi_user_kernel<<<ugrid, BI_THREADS, 0, st>>>(d->padding_mask, d->target_ids, d->B, d->L, d->n_item_rows, ws, d->meta);
   RS_LAUNCH_CHECK();
-  bi_scan_kernel<<<2, BI_SCAN_THREADS, 0, st>>>(d->B, d->n_item_rows, d->tok_cap, d->col_cap, d->grid_cap, ws, o, 0);
+  bi_scan_kernel<<<1, BI_SCAN_THREADS, 0, st>>>(d->B, d->n_item_rows, d->tok_cap, d->col_cap, d->grid_cap, ws, o, 0);
   RS_LAUNCH_CHECK();
+  // columns: the distinct valid targets in ascending id order with their multiplicities; colidx[id] = column
+  int rc = rs_owner_compact(ws.cnt, 1, d->n_item_rows, d->n_item_rows, d->col_cap, nullptr, d->col_item_ids, d->col_counts,
+                            ws.colidx, ws.cmeta, ws.oc_ws, rs_owner_compact_workspace_bytes(1, d->n_item_rows), stream);
+  if (rc != RS_OK) return rc;
   const int fgrid = ugrid < RS_NUM_SMS * 8 ? ugrid : RS_NUM_SMS * 8;
   bi_fill_kernel<<<fgrid, BI_THREADS, 0, st>>>(d->padding_mask, d->item_ids, d->time_ids, d->target_ids, d->B, d->L,
                                                d->n_item_rows, d->tok_cap, d->grid_cap, ws, o);

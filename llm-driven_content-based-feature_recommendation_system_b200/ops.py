@@ -561,8 +561,9 @@ def owner_compact(cnt: Tensor, world: int, rows_per_owner: int, cap: int, want_i
     cf = torch.empty(world * cap, dtype=torch.float32, device=dev) if want_ids else None
     slot_of = torch.empty(n_ids, dtype=torch.int32, device=dev)
     meta = torch.empty(4, dtype=torch.int32, device=dev)
+    ws = L.workspace(_lib.rs_owner_compact_workspace_bytes(world, rows_per_owner), dev)
     L.check(_lib.rs_owner_compact(L.ptr(cnt), world, rows_per_owner, n_ids, cap, L.ptr(rows), L.ptr(ids), L.ptr(cf),
-                                  L.ptr(slot_of), L.ptr(meta), L.stream()), "rs_owner_compact")
+                                  L.ptr(slot_of), L.ptr(meta), L.ptr(ws), ws.numel(), L.stream()), "rs_owner_compact")
     return rows, ids, cf, slot_of, meta
 
 

@@ -148,3 +148,45 @@ def test_bucketed_graphs_serve_fresh_batches(rs):
         want = tr.two_tower_step(model, item, tr.prepare_batch(tr.add_host_index(hb), DEV), lookup, None)
         assert abs(mn.item() - want[1].item()) < 5e-3 and abs(cl.item() - want[2].item()) < 5e-3, (seed, key)
     assert len(bs.graphs) == len(seen) and len(bs.graphs) < 12
+
+
+def _owner_compact_ref(cnt, world, R, cap):
+    """plain-Python statement of rs_owner_compact: owner by owner, ascending local row, `cap` slots per owner"""
+    n_ids = cnt.numel()
+    rows = torch.full((world * cap,), -1, dtype=torch.int64)
+    ids = torch.zeros(world * cap, dtype=torch.int64)
+    counts = torch.zeros(world * cap)
+    slot_of = torch.full((n_ids,), -1, dtype=torch.int32)
+    sizes = []
+    for r in range(world):
+        present = [i for i in range(r, n_ids, world) if cnt[i] > 0]
+        sizes.append(len(present))
+        for s, i in enumerate(present[:cap]):
+            o = r * cap + s
+            rows[o], ids[o], counts[o], slot_of[i] = i // world, i, float(cnt[i]), o
+    return rows, ids, counts, slot_of, sizes
+
+
+@pytest.mark.parametrize("n_ids,world,cap,density", [(1, 1, 4, 1.0), (37, 2, 16, 0.5), (5000, 3, 900, 0.4), (105543, 8, 4096, 0.2),
+                                                     (105543, 1, 30000, 0.2), (3001, 4, 64, 0.3), (1371981, 8, 2048, 0.005)])
+def test_owner_compact_vs_reference(rs, n_ids, world, cap, density):
+    g = torch.Generator().manual_seed(n_ids + world)
+    cnt = (torch.rand(n_ids, generator=g) < density).to(torch.int32) * torch.randint(1, 50, (n_ids,), generator=g, dtype=torch.int32)
+    R = (n_ids + world - 1) // world
+    rows, ids, counts, slot_of, meta = rs.ops.owner_compact(cnt.to(DEV), world, R, cap, want_ids=True)
+    w_rows, w_ids, w_counts, w_slot, sizes = _owner_compact_ref(cnt, world, R, cap)
+    m = meta.cpu().tolist()
+    assert m[0] == max(sizes) and m[1] == int(max(sizes) > cap) and m[2] == sum(sizes)
+    assert torch.equal(rows.cpu(), w_rows) and torch.equal(ids.cpu(), w_ids) and torch.equal(counts.cpu(), w_counts)
+    assert torch.equal(slot_of.cpu(), w_slot)
+    # histogram + slot lookup
+    toks = torch.randint(0, n_ids, (4000,), generator=g)
+    h = rs.ops.id_histogram(toks.to(DEV), n_ids, force_bin0=True).cpu()
+    want_h = torch.bincount(toks, minlength=n_ids).to(torch.int32)
+    want_h[0] += 1
+    assert torch.equal(h, want_h)
+    nv = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    h2 = rs.ops.id_histogram(toks.to(DEV), n_ids, n_valid=nv).cpu()
+    assert torch.equal(h2, torch.bincount(toks[:1234], minlength=n_ids).to(torch.int32))
+    got = rs.ops.lookup_i32(slot_of, toks.to(DEV), fill=0).cpu()
+    assert torch.equal(got, torch.where(w_slot[toks] >= 0, w_slot[toks].long(), torch.zeros(4000, dtype=torch.int64)))

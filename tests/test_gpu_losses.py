@@ -232,6 +232,27 @@ def test_retrieval_sizes_vs_oracle(rs, nu, ni, k):
     assert (srt[:, 1:] != srt[:, :-1]).all()                                                      # no duplicates
 
 
+def test_retrieval_all_rows_bit_exact_on_gap_separated_inputs(rs):
+    """inputs are REGENERATED until every user's top-13 scores are separated by more than the fp32
+    summation noise (1e-5); then the ids of ALL rows are compared, exactly, against the fp32 CPU oracle (105,542 items,
+    k = 12)."""
+    g = torch.Generator().manual_seed(77)
+    nu, ni, k = 1024, 105542, 12
+    I = F.normalize(torch.randn(ni, 128, generator=g), dim=1)
+    U = F.normalize(torch.randn(nu, 128, generator=g), dim=1)
+    for _ in range(20):
+        sc = torch.topk(U @ I.T, k + 1, dim=1).values
+        bad = ((sc[:, :-1] - sc[:, 1:]).min(dim=1).values <= 1e-5).nonzero().flatten()
+        if bad.numel() == 0:
+            break
+        U[bad] = F.normalize(torch.randn(bad.numel(), 128, generator=g), dim=1)
+    assert bad.numel() == 0
+    sc_w, ids_w = oretr.retrieve_topk(U, I, k)
+    sc, ids = rs.retrieve_topk(U.to(DEV), I.to(DEV), k)
+    assert torch.equal(ids.cpu(), ids_w)                                   # every row, every rank
+    torch.testing.assert_close(sc.cpu(), sc_w, rtol=0, atol=3e-6)
+
+
 # ------------------------------------------------------------------------------------------ F1
 @pytest.mark.parametrize("k", [4, 16, 128])
 def test_fm_vs_oracle(rs, k):
