@@ -19,7 +19,10 @@ import argparse
 import os
 # one-time allocator choice for a workload whose per-batch shapes differ (valid tokens, distinct items): growing the
 # pool by mapping pages instead of cudaMalloc-ing new blocks avoids multi-ms allocation stalls inside timed steps
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    # (not for N > 1: replaying captured graphs that contain NCCL collectives deadlocked on this stack with expandable
+    # segments -- both ranks stuck behind the first replays, gpurun_out/r2_b2_graphA.log -- and runs fine without)
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 import importlib
 import json
 import os

@@ -483,7 +483,9 @@ class ShardedDeviceStep(ShardedTwoTower):
         super().__init__(model, item_tower, group)
         self.R = self.sh.padded_rows(self.n_rows, self.world)
         self.front_cap = self.col_cap = None
-        self.flags = []
+        # overflow flags of every step since the last check(), OR-ed into ONE persistent word (a captured graph keeps
+        # writing to it on every replay; tensors created inside a capture live in the graphs' shared pool and are reused)
+        self.flag_acc = torch.zeros(4, dtype=torch.int32, device=item_tower.item_matrix.weight.device)
 
     # -- routing (device, stream-ordered)
     def _front_route(self, batch, cap):
@@ -515,9 +517,9 @@ class ShardedDeviceStep(ShardedTwoTower):
 
     def check(self):
         """Raise if a request list overflowed its capacity in any step since the last check (synchronises)."""
-        bad = [int(m[1]) for m in self.flags]
-        self.flags = []
-        if any(bad):
+        bad = int(self.flag_acc[1])
+        self.flag_acc.zero_()
+        if bad:
             raise RuntimeError("sharded step: a per-owner request list exceeded its capacity; re-run calibrate()")
 
     def step(self, batch, pretrained_lookup, optimizer=None, lambda_logq=1.0, lambda_sup=0.1, lambda_cl=0.2,
@@ -556,7 +558,7 @@ class ShardedDeviceStep(ShardedTwoTower):
                                                max_rows_per_user=L, row_weight=rw)
             cl = self._duorec(out1[n_main:], out2, batch["last_tgt"], lambda_sup) / self.world
             total = main + lambda_cl * cl
-        self.flags.append(torch.maximum(meta_f, meta_c))
+        torch.maximum(self.flag_acc, torch.maximum(meta_f, meta_c), out=self.flag_acc)
         if optimizer is not None:
             total.backward()
             self._sync_replicated()
