@@ -500,9 +500,11 @@ class ShardedDeviceStep(ShardedTwoTower):
         rows, ids, counts, slot_of, meta = ops.owner_compact(cnt, self.world, self.R, cap, want_ids=True)
         return rows, ids, counts, ops.lookup_i32(slot_of, batch["main_tgt"], 0), meta
 
-    def calibrate(self, batches, margin: float = 1.15, q: int = 128):
+    def calibrate(self, batches, margin: float = 1.15, col_margin: float = 1.05, q: int = 128):
         """Fix the per-owner capacities from a few (device-indexed) batches of every rank: largest list seen anywhere,
-        plus a margin.  Collective + host read: start-up only."""
+        plus a margin (request slots only cost exchange volume: generous; column slots cost tensor-core work: the
+        box-wide distinct-target count varies by well under 1 % between batches, 5 % is plenty).  Collective + host
+        read: start-up only."""
         mf = mc = 0
         for b in batches:
             mf = max(mf, int(self._front_route(b, self.R)[2][0]))
@@ -512,7 +514,7 @@ class ShardedDeviceStep(ShardedTwoTower):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         mf, mc = (int(x) for x in t.tolist())
         self.front_cap = min(self.R, ops.round_up(int(mf * margin) + 1, q))
-        self.col_cap = min(self.R, ops.round_up(int(mc * margin) + 1, q))
+        self.col_cap = min(self.R, ops.round_up(int(mc * col_margin) + 1, q))
         return self.front_cap, self.col_cap
 
     def check(self):
