@@ -648,6 +648,15 @@ def run_bucketed(args, rs, dev, rank, world):
                 loss=dict(total=total, main=main, cl=cl), host_batch_generation_s=round(gen_s, 1))
     if parity is not None:
         line["sharded_parity"] = parity
+        # how much of the step is the loss's column growth (inherent to "negatives span the box"): the fused-softmax time
+        # scales with the column count; had the columns stayed at this rank's own distinct targets, the step would be
+        # shorter by extra_ms -- (ms - extra_ms) / ms is the efficiency this run would show if column growth were free
+        ce_ms = sum(kernels[n]["ms_per_step"] for n in ("rs_ce_fwd_grad", "rs_ce_bwd_from_grad") if n in kernels)
+        extra_ms = ce_ms * (1.0 - chk["columns"] / max(n_cols, 1))
+        step_ms = ms / args.steps
+        line["column_growth"] = dict(columns_this_rank_alone=chk["columns"], columns_box_wide_padded=n_cols,
+                                     fused_softmax_ms=round(ce_ms, 3), extra_ms_from_growth=round(extra_ms, 3),
+                                     efficiency_bound_if_only_columns_grew=round(1.0 / (1.0 + extra_ms / max(step_ms - extra_ms, 1e-9)), 3))
     if extra:
         line["gather_frac"] = extra.get("gather_frac")
         line["scatter_frac"] = extra.get("scatter_frac")
