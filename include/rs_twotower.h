@@ -365,8 +365,10 @@ typedef struct {
   int64_t* fold_inv2;            /* [grid_cap]  ... of the view-2 copy */
   int32_t* cu_seqlens_2v;        /* [2B + 2] */
   int32_t* row_cu;               /* [B + 1]  rows of every user among the main-loss rows */
-  int64_t* select_2v;            /* [tok_cap + 2B] encoder slots of: the main rows | DuoRec rows view 1 | view 2 */
-  int64_t* users_2v;             /* [tok_cap + 2B] row of the (2B-row, two-view) profile matrix for each of those */
+  int64_t* select_2v;            /* [tok_cap + 2B] encoder slots of: the main rows (slot t for row t, padding rows too) |
+                                    DuoRec rows view 1 | view 2 */
+  int64_t* users_2v;             /* [tok_cap + 2B] row of the (2B-row, two-view) profile matrix for each of those; ascending
+                                    over the main rows (padding rows: B), then 0..B-1, B..2B-1 */
   int64_t* main_tgt;             /* [tok_cap] target item of every main row */
   int64_t* last_tgt;             /* [B] target at the DuoRec position */
   float* row_weight;             /* [tok_cap] 1/T for real rows, 0 for padding */

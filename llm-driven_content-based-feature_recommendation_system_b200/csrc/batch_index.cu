@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(BI_THREADS) bi_fill_kernel(const uint8_t* __re
   // ---- padding: main rows [T, tok_cap), U1 rows [T+E, grid_cap) and their two encoder slots each
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gn = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = T + gtid; t < tok_cap; t += gn) {
-    o.main_tgt[t] = 0; o.pos_col[t] = 0; o.select_2v[t] = 0; o.users_2v[t] = 0; o.row_weight[t] = 0.f;
+    // padding rows: encoder row t itself (a finite, real row: a view-2 token), profile row B -- the users column stays
+    // ascending, which the head's sort-free backward relies on (towers._forward_packed, select_prefix)
+    o.main_tgt[t] = 0; o.pos_col[t] = 0; o.select_2v[t] = t; o.users_2v[t] = B; o.row_weight[t] = 0.f;
   }
   const int64_t used = T + E, npad = grid_cap - used;
   for (int64_t k = gtid; k < npad; k += gn) {

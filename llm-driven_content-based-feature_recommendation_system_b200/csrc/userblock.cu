@@ -19,7 +19,7 @@
 namespace rs {
 
 #define UB_D 128
-#define UB_STRIDE 132          // padded row stride (floats): 128-bit reads of 32 different rows hit all banks evenly
+#define UB_STRIDE 132          // padded row stride (elements), see UbStore
 #define UB_THREADS 128
 
 struct UbParams {
@@ -32,22 +32,46 @@ struct UbParams {
   float scale;
 };
 
+// The staged rows keep the operands' own element type (16-bit operands: half the shared memory of an fp32 copy, so
+// twice as many user blocks are resident per SM -- the kernels are bound by the latency of the row gathers, not by
+// arithmetic).  Row stride 132 elements: 528 B (fp32, 128-bit reads) / 264 B (16-bit, 64-bit reads) -- reads of the
+// same column of 32 different rows are bank-conflict free in both cases.
+template <int DT> struct UbStore { using T = uint16_t; };
+template <> struct UbStore<RS_F32> { using T = float; };
+
 template <int DT>
-__device__ __forceinline__ float4 ub_ld4(const void* base, int64_t off) {
-  if constexpr (DT == RS_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+__device__ __forceinline__ float4 ub_lds4(const typename UbStore<DT>::T* p) {         // 4 consecutive elements as fp32
+  if constexpr (DT == RS_F32) return *reinterpret_cast<const float4*>(p);
   else {
-    const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off));
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
     float2 a, b;
     if constexpr (DT == RS_BF16) { a = unpack_bf16(w.x); b = unpack_bf16(w.y); }
     else { a = unpack_f16(w.x); b = unpack_f16(w.y); }
     return make_float4(a.x, a.y, b.x, b.y);
   }
 }
+template <int DT>
+__device__ __forceinline__ float ub_lds1(const typename UbStore<DT>::T* p) {
+  if constexpr (DT == RS_F32) return *p;
+  else if constexpr (DT == RS_BF16) return __uint_as_float((uint32_t)(*p) << 16);
+  else return __half2float(*reinterpret_cast<const __half*>(p));
+}
+// copy 4 consecutive elements of a global row (element offset `off`) into shared memory, bit for bit
+template <int DT>
+__device__ __forceinline__ void ub_copy4(typename UbStore<DT>::T* dst, const void* base, int64_t off, bool ok) {
+  if constexpr (DT == RS_F32) {
+    *reinterpret_cast<float4*>(dst) = ok ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    *reinterpret_cast<uint2*>(dst) = ok ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off))
+                                        : make_uint2(0u, 0u);
+  }
+}
 
 // stage the user's rows: sU[i][:] = u[r0 + i], sC[i][:] = cols[pos_col[r0 + i]]; sCol[i] = pos_col (int), sBias[i]
 template <int DT>
-__device__ __forceinline__ void ub_stage(const UbParams& p, int64_t r0, int len, float* sU, float* sC, int* sCol,
-                                         float* sBias) {
+__device__ __forceinline__ void ub_stage(const UbParams& p, int64_t r0, int len, typename UbStore<DT>::T* sU,
+                                         typename UbStore<DT>::T* sC, int* sCol, float* sBias) {
   for (int i = threadIdx.x; i < len; i += UB_THREADS) {
     const int64_t c = __ldg(p.pos_col + r0 + i);
     const bool ok = c >= 0 && c < p.n_cols;
@@ -57,25 +81,25 @@ __device__ __forceinline__ void ub_stage(const UbParams& p, int64_t r0, int len,
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int i = w; i < len; i += UB_THREADS / 32) {
-    *reinterpret_cast<float4*>(sU + i * UB_STRIDE + 4 * lane) = ub_ld4<DT>(p.u, (r0 + i) * UB_D + 4 * lane);
+    ub_copy4<DT>(sU + i * UB_STRIDE + 4 * lane, p.u, (r0 + i) * UB_D + 4 * lane, true);
     const int c = sCol[i];
-    *reinterpret_cast<float4*>(sC + i * UB_STRIDE + 4 * lane) =
-        c >= 0 ? ub_ld4<DT>(p.cols, (int64_t)c * UB_D + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ub_copy4<DT>(sC + i * UB_STRIDE + 4 * lane, p.cols, (int64_t)(c >= 0 ? c : 0) * UB_D + 4 * lane, c >= 0);
   }
   __syncthreads();
 }
 
 // sS[i][j] = scale * <u_i, c_j> - bias_j for all (i, j) of the block
-__device__ __forceinline__ void ub_logits(const UbParams& p, int len, const float* sU, const float* sC,
-                                          const float* sBias, float* sS) {
+template <int DT>
+__device__ __forceinline__ void ub_logits(const UbParams& p, int len, const typename UbStore<DT>::T* sU,
+                                          const typename UbStore<DT>::T* sC, const float* sBias, float* sS) {
   for (int pr = threadIdx.x; pr < len * len; pr += UB_THREADS) {
     const int i = pr / len, j = pr - i * len;
-    const float* a = sU + i * UB_STRIDE;
-    const float* b = sC + j * UB_STRIDE;
+    const typename UbStore<DT>::T* a = sU + i * UB_STRIDE;
+    const typename UbStore<DT>::T* b = sC + j * UB_STRIDE;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
     for (int k = 0; k < UB_D; k += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(a + k), y = *reinterpret_cast<const float4*>(b + k);
+      const float4 x = ub_lds4<DT>(a + k), y = ub_lds4<DT>(b + k);
       a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1); a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
     }
     sS[i * p.max_len + j] = ((a0 + a1) + (a2 + a3)) * p.scale - sBias[j];
@@ -86,10 +110,11 @@ __device__ __forceinline__ void ub_logits(const UbParams& p, int len, const floa
 template <int DT>
 __global__ void __launch_bounds__(UB_THREADS) ub_fwd_kernel(UbParams p, float* __restrict__ s_pos,
                                                             float* __restrict__ own_lse) {
-  extern __shared__ float smem[];
-  float* sU = smem;
-  float* sC = sU + p.max_len * UB_STRIDE;
-  float* sS = sC + p.max_len * UB_STRIDE;
+  using ST = typename UbStore<DT>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ST* sU = reinterpret_cast<ST*>(smem_raw);
+  ST* sC = sU + p.max_len * UB_STRIDE;
+  float* sS = reinterpret_cast<float*>(sC + p.max_len * UB_STRIDE);
   float* sBias = sS + p.max_len * p.max_len;
   int* sCol = reinterpret_cast<int*>(sBias + p.max_len);
   for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
@@ -104,7 +129,7 @@ __global__ void __launch_bounds__(UB_THREADS) ub_fwd_kernel(UbParams p, float* _
     }
     __syncthreads();
     ub_stage<DT>(p, r0, len, sU, sC, sCol, sBias);
-    ub_logits(p, len, sU, sC, sBias, sS);
+    ub_logits<DT>(p, len, sU, sC, sBias, sS);
     for (int i = threadIdx.x; i < len; i += UB_THREADS) {
       const int ci = sCol[i];
       float m = -INFINITY;
@@ -127,10 +152,11 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const fl
                                                             const float* __restrict__ g_pos,
                                                             const float* __restrict__ g_own, float* __restrict__ d_u,
                                                             float* __restrict__ d_cols) {
-  extern __shared__ float smem[];
-  float* sU = smem;
-  float* sC = sU + p.max_len * UB_STRIDE;
-  float* sS = sC + p.max_len * UB_STRIDE;
+  using ST = typename UbStore<DT>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ST* sU = reinterpret_cast<ST*>(smem_raw);
+  ST* sC = sU + p.max_len * UB_STRIDE;
+  float* sS = reinterpret_cast<float*>(sC + p.max_len * UB_STRIDE);
   float* sBias = sS + p.max_len * p.max_len;
   int* sCol = reinterpret_cast<int*>(sBias + p.max_len);
   for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
@@ -138,7 +164,7 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const fl
     const int len = min((int)(__ldg(p.row_cu + b + 1) - r0), p.max_len);
     __syncthreads();
     ub_stage<DT>(p, r0, len, sU, sC, sCol, sBias);
-    ub_logits(p, len, sU, sC, sBias, sS);
+    ub_logits<DT>(p, len, sU, sC, sBias, sS);
     // logits -> coefficients, in place
     for (int pr = threadIdx.x; pr < len * len; pr += UB_THREADS) {
       const int i = pr / len, j = pr - i * len;
@@ -158,14 +184,14 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const fl
     const int k = threadIdx.x;
     for (int i = 0; i < len; ++i) {
       float acc = 0.f;
-      for (int j = 0; j < len; ++j) acc = fmaf(sS[i * p.max_len + j], sC[j * UB_STRIDE + k], acc);
+      for (int j = 0; j < len; ++j) acc = fmaf(sS[i * p.max_len + j], ub_lds1<DT>(sC + j * UB_STRIDE + k), acc);
       d_u[(r0 + i) * UB_D + k] = acc;
     }
     for (int j = 0; j < len; ++j) {
       const int cj = sCol[j];
       if (cj < 0) continue;
       float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(sS[i * p.max_len + j], sU[i * UB_STRIDE + k], acc);
+      for (int i = 0; i < len; ++i) acc = fmaf(sS[i * p.max_len + j], ub_lds1<DT>(sU + i * UB_STRIDE + k), acc);
       atomicAdd(d_cols + (int64_t)cj * UB_D + k, acc);
     }
   }
@@ -175,8 +201,9 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const fl
 
 using namespace rs;
 
-static size_t ub_smem(int max_len) {
-  return ((size_t)2 * max_len * UB_STRIDE + (size_t)max_len * max_len + 2 * (size_t)max_len) * sizeof(float);
+static size_t ub_smem(int max_len, int dtype) {
+  const size_t esz = dtype == RS_F32 ? 4 : 2;
+  return (size_t)2 * max_len * UB_STRIDE * esz + ((size_t)max_len * max_len + 2 * (size_t)max_len) * sizeof(float);
 }
 
 #define UB_DISPATCH(dt, NAME, ...)                                      \
@@ -202,8 +229,8 @@ extern "C" int rs_user_block_logits_fwd(const void* u, const void* cols, int dty
   if (!s_pos || !own_lse) return RS_ERR_BAD_ARG;
   max_len = (max_len + 3) & ~3;
   UbParams p = {u, cols, pos_col, row_cu, col_bias, n_users, n_cols, max_len, scale};
-  const size_t smem = ub_smem(max_len);
-  const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 8 ? n_users : (int64_t)RS_NUM_SMS * 8);
+  const size_t smem = ub_smem(max_len, dtype);
+  const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 12 ? n_users : (int64_t)RS_NUM_SMS * 12);
   cudaStream_t st = (cudaStream_t)stream;
   UB_DISPATCH(dtype, DT, {
     cudaError_t e = cudaFuncSetAttribute(ub_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -223,8 +250,8 @@ extern "C" int rs_user_block_logits_bwd(const void* u, const void* cols, int dty
   if (!own_lse || !g_pos || !g_own || !d_u || !d_cols) return RS_ERR_BAD_ARG;
   max_len = (max_len + 3) & ~3;
   UbParams p = {u, cols, pos_col, row_cu, col_bias, n_users, n_cols, max_len, scale};
-  const size_t smem = ub_smem(max_len);
-  const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 8 ? n_users : (int64_t)RS_NUM_SMS * 8);
+  const size_t smem = ub_smem(max_len, dtype);
+  const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 12 ? n_users : (int64_t)RS_NUM_SMS * 12);
   cudaStream_t st = (cudaStream_t)stream;
   UB_DISPATCH(dtype, DT, {
     cudaError_t e = cudaFuncSetAttribute(ub_bwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -750,6 +750,78 @@ def gather_rows(table: Tensor, ids: Tensor, padding_idx: int = -1, clamp_max: in
     return _GatherRows.apply(table, ids, padding_idx, clamp_max, od)
 
 
+class _SelectPrefix(torch.autograd.Function):
+    """cat([x[:n_prefix], x[idx]]) for row matrices.  Backward: the prefix's gradient is COPIED into place and the
+    gathered rows' gradients are added on top (idx must not repeat a row: every row then has at most one addend after
+    the copy, so the result is deterministic although the add is an atomic) -- no sort, no segment reduce."""
+
+    @staticmethod
+    def forward(ctx, x, n_prefix, idx):
+        L.require_cuda(x, idx)
+        x, idx = x.contiguous(), _ids(idx)
+        P, D = x.shape
+        m = idx.numel()
+        out = torch.empty(n_prefix + m, D, dtype=x.dtype, device=x.device)
+        out[:n_prefix].copy_(x[:n_prefix])
+        esz = x.element_size()
+        L.check(_lib.rs_gather_rows(L.ptr(x), L.dt(x), P, D, L.ptr(idx), m, -1,
+                                    L.C.c_void_p(out.data_ptr() + n_prefix * D * esz), L.dt(x),
+                                    L.ptr(L.oob_flag(x.device)), L.stream()), "rs_gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.meta = (P, n_prefix, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        P, n_prefix, xdt = ctx.meta
+        g = g.contiguous()
+        D = g.shape[1]
+        d = torch.empty(P, D, dtype=torch.float32, device=g.device)
+        d[:n_prefix].copy_(g[:n_prefix])
+        d[n_prefix:].zero_()
+        tail = g[n_prefix:]
+        L.check(_lib.rs_scatter_add_rows(L.ptr(tail), L.dt(tail), L.ptr(idx), idx.numel(), D, P, -1, -1, 1.0, L.ptr(d),
+                                         L.ptr(L.oob_flag(g.device)), L.stream()), "rs_scatter_add_rows")
+        return d.to(xdt), None, None
+
+
+def select_prefix_rows(x: Tensor, n_prefix: int, idx: Tensor) -> Tensor:
+    """cat([x[:n_prefix], x[idx]]) with a sort-free backward; `idx` must hold distinct rows."""
+    return _SelectPrefix.apply(x, int(n_prefix), idx)
+
+
+class _GatherRowsSorted(torch.autograd.Function):
+    """table[ids] for ASCENDING ids (e.g. the user of every packed row, batch-major): the backward is a segment sum over
+    runs of equal ids -- the segment-reduce kernel on (ids, arange) directly, without the radix sort."""
+
+    @staticmethod
+    def forward(ctx, table, ids):
+        ctx.save_for_backward(ids)
+        ctx.meta = (table.shape[0], table.dtype)
+        return L.direct.gather_rows(table, ids, -1, L.dt(table))
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        rows, tdt = ctx.meta
+        g = g.reshape(-1, g.shape[-1]).contiguous()
+        n, dim = g.shape
+        sk = ids.reshape(-1).to(torch.int32)
+        sp = torch.arange(n, dtype=torch.int32, device=g.device)
+        d_table = torch.zeros(rows, dim, dtype=torch.float32, device=g.device)
+        ws = L.workspace(_lib.rs_segment_reduce_workspace_bytes(n, dim), g.device)
+        L.check(_lib.rs_segment_reduce_rows(L.ptr(g), L.dt(g), L.ptr(sk), L.ptr(sp), n, dim, rows, -1, None, None,
+                                            L.ptr(d_table), None, L.ptr(ws), ws.numel(), L.stream()),
+                "rs_segment_reduce_rows")
+        return d_table.to(tdt), None
+
+
+def gather_rows_sorted(table: Tensor, ids: Tensor) -> Tensor:
+    """`table[ids]` where the caller vouches that `ids` is ascending (sort-free segment-sum backward)."""
+    return _GatherRowsSorted.apply(table, _ids(ids))
+
+
 class _SeqFront(torch.autograd.Function):
     @staticmethod
     def forward(ctx, base, gates, pos_table, padding_idx, out_dtype, n_live, *rest):

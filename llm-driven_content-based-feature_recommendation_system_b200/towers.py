@@ -143,7 +143,7 @@ class SASRecUserTower(nn.Module):
                 age_bucket, price_bucket, cnt_bucket, recency_bucket, channel_ids, club_status_ids, news_freq_ids,
                 fn_ids, active_ids, cont_feats, padding_mask=None, training_mode=True, select_index=None,
                 item_id_rows=None, packed_index=None, cu_seqlens=None, packed_zero_tail=0, views=1, packed_fold=None,
-                select_users=None, packed_inputs=None, packed_fold_inv=None):
+                select_users=None, packed_inputs=None, packed_fold_inv=None, select_prefix=None):
         """Reference signature (:417-429) plus one optional extension: `select_index` (flat b*L+l positions).
         When given (training_mode only) the late-fusion head runs on those rows alone and [len(index),128] is
         returned -- the train step only ever consumes the valid / last time steps (v1_usertower_train.py:794-842),
@@ -162,7 +162,8 @@ class SASRecUserTower(nn.Module):
             # every token `views` times (train.add_host_index), and each copy draws its own dropout masks
             user_profile_vec = enc.sequential(self.static_mlp, static_input if views == 1 else static_input.repeat(views, 1))
             return self._forward_packed(seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index,
-                                        cu_seqlens, packed_zero_tail, select_users, packed_fold, packed_fold_inv)
+                                        cu_seqlens, packed_zero_tail, select_users, packed_fold, packed_fold_inv,
+                                        select_prefix)
         user_profile_vec = self.static_mlp(static_input)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
         # is_causal=True only tells nn.TransformerEncoder not to PROBE the mask: with is_causal=None it compares the
@@ -185,7 +186,7 @@ class SASRecUserTower(nn.Module):
         return F.normalize(final_vec, p=2, dim=-1)
 
     def _forward_packed(self, seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index, cu_seqlens,
-                        zero_tail=0, select_users=None, packed_fold=None, packed_fold_inv=None):
+                        zero_tail=0, select_users=None, packed_fold=None, packed_fold_inv=None, select_prefix=None):
         """The encoder on the packed valid tokens (encoder.py): `packed_index` [T] = flat b*L+l positions of the
         valid time steps in batch-major order, `cu_seqlens` int32 their per-sequence offsets (every sequence
         non-empty).  `select_index` then indexes PACKED rows; returns [len(select_index), 128] (all T rows when
@@ -201,6 +202,15 @@ class SASRecUserTower(nn.Module):
         output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
         if not training_mode:
             select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1
+        if select_prefix is not None:
+            # device-built index (ops.batch_index_build): the first `select_prefix` selected rows ARE the first packed
+            # rows (identity), their users ascend (batch-major), and the remaining selected rows are one DuoRec row per
+            # (view, user) in the order of `user_profile_vec` -- no gather for the main rows, no sort in any backward
+            n = int(select_prefix)
+            output = ops.select_prefix_rows(output, n, select_index[n:])
+            prof = torch.cat([ops.gather_rows_sorted(user_profile_vec, select_users[:n]), user_profile_vec])
+            final_vec = enc.sequential(self.output_proj, torch.cat([output, prof.to(output.dtype)], dim=-1))
+            return enc.l2_normalize(final_vec)
         users = select_users
         if users is None:
             users = packed_index // seq_len

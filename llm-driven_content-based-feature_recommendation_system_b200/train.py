@@ -163,6 +163,7 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
         out = model(pretrained_vecs=pretrained_vecs, **kw, training_mode=True, select_index=batch["select_2v"],
                     select_users=batch["users_2v"], cu_seqlens=batch["cu_seqlens_2v"], packed_zero_tail=1, views=2,
                     packed_index=batch["pk_index_2v"], packed_fold_inv=(batch["fold_inv1"], batch["fold_inv2"]),
+                    select_prefix=batch["main_tgt"].numel(),
                     packed_inputs=dict(item_ids=batch["pk_item_ids"], time_bucket_ids=batch["pk_time_ids"],
                                        pos_ids=batch["pk_pos_ids"]), **extra)
         B = batch["item_ids"].shape[0]
@@ -500,10 +501,10 @@ class ShardedDeviceStep(ShardedTwoTower):
         rows, ids, counts, slot_of, meta = ops.owner_compact(cnt, self.world, self.R, cap, want_ids=True)
         return rows, ids, counts, ops.lookup_i32(slot_of, batch["main_tgt"], 0), meta
 
-    def calibrate(self, batches, margin: float = 1.15, col_margin: float = 1.05, q: int = 128):
+    def calibrate(self, batches, margin: float = 1.15, col_margin: float = 1.03, q: int = 128):
         """Fix the per-owner capacities from a few (device-indexed) batches of every rank: largest list seen anywhere,
         plus a margin (request slots only cost exchange volume: generous; column slots cost tensor-core work: the
-        box-wide distinct-target count varies by well under 1 % between batches, 5 % is plenty).  Collective + host
+        box-wide distinct-target count varies by well under 1 % between batches, 3 % is plenty).  Collective + host
         read: start-up only."""
         mf = mc = 0
         for b in batches:
