@@ -180,19 +180,40 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const fl
       sS[i * p.max_len + j] = c * p.scale;
     }
     __syncthreads();
-    // thread k owns feature k of every row
+    // thread k owns feature k of every row; 8 rows (resp. 8 columns) of the coefficient block per pass over the other
+    // index, so that one staged element feeds 8 FMAs (the kernel is instruction-issue bound: ncu r02b, 63 % issue)
     const int k = threadIdx.x;
-    for (int i = 0; i < len; ++i) {
-      float acc = 0.f;
-      for (int j = 0; j < len; ++j) acc = fmaf(sS[i * p.max_len + j], ub_lds1<DT>(sC + j * UB_STRIDE + k), acc);
-      d_u[(r0 + i) * UB_D + k] = acc;
+    for (int i0 = 0; i0 < len; i0 += 8) {
+      float acc[8];
+      int ri[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { acc[e] = 0.f; ri[e] = min(i0 + e, len - 1) * p.max_len; }
+      for (int j = 0; j < len; ++j) {
+        const float c = ub_lds1<DT>(sC + j * UB_STRIDE + k);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(sS[ri[e] + j], c, acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (i0 + e < len) d_u[(r0 + i0 + e) * UB_D + k] = acc[e];
     }
-    for (int j = 0; j < len; ++j) {
-      const int cj = sCol[j];
-      if (cj < 0) continue;
-      float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(sS[i * p.max_len + j], ub_lds1<DT>(sU + i * UB_STRIDE + k), acc);
-      atomicAdd(d_cols + (int64_t)cj * UB_D + k, acc);
+    for (int j0 = 0; j0 < len; j0 += 8) {          // (max_len is a multiple of 4: the second float4 may lie past `len`,
+      float acc[8];                                //  inside the row's padding or the next row -- finite, discarded)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      const bool two = j0 + 4 < p.max_len;
+      for (int i = 0; i < len; ++i) {
+        const float u = ub_lds1<DT>(sU + i * UB_STRIDE + k);
+        const float4 s0 = *reinterpret_cast<const float4*>(sS + i * p.max_len + j0);
+        const float4 s1 = two ? *reinterpret_cast<const float4*>(sS + i * p.max_len + j0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[0] = fmaf(s0.x, u, acc[0]); acc[1] = fmaf(s0.y, u, acc[1]); acc[2] = fmaf(s0.z, u, acc[2]); acc[3] = fmaf(s0.w, u, acc[3]);
+        acc[4] = fmaf(s1.x, u, acc[4]); acc[5] = fmaf(s1.y, u, acc[5]); acc[6] = fmaf(s1.z, u, acc[6]); acc[7] = fmaf(s1.w, u, acc[7]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = j0 + e;
+        if (j < len && sCol[j] >= 0) atomicAdd(d_cols + (int64_t)sCol[j] * UB_D + k, acc[e]);
+      }
     }
   }
 }
