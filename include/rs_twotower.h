@@ -439,6 +439,16 @@ int rs_ensemble_merge(const int64_t* cand_ids, const float* s1, const float* s2,
                       int mode, float k_rrf, const double* alphas /*host*/, int n_alpha, int64_t k_sel,
                       int64_t* out_ids, int32_t* out_cnt, float* out_n1, float* out_n2, void* stream);
 
+/* Same contract as rs_retrieve_topk (same reference lines), with the contraction on the tensor cores as a FILTER:
+ * bf16 candidate pass on tcgen05 (every item whose approximate score is within twice the rounding bound
+ * 2^-8 |u| |i|max of the row's k-th best survives) + exact fp32 re-scoring of the survivors + top-k by (score desc,
+ * id asc): the ids are the fp32 ranking's.  If a candidate list overflows, a device flag routes the call through the
+ * exact fp32 kernel (launched behind, returning at once otherwise).  dim == 128, k <= 32. */
+size_t rs_retrieve_topk_tc_workspace_bytes(int64_t n_users, int64_t n_items, int64_t dim, int64_t k);
+int rs_retrieve_topk_tc(const float* users, int64_t n_users, const float* items, int64_t n_items, int64_t dim,
+                        int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------- C4 / C5: hard-negative mining + sparse logits */
 
 /* Mining (no gradient) of tower_code/v1_refine_usertower.py:775-791 (:643-668, :707-719): for each row i the

@@ -99,6 +99,8 @@ PROTOTYPES = {
     "rs_ensemble_merge": (i32, [vp, vp, vp, i64, i64, i32, f32, vp, i32, i64, vp, vp, vp, vp, vp]),
     "rs_topk_workspace_bytes": (sz, [i64, i64, i64, i64]),
     "rs_retrieve_topk": (i32, [vp, i64, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
+    "rs_retrieve_topk_tc_workspace_bytes": (sz, [i64, i64, i64, i64]),
+    "rs_retrieve_topk_tc": (i32, [vp, i64, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
     "rs_mine_workspace_bytes": (sz, [i64, i64, i64]),
     "rs_mine_hard_negatives": (i32, [vp, vp, vp, i64, i64, i64, f32, vp, vp, vp, vp, sz, vp]),
     "rs_sparse_logits_fwd": (i32, [vp, vp, i32, vp, i64, i64, i64, i64, f32, vp, vp, vp, vp, vp]),

@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
                                                           int k, int mask0, int nsplit, int64_t* __restrict__ out_ids,
                                                           float* __restrict__ out_scores,
                                                           float* __restrict__ part_scores,
-                                                          int* __restrict__ part_ids, MineArgs mine) {
+                                                          int* __restrict__ part_ids, MineArgs mine,
+                                                          const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;      // (uniform) conditional launch: the tensor-core path did not overflow
   constexpr int TM = BM / 16;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lda = dim + 4;
@@ -269,7 +271,9 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ part_scores,
                                                          const int* __restrict__ part_ids, int64_t n_users, int k,
                                                          int nsplit, int64_t* __restrict__ out_ids,
-                                                         float* __restrict__ out_scores) {
+                                                         float* __restrict__ out_scores,
+                                                         const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -339,9 +343,11 @@ extern "C" size_t rs_topk_workspace_bytes(int64_t n_users, int64_t n_items, int6
   return (size_t)n_users * pl.nsplit * k * 8 + 256;
 }
 
-extern "C" int rs_retrieve_topk(const float* users, int64_t n_users, const float* items, int64_t n_items,
-                                int64_t dim, int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+// `run_if` (device int, may be NULL): when given, every kernel of this call returns at once unless *run_if != 0 -- the
+// exact path behind the tensor-core candidate path (topk_tc.cu), taken only when that path flagged an overflow
+int rs_retrieve_topk_cond(const float* users, int64_t n_users, const float* items, int64_t n_items,
+                          int64_t dim, int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
+                          void* workspace, size_t workspace_bytes, const int* run_if, void* stream) {
   if (n_users == 0) return RS_OK;
   if (!users || !items || !out_ids || !out_scores) return RS_ERR_BAD_ARG;
   TopkPlan pl;
@@ -364,16 +370,23 @@ extern "C" int rs_retrieve_topk(const float* users, int64_t n_users, const float
                                          (int)pl.smem);                                                     \
     if (e != cudaSuccess) return (int)e;                                                                    \
     topk_kernel<BM, false><<<grid, TK_THREADS, pl.smem, st>>>(users, n_users, items, n_items, (int)dim, (int)k, \
-                                                       mask_index0, pl.nsplit, out_ids, out_scores, ps, pi, none); \
+                                                       mask_index0, pl.nsplit, out_ids, out_scores, ps, pi, none, run_if); \
   } while (0)
   if (pl.bm == 64) LAUNCH_TK(64); else if (pl.bm == 32) LAUNCH_TK(32); else LAUNCH_TK(16);
   RS_LAUNCH_CHECK();
   if (pl.nsplit > 1) {
     const int g = grid_for_warps(n_users, 8, 8);
-    topk_merge_kernel<<<g, 256, 0, st>>>(ps, pi, n_users, (int)k, pl.nsplit, out_ids, out_scores);
+    topk_merge_kernel<<<g, 256, 0, st>>>(ps, pi, n_users, (int)k, pl.nsplit, out_ids, out_scores, run_if);
     RS_LAUNCH_CHECK();
   }
   return RS_OK;
+}
+
+extern "C" int rs_retrieve_topk(const float* users, int64_t n_users, const float* items, int64_t n_items,
+                                int64_t dim, int64_t k, int mask_index0, int64_t* out_ids, float* out_scores,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  return rs_retrieve_topk_cond(users, n_users, items, n_items, dim, k, mask_index0, out_ids, out_scores, workspace,
+                               workspace_bytes, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -410,13 +423,13 @@ extern "C" int rs_mine_hard_negatives(const float* u, const float* v, const int6
     e = cudaFuncSetAttribute(topk_kernel<BM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
     if (e != cudaSuccess) return (int)e;                                                                    \
     topk_kernel<BM, true><<<grid, TK_THREADS, pl.smem, st>>>(u, n, v, n, (int)dim, (int)k, 0, pl.nsplit,    \
-                                                             out_ids, out_scores, ps, pi, ma);             \
+                                                             out_ids, out_scores, ps, pi, ma, nullptr);    \
   } while (0)
   if (pl.bm == 32) LAUNCH_MINE(32); else LAUNCH_MINE(16);
   RS_LAUNCH_CHECK();
   if (pl.nsplit > 1) {
     const int g = grid_for_warps(n, 8, 8);
-    topk_merge_kernel<<<g, 256, 0, st>>>(ps, pi, n, (int)k, pl.nsplit, out_ids, out_scores);
+    topk_merge_kernel<<<g, 256, 0, st>>>(ps, pi, n, (int)k, pl.nsplit, out_ids, out_scores, nullptr);
     RS_LAUNCH_CHECK();
   }
   return RS_OK;

@@ -376,6 +376,35 @@ def _(users, items, k, mask_index0):
     return users.new_empty(users.shape[0], k), users.new_empty(users.shape[0], k, dtype=torch.int64)
 
 
+TC_RETRIEVAL_CHUNK = 65536      # users per call of the tensor-core path (bounds its candidate workspace to ~0.5 GB)
+
+
+@torch.library.custom_op("rs::retrieve_topk_tc", mutates_args=())
+def retrieve_topk_tc_op(users: Tensor, items: Tensor, k: int, mask_index0: bool) -> Tuple[Tensor, Tensor]:
+    """R1 with a tcgen05 bf16 candidate pass + exact fp32 re-scoring (rs_retrieve_topk_tc): same results contract as
+    retrieve_topk (fp32 ranking, ties by ascending id); dim == 128, k <= 32."""
+    L.require_cuda(users, items)
+    users, items = _f32(users, "user_emb"), _f32(items, "item_emb")
+    nu, dim = users.shape
+    ni = items.shape[0]
+    if k > ni:
+        raise RuntimeError("selected index k out of range")
+    ids = torch.empty(nu, k, dtype=torch.int64, device=users.device)
+    scores = torch.empty(nu, k, dtype=torch.float32, device=users.device)
+    for u0 in range(0, nu, TC_RETRIEVAL_CHUNK):
+        n = min(TC_RETRIEVAL_CHUNK, nu - u0)
+        ws = L.workspace(_lib.rs_retrieve_topk_tc_workspace_bytes(n, ni, dim, k), users.device)
+        L.check(_lib.rs_retrieve_topk_tc(L.ptr(users[u0:u0 + n]), n, L.ptr(items), ni, dim, k, int(mask_index0),
+                                         L.ptr(ids[u0:u0 + n]), L.ptr(scores[u0:u0 + n]), L.ptr(ws), ws.numel(),
+                                         L.stream()), "rs_retrieve_topk_tc")
+    return scores, ids
+
+
+@retrieve_topk_tc_op.register_fake
+def _(users, items, k, mask_index0):
+    return users.new_empty(users.shape[0], k), users.new_empty(users.shape[0], k, dtype=torch.int64)
+
+
 @torch.library.custom_op("rs::fm_fwd", mutates_args=())
 def fm_fwd_op(ids: Tensor, offsets: Tensor, emb: Tensor, lin: Optional[Tensor], want_concat: bool,
               concat_dtype: int) -> Tuple[Tensor, Tensor]:
@@ -945,8 +974,16 @@ def fm_interaction(ids, offsets, emb, lin=None, want_concat=True, concat_dtype=N
     return _FM.apply(ids, offsets, emb, lin, want_concat, cd)
 
 
-def retrieve_topk(user_emb: Tensor, item_emb: Tensor, k: int, mask_index0: bool = False):
-    """R1: topk(user_emb @ item_emb.T, k) -> (scores, ids); score desc, ties by ascending id."""
+RETRIEVAL_TENSOR_CORES = True      # route 128-dim, k <= 32 retrievals through the tcgen05 candidate pass
+
+
+def retrieve_topk(user_emb: Tensor, item_emb: Tensor, k: int, mask_index0: bool = False, tensor_cores=None):
+    """R1: topk(user_emb @ item_emb.T, k) -> (scores, ids); score desc, ties by ascending id.  The ranking is the fp32
+    one on both paths: `tensor_cores` (default: RETRIEVAL_TENSOR_CORES when the shape allows -- 128-dim rows, k <= 32,
+    at least 1024 items) uses the bf16 tcgen05 pass only as a candidate filter in front of exact fp32 re-scoring."""
+    use_tc = RETRIEVAL_TENSOR_CORES if tensor_cores is None else tensor_cores
+    if use_tc and user_emb.shape[-1] == 128 and k <= 32 and item_emb.shape[0] >= 1024:
+        return L.direct.retrieve_topk_tc(user_emb.float(), item_emb.float(), k, mask_index0)
     return L.direct.retrieve_topk(user_emb.float(), item_emb.float(), k, mask_index0)
 
 

@@ -253,6 +253,43 @@ def test_retrieval_all_rows_bit_exact_on_gap_separated_inputs(rs):
     torch.testing.assert_close(sc.cpu(), sc_w, rtol=0, atol=3e-6)
 
 
+@pytest.mark.parametrize("nu,ni,k,mask0", [(1, 1024, 1, False), (130, 5000, 12, True), (3000, 105542, 12, False),
+                                           (200, 20000, 32, False), (70000, 2048, 17, False)])
+def test_retrieval_tensor_core_path_equals_fp32_path(rs, nu, ni, k, mask0):
+    """bf16 tcgen05 candidate pass + exact re-scoring vs the fp32 kernel: same ids everywhere both are unambiguous, same
+    scores; non-unit norms (the rounding bound scales with |u| |i|max), few users (column splits), k up to 32."""
+    g = torch.Generator().manual_seed(nu + ni + k)
+    U = (torch.randn(nu, 128, generator=g) * (0.2 + 3 * torch.rand(nu, 1, generator=g))).to(DEV)
+    I = (torch.randn(ni, 128, generator=g) * (0.5 + torch.rand(ni, 1, generator=g))).to(DEV)
+    sc0, id0 = rs.ops.retrieve_topk(U, I, k, mask0, tensor_cores=False)
+    sc1, id1 = rs.ops.retrieve_topk(U, I, k, mask0, tensor_cores=True)
+    torch.testing.assert_close(sc1, sc0, rtol=1e-5, atol=1e-5)
+    gap = sc0.abs().max(dim=1, keepdim=True).values * 1e-5
+    d = (sc0[:, :-1] - sc0[:, 1:]) > gap if k > 1 else torch.ones(nu, 0, dtype=torch.bool, device=DEV)
+    t = torch.ones(nu, 1, dtype=torch.bool, device=DEV)
+    safe = torch.cat([t, d], 1) & torch.cat([d, t], 1)
+    safe[:, -1] &= (k == ni)                      # the k-th entry competes with the unseen (k+1)-th
+    if k > 1:
+        assert safe.float().mean() > 0.5
+    assert torch.equal(id1[safe], id0[safe])
+    if mask0:
+        assert not (id1 == 0).any()
+    # the ids it returns really carry those scores
+    torch.testing.assert_close(torch.gather(U @ I.T, 1, id1), sc1, rtol=1e-4, atol=1e-4)
+
+
+def test_retrieval_tensor_core_path_falls_back_on_overflow(rs):
+    """every item equal -> every score ties -> every element passes the candidate threshold -> the lists overflow: the
+    device flag routes the call through the exact kernel, ids = ties by ascending id."""
+    g = torch.Generator().manual_seed(5)
+    U = F.normalize(torch.randn(300, 128, generator=g), dim=1).to(DEV)
+    I = F.normalize(torch.randn(1, 128, generator=g), dim=1).repeat(4096, 1).to(DEV)
+    sc0, id0 = rs.ops.retrieve_topk(U, I, 12, False, tensor_cores=False)
+    sc1, id1 = rs.ops.retrieve_topk(U, I, 12, False, tensor_cores=True)
+    assert torch.equal(id1, id0) and torch.equal(id1[0].cpu(), torch.arange(12))
+    torch.testing.assert_close(sc1, sc0, rtol=0, atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------ F1
 @pytest.mark.parametrize("k", [4, 16, 128])
 def test_fm_vs_oracle(rs, k):
