@@ -168,6 +168,7 @@ tt_cand_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int q = 0; q < KT; ++q) top[q] = -INFINITY;
       int cnt = 0;
+      bool first = true;
       const int64_t list = ((int64_t)sp * TT_NWG + wg) * p.n_users + row;
       float2* my = p.cand + list * TT_CAP;
       // all warpgroups are done with the previous item's thresholds before they are reset
@@ -197,9 +198,28 @@ tt_cand_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float mx = __uint_as_float(r[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-          // threshold: k-th largest of the chunk maxima seen so far (each is a distinct item) -- this list's, or
-          // another warpgroup's of the same row when that is tighter
-          if (mx > top[KT - 1]) {
+          // threshold: k-th largest of a set of DISTINCT items' scores seen so far -- every element of the list's first
+          // chunk (so that the bound is finite after 32 >= k elements instead of after k chunks), then one element
+          // per chunk (its maximum) -- this list's, or another warpgroup's of the same row when that is tighter
+          bool changed = false;
+          if (first) {
+            first = false;
+            changed = true;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (v > top[KT - 1]) {
+                top[KT - 1] = v;
+#pragma unroll
+                for (int q = KT - 1; q > 0; --q) {
+                  const float a = top[q - 1], b = top[q];
+                  top[q - 1] = fmaxf(a, b);
+                  top[q] = fminf(a, b);
+                }
+              }
+            }
+          } else if (mx > top[KT - 1]) {
+            changed = true;
             top[KT - 1] = mx;
 #pragma unroll
             for (int q = KT - 1; q > 0; --q) {
@@ -207,6 +227,8 @@ tt_cand_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               top[q - 1] = fmaxf(a, b);
               top[q] = fminf(a, b);
             }
+          }
+          if (changed) {
             float mine = -INFINITY;
 #pragma unroll
             for (int q = 0; q < KT; ++q) if (q == p.k - 1) mine = top[q];
