@@ -46,13 +46,36 @@ def _operand_dtype(*ts) -> torch.dtype:
     return COMPUTE_DTYPE
 
 
+# one-entry-per-tensor memo of 16-bit operand casts inside one loss call: the fused softmax and the user-block kernel
+# of losses.logq_infonce_columns read the SAME rows and columns, each through its own autograd Function (so that the
+# gradients come back in fp32): the cast is done once.  Keyed by storage + version; holds no tensor across calls.
+_cast_memo: dict = {}
+
+
+def _cast16(t: Tensor, dtype: torch.dtype) -> Tensor:
+    t = t.detach()
+    if t.dtype == dtype and t.is_contiguous():
+        return t
+    key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype, dtype)
+    hit = _cast_memo.get(key)
+    if hit is not None:
+        return hit
+    out = t.to(dtype).contiguous()
+    if _cast_memo_on:
+        _cast_memo[key] = out
+    return out
+
+
+_cast_memo_on = False
+
+
 class _FusedSoftmax(torch.autograd.Function):
     """(lse, diag, pos_sum, pos_cnt) = rows of softmax statistics of S = scale*A@B^T - bias (+masks)."""
 
     @staticmethod
     def forward(ctx, a, b, scale, col_bias, key_a_row, key_a_col, key_b_row, key_b_col, diag_offset, mask_value,
                 flags, dtype, logit_bound):
-        a16, b16 = a.detach().to(dtype).contiguous(), b.detach().to(dtype).contiguous()
+        a16, b16 = _cast16(a, dtype), _cast16(b, dtype)
         g_parts = g_info = None
         if FUSE_ROW_GRAD and ctx.needs_input_grad[0] and ops.ce_fwd_grad_supported(
                 a16, flags, mask_value, logit_bound, key_a_row is not None or key_b_row is not None):
@@ -180,6 +203,18 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
     bias = -torch.log(col_counts.float())
     if lq is not None:
         bias = bias + lq
+    global _cast_memo_on
+    _cast_memo_on = True
+    try:
+        return _columns_body(user_emb, col_rows, col_item_ids, target_ids, pos_col, own_cols, lq, bias, scale, dtype,
+                             row_cu, max_rows_per_user, unit_norm, row_weight)
+    finally:
+        _cast_memo_on = False
+        _cast_memo.clear()
+
+
+def _columns_body(user_emb, col_rows, col_item_ids, target_ids, pos_col, own_cols, lq, bias, scale, dtype, row_cu,
+                  max_rows_per_user, unit_norm, row_weight):
     lse0 = fused_softmax_stats(user_emb, col_rows, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
                                mask_value=NEG_INF, flags=L.RS_CE_NO_DIAG, dtype=dtype, unit_norm=unit_norm)[0]
     if row_cu is not None:

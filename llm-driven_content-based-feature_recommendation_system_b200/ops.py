@@ -785,16 +785,15 @@ class _SelectPrefix(torch.autograd.Function):
     the copy, so the result is deterministic although the add is an atomic) -- no sort, no segment reduce."""
 
     @staticmethod
-    def forward(ctx, x, n_prefix, idx):
+    def forward(ctx, x, n_prefix, idx, out_dtype):
         L.require_cuda(x, idx)
         x, idx = x.contiguous(), _ids(idx)
         P, D = x.shape
         m = idx.numel()
-        out = torch.empty(n_prefix + m, D, dtype=x.dtype, device=x.device)
-        out[:n_prefix].copy_(x[:n_prefix])
-        esz = x.element_size()
+        out = torch.empty(n_prefix + m, D, dtype=out_dtype or x.dtype, device=x.device)
+        out[:n_prefix].copy_(x[:n_prefix])                       # (converts on the way when out_dtype differs)
         L.check(_lib.rs_gather_rows(L.ptr(x), L.dt(x), P, D, L.ptr(idx), m, -1,
-                                    L.C.c_void_p(out.data_ptr() + n_prefix * D * esz), L.dt(x),
+                                    L.C.c_void_p(out.data_ptr() + n_prefix * D * out.element_size()), L.dt(out),
                                     L.ptr(L.oob_flag(x.device)), L.stream()), "rs_gather_rows")
         ctx.save_for_backward(idx)
         ctx.meta = (P, n_prefix, x.dtype)
@@ -812,12 +811,13 @@ class _SelectPrefix(torch.autograd.Function):
         tail = g[n_prefix:]
         L.check(_lib.rs_scatter_add_rows(L.ptr(tail), L.dt(tail), L.ptr(idx), idx.numel(), D, P, -1, -1, 1.0, L.ptr(d),
                                          L.ptr(L.oob_flag(g.device)), L.stream()), "rs_scatter_add_rows")
-        return d.to(xdt), None, None
+        return d.to(xdt), None, None, None
 
 
-def select_prefix_rows(x: Tensor, n_prefix: int, idx: Tensor) -> Tensor:
-    """cat([x[:n_prefix], x[idx]]) with a sort-free backward; `idx` must hold distinct rows."""
-    return _SelectPrefix.apply(x, int(n_prefix), idx)
+def select_prefix_rows(x: Tensor, n_prefix: int, idx: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """cat([x[:n_prefix], x[idx]]) with a sort-free backward; `idx` must hold distinct rows.  `out_dtype`: emit the rows
+    in this dtype (the cast a consuming autocast Linear would apply anyway, folded into the copy)."""
+    return _SelectPrefix.apply(x, int(n_prefix), idx, out_dtype)
 
 
 class _GatherRowsSorted(torch.autograd.Function):
@@ -825,10 +825,10 @@ class _GatherRowsSorted(torch.autograd.Function):
     runs of equal ids -- the segment-reduce kernel on (ids, arange) directly, without the radix sort."""
 
     @staticmethod
-    def forward(ctx, table, ids):
+    def forward(ctx, table, ids, out_dtype):
         ctx.save_for_backward(ids)
         ctx.meta = (table.shape[0], table.dtype)
-        return L.direct.gather_rows(table, ids, -1, L.dt(table))
+        return L.direct.gather_rows(table, ids, -1, L.dt(out_dtype or table.dtype))
 
     @staticmethod
     def backward(ctx, g):
@@ -843,12 +843,12 @@ class _GatherRowsSorted(torch.autograd.Function):
         L.check(_lib.rs_segment_reduce_rows(L.ptr(g), L.dt(g), L.ptr(sk), L.ptr(sp), n, dim, rows, -1, None, None,
                                             L.ptr(d_table), None, L.ptr(ws), ws.numel(), L.stream()),
                 "rs_segment_reduce_rows")
-        return d_table.to(tdt), None
+        return d_table.to(tdt), None, None
 
 
-def gather_rows_sorted(table: Tensor, ids: Tensor) -> Tensor:
+def gather_rows_sorted(table: Tensor, ids: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor:
     """`table[ids]` where the caller vouches that `ids` is ascending (sort-free segment-sum backward)."""
-    return _GatherRowsSorted.apply(table, _ids(ids))
+    return _GatherRowsSorted.apply(table, _ids(ids), out_dtype)
 
 
 class _SeqFront(torch.autograd.Function):
@@ -1058,8 +1058,9 @@ def _(u, cols, pos_col, row_cu, max_len, scale, bias, own_lse, g_pos, g_own):
 class _UserBlockLogits(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, cols, pos_col, row_cu, max_len, scale, bias, compute_dtype):
-        uc = u.detach() if compute_dtype is None else u.detach().to(compute_dtype)
-        cc = cols.detach() if compute_dtype is None else cols.detach().to(compute_dtype)
+        from .losses import _cast16              # (shares the cast with the fused softmax of the same loss call)
+        uc = u.detach() if compute_dtype is None else _cast16(u, compute_dtype)
+        cc = cols.detach() if compute_dtype is None else _cast16(cols, compute_dtype)
         s_pos, own = L.direct.user_block_logits(uc, cc, pos_col, row_cu, max_len, scale, bias)
         ctx.save_for_backward(uc, cc, pos_col, row_cu, bias, own)
         ctx.meta = (max_len, scale, u.dtype, cols.dtype)

@@ -207,9 +207,13 @@ class SASRecUserTower(nn.Module):
             # rows (identity), their users ascend (batch-major), and the remaining selected rows are one DuoRec row per
             # (view, user) in the order of `user_profile_vec` -- no gather for the main rows, no sort in any backward
             n = int(select_prefix)
-            output = ops.select_prefix_rows(output, n, select_index[n:])
-            prof = torch.cat([ops.gather_rows_sorted(user_profile_vec, select_users[:n]), user_profile_vec])
-            final_vec = enc.sequential(self.output_proj, torch.cat([output, prof.to(output.dtype)], dim=-1))
+            # the head's first Linear autocasts its input: emit both halves in that dtype right away (a cast commutes
+            # with the concatenation; half the bytes through the cat and through the gradient's split)
+            ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else output.dtype
+            output = ops.select_prefix_rows(output, n, select_index[n:], out_dtype=ad)
+            prof = torch.cat([ops.gather_rows_sorted(user_profile_vec, select_users[:n], out_dtype=ad),
+                              user_profile_vec.to(ad)])
+            final_vec = enc.sequential(self.output_proj, torch.cat([output, prof], dim=-1))
             return enc.l2_normalize(final_vec)
         users = select_users
         if users is None:
