@@ -424,7 +424,14 @@ class _LinearColsumBias(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        y = F.linear(x, weight, bias)                # (autocast, if active, applies here as for nn.Linear)
+        if x.shape[-1] % 8:
+            # a 16-bit operand whose rows are not 16-byte aligned (static_mlp's Linear(100 -> 128)) sends the library to
+            # an sm_80 `align2` GEMM (profiles/r01e_launches.md); the layer is tiny: run it in fp32 (>= the reference's
+            # fp16 autocast precision), whose 400-byte rows are aligned
+            with torch.autocast("cuda", enabled=False):
+                y = F.linear(x.float(), weight.float(), bias.float())
+        else:
+            y = F.linear(x, weight, bias)            # (autocast, if active, applies here as for nn.Linear)
         ctx.save_for_backward(x, weight)
         ctx.bias_dtype = bias.dtype
         return y
