@@ -470,12 +470,59 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segment_tile_kernel(
   }
 }
 
+// Second level of the fix-up.  A Zipf head item spans hundreds of tiles; one warp adding their partial rows one after
+// the other is a serial chain of L2 latencies (ncu r02b: segment_fixup 7-13 % issue, 0.3 % DRAM).  Groups of 32
+// consecutive tiles that lie entirely INSIDE one segment are pre-reduced here, one warp per group, so that the chain
+// walks 32 tiles per step.  Fixed summation order -> deterministic.
+template <int NV>
+__global__ void __launch_bounds__(SEG_WARPS * 32) segment_group_kernel(const int* __restrict__ skeys, int64_t n,
+                                                                       int64_t dim, const float* __restrict__ partL,
+                                                                       float* __restrict__ partG) {
+  const int lane = threadIdx.x & 31;
+  const int vecs = (int)(dim >> 2);
+  const int64_t gw = (int64_t)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * SEG_WARPS;
+  const int64_t ntiles = (n + SEG_TILE - 1) / SEG_TILE;
+  const int64_t ngroups = ntiles / 32;                       // only complete groups can be interior
+  constexpr int FX_G = NV == 1 ? 8 : (NV == 2 ? 4 : 1);
+  for (int64_t g = gw; g < ngroups; g += nw) {
+    const int64_t e0 = g * 32 * SEG_TILE, e1 = e0 + 32 * SEG_TILE;
+    if (e0 == 0 || e1 >= n) continue;
+    const int k = skeys[e0];
+    if (skeys[e0 - 1] != k || skeys[e1 - 1] != k || skeys[e1] != k) continue;
+    float4 acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < 32; j0 += FX_G) {
+      float4 gb[FX_G][NV];
+#pragma unroll
+      for (int q = 0; q < FX_G; ++q)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + 32 * i;
+          gb[q][i] = v < vecs ? *reinterpret_cast<const float4*>(partL + (g * 32 + j0 + q) * dim + 4 * v)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int q = 0; q < FX_G; ++q)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          acc[i].x += gb[q][i].x; acc[i].y += gb[q][i].y; acc[i].z += gb[q][i].z; acc[i].w += gb[q][i].w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < vecs) *reinterpret_cast<float4*>(partG + g * dim + 4 * v) = acc[i];
+    }
+  }
+}
+
 // one warp per tile whose last segment continues into the following tiles and STARTS in this tile
 template <int NV>
 __global__ void __launch_bounds__(SEG_WARPS * 32) segment_fixup_kernel(
     const int* __restrict__ skeys, int64_t n, int64_t dim, int64_t rows, int64_t padding_idx,
     const float* __restrict__ scale_dev, float* __restrict__ d_table, const float* __restrict__ partL,
-    const float* __restrict__ partR) {
+    const float* __restrict__ partR, const float* __restrict__ partG) {
   const int lane = threadIdx.x & 31;
   const int vecs = (int)(dim >> 2);
   const int64_t gw = (int64_t)blockIdx.x * SEG_WARPS + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * SEG_WARPS;
@@ -493,22 +540,40 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segment_fixup_kernel(
       const int v = lane + 32 * i;
       acc[i] = v < vecs ? *reinterpret_cast<const float4*>(partR + tile * dim + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // walk the chain 32 tiles at a time: lane j tests whether the segment runs through tile u0+j, a ballot finds
-    // where it ends, then the partial rows are summed in tile order with FX_G independent loads in flight
-    // (a Zipf head item spans >1000 tiles: a one-tile-per-iteration walk is a serial chain of L2 latencies)
+    // walk the chain: whole groups of 32 tiles that lie inside the segment come pre-reduced from segment_group_kernel;
+    // up to the next group boundary lane j tests whether the segment runs through tile u0+j, a ballot finds where it
+    // ends, and the partial rows are summed in tile order with FX_G independent loads in flight
     constexpr int FX_G = NV == 1 ? 8 : (NV == 2 ? 4 : 1);
     bool more = true;
-    for (int64_t u0 = tile + 1; more && u0 < ntiles; u0 += 32) {
+    int64_t u0 = tile + 1;
+    while (more && u0 < ntiles) {
+      if ((u0 & 31) == 0) {
+        const int64_t e1 = (u0 + 32) * SEG_TILE;             // (skeys[u0 * SEG_TILE - 1] == skeys[u0 * SEG_TILE] == k: inside the chain)
+        if (e1 < n && skeys[e1 - 1] == k && skeys[e1] == k) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < vecs) {
+              const float4 gq = *reinterpret_cast<const float4*>(partG + (u0 >> 5) * dim + 4 * v);
+              acc[i].x += gq.x; acc[i].y += gq.y; acc[i].z += gq.z; acc[i].w += gq.w;
+            }
+          }
+          u0 += 32;
+          continue;
+        }
+      }
+      const int nb = 32 - (int)(u0 & 31);                     // tiles up to the next group boundary
       const int64_t u = u0 + lane;
-      bool through = false;                        // segment covers tile u entirely AND continues past it
-      if (u < ntiles) {
+      bool through = false;                                   // segment covers tile u entirely AND continues past it
+      if (lane < nb && u < ntiles) {
         const int64_t u1 = (u + 1) * SEG_TILE;
         through = (u1 < n) && skeys[u1 - 1] == k && skeys[u1] == k;
       }
       const unsigned bal = __ballot_sync(0xffffffffu, through);
-      const int run = (bal == 0xffffffffu) ? 32 : __ffs(~bal) - 1;   // tiles u0..u0+run-1 pass through; u0+run ends it
-      int last = run < 32 ? run : 31;              // last tile of this batch that contributes a partL piece
-      if (run < 32) more = false;
+      const unsigned full = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+      const int run = (bal == full) ? nb : __ffs(~bal) - 1;   // tiles u0..u0+run-1 pass through; u0+run ends the segment
+      int last = run < nb ? run : nb - 1;                     // last tile of this batch that contributes a partL piece
+      if (run < nb) more = false;
       if (u0 + last >= ntiles) last = (int)(ntiles - 1 - u0);
       for (int j0 = 0; j0 <= last; j0 += FX_G) {
         float4 gb[FX_G][NV];
@@ -528,6 +593,7 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segment_fixup_kernel(
             acc[i].x += gb[q][i].x; acc[i].y += gb[q][i].y; acc[i].z += gb[q][i].z; acc[i].w += gb[q][i].w;
           }
       }
+      u0 += nb;
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -725,7 +791,8 @@ static inline int seg_grid(int64_t n) {
 }
 extern "C" size_t rs_segment_reduce_workspace_bytes(int64_t n, int64_t dim) {
   const size_t ntiles = (size_t)((n + SEG_TILE - 1) / SEG_TILE);
-  return 2 * align256(ntiles * dim * sizeof(float)) + align256((size_t)RS_NUM_SMS * 8 * SEG_WARPS * sizeof(float)) + 256;
+  return 2 * align256(ntiles * dim * sizeof(float)) + align256((size_t)RS_NUM_SMS * 8 * SEG_WARPS * sizeof(float)) +
+         align256((ntiles / 32 + 1) * dim * sizeof(float)) + 256;
 }
 
 extern "C" int rs_segment_reduce_rows(const void* d_out, int d_out_dtype, const int32_t* sorted_ids,
@@ -742,21 +809,25 @@ extern "C" int rs_segment_reduce_rows(const void* d_out, int d_out_dtype, const 
   float* partL = (float*)ws;
   float* partR = (float*)(ws + pb);
   float* dot_part = (float*)(ws + 2 * pb);
+  float* partG = (float*)(ws + 2 * pb + align256((size_t)RS_NUM_SMS * 8 * SEG_WARPS * sizeof(float)));
   const int grid = seg_grid(n);
   if (rows <= 0) return RS_ERR_BAD_ARG;        // keys == rows mark out-of-range ids (rs_sort_ids) and are skipped
   cudaStream_t st = (cudaStream_t)stream;
   const int need = (int)(((dim >> 2) + 31) / 32);
   if (need > 8) return RS_ERR_UNSUPPORTED;
+  const int64_t ngroups = (int64_t)ntiles / 32;
+  const int ggrid = (int)(ngroups < SEG_WARPS ? 1 : (ngroups / SEG_WARPS < (int64_t)RS_NUM_SMS * 8 ? ngroups / SEG_WARPS + 1 : (int64_t)RS_NUM_SMS * 8));
 #define LAUNCH_SEG(GD, NV)                                                                                    \
   do {                                                                                                        \
     segment_tile_kernel<GD, NV><<<grid, SEG_WARPS * 32, 0, st>>>(d_out, sorted_ids, sorted_pos, n, dim, rows, \
                                                                  padding_idx, scale_dev, dot_table, d_table,  \
                                                                  partL, partR, dot_table ? dot_part : nullptr); \
+    segment_group_kernel<NV><<<ggrid, SEG_WARPS * 32, 0, st>>>(sorted_ids, n, dim, partL, partG);             \
     segment_fixup_kernel<NV><<<grid, SEG_WARPS * 32, 0, st>>>(sorted_ids, n, dim, rows, padding_idx, scale_dev, \
-                                                              d_table, partL, partR);                         \
+                                                              d_table, partL, partR, partG);                  \
   } while (0)
   DISPATCH_DT(d_out_dtype, GD, if (need <= 1) LAUNCH_SEG(GD, 1); else if (need <= 2) LAUNCH_SEG(GD, 2); else LAUNCH_SEG(GD, 8));
-  RS_LAUNCH_CHECK_N(2);
+  RS_LAUNCH_CHECK_N(3);
   if (dot_table) {
     dot_finalize_kernel<<<1, 1024, 0, st>>>(dot_part, grid * SEG_WARPS, dot_out);
     RS_LAUNCH_CHECK();
