@@ -430,11 +430,20 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restr
   const int rpi = blockDim.x / c4n;                // rows handled per iteration by this CTA
   const int c4 = threadIdx.x % c4n, rr = threadIdx.x / c4n;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rr < rpi)
-    for (int64_t r = (int64_t)blockIdx.x * rpi + rr; r < n_rows; r += (int64_t)gridDim.x * rpi) {
+  if (rr < rpi) {
+    const int64_t step = (int64_t)gridDim.x * rpi;
+    int64_t r = (int64_t)blockIdx.x * rpi + rr;
+    for (; r + 3 * step < n_rows; r += 4 * step) {            // four independent row loads in flight, fixed add order
+      const float4 v0 = ld4<DT>(x, r * n_cols + 4 * c4), v1 = ld4<DT>(x, (r + step) * n_cols + 4 * c4);
+      const float4 v2 = ld4<DT>(x, (r + 2 * step) * n_cols + 4 * c4), v3 = ld4<DT>(x, (r + 3 * step) * n_cols + 4 * c4);
+      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; r < n_rows; r += step) {
       const float4 v = ld4<DT>(x, r * n_cols + 4 * c4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+  }
   if (rr < rpi) cred[rr * c4n + c4] = s;
   __syncthreads();
   if (rr == 0) {
@@ -543,16 +552,21 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restric
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  float s0 = 0.f, s1 = 0.f;
+  // (8 independent partial rows in flight per warp: the kernel is a chain of L2 latencies otherwise -- ~10 us per call,
+  // 19 calls per step in profiles/r02c_launches.md; the association order is fixed, so the result stays deterministic)
+  float s[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s[q] = 0.f;
   if (c < n_cols_total) {
-    int b = w;
-    for (; b + 8 < n_blocks; b += 16) {
-      s0 += part[(int64_t)b * n_cols_total + c];
-      s1 += part[(int64_t)(b + 8) * n_cols_total + c];
+    for (int b = w; b < n_blocks; b += 64) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int bb = b + 8 * q;
+        if (bb < n_blocks) s[q] += part[(int64_t)bb * n_cols_total + c];
+      }
     }
-    if (b < n_blocks) s0 += part[(int64_t)b * n_cols_total + c];
   }
-  red[w][lane] = s0 + s1;
+  red[w][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   if (w == 0 && c < n_cols_total) {
     float s = red[0][lane];
