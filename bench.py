@@ -549,14 +549,31 @@ def run_bucketed(args, rs, dev, rank, world):
             late_captures.append(j)
             bs.ensure(key)
         t, m, c = bs.run(key)
+        # D2H read of the step's result, every step: the three losses go to pinned memory behind the replay; the host
+        # reads them one step later, after it has enqueued the next step, so that the device never waits for the host
+        # (the graphs share one memory pool: the losses must leave it before the next replay anyway)
+        loss_pin[slot].copy_(torch.stack([t, m, c]), non_blocking=True)
+        loss_ev[slot] = torch.cuda.Event()
+        loss_ev[slot].record()
         if j + 1 < n_e2e:
             stage(j + 1)
-        last["host_loss"] = (t.item(), m.item(), c.item())       # D2H read of the step's result
+        prev = 1 - slot
+        if loss_ev[prev] is not None:
+            loss_ev[prev].synchronize()
+            last["host_loss"] = tuple(loss_pin[prev].tolist())
+            loss_ev[prev] = None
 
+    loss_pin = [torch.zeros(3).pin_memory() for _ in range(2)]
+    loss_ev = [None, None]
     for j in range(W):
         e2e_step(j)
     n_late_warm = len(late_captures)
     ms_e2e, _ = _cuda_timed(args.steps, lambda i: e2e_step(W + i), barrier, dev, world)
+    for ev_, pin_ in zip(loss_ev, loss_pin):                     # the last step's losses
+        if ev_ is not None:
+            ev_.synchronize()
+            last["host_loss"] = tuple(pin_.tolist())
+    assert all(v == v for v in last["host_loss"]), last["host_loss"]
     if trainer is not None:
         trainer.check()
     h2d_bytes = host[0].nbytes
