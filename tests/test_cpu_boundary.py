@@ -152,3 +152,40 @@ def test_host_wrappers_reject_cpu_tensors(rs):
                  lambda: rs.encoder.l2_normalize(torch.randn(5, 128, generator=g))):
         with pytest.raises(RuntimeError, match="CUDA tensors only"):
             call()
+
+
+def _header_struct_fields(name):
+    src = open(os.path.join(ROOT, "include", "rs_twotower.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct \{([^}]*)\}\s*" + name + r"\s*;", src, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    return fields
+
+
+def test_ctypes_structs_mirror_the_header(rs):
+    """rs_ce_problem / rs_batch_index are passed by pointer: the ctypes mirrors must list the same fields in the same order."""
+    L = rs._lib
+    assert [f[0] for f in L.CEProblem._fields_] == _header_struct_fields("rs_ce_problem")
+    assert [f[0] for f in L.BatchIndex._fields_] == _header_struct_fields("rs_batch_index")
+
+
+def test_flat_batch_and_buckets_host_logic(rs):
+    tr, syn = rs.train, rs.synthetic
+    hb = syn.make_batch(16, 50, 500, seed=2)
+    a, b = tr.FlatBatch(16, 50), tr.FlatBatch(16, 50)
+    a.fill(hb)
+    b.copy_(a, non_blocking=False)
+    assert set(b.views) == set(hb) and all(torch.equal(b.views[k], hb[k]) for k in hb)
+    assert all(v.data_ptr() % 256 == a.buf.data_ptr() % 256 for v in a.views.values())     # 256-byte aligned views
+    assert a.nbytes == b.nbytes and a.nbytes >= sum(v.numel() * v.element_size() for v in hb.values())
+    assert tr.bucket_of(1, 1) == (tr.TOK_BUCKET, tr.COL_BUCKET)
+    assert tr.bucket_of(2048, 512) == (2048, 512) and tr.bucket_of(2049, 513) == (4096, 1024)
+    assert tr.bucket_of(100, 70, 64, 32) == (128, 96)
+    bs = tr.BucketedStep(lambda b_: None, 16, 50, 501, "cpu", use_graph=False, tok_q=256, col_q=64)
+    assert bs.bucket(300, 70) == (512, 128) and bs.bucket(300, None) == (512, 512)
