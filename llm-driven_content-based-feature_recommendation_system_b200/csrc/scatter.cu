@@ -2,7 +2,7 @@
 //   * rs_seq_front_bwd      one sequential pass over dX: positional column sums in registers, small
 //                           tables in per-warp private shared-memory copies (no atomics), wide tables
 //                           by 128-bit vector atomics (mode 1) or left to the sorted path (mode 0)
-//   * rs_sort_ids           stable LSD radix sort of (id, position), 8 bits per pass
+//   * rs_sort_ids           stable LSD radix sort of (id, position), 9 bits per pass
 //   * rs_segment_reduce_rows  deterministic segmented sum over the sorted order (tile partials + fix-up)
 #include "common.cuh"
 #include "../../include/rs_twotower.h"
@@ -257,12 +257,18 @@ __global__ void seq_front_bwd_finalize(SeqBwdParams prm, int64_t L, int64_t dim,
 }
 
 // =============================================================================================
-// stable LSD radix sort of (id, position); ids < 2^31
+// stable LSD radix sort of (id, position); ids < 2^31.  9-bit digits: the 105,543-row item table (17-bit keys) sorts
+// in two passes.  Per pass: per-tile digit histogram -> one CTA per digit scans its row of the [digit][tile] table
+// (the single-CTA scan of round 1 was 45 us of every 60 us pass, profiles/r02d) -> stable scatter, which adds the
+// digit bases from a 512-entry block scan of the digit totals.
 // =============================================================================================
 #define SORT_THREADS 256
 #define SORT_WARPS 8
 #define SORT_ITEMS 8                       // rounds of 32 per warp
 #define SORT_TILE (SORT_THREADS * SORT_ITEMS)
+#define SORT_BITS 9
+#define SORT_DIGITS (1 << SORT_BITS)
+#define SORT_DPT (SORT_DIGITS / SORT_THREADS)   // digits per thread
 
 // first pass reads the int64 ids (clamp + range check); later passes read int32 keys
 __device__ __forceinline__ int sort_key_first(const int64_t* ids, int64_t i, int64_t rows, int64_t clamp_max,
@@ -279,44 +285,52 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const int64_t* 
                                                                  int64_t rows, int64_t clamp_max, int shift,
                                                                  int ntiles, unsigned* __restrict__ hist,
                                                                  int* __restrict__ oob) {
-  __shared__ unsigned h[256];
-  h[threadIdx.x] = 0;
+  __shared__ unsigned h[SORT_DIGITS];
+#pragma unroll
+  for (int q = 0; q < SORT_DPT; ++q) h[threadIdx.x + q * SORT_THREADS] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
   for (int k = 0; k < SORT_ITEMS; ++k) {
     const int64_t i = base + k * SORT_THREADS + threadIdx.x;
     if (i < n) {
       const int key = FIRST ? sort_key_first(ids, i, rows, clamp_max, oob) : keys_in[i];
-      atomicAdd(&h[(key >> shift) & 255], 1u);          // integer counts: order-independent
+      atomicAdd(&h[(key >> shift) & (SORT_DIGITS - 1)], 1u);          // integer counts: order-independent
     }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+#pragma unroll
+  for (int q = 0; q < SORT_DPT; ++q) {
+    const int d = threadIdx.x + q * SORT_THREADS;
+    hist[(size_t)d * ntiles + blockIdx.x] = h[d];
+  }
 }
 
-// exclusive scan of hist[256*ntiles] in place (single CTA)
-__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned* __restrict__ hist, int total) {
-  __shared__ unsigned s_warp[32];
-  const int per = (total + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(lo + per, total);
-  unsigned sum = 0;
-  for (int i = lo; i < hi; ++i) sum += hist[i];
-  // block exclusive scan of `sum`
+// CTA d: exclusive scan of hist[d][0..ntiles) in place, total -> totals[d]
+__global__ void __launch_bounds__(SORT_THREADS) sort_scan_kernel(unsigned* __restrict__ hist, int ntiles,
+                                                                 unsigned* __restrict__ totals) {
+  __shared__ unsigned s_warp[SORT_WARPS];
+  __shared__ unsigned s_carry;
+  unsigned* row = hist + (size_t)blockIdx.x * ntiles;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned x = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-  if (lane == 31) s_warp[w] = x;
+  if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  if (w == 0) {
-    unsigned v = s_warp[lane];
+  for (int c0 = 0; c0 < ntiles; c0 += SORT_THREADS) {
+    const int i = c0 + threadIdx.x;
+    const unsigned v = i < ntiles ? row[i] : 0u;
+    unsigned x = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
-    s_warp[lane] = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    unsigned before = s_carry;
+#pragma unroll
+    for (int ww = 0; ww < SORT_WARPS; ++ww) if (ww < w) before += s_warp[ww];
+    if (i < ntiles) row[i] = before + x - v;
+    __syncthreads();
+    if (threadIdx.x == SORT_THREADS - 1) s_carry = before + x;
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned run = (x - sum) + (w > 0 ? s_warp[w - 1] : 0u);
-  for (int i = lo; i < hi; ++i) { unsigned c = hist[i]; hist[i] = run; run += c; }
+  if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
 }
 
 template <bool FIRST>
@@ -325,11 +339,30 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const int64_
                                                                     const int* __restrict__ vals_in, int64_t n,
                                                                     int64_t rows, int64_t clamp_max, int shift,
                                                                     int ntiles, const unsigned* __restrict__ offs,
+                                                                    const unsigned* __restrict__ totals,
                                                                     int* __restrict__ keys_out,
                                                                     int* __restrict__ vals_out) {
-  __shared__ unsigned wcount[SORT_WARPS][256];     // phase A: per-warp digit counts; phase B: running bases
+  __shared__ unsigned wcount[SORT_WARPS][SORT_DIGITS];     // phase A: per-warp digit counts; phase B: running bases
+  __shared__ unsigned dbase[SORT_DIGITS];                   // exclusive scan of the digit totals
+  __shared__ unsigned s_warp[SORT_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&wcount[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < SORT_WARPS * SORT_DIGITS; i += SORT_THREADS) (&wcount[0][0])[i] = 0;
+  {
+    // thread t owns digits [t*DPT, (t+1)*DPT): local sums, block scan, write back
+    unsigned loc[SORT_DPT], sum = 0;
+#pragma unroll
+    for (int q = 0; q < SORT_DPT; ++q) { loc[q] = totals[threadIdx.x * SORT_DPT + q]; sum += loc[q]; }
+    unsigned x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    unsigned run = x - sum;
+#pragma unroll
+    for (int ww = 0; ww < SORT_WARPS; ++ww) if (ww < w) run += s_warp[ww];
+#pragma unroll
+    for (int q = 0; q < SORT_DPT; ++q) { dbase[threadIdx.x * SORT_DPT + q] = run; run += loc[q]; }
+  }
   __syncthreads();
   // warp w owns the contiguous sub-range [base + w*256, base + (w+1)*256) of the tile, walked in order
   const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)w * (32 * SORT_ITEMS);
@@ -346,16 +379,17 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const int64_
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; ++k) {
     const bool live = key[k] >= 0;
-    const int dg = live ? ((key[k] >> shift) & 255) : 256 + lane;      // dead lanes: unique pseudo-digit
+    const int dg = live ? ((key[k] >> shift) & (SORT_DIGITS - 1)) : SORT_DIGITS + lane;   // dead lanes: unique pseudo-digit
     const unsigned peers = __match_any_sync(0xffffffffu, dg);
     if (live && (peers & ((1u << lane) - 1)) == 0) wcount[w][dg] += __popc(peers);
     __syncwarp();
   }
   __syncthreads();
   // exclusive prefix over warps per digit + global offset of (digit, tile)
-  {
-    const int dg = threadIdx.x;     // 256 threads == 256 digits
-    unsigned run = offs[(size_t)dg * ntiles + blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < SORT_DPT; ++q) {
+    const int dg = threadIdx.x + q * SORT_THREADS;
+    unsigned run = dbase[dg] + offs[(size_t)dg * ntiles + blockIdx.x];
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ++ww) { unsigned c = wcount[ww][dg]; wcount[ww][dg] = run; run += c; }
   }
@@ -364,7 +398,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const int64_
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; ++k) {
     const bool live = key[k] >= 0;
-    const int dg = live ? ((key[k] >> shift) & 255) : 256 + lane;
+    const int dg = live ? ((key[k] >> shift) & (SORT_DIGITS - 1)) : SORT_DIGITS + lane;
     const unsigned peers = __match_any_sync(0xffffffffu, dg);
     const int rank = __popc(peers & ((1u << lane) - 1));
     unsigned dst = 0;
@@ -742,7 +776,7 @@ extern "C" int rs_seq_front_bwd(const void* dx, int dx_dtype, const int64_t* con
 static inline int sort_ntiles(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
 
 extern "C" size_t rs_sort_ids_workspace_bytes(int64_t n) {
-  return 4 * align256((size_t)n * sizeof(int)) + align256((size_t)256 * sort_ntiles(n) * sizeof(unsigned)) + 256;
+  return 4 * align256((size_t)n * sizeof(int)) + align256((size_t)SORT_DIGITS * (sort_ntiles(n) + 1) * sizeof(unsigned)) + 256;
 }
 
 extern "C" int rs_sort_ids(const int64_t* ids, int64_t n, int64_t rows, int64_t clamp_max, int32_t* sorted_ids,
@@ -754,27 +788,28 @@ extern "C" int rs_sort_ids(const int64_t* ids, int64_t n, int64_t rows, int64_t 
   if (workspace_bytes < rs_sort_ids_workspace_bytes(n)) return RS_ERR_WORKSPACE;
   int bits = 1;
   while ((1ll << bits) <= rows) ++bits;           // keys lie in [0, rows] (rows == out-of-range marker)
-  const int passes = (bits + 7) / 8;
+  const int passes = (bits + SORT_BITS - 1) / SORT_BITS;
   const int ntiles = sort_ntiles(n);
   char* ws = (char*)workspace;
   const size_t nb = align256((size_t)n * sizeof(int));
   int* kbuf[2] = {(int*)ws, (int*)(ws + nb)};
   int* vbuf[2] = {(int*)(ws + 2 * nb), (int*)(ws + 3 * nb)};
   unsigned* hist = (unsigned*)(ws + 4 * nb);
+  unsigned* totals = hist + (size_t)SORT_DIGITS * ntiles;
   cudaStream_t st = (cudaStream_t)stream;
   const int* kin = nullptr;
   const int* vin = nullptr;
   for (int p = 0; p < passes; ++p) {
-    const int shift = 8 * p;
+    const int shift = SORT_BITS * p;
     int* kout = (p == passes - 1) ? sorted_ids : kbuf[p & 1];
     int* vout = (p == passes - 1) ? sorted_pos : vbuf[p & 1];
     if (p == 0) sort_hist_kernel<true><<<ntiles, SORT_THREADS, 0, st>>>(ids, nullptr, n, rows, clamp_max, shift, ntiles, hist, oob_flag);
     else sort_hist_kernel<false><<<ntiles, SORT_THREADS, 0, st>>>(nullptr, kin, n, rows, clamp_max, shift, ntiles, hist, nullptr);
     RS_LAUNCH_CHECK();
-    sort_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * ntiles);
+    sort_scan_kernel<<<SORT_DIGITS, SORT_THREADS, 0, st>>>(hist, ntiles, totals);
     RS_LAUNCH_CHECK();
-    if (p == 0) sort_scatter_kernel<true><<<ntiles, SORT_THREADS, 0, st>>>(ids, nullptr, nullptr, n, rows, clamp_max, shift, ntiles, hist, kout, vout);
-    else sort_scatter_kernel<false><<<ntiles, SORT_THREADS, 0, st>>>(nullptr, kin, vin, n, rows, clamp_max, shift, ntiles, hist, kout, vout);
+    if (p == 0) sort_scatter_kernel<true><<<ntiles, SORT_THREADS, 0, st>>>(ids, nullptr, nullptr, n, rows, clamp_max, shift, ntiles, hist, totals, kout, vout);
+    else sort_scatter_kernel<false><<<ntiles, SORT_THREADS, 0, st>>>(nullptr, kin, vin, n, rows, clamp_max, shift, ntiles, hist, totals, kout, vout);
     RS_LAUNCH_CHECK();
     kin = kout;
     vin = vout;
