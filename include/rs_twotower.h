@@ -210,6 +210,20 @@ int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int 
 int rs_ln_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, int64_t dim, const float* w,
               const float* b, float eps, float dropout_p, uint64_t seed, void* y, int y_dtype, float* mean,
               float* rstd, void* stream);
+/* y[r,:] = dropout(act(LayerNorm(x[r,:] + add[add_rows ? add_rows[r] : r, :] + lin_bias))), dim == 128; act: 0 identity,
+ * 1 exact (erf) GELU.  The late-fusion head output_proj = Linear(256,128) -> LayerNorm -> GELU -> Linear
+ * (tower_code/v1_refine_usertower.py:394-399, applied to cat([sequence output, user profile]) at :499-510) without the
+ * concatenation: x = the sequence half of the first Linear (one GEMM on the rows), add = the profile half, fp32, one row
+ * per user (`add`, `add_rows`, `lin_bias` nullable).  Also serves static_mlp's LayerNorm -> GELU -> Dropout (:384-389).
+ * Backward: dx[n_rows,128] (x's dtype) = gradient of the LN input of every row; the caller sums it per profile row for
+ * d add and over all rows for d lin_bias.  Workspace: rs_ln_bwd_workspace_bytes(n_rows). */
+int rs_ln_act_fwd(const void* x, int x_dtype, const float* add, const int64_t* add_rows, const float* lin_bias,
+                  int64_t n_rows, int64_t dim, const float* w, const float* b, float eps, int act, float dropout_p,
+                  uint64_t seed, void* y, int y_dtype, float* mean, float* rstd, void* stream);
+int rs_ln_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* add, const int64_t* add_rows,
+                  const float* lin_bias, int64_t n_rows, int64_t dim, const float* w, const float* b, const float* mean,
+                  const float* rstd, int act, float dropout_p, uint64_t seed, void* dx, float* dw, float* db,
+                  void* workspace, size_t workspace_bytes, void* stream);
 size_t rs_ln_bwd_workspace_bytes(int64_t n_rows);
 int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const int64_t* index, int64_t n_rows,
               int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p, uint64_t seed,

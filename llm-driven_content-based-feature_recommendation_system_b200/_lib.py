@@ -76,6 +76,8 @@ PROTOTYPES = {
     "rs_colsum_workspace_bytes": (sz, [i64, i64]),
     "rs_colsum": (i32, [vp, i32, i64, i64, vp, vp, sz, vp]),
     "rs_ln_fwd": (i32, [vp, i32, vp, i64, i64, vp, vp, f32, f32, u64, vp, i32, vp, vp, vp]),
+    "rs_ln_act_fwd": (i32, [vp, i32, vp, vp, vp, i64, i64, vp, vp, f32, i32, f32, u64, vp, i32, vp, vp, vp]),
+    "rs_ln_act_bwd": (i32, [vp, i32, vp, i32, vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, f32, u64, vp, vp, vp, vp, sz, vp]),
     "rs_ln_bwd_workspace_bytes": (sz, [i64]),
     "rs_ln_bwd": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, vp, vp, f32, u64, vp, vp, vp, vp, vp, sz, vp]),
     "rs_dropout_add_fwd": (i32, [vp, i32, vp, i32, vp, i64, i64, f32, u64, vp, vp]),

@@ -664,6 +664,115 @@ __global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LN + activation
+// y[r] = dropout(act(LN(x[r] + add[add_rows[r]] + lin_bias))), act = exact GELU (ACT == 1) or identity.  The late-fusion
+// head (v1_refine_usertower.py:394-399, :499-510) is Linear(256 -> 128) on cat([sequence row, profile row of its user]) -> LayerNorm
+// -> GELU: the Linear splits into a GEMM on the sequence rows (x) and a small GEMM on the distinct profile rows (add, fp32,
+// one row per user), the concat never exists, and LN / GELU / the cast for the next Linear are one pass over the rows.
+// One warp per row, lane owns 4 consecutive features.
+template <int DTI, int DTO, int ACT>
+__global__ void __launch_bounds__(256) ln_act_fwd_kernel(const void* __restrict__ x, const float* __restrict__ add,
+                                                         const int64_t* __restrict__ add_rows,
+                                                         const float* __restrict__ lin_bias, int64_t n_rows,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float eps, uint32_t drop_thresh, float inv_keep, uint64_t seed,
+                                                         void* __restrict__ y, float* __restrict__ mean,
+                                                         float* __restrict__ rstd) {
+  seed = epoch_seed(seed);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w4 = ldg_f4(w + 4 * lane), b4 = ldg_f4(bias + 4 * lane);
+  const float4 lb = lin_bias ? ldg_f4(lin_bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    float4 v = ld4<DTI>(x, r * ENC_D + 4 * lane);
+    if (add) {
+      const int64_t u = add_rows ? __ldg(add_rows + r) : r;
+      const float4 a = ldg_f4(add + u * ENC_D + 4 * lane);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    v.x += lb.x; v.y += lb.y; v.z += lb.z; v.w += lb.w;
+    const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / ENC_D);
+    const float4 c = make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu);
+    const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / ENC_D);
+    const float rs = rsqrtf(var + eps);
+    float4 o = make_float4(c.x * rs * w4.x + b4.x, c.y * rs * w4.y + b4.y, c.z * rs * w4.z + b4.z, c.w * rs * w4.w + b4.w);
+    if (ACT == 1) o = make_float4(gelu_f(o.x), gelu_f(o.y), gelu_f(o.z), gelu_f(o.w));
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      o.x = (rnd32(seed, e, 0x5bd1e995u) >= drop_thresh) ? o.x * inv_keep : 0.f;
+      o.y = (rnd32(seed, e, 1u) >= drop_thresh) ? o.y * inv_keep : 0.f;
+      o.z = (rnd32(seed, e, 2u) >= drop_thresh) ? o.z * inv_keep : 0.f;
+      o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
+    }
+    st4<DTO>(y, r * ENC_D + 4 * lane, o);
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+// dx[r] = gradient w.r.t. the LN input of row r (== gradient of x[r]; the caller sums it over the rows that share a
+// profile row to get d add, and over all rows to get d lin_bias); per-CTA partial d gamma / d beta
+template <int DTI, int DTG, int ACT>
+__global__ void __launch_bounds__(256) ln_act_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+                                                         const float* __restrict__ add,
+                                                         const int64_t* __restrict__ add_rows,
+                                                         const float* __restrict__ lin_bias, int64_t n_rows,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         uint32_t drop_thresh, float inv_keep, uint64_t seed,
+                                                         void* __restrict__ dx, float* __restrict__ part /*[grid][2][128]*/) {
+  __shared__ float4 red[2][8][32];
+  seed = epoch_seed(seed);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w4 = ldg_f4(w + 4 * lane), b4 = ldg_f4(bias + 4 * lane);
+  const float4 lb = lin_bias ? ldg_f4(lin_bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    float4 v = ld4<DTI>(x, r * ENC_D + 4 * lane);
+    if (add) {
+      const int64_t u = add_rows ? __ldg(add_rows + r) : r;
+      const float4 a = ldg_f4(add + u * ENC_D + 4 * lane);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    v.x += lb.x; v.y += lb.y; v.z += lb.z; v.w += lb.w;
+    float4 g = ld4<DTG>(dy, r * ENC_D + 4 * lane);
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      g.x = (rnd32(seed, e, 0x5bd1e995u) >= drop_thresh) ? g.x * inv_keep : 0.f;
+      g.y = (rnd32(seed, e, 1u) >= drop_thresh) ? g.y * inv_keep : 0.f;
+      g.z = (rnd32(seed, e, 2u) >= drop_thresh) ? g.z * inv_keep : 0.f;
+      g.w = (rnd32(seed, e, 3u) >= drop_thresh) ? g.w * inv_keep : 0.f;
+    }
+    const float mu = mean[r], rs = rstd[r];
+    const float4 xh = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+    if (ACT == 1) {
+      g.x *= gelu_grad_f(xh.x * w4.x + b4.x); g.y *= gelu_grad_f(xh.y * w4.y + b4.y);
+      g.z *= gelu_grad_f(xh.z * w4.z + b4.z); g.w *= gelu_grad_f(xh.w * w4.w + b4.w);
+    }
+    dw.x += g.x * xh.x; dw.y += g.y * xh.y; dw.z += g.z * xh.z; dw.w += g.w * xh.w;
+    db.x += g.x; db.y += g.y; db.z += g.z; db.w += g.w;
+    const float4 gw = make_float4(g.x * w4.x, g.y * w4.y, g.z * w4.z, g.w * w4.w);
+    const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
+    const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
+    st4<DTI>(dx, r * ENC_D + 4 * lane,
+             make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
+                         rs * (gw.w - m1 - xh.w * m2)));
+  }
+  red[0][wib][lane] = dw;
+  red[1][wib][lane] = db;
+  __syncthreads();
+  if (wib < 2) {                                   // warp 0 folds dw, warp 1 folds db, in a fixed order
+    float4 s = red[wib][0][lane];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      const float4 t = red[wib][k][lane];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * ENC_D + 4 * lane) = s;
+  }
+}
+
 static inline void drop_consts(float p, uint32_t& thresh, float& inv_keep) {
   if (p <= 0.f) { thresh = 0u; inv_keep = 1.f; return; }
   double t = (double)p * 4294967296.0;
@@ -843,6 +952,53 @@ extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtyp
   float* part = (float*)workspace;
   ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dy_dtype, DTO, (ln_bwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
       dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, residual_grad, part))));
+  RS_LAUNCH_CHECK();
+  partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_ln_act_fwd(const void* x, int x_dtype, const float* add, const int64_t* add_rows,
+                             const float* lin_bias, int64_t n_rows, int64_t dim, const float* w, const float* b,
+                             float eps, int act, float dropout_p, uint64_t seed, void* y, int y_dtype, float* mean,
+                             float* rstd, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!x || !w || !b || !y || !mean || !rstd || n_rows < 0 || (add_rows && !add)) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D || (act != 0 && act != 1)) return RS_ERR_UNSUPPORTED;
+  if (n_rows * (ENC_D / 4) >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+#define LN_ACT_FWD(ACT)                                                                                          \
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(y_dtype, DTO, (ln_act_fwd_kernel<DTI, DTO, ACT><<<grid, 256, 0, st>>>( \
+      x, add, add_rows, lin_bias, n_rows, w, b, eps, th, ik, seed, y, mean, rstd))))
+  if (act == 1) { LN_ACT_FWD(1); } else { LN_ACT_FWD(0); }
+#undef LN_ACT_FWD
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_ln_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* add,
+                             const int64_t* add_rows, const float* lin_bias, int64_t n_rows, int64_t dim,
+                             const float* w, const float* b, const float* mean, const float* rstd, int act,
+                             float dropout_p, uint64_t seed, void* dx, float* dw, float* db, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!dy || !x || !w || !b || !mean || !rstd || !dx || !dw || !db || !workspace || (add_rows && !add))
+    return RS_ERR_BAD_ARG;
+  if (dim != ENC_D || (act != 0 && act != 1)) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_ln_bwd_workspace_bytes(n_rows)) return RS_ERR_WORKSPACE;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  float* part = (float*)workspace;
+#define LN_ACT_BWD(ACT)                                                                                           \
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dy_dtype, DTG, (ln_act_bwd_kernel<DTI, DTG, ACT><<<grid, 256, 0, st>>>( \
+      dy, x, add, add_rows, lin_bias, n_rows, w, b, mean, rstd, th, ik, seed, dx, part))))
+  if (act == 1) { LN_ACT_BWD(1); } else { LN_ACT_BWD(0); }
+#undef LN_ACT_BWD
   RS_LAUNCH_CHECK();
   partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
   RS_LAUNCH_CHECK();

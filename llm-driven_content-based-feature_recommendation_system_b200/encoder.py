@@ -154,6 +154,53 @@ def _(dy, x, index, w, mean, rstd, dropout_p, seed, res=None):
     return [x.new_empty(dy.shape[0], x.shape[1]), torch.empty_like(w), torch.empty_like(w)]
 
 
+@torch.library.custom_op("rs::ln_act", mutates_args=())
+def ln_act_op(x: Tensor, add: Optional[Tensor], add_rows: Optional[Tensor], lin_bias: Optional[Tensor], w: Tensor,
+              b: Tensor, eps: float, act: int, dropout_p: float, seed: int, out_dtype: int) -> List[Tensor]:
+    """dropout(act(LayerNorm(x + add[add_rows] + lin_bias))) for 128-wide rows -> [y, mean, rstd] (rs_ln_act_fwd)."""
+    L.require_cuda(x, w, b)
+    x = x.contiguous()
+    n = x.shape[0]
+    if add is not None:
+        assert add.dtype == torch.float32 and add.is_contiguous() and add.shape[1] == x.shape[1]
+        assert add_rows is None or (add_rows.dtype == torch.int64 and add_rows.numel() == n and add_rows.is_contiguous())
+    y = torch.empty(n, x.shape[1], dtype=L.torch_dtype(out_dtype), device=x.device)
+    mean = torch.empty(n, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+    L.check(_lib.rs_ln_act_fwd(L.ptr(x), L.dt(x), L.ptr(add), L.ptr(add_rows), L.ptr(lin_bias), n, x.shape[1], L.ptr(w),
+                               L.ptr(b), eps, act, dropout_p, seed, L.ptr(y), out_dtype, L.ptr(mean), L.ptr(rstd),
+                               L.stream()), "rs_ln_act_fwd")
+    return [y, mean, rstd]
+
+
+@ln_act_op.register_fake
+def _(x, add, add_rows, lin_bias, w, b, eps, act, dropout_p, seed, out_dtype):
+    n = x.shape[0]
+    return [x.new_empty(n, x.shape[1], dtype=L.torch_dtype(out_dtype)), x.new_empty(n, dtype=torch.float32),
+            x.new_empty(n, dtype=torch.float32)]
+
+
+@torch.library.custom_op("rs::ln_act_bwd", mutates_args=())
+def ln_act_bwd_op(dy: Tensor, x: Tensor, add: Optional[Tensor], add_rows: Optional[Tensor], lin_bias: Optional[Tensor],
+                  w: Tensor, b: Tensor, mean: Tensor, rstd: Tensor, act: int, dropout_p: float, seed: int) -> List[Tensor]:
+    """-> [dx (x's dtype: gradient of the LN input of every row), d gamma, d beta] (rs_ln_act_bwd)."""
+    dy = dy.contiguous()
+    n = dy.shape[0]
+    dx = torch.empty(n, x.shape[1], dtype=x.dtype, device=x.device)
+    dw = torch.empty_like(w)
+    db = torch.empty_like(w)
+    ws = L.workspace(_lib.rs_ln_bwd_workspace_bytes(n), x.device)
+    L.check(_lib.rs_ln_act_bwd(L.ptr(dy), L.dt(dy), L.ptr(x), L.dt(x), L.ptr(add), L.ptr(add_rows), L.ptr(lin_bias), n,
+                               x.shape[1], L.ptr(w), L.ptr(b), L.ptr(mean), L.ptr(rstd), act, dropout_p, seed, L.ptr(dx),
+                               L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(), L.stream()), "rs_ln_act_bwd")
+    return [dx, dw, db]
+
+
+@ln_act_bwd_op.register_fake
+def _(dy, x, add, add_rows, lin_bias, w, b, mean, rstd, act, dropout_p, seed):
+    return [x.new_empty(dy.shape[0], x.shape[1]), torch.empty_like(w), torch.empty_like(w)]
+
+
 @torch.library.custom_op("rs::dropout_add", mutates_args=())
 def dropout_add_op(x: Tensor, y: Tensor, bias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:
     L.require_cuda(x, y)
@@ -292,6 +339,81 @@ def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, index
                             index_fold, inv1, inv2)
 
 
+class _LayerNormAct(torch.autograd.Function):
+    """dropout(act(LayerNorm(x))) in one pass each way (static_mlp's LayerNorm -> GELU -> Dropout)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, act, dropout_p, seed, out_dtype):
+        y, mean, rstd = L.direct.ln_act(x, None, None, None, w, b, eps, act, dropout_p, seed, out_dtype)
+        ctx.save_for_backward(x, w, b, mean, rstd)
+        ctx.meta = (act, dropout_p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, b, mean, rstd = ctx.saved_tensors
+        dx, dw, db = L.direct.ln_act_bwd(g, x, None, None, None, w, b, mean, rstd, *ctx.meta)
+        return dx, dw, db, None, None, None, None, None
+
+
+def layer_norm_act(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, act: str = "gelu",
+                   dropout_p: float = 0.0, out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """dropout(act(LayerNorm(x))) for 128-wide rows; act: "gelu" (exact) or "none"."""
+    od = L.dt(out_dtype) if out_dtype is not None else L.dt(x)
+    return _LayerNormAct.apply(x, weight, bias, float(eps), 1 if act == "gelu" else 0, float(dropout_p),
+                               _seed() if dropout_p > 0 else 0, od)
+
+
+def _mm32(a: Tensor, b: Tensor) -> Tensor:
+    """a @ b with an fp32 result from 16-bit operands (weight gradients: no 16-bit rounding of the sum over ~10^5 rows)."""
+    if a.dtype == torch.float32:
+        return a @ b
+    return torch.mm(a, b, out_dtype=torch.float32)
+
+
+class _FusedHead(torch.autograd.Function):
+    """GELU(LayerNorm(Linear(256 -> 128)(cat([rows, prof[users]], -1)))) -- the first three layers of the late-fusion head
+    (v1_refine_usertower.py:394-399 on :499-502) -- without the concatenation: the Linear splits into W[:, :128] on the
+    sequence rows and W[:, 128:] on the DISTINCT profile rows (one per user instead of one per time step; fp32 result),
+    and rs::ln_act adds the two halves + the bias, normalises, applies the GELU and emits the next Linear's operand dtype.
+    `users` [R] int64: the first `n_sorted` entries ascend (batch-major valid steps), the rest name distinct rows."""
+
+    @staticmethod
+    def forward(ctx, rows, prof, users, n_sorted, W, bias, ln_w, ln_b, eps):
+        cd = rows.dtype
+        Wc = W.to(cd)
+        profc = prof.to(cd)
+        h1 = rows @ Wc[:, :128].t()
+        p2 = _mm32(profc, Wc[:, 128:].t())
+        y, mean, rstd = L.direct.ln_act(h1, p2, users, bias, ln_w, ln_b, eps, 1, 0.0, 0, L.dt(rows))
+        ctx.save_for_backward(rows, profc, users, Wc, bias, ln_w, ln_b, h1, p2, mean, rstd)
+        ctx.meta = (n_sorted, prof.dtype, W.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, profc, users, Wc, bias, ln_w, ln_b, h1, p2, mean, rstd = ctx.saved_tensors
+        n, pdt, wdt = ctx.meta
+        dpre, dlw, dlb = L.direct.ln_act_bwd(g, h1, p2, users, bias, ln_w, ln_b, mean, rstd, 1, 0.0, 0)
+        d_rows = dpre @ Wc[:, :128] if ctx.needs_input_grad[0] else None
+        # d p2 = per-user sums of dpre: a segment sum over the ascending prefix + one distinct row each for the rest
+        dp2 = ops.segment_sum_sorted(dpre[:n], users[:n], p2.shape[0])
+        ops.scatter_add_distinct_(dp2, dpre[n:], users[n:])
+        dbias = _colsum(dp2)
+        dp2c = dp2.to(rows.dtype)
+        dW = torch.cat([_mm32(dpre.t(), rows), _mm32(dp2c.t(), profc)], dim=1).to(wdt)
+        d_prof = (dp2c @ Wc[:, 128:]).to(pdt) if ctx.needs_input_grad[1] else None
+        return d_rows, d_prof, None, None, dW, dbias.to(bias.dtype), dlw, dlb, None
+
+
+def fused_head(rows: Tensor, prof: Tensor, users: Tensor, n_sorted: int, linear: torch.nn.Linear,
+               norm: torch.nn.LayerNorm) -> Tensor:
+    """see _FusedHead; `rows` [R, 128] in the operand dtype of the GEMMs (the autocast dtype), `prof` [U, 128]."""
+    L.require_cuda(rows, prof)
+    return _FusedHead.apply(rows.contiguous(), prof.contiguous(), users.contiguous(), int(n_sorted), linear.weight,
+                            linear.bias, norm.weight, norm.bias, float(norm.eps))
+
+
 class _ResidualLN(torch.autograd.Function):
     """(x, LN(x)) for a pre-norm residual block: x is handed through so that the gradient arriving on the residual path
     and the gradient of the LN branch meet in ONE backward kernel (ln_bwd adds the former to its dx) instead of an
@@ -424,13 +546,17 @@ class _LinearColsumBias(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
+        ctx.xdt = x.dtype
         if x.shape[-1] % 8:
             # a 16-bit operand whose rows are not 16-byte aligned (static_mlp's Linear(100 -> 128)) sends the library to
             # an sm_80 `align2` GEMM (profiles/r01e_launches.md); the layer is tiny: run it in fp32 (>= the reference's
             # fp16 autocast precision), whose 400-byte rows are aligned
             with torch.autocast("cuda", enabled=False):
-                y = F.linear(x.float(), weight.float(), bias.float())
+                x = x.float()
+                y = F.linear(x, weight.float(), bias.float())
         else:
+            if torch.is_autocast_enabled("cuda"):
+                x = x.to(torch.get_autocast_dtype("cuda"))   # the cast autocast applies; kept for the backward (one cast, not two)
             y = F.linear(x, weight, bias)            # (autocast, if active, applies here as for nn.Linear)
         ctx.save_for_backward(x, weight)
         ctx.bias_dtype = bias.dtype
@@ -443,9 +569,9 @@ class _LinearColsumBias(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1]).to(g2.dtype)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = (g2 @ weight.to(g2.dtype)).view(x.shape).to(x.dtype)
+            dx = (g2 @ weight.to(g2.dtype)).view(x.shape).to(ctx.xdt)
         if ctx.needs_input_grad[1]:
-            dw = (g2.t() @ x2).to(weight.dtype)
+            dw = _mm32(g2.t(), x2).to(weight.dtype)
         db = _colsum(g2).to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 
@@ -460,19 +586,44 @@ def linear(module: torch.nn.Linear, x: Tensor) -> Tensor:
     return _LinearColsumBias.apply(x, module.weight, module.bias)
 
 
+def _is_ln128(m, x) -> bool:
+    return (isinstance(m, torch.nn.LayerNorm) and tuple(m.normalized_shape) == (128,) and m.elementwise_affine
+            and m.bias is not None and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+
 def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
-    """`seq(x)` with its nn.Linear members routed through `linear` (same modules, same parameters).  CUDA tensors only."""
+    """`seq(x)` with its nn.Linear members routed through `linear` and LayerNorm(128) [-> GELU [-> Dropout]] runs through
+    the row kernels (same modules, same parameters).  CUDA tensors only."""
     L.require_cuda(x)
-    for m in seq:
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
         if isinstance(m, torch.nn.Linear):
             x = linear(m, x)
-        elif (isinstance(m, torch.nn.LayerNorm) and tuple(m.normalized_shape) == (128,) and m.elementwise_affine
-              and m.bias is not None and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
-            # LayerNorm(128): the row kernel (fp32 statistics and fp32 output, as torch's layer_norm under autocast;
-            # its backward folds d_gamma / d_beta into the same pass)
-            x = layer_norm(x.reshape(-1, 128), m.weight, m.bias, m.eps, out_dtype=torch.float32).view(*x.shape)
+        elif _is_ln128(m, x):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(nxt, torch.nn.GELU) and nxt.approximate == "none":
+                # LayerNorm -> GELU [-> Dropout] in one pass (fp32 statistics, GELU in fp32 as under autocast).  When a
+                # Linear follows under autocast the result is emitted in its operand dtype (the cast it would apply)
+                i += 1
+                p = 0.0
+                after = mods[i + 1] if i + 1 < len(mods) else None
+                if isinstance(after, torch.nn.Dropout):
+                    p = after.p if after.training else 0.0
+                    i += 1
+                    after = mods[i + 1] if i + 1 < len(mods) else None
+                od = torch.float32
+                if isinstance(after, torch.nn.Linear) and torch.is_autocast_enabled("cuda"):
+                    od = torch.get_autocast_dtype("cuda")
+                x = layer_norm_act(x.reshape(-1, 128), m.weight, m.bias, m.eps, "gelu", p, od).view(*x.shape)
+            else:
+                # the row kernel (fp32 statistics and fp32 output, as torch's layer_norm under autocast; its backward
+                # folds d_gamma / d_beta into the same pass)
+                x = layer_norm(x.reshape(-1, 128), m.weight, m.bias, m.eps, out_dtype=torch.float32).view(*x.shape)
         else:
             x = m(x)
+        i += 1
     return x
 
 

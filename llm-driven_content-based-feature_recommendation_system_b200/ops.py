@@ -779,6 +779,29 @@ def gather_rows(table: Tensor, ids: Tensor, padding_idx: int = -1, clamp_max: in
     return _GatherRows.apply(table, ids, padding_idx, clamp_max, od)
 
 
+class _SplitRows(torch.autograd.Function):
+    """torch.split(x, sizes) along dim 0 whose backward is ONE concatenation of the pieces' gradients (the stock slices
+    each allocate a zero tensor of the whole shape, copy their piece into it, and autograd then adds the results)."""
+
+    @staticmethod
+    def forward(ctx, x, *sizes):
+        ctx.sizes = sizes
+        ctx.meta = (x.shape[1:], x.dtype, x.device)
+        return tuple(torch.split(x, list(sizes)))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        tail, dt, dev = ctx.meta
+        parts = [g if g is not None else torch.zeros(n, *tail, dtype=dt, device=dev) for g, n in zip(gs, ctx.sizes)]
+        return (torch.cat([p.to(dt) for p in parts]),) + (None,) * len(ctx.sizes)
+
+
+def split_rows(x: Tensor, *sizes: int):
+    """`torch.split(x, sizes)` (views of x; do not modify them in place) with a single-pass backward."""
+    assert sum(sizes) == x.shape[0]
+    return _SplitRows.apply(x, *[int(n) for n in sizes])
+
+
 class _SelectPrefix(torch.autograd.Function):
     """cat([x[:n_prefix], x[idx]]) for row matrices.  Backward: the prefix's gradient is COPIED into place and the
     gathered rows' gradients are added on top (idx must not repeat a row: every row then has at most one addend after
@@ -820,9 +843,34 @@ def select_prefix_rows(x: Tensor, n_prefix: int, idx: Tensor, out_dtype: Optiona
     return _SelectPrefix.apply(x, int(n_prefix), idx, out_dtype)
 
 
+def segment_sum_sorted(g: Tensor, ids: Tensor, rows: int) -> Tensor:
+    """out[k] = sum of the rows g[i] with ids[i] == k, fp32 [rows, dim], for ASCENDING ids: the segment-reduce kernel on
+    (ids, arange) directly, without the radix sort (fixed summation order)."""
+    g = g.reshape(-1, g.shape[-1]).contiguous()
+    n, dim = g.shape
+    sk = ids.reshape(-1).to(torch.int32)
+    sp = torch.arange(n, dtype=torch.int32, device=g.device)
+    out = torch.zeros(rows, dim, dtype=torch.float32, device=g.device)
+    ws = L.workspace(_lib.rs_segment_reduce_workspace_bytes(n, dim), g.device)
+    L.check(_lib.rs_segment_reduce_rows(L.ptr(g), L.dt(g), L.ptr(sk), L.ptr(sp), n, dim, rows, -1, None, None,
+                                        L.ptr(out), None, L.ptr(ws), ws.numel(), L.stream()),
+            "rs_segment_reduce_rows")
+    return out
+
+
+def scatter_add_distinct_(dst: Tensor, g: Tensor, ids: Tensor) -> Tensor:
+    """dst[ids[i]] += g[i] in place (dst fp32) for DISTINCT ids: one addend per row, so the atomic adds cannot reorder
+    anything and the result is deterministic."""
+    g = g.contiguous()
+    ids = _ids(ids)
+    L.check(_lib.rs_scatter_add_rows(L.ptr(g), L.dt(g), L.ptr(ids), ids.numel(), g.shape[1], dst.shape[0], -1, -1, 1.0,
+                                     L.ptr(dst), L.ptr(L.oob_flag(g.device)), L.stream()), "rs_scatter_add_rows")
+    return dst
+
+
 class _GatherRowsSorted(torch.autograd.Function):
     """table[ids] for ASCENDING ids (e.g. the user of every packed row, batch-major): the backward is a segment sum over
-    runs of equal ids -- the segment-reduce kernel on (ids, arange) directly, without the radix sort."""
+    runs of equal ids (segment_sum_sorted)."""
 
     @staticmethod
     def forward(ctx, table, ids, out_dtype):
@@ -834,16 +882,7 @@ class _GatherRowsSorted(torch.autograd.Function):
     def backward(ctx, g):
         (ids,) = ctx.saved_tensors
         rows, tdt = ctx.meta
-        g = g.reshape(-1, g.shape[-1]).contiguous()
-        n, dim = g.shape
-        sk = ids.reshape(-1).to(torch.int32)
-        sp = torch.arange(n, dtype=torch.int32, device=g.device)
-        d_table = torch.zeros(rows, dim, dtype=torch.float32, device=g.device)
-        ws = L.workspace(_lib.rs_segment_reduce_workspace_bytes(n, dim), g.device)
-        L.check(_lib.rs_segment_reduce_rows(L.ptr(g), L.dt(g), L.ptr(sk), L.ptr(sp), n, dim, rows, -1, None, None,
-                                            L.ptr(d_table), None, L.ptr(ws), ws.numel(), L.stream()),
-                "rs_segment_reduce_rows")
-        return d_table.to(tdt), None, None
+        return segment_sum_sorted(g, ids, rows).to(tdt), None, None
 
 
 def gather_rows_sorted(table: Tensor, ids: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor:

@@ -207,10 +207,17 @@ class SASRecUserTower(nn.Module):
             # rows (identity), their users ascend (batch-major), and the remaining selected rows are one DuoRec row per
             # (view, user) in the order of `user_profile_vec` -- no gather for the main rows, no sort in any backward
             n = int(select_prefix)
-            # the head's first Linear autocasts its input: emit both halves in that dtype right away (a cast commutes
-            # with the concatenation; half the bytes through the cat and through the gradient's split)
+            # the head's first Linear autocasts its input: emit the rows in that dtype right away
             ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else output.dtype
             output = ops.select_prefix_rows(output, n, select_index[n:], out_dtype=ad)
+            # Linear(256 -> 128) -> LayerNorm -> GELU without the [rows, 256] concatenation (encoder.fused_head): the
+            # profile half of the Linear runs once per (view, user) row of `user_profile_vec`, not once per time step
+            op = self.output_proj
+            if (len(op) == 4 and isinstance(op[0], nn.Linear) and op[0].in_features == 256 and op[0].out_features == 128
+                    and op[0].bias is not None and isinstance(op[1], nn.LayerNorm) and isinstance(op[2], nn.GELU)
+                    and op[2].approximate == "none" and output.dtype in (torch.bfloat16, torch.float16)):
+                h = enc.fused_head(output, user_profile_vec, select_users, n, op[0], op[1])
+                return enc.l2_normalize(enc.linear(op[3], h))
             prof = torch.cat([ops.gather_rows_sorted(user_profile_vec, select_users[:n], out_dtype=ad),
                               user_profile_vec.to(ad)])
             final_vec = enc.sequential(self.output_proj, torch.cat([output, prof], dim=-1))

@@ -167,7 +167,8 @@ def _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed, **extra):
                     packed_inputs=dict(item_ids=batch["pk_item_ids"], time_bucket_ids=batch["pk_time_ids"],
                                        pos_ids=batch["pk_pos_ids"]), **extra)
         B = batch["item_ids"].shape[0]
-        return out[:-B], out[-B:]
+        # (main rows, view 1's last steps, view 2's last steps): one split, one concatenation in the backward
+        return ops.split_rows(out, out.shape[0] - 2 * B, B, B)
     if packed and "cu_seqlens_2v" in batch:
         B = batch["item_ids"].shape[0]
         k = "all" if loss_scope == "all" else "last"
@@ -199,14 +200,14 @@ def _losses_device_index(model, item_tower, batch, pretrained_vecs, kw, loss_sco
     L = batch["item_ids"].shape[1]
     tgt = batch["main_tgt"]
     n_main = tgt.numel()
-    out1, out2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
-    u = encoder.l2_normalize(out1[:n_main])                                          # :794-807
+    out_main, last1, last2 = _two_views(model, batch, pretrained_vecs, kw, loss_scope, packed)
+    u = encoder.l2_normalize(out_main)                                               # :794-807
     cid = batch["col_item_ids"]
     v = item_tower.normalized_rows(cid)                                              # :810-811 + :833
     main = losses.logq_infonce_columns(u, v, cid, batch["col_counts"], tgt, batch["pos_col"], None,
                                        item_tower.get_log_q(), 0.1, lambda_logq, unit_norm=True,
                                        row_cu=batch["row_cu"], max_rows_per_user=L, row_weight=batch["row_weight"])
-    cl = losses.duorec_loss_refined(out1[n_main:], out2, batch["last_tgt"], lambda_sup=lambda_sup)   # :830-842
+    cl = losses.duorec_loss_refined(last1, last2, batch["last_tgt"], lambda_sup=lambda_sup)   # :830-842
     return main, cl
 
 
@@ -263,7 +264,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
     with torch.no_grad():
-        pretrained_vecs = ops.gather_rows(pretrained_lookup, _front_item_ids(batch, packed))
+        pretrained_vecs = ops.gather_rows(pretrained_lookup, _front_item_ids(batch, packed), out_dtype=amp_dtype)  # (item_proj's autocast cast, folded in)
     kw = {k: batch[k] for k in FORWARD_KEYS}
     # The encoder is stock nn.TransformerEncoder (as in the reference).  For its shape (L=50, 4 heads x 32, explicit
     # causal + padding mask) PyTorch's default pick on sm_100, the cuDNN flash kernel with 128-wide tiles, is 28 %
@@ -393,7 +394,7 @@ class ShardedTwoTower:
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
-            pretrained_vecs = ops.gather_rows(pretrained_lookup, _front_item_ids(batch, packed))
+            pretrained_vecs = ops.gather_rows(pretrained_lookup, _front_item_ids(batch, packed), out_dtype=amp_dtype)  # (item_proj's autocast cast, folded in)
         kw = {k: batch[k] for k in FORWARD_KEYS}
         # one exchange serves both dropout views (their gradients add up in the buffer before travelling back)
         id_rows = sh.planned_lookup(model.item_id_emb.weight, batch["lookup_plan"], self.group, lead_rows=1,
@@ -537,7 +538,7 @@ class ShardedDeviceStep(ShardedTwoTower):
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
-            pretrained_vecs = ops.gather_rows(pretrained_lookup, batch["pk_item_ids"])
+            pretrained_vecs = ops.gather_rows(pretrained_lookup, batch["pk_item_ids"], out_dtype=amp_dtype)
         kw = {k: batch[k] for k in FORWARD_KEYS}
         # one de-duplicated exchange serves every token of both dropout views
         req, slots, meta_f = self._front_route(batch, self.front_cap)
@@ -546,8 +547,8 @@ class ShardedDeviceStep(ShardedTwoTower):
         with sdpa, torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
             tgt = batch["main_tgt"]
             n_main = tgt.numel()
-            out1, out2 = _two_views(model, batch, pretrained_vecs, kw, "all", packed, item_id_rows=(buf, slots))
-            u = encoder.l2_normalize(out1[:n_main])
+            out_main, last1, last2 = _two_views(model, batch, pretrained_vecs, kw, "all", packed, item_id_rows=(buf, slots))
+            u = encoder.l2_normalize(out_main)
             # columns: the distinct targets of the whole box, owner-major; this rank contributes its own segment
             rows, cid, cnt, pos_col, meta_c = self._col_route(batch, self.col_cap)
             own = rows[self.rank * self.col_cap:(self.rank + 1) * self.col_cap]
@@ -559,7 +560,7 @@ class ShardedDeviceStep(ShardedTwoTower):
             main = losses.logq_infonce_columns(u, v_cols, cid, cnt, tgt, pos_col, None, self.log_q_by_id, 0.1,
                                                lambda_logq, unit_norm=True, row_cu=batch["row_cu"],
                                                max_rows_per_user=L, row_weight=rw)
-            cl = self._duorec(out1[n_main:], out2, batch["last_tgt"], lambda_sup) / self.world
+            cl = self._duorec(last1, last2, batch["last_tgt"], lambda_sup) / self.world
             total = main + lambda_cl * cl
         torch.maximum(self.flag_acc, torch.maximum(meta_f, meta_c), out=self.flag_acc)
         if optimizer is not None:

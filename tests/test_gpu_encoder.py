@@ -353,3 +353,94 @@ def test_l2_normalize_vs_torch(rs, dtype):
     tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(b.grad.float()[rows], a.grad[rows], **tol)
     assert torch.isfinite(b.grad.float()).all()
+
+
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16)])
+def test_layer_norm_gelu_vs_torch(rs, xdt, ydt):
+    """rs::ln_act (LayerNorm -> exact GELU in one pass) against F.layer_norm + F.gelu in fp32."""
+    g = torch.Generator().manual_seed(11)
+    n = 517
+    x = (torch.randn(n, 128, generator=g) * 2 + 0.5).to(xdt)
+    w, b = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    cot = torch.randn(n, 128, generator=g).to(DEV)
+    xr, wr, br = x.float().to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    want = F.gelu(F.layer_norm(xr, (128,), wr, br, 1e-5))
+    (want * cot).sum().backward()
+    xp, wp, bp = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    got = rs.encoder.layer_norm_act(xp, wp, bp, 1e-5, "gelu", 0.0, ydt)
+    assert got.dtype == ydt
+    (got.float() * cot).sum().backward()
+    lo = xdt != torch.float32
+    tol = dict(rtol=2e-2, atol=3e-2) if lo else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got.float(), want.detach(), **tol)
+    torch.testing.assert_close(xp.grad.float(), xr.grad, **tol)
+    torch.testing.assert_close(wp.grad, wr.grad, **(dict(rtol=2e-2, atol=0.3) if lo else dict(rtol=1e-4, atol=1e-3)))
+    torch.testing.assert_close(bp.grad, br.grad, **(dict(rtol=2e-2, atol=0.3) if lo else dict(rtol=1e-4, atol=1e-3)))
+
+
+def test_sequential_fuses_ln_gelu_dropout_like_the_stock_modules(rs):
+    """encoder.sequential on static_mlp's layout (Linear -> LayerNorm -> GELU -> Dropout): eval mode equals the stock
+    modules; in train mode the dropout keeps ~1-p of the entries, scales the kept ones by 1/(1-p), and the backward uses
+    the same mask."""
+    torch.manual_seed(5)
+    seq = torch.nn.Sequential(torch.nn.Linear(100, 128), torch.nn.LayerNorm(128), torch.nn.GELU(), torch.nn.Dropout(0.25)).to(DEV)
+    x = torch.randn(4096, 100, device=DEV)
+    seq.eval()
+    torch.testing.assert_close(rs.encoder.sequential(seq, x), seq(x), rtol=1e-4, atol=1e-4)
+    seq.train()
+    rs.encoder.rng_advance()
+    xg = x.clone().requires_grad_(True)
+    y = rs.encoder.sequential(seq, xg)
+    seq.eval()
+    full = seq(x)
+    kept = y != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - 0.75 * (full != 0).float().mean().item()) < 0.01
+    torch.testing.assert_close(y[kept], (full / 0.75)[kept], rtol=1e-4, atol=1e-4)
+    # the gradient flows only through kept entries: d/dy sum(y) with the mask == the stock modules' gradient of sum(mask * y / 0.75)
+    y.sum().backward()
+    xr = x.clone().requires_grad_(True)
+    (seq(xr) * kept / 0.75).sum().backward()
+    torch.testing.assert_close(xg.grad, xr.grad, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_fused_head_matches_concat_linear_ln_gelu(rs, dtype):
+    """encoder.fused_head (split Linear(256 -> 128), no concatenation, LN + GELU in one pass) against the stock modules in
+    fp32 on cat([rows, prof[users]]): values and every gradient (rows, profile rows, Linear weight / bias, LN gamma /
+    beta).  Tolerance: 16-bit operands (rel 2^-8) through a K = 256 contraction and a LayerNorm."""
+    g = torch.Generator().manual_seed(21)
+    U, n_sorted, extra = 96, 1500, 64
+    lin, ln = torch.nn.Linear(256, 128).to(DEV), torch.nn.LayerNorm(128).to(DEV)
+    with torch.no_grad():
+        ln.weight.add_(torch.randn(128, generator=g).to(DEV) * 0.1)
+        ln.bias.add_(torch.randn(128, generator=g).to(DEV) * 0.1)
+    users = torch.cat([torch.sort(torch.randint(0, U, (n_sorted,), generator=g)).values,
+                       torch.randperm(U, generator=g)[:extra]]).to(DEV)
+    rows = torch.randn(n_sorted + extra, 128, generator=g).to(DEV)
+    prof = torch.randn(U, 128, generator=g).to(DEV)
+    cot = torch.randn(n_sorted + extra, 128, generator=g).to(DEV)
+    rr, pr = rows.clone().requires_grad_(True), prof.clone().requires_grad_(True)
+    want = F.gelu(ln(lin(torch.cat([rr, pr[users]], -1))))
+    (want * cot).sum().backward()
+    ref = [rr.grad, pr.grad, lin.weight.grad.clone(), lin.bias.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()]
+    for p in list(lin.parameters()) + list(ln.parameters()):
+        p.grad = None
+    rp, pp = rows.to(dtype).requires_grad_(True), prof.clone().requires_grad_(True)
+    got = rs.encoder.fused_head(rp, pp, users, n_sorted, lin, ln)
+    assert got.dtype == dtype
+    (got.float() * cot).sum().backward()
+    torch.testing.assert_close(got.float(), want.detach(), rtol=3e-2, atol=3e-2)
+    mine = [rp.grad.float(), pp.grad, lin.weight.grad, lin.bias.grad, ln.weight.grad, ln.bias.grad]
+    for a, b in zip(mine, ref):
+        rel = (a - b).norm() / b.norm()
+        assert rel < 2e-2, rel
+
+
+def test_split_rows_backward_is_one_concatenation(rs):
+    x = torch.randn(100, 8, device=DEV, requires_grad=True)
+    a, b, c = rs.ops.split_rows(x, 70, 20, 10)
+    assert a.shape[0] == 70 and b.shape[0] == 20 and c.shape[0] == 10
+    (a.sum() * 2 + c.sum() * 3).backward()                 # b unused: its gradient is zeros
+    want = torch.cat([torch.full((70, 8), 2.0), torch.zeros(20, 8), torch.full((10, 8), 3.0)]).to(DEV)
+    torch.testing.assert_close(x.grad, want)
