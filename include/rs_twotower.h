@@ -324,6 +324,17 @@ int rs_ce_bwd(const rs_ce_problem* p /*host*/, const float* lse, const float* w_
  * bf16 operands only; no RS_CE_SUPCON; masks must be -inf (a masked entry must carry no softmax mass).
  * lse / diag exactly as rs_ce_fwd. */
 size_t rs_ce_fwd_grad_bytes(const rs_ce_problem* p);
+/* The per-row tail of the in-batch loss over DISTINCT item columns (tower_code/v1_refine_usertower.py:826-861 regrouped by
+ * item, see losses.logq_infonce_columns):  Z_i = e^{lse0_i} + e^{pos_i} - e^{own_i},  loss = sum_i w_i (log max(Z_i, 1e-30)
+ * - pos_i), w_i = row_weight[i] (NULL: 1/n, the mean).  lse0 = log-sum-exp over the columns without the row's own item
+ * (rs_ce_fwd), pos = the label's logit, own = log-sum-exp of the row's user's OTHER targets (NULL: none).  Also returns
+ * the gradient coefficients c_lse0 / c_pos / c_own [n] (d loss / d input).  Fixed-order two-stage sum.  Rows with
+ * w_i == 0 (the padding rows of a bucketed batch) contribute exactly 0 whatever their inputs hold. */
+size_t rs_ce_row_combine_workspace_bytes(int64_t n);
+int rs_ce_row_combine(const float* lse0, const float* pos, const float* own, const float* row_weight, int64_t n,
+                      float* loss, float* c_lse0, float* c_pos, float* c_own, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 int rs_ce_fwd_grad(const rs_ce_problem* p /*host*/, float* lse /*[M]*/, float* diag /*[M]*/, float* g_parts,
                    float* g_info, void* workspace, size_t workspace_bytes, void* stream);
 /* rs_ce_bwd with the row side taken from rs_ce_fwd_grad's outputs: dA = scale * (w_lse/l) * G + scale * w_diag * B[label]

@@ -88,6 +88,8 @@ PROTOTYPES = {
     "rs_ce_fwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_bwd": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_fwd_grad_bytes": (sz, [C.POINTER(CEProblem)]),
+    "rs_ce_row_combine_workspace_bytes": (sz, [i64]),
+    "rs_ce_row_combine": (i32, [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_fwd_grad": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, sz, vp]),
     "rs_ce_bwd_from_grad": (i32, [C.POINTER(CEProblem), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "rs_batch_index_workspace_bytes": (sz, [i64, i64, i64]),

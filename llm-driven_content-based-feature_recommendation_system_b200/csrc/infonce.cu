@@ -1226,6 +1226,61 @@ __global__ void ce_bwd_reduce(const float* __restrict__ part, int nsplit, int64_
   *reinterpret_cast<float4*>(out + i * 4) = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The per-row tail of the distinct-column loss (losses.logq_infonce_columns):
+//   Z_i = e^{lse0_i} + e^{pos_i} - e^{own_i},  loss = sum_i w_i (log Z_i - pos_i)
+// with its three gradient coefficient vectors, in one pass (torch ran ~25 elementwise launches each way for it).
+// Stage 1: per-CTA partial sums in a fixed order; stage 2: one CTA folds the partials (deterministic).
+__global__ void __launch_bounds__(256) ce_row_combine_kernel(const float* __restrict__ lse0, const float* __restrict__ pos,
+                                                             const float* __restrict__ own, const float* __restrict__ w,
+                                                             float w_const, int64_t n, float* __restrict__ c_lse0,
+                                                             float* __restrict__ c_pos, float* __restrict__ c_own,
+                                                             float* __restrict__ part) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float wi = w ? w[i] : w_const;
+    float g0 = 0.f, gp = 0.f, go = 0.f;
+    if (wi != 0.f) {
+      const float a = lse0[i], b = pos[i], c = own ? own[i] : -INFINITY;
+      const float mx = fmaxf(a, b);
+      const float ea = __expf(a - mx), eb = __expf(b - mx), ec = own ? __expf(c - mx) : 0.f;
+      const float z = ea + eb - ec;
+      const bool live = z >= 1e-30f;                       // (clamp_min(1e-30): no gradient through a clamped Z)
+      const float zc = live ? z : 1e-30f;
+      acc += wi * (mx + __logf(zc) - b);
+      const float iz = live ? wi / zc : 0.f;
+      g0 = ea * iz; gp = eb * iz - wi; go = -ec * iz;
+    }
+    c_lse0[i] = g0; c_pos[i] = gp;
+    if (c_own) c_own[i] = go;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = red[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k];
+    part[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256) ce_row_combine_final(const float* __restrict__ part, int nparts,
+                                                            float* __restrict__ loss) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) s += part[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k];
+    *loss = t;
+  }
+}
+
 }  // namespace rs
 
 // =============================================================================================
@@ -1512,6 +1567,28 @@ extern "C" int rs_ce_fwd_grad(const rs_ce_problem* p, float* lse, float* diag, f
   RS_LAUNCH_CHECK();
   ce_fwd_finalize<<<(int)((p->M + 255) / 256), 256, 0, st>>>(p->M, pl.nsplit, k.part_m, k.part_l, nullptr, nullptr, lse,
                                                              nullptr, nullptr);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+#define CE_COMBINE_GRID (RS_NUM_SMS * 2)
+extern "C" size_t rs_ce_row_combine_workspace_bytes(int64_t n) { (void)n; return CE_COMBINE_GRID * sizeof(float); }
+
+extern "C" int rs_ce_row_combine(const float* lse0, const float* pos, const float* own, const float* row_weight,
+                                 int64_t n, float* loss, float* c_lse0, float* c_pos, float* c_own, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!loss || n < 0) return RS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { cudaMemsetAsync(loss, 0, sizeof(float), st); return RS_OK; }
+  if (!lse0 || !pos || !c_lse0 || !c_pos || (own && !c_own) || !workspace) return RS_ERR_BAD_ARG;
+  if (workspace_bytes < rs_ce_row_combine_workspace_bytes(n)) return RS_ERR_WORKSPACE;
+  int grid = (int)((n + 255) / 256);
+  if (grid > CE_COMBINE_GRID) grid = CE_COMBINE_GRID;
+  float* part = (float*)workspace;
+  ce_row_combine_kernel<<<grid, 256, 0, st>>>(lse0, pos, own, row_weight, 1.0f / (float)n, n, c_lse0, c_pos,
+                                              own ? c_own : nullptr, part);
+  RS_LAUNCH_CHECK();
+  ce_row_combine_final<<<1, 256, 0, st>>>(part, grid, loss);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

@@ -23,7 +23,7 @@ masks come from a counter-based hash instead of Philox (same Bernoulli(1-p)/(1-p
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn.functional as F
@@ -364,6 +364,78 @@ def layer_norm_act(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, a
                                _seed() if dropout_p > 0 else 0, od)
 
 
+# 16-bit copies of the GEMM weights for one train step.  Autocast casts every fp32 weight where it is used (one small
+# kernel per weight per step) and autograd casts every weight gradient back (another one): ~35 launches of ~3 us in
+# profiles/r02d_small_launches.txt.  `prepare_weights` makes all the copies with ONE multi-tensor launch at the start of
+# the step; the GEMM wrappers below pick them up and hand fp32 weight gradients straight out of the GEMM.
+_wcache: Dict[int, Tensor] = {}
+_wlists: Dict[int, list] = {}
+
+
+def prepare_weights(module: torch.nn.Module, dtype: Optional[torch.dtype]) -> None:
+    """Refresh the 16-bit copies of `module`'s Linear / attention-projection weights and biases (call once per step,
+    after the optimizer has updated them; `release_weights()` drops them)."""
+    _wcache.clear()
+    if dtype is None or dtype == torch.float32:
+        return
+    ws = _wlists.get(id(module))
+    if ws is None:
+        ws = []
+        for m in module.modules():
+            if isinstance(m, torch.nn.Linear):
+                ws += [m.weight] + ([m.bias] if m.bias is not None else [])
+            elif isinstance(m, torch.nn.MultiheadAttention) and m.in_proj_weight is not None:
+                ws.append(m.in_proj_weight)
+        ws = [w for w in ws if w.dtype == torch.float32 and w.is_cuda]
+        _wlists[id(module)] = ws
+    if not ws:
+        return
+    with torch.no_grad():
+        outs = [torch.empty(w.shape, dtype=dtype, device=w.device) for w in ws]
+        torch._foreach_copy_(outs, ws)
+    for w, o in zip(ws, outs):
+        _wcache[id(w)] = o
+
+
+def release_weights() -> None:
+    _wcache.clear()
+
+
+def _w16(weight: Tensor, dtype: torch.dtype) -> Tensor:
+    """`weight` in `dtype`: the step's prepared copy when there is one, else a fresh cast (no autograd either way)."""
+    if weight.dtype == dtype:
+        return weight.detach()
+    c = _wcache.get(id(weight))
+    if c is not None and c.dtype == dtype:
+        return c
+    return weight.detach().to(dtype)
+
+
+class _MatmulW(torch.autograd.Function):
+    """x @ W^T for an fp32 parameter W and a 16-bit (or fp32) activation x: the GEMM runs in x's dtype on W's prepared
+    copy; the weight gradient comes out of its GEMM in fp32 (no 16-bit rounding of a sum over ~10^5 rows, no cast)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        wb = _w16(weight, x.dtype)
+        ctx.save_for_backward(x, wb)
+        ctx.wdt = weight.dtype
+        return x @ wb.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wb = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        dx = (g2 @ wb).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = _mm32(g2.t(), x.reshape(-1, x.shape[-1])).to(ctx.wdt) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def matmul_w(x: Tensor, weight: Tensor) -> Tensor:
+    """F.linear(x, weight) (no bias) -- see _MatmulW."""
+    return _MatmulW.apply(x, weight)
+
+
 def _mm32(a: Tensor, b: Tensor) -> Tensor:
     """a @ b with an fp32 result from 16-bit operands (weight gradients: no 16-bit rounding of the sum over ~10^5 rows)."""
     if a.dtype == torch.float32:
@@ -381,7 +453,7 @@ class _FusedHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows, prof, users, n_sorted, W, bias, ln_w, ln_b, eps):
         cd = rows.dtype
-        Wc = W.to(cd)
+        Wc = _w16(W, cd)
         profc = prof.to(cd)
         h1 = rows @ Wc[:, :128].t()
         p2 = _mm32(profc, Wc[:, 128:].t())
@@ -546,7 +618,7 @@ class _LinearColsumBias(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        ctx.xdt = x.dtype
+        ctx.xdt, ctx.wdt = x.dtype, weight.dtype
         if x.shape[-1] % 8:
             # a 16-bit operand whose rows are not 16-byte aligned (static_mlp's Linear(100 -> 128)) sends the library to
             # an sm_80 `align2` GEMM (profiles/r01e_launches.md); the layer is tiny: run it in fp32 (>= the reference's
@@ -557,7 +629,9 @@ class _LinearColsumBias(torch.autograd.Function):
         else:
             if torch.is_autocast_enabled("cuda"):
                 x = x.to(torch.get_autocast_dtype("cuda"))   # the cast autocast applies; kept for the backward (one cast, not two)
-            y = F.linear(x, weight, bias)            # (autocast, if active, applies here as for nn.Linear)
+            weight = _w16(weight, x.dtype)                   # the step's prepared 16-bit copies (no per-use cast kernels)
+            with torch.autocast("cuda", enabled=False):
+                y = F.linear(x, weight, _w16(bias, x.dtype))
         ctx.save_for_backward(x, weight)
         ctx.bias_dtype = bias.dtype
         return y
@@ -571,7 +645,7 @@ class _LinearColsumBias(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = (g2 @ weight.to(g2.dtype)).view(x.shape).to(ctx.xdt)
         if ctx.needs_input_grad[1]:
-            dw = _mm32(g2.t(), x2).to(weight.dtype)
+            dw = _mm32(g2.t(), x2).to(ctx.wdt)
         db = _colsum(g2).to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 
@@ -637,13 +711,13 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     x, h = residual_layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ad)
     # the four biases are folded into the kernels that consume the GEMM outputs: plain matmuls, and the bias
     # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
-    qkv = F.linear(h, attn.in_proj_weight)
+    qkv = matmul_w(h, attn.in_proj_weight)
     o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail,
                     bias=attn.in_proj_bias)
-    x = dropout_add(x, F.linear(o, attn.out_proj.weight), layer.dropout1.p if tr else 0.0, bias=attn.out_proj.bias)
+    x = dropout_add(x, matmul_w(o, attn.out_proj.weight), layer.dropout1.p if tr else 0.0, bias=attn.out_proj.bias)
     x, h = residual_layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, ad)
-    f = gelu_dropout(F.linear(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
-    return dropout_add(x, F.linear(f, layer.linear2.weight), layer.dropout2.p if tr else 0.0, bias=layer.linear2.bias)
+    f = gelu_dropout(matmul_w(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
+    return dropout_add(x, matmul_w(f, layer.linear2.weight), layer.dropout2.p if tr else 0.0, bias=layer.linear2.bias)
 
 
 def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,

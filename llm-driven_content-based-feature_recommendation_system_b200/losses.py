@@ -27,12 +27,16 @@ from torch import Tensor
 from . import _lib as L
 from . import ops
 
+_lib = L.load()
+
 COMPUTE_DTYPE = torch.bfloat16
 UNIT_NORM_BOUND = 1.0 + 2.0 ** -6        # |<a, b>| of 16-bit-rounded unit rows
 NEG_INF = float("-inf")
 # True: when the row operand needs a gradient the forward pass also accumulates its unnormalised gradient on the tensor
 # cores (ops.ce_fwd_grad, "flash" form) and the backward runs one tensor-core pass (dB side) instead of two.
 FUSE_ROW_GRAD = True
+# the per-row tail of logq_infonce_columns in one kernel each way (False: the torch expression, kept as the checker)
+FUSE_ROW_COMBINE = True
 
 
 def _operand_dtype(*ts) -> torch.dtype:
@@ -213,6 +217,38 @@ def logq_infonce_columns(user_emb: Tensor, col_rows: Tensor, col_item_ids: Tenso
         _cast_memo.clear()
 
 
+class _RowCombine(torch.autograd.Function):
+    """sum_i w_i (log(e^{lse0_i} + e^{pos_i} - e^{own_i}) - pos_i) and its three gradient vectors in one pass
+    (rs_ce_row_combine) -- the per-row tail of logq_infonce_columns."""
+
+    @staticmethod
+    def forward(ctx, lse0, pos, own, row_weight):
+        lse0, pos = lse0.float().contiguous(), pos.float().contiguous()
+        own = own.float().contiguous() if own is not None else None
+        rw = row_weight.float().contiguous() if row_weight is not None else None
+        n = lse0.numel()
+        loss = torch.empty((), dtype=torch.float32, device=lse0.device)
+        c = torch.empty(3 if own is not None else 2, n, dtype=torch.float32, device=lse0.device)
+        ws = L.workspace(_lib.rs_ce_row_combine_workspace_bytes(n), lse0.device)
+        L.check(_lib.rs_ce_row_combine(L.ptr(lse0), L.ptr(pos), L.ptr(own), L.ptr(rw), n, L.ptr(loss), L.ptr(c[0]),
+                                       L.ptr(c[1]), L.ptr(c[2]) if own is not None else None, L.ptr(ws), ws.numel(),
+                                       L.stream()), "rs_ce_row_combine")
+        ctx.save_for_backward(c)
+        ctx.has_own = own is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (c,) = ctx.saved_tensors
+        d = c * g                                   # one launch for all three vectors
+        return d[0], d[1], (d[2] if ctx.has_own else None), None
+
+
+def row_combine(lse0: Tensor, pos: Tensor, own: Optional[Tensor], row_weight: Optional[Tensor]) -> Tensor:
+    L.require_cuda(lse0, pos)
+    return _RowCombine.apply(lse0, pos, own, row_weight)
+
+
 def _columns_body(user_emb, col_rows, col_item_ids, target_ids, pos_col, own_cols, lq, bias, scale, dtype, row_cu,
                   max_rows_per_user, unit_norm, row_weight):
     lse0 = fused_softmax_stats(user_emb, col_rows, scale, col_bias=bias, key_a_row=target_ids, key_a_col=col_item_ids,
@@ -220,6 +256,8 @@ def _columns_body(user_emb, col_rows, col_item_ids, target_ids, pos_col, own_col
     if row_cu is not None:
         s_pos, own_lse = ops.user_block_logits(user_emb, col_rows, pos_col, row_cu, max_rows_per_user, scale, lq,
                                                compute_dtype=dtype)
+        if FUSE_ROW_COMBINE:
+            return row_combine(lse0, s_pos, own_lse, row_weight)
         mx = torch.maximum(lse0, s_pos).detach()
         z = torch.exp(lse0 - mx) + torch.exp(s_pos - mx) - torch.exp(own_lse - mx)
     else:

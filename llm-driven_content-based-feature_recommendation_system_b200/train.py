@@ -261,6 +261,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
     item_ids = batch["item_ids"]
     B, L = item_ids.shape
     encoder.rng_advance()            # new dropout epoch (also what makes a captured graph draw new masks per replay)
+    encoder.prepare_weights(model, amp_dtype)      # 16-bit copies of the GEMM weights: one multi-tensor launch
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
     with torch.no_grad():
@@ -292,6 +293,7 @@ def two_tower_step(model, item_tower, batch, pretrained_lookup, optimizer=None, 
                 grad_hook()
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
             optimizer.step()
+    encoder.release_weights()
     return total.detach(), main.detach(), cl.detach()
 
 
@@ -391,6 +393,7 @@ class ShardedTwoTower:
         item_ids = batch["item_ids"]
         B, L = item_ids.shape
         encoder.rng_advance()
+        encoder.prepare_weights(model, amp_dtype)
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
@@ -440,6 +443,7 @@ class ShardedTwoTower:
             optimizer.step()
         out = torch.stack([total.detach(), main.detach(), cl.detach()])
         dist.all_reduce(out, group=self.group)                                   # global-batch losses (for logging)
+        encoder.release_weights()
         return out[0], out[1], out[2]
 
     def _duorec(self, e1, e2, tgt, lambda_sup, temperature=0.1):
@@ -535,6 +539,7 @@ class ShardedDeviceStep(ShardedTwoTower):
         dist, sh, model, item_tower = self.dist, self.sh, self.model, self.item_tower
         B, L = batch["item_ids"].shape
         encoder.rng_advance()
+        encoder.prepare_weights(model, amp_dtype)
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
@@ -570,6 +575,7 @@ class ShardedDeviceStep(ShardedTwoTower):
             optimizer.step()
         out = torch.stack([total.detach(), main.detach(), cl.detach()])
         dist.all_reduce(out, group=self.group)                                   # global-batch losses (for logging)
+        encoder.release_weights()
         return out[0], out[1], out[2]
 
     def full_state_dict(self):

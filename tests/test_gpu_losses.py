@@ -493,3 +493,66 @@ def test_fixed_offset_and_folded_paths_vs_oracle(rs, N, V):
     assert abs(a[0].item() - b[0].item()) < 1e-4
     for x, y in zip(a[1], b[1]):
         assert (x - y).abs().max() <= 1e-2 * y.abs().max() + 1e-8
+
+
+def test_row_combine_kernel_matches_torch_expression(rs):
+    """rs_ce_row_combine (per-row tail of logq_infonce_columns: value + three gradient vectors) against the torch
+    expression it replaces, incl. zero-weight rows with non-finite inputs and rows without a same-user term."""
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    lse0 = (torch.randn(n, generator=g) * 3).to(DEV).requires_grad_(True)
+    pos = (torch.randn(n, generator=g) * 3).to(DEV).requires_grad_(True)
+    own_v = pos.detach() - torch.rand(n, generator=g).to(DEV) * 4 - 0.05
+    own_v[::7] = float("-inf")                                  # no other target of the same user
+    own = own_v.clone().requires_grad_(True)
+    w = torch.rand(n, generator=g).to(DEV) / n
+    w[-100:] = 0
+    mx = torch.maximum(lse0, pos).detach()
+    z = torch.exp(lse0 - mx) + torch.exp(pos - mx) - torch.exp(own - mx)
+    want = (((mx + torch.log(z.clamp_min(1e-30))) - pos) * w).sum()
+    want.backward()
+    ref = [lse0.grad.clone(), pos.grad.clone(), own.grad.clone()]
+    lse0.grad = pos.grad = own.grad = None
+    bad = lse0.detach().clone()
+    bad[-50:] = float("nan")                                    # padding rows: weight 0 -> ignored whatever they hold
+    bad.requires_grad_(True)
+    got = rs.losses.row_combine(bad, pos, own, w)
+    (got * 2.0).backward()
+    torch.testing.assert_close(got, want.detach(), rtol=1e-5, atol=1e-6)
+    for a, b in zip([bad.grad, pos.grad, own.grad], ref):
+        torch.testing.assert_close(a, 2.0 * b, rtol=1e-4, atol=1e-9)
+    # mean form, no same-user term
+    got2 = rs.losses.row_combine(lse0.detach(), pos.detach(), None, None)
+    mx = torch.maximum(lse0, pos).detach()
+    want2 = (mx + torch.log(torch.exp(lse0 - mx) + torch.exp(pos - mx)) - pos).mean()
+    torch.testing.assert_close(got2, want2.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_columns_loss_fused_tail_matches_torch_tail(rs):
+    """logq_infonce_columns with the fused per-row tail == with the torch tail (same kernels before it)."""
+    g = torch.Generator().manual_seed(4)
+    B, Lr, U, D = 64, 6, 300, 128
+    n = B * Lr
+    u = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=1).to(DEV)
+    v = torch.nn.functional.normalize(torch.randn(U, D, generator=g), dim=1).to(DEV)
+    tgt_cols = torch.randint(0, U, (n,), generator=g)
+    cid = (torch.randperm(5000, generator=g)[:U].sort().values).to(DEV)
+    cnt = torch.bincount(tgt_cols, minlength=U).float().to(DEV)
+    tgt = cid[tgt_cols.to(DEV)]
+    row_cu = (torch.arange(B + 1, dtype=torch.int32) * Lr).to(DEV)
+    logq = torch.randn(5000, generator=g).to(DEV) * 0.3 - 8
+    w = torch.full((n,), 1.0 / n, device=DEV)
+    outs = []
+    for fused in (True, False):
+        rs.losses.FUSE_ROW_COMBINE = fused
+        try:
+            uu, vv = u.clone().requires_grad_(True), v.clone().requires_grad_(True)
+            loss = rs.losses.logq_infonce_columns(uu, vv, cid, cnt, tgt, tgt_cols.to(DEV), None, logq, 0.1, 1.0,
+                                                  row_cu=row_cu, max_rows_per_user=Lr, unit_norm=True, row_weight=w)
+            loss.backward()
+            outs.append((loss.detach(), uu.grad, vv.grad))
+        finally:
+            rs.losses.FUSE_ROW_COMBINE = True
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5)
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert (a - b).norm() / b.norm() < 1e-3
