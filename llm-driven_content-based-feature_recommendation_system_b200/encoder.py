@@ -702,7 +702,11 @@ def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
 
 
 def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int,
-                         zero_tail: int = 0) -> Tensor:
+                         zero_tail: int = 0, rows=None) -> Tensor:
+    """One pre-norm layer on the packed tokens.  `rows` = (n_prefix, idx): only the rows cat([arange(n_prefix), idx]) are
+    wanted from this layer (idx: rows outside the prefix, -1 = none -> a zero row).  Attention still sees every token --
+    the wanted rows attend to the others -- but everything behind it is position-wise, so the out-projection, the residual
+    adds, the second LayerNorm and the feed-forward block run on the wanted rows alone; returns [n_prefix + len(idx), 128]."""
     if not layer.norm_first or layer.activation_relu_or_gelu != 2:
         raise NotImplementedError("packed encoder: pre-norm GELU layers only (the reference's configuration)")
     tr = layer.training
@@ -714,6 +718,9 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     qkv = matmul_w(h, attn.in_proj_weight)
     o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail,
                     bias=attn.in_proj_bias)
+    if rows is not None:
+        o = ops.select_prefix_rows(o, rows[0], rows[1], disjoint=True)
+        x = ops.select_prefix_rows(x, rows[0], rows[1], disjoint=True)
     x = dropout_add(x, matmul_w(o, attn.out_proj.weight), layer.dropout1.p if tr else 0.0, bias=attn.out_proj.bias)
     x, h = residual_layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, ad)
     f = gelu_dropout(matmul_w(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
@@ -721,10 +728,12 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
 
 
 def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,
-                   zero_tail: int = 0) -> Tensor:
-    """x: [T, 128] fp32 residual stream of the packed valid tokens -> same shape."""
-    for layer in encoder.layers:
-        x = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail)
+                   zero_tail: int = 0, last_rows=None) -> Tensor:
+    """x: [T, 128] fp32 residual stream of the packed valid tokens -> same shape; with `last_rows` = (n_prefix, idx) only
+    those rows of the LAST layer's output, [n_prefix + len(idx), 128] (see packed_encoder_layer)."""
+    n_layers = len(encoder.layers)
+    for i, layer in enumerate(encoder.layers):
+        x = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail, last_rows if i == n_layers - 1 else None)
     if encoder.norm is not None:
         x = encoder.norm(x)
     return x

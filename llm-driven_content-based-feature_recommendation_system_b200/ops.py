@@ -805,10 +805,12 @@ def split_rows(x: Tensor, *sizes: int):
 class _SelectPrefix(torch.autograd.Function):
     """cat([x[:n_prefix], x[idx]]) for row matrices.  Backward: the prefix's gradient is COPIED into place and the
     gathered rows' gradients are added on top (idx must not repeat a row: every row then has at most one addend after
-    the copy, so the result is deterministic although the add is an atomic) -- no sort, no segment reduce."""
+    the copy, so the result is deterministic although the add is an atomic) -- no sort, no segment reduce.
+    `disjoint`: the caller vouches that every idx entry is either -1 (the null id: a zero row, no gradient) or a row
+    OUTSIDE the prefix; the backward is then pure data movement in x's own dtype (copy, clear, row scatter)."""
 
     @staticmethod
-    def forward(ctx, x, n_prefix, idx, out_dtype):
+    def forward(ctx, x, n_prefix, idx, out_dtype, disjoint):
         L.require_cuda(x, idx)
         x, idx = x.contiguous(), _ids(idx)
         P, D = x.shape
@@ -818,29 +820,39 @@ class _SelectPrefix(torch.autograd.Function):
         L.check(_lib.rs_gather_rows(L.ptr(x), L.dt(x), P, D, L.ptr(idx), m, -1,
                                     L.C.c_void_p(out.data_ptr() + n_prefix * D * out.element_size()), L.dt(out),
                                     L.ptr(L.oob_flag(x.device)), L.stream()), "rs_gather_rows")
+        if disjoint:
+            idx = torch.where(idx < 0, P, idx)                   # null ids -> a scratch row behind the matrix
         ctx.save_for_backward(idx)
-        ctx.meta = (P, n_prefix, x.dtype)
+        ctx.meta = (P, n_prefix, x.dtype, disjoint)
         return out
 
     @staticmethod
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
-        P, n_prefix, xdt = ctx.meta
+        P, n_prefix, xdt, disjoint = ctx.meta
         g = g.contiguous()
         D = g.shape[1]
+        if disjoint:
+            d = torch.empty(P + 1, D, dtype=xdt, device=g.device)
+            d[:n_prefix].copy_(g[:n_prefix])
+            d[n_prefix:].zero_()
+            d.index_copy_(0, idx, g[n_prefix:].to(xdt))
+            return d[:P], None, None, None, None
         d = torch.empty(P, D, dtype=torch.float32, device=g.device)
         d[:n_prefix].copy_(g[:n_prefix])
         d[n_prefix:].zero_()
         tail = g[n_prefix:]
         L.check(_lib.rs_scatter_add_rows(L.ptr(tail), L.dt(tail), L.ptr(idx), idx.numel(), D, P, -1, -1, 1.0, L.ptr(d),
                                          L.ptr(L.oob_flag(g.device)), L.stream()), "rs_scatter_add_rows")
-        return d.to(xdt), None, None, None
+        return d.to(xdt), None, None, None, None
 
 
-def select_prefix_rows(x: Tensor, n_prefix: int, idx: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor:
+def select_prefix_rows(x: Tensor, n_prefix: int, idx: Tensor, out_dtype: Optional[torch.dtype] = None,
+                       disjoint: bool = False) -> Tensor:
     """cat([x[:n_prefix], x[idx]]) with a sort-free backward; `idx` must hold distinct rows.  `out_dtype`: emit the rows
-    in this dtype (the cast a consuming autocast Linear would apply anyway, folded into the copy)."""
-    return _SelectPrefix.apply(x, int(n_prefix), idx, out_dtype)
+    in this dtype (the cast a consuming autocast Linear would apply anyway, folded into the copy).  `disjoint`: see
+    _SelectPrefix."""
+    return _SelectPrefix.apply(x, int(n_prefix), idx, out_dtype, bool(disjoint))
 
 
 def segment_sum_sorted(g: Tensor, ids: Tensor, rows: int) -> Tensor:

@@ -199,17 +199,24 @@ class SASRecUserTower(nn.Module):
         x = enc.layer_norm(seq_emb.reshape(-1, seq_emb.shape[-1]), self.emb_ln.weight, self.emb_ln.bias, self.emb_ln.eps,
                            index=packed_index, dropout_p=self.emb_dropout.p if tr else 0.0, out_dtype=torch.float32,
                            index_fold=packed_fold, index_inv=packed_fold_inv)
-        output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
-        if not training_mode:
-            select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1
         if select_prefix is not None:
             # device-built index (ops.batch_index_build): the first `select_prefix` selected rows ARE the first packed
             # rows (identity), their users ascend (batch-major), and the remaining selected rows are one DuoRec row per
-            # (view, user) in the order of `user_profile_vec` -- no gather for the main rows, no sort in any backward
+            # (view, user) in the order of `user_profile_vec` -- no gather for the main rows, no sort in any backward.
+            # Only those rows are read from the encoder, so its last layer runs its position-wise half on them alone
+            # (half the tokens: the second dropout view feeds nothing but its DuoRec rows).  A DuoRec row that lies
+            # inside the prefix is NOT computed a second time (it would draw other dropout masks than the main-loss row
+            # it is, v1_usertower_train.py:788-842): it is picked from the prefix afterwards.
             n = int(select_prefix)
+            tail = select_index[n:]
+            m = tail.numel()
+            inside = tail < n
+            output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail,
+                                        last_rows=(n, torch.where(inside, -1, tail)))
+            pick = torch.where(inside, tail, n + torch.arange(m, device=tail.device))
             # the head's first Linear autocasts its input: emit the rows in that dtype right away
             ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else output.dtype
-            output = ops.select_prefix_rows(output, n, select_index[n:], out_dtype=ad)
+            output = ops.select_prefix_rows(output, n, pick, out_dtype=ad)
             # Linear(256 -> 128) -> LayerNorm -> GELU without the [rows, 256] concatenation (encoder.fused_head): the
             # profile half of the Linear runs once per (view, user) row of `user_profile_vec`, not once per time step
             op = self.output_proj
@@ -222,6 +229,9 @@ class SASRecUserTower(nn.Module):
                               user_profile_vec.to(ad)])
             final_vec = enc.sequential(self.output_proj, torch.cat([output, prof], dim=-1))
             return enc.l2_normalize(final_vec)
+        output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
+        if not training_mode:
+            select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1
         users = select_users
         if users is None:
             users = packed_index // seq_len
