@@ -243,6 +243,16 @@ int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, int64_t n_c
                         uint64_t seed, void* out, void* stream);
 int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
                         float dropout_p, uint64_t seed, void* dz, void* stream);
+/* The two backward kernels with the bias gradient folded in: d_bias[n_cols] = column sums of their output (fp32, fixed
+ * order), no second pass over dy / dz.  n_cols / 4 must divide 256.  Workspace: rs_ew_colsum_workspace_bytes(n, n_cols).
+ * For 16-bit activations the GELU uses erfc by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 << the 2^-9 rounding of the
+ * result); fp32 activations use erff. */
+size_t rs_ew_colsum_workspace_bytes(int64_t n, int64_t n_cols);
+int rs_dropout_bwd_bias(const void* g, int g_dtype, int64_t n, int64_t n_cols, float dropout_p, uint64_t seed, void* dy,
+                        int dy_dtype, float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+int rs_gelu_dropout_bwd_bias(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
+                             float dropout_p, uint64_t seed, void* dz, float* d_bias, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* Advance the device-side dropout epoch that every kernel above mixes into its (by-value) seed.  Stream-ordered: call
  * it once at the start of a train step.  Inside a captured CUDA graph it is what makes every REPLAY draw new masks. */
 int rs_rng_advance(void* stream);

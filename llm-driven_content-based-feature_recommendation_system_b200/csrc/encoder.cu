@@ -546,22 +546,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
 }
 
 // out[c] = sum_b part[b][c] over n_blocks partial rows of n_cols_total columns, fixed order (deterministic).
-// One CTA per 32 columns; warp w adds partial rows w, w+8, ... (coalesced 128 B reads), then the 8 warps are folded.
-__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, int n_blocks, int n_cols_total,
-                                                          float* __restrict__ out0, float* __restrict__ out1, int split) {
-  __shared__ float red[8][32];
+// One CTA of 32 warps per 32 columns; warp w adds partial rows w, w+32, ... (coalesced 128 B reads, 8 independent rows
+// in flight), then the 32 warps are folded.  (profiles/r02d_launches.md: with 8 warps per CTA a call was a chain of ~19
+// exposed memory latencies, ~20 us cold, 19 calls per step.)
+#define PS_WARPS 32
+__global__ void __launch_bounds__(PS_WARPS * 32) partial_sum_kernel(const float* __restrict__ part, int n_blocks,
+                                                                    int n_cols_total, float* __restrict__ out0,
+                                                                    float* __restrict__ out1, int split) {
+  __shared__ float red[PS_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  // (8 independent partial rows in flight per warp: the kernel is a chain of L2 latencies otherwise -- ~10 us per call,
-  // 19 calls per step in profiles/r02c_launches.md; the association order is fixed, so the result stays deterministic)
   float s[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) s[q] = 0.f;
   if (c < n_cols_total) {
-    for (int b = w; b < n_blocks; b += 64) {
+    for (int b = w; b < n_blocks; b += 8 * PS_WARPS) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int bb = b + 8 * q;
+        const int bb = b + PS_WARPS * q;
         if (bb < n_blocks) s[q] += part[(int64_t)bb * n_cols_total + c];
       }
     }
@@ -569,10 +571,11 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restric
   red[w][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   if (w == 0 && c < n_cols_total) {
-    float s = red[0][lane];
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s += red[k][lane];
-    if (c < split) out0[c] = s; else if (out1) out1[c - split] = s;
+    for (int k = 0; k < PS_WARPS; k += 4) { t[0] += red[k][lane]; t[1] += red[k + 1][lane]; t[2] += red[k + 2][lane]; t[3] += red[k + 3][lane]; }
+    const float r = (t[0] + t[1]) + (t[2] + t[3]);
+    if (c < split) out0[c] = r; else if (out1) out1[c - split] = r;
   }
 }
 
@@ -601,11 +604,30 @@ __global__ void __launch_bounds__(256) dropout_add_fwd_kernel(const void* __rest
     st4<DTX>(out, 4 * i, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
   }
 }
-// dy = dropout_mask(g)     g DTX (fp32), dy DTY
+// Column sums fused into a grid-stride elementwise kernel over a [rows, 4*c4n] matrix walked as float4 groups: with
+// 256 % c4n == 0 the grid stride is a multiple of c4n, so a thread meets ONE column group (threadIdx.x % c4n) and keeps
+// its sum in registers; the CTA folds the 256 / c4n threads of a group in a fixed order -> part[blockIdx.x][4*c4n].
+__device__ __forceinline__ void cta_colsum(float4 cs, int c4n, float4* cred, float* __restrict__ part) {
+  cred[threadIdx.x] = cs;
+  __syncthreads();
+  if ((int)threadIdx.x < c4n) {
+    float4 s = cred[threadIdx.x];
+    for (int k = threadIdx.x + c4n; k < 256; k += c4n) {
+      const float4 t = cred[k];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * c4n + threadIdx.x) * 4) = s;
+  }
+}
+
+// dy = dropout_mask(g)     g DTX (fp32), dy DTY    (+ per-CTA column sums of dy -> part when given)
 template <int DTX, int DTY>
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const void* __restrict__ g, int64_t n4, uint32_t drop_thresh,
-                                                          float inv_keep, uint64_t seed, void* __restrict__ dy) {
+                                                          float inv_keep, uint64_t seed, void* __restrict__ dy, int c4n,
+                                                          float* __restrict__ part) {
+  __shared__ float4 cred[256];
   seed = epoch_seed(seed);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 b = ld4<DTX>(g, 4 * i);
     if (drop_thresh) {
@@ -616,7 +638,9 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const void* __restrict
       b.w = (rnd32(seed, e, 3u) >= drop_thresh) ? b.w * inv_keep : 0.f;
     }
     st4<DTY>(dy, 4 * i, b);
+    cs.x += b.x; cs.y += b.y; cs.z += b.z; cs.w += b.w;
   }
+  if (part) cta_colsum(cs, c4n, cred, part);
 }
 
 template <int DT> __device__ __forceinline__ float round_dt(float x) {
@@ -630,13 +654,40 @@ __device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.f + erff
 __device__ __forceinline__ float gelu_grad_f(float z) {
   return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
 }
-// out = dropout(gelu(z + bias)) ; BWD: dz = dropout_mask(g) * gelu'(z + bias)
+// 16-bit activations: Phi(z) = 0.5 erfc(-z / sqrt 2) with erfc by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, three
+// orders of magnitude below the 2^-9 rounding of the result): one ex2 + one rcp + 6 FMAs instead of libdevice's erff, and
+// the backward's exp(-z^2/2) is the same exponential.  The kernels were issue-bound on erff + the dropout hashes
+// (profiles/r02d_launches.md: 2.3 TB/s of a 6.5 TB/s stream).  fp32 activations keep erff.
+__device__ __forceinline__ void phi_fast(float z, float& Phi, float& e) {
+  const float x = fabsf(z) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+  e = __expf(-x * x);                                                    // = exp(-z^2 / 2)
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float half_erfc = 0.5f * poly * e;                               // 0.5 erfc(|z| / sqrt 2)
+  Phi = z >= 0.f ? 1.f - half_erfc : half_erfc;
+}
+template <int DT> __device__ __forceinline__ float gelu_dt(float z) {
+  if constexpr (DT == RS_F32) return gelu_f(z);
+  float Phi, e;
+  phi_fast(z, Phi, e);
+  return z * Phi;
+}
+template <int DT> __device__ __forceinline__ float gelu_grad_dt(float z) {
+  if constexpr (DT == RS_F32) return gelu_grad_f(z);
+  float Phi, e;
+  phi_fast(z, Phi, e);
+  return fmaf(z * 0.3989422804014327f, e, Phi);
+}
+// out = dropout(gelu(z + bias)) ; BWD: dz = dropout_mask(g) * gelu'(z + bias)  (+ per-CTA column sums of dz -> part,
+// the bias gradient, when `part` is given: thread t of every CTA always meets column group t % c4n)
 template <int DT, bool BWD>
 __global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restrict__ z, const void* __restrict__ g,
                                                            const float* __restrict__ bias, int c4n, int64_t n4,
                                                            uint32_t drop_thresh, float inv_keep, uint64_t seed,
-                                                           void* __restrict__ out) {
+                                                           void* __restrict__ out, float* __restrict__ part) {
+  __shared__ float4 cred[256];
   seed = epoch_seed(seed);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = ld4<DT>(z, 4 * i);
     if (bias) {
@@ -647,11 +698,12 @@ __global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restric
     float4 o;
     if (BWD) {
       const float4 gg = ld4<DT>(g, 4 * i);
-      o = make_float4(gg.x * gelu_grad_f(a.x), gg.y * gelu_grad_f(a.y), gg.z * gelu_grad_f(a.z), gg.w * gelu_grad_f(a.w));
+      o = make_float4(gg.x * gelu_grad_dt<DT>(a.x), gg.y * gelu_grad_dt<DT>(a.y), gg.z * gelu_grad_dt<DT>(a.z),
+                      gg.w * gelu_grad_dt<DT>(a.w));
     } else {
       // the reference's gelu output is rounded to the activation dtype BEFORE its dropout scales it: do the same
-      o = make_float4(round_dt<DT>(gelu_f(a.x)), round_dt<DT>(gelu_f(a.y)), round_dt<DT>(gelu_f(a.z)),
-                      round_dt<DT>(gelu_f(a.w)));
+      o = make_float4(round_dt<DT>(gelu_dt<DT>(a.x)), round_dt<DT>(gelu_dt<DT>(a.y)), round_dt<DT>(gelu_dt<DT>(a.z)),
+                      round_dt<DT>(gelu_dt<DT>(a.w)));
     }
     if (drop_thresh) {
       const uint32_t e = (uint32_t)i;
@@ -661,7 +713,9 @@ __global__ void __launch_bounds__(256) gelu_dropout_kernel(const void* __restric
       o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
     }
     st4<DT>(out, 4 * i, o);
+    if (BWD) { cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w; }
   }
+  if (BWD && part) cta_colsum(cs, c4n, cred, part);
 }
 
 // ------------------------------------------------------------------------------------------------ LN + activation
@@ -697,7 +751,7 @@ __global__ void __launch_bounds__(256) ln_act_fwd_kernel(const void* __restrict_
     const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / ENC_D);
     const float rs = rsqrtf(var + eps);
     float4 o = make_float4(c.x * rs * w4.x + b4.x, c.y * rs * w4.y + b4.y, c.z * rs * w4.z + b4.z, c.w * rs * w4.w + b4.w);
-    if (ACT == 1) o = make_float4(gelu_f(o.x), gelu_f(o.y), gelu_f(o.z), gelu_f(o.w));
+    if (ACT == 1) o = make_float4(gelu_dt<DTO>(o.x), gelu_dt<DTO>(o.y), gelu_dt<DTO>(o.z), gelu_dt<DTO>(o.w));
     if (drop_thresh) {
       const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
       o.x = (rnd32(seed, e, 0x5bd1e995u) >= drop_thresh) ? o.x * inv_keep : 0.f;
@@ -748,8 +802,8 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const void* __restrict_
     const float mu = mean[r], rs = rstd[r];
     const float4 xh = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
     if (ACT == 1) {
-      g.x *= gelu_grad_f(xh.x * w4.x + b4.x); g.y *= gelu_grad_f(xh.y * w4.y + b4.y);
-      g.z *= gelu_grad_f(xh.z * w4.z + b4.z); g.w *= gelu_grad_f(xh.w * w4.w + b4.w);
+      g.x *= gelu_grad_dt<DTG>(xh.x * w4.x + b4.x); g.y *= gelu_grad_dt<DTG>(xh.y * w4.y + b4.y);
+      g.z *= gelu_grad_dt<DTG>(xh.z * w4.z + b4.z); g.w *= gelu_grad_dt<DTG>(xh.w * w4.w + b4.w);
     }
     dw.x += g.x * xh.x; dw.y += g.y * xh.y; dw.z += g.z * xh.z; dw.w += g.w * xh.w;
     db.x += g.x; db.y += g.y; db.z += g.z; db.w += g.w;
@@ -910,7 +964,7 @@ extern "C" int rs_colsum(const void* x, int dtype, int64_t n_rows, int64_t n_col
   float* part = (float*)workspace;
   ENC_DISPATCH1(dtype, DT, (colsum_partial_kernel<DT><<<grid, 256, smem, st>>>(x, n_rows, (int)n_cols, part)));
   RS_LAUNCH_CHECK();
-  partial_sum_kernel<<<(int)((n_cols + 31) / 32), 256, 0, st>>>(part, grid, (int)n_cols, out, nullptr, (int)n_cols);
+  partial_sum_kernel<<<(int)((n_cols + 31) / 32), PS_WARPS * 32, 0, st>>>(part, grid, (int)n_cols, out, nullptr, (int)n_cols);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -953,7 +1007,7 @@ extern "C" int rs_ln_bwd(const void* dy, int dy_dtype, const void* x, int x_dtyp
   ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dy_dtype, DTO, (ln_bwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
       dy, x, index, n_rows, w, mean, rstd, th, ik, seed, dx, residual_grad, part))));
   RS_LAUNCH_CHECK();
-  partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
+  partial_sum_kernel<<<(2 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -1000,7 +1054,7 @@ extern "C" int rs_ln_act_bwd(const void* dy, int dy_dtype, const void* x, int x_
   if (act == 1) { LN_ACT_BWD(1); } else { LN_ACT_BWD(0); }
 #undef LN_ACT_BWD
   RS_LAUNCH_CHECK();
-  partial_sum_kernel<<<(2 * ENC_D + 31) / 32, 256, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
+  partial_sum_kernel<<<(2 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -1060,7 +1114,53 @@ extern "C" int rs_dropout_bwd(const void* g, int g_dtype, int64_t n, float dropo
   drop_consts(dropout_p, th, ik);
   cudaStream_t st = (cudaStream_t)stream;
   ENC_DISPATCH1(g_dtype, DTX, ENC_DISPATCH1(dy_dtype, DTY, (dropout_bwd_kernel<DTX, DTY><<<ew_grid(n / 4), 256, 0, st>>>(
-      g, n / 4, th, ik, seed, dy))));
+      g, n / 4, th, ik, seed, dy, 0, nullptr))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+// the same two backward kernels with the bias gradient (column sums of their output) folded in: no second pass over dy
+static bool cs_cols_ok(int64_t n_cols) { return n_cols > 0 && (n_cols & 3) == 0 && 256 % (n_cols / 4) == 0; }
+extern "C" size_t rs_ew_colsum_workspace_bytes(int64_t n, int64_t n_cols) {
+  return (size_t)ew_grid(n / 4) * (size_t)n_cols * sizeof(float);
+}
+extern "C" int rs_dropout_bwd_bias(const void* g, int g_dtype, int64_t n, int64_t n_cols, float dropout_p, uint64_t seed,
+                                   void* dy, int dy_dtype, float* d_bias, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (!d_bias || n_cols <= 0) return RS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { cudaMemsetAsync(d_bias, 0, (size_t)n_cols * sizeof(float), st); return RS_OK; }
+  if (!g || !dy || !workspace || n < 0 || (n & 3) || n % n_cols) return RS_ERR_BAD_ARG;
+  if (!cs_cols_ok(n_cols)) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_ew_colsum_workspace_bytes(n, n_cols)) return RS_ERR_WORKSPACE;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  const int grid = ew_grid(n / 4);
+  float* part = (float*)workspace;
+  ENC_DISPATCH1(g_dtype, DTX, ENC_DISPATCH1(dy_dtype, DTY, (dropout_bwd_kernel<DTX, DTY><<<grid, 256, 0, st>>>(
+      g, n / 4, th, ik, seed, dy, (int)(n_cols / 4), part))));
+  RS_LAUNCH_CHECK();
+  partial_sum_kernel<<<(int)((n_cols + 31) / 32), PS_WARPS * 32, 0, st>>>(part, grid, (int)n_cols, d_bias, nullptr, (int)n_cols);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_gelu_dropout_bwd_bias(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols,
+                                        int64_t n, float dropout_p, uint64_t seed, void* dz, float* d_bias,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!d_bias || n_cols <= 0) return RS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { cudaMemsetAsync(d_bias, 0, (size_t)n_cols * sizeof(float), st); return RS_OK; }
+  if (!z || !g || !dz || !workspace || n < 0 || (n & 3) || n % n_cols) return RS_ERR_BAD_ARG;
+  if (!cs_cols_ok(n_cols)) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_ew_colsum_workspace_bytes(n, n_cols)) return RS_ERR_WORKSPACE;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  const int grid = ew_grid(n / 4);
+  float* part = (float*)workspace;
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, true><<<grid, 256, 0, st>>>(z, g, bias, (int)(n_cols / 4), n / 4, th, ik, seed, dz, part)));
+  RS_LAUNCH_CHECK();
+  partial_sum_kernel<<<(int)((n_cols + 31) / 32), PS_WARPS * 32, 0, st>>>(part, grid, (int)n_cols, d_bias, nullptr, (int)n_cols);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -1073,7 +1173,7 @@ extern "C" int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, 
   uint32_t th; float ik;
   drop_consts(dropout_p, th, ik);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, false><<<ew_grid(n / 4), 256, 0, st>>>(z, nullptr, bias, (int)(n_cols / 4), n / 4, th, ik, seed, out)));
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, false><<<ew_grid(n / 4), 256, 0, st>>>(z, nullptr, bias, (int)(n_cols / 4), n / 4, th, ik, seed, out, nullptr)));
   RS_LAUNCH_CHECK();
   return RS_OK;
 }
@@ -1085,7 +1185,7 @@ extern "C" int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, cons
   uint32_t th; float ik;
   drop_consts(dropout_p, th, ik);
   cudaStream_t st = (cudaStream_t)stream;
-  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, true><<<ew_grid(n / 4), 256, 0, st>>>(z, g, bias, (int)(n_cols / 4), n / 4, th, ik, seed, dz)));
+  ENC_DISPATCH1(dtype, DT, (gelu_dropout_kernel<DT, true><<<ew_grid(n / 4), 256, 0, st>>>(z, g, bias, (int)(n_cols / 4), n / 4, th, ik, seed, dz, nullptr)));
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

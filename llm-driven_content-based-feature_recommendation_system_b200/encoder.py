@@ -57,6 +57,11 @@ def _colsum(x: Tensor) -> Tensor:
     return out
 
 
+def _fused_colsum_ok(n_cols: int) -> bool:
+    """the elementwise backward kernels can fold the column sums in when a CTA's 256 threads tile the column groups"""
+    return n_cols > 0 and n_cols % 4 == 0 and 256 % (n_cols // 4) == 0
+
+
 @torch.library.custom_op("rs::colsum", mutates_args=())
 def colsum_op(x: Tensor) -> Tensor:
     """fp32 column sums of a [rows, cols] matrix in a fixed order (bias gradients)."""
@@ -221,6 +226,13 @@ def dropout_bwd_op(g: Tensor, dropout_p: float, seed: int, out_dtype: int, want_
     """[dy, colsum(dy)] -- the gradient of the dropped branch and (optionally) of the bias folded into it."""
     g = g.contiguous()
     dy = torch.empty(g.shape, dtype=L.torch_dtype(out_dtype), device=g.device)
+    n_cols = g.shape[-1]
+    if want_colsum and _fused_colsum_ok(n_cols):
+        db = torch.empty(n_cols, dtype=torch.float32, device=g.device)
+        ws = L.workspace(_lib.rs_ew_colsum_workspace_bytes(g.numel(), n_cols), g.device)
+        L.check(_lib.rs_dropout_bwd_bias(L.ptr(g), L.dt(g), g.numel(), n_cols, dropout_p, seed, L.ptr(dy), out_dtype,
+                                         L.ptr(db), L.ptr(ws), ws.numel(), L.stream()), "rs_dropout_bwd_bias")
+        return [dy, db]
     L.check(_lib.rs_dropout_bwd(L.ptr(g), L.dt(g), g.numel(), dropout_p, seed, L.ptr(dy), out_dtype, L.stream()),
             "rs_dropout_bwd")
     return [dy, _colsum(dy) if want_colsum else g.new_empty(0, dtype=torch.float32)]
@@ -251,6 +263,14 @@ def _(z, bias, dropout_p, seed):
 def gelu_dropout_bwd_op(z: Tensor, bias: Optional[Tensor], g: Tensor, dropout_p: float, seed: int) -> List[Tensor]:
     g = g.to(z.dtype).contiguous()
     dz = torch.empty_like(z)
+    n_cols = z.shape[-1]
+    if bias is not None and _fused_colsum_ok(n_cols):
+        db = torch.empty(n_cols, dtype=torch.float32, device=z.device)
+        ws = L.workspace(_lib.rs_ew_colsum_workspace_bytes(z.numel(), n_cols), z.device)
+        L.check(_lib.rs_gelu_dropout_bwd_bias(L.ptr(z), L.ptr(g), L.dt(z), L.ptr(bias), n_cols, z.numel(), dropout_p, seed,
+                                              L.ptr(dz), L.ptr(db), L.ptr(ws), ws.numel(), L.stream()),
+                "rs_gelu_dropout_bwd_bias")
+        return [dz, db]
     L.check(_lib.rs_gelu_dropout_bwd(L.ptr(z), L.ptr(g), L.dt(z), L.ptr(bias), z.shape[-1], z.numel(), dropout_p, seed,
                                      L.ptr(dz), L.stream()), "rs_gelu_dropout_bwd")
     return [dz, _colsum(dz) if bias is not None else z.new_empty(0, dtype=torch.float32)]
