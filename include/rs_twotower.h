@@ -193,16 +193,22 @@ int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, i
  * key of such a query is masked and the attention output is 0 (fully-masked softmax row); they get out = 0 and no
  * gradient.  The reference reads such rows: `last_indices = valid_mask.sum(1) - 1` (v1_usertower_train.py:830)
  * addresses its LEFT-padded grid from the left, i.e. a padded position whenever a sequence fills less than half
- * of the window; the packed encoder carries those positions as extra one-token sequences to reproduce it. */
+ * of the window; the packed encoder carries those positions as extra one-token sequences to reproduce it.
+ * one_row_from / one_rows: the sequences [one_row_from, n_seq - zero_tail) are only read at ONE token each (the second
+ * dropout view in the last encoder layer feeds nothing but its DuoRec row, v1_usertower_train.py:789,830-842):
+ * one_rows[k] (int64) is the packed row of that token for sequence one_row_from + k (NULL: the last token; a row
+ * outside the sequence: none).  That row is computed by a matrix-vector kernel, the sequence's other rows of `out` are
+ * zeros, and the backward builds d_qkv of all its tokens from that row's gradient alone.  one_row_from = -1: none. */
 int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias /*[3*H*32] in_proj bias added on load, or NULL*/,
                        const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens,
-                       int n_heads, int head_dim, int max_len, int64_t zero_tail, float scale, float dropout_p,
-                       uint64_t seed, void* out, float* lse, void* stream);
+                       int n_heads, int head_dim, int max_len, int64_t zero_tail, int64_t one_row_from,
+                       const int64_t* one_rows, float scale, float dropout_p, uint64_t seed, void* out, float* lse,
+                       void* stream);
 int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* bias,
                        const float* lse,
                        const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads, int head_dim,
-                       int max_len, int64_t zero_tail, float scale, float dropout_p, uint64_t seed, void* d_qkv,
-                       void* stream);
+                       int max_len, int64_t zero_tail, int64_t one_row_from, const int64_t* one_rows, float scale,
+                       float dropout_p, uint64_t seed, void* d_qkv, void* stream);
 /* y[r,:] = dropout(LayerNorm(x[index ? index[r] : r, :])), dim == 128, fp32 statistics (mean/rstd[n_rows] saved).
  * `index` packs the valid rows of the padded grid on the way in (emb_ln, :458-459) and may repeat a row (one copy per
  * dropout view).  Backward: dx[r] = gradient w.r.t. the row that was normalised for output r ([n_rows,128], packed

@@ -68,8 +68,8 @@ PROTOTYPES = {
     "rs_bert_embed_fwd": (i32, [vp, i64, vp, vp, vp, vp, f32, vp, i64, i64, i64, f32, u64, vp, i32, vp, vp]),
     "rs_masked_mean_fwd": (i32, [vp, i32, vp, i64, i64, i64, vp, vp]),
     "rs_masked_mean_bwd": (i32, [vp, vp, i64, i64, i64, vp, i32, vp]),
-    "rs_attn_varlen_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, i32, i64, f32, f32, u64, vp, vp, vp]),
-    "rs_attn_varlen_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i64, i64, i32, i32, i32, i64, f32, f32, u64, vp, vp]),
+    "rs_attn_varlen_fwd": (i32, [vp, i32, vp, vp, i64, i64, i32, i32, i32, i64, i64, vp, f32, f32, u64, vp, vp, vp]),
+    "rs_attn_varlen_bwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i64, i64, i32, i32, i32, i64, i64, vp, f32, f32, u64, vp, vp]),
     "rs_rng_advance": (i32, [vp]),
     "rs_l2_normalize_fwd": (i32, [vp, i32, i64, i64, f32, vp, i32, vp, vp]),
     "rs_l2_normalize_bwd": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, i32, vp]),

@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256, 3) attn3_fwd_kernel(const void* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   uint16_t* sT = smem + warp * 16 * AT3_LD;
-  const int64_t n_items = p.zero_from * p.H;            // the zero tail (queries with every key masked) is bulk-filled
+  const int64_t n_items = p.full_to * p.H;              // the zero tail (queries with every key masked) is bulk-filled;
+                                                        // sequences in [full_to, zero_from): attn_one_fwd_kernel
   const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
   const bool hb = p.bias != nullptr;
   {
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_kernel(const void* __restric
   uint16_t* sT1 = sT0 + 16 * AT3_LD;
   float* sLse = sstat + warp * 128;
   float* sDelta = sLse + 64;
-  const int64_t n_items = p.zero_from * p.H;
+  const int64_t n_items = p.full_to * p.H;
   const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
   const bool hb = p.bias != nullptr;
   const uint32_t nob[2][2] = {{0u, 0u}, {0u, 0u}};

@@ -63,6 +63,12 @@ template <int DT> __device__ __forceinline__ void st4(void* base, int64_t off, f
   }
 }
 
+template <int DT> __device__ __forceinline__ float round_dt(float x) {
+  if constexpr (DT == RS_BF16) return __bfloat162float(__float2bfloat16_rn(x));
+  else if constexpr (DT == RS_F16) return __half2float(__float2half_rn(x));
+  else return x;
+}
+
 // element type as stored (only used to write zeros)
 template <int DT> struct DTStoreT { typedef float type; };
 template <> struct DTStoreT<RS_F16> { typedef __half type; };
@@ -76,6 +82,10 @@ struct AttnParams {
   int64_t n_seq;
   int H, max_len;
   int64_t zero_from;        // sequences b >= zero_from are fully masked queries: output 0, no gradient
+  int64_t full_to;          // sequences in [full_to, zero_from) are only read at ONE token each (attn_one_* kernels):
+                            // the main kernels skip them
+  const int64_t* one_row;   // [zero_from - full_to] packed row of that token (NULL: the last token; a row outside the
+                            // sequence: none -- the sequence produces zeros only)
   float scale;
   uint32_t drop_thresh;     // keep iff rnd32 >= thresh   (0: no dropout)
   float inv_keep;
@@ -244,6 +254,7 @@ __global__ void __launch_bounds__(256, 3) attn2_fwd_kernel(const void* __restric
     const int h = (int)(item % p.H);
     const int64_t t0 = __ldg(p.cu + b);
     const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (b >= p.full_to && b < p.zero_from) continue;    // single-row sequences: attn_one_fwd_kernel
     if (b >= p.zero_from) {                             // a query whose every key is masked (see rs_twotower.h)
       for (int i = 0; i < len; ++i) {
         reinterpret_cast<DTStore<DT>*>(out)[(t0 + i) * os_ + h * ENC_HD + lane] = DTStore<DT>(0);
@@ -401,6 +412,7 @@ __global__ void __launch_bounds__(256, 2) attn2_bwd_kernel(const void* __restric
     const int h = (int)(item % p.H);
     const int64_t t0 = __ldg(p.cu + b);
     const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (b >= p.full_to && b < p.zero_from) continue;    // single-row sequences: attn_one_bwd_kernel
     if (b >= p.zero_from) {
       for (int i = 0; i < len; ++i)
         for (int c = 0; c < 3; ++c)
@@ -419,6 +431,183 @@ __global__ void __launch_bounds__(256, 2) attn2_bwd_kernel(const void* __restric
 }
 
 #include "attn_mma.cuh"
+
+// ------------------------------------------------------------------------------------------------ single-row attention
+// Sequences whose output is only read at ONE token (the second dropout view in the last encoder layer: it feeds nothing
+// but its DuoRec row, v1_usertower_train.py:789,830-842 -- position len-1 of the LEFT-padded grid, i.e. some token in
+// the middle of the sequence).  One query against <= 64 keys is a matrix-vector product: one warp per (sequence,
+// head), lane j scores keys j and j + 32 against the broadcast query, lane d then accumulates output dimension d over
+// the keys (coalesced 64-byte V reads).  The other rows of `out` are written as zeros (they are never read where it
+// matters: rows with loss weight 0 at most).  Same bias / rounding convention as the tile kernels (bias added in the
+// operand precision); probabilities stay fp32.
+template <int DT> __device__ __forceinline__ float ld1(const void* base, int64_t off) {
+  if constexpr (DT == RS_F32) return __ldg(reinterpret_cast<const float*>(base) + off);
+  else if constexpr (DT == RS_BF16) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+  else return __half2float(__ldg(reinterpret_cast<const __half*>(base) + off));
+}
+template <int DT> __device__ __forceinline__ void st1(void* base, int64_t off, float v) {
+  reinterpret_cast<DTStore<DT>*>(base)[off] = DTStore<DT>(v);
+}
+// row `tok`, 32 dims starting at column `col0`, + bias (rounded to DT like a Linear's output) -> r[32] in every lane
+template <int DT>
+__device__ __forceinline__ void load_row32(float (&r)[ENC_HD], const void* src, int64_t off, const float* bias, int64_t boff) {
+#pragma unroll
+  for (int c = 0; c < ENC_HD / 4; ++c) {
+    float4 v = ld4<DT>(src, off + 4 * c);
+    if (bias) {
+      const float4 b4 = ldg_f4(bias + boff + 4 * c);
+      v = make_float4(round_dt<DT>(v.x + b4.x), round_dt<DT>(v.y + b4.y), round_dt<DT>(v.z + b4.z), round_dt<DT>(v.w + b4.w));
+    }
+    r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+  }
+}
+// the one query row of sequence `b` (index within the sequence), or -1
+__device__ __forceinline__ int one_row_of(const AttnParams& p, int64_t b, int64_t t0, int len) {
+  if (!p.one_row) return len - 1;
+  const int64_t r = __ldg(p.one_row + (b - p.full_to)) - t0;
+  return (r >= 0 && r < len) ? (int)r : -1;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) attn_one_fwd_kernel(const void* __restrict__ qkv, AttnParams p,
+                                                           void* __restrict__ out, float* __restrict__ lse) {
+  __shared__ float sP[8][64];
+  p.seed = epoch_seed(p.seed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int64_t n_items = (p.zero_from - p.full_to) * p.H;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
+    const int64_t b = p.full_to + item / p.H;
+    const int h = (int)(item % p.H);
+    const int64_t t0 = __ldg(p.cu + b);
+    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (len <= 0) continue;
+    const int i = one_row_of(p, b, t0, len);
+    for (int j = 0; j < len; ++j) {
+      if (j == i) continue;
+      st1<DT>(out, (t0 + j) * os_ + h * ENC_HD + lane, 0.f);
+      if (lane == 0) lse[(t0 + j) * p.H + h] = 0.f;
+    }
+    if (i < 0) continue;
+    float q[ENC_HD];
+    load_row32<DT>(q, qkv, (t0 + i) * rs_ + h * ENC_HD, p.bias, h * ENC_HD);
+    float sc[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int j = lane + 32 * kk;
+      sc[kk] = -INFINITY;
+      if (j <= i) {
+        float k[ENC_HD];
+        load_row32<DT>(k, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD, p.bias, os_ + h * ENC_HD);
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < ENC_HD; ++c) d = fmaf(q[c], k[c], d);
+        sc[kk] = d * p.scale;
+      }
+    }
+    const float m = warp_max(fmaxf(sc[0], sc[1]));
+    const float e0 = __expf(sc[0] - m), e1 = __expf(sc[1] - m);        // (-inf -> 0)
+    const float l = warp_sum(e0 + e1);
+    const float inv = 1.f / l;
+    __syncwarp();
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int j = lane + 32 * kk;
+      float pr = (kk ? e1 : e0) * inv;
+      if (p.drop_thresh) pr = (rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh) ? pr * p.inv_keep : 0.f;
+      sP[warp][j] = pr;
+    }
+    __syncwarp();
+    const float bv = p.bias ? __ldg(p.bias + 2 * os_ + h * ENC_HD + lane) : 0.f;
+    float acc = 0.f;
+    for (int j = 0; j <= i; ++j) {
+      float v = ld1<DT>(qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD + lane);
+      if (p.bias) v = round_dt<DT>(v + bv);
+      acc = fmaf(sP[warp][j], v, acc);
+    }
+    st1<DT>(out, (t0 + i) * os_ + h * ENC_HD + lane, acc);
+    if (lane == 0) lse[(t0 + i) * p.H + h] = m + __logf(l);
+  }
+}
+
+// d_qkv of the same sequences from the gradient of their one row alone: dq (that row; zeros elsewhere), dk_j = ds_j q,
+// dv_j = p_j dO for the keys j <= i, zeros behind it
+template <int DT>
+__global__ void __launch_bounds__(256) attn_one_bwd_kernel(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                                           const void* __restrict__ out, const float* __restrict__ lse,
+                                                           AttnParams p, void* __restrict__ d_qkv) {
+  __shared__ float sS[8][2][64];                       // [0] ds_j   [1] dropped p_j
+  p.seed = epoch_seed(p.seed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int64_t n_items = (p.zero_from - p.full_to) * p.H;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  for (int64_t item = (int64_t)blockIdx.x * wpc + warp; item < n_items; item += (int64_t)gridDim.x * wpc) {
+    const int64_t b = p.full_to + item / p.H;
+    const int h = (int)(item % p.H);
+    const int64_t t0 = __ldg(p.cu + b);
+    const int len = min((int)(__ldg(p.cu + b + 1) - t0), p.max_len);
+    if (len <= 0) continue;
+    const int i = one_row_of(p, b, t0, len);
+    for (int j = i + 1; j < len; ++j) {                // keys behind the query (all keys when there is no query)
+      const int64_t row = (t0 + j) * rs_ + h * ENC_HD + lane;
+      st1<DT>(d_qkv, row, 0.f); st1<DT>(d_qkv, row + os_, 0.f); st1<DT>(d_qkv, row + 2 * os_, 0.f);
+    }
+    if (i < 0) continue;
+    float q[ENC_HD], go[ENC_HD];
+    load_row32<DT>(q, qkv, (t0 + i) * rs_ + h * ENC_HD, p.bias, h * ENC_HD);
+    load_row32<DT>(go, d_out, (t0 + i) * os_ + h * ENC_HD, nullptr, 0);
+    const float g_d = ld1<DT>(d_out, (t0 + i) * os_ + h * ENC_HD + lane);
+    const float o_d = ld1<DT>(out, (t0 + i) * os_ + h * ENC_HD + lane);
+    const float delta = warp_sum(g_d * o_d);
+    const float li = __ldg(lse + (t0 + i) * p.H + h);
+    __syncwarp();                                      // the previous item's sS reads are done
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int j = lane + 32 * kk;
+      float ds = 0.f, pd = 0.f;
+      if (j <= i) {
+        float k[ENC_HD];
+        load_row32<DT>(k, qkv, (t0 + j) * rs_ + os_ + h * ENC_HD, p.bias, os_ + h * ENC_HD);
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < ENC_HD; ++c) d = fmaf(q[c], k[c], d);
+        const float pr = __expf(d * p.scale - li);
+        float v[ENC_HD];
+        load_row32<DT>(v, qkv, (t0 + j) * rs_ + 2 * os_ + h * ENC_HD, p.bias, 2 * os_ + h * ENC_HD);
+        float dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < ENC_HD; ++c) dp = fmaf(go[c], v[c], dp);
+        pd = pr;
+        if (p.drop_thresh) {
+          const bool keep = rnd32(p.seed, (uint32_t)((t0 + i) * p.H + h), (uint32_t)j) >= p.drop_thresh;
+          dp = keep ? dp * p.inv_keep : 0.f;
+          pd = keep ? pr * p.inv_keep : 0.f;
+        }
+        ds = pr * (dp - delta);
+      }
+      sS[warp][0][j] = ds;
+      sS[warp][1][j] = pd;
+    }
+    __syncwarp();
+    // lane = feature d: dq_d = scale sum_j ds_j k_jd ; rows j: dk_jd = scale ds_j q_d, dv_jd = pd_j dO_d
+    const float bk = p.bias ? __ldg(p.bias + os_ + h * ENC_HD + lane) : 0.f;
+    const float bq = p.bias ? __ldg(p.bias + h * ENC_HD + lane) : 0.f;
+    float q_d = ld1<DT>(qkv, (t0 + i) * rs_ + h * ENC_HD + lane);
+    if (p.bias) q_d = round_dt<DT>(q_d + bq);
+    float dq = 0.f;
+    for (int j = 0; j <= i; ++j) {
+      float k = ld1<DT>(qkv, (t0 + j) * rs_ + os_ + h * ENC_HD + lane);
+      if (p.bias) k = round_dt<DT>(k + bk);
+      const float ds = sS[warp][0][j];
+      dq = fmaf(ds, k, dq);
+      const int64_t row = (t0 + j) * rs_ + h * ENC_HD + lane;
+      if (j < i) st1<DT>(d_qkv, row, 0.f);
+      st1<DT>(d_qkv, row + os_, ds * q_d * p.scale);
+      st1<DT>(d_qkv, row + 2 * os_, sS[warp][1][j] * g_d);
+    }
+    st1<DT>(d_qkv, (t0 + i) * rs_ + h * ENC_HD + lane, dq * p.scale);
+  }
+}
 
 // out[c] = sum_r x[r, c]  -- column sums of a [n_rows, n_cols] matrix (bias gradients), two deterministic stages:
 // thread t of a CTA owns column group (t % (n_cols/4)) and walks rows t / (n_cols/4), + row-groups ...; per-CTA partials
@@ -641,12 +830,6 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const void* __restrict
     cs.x += b.x; cs.y += b.y; cs.z += b.z; cs.w += b.w;
   }
   if (part) cta_colsum(cs, c4n, cred, part);
-}
-
-template <int DT> __device__ __forceinline__ float round_dt(float x) {
-  if constexpr (DT == RS_BF16) return __bfloat162float(__float2bfloat16_rn(x));
-  else if constexpr (DT == RS_F16) return __half2float(__float2half_rn(x));
-  else return x;
 }
 
 // exact (erf) GELU, as nn.TransformerEncoderLayer(activation="gelu") -> F.gelu(approximate="none")
@@ -900,17 +1083,21 @@ static int attn_check(int64_t n_seq, int64_t total, int H, int hd, int max_len, 
 
 extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias, const int32_t* cu_seqlens, int64_t n_seq,
                                   int64_t total_tokens, int n_heads, int head_dim, int max_len, int64_t zero_tail,
-                                  float scale, float dropout_p, uint64_t seed, void* out, float* lse, void* stream) {
+                                  int64_t one_row_from, const int64_t* one_rows, float scale, float dropout_p,
+                                  uint64_t seed, void* out, float* lse, void* stream) {
   int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p, zero_tail);
   if (rc != RS_OK) return rc;
+  if (one_row_from < 0 || one_row_from > n_seq - zero_tail) one_row_from = n_seq - zero_tail;
   if (total_tokens == 0) return RS_OK;
   if (!qkv || !cu_seqlens || !out || !lse) return RS_ERR_BAD_ARG;
   AttnParams p;
   max_len = (max_len + 3) & ~3;      // keeps every per-warp shared-memory region 16-byte aligned
   p.cu = cu_seqlens; p.bias = bias; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
   p.zero_from = n_seq - zero_tail;
+  p.full_to = one_row_from;
+  p.one_row = one_rows;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
-  const int grid = grid_for_warps(n_seq * n_heads, 8, 8);
+  const int grid = grid_for_warps((dtype == RS_F32 ? n_seq : (p.full_to > 0 ? p.full_to : 1)) * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
   // 16-bit operands: tensor-core tiles (attn_mma.cuh); fp32: the SIMT kernel
   if (dtype == RS_BF16) attn3_fwd_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, p, out, lse);
@@ -918,30 +1105,44 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias,
   else if (dtype == RS_F32) attn2_fwd_kernel<RS_F32><<<grid, 256, 0, st>>>(qkv, p, out, lse);
   else return RS_ERR_BAD_ARG;
   RS_LAUNCH_CHECK();
+  if (p.full_to < p.zero_from) {
+    const int g2 = grid_for_warps((p.zero_from - p.full_to) * n_heads, 8, 8);
+    ENC_DISPATCH1(dtype, DT, (attn_one_fwd_kernel<DT><<<g2, 256, 0, st>>>(qkv, p, out, lse)));
+    RS_LAUNCH_CHECK();
+  }
   return RS_OK;
 }
 
 extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* bias,
                                   const float* lse,
                                   const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens, int n_heads,
-                                  int head_dim, int max_len, int64_t zero_tail, float scale, float dropout_p,
-                                  uint64_t seed, void* d_qkv, void* stream) {
+                                  int head_dim, int max_len, int64_t zero_tail, int64_t one_row_from,
+                                  const int64_t* one_rows, float scale, float dropout_p, uint64_t seed, void* d_qkv,
+                                  void* stream) {
   int rc = attn_check(n_seq, total_tokens, n_heads, head_dim, max_len, dropout_p, zero_tail);
   if (rc != RS_OK) return rc;
+  if (one_row_from < 0 || one_row_from > n_seq - zero_tail) one_row_from = n_seq - zero_tail;
   if (total_tokens == 0) return RS_OK;
   if (!qkv || !d_out || !out || !lse || !cu_seqlens || !d_qkv) return RS_ERR_BAD_ARG;
   AttnParams p;
   max_len = (max_len + 3) & ~3;      // keeps every per-warp shared-memory region 16-byte aligned
   p.cu = cu_seqlens; p.bias = bias; p.n_seq = n_seq; p.H = n_heads; p.max_len = max_len; p.scale = scale; p.seed = seed;
   p.zero_from = n_seq - zero_tail;
+  p.full_to = one_row_from;
+  p.one_row = one_rows;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
-  const int grid = grid_for_warps(n_seq * n_heads, 8, 8);
+  const int grid = grid_for_warps((dtype == RS_F32 ? n_seq : (p.full_to > 0 ? p.full_to : 1)) * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == RS_BF16) attn3_bwd_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
   else if (dtype == RS_F16) attn3_bwd_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
   else if (dtype == RS_F32) attn2_bwd_kernel<RS_F32><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
   else return RS_ERR_BAD_ARG;
   RS_LAUNCH_CHECK();
+  if (p.full_to < p.zero_from) {
+    const int g2 = grid_for_warps((p.zero_from - p.full_to) * n_heads, 8, 8);
+    ENC_DISPATCH1(dtype, DT, (attn_one_bwd_kernel<DT><<<g2, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv)));
+    RS_LAUNCH_CHECK();
+  }
   return RS_OK;
 }
 

@@ -74,9 +74,18 @@ def _(x):
     return x.new_empty(x.shape[-1], dtype=torch.float32)
 
 
+def _one_rows(one_rows: Optional[Tensor], cu_seqlens: Tensor, zero_tail: int, one_row_from: int) -> Optional[Tensor]:
+    if one_rows is None or one_row_from < 0:
+        return None
+    assert one_rows.dtype == torch.int64 and one_rows.is_contiguous() and one_rows.is_cuda
+    assert one_rows.numel() == cu_seqlens.numel() - 1 - zero_tail - one_row_from, "one row index per single-row sequence"
+    return one_rows
+
+
 @torch.library.custom_op("rs::attn_varlen", mutates_args=())
 def attn_varlen_op(qkv: Tensor, bias: Optional[Tensor], cu_seqlens: Tensor, n_heads: int, max_len: int, zero_tail: int,
-                   scale: float, dropout_p: float, seed: int) -> List[Tensor]:
+                   scale: float, dropout_p: float, seed: int, one_row_from: int = -1,
+                   one_rows: Optional[Tensor] = None) -> List[Tensor]:
     L.require_cuda(qkv, cu_seqlens)
     qkv = qkv.contiguous()
     T = qkv.shape[0]
@@ -84,20 +93,20 @@ def attn_varlen_op(qkv: Tensor, bias: Optional[Tensor], cu_seqlens: Tensor, n_he
     out = torch.empty(T, n_heads * hd, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(T, n_heads, dtype=torch.float32, device=qkv.device)
     L.check(_lib.rs_attn_varlen_fwd(L.ptr(qkv), L.dt(qkv), L.ptr(bias), L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T,
-                                    n_heads, hd, max_len, zero_tail, scale, dropout_p, seed, L.ptr(out), L.ptr(lse),
-                                    L.stream()), "rs_attn_varlen_fwd")
+                                    n_heads, hd, max_len, zero_tail, one_row_from, L.ptr(_one_rows(one_rows, cu_seqlens, zero_tail, one_row_from)),
+                                    scale, dropout_p, seed, L.ptr(out), L.ptr(lse), L.stream()), "rs_attn_varlen_fwd")
     return [out, lse]
 
 
 @attn_varlen_op.register_fake
-def _(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
+def _(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed, one_row_from=-1, one_rows=None):
     return [qkv.new_empty(qkv.shape[0], qkv.shape[1] // 3), qkv.new_empty(qkv.shape[0], n_heads, dtype=torch.float32)]
 
 
 @torch.library.custom_op("rs::attn_varlen_bwd", mutates_args=())
 def attn_varlen_bwd_op(qkv: Tensor, bias: Optional[Tensor], d_out: Tensor, out: Tensor, lse: Tensor, cu_seqlens: Tensor,
                        n_heads: int, max_len: int, zero_tail: int, scale: float, dropout_p: float,
-                       seed: int) -> List[Tensor]:
+                       seed: int, one_row_from: int = -1, one_rows: Optional[Tensor] = None) -> List[Tensor]:
     """[d_qkv, d_bias] (d_bias empty when there is no bias)."""
     d_out = d_out.to(qkv.dtype).contiguous()
     T = qkv.shape[0]
@@ -105,13 +114,15 @@ def attn_varlen_bwd_op(qkv: Tensor, bias: Optional[Tensor], d_out: Tensor, out: 
     d_qkv = torch.empty_like(qkv)
     L.check(_lib.rs_attn_varlen_bwd(L.ptr(qkv), L.ptr(d_out), L.ptr(out), L.dt(qkv), L.ptr(bias), L.ptr(lse),
                                     L.ptr(cu_seqlens), cu_seqlens.numel() - 1, T, n_heads, hd, max_len, zero_tail,
-                                    scale, dropout_p, seed, L.ptr(d_qkv), L.stream()), "rs_attn_varlen_bwd")
+                                    one_row_from, L.ptr(_one_rows(one_rows, cu_seqlens, zero_tail, one_row_from)), scale,
+                                    dropout_p, seed, L.ptr(d_qkv), L.stream()), "rs_attn_varlen_bwd")
     d_bias = _colsum(d_qkv) if bias is not None else qkv.new_empty(0, dtype=torch.float32)
     return [d_qkv, d_bias]
 
 
 @attn_varlen_bwd_op.register_fake
-def _(qkv, bias, d_out, out, lse, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
+def _(qkv, bias, d_out, out, lse, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed, one_row_from=-1,
+      one_rows=None):
     return [torch.empty_like(qkv), qkv.new_empty(qkv.shape[1] if bias is not None else 0, dtype=torch.float32)]
 
 
@@ -284,28 +295,33 @@ def _(z, bias, g, dropout_p, seed):
 # ------------------------------------------------------------------------------------------------ autograd
 class _AttnVarlen(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed):
-        out, lse = L.direct.attn_varlen(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed)
-        ctx.save_for_backward(qkv, bias, out, lse, cu_seqlens)
-        ctx.meta = (n_heads, max_len, zero_tail, scale, dropout_p, seed)
+    def forward(ctx, qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed, one_row_from, one_rows):
+        out, lse = L.direct.attn_varlen(qkv, bias, cu_seqlens, n_heads, max_len, zero_tail, scale, dropout_p, seed,
+                                        one_row_from, one_rows)
+        ctx.save_for_backward(qkv, bias, out, lse, cu_seqlens, one_rows)
+        ctx.meta = (n_heads, max_len, zero_tail, scale, dropout_p, seed, one_row_from)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        qkv, bias, out, lse, cu = ctx.saved_tensors
-        d_qkv, d_bias = L.direct.attn_varlen_bwd(qkv, bias, g, out, lse, cu, *ctx.meta)
-        return (d_qkv, d_bias if bias is not None else None) + (None,) * 7
+        qkv, bias, out, lse, cu, one_rows = ctx.saved_tensors
+        d_qkv, d_bias = L.direct.attn_varlen_bwd(qkv, bias, g, out, lse, cu, *ctx.meta, one_rows)
+        return (d_qkv, d_bias if bias is not None else None) + (None,) * 9
 
 
 def attn_varlen(qkv: Tensor, cu_seqlens: Tensor, n_heads: int, max_len: int, dropout_p: float = 0.0,
-                scale: Optional[float] = None, zero_tail: int = 0, bias: Optional[Tensor] = None) -> Tensor:
+                scale: Optional[float] = None, zero_tail: int = 0, bias: Optional[Tensor] = None,
+                one_row_from: int = -1, one_rows: Optional[Tensor] = None) -> Tensor:
     """Causal self-attention over packed sequences: qkv [T, 3*H*32] (in_proj output; its `bias` [3*H*32] may be
     passed separately and is added on load) -> [T, H*32].  The last `zero_tail` sequences are queries at padded
-    positions (every key masked): output 0, no gradient."""
+    positions (every key masked): output 0, no gradient.  `one_row_from` >= 0: the caller reads only ONE row of each
+    sequence from that index on (before the zero tail) -- `one_rows` [that many] int64 packed row indices (None: the last
+    token; an index outside its sequence: none); their other output rows are zeros and only that row's gradient is
+    propagated (a matrix-vector kernel instead of the tile kernel)."""
     hd = qkv.shape[1] // (3 * n_heads)
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
     return _AttnVarlen.apply(qkv, bias, cu_seqlens, n_heads, max_len, int(zero_tail), float(scale), float(dropout_p),
-                             _seed() if dropout_p > 0 else 0)
+                             _seed() if dropout_p > 0 else 0, int(one_row_from), one_rows)
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -722,7 +738,7 @@ def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
 
 
 def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int,
-                         zero_tail: int = 0, rows=None) -> Tensor:
+                         zero_tail: int = 0, rows=None, one_row_from: int = -1, one_rows=None) -> Tensor:
     """One pre-norm layer on the packed tokens.  `rows` = (n_prefix, idx): only the rows cat([arange(n_prefix), idx]) are
     wanted from this layer (idx: rows outside the prefix, -1 = none -> a zero row).  Attention still sees every token --
     the wanted rows attend to the others -- but everything behind it is position-wise, so the out-projection, the residual
@@ -737,7 +753,8 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
     qkv = matmul_w(h, attn.in_proj_weight)
     o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail,
-                    bias=attn.in_proj_bias)
+                    bias=attn.in_proj_bias, one_row_from=one_row_from if rows is not None else -1,
+                    one_rows=one_rows if rows is not None else None)
     if rows is not None:
         o = ops.select_prefix_rows(o, rows[0], rows[1], disjoint=True)
         x = ops.select_prefix_rows(x, rows[0], rows[1], disjoint=True)
@@ -748,12 +765,17 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
 
 
 def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,
-                   zero_tail: int = 0, last_rows=None) -> Tensor:
+                   zero_tail: int = 0, last_rows=None, one_row_from: int = -1, one_rows=None) -> Tensor:
     """x: [T, 128] fp32 residual stream of the packed valid tokens -> same shape; with `last_rows` = (n_prefix, idx) only
-    those rows of the LAST layer's output, [n_prefix + len(idx), 128] (see packed_encoder_layer)."""
+    those rows of the LAST layer's output, [n_prefix + len(idx), 128] (see packed_encoder_layer).  `one_row_from` /
+    `one_rows` (with last_rows): the caller vouches that of the sequences from that index on, `last_rows` names nothing
+    but the token `one_rows` gives (or tokens whose value does not matter) -- the last layer's attention then computes
+    only that row of them (attn_varlen)."""
     n_layers = len(encoder.layers)
     for i, layer in enumerate(encoder.layers):
-        x = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail, last_rows if i == n_layers - 1 else None)
+        last = i == n_layers - 1
+        x = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail, last_rows if last else None,
+                                 one_row_from if last else -1, one_rows if last else None)
     if encoder.norm is not None:
         x = encoder.norm(x)
     return x

@@ -163,7 +163,7 @@ class SASRecUserTower(nn.Module):
             user_profile_vec = enc.sequential(self.static_mlp, static_input if views == 1 else static_input.repeat(views, 1))
             return self._forward_packed(seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index,
                                         cu_seqlens, packed_zero_tail, select_users, packed_fold, packed_fold_inv,
-                                        select_prefix)
+                                        select_prefix, views)
         user_profile_vec = self.static_mlp(static_input)
         seq_emb = self.emb_dropout(self.emb_ln(seq_emb))
         # is_causal=True only tells nn.TransformerEncoder not to PROBE the mask: with is_causal=None it compares the
@@ -186,7 +186,8 @@ class SASRecUserTower(nn.Module):
         return F.normalize(final_vec, p=2, dim=-1)
 
     def _forward_packed(self, seq_emb, user_profile_vec, seq_len, training_mode, select_index, packed_index, cu_seqlens,
-                        zero_tail=0, select_users=None, packed_fold=None, packed_fold_inv=None, select_prefix=None):
+                        zero_tail=0, select_users=None, packed_fold=None, packed_fold_inv=None, select_prefix=None,
+                        views=1):
         """The encoder on the packed valid tokens (encoder.py): `packed_index` [T] = flat b*L+l positions of the
         valid time steps in batch-major order, `cu_seqlens` int32 their per-sequence offsets (every sequence
         non-empty).  `select_index` then indexes PACKED rows; returns [len(select_index), 128] (all T rows when
@@ -211,8 +212,13 @@ class SASRecUserTower(nn.Module):
             tail = select_index[n:]
             m = tail.numel()
             inside = tail < n
+            # With two views the sequences of the second one (index B on) feed only their DuoRec rows, the second half of
+            # `tail` (one row per user, some token in the middle of the sequence -- or a zero-tail row: none); the prefix
+            # rows that belong to them are padding rows of weight 0: single-row attention for them in the last layer.
+            n_users = user_profile_vec.shape[0] // max(views, 1)
+            one = dict(one_row_from=n_users, one_rows=tail[m - n_users:].contiguous()) if views == 2 and m == 2 * n_users else {}
             output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail,
-                                        last_rows=(n, torch.where(inside, -1, tail)))
+                                        last_rows=(n, torch.where(inside, -1, tail)), **one)
             pick = torch.where(inside, tail, n + torch.arange(m, device=tail.device))
             # the head's first Linear autocasts its input: emit the rows in that dtype right away
             ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else output.dtype

@@ -444,3 +444,78 @@ def test_split_rows_backward_is_one_concatenation(rs):
     (a.sum() * 2 + c.sum() * 3).backward()                 # b unused: its gradient is zeros
     want = torch.cat([torch.full((70, 8), 2.0), torch.zeros(20, 8), torch.full((10, 8), 3.0)]).to(DEV)
     torch.testing.assert_close(x.grad, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attn_last_only_rows_match_full_attention(rs, dtype):
+    """attn_varlen(one_row_from=k): for the sequences from k on only the LAST row is computed (matrix-vector kernel);
+    that row and the d_qkv it induces must equal full attention with a gradient that is zero on the other rows; the
+    sequences before k are untouched; the other rows of the last-only sequences are zeros."""
+    g = torch.Generator().manual_seed(17)
+    lens = [5, 50, 17, 1, 33, 16, 2, 64, 9, 31]
+    k, H = 4, 4
+    cu = _cu(lens).to(DEV)
+    T = sum(lens)
+    qkv = (torch.randn(T, 3 * H * 32, generator=g) * 0.7).to(dtype).to(DEV)
+    bias = (torch.randn(3 * H * 32, generator=g) * 0.1).to(DEV)
+    cot = torch.randn(T, H * 32, generator=g).to(DEV)
+    last = torch.tensor([sum(lens[:i + 1]) - 1 for i in range(len(lens))])
+    t_k = sum(lens[:k])
+    keep = torch.zeros(T, dtype=torch.bool)
+    keep[:t_k] = True
+    keep[last[k:]] = True
+    keep = keep.to(DEV)
+    cot = cot * keep.unsqueeze(1)
+    a = qkv.clone().requires_grad_(True)
+    full = rs.encoder.attn_varlen(a, cu, H, 64, bias=bias)
+    (full.float() * cot).sum().backward()
+    b = qkv.clone().requires_grad_(True)
+    part = rs.encoder.attn_varlen(b, cu, H, 64, bias=bias, one_row_from=k)
+    (part.float() * cot).sum().backward()
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(part[keep].float(), full[keep].float(), **tol)
+    assert (part[~keep] == 0).all()
+    if dtype == torch.float32:
+        torch.testing.assert_close(b.grad, a.grad, rtol=1e-4, atol=1e-5)
+    else:
+        rel = (b.grad.float() - a.grad.float()).norm() / a.grad.float().norm()
+        assert rel < 2e-2, rel
+    # dropout: forward and backward of the last-row kernel agree on the mask (gradient of sum(out) w.r.t. V rows is
+    # the dropped probability row: it is zero exactly where the forward dropped a key)
+    rs.encoder.rng_advance()
+    torch.manual_seed(3)
+    c = qkv.float().clone().requires_grad_(True)
+    out = rs.encoder.attn_varlen(c, cu, H, 64, dropout_p=0.5, one_row_from=0)
+    out[last].sum().backward()
+    dv = c.grad.view(T, 3, H, 32)[:, 2]                       # [T, H, 32]: p_drop[j] * 1
+    dropped = (dv.abs().sum(-1) == 0)                          # key j dropped for head h
+    frac = dropped.float().mean().item()
+    assert 0.3 < frac < 0.7, frac
+
+
+def test_attn_one_row_in_the_middle_of_a_sequence(rs):
+    """attn_varlen(one_row_from=k, one_rows=...): the single row may be ANY token of its sequence (DuoRec reads position
+    len-1 of the left-padded grid), or none (a row index outside the sequence)."""
+    g = torch.Generator().manual_seed(18)
+    lens = [7, 40, 12, 1, 33, 20]
+    k, H = 2, 4
+    cu = _cu(lens).to(DEV)
+    T = sum(lens)
+    starts = [sum(lens[:i]) for i in range(len(lens))]
+    one = torch.tensor([starts[2] + 5, starts[3] + 0, T + 3, starts[5] + 19])          # seq 4: none
+    qkv = (torch.randn(T, 3 * H * 32, generator=g) * 0.7).to(DEV)
+    bias = (torch.randn(3 * H * 32, generator=g) * 0.1).to(DEV)
+    keep = torch.zeros(T, dtype=torch.bool)
+    keep[:starts[k]] = True
+    keep[one[one < T]] = True
+    keep = keep.to(DEV)
+    cot = torch.randn(T, H * 32, generator=g).to(DEV) * keep.unsqueeze(1)
+    a = qkv.clone().requires_grad_(True)
+    full = rs.encoder.attn_varlen(a, cu, H, 64, bias=bias)
+    (full * cot).sum().backward()
+    b = qkv.clone().requires_grad_(True)
+    part = rs.encoder.attn_varlen(b, cu, H, 64, bias=bias, one_row_from=k, one_rows=one.to(DEV))
+    (part * cot).sum().backward()
+    torch.testing.assert_close(part[keep], full[keep], rtol=1e-4, atol=1e-5)
+    assert (part[~keep] == 0).all()
+    torch.testing.assert_close(b.grad, a.grad, rtol=1e-4, atol=1e-5)
