@@ -249,6 +249,19 @@ int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, int64_t n_c
                         uint64_t seed, void* out, void* stream);
 int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
                         float dropout_p, uint64_t seed, void* dz, void* stream);
+/* A pre-norm block ends with x1 = x + dropout(y + lin_bias) and the next one starts with h = LayerNorm(x1)
+ * (nn.TransformerEncoderLayer, norm_first=True; tower_code/v1_refine_usertower.py:343-352): both in one pass (x, x1 fp32
+ * residual stream; y the GEMM output; h in the next GEMM's operand dtype; mean/rstd saved), and one backward pass:
+ * dx = residual_grad + LN'(dh) (fp32), dy = mask(dx)/keep (y's dtype), d gamma / d beta / d lin_bias reduced in a fixed
+ * order.  dim == 128.  Workspace: rs_ln_bwd_dropout_workspace_bytes(n_rows). */
+int rs_dropout_add_ln_fwd(const float* x, const void* y, int y_dtype, const float* lin_bias, int64_t n_rows, int64_t dim,
+                          float dropout_p, uint64_t seed, const float* w, const float* b, float eps, float* x1, void* h,
+                          int h_dtype, float* mean, float* rstd, void* stream);
+size_t rs_ln_bwd_dropout_workspace_bytes(int64_t n_rows);
+int rs_ln_bwd_dropout(const void* dh, int dh_dtype, const float* x1, const float* residual_grad /*nullable*/,
+                      int64_t n_rows, int64_t dim, const float* w, const float* mean, const float* rstd, float dropout_p,
+                      uint64_t seed, float* dx, void* dy, int dy_dtype, float* dw, float* db, float* d_lin_bias,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* The two backward kernels with the bias gradient folded in: d_bias[n_cols] = column sums of their output (fp32, fixed
  * order), no second pass over dy / dz.  n_cols / 4 must divide 256.  Workspace: rs_ew_colsum_workspace_bytes(n, n_cols).
  * For 16-bit activations the GELU uses erfc by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 << the 2^-9 rounding of the

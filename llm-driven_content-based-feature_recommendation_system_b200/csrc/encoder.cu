@@ -768,6 +768,34 @@ __global__ void __launch_bounds__(PS_WARPS * 32) partial_sum_kernel(const float*
   }
 }
 
+// the same fold for [n_blocks][3][128] partials -> three 128-vectors
+__global__ void __launch_bounds__(PS_WARPS * 32) partial_sum3_kernel(const float* __restrict__ part, int n_blocks,
+                                                                     float* __restrict__ out0, float* __restrict__ out1,
+                                                                     float* __restrict__ out2) {
+  __shared__ float red[PS_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;                 // < 384
+  float s[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s[q] = 0.f;
+  for (int b = w; b < n_blocks; b += 8 * PS_WARPS) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int bb = b + PS_WARPS * q;
+      if (bb < n_blocks) s[q] += part[(int64_t)bb * (3 * ENC_D) + c];
+    }
+  }
+  red[w][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  __syncthreads();
+  if (w == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < PS_WARPS; k += 4) { t[0] += red[k][lane]; t[1] += red[k + 1][lane]; t[2] += red[k + 2][lane]; t[3] += red[k + 3][lane]; }
+    const float r = (t[0] + t[1]) + (t[2] + t[3]);
+    if (c < ENC_D) out0[c] = r; else if (c < 2 * ENC_D) out1[c - ENC_D] = r; else out2[c - 2 * ENC_D] = r;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ elementwise
 // out = x + dropout(y + bias)     x, out fp32 (or DTX), y DTY, bias fp32 [4*c4n] or NULL
 template <int DTX, int DTY>
@@ -1007,6 +1035,103 @@ __global__ void __launch_bounds__(256) ln_act_bwd_kernel(const void* __restrict_
       s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
     }
     *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + wib) * ENC_D + 4 * lane) = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ residual add + LN
+// A pre-norm block ends with  x1 = x + dropout(y + bias)  and the next block starts with  h = LayerNorm(x1): one pass
+// instead of two (x1 is written once and not read back), and one backward pass instead of two:
+//   dx1 = res + LN'(dh)   (res: the gradient reaching x1 through the residual path)      -> dx   (fp32, to x)
+//   dy  = mask(dx1) / keep                                                                 -> dyy  (y's dtype)
+// with per-CTA partials of d gamma, d beta and d bias (= column sums of dy).  One warp per row, lane owns 4 features.
+template <int DTY, int DTO>
+__global__ void __launch_bounds__(256) dropout_add_ln_fwd_kernel(const float* __restrict__ x, const void* __restrict__ y,
+                                                                 const float* __restrict__ lin_bias, int64_t n_rows,
+                                                                 uint32_t drop_thresh, float inv_keep, uint64_t seed,
+                                                                 const float* __restrict__ w, const float* __restrict__ bias,
+                                                                 float eps, float* __restrict__ x1, void* __restrict__ h,
+                                                                 float* __restrict__ mean, float* __restrict__ rstd) {
+  seed = epoch_seed(seed);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w4 = ldg_f4(w + 4 * lane), b4 = ldg_f4(bias + 4 * lane);
+  const float4 lb = lin_bias ? ldg_f4(lin_bias + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const float4 a = ldg_f4(x + r * ENC_D + 4 * lane);
+    float4 t = ld4<DTY>(y, r * ENC_D + 4 * lane);
+    t.x += lb.x; t.y += lb.y; t.z += lb.z; t.w += lb.w;
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      t.x = (rnd32(seed, e, 0u) >= drop_thresh) ? t.x * inv_keep : 0.f;
+      t.y = (rnd32(seed, e, 1u) >= drop_thresh) ? t.y * inv_keep : 0.f;
+      t.z = (rnd32(seed, e, 2u) >= drop_thresh) ? t.z * inv_keep : 0.f;
+      t.w = (rnd32(seed, e, 3u) >= drop_thresh) ? t.w * inv_keep : 0.f;
+    }
+    const float4 v = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+    *reinterpret_cast<float4*>(x1 + r * ENC_D + 4 * lane) = v;
+    const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / ENC_D);
+    const float4 c = make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu);
+    const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / ENC_D);
+    const float rs = rsqrtf(var + eps);
+    st4<DTO>(h, r * ENC_D + 4 * lane,
+             make_float4(c.x * rs * w4.x + b4.x, c.y * rs * w4.y + b4.y, c.z * rs * w4.z + b4.z, c.w * rs * w4.w + b4.w));
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+template <int DTY, int DTO>
+__global__ void __launch_bounds__(256) ln_bwd_dropout_kernel(const void* __restrict__ dh, const float* __restrict__ x1,
+                                                             const float* __restrict__ res, int64_t n_rows,
+                                                             const float* __restrict__ w, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, uint32_t drop_thresh,
+                                                             float inv_keep, uint64_t seed, float* __restrict__ dx,
+                                                             void* __restrict__ dyy, float* __restrict__ part /*[grid][3][128]*/) {
+  __shared__ float4 red[3][8][32];
+  seed = epoch_seed(seed);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w4 = ldg_f4(w + 4 * lane);
+  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f), db = dw, dl = dw;
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const float4 v = ldg_f4(x1 + r * ENC_D + 4 * lane);
+    const float4 g = ld4<DTO>(dh, r * ENC_D + 4 * lane);
+    const float mu = mean[r], rs = rstd[r];
+    const float4 xh = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+    dw.x += g.x * xh.x; dw.y += g.y * xh.y; dw.z += g.z * xh.z; dw.w += g.w * xh.w;
+    db.x += g.x; db.y += g.y; db.z += g.z; db.w += g.w;
+    const float4 gw = make_float4(g.x * w4.x, g.y * w4.y, g.z * w4.z, g.w * w4.w);
+    const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
+    const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
+    float4 o = make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
+                           rs * (gw.w - m1 - xh.w * m2));
+    if (res) {
+      const float4 rg = ldg_f4(res + r * ENC_D + 4 * lane);
+      o.x += rg.x; o.y += rg.y; o.z += rg.z; o.w += rg.w;
+    }
+    *reinterpret_cast<float4*>(dx + r * ENC_D + 4 * lane) = o;
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      o.x = (rnd32(seed, e, 0u) >= drop_thresh) ? o.x * inv_keep : 0.f;
+      o.y = (rnd32(seed, e, 1u) >= drop_thresh) ? o.y * inv_keep : 0.f;
+      o.z = (rnd32(seed, e, 2u) >= drop_thresh) ? o.z * inv_keep : 0.f;
+      o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
+    }
+    st4<DTY>(dyy, r * ENC_D + 4 * lane, o);
+    dl.x += o.x; dl.y += o.y; dl.z += o.z; dl.w += o.w;
+  }
+  red[0][wib][lane] = dw;
+  red[1][wib][lane] = db;
+  red[2][wib][lane] = dl;
+  __syncthreads();
+  if (wib < 3) {                                   // warps 0 / 1 / 2 fold d gamma / d beta / d bias in a fixed order
+    float4 s = red[wib][0][lane];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      const float4 t = red[wib][k][lane];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 3 + wib) * ENC_D + 4 * lane) = s;
   }
 }
 
@@ -1256,6 +1381,50 @@ extern "C" int rs_ln_act_bwd(const void* dy, int dy_dtype, const void* x, int x_
 #undef LN_ACT_BWD
   RS_LAUNCH_CHECK();
   partial_sum_kernel<<<(2 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, 2 * ENC_D, dw, db, ENC_D);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_dropout_add_ln_fwd(const float* x, const void* y, int y_dtype, const float* lin_bias, int64_t n_rows,
+                                     int64_t dim, float dropout_p, uint64_t seed, const float* w, const float* b,
+                                     float eps, float* x1, void* h, int h_dtype, float* mean, float* rstd,
+                                     void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!x || !y || !w || !b || !x1 || !h || !mean || !rstd || n_rows < 0) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (n_rows * (ENC_D / 4) >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  ENC_DISPATCH1(y_dtype, DTY, ENC_DISPATCH1(h_dtype, DTO, (dropout_add_ln_fwd_kernel<DTY, DTO><<<grid, 256, 0, st>>>(
+      x, y, lin_bias, n_rows, th, ik, seed, w, b, eps, x1, h, mean, rstd))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" size_t rs_ln_bwd_dropout_workspace_bytes(int64_t n_rows) {
+  return (size_t)ln_grid(n_rows) * 3 * ENC_D * sizeof(float);
+}
+
+extern "C" int rs_ln_bwd_dropout(const void* dh, int dh_dtype, const float* x1, const float* residual_grad,
+                                 int64_t n_rows, int64_t dim, const float* w, const float* mean, const float* rstd,
+                                 float dropout_p, uint64_t seed, float* dx, void* dy, int dy_dtype, float* dw, float* db,
+                                 float* d_lin_bias, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!dh || !x1 || !w || !mean || !rstd || !dx || !dy || !dw || !db || !d_lin_bias || !workspace) return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_ln_bwd_dropout_workspace_bytes(n_rows)) return RS_ERR_WORKSPACE;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  float* part = (float*)workspace;
+  ENC_DISPATCH1(dy_dtype, DTY, ENC_DISPATCH1(dh_dtype, DTO, (ln_bwd_dropout_kernel<DTY, DTO><<<grid, 256, 0, st>>>(
+      dh, x1, residual_grad, n_rows, w, mean, rstd, th, ik, seed, dx, dy, part))));
+  RS_LAUNCH_CHECK();
+  // part rows are [d gamma | d beta | d bias]: the first two go to (dw, db), the third to d_lin_bias
+  partial_sum3_kernel<<<(3 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, dw, db, d_lin_bias);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

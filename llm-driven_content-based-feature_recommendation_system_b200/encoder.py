@@ -217,6 +217,54 @@ def _(dy, x, add, add_rows, lin_bias, w, b, mean, rstd, act, dropout_p, seed):
     return [x.new_empty(dy.shape[0], x.shape[1]), torch.empty_like(w), torch.empty_like(w)]
 
 
+@torch.library.custom_op("rs::dropout_add_ln", mutates_args=())
+def dropout_add_ln_op(x: Tensor, y: Tensor, lin_bias: Optional[Tensor], w: Tensor, b: Tensor, eps: float,
+                      dropout_p: float, seed: int, out_dtype: int) -> List[Tensor]:
+    """x1 = x + dropout(y + lin_bias); h = LayerNorm(x1) -> [x1 fp32, h, mean, rstd] (rs_dropout_add_ln_fwd)."""
+    L.require_cuda(x, y, w, b)
+    assert x.dtype == torch.float32 and x.shape == y.shape and x.shape[1] == 128
+    x, y = x.contiguous(), y.contiguous()
+    n = x.shape[0]
+    x1 = torch.empty_like(x)
+    h = torch.empty(n, 128, dtype=L.torch_dtype(out_dtype), device=x.device)
+    mean = torch.empty(n, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+    L.check(_lib.rs_dropout_add_ln_fwd(L.ptr(x), L.ptr(y), L.dt(y), L.ptr(lin_bias), n, 128, dropout_p, seed, L.ptr(w),
+                                       L.ptr(b), eps, L.ptr(x1), L.ptr(h), out_dtype, L.ptr(mean), L.ptr(rstd),
+                                       L.stream()), "rs_dropout_add_ln_fwd")
+    return [x1, h, mean, rstd]
+
+
+@dropout_add_ln_op.register_fake
+def _(x, y, lin_bias, w, b, eps, dropout_p, seed, out_dtype):
+    n = x.shape[0]
+    return [torch.empty_like(x), x.new_empty(n, 128, dtype=L.torch_dtype(out_dtype)), x.new_empty(n), x.new_empty(n)]
+
+
+@torch.library.custom_op("rs::ln_bwd_dropout", mutates_args=())
+def ln_bwd_dropout_op(dh: Tensor, x1: Tensor, res: Optional[Tensor], w: Tensor, mean: Tensor, rstd: Tensor,
+                      dropout_p: float, seed: int, dy_dtype: int) -> List[Tensor]:
+    """-> [dx fp32, dy, d gamma, d beta, d lin_bias] (rs_ln_bwd_dropout)."""
+    dh = dh.contiguous()
+    if res is not None:
+        res = res.float().contiguous()
+    n = dh.shape[0]
+    dx = torch.empty_like(x1)
+    dy = torch.empty(n, 128, dtype=L.torch_dtype(dy_dtype), device=x1.device)
+    dw, db, dl = torch.empty_like(w), torch.empty_like(w), torch.empty_like(w)
+    ws = L.workspace(_lib.rs_ln_bwd_dropout_workspace_bytes(n), x1.device)
+    L.check(_lib.rs_ln_bwd_dropout(L.ptr(dh), L.dt(dh), L.ptr(x1), L.ptr(res), n, 128, L.ptr(w), L.ptr(mean), L.ptr(rstd),
+                                   dropout_p, seed, L.ptr(dx), L.ptr(dy), dy_dtype, L.ptr(dw), L.ptr(db), L.ptr(dl),
+                                   L.ptr(ws), ws.numel(), L.stream()), "rs_ln_bwd_dropout")
+    return [dx, dy, dw, db, dl]
+
+
+@ln_bwd_dropout_op.register_fake
+def _(dh, x1, res, w, mean, rstd, dropout_p, seed, dy_dtype):
+    return [torch.empty_like(x1), x1.new_empty(x1.shape, dtype=L.torch_dtype(dy_dtype)), torch.empty_like(w),
+            torch.empty_like(w), torch.empty_like(w)]
+
+
 @torch.library.custom_op("rs::dropout_add", mutates_args=())
 def dropout_add_op(x: Tensor, y: Tensor, bias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:
     L.require_cuda(x, y)
@@ -547,6 +595,37 @@ def residual_layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, out
     return _ResidualLN.apply(x, weight, bias, float(eps), L.dt(out_dtype))
 
 
+class _DropoutAddLN(torch.autograd.Function):
+    """(x1, h) with x1 = x + dropout(y + bias), h = LayerNorm(x1): the end of one pre-norm block and the start of the next
+    in one pass each way (rs_dropout_add_ln_fwd / rs_ln_bwd_dropout).  The gradient reaching x1 through the residual
+    path and the gradient of the LN branch meet in the one backward kernel, which also emits dy and the three parameter
+    gradients."""
+
+    @staticmethod
+    def forward(ctx, x, y, bias, w, b, eps, dropout_p, seed, out_dtype):
+        x1, h, mean, rstd = L.direct.dropout_add_ln(x, y, bias, w, b, eps, dropout_p, seed, out_dtype)
+        ctx.save_for_backward(x1, w, mean, rstd)
+        ctx.meta = (dropout_p, seed, L.dt(y), bias is not None)
+        return x1, h
+
+    @staticmethod
+    def backward(ctx, gx1, gh):
+        x1, w, mean, rstd = ctx.saved_tensors
+        p, seed, ydt, has_bias = ctx.meta
+        if gh is None:                              # the LN branch is unused: only the residual path carries a gradient
+            dy, dl = L.direct.dropout_bwd(gx1, p, seed, ydt, has_bias)
+            return gx1, dy, (dl if has_bias else None), None, None, None, None, None, None
+        dx, dy, dw, db, dl = L.direct.ln_bwd_dropout(gh, x1, gx1, w, mean, rstd, p, seed, ydt)
+        return dx, dy, (dl if has_bias else None), dw, db, None, None, None, None
+
+
+def dropout_add_layer_norm(x: Tensor, y: Tensor, dropout_p: float, bias: Optional[Tensor], weight: Tensor,
+                           ln_bias: Tensor, eps: float, out_dtype: torch.dtype):
+    """returns (x + dropout(y + bias), LayerNorm of that); x: the fp32 residual stream [T, 128]."""
+    return _DropoutAddLN.apply(x, y, bias, weight, ln_bias, float(eps), float(dropout_p),
+                               _seed() if dropout_p > 0 else 0, L.dt(out_dtype))
+
+
 class _DropoutAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, bias, dropout_p, seed):
@@ -737,18 +816,32 @@ def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
     return x
 
 
+def _add_norm(x: Tensor, pending, norm: torch.nn.LayerNorm, ad: torch.dtype):
+    """(residual stream, LayerNorm of it); `pending` = (y, bias, p): a block's closing  x + dropout(y + bias)  that has not
+    been applied yet -- it is then folded into the same pass as the LayerNorm (fp32 residual stream only)."""
+    if pending is None:
+        return residual_layer_norm(x, norm.weight, norm.bias, norm.eps, ad)
+    y, bias, p = pending
+    if x.dtype != torch.float32:
+        return residual_layer_norm(dropout_add(x, y, p, bias=bias), norm.weight, norm.bias, norm.eps, ad)
+    return dropout_add_layer_norm(x, y, p, bias, norm.weight, norm.bias, norm.eps, ad)
+
+
 def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int,
-                         zero_tail: int = 0, rows=None, one_row_from: int = -1, one_rows=None) -> Tensor:
+                         zero_tail: int = 0, rows=None, one_row_from: int = -1, one_rows=None, pending=None,
+                         defer_close: bool = False):
     """One pre-norm layer on the packed tokens.  `rows` = (n_prefix, idx): only the rows cat([arange(n_prefix), idx]) are
     wanted from this layer (idx: rows outside the prefix, -1 = none -> a zero row).  Attention still sees every token --
     the wanted rows attend to the others -- but everything behind it is position-wise, so the out-projection, the residual
-    adds, the second LayerNorm and the feed-forward block run on the wanted rows alone; returns [n_prefix + len(idx), 128]."""
+    adds, the second LayerNorm and the feed-forward block run on the wanted rows alone; returns [n_prefix + len(idx), 128].
+    `pending`: the previous layer's closing residual add, not yet applied (see _add_norm); `defer_close`: return
+    (x, pending) instead of applying this layer's own closing add, for the next layer to fold into its first LayerNorm."""
     if not layer.norm_first or layer.activation_relu_or_gelu != 2:
         raise NotImplementedError("packed encoder: pre-norm GELU layers only (the reference's configuration)")
     tr = layer.training
     attn = layer.self_attn
     ad = _act_dtype(x)
-    x, h = residual_layer_norm(x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ad)
+    x, h = _add_norm(x, pending, layer.norm1, ad)
     # the four biases are folded into the kernels that consume the GEMM outputs: plain matmuls, and the bias
     # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
     qkv = matmul_w(h, attn.in_proj_weight)
@@ -758,10 +851,13 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     if rows is not None:
         o = ops.select_prefix_rows(o, rows[0], rows[1], disjoint=True)
         x = ops.select_prefix_rows(x, rows[0], rows[1], disjoint=True)
-    x = dropout_add(x, matmul_w(o, attn.out_proj.weight), layer.dropout1.p if tr else 0.0, bias=attn.out_proj.bias)
-    x, h = residual_layer_norm(x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, ad)
+    x, h = _add_norm(x, (matmul_w(o, attn.out_proj.weight), attn.out_proj.bias, layer.dropout1.p if tr else 0.0),
+                     layer.norm2, ad)
     f = gelu_dropout(matmul_w(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
-    return dropout_add(x, matmul_w(f, layer.linear2.weight), layer.dropout2.p if tr else 0.0, bias=layer.linear2.bias)
+    close = (matmul_w(f, layer.linear2.weight), layer.linear2.bias, layer.dropout2.p if tr else 0.0)
+    if defer_close:
+        return x, close
+    return dropout_add(x, close[0], close[2], bias=close[1])
 
 
 def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,
@@ -772,10 +868,13 @@ def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: 
     but the token `one_rows` gives (or tokens whose value does not matter) -- the last layer's attention then computes
     only that row of them (attn_varlen)."""
     n_layers = len(encoder.layers)
+    pending = None
     for i, layer in enumerate(encoder.layers):
         last = i == n_layers - 1
-        x = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail, last_rows if last else None,
-                                 one_row_from if last else -1, one_rows if last else None)
+        out = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail, last_rows if last else None,
+                                   one_row_from if last else -1, one_rows if last else None, pending=pending,
+                                   defer_close=not last)
+        x, pending = out if not last else (out, None)
     if encoder.norm is not None:
         x = encoder.norm(x)
     return x

@@ -519,3 +519,54 @@ def test_attn_one_row_in_the_middle_of_a_sequence(rs):
     torch.testing.assert_close(part[keep], full[keep], rtol=1e-4, atol=1e-5)
     assert (part[~keep] == 0).all()
     torch.testing.assert_close(b.grad, a.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_dropout_add_layer_norm_fused_pass(rs):
+    """encoder.dropout_add_layer_norm == (x + dropout(y + bias), LayerNorm of it): against torch in fp32 with p = 0 (values
+    and all five gradients, both outputs used); with p > 0 the forward and backward share one mask and the bias gradient
+    is the column sum of dy."""
+    g = torch.Generator().manual_seed(31)
+    n = 777
+    x = torch.randn(n, 128, generator=g).to(DEV)
+    y = torch.randn(n, 128, generator=g).to(DEV)
+    bias, w, b = (torch.randn(128, generator=g).to(DEV) * 0.3 for _ in range(3))
+    w = w + 1.0
+    c1, c2 = torch.randn(n, 128, generator=g).to(DEV), torch.randn(n, 128, generator=g).to(DEV)
+    ref = [t.clone().requires_grad_(True) for t in (x, y, bias, w, b)]
+    x1 = ref[0] + ref[1] + ref[2]
+    h = F.layer_norm(x1, (128,), ref[3], ref[4], 1e-5)
+    ((x1 * c1).sum() + (h * c2).sum()).backward()
+    mine = [t.clone().requires_grad_(True) for t in (x, y, bias, w, b)]
+    x1m, hm = rs.encoder.dropout_add_layer_norm(mine[0], mine[1], 0.0, mine[2], mine[3], mine[4], 1e-5, torch.float32)
+    ((x1m * c1).sum() + (hm * c2).sum()).backward()
+    torch.testing.assert_close(x1m, x1.detach(), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(hm, h.detach(), rtol=1e-4, atol=1e-4)
+    for a, r in zip(mine, ref):
+        torch.testing.assert_close(a.grad, r.grad, rtol=1e-4, atol=1e-3)
+    # bf16 branch + dropout: kept entries of x1 - x equal (y + bias) / keep; dy is zero exactly where the forward dropped
+    p = 0.3
+    rs.encoder.rng_advance()
+    torch.manual_seed(5)
+    xb = x.clone().requires_grad_(True)
+    yb = y.to(torch.bfloat16).requires_grad_(True)
+    bb = bias.clone().requires_grad_(True)
+    x1d, hd = rs.encoder.dropout_add_layer_norm(xb, yb, p, bb, w, b, 1e-5, torch.bfloat16)
+    assert hd.dtype == torch.bfloat16
+    delta = x1d.detach() - x
+    kept = delta != 0
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.01
+    torch.testing.assert_close(delta[kept], ((yb.detach().float() + bias) / (1 - p))[kept], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(hd.float(), F.layer_norm(x1d.detach(), (128,), w, b, 1e-5), rtol=2e-2, atol=2e-2)
+    (x1d * c1).sum().backward()                              # LN branch unused
+    torch.testing.assert_close(yb.grad.float(), (c1 * kept / (1 - p)).to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(bb.grad, (c1 * kept / (1 - p)).to(torch.bfloat16).float().sum(0), rtol=1e-2, atol=2e-1)
+    torch.testing.assert_close(xb.grad, c1)
+    xb.grad = yb.grad = bb.grad = None
+    rs.encoder.rng_advance()
+    torch.manual_seed(6)
+    x1d, hd = rs.encoder.dropout_add_layer_norm(xb, yb, p, bb, w, b, 1e-5, torch.bfloat16)
+    kept = (x1d.detach() - x) != 0
+    ((x1d * c1).sum() + (hd.float() * c2).sum()).backward()   # both branches
+    assert ((yb.grad.float() == 0) | kept).all() and (yb.grad.float()[kept] != 0).float().mean() > 0.99
+    torch.testing.assert_close(yb.grad.float()[kept], (xb.grad / (1 - p))[kept], rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(bb.grad, yb.grad.float().sum(0), rtol=1e-2, atol=3e-1)
