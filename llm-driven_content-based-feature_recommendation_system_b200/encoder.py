@@ -23,6 +23,7 @@ masks come from a counter-based hash instead of Philox (same Bernoulli(1-p)/(1-p
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -453,7 +454,7 @@ def layer_norm_act(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, a
 # profiles/r02d_small_launches.txt.  `prepare_weights` makes all the copies with ONE multi-tensor launch at the start of
 # the step; the GEMM wrappers below pick them up and hand fp32 weight gradients straight out of the GEMM.
 _wcache: Dict[int, Tensor] = {}
-_wlists: Dict[int, list] = {}
+_wlists = weakref.WeakKeyDictionary()        # module -> its GEMM weights / biases (collected once)
 
 
 def prepare_weights(module: torch.nn.Module, dtype: Optional[torch.dtype]) -> None:
@@ -462,7 +463,7 @@ def prepare_weights(module: torch.nn.Module, dtype: Optional[torch.dtype]) -> No
     _wcache.clear()
     if dtype is None or dtype == torch.float32:
         return
-    ws = _wlists.get(id(module))
+    ws = _wlists.get(module)
     if ws is None:
         ws = []
         for m in module.modules():
@@ -471,7 +472,7 @@ def prepare_weights(module: torch.nn.Module, dtype: Optional[torch.dtype]) -> No
             elif isinstance(m, torch.nn.MultiheadAttention) and m.in_proj_weight is not None:
                 ws.append(m.in_proj_weight)
         ws = [w for w in ws if w.dtype == torch.float32 and w.is_cuda]
-        _wlists[id(module)] = ws
+        _wlists[module] = ws
     if not ws:
         return
     with torch.no_grad():
