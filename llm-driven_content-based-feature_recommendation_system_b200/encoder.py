@@ -320,11 +320,14 @@ def _(z, bias, dropout_p, seed):
 
 
 @torch.library.custom_op("rs::gelu_dropout_bwd", mutates_args=())
-def gelu_dropout_bwd_op(z: Tensor, bias: Optional[Tensor], g: Tensor, dropout_p: float, seed: int) -> List[Tensor]:
+def gelu_dropout_bwd_op(z: Tensor, bias: Optional[Tensor], g: Tensor, dropout_p: float, seed: int,
+                        want_colsum: bool = False) -> List[Tensor]:
+    """[dz, column sums of dz] (the sums when a bias was folded in, or `want_colsum`: the bias then sits in z already)."""
     g = g.to(z.dtype).contiguous()
     dz = torch.empty_like(z)
     n_cols = z.shape[-1]
-    if bias is not None and _fused_colsum_ok(n_cols):
+    want_colsum = want_colsum or bias is not None
+    if want_colsum and _fused_colsum_ok(n_cols):
         db = torch.empty(n_cols, dtype=torch.float32, device=z.device)
         ws = L.workspace(_lib.rs_ew_colsum_workspace_bytes(z.numel(), n_cols), z.device)
         L.check(_lib.rs_gelu_dropout_bwd_bias(L.ptr(z), L.ptr(g), L.dt(z), L.ptr(bias), n_cols, z.numel(), dropout_p, seed,
@@ -333,12 +336,12 @@ def gelu_dropout_bwd_op(z: Tensor, bias: Optional[Tensor], g: Tensor, dropout_p:
         return [dz, db]
     L.check(_lib.rs_gelu_dropout_bwd(L.ptr(z), L.ptr(g), L.dt(z), L.ptr(bias), z.shape[-1], z.numel(), dropout_p, seed,
                                      L.ptr(dz), L.stream()), "rs_gelu_dropout_bwd")
-    return [dz, _colsum(dz) if bias is not None else z.new_empty(0, dtype=torch.float32)]
+    return [dz, _colsum(dz) if want_colsum else z.new_empty(0, dtype=torch.float32)]
 
 
 @gelu_dropout_bwd_op.register_fake
-def _(z, bias, g, dropout_p, seed):
-    return [torch.empty_like(z), z.new_empty(z.shape[-1] if bias is not None else 0, dtype=torch.float32)]
+def _(z, bias, g, dropout_p, seed, want_colsum=False):
+    return [torch.empty_like(z), z.new_empty(z.shape[-1] if (bias is not None or want_colsum) else 0, dtype=torch.float32)]
 
 
 # ------------------------------------------------------------------------------------------------ autograd
@@ -470,7 +473,7 @@ def prepare_weights(module: torch.nn.Module, dtype: Optional[torch.dtype]) -> No
             if isinstance(m, torch.nn.Linear):
                 ws += [m.weight] + ([m.bias] if m.bias is not None else [])
             elif isinstance(m, torch.nn.MultiheadAttention) and m.in_proj_weight is not None:
-                ws.append(m.in_proj_weight)
+                ws += [m.in_proj_weight] + ([m.in_proj_bias] if m.in_proj_bias is not None else [])
         ws = [w for w in ws if w.dtype == torch.float32 and w.is_cuda]
         _wlists[module] = ws
     if not ws:
@@ -659,6 +662,35 @@ class _GeluDropout(torch.autograd.Function):
         return dz, (db if bias is not None else None), None, None
 
 
+class _LinearGeluDropout(torch.autograd.Function):
+    """dropout(gelu(x @ W^T + b)) for an fp32 nn.Linear under a 16-bit activation x: the bias rides in the GEMM's epilogue
+    (one rounding of acc + b, as the reference's Linear), the GELU / dropout kernel has no bias work, and the bias gradient
+    is still the column sum that the GELU backward kernel accumulates while it writes dz."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, dropout_p, seed):
+        wb, bb = _w16(weight, x.dtype), _w16(bias, x.dtype)
+        with torch.autocast("cuda", enabled=False):
+            z = torch.addmm(bb, x, wb.t())
+        ctx.save_for_backward(x, wb, z)
+        ctx.meta = (dropout_p, seed, weight.dtype, bias.dtype)
+        return L.direct.gelu_dropout(z, None, dropout_p, seed)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wb, z = ctx.saved_tensors
+        p, seed, wdt, bdt = ctx.meta
+        dz, db = L.direct.gelu_dropout_bwd(z, None, g, p, seed, True)
+        dx = dz @ wb if ctx.needs_input_grad[0] else None
+        dw = _mm32(dz.t(), x).to(wdt) if ctx.needs_input_grad[1] else None
+        return dx, dw, db.to(bdt), None, None
+
+
+def linear_gelu_dropout(x: Tensor, lin: torch.nn.Linear, dropout_p: float = 0.0) -> Tensor:
+    """dropout(gelu(lin(x))) -- see _LinearGeluDropout; x [rows, in_features] in the GEMM's operand dtype."""
+    return _LinearGeluDropout.apply(x, lin.weight, lin.bias, float(dropout_p), _seed() if dropout_p > 0 else 0)
+
+
 def gelu_dropout(z: Tensor, dropout_p: float = 0.0, bias: Optional[Tensor] = None) -> Tensor:
     """dropout(gelu(z + bias))"""
     return _GeluDropout.apply(z, bias, float(dropout_p), _seed() if dropout_p > 0 else 0)
@@ -817,6 +849,13 @@ def sequential(seq: torch.nn.Sequential, x: Tensor) -> Tensor:
     return x
 
 
+import os as _os
+# in_proj / linear1: the bias in the library GEMM's epilogue (True) or folded into the kernel that consumes the GEMM output
+# (False; the round-1 layout, kept for A/B runs: RS_BIAS_IN_GEMM=0).  The consumers of these two GEMMs -- the attention
+# tiles and the GELU kernel -- are instruction-bound, so the add belongs in the epilogue: 7.88 -> 7.75 ms per step.
+BIAS_IN_GEMM = _os.environ.get('RS_BIAS_IN_GEMM', '1') == '1'
+
+
 def _add_norm(x: Tensor, pending, norm: torch.nn.LayerNorm, ad: torch.dtype):
     """(residual stream, LayerNorm of it); `pending` = (y, bias, p): a block's closing  x + dropout(y + bias)  that has not
     been applied yet -- it is then folded into the same pass as the LayerNorm (fp32 residual stream only)."""
@@ -845,16 +884,24 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     x, h = _add_norm(x, pending, layer.norm1, ad)
     # the four biases are folded into the kernels that consume the GEMM outputs: plain matmuls, and the bias
     # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
-    qkv = matmul_w(h, attn.in_proj_weight)
+    # (in_proj: the bias rides in the GEMM's epilogue -- free there, one add per fragment load in the attention kernels
+    # otherwise -- and its gradient is still the column sum of d_qkv, taken by the Linear wrapper's backward)
+    if BIAS_IN_GEMM and attn.in_proj_bias is not None:
+        qkv, qkv_bias = _LinearColsumBias.apply(h, attn.in_proj_weight, attn.in_proj_bias), None
+    else:
+        qkv, qkv_bias = matmul_w(h, attn.in_proj_weight), attn.in_proj_bias
     o = attn_varlen(qkv, cu_seqlens, attn.num_heads, max_len, attn.dropout if tr else 0.0, zero_tail=zero_tail,
-                    bias=attn.in_proj_bias, one_row_from=one_row_from if rows is not None else -1,
+                    bias=qkv_bias, one_row_from=one_row_from if rows is not None else -1,
                     one_rows=one_rows if rows is not None else None)
     if rows is not None:
         o = ops.select_prefix_rows(o, rows[0], rows[1], disjoint=True)
         x = ops.select_prefix_rows(x, rows[0], rows[1], disjoint=True)
     x, h = _add_norm(x, (matmul_w(o, attn.out_proj.weight), attn.out_proj.bias, layer.dropout1.p if tr else 0.0),
                      layer.norm2, ad)
-    f = gelu_dropout(matmul_w(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
+    if BIAS_IN_GEMM and layer.linear1.bias is not None and h.dtype != torch.float32:
+        f = linear_gelu_dropout(h, layer.linear1, layer.dropout.p if tr else 0.0)
+    else:
+        f = gelu_dropout(matmul_w(h, layer.linear1.weight), layer.dropout.p if tr else 0.0, bias=layer.linear1.bias)
     close = (matmul_w(f, layer.linear2.weight), layer.linear2.bias, layer.dropout2.p if tr else 0.0)
     if defer_close:
         return x, close
