@@ -570,3 +570,26 @@ def test_dropout_add_layer_norm_fused_pass(rs):
     assert ((yb.grad.float() == 0) | kept).all() and (yb.grad.float()[kept] != 0).float().mean() > 0.99
     torch.testing.assert_close(yb.grad.float()[kept], (xb.grad / (1 - p))[kept], rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(bb.grad, yb.grad.float().sum(0), rtol=1e-2, atol=3e-1)
+
+
+def test_gelu_dropout_mask_law_and_fwd_bwd_agreement(rs):
+    """gelu_dropout with p > 0 (two 32-bit hashes -> four 16-bit keep decisions): keep rate, independence of the four
+    decisions of one hash pair, per-column rates, and the backward uses the forward's mask."""
+    p = 0.25
+    rs.encoder.rng_advance()
+    torch.manual_seed(11)
+    z = (torch.randn(4096, 256, device=DEV) + 3.0).bfloat16().requires_grad_(True)      # gelu(z) != 0 almost surely
+    f = rs.encoder.gelu_dropout(z, p)
+    kept = f != 0
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.005
+    assert (kept.float().mean(0) - (1 - p)).abs().max() < 0.04
+    k4 = kept.view(-1, 4).float()
+    for a in range(4):
+        for b in range(a + 1, 4):                               # pairwise joint keep rate == (1-p)^2
+            assert abs((k4[:, a] * k4[:, b]).mean().item() - (1 - p) ** 2) < 0.01, (a, b)
+    ref = torch.nn.functional.gelu(z.detach().float()).bfloat16().float() / (1 - p)
+    torch.testing.assert_close(f.float()[kept], ref[kept], rtol=2e-2, atol=2e-2)
+    f.float().sum().backward()
+    assert ((z.grad != 0) == kept).float().mean().item() > 0.999
+    f2 = rs.encoder.gelu_dropout(z, p)
+    assert not torch.equal(f2 != 0, kept)
