@@ -68,6 +68,17 @@ __device__ __forceinline__ void ub_copy4(typename UbStore<DT>::T* dst, const voi
   }
 }
 
+// 4 consecutive elements of a global row as stored (bit for bit), zeros when !ok
+template <int DT> struct UbVec { using T = uint2; };
+template <> struct UbVec<RS_F32> { using T = float4; };
+template <int DT>
+__device__ __forceinline__ typename UbVec<DT>::T ub_ldg4(const void* base, int64_t off, bool ok) {
+  if constexpr (DT == RS_F32)
+    return ok ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  else
+    return ok ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off)) : make_uint2(0u, 0u);
+}
+
 // stage the user's rows: sU[i][:] = u[r0 + i], sC[i][:] = cols[pos_col[r0 + i]]; sCol[i] = pos_col (int), sBias[i]
 template <int DT>
 __device__ __forceinline__ void ub_stage(const UbParams& p, int64_t r0, int len, typename UbStore<DT>::T* sU,
@@ -79,11 +90,29 @@ __device__ __forceinline__ void ub_stage(const UbParams& p, int64_t r0, int len,
     sBias[i] = (ok && p.col_bias) ? __ldg(p.col_bias + c) : 0.f;
   }
   __syncthreads();
+  // a warp fetches 4 row pairs per round: all 8 global loads are issued before the first shared-memory store (the
+  // one-pair-per-iteration loop exposed a full memory latency per row: the kernels are bound by these gathers)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = w; i < len; i += UB_THREADS / 32) {
-    ub_copy4<DT>(sU + i * UB_STRIDE + 4 * lane, p.u, (r0 + i) * UB_D + 4 * lane, true);
-    const int c = sCol[i];
-    ub_copy4<DT>(sC + i * UB_STRIDE + 4 * lane, p.cols, (int64_t)(c >= 0 ? c : 0) * UB_D + 4 * lane, c >= 0);
+  constexpr int NW = UB_THREADS / 32, G = 4;
+  using VT = typename UbVec<DT>::T;
+  for (int i0 = w; i0 < len; i0 += NW * G) {
+    VT vu[G], vc[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int i = i0 + q * NW;
+      const bool live = i < len;
+      const int c = live ? sCol[i] : -1;
+      vu[q] = ub_ldg4<DT>(p.u, (r0 + (live ? i : 0)) * UB_D + 4 * lane, live);
+      vc[q] = ub_ldg4<DT>(p.cols, (int64_t)(c >= 0 ? c : 0) * UB_D + 4 * lane, c >= 0);
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int i = i0 + q * NW;
+      if (i < len) {
+        *reinterpret_cast<VT*>(sU + i * UB_STRIDE + 4 * lane) = vu[q];
+        *reinterpret_cast<VT*>(sC + i * UB_STRIDE + 4 * lane) = vc[q];
+      }
+    }
   }
   __syncthreads();
 }
