@@ -170,6 +170,7 @@ def seq_front_bwd_op(dx: Tensor, ids: Sequence[Tensor], tables: Sequence[Tensor]
             small_budget -= r
         else:
             mode.append(0 if deterministic else 1)
+    # (outputs of a registered custom op must not share storage: one allocation each)
     d_tables = [torch.zeros(r, dim, dtype=torch.float32, device=dev) for r in rows]
     d_gates = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
     d_pos = torch.empty(seq_len, dim, dtype=torch.float32, device=dev)
@@ -514,6 +515,21 @@ def _(a, b, idx, scale, key_row, key_col, g):
 
 
 # ---- N1: on-device batch assembly ---------------------------------------------------------------
+def zeros_many(shapes, device, dtype=torch.float32):
+    """One zero-filled allocation, returned as one contiguous tensor per shape (256-byte aligned views): a single fill
+    launch instead of one per tensor.  Only for tensors built inside autograd Functions: the outputs of a registered
+    custom op must not share storage."""
+    esz = torch.empty(0, dtype=dtype).element_size()
+    q = 256 // esz
+    sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + q - 1) // q * q
+    flat = torch.zeros(max(total, 1), dtype=dtype, device=device)
+    return [flat[o:o + n].view(*sh) for o, n, sh in zip(offs, sizes, shapes)]
+
+
 def round_up(n: int, q: int) -> int:
     return (int(n) + q - 1) // q * q
 
@@ -925,8 +941,8 @@ class _SeqFront(torch.autograd.Function):
         tables = list(ctx.saved_tensors[1 + n_live:])
         res = L.direct.seq_front_bwd(dx, ids, tables[:n_live], gates[:n_live].contiguous(), L_, padding_idx,
                                          DETERMINISTIC)
-        d_tables = list(res[:n_live]) + [torch.zeros_like(t) for t in tables[n_live:]]
-        d_gates = torch.zeros_like(gates)
+        *dead, d_gates = zeros_many([tuple(t.shape) for t in tables[n_live:]] + [tuple(gates.shape)], dx.device)
+        d_tables = list(res[:n_live]) + dead
         d_gates[:n_live] = res[n_live][:n_live]
         d_pos = None
         if pos_rows is not None:

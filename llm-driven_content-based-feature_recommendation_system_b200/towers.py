@@ -36,7 +36,7 @@ class _ZeroGradTables(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (g,) + tuple(torch.zeros_like(t) for t in ctx.saved_tensors)
+        return (g,) + tuple(ops.zeros_many([tuple(t.shape) for t in ctx.saved_tensors], g.device))
 
 
 class SASRecUserTower(nn.Module):
