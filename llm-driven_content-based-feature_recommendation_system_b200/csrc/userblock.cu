@@ -247,10 +247,320 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_kernel(UbParams p, const fl
   }
 }
 
+// =============================================================================================
+// 16-bit operands: the three small products of a user block on the tensor cores (mma.sync m16n8k16)
+// =============================================================================================
+// A user block is l <= 64 rows: S = U C^T is [l, l] over K = 128, and the two gradient products are [l, l] x [l, 128].
+// The SIMT kernels above spend ~1000 issue slots per thread on them (ub_bwd_kernel: 63 % issue in ncu r02b); here a warp
+// owns a 16-row tile and the whole block costs a few dozen mma instructions.  Operands stay in shared memory as staged
+// (row pitch 136 elements = 272 B: 16-byte aligned rows, conflict-free ldmatrix).  The gradient coefficients are split
+// into a 16-bit head and a 16-bit remainder (two mma per product): their rounding error is 2^-17, not 2^-9, so the
+// gradients keep the accuracy of the fp32-coefficient kernels.  Logits, softmax statistics and coefficients never
+// leave registers (quad shuffles reduce a row).
+#define UBM_LD 136
+#define UBM_CLD 72             // coefficient planes: [64][72] 16-bit
+
+template <int DT>
+__device__ __forceinline__ void ubm_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (DT == RS_BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ubm_ldsm4(uint32_t (&r)[4], const uint16_t* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ubm_ldsm4_trans(uint32_t (&r)[4], const uint16_t* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <int DT> __device__ __forceinline__ uint16_t ubm_to16(float x) {
+  if constexpr (DT == RS_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(x); return *reinterpret_cast<uint16_t*>(&h); }
+  else { __half h = __float2half_rn(x); return *reinterpret_cast<uint16_t*>(&h); }
+}
+template <int DT> __device__ __forceinline__ float ubm_from16(uint16_t u) {
+  if constexpr (DT == RS_BF16) return __uint_as_float((uint32_t)u << 16);
+  else return __half2float(*reinterpret_cast<const __half*>(&u));
+}
+__device__ __forceinline__ float ubm_quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float ubm_quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ void red_add_f2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// stage rows [0, LT) (LT = len rounded up to 16): real rows from global memory, the padding rows as zeros
+__device__ __forceinline__ void ubm_stage(const UbParams& p, int64_t r0, int len, int LT, uint16_t* sU, uint16_t* sC,
+                                          int* sCol, float* sBias) {
+  for (int i = threadIdx.x; i < LT; i += UB_THREADS) {
+    int64_t c = -1;
+    if (i < len) c = __ldg(p.pos_col + r0 + i);
+    const bool ok = c >= 0 && c < p.n_cols;
+    sCol[i] = ok ? (int)c : -1;
+    sBias[i] = (ok && p.col_bias) ? __ldg(p.col_bias + c) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int NW = UB_THREADS / 32, G = 4;
+  for (int i0 = w; i0 < LT; i0 += NW * G) {
+    uint2 vu[G], vc[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int i = i0 + q * NW;
+      const bool live = i < len;
+      const int c = i < LT ? sCol[i] : -1;
+      vu[q] = live ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.u) + (r0 + i) * UB_D + 4 * lane))
+                   : make_uint2(0u, 0u);
+      vc[q] = c >= 0 ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.cols) + (int64_t)c * UB_D + 4 * lane))
+                     : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int i = i0 + q * NW;
+      if (i < LT) {
+        *reinterpret_cast<uint2*>(sU + i * UBM_LD + 4 * lane) = vu[q];
+        *reinterpret_cast<uint2*>(sC + i * UBM_LD + 4 * lane) = vc[q];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// s[ct][e]: logits of the warp's 16-row tile `rt` against the column tiles ct < LT/8 (8 columns each), scale and bias
+// applied.  Fragment layout: e = 0,1 -> row g, columns 8 ct + 2 t (+1); e = 2,3 -> row g + 8.
+template <int DT>
+__device__ __forceinline__ void ubm_logits(float (&s)[8][4], const UbParams& p, int rt, int LT, const uint16_t* sU,
+                                           const uint16_t* sC, const float* sBias, int lane) {
+  uint32_t a[8][4];
+  {
+    const uint16_t* base = sU + (rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * UBM_LD + (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) ubm_ldsm4(a[ks], base + 16 * ks);
+  }
+  const int t = lane & 3;
+#pragma unroll
+  for (int ct = 0; ct < 8; ++ct) {
+    s[ct][0] = s[ct][1] = s[ct][2] = s[ct][3] = 0.f;
+    if (ct * 8 < LT) {
+      const uint16_t* bb = sC + (ct * 8 + (lane & 7)) * UBM_LD + (lane >> 3) * 8;
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {                  // two k-steps per ldmatrix.x4
+        uint32_t r[4];
+        ubm_ldsm4(r, bb + 32 * k2);
+        ubm_mma<DT>(s[ct], a[2 * k2], r[0], r[1]);
+        ubm_mma<DT>(s[ct], a[2 * k2 + 1], r[2], r[3]);
+      }
+      const float b0 = sBias[ct * 8 + 2 * t], b1 = sBias[ct * 8 + 2 * t + 1];
+      s[ct][0] = s[ct][0] * p.scale - b0; s[ct][1] = s[ct][1] * p.scale - b1;
+      s[ct][2] = s[ct][2] * p.scale - b0; s[ct][3] = s[ct][3] * p.scale - b1;
+    }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(UB_THREADS) ub_fwd_mma_kernel(UbParams p, int ML16, float* __restrict__ s_pos,
+                                                                float* __restrict__ own_lse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* sU = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* sC = sU + ML16 * UBM_LD;
+  float* sBias = reinterpret_cast<float*>(sC + ML16 * UBM_LD);
+  int* sCol = reinterpret_cast<int*>(sBias + ML16);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
+    const int64_t r0 = __ldg(p.row_cu + b);
+    const int true_len = (int)(__ldg(p.row_cu + b + 1) - r0);
+    const int len = min(true_len, p.max_len);
+    for (int i = len + threadIdx.x; i < true_len; i += UB_THREADS) {          // (see ub_fwd_kernel)
+      s_pos[r0 + i] = __int_as_float(0x7fc00000);
+      own_lse[r0 + i] = __int_as_float(0x7fc00000);
+    }
+    if (len <= 0) continue;
+    const int LT = (len + 15) & ~15;
+    __syncthreads();
+    ubm_stage(p, r0, len, LT, sU, sC, sCol, sBias);
+    if (w * 16 < len) {
+      float s[8][4];
+      ubm_logits<DT>(s, p, w, LT, sU, sC, sBias, lane);
+      const int i0 = w * 16 + g, i1 = i0 + 8;
+      const int ci[2] = {sCol[i0], sCol[i1]};
+      float m[2] = {-INFINITY, -INFINITY}, sp[2] = {0.f, 0.f};
+#pragma unroll
+      for (int ct = 0; ct < 8; ++ct)
+        if (ct * 8 < LT) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
+            const int cj = sCol[j];
+            if (j == (r ? i1 : i0)) sp[r] = s[ct][e];
+            if (cj >= 0 && cj != ci[r]) m[r] = fmaxf(m[r], s[ct][e]);
+          }
+        }
+      m[0] = ubm_quad_max(m[0]); m[1] = ubm_quad_max(m[1]);
+      float l[2] = {0.f, 0.f};
+#pragma unroll
+      for (int ct = 0; ct < 8; ++ct)
+        if (ct * 8 < LT) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
+            const int cj = sCol[j];
+            if (cj >= 0 && cj != ci[r] && m[r] > -INFINITY) l[r] += __expf(s[ct][e] - m[r]);
+          }
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float lt = ubm_quad_sum(l[r]), spv = ubm_quad_sum(sp[r]);
+        const int i = r ? i1 : i0;
+        if (t == 0 && i < len) {
+          s_pos[r0 + i] = ci[r] >= 0 ? spv : -INFINITY;
+          own_lse[r0 + i] = m[r] > -INFINITY ? m[r] + __logf(lt) : -INFINITY;
+        }
+      }
+    }
+  }
+}
+
+// acc[4 n-tiles of 8 features][4] += (A_hi + A_lo)[16 x 16] . T[16 rows x 32 features], T staged with pitch UBM_LD
+template <int DT>
+__device__ __forceinline__ void ubm_mma_tile(float (&acc)[4][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                             const uint16_t* tile, int lane) {
+  const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int np = 0; np < 2; ++np) {
+    uint32_t r[4];
+    ubm_ldsm4_trans(r, tile + ((mi & 1) * 8 + rr) * UBM_LD + 8 * (2 * np + (mi >> 1)));
+    ubm_mma<DT>(acc[2 * np], ah, r[0], r[1]);
+    ubm_mma<DT>(acc[2 * np], al, r[0], r[1]);
+    ubm_mma<DT>(acc[2 * np + 1], ah, r[2], r[3]);
+    ubm_mma<DT>(acc[2 * np + 1], al, r[2], r[3]);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(UB_THREADS) ub_bwd_mma_kernel(UbParams p, int ML16, const float* __restrict__ own_lse,
+                                                                const float* __restrict__ g_pos,
+                                                                const float* __restrict__ g_own, float* __restrict__ d_u,
+                                                                float* __restrict__ d_cols) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* sU = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* sC = sU + ML16 * UBM_LD;
+  uint16_t* sH = sC + ML16 * UBM_LD;                    // coefficient heads  [ML16][UBM_CLD]
+  uint16_t* sL = sH + ML16 * UBM_CLD;                   // coefficient remainders
+  float* sBias = reinterpret_cast<float*>(sL + ML16 * UBM_CLD);
+  int* sCol = reinterpret_cast<int*>(sBias + ML16);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
+    const int64_t r0 = __ldg(p.row_cu + b);
+    const int len = min((int)(__ldg(p.row_cu + b + 1) - r0), p.max_len);
+    if (len <= 0) continue;
+    const int LT = (len + 15) & ~15;
+    __syncthreads();
+    ubm_stage(p, r0, len, LT, sU, sC, sCol, sBias);
+    if (w * 16 < LT) {
+      float s[8][4];
+      ubm_logits<DT>(s, p, w, LT, sU, sC, sBias, lane);
+      const int i0 = w * 16 + g, i1 = i0 + 8;
+      const int ci[2] = {sCol[i0], sCol[i1]};
+      float gp[2] = {0.f, 0.f}, go[2] = {0.f, 0.f}, ol[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = r ? i1 : i0;
+        if (i < len && ci[r] >= 0) { gp[r] = __ldg(g_pos + r0 + i); go[r] = __ldg(g_own + r0 + i); ol[r] = __ldg(own_lse + r0 + i); }
+      }
+#pragma unroll
+      for (int ct = 0; ct < 8; ++ct)
+        if (ct * 8 < LT) {
+          float c[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
+            const int i = r ? i1 : i0;
+            const int cj = sCol[j];
+            float v = 0.f;
+            if (ci[r] >= 0 && cj >= 0) {
+              if (i == j) v = gp[r];
+              else if (cj != ci[r] && ol[r] > -INFINITY) v = go[r] * __expf(s[ct][e] - ol[r]);
+            }
+            c[e] = v * p.scale;
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int i = r ? i1 : i0;
+            const uint16_t h0 = ubm_to16<DT>(c[2 * r]), h1 = ubm_to16<DT>(c[2 * r + 1]);
+            const uint16_t l0 = ubm_to16<DT>(c[2 * r] - ubm_from16<DT>(h0)), l1 = ubm_to16<DT>(c[2 * r + 1] - ubm_from16<DT>(h1));
+            *reinterpret_cast<uint32_t*>(sH + i * UBM_CLD + ct * 8 + 2 * t) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            *reinterpret_cast<uint32_t*>(sL + i * UBM_CLD + ct * 8 + 2 * t) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+          }
+        }
+    }
+    __syncthreads();
+    if (w * 16 < LT) {
+      // ---- d_u rows of tile w:  sum_j coef[i][j] c_j      A = coef[16 i][16 j] (row-major), B = sC rows j (trans)
+      const uint16_t* abase = (w * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * UBM_CLD + (lane >> 4) * 8 + sH;
+      const int i0 = w * 16 + g, i1 = i0 + 8;
+#pragma unroll 1
+      for (int fg = 0; fg < 4; ++fg) {
+        float acc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        for (int kt = 0; kt * 16 < LT; ++kt) {
+          uint32_t ah[4], al[4];
+          ubm_ldsm4(ah, abase + kt * 16);
+          ubm_ldsm4(al, abase + kt * 16 + (sL - sH));
+          ubm_mma_tile<DT>(acc, ah, al, sC + kt * 16 * UBM_LD + fg * 32, lane);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int f = fg * 32 + 8 * n + 2 * t;
+          if (i0 < len) *reinterpret_cast<float2*>(d_u + (r0 + i0) * UB_D + f) = make_float2(acc[n][0], acc[n][1]);
+          if (i1 < len) *reinterpret_cast<float2*>(d_u + (r0 + i1) * UB_D + f) = make_float2(acc[n][2], acc[n][3]);
+        }
+      }
+      // ---- d_cols rows of the items j of tile w:  sum_i coef[i][j] u_i      A = coef^T (ldmatrix.trans), B = sU rows i
+      const int j0 = w * 16 + g, j1 = j0 + 8;
+      const int cj0 = sCol[j0], cj1 = sCol[j1];
+      const uint16_t* tbase = sH + ((lane & 7) + (lane >> 4) * 8) * UBM_CLD + w * 16 + ((lane >> 3) & 1) * 8;
+#pragma unroll 1
+      for (int fg = 0; fg < 4; ++fg) {
+        float acc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        for (int it = 0; it * 16 < LT; ++it) {
+          uint32_t ah[4], al[4];
+          ubm_ldsm4_trans(ah, tbase + it * 16 * UBM_CLD);
+          ubm_ldsm4_trans(al, tbase + it * 16 * UBM_CLD + (sL - sH));
+          ubm_mma_tile<DT>(acc, ah, al, sU + it * 16 * UBM_LD + fg * 32, lane);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int f = fg * 32 + 8 * n + 2 * t;
+          if (cj0 >= 0) red_add_f2(d_cols + (int64_t)cj0 * UB_D + f, acc[n][0], acc[n][1]);
+          if (cj1 >= 0) red_add_f2(d_cols + (int64_t)cj1 * UB_D + f, acc[n][2], acc[n][3]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace rs
 
 using namespace rs;
 
+static size_t ubm_smem(int ml16, bool bwd) {
+  return (size_t)2 * ml16 * UBM_LD * 2 + (bwd ? (size_t)2 * ml16 * UBM_CLD * 2 : 0) + (size_t)ml16 * (sizeof(float) + sizeof(int));
+}
 static size_t ub_smem(int max_len, int dtype) {
   const size_t esz = dtype == RS_F32 ? 4 : 2;
   return (size_t)2 * max_len * UB_STRIDE * esz + ((size_t)max_len * max_len + 2 * (size_t)max_len) * sizeof(float);
@@ -282,6 +592,20 @@ extern "C" int rs_user_block_logits_fwd(const void* u, const void* cols, int dty
   const size_t smem = ub_smem(max_len, dtype);
   const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 12 ? n_users : (int64_t)RS_NUM_SMS * 12);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype != RS_F32) {                       // 16-bit operands: tensor-core tiles
+    const int ml16 = (max_len + 15) & ~15;
+    const size_t sm = ubm_smem(ml16, false);
+#define UBM_FWD(DT)                                                                                                   \
+    do {                                                                                                              \
+      cudaError_t e = cudaFuncSetAttribute(ub_fwd_mma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+      if (e != cudaSuccess) return (int)e;                                                                            \
+      ub_fwd_mma_kernel<DT><<<grid, UB_THREADS, sm, st>>>(p, ml16, s_pos, own_lse);                                    \
+    } while (0)
+    if (dtype == RS_BF16) UBM_FWD(RS_BF16); else if (dtype == RS_F16) UBM_FWD(RS_F16); else return RS_ERR_BAD_ARG;
+#undef UBM_FWD
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+  }
   UB_DISPATCH(dtype, DT, {
     cudaError_t e = cudaFuncSetAttribute(ub_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -303,6 +627,20 @@ extern "C" int rs_user_block_logits_bwd(const void* u, const void* cols, int dty
   const size_t smem = ub_smem(max_len, dtype);
   const int grid = (int)(n_users < (int64_t)RS_NUM_SMS * 12 ? n_users : (int64_t)RS_NUM_SMS * 12);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype != RS_F32) {
+    const int ml16 = (max_len + 15) & ~15;
+    const size_t sm = ubm_smem(ml16, true);
+#define UBM_BWD(DT)                                                                                                   \
+    do {                                                                                                              \
+      cudaError_t e = cudaFuncSetAttribute(ub_bwd_mma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+      if (e != cudaSuccess) return (int)e;                                                                            \
+      ub_bwd_mma_kernel<DT><<<grid, UB_THREADS, sm, st>>>(p, ml16, own_lse, g_pos, g_own, d_u, d_cols);                \
+    } while (0)
+    if (dtype == RS_BF16) UBM_BWD(RS_BF16); else if (dtype == RS_F16) UBM_BWD(RS_F16); else return RS_ERR_BAD_ARG;
+#undef UBM_BWD
+    RS_LAUNCH_CHECK();
+    return RS_OK;
+  }
   UB_DISPATCH(dtype, DT, {
     cudaError_t e = cudaFuncSetAttribute(ub_bwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -429,9 +429,10 @@ def test_train_step_column_modes_agree(rs):
             assert (g - w).abs().max() <= 2e-2 * w.abs().max() + 1e-8, (mode, (g - w).abs().max(), w.abs().max())
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_user_block_logits_vs_torch(rs, dtype):
-    """per-user dense blocks: label logit, log-sum-exp over the user's OTHER items, and both gradients."""
+    """per-user dense blocks: label logit, log-sum-exp over the user's OTHER items, and both gradients (fp32: the SIMT
+    kernels; 16-bit operands: the mma.sync tile kernels with head + remainder coefficients -- same tolerance)."""
     g = torch.Generator().manual_seed(11)
     lens = [1, 5, 50, 2, 17, 33, 1, 8]
     n, n_cols = sum(lens), 40
