@@ -84,6 +84,7 @@ struct AttnParams {
   int64_t zero_from;        // sequences b >= zero_from are fully masked queries: output 0, no gradient
   int64_t full_to;          // sequences in [full_to, zero_from) are only read at ONE token each (attn_one_* kernels):
                             // the main kernels skip them
+  int short_split;          // backward: one-tile sequences (<= 16 tokens) are left to attn3_bwd_short_kernel
   const int64_t* one_row;   // [zero_from - full_to] packed row of that token (NULL: the last token; a row outside the
                             // sequence: none -- the sequence produces zeros only)
   float scale;
@@ -1224,6 +1225,7 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias,
   p.zero_from = n_seq - zero_tail;
   p.full_to = one_row_from;
   p.one_row = one_rows;
+  p.short_split = 0;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const int grid = grid_for_warps((dtype == RS_F32 ? n_seq : (p.full_to > 0 ? p.full_to : 1)) * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1240,6 +1242,8 @@ extern "C" int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias,
   }
   return RS_OK;
 }
+
+static const int ATTN_SHORT_SPLIT = [] { const char* e = getenv("RS_ATTN_SHORT_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }();
 
 extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void* out, int dtype, const float* bias,
                                   const float* lse,
@@ -1258,9 +1262,16 @@ extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void
   p.zero_from = n_seq - zero_tail;
   p.full_to = one_row_from;
   p.one_row = one_rows;
+  // one-tile sequences go to their own kernel (16-bit operands, bias already inside qkv)
+  p.short_split = (dtype != RS_F32 && bias == nullptr && ATTN_SHORT_SPLIT) ? 1 : 0;
   drop_consts(dropout_p, p.drop_thresh, p.inv_keep);
   const int grid = grid_for_warps((dtype == RS_F32 ? n_seq : (p.full_to > 0 ? p.full_to : 1)) * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if (p.short_split) {
+    if (dtype == RS_BF16) attn3_bwd_short_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+    else attn3_bwd_short_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+    RS_LAUNCH_CHECK();
+  }
   if (dtype == RS_BF16) attn3_bwd_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
   else if (dtype == RS_F16) attn3_bwd_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
   else if (dtype == RS_F32) attn2_bwd_kernel<RS_F32><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);

@@ -593,3 +593,33 @@ def test_gelu_dropout_mask_law_and_fwd_bwd_agreement(rs):
     assert ((z.grad != 0) == kept).float().mean().item() > 0.999
     f2 = rs.encoder.gelu_dropout(z, p)
     assert not torch.equal(f2 != 0, kept)
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.25])
+def test_attn_one_tile_backward_matches_two_phase_backward(rs, p_drop):
+    """16-bit operands without an in_proj bias: sequences of <= 16 tokens take the one-tile backward kernel (S and dP
+    computed once, P^T / dS^T by movmatrix).  With an all-zero bias the same call takes the two-phase kernel for every
+    sequence: same seed -> same dropout mask -> the two d_qkv must agree to 16-bit rounding, and both must match the
+    fp32 SIMT kernels."""
+    g = torch.Generator().manual_seed(23)
+    lens = [1, 2, 3, 5, 8, 9, 13, 15, 16, 17, 30, 16, 4, 50, 7, 11]
+    H = 4
+    cu = _cu(lens).to(DEV)
+    T = sum(lens)
+    qkv = (torch.randn(T, 3 * H * 32, generator=g) * 0.7).bfloat16().to(DEV)
+    w = torch.randn(T, H * 32, generator=g).bfloat16().to(DEV)
+    zero_bias = torch.zeros(3 * H * 32, device=DEV)
+    scale, seed = 1 / math.sqrt(32), 987654321
+    res = []
+    for bias in (None, zero_bias):
+        out, lse = torch.ops.rs.attn_varlen(qkv, bias, cu, H, 64, 0, scale, p_drop, seed)
+        dq, _ = torch.ops.rs.attn_varlen_bwd(qkv, bias, w, out, lse, cu, H, 64, 0, scale, p_drop, seed)
+        res.append((out, dq))
+    assert torch.equal(res[0][0], res[1][0])
+    a, b = res[0][1].float(), res[1][1].float()
+    assert (a - b).norm() / b.norm() < 5e-3
+    torch.testing.assert_close(a, b, rtol=3e-2, atol=3e-2)
+    if p_drop == 0.0:                                       # (the fp32 kernels draw the same mask only per dtype path)
+        out32, lse32 = torch.ops.rs.attn_varlen(qkv.float(), None, cu, H, 64, 0, scale, 0.0, 0)
+        d32, _ = torch.ops.rs.attn_varlen_bwd(qkv.float(), None, w.float(), out32, lse32, cu, H, 64, 0, scale, 0.0, 0)
+        assert (a - d32).norm() / d32.norm() < 1e-2
