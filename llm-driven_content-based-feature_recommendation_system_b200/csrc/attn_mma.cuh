@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_kernel(const void* __restric
       t0n = __ldg(p.cu + (item + stride) / p.H);
       t1n = __ldg(p.cu + (item + stride) / p.H + 1);
     }
-    if (p.short_split && len <= 16) continue;           // one-tile sequences: attn3_bwd_short_kernel
+    if (p.short_split) continue;                        // (every sequence is served by attn3_bwd_short / _long_kernel)
     uint32_t bq[2][2], bk[2][2], bv[2][2];
     frag_bias<DT>(bq, p.bias, h * ENC_HD, t);
     frag_bias<DT>(bk, p.bias, os_ + h * ENC_HD, t);
@@ -595,5 +595,172 @@ __global__ void __launch_bounds__(256, 2) attn3_bwd_short_kernel(const void* __r
         }
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward, 17..64 tokens
+// The same idea for longer sequences: every (query tile, key tile) pair is visited ONCE (outer loop over key tiles, inner
+// over the query tiles at or behind it): S, dP, P and dS are formed once per pair and feed dQ (dS . K), dV (P^T . dO) and
+// dK (dS^T . Q) right away.  dK / dV of the key tile stay in registers across the inner loop; the dQ contributions of
+// the different key tiles are added up in a per-warp fp32 buffer in shared memory (each lane only ever touches the
+// fragment elements it owns: no synchronisation), and lse / delta of every row are computed during the first key tile
+// and kept in shared memory.  Per pair: 20 mma instead of 28, half the fragment loads, half the exponentials / hashes.
+#define AT3L_DQ_LD 34
+#define AT3L_WARP_BYTES (3 * 16 * AT3_LD * 2 + 64 * AT3L_DQ_LD * 4 + 2 * 64 * 4)
+template <int DT>
+__global__ void __launch_bounds__(256, 2) attn3_bwd_long_kernel(const void* __restrict__ qkv, const void* __restrict__ d_out,
+                                                                const void* __restrict__ out, const float* __restrict__ lse,
+                                                                AttnParams p, void* __restrict__ d_qkv) {
+  extern __shared__ __align__(16) unsigned char at3l_smem[];
+  p.seed = epoch_seed(p.seed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  unsigned char* wbase = at3l_smem + (size_t)warp * AT3L_WARP_BYTES;
+  uint16_t* sK = reinterpret_cast<uint16_t*>(wbase);
+  uint16_t* sQ = sK + 16 * AT3_LD;
+  uint16_t* sG = sQ + 16 * AT3_LD;
+  float* sDq = reinterpret_cast<float*>(sG + 16 * AT3_LD);
+  float* sLse = sDq + 64 * AT3L_DQ_LD;
+  float* sDelta = sLse + 64;
+  const int64_t n_items = p.full_to * p.H;
+  const int64_t rs_ = 3 * (int64_t)p.H * ENC_HD, os_ = (int64_t)p.H * ENC_HD;
+  const uint32_t nob[2][2] = {{0u, 0u}, {0u, 0u}};
+  const uint32_t shi = (uint32_t)(p.seed >> 32);
+  const int64_t stride = (int64_t)gridDim.x * wpc;
+  int64_t item = (int64_t)blockIdx.x * wpc + warp;
+  int64_t t0n = 0, t1n = 0;
+  if (item < n_items) { t0n = __ldg(p.cu + item / p.H); t1n = __ldg(p.cu + item / p.H + 1); }
+  for (; item < n_items; item += stride) {
+    const int h = (int)(item % p.H);
+    const int64_t t0 = t0n;
+    const int len = min((int)(t1n - t0n), p.max_len);
+    if (item + stride < n_items) {
+      t0n = __ldg(p.cu + (item + stride) / p.H);
+      t1n = __ldg(p.cu + (item + stride) / p.H + 1);
+    }
+    if (len <= 16) continue;                            // attn3_bwd_short_kernel
+    const int ntile = (len + 15) >> 4;
+    for (int kt = 0; kt < ntile; ++kt) {
+      const TileRegs kt_ = tile_load<DT>(qkv, t0, kt * 16, len, rs_, os_ + h * ENC_HD, nullptr, lane);
+      uint32_t kb[2][2][2], vb[2][2][2];
+      load_b<DT>(kb, qkv, t0, kt * 16, len, rs_, os_ + h * ENC_HD, nob, false, g, t);
+      load_b<DT>(vb, qkv, t0, kt * 16, len, rs_, 2 * os_ + h * ENC_HD, nob, false, g, t);
+      float dk[4][4], dv[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dk[n][e] = 0.f; dv[n][e] = 0.f; }
+      __syncwarp();                                     // the previous key tile's ldmatrix reads of sK are done
+      tile_store(sK, kt_, lane);
+      for (int qt = kt; qt < ntile; ++qt) {
+        const TileRegs qt_ = tile_load<DT>(qkv, t0, qt * 16, len, rs_, h * ENC_HD, nullptr, lane);
+        const TileRegs gt_ = tile_load<DT>(d_out, t0, qt * 16, len, os_, h * ENC_HD, nullptr, lane);
+        uint32_t qa[2][4], ga[2][4];
+        load_a<DT>(qa, qkv, t0, qt * 16, len, rs_, h * ENC_HD, nob, false, g, t);
+        load_a<DT>(ga, d_out, t0, qt * 16, len, os_, h * ENC_HD, nob, false, g, t);
+        const int i0 = qt * 16 + g;
+        float li[2], di[2];
+        if (kt == 0) {                                  // first visit of this query tile: row statistics
+          uint32_t oa[2][4];
+          load_a<DT>(oa, out, t0, qt * 16, len, os_, h * ENC_HD, nob, false, g, t);
+          float part[2] = {0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack16<DT>(ga[ks][e]), y = unpack16<DT>(oa[ks][e]);
+              part[e & 1] = fmaf(x.x, y.x, fmaf(x.y, y.y, part[e & 1]));
+            }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            di[r] = quad_sum(part[r]);
+            const int i = i0 + 8 * r;
+            li[r] = (i < len) ? __ldg(lse + (t0 + i) * p.H + h) : 0.f;
+            if (t == 0) { sLse[i] = li[r]; sDelta[i] = di[r]; }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) { li[r] = sLse[i0 + 8 * r]; di[r] = sDelta[i0 + 8 * r]; }
+        }
+        float s[2][4], dp[2][4], pk[2][4];
+        mma_abt<DT>(s, qa, kb);
+        mma_abt<DT>(dp, ga, vb);
+        const uint32_t hr[2] = {rnd_row(p.seed, (uint32_t)((t0 + i0) * p.H + h)), rnd_row(p.seed, (uint32_t)((t0 + i0 + 8) * p.H + h))};
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = e >> 1;
+            const int i = i0 + 8 * r, j = kt * 16 + 8 * nt + 2 * t + (e & 1);
+            const float pr = (j <= i && i < len) ? __expf(s[nt][e] * p.scale - li[r]) : 0.f;
+            float d = dp[nt][e], q = pr;
+            if (p.drop_thresh) {
+              const bool keep = rnd_col(shi, hr[r], (uint32_t)j) >= p.drop_thresh;
+              d = keep ? d * p.inv_keep : 0.f;
+              q = keep ? pr * p.inv_keep : 0.f;
+            }
+            pk[nt][e] = q;
+            s[nt][e] = pr * (d - di[r]);
+          }
+        uint32_t pa[4], da[4];
+        c_to_a<DT>(pa, pk);
+        c_to_a<DT>(da, s);
+        __syncwarp();                                   // the previous pair's ldmatrix reads of sQ / sG are done
+        tile_store(sQ, qt_, lane);
+        tile_store(sG, gt_, lane);
+        __syncwarp();
+        {
+          float dq[4][4];
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dq[n][e] = 0.f;
+          mma_a_tile<DT>(dq, da, sK, lane);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float* row = sDq + (i0 + 8 * r) * AT3L_DQ_LD + 2 * t;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              float2 v = make_float2(dq[n][2 * r], dq[n][2 * r + 1]);
+              if (kt > 0) { const float2 o = *reinterpret_cast<const float2*>(row + 8 * n); v.x += o.x; v.y += o.y; }
+              *reinterpret_cast<float2*>(row + 8 * n) = v;
+            }
+          }
+        }
+        const uint32_t paT[4] = {movm_trans(pa[0]), movm_trans(pa[2]), movm_trans(pa[1]), movm_trans(pa[3])};
+        const uint32_t daT[4] = {movm_trans(da[0]), movm_trans(da[2]), movm_trans(da[1]), movm_trans(da[3])};
+        mma_a_tile<DT>(dv, paT, sG, lane);
+        mma_a_tile<DT>(dk, daT, sQ, lane);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int j = kt * 16 + g + 8 * r;
+        if (j < len) {
+          uint16_t* row = reinterpret_cast<uint16_t*>(d_qkv) + (t0 + j) * rs_ + h * ENC_HD + 2 * t;
+          uint32_t* dkp = reinterpret_cast<uint32_t*>(row + os_);
+          uint32_t* dvp = reinterpret_cast<uint32_t*>(row + 2 * os_);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            dkp[4 * n] = pack16<DT>(dk[n][2 * r] * p.scale, dk[n][2 * r + 1] * p.scale);
+            dvp[4 * n] = pack16<DT>(dv[n][2 * r], dv[n][2 * r + 1]);
+          }
+        }
+      }
+    }
+    // dQ: every lane writes back the fragment elements it accumulated (its own addresses: program order suffices)
+    for (int qt = 0; qt < ntile; ++qt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = qt * 16 + g + 8 * r;
+        if (i < len) {
+          const float* row = sDq + i * AT3L_DQ_LD + 2 * t;
+          uint32_t* dqp = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(d_qkv) + (t0 + i) * rs_ + h * ENC_HD + 2 * t);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float2 v = *reinterpret_cast<const float2*>(row + 8 * n);
+            dqp[4 * n] = pack16<DT>(v.x * p.scale, v.y * p.scale);
+          }
+        }
+      }
   }
 }

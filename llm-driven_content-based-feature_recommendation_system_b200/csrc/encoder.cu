@@ -1268,9 +1268,21 @@ extern "C" int rs_attn_varlen_bwd(const void* qkv, const void* d_out, const void
   const int grid = grid_for_warps((dtype == RS_F32 ? n_seq : (p.full_to > 0 ? p.full_to : 1)) * n_heads, 8, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (p.short_split) {
-    if (dtype == RS_BF16) attn3_bwd_short_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
-    else attn3_bwd_short_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
-    RS_LAUNCH_CHECK();
+    // once-per-pair kernels: <= 16 tokens (one tile, registers only) and 17..64 tokens (dQ summed in shared memory); the
+    // two-phase kernel below then only clears the zero tail
+    const int smem_long = 8 * AT3L_WARP_BYTES;
+    if (dtype == RS_BF16) {
+      attn3_bwd_short_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+      cudaError_t e = cudaFuncSetAttribute(attn3_bwd_long_kernel<RS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_long);
+      if (e != cudaSuccess) return (int)e;
+      attn3_bwd_long_kernel<RS_BF16><<<grid, 256, smem_long, st>>>(qkv, d_out, out, lse, p, d_qkv);
+    } else {
+      attn3_bwd_short_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
+      cudaError_t e = cudaFuncSetAttribute(attn3_bwd_long_kernel<RS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_long);
+      if (e != cudaSuccess) return (int)e;
+      attn3_bwd_long_kernel<RS_F16><<<grid, 256, smem_long, st>>>(qkv, d_out, out, lse, p, d_qkv);
+    }
+    RS_LAUNCH_CHECK_N(2);
   }
   if (dtype == RS_BF16) attn3_bwd_kernel<RS_BF16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
   else if (dtype == RS_F16) attn3_bwd_kernel<RS_F16><<<grid, 256, 0, st>>>(qkv, d_out, out, lse, p, d_qkv);
