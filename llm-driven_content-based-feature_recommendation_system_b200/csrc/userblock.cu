@@ -369,6 +369,51 @@ __device__ __forceinline__ void ubm_logits(float (&s)[8][4], const UbParams& p, 
   }
 }
 
+// label logit and same-user log-sum-exp of the 16 rows of tile `rt` (one warp)
+template <int DT>
+__device__ __forceinline__ void ubm_fwd_rows(const UbParams& p, int64_t r0, int len, int LT, int rt, const uint16_t* sU,
+                                             const uint16_t* sC, const float* sBias, const int* sCol, int lane,
+                                             float* __restrict__ s_pos, float* __restrict__ own_lse) {
+  const int g = lane >> 2, t = lane & 3;
+    float s[8][4];
+    ubm_logits<DT>(s, p, rt, LT, sU, sC, sBias, lane);
+    const int i0 = rt * 16 + g, i1 = i0 + 8;
+    const int ci[2] = {sCol[i0], sCol[i1]};
+    float m[2] = {-INFINITY, -INFINITY}, sp[2] = {0.f, 0.f};
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct)
+      if (ct * 8 < LT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
+          const int cj = sCol[j];
+          if (j == (r ? i1 : i0)) sp[r] = s[ct][e];
+          if (cj >= 0 && cj != ci[r]) m[r] = fmaxf(m[r], s[ct][e]);
+        }
+      }
+    m[0] = ubm_quad_max(m[0]); m[1] = ubm_quad_max(m[1]);
+    float l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct)
+      if (ct * 8 < LT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
+          const int cj = sCol[j];
+          if (cj >= 0 && cj != ci[r] && m[r] > -INFINITY) l[r] += __expf(s[ct][e] - m[r]);
+        }
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float lt = ubm_quad_sum(l[r]), spv = ubm_quad_sum(sp[r]);
+      const int i = r ? i1 : i0;
+      if (t == 0 && i < len) {
+        s_pos[r0 + i] = ci[r] >= 0 ? spv : -INFINITY;
+        own_lse[r0 + i] = m[r] > -INFINITY ? m[r] + __logf(lt) : -INFINITY;
+      }
+    }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(UB_THREADS) ub_fwd_mma_kernel(UbParams p, int ML16, float* __restrict__ s_pos,
                                                                 float* __restrict__ own_lse) {
@@ -377,7 +422,7 @@ __global__ void __launch_bounds__(UB_THREADS) ub_fwd_mma_kernel(UbParams p, int 
   uint16_t* sC = sU + ML16 * UBM_LD;
   float* sBias = reinterpret_cast<float*>(sC + ML16 * UBM_LD);
   int* sCol = reinterpret_cast<int*>(sBias + ML16);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
     const int64_t r0 = __ldg(p.row_cu + b);
     const int true_len = (int)(__ldg(p.row_cu + b + 1) - r0);
@@ -390,45 +435,7 @@ __global__ void __launch_bounds__(UB_THREADS) ub_fwd_mma_kernel(UbParams p, int 
     const int LT = (len + 15) & ~15;
     __syncthreads();
     ubm_stage(p, r0, len, LT, sU, sC, sCol, sBias);
-    if (w * 16 < len) {
-      float s[8][4];
-      ubm_logits<DT>(s, p, w, LT, sU, sC, sBias, lane);
-      const int i0 = w * 16 + g, i1 = i0 + 8;
-      const int ci[2] = {sCol[i0], sCol[i1]};
-      float m[2] = {-INFINITY, -INFINITY}, sp[2] = {0.f, 0.f};
-#pragma unroll
-      for (int ct = 0; ct < 8; ++ct)
-        if (ct * 8 < LT) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
-            const int cj = sCol[j];
-            if (j == (r ? i1 : i0)) sp[r] = s[ct][e];
-            if (cj >= 0 && cj != ci[r]) m[r] = fmaxf(m[r], s[ct][e]);
-          }
-        }
-      m[0] = ubm_quad_max(m[0]); m[1] = ubm_quad_max(m[1]);
-      float l[2] = {0.f, 0.f};
-#pragma unroll
-      for (int ct = 0; ct < 8; ++ct)
-        if (ct * 8 < LT) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
-            const int cj = sCol[j];
-            if (cj >= 0 && cj != ci[r] && m[r] > -INFINITY) l[r] += __expf(s[ct][e] - m[r]);
-          }
-        }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float lt = ubm_quad_sum(l[r]), spv = ubm_quad_sum(sp[r]);
-        const int i = r ? i1 : i0;
-        if (t == 0 && i < len) {
-          s_pos[r0 + i] = ci[r] >= 0 ? spv : -INFINITY;
-          own_lse[r0 + i] = m[r] > -INFINITY ? m[r] + __logf(lt) : -INFINITY;
-        }
-      }
-    }
+    if (w * 16 < len) ubm_fwd_rows<DT>(p, r0, len, LT, w, sU, sC, sBias, sCol, lane, s_pos, own_lse);
   }
 }
 
@@ -448,6 +455,103 @@ __device__ __forceinline__ void ubm_mma_tile(float (&acc)[4][4], const uint32_t 
   }
 }
 
+// gradient coefficients of the 16 rows of tile `rt` (one warp) -> sH / sL (16-bit head + remainder)
+template <int DT>
+__device__ __forceinline__ void ubm_bwd_coef(const UbParams& p, int64_t r0, int len, int LT, int rt, const uint16_t* sU,
+                                             const uint16_t* sC, uint16_t* sH, uint16_t* sL, const float* sBias,
+                                             const int* sCol, int lane, const float* __restrict__ own_lse,
+                                             const float* __restrict__ g_pos, const float* __restrict__ g_own) {
+  const int g = lane >> 2, t = lane & 3;
+    float s[8][4];
+    ubm_logits<DT>(s, p, rt, LT, sU, sC, sBias, lane);
+    const int i0 = rt * 16 + g, i1 = i0 + 8;
+    const int ci[2] = {sCol[i0], sCol[i1]};
+    float gp[2] = {0.f, 0.f}, go[2] = {0.f, 0.f}, ol[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = r ? i1 : i0;
+      if (i < len && ci[r] >= 0) { gp[r] = __ldg(g_pos + r0 + i); go[r] = __ldg(g_own + r0 + i); ol[r] = __ldg(own_lse + r0 + i); }
+    }
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct)
+      if (ct * 8 < LT) {
+        float c[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
+          const int i = r ? i1 : i0;
+          const int cj = sCol[j];
+          float v = 0.f;
+          if (ci[r] >= 0 && cj >= 0) {
+            if (i == j) v = gp[r];
+            else if (cj != ci[r] && ol[r] > -INFINITY) v = go[r] * __expf(s[ct][e] - ol[r]);
+          }
+          c[e] = v * p.scale;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int i = r ? i1 : i0;
+          const uint16_t h0 = ubm_to16<DT>(c[2 * r]), h1 = ubm_to16<DT>(c[2 * r + 1]);
+          const uint16_t l0 = ubm_to16<DT>(c[2 * r] - ubm_from16<DT>(h0)), l1 = ubm_to16<DT>(c[2 * r + 1] - ubm_from16<DT>(h1));
+          *reinterpret_cast<uint32_t*>(sH + i * UBM_CLD + ct * 8 + 2 * t) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          *reinterpret_cast<uint32_t*>(sL + i * UBM_CLD + ct * 8 + 2 * t) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+      }
+}
+
+// d_u rows of tile `rt` and the d_cols contributions of the items of tile `rt` (one warp; the coefficient planes of ALL
+// tiles must be complete)
+template <int DT>
+__device__ __forceinline__ void ubm_bwd_products(const UbParams& p, int64_t r0, int len, int LT, int rt, const uint16_t* sU,
+                                                 const uint16_t* sC, const uint16_t* sH, const uint16_t* sL,
+                                                 const int* sCol, int lane, float* __restrict__ d_u,
+                                                 float* __restrict__ d_cols) {
+  const int g = lane >> 2, t = lane & 3;
+    // ---- d_u rows of tile rt:  sum_j coef[i][j] c_j      A = coef[16 i][16 j] (row-major), B = sC rows j (trans)
+    const uint16_t* abase = (rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * UBM_CLD + (lane >> 4) * 8 + sH;
+    const int i0 = rt * 16 + g, i1 = i0 + 8;
+#pragma unroll 1
+    for (int fg = 0; fg < 4; ++fg) {
+      float acc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      for (int kt = 0; kt * 16 < LT; ++kt) {
+        uint32_t ah[4], al[4];
+        ubm_ldsm4(ah, abase + kt * 16);
+        ubm_ldsm4(al, abase + kt * 16 + (sL - sH));
+        ubm_mma_tile<DT>(acc, ah, al, sC + kt * 16 * UBM_LD + fg * 32, lane);
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int f = fg * 32 + 8 * n + 2 * t;
+        if (i0 < len) *reinterpret_cast<float2*>(d_u + (r0 + i0) * UB_D + f) = make_float2(acc[n][0], acc[n][1]);
+        if (i1 < len) *reinterpret_cast<float2*>(d_u + (r0 + i1) * UB_D + f) = make_float2(acc[n][2], acc[n][3]);
+      }
+    }
+    // ---- d_cols rows of the items j of tile rt:  sum_i coef[i][j] u_i      A = coef^T (ldmatrix.trans), B = sU rows i
+    const int j0 = rt * 16 + g, j1 = j0 + 8;
+    const int cj0 = sCol[j0], cj1 = sCol[j1];
+    const uint16_t* tbase = sH + ((lane & 7) + (lane >> 4) * 8) * UBM_CLD + rt * 16 + ((lane >> 3) & 1) * 8;
+#pragma unroll 1
+    for (int fg = 0; fg < 4; ++fg) {
+      float acc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      for (int it = 0; it * 16 < LT; ++it) {
+        uint32_t ah[4], al[4];
+        ubm_ldsm4_trans(ah, tbase + it * 16 * UBM_CLD);
+        ubm_ldsm4_trans(al, tbase + it * 16 * UBM_CLD + (sL - sH));
+        ubm_mma_tile<DT>(acc, ah, al, sU + it * 16 * UBM_LD + fg * 32, lane);
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int f = fg * 32 + 8 * n + 2 * t;
+        if (cj0 >= 0) red_add_f2(d_cols + (int64_t)cj0 * UB_D + f, acc[n][0], acc[n][1]);
+        if (cj1 >= 0) red_add_f2(d_cols + (int64_t)cj1 * UB_D + f, acc[n][2], acc[n][3]);
+      }
+    }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(UB_THREADS) ub_bwd_mma_kernel(UbParams p, int ML16, const float* __restrict__ own_lse,
                                                                 const float* __restrict__ g_pos,
@@ -460,100 +564,24 @@ __global__ void __launch_bounds__(UB_THREADS) ub_bwd_mma_kernel(UbParams p, int 
   uint16_t* sL = sH + ML16 * UBM_CLD;                   // coefficient remainders
   float* sBias = reinterpret_cast<float*>(sL + ML16 * UBM_CLD);
   int* sCol = reinterpret_cast<int*>(sBias + ML16);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int64_t b = blockIdx.x; b < p.n_users; b += gridDim.x) {
     const int64_t r0 = __ldg(p.row_cu + b);
-    const int len = min((int)(__ldg(p.row_cu + b + 1) - r0), p.max_len);
+    const int true_len = (int)(__ldg(p.row_cu + b + 1) - r0);
+    const int len = min(true_len, p.max_len);
     if (len <= 0) continue;
     const int LT = (len + 15) & ~15;
     __syncthreads();
     ubm_stage(p, r0, len, LT, sU, sC, sCol, sBias);
-    if (w * 16 < LT) {
-      float s[8][4];
-      ubm_logits<DT>(s, p, w, LT, sU, sC, sBias, lane);
-      const int i0 = w * 16 + g, i1 = i0 + 8;
-      const int ci[2] = {sCol[i0], sCol[i1]};
-      float gp[2] = {0.f, 0.f}, go[2] = {0.f, 0.f}, ol[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i = r ? i1 : i0;
-        if (i < len && ci[r] >= 0) { gp[r] = __ldg(g_pos + r0 + i); go[r] = __ldg(g_own + r0 + i); ol[r] = __ldg(own_lse + r0 + i); }
-      }
-#pragma unroll
-      for (int ct = 0; ct < 8; ++ct)
-        if (ct * 8 < LT) {
-          float c[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = ct * 8 + 2 * t + (e & 1), r = e >> 1;
-            const int i = r ? i1 : i0;
-            const int cj = sCol[j];
-            float v = 0.f;
-            if (ci[r] >= 0 && cj >= 0) {
-              if (i == j) v = gp[r];
-              else if (cj != ci[r] && ol[r] > -INFINITY) v = go[r] * __expf(s[ct][e] - ol[r]);
-            }
-            c[e] = v * p.scale;
-          }
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int i = r ? i1 : i0;
-            const uint16_t h0 = ubm_to16<DT>(c[2 * r]), h1 = ubm_to16<DT>(c[2 * r + 1]);
-            const uint16_t l0 = ubm_to16<DT>(c[2 * r] - ubm_from16<DT>(h0)), l1 = ubm_to16<DT>(c[2 * r + 1] - ubm_from16<DT>(h1));
-            *reinterpret_cast<uint32_t*>(sH + i * UBM_CLD + ct * 8 + 2 * t) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            *reinterpret_cast<uint32_t*>(sL + i * UBM_CLD + ct * 8 + 2 * t) = (uint32_t)l0 | ((uint32_t)l1 << 16);
-          }
-        }
-    }
+    if (w * 16 < LT) ubm_bwd_coef<DT>(p, r0, len, LT, w, sU, sC, sH, sL, sBias, sCol, lane, own_lse, g_pos, g_own);
     __syncthreads();
-    if (w * 16 < LT) {
-      // ---- d_u rows of tile w:  sum_j coef[i][j] c_j      A = coef[16 i][16 j] (row-major), B = sC rows j (trans)
-      const uint16_t* abase = (w * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * UBM_CLD + (lane >> 4) * 8 + sH;
-      const int i0 = w * 16 + g, i1 = i0 + 8;
-#pragma unroll 1
-      for (int fg = 0; fg < 4; ++fg) {
-        float acc[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-        for (int kt = 0; kt * 16 < LT; ++kt) {
-          uint32_t ah[4], al[4];
-          ubm_ldsm4(ah, abase + kt * 16);
-          ubm_ldsm4(al, abase + kt * 16 + (sL - sH));
-          ubm_mma_tile<DT>(acc, ah, al, sC + kt * 16 * UBM_LD + fg * 32, lane);
-        }
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int f = fg * 32 + 8 * n + 2 * t;
-          if (i0 < len) *reinterpret_cast<float2*>(d_u + (r0 + i0) * UB_D + f) = make_float2(acc[n][0], acc[n][1]);
-          if (i1 < len) *reinterpret_cast<float2*>(d_u + (r0 + i1) * UB_D + f) = make_float2(acc[n][2], acc[n][3]);
-        }
-      }
-      // ---- d_cols rows of the items j of tile w:  sum_i coef[i][j] u_i      A = coef^T (ldmatrix.trans), B = sU rows i
-      const int j0 = w * 16 + g, j1 = j0 + 8;
-      const int cj0 = sCol[j0], cj1 = sCol[j1];
-      const uint16_t* tbase = sH + ((lane & 7) + (lane >> 4) * 8) * UBM_CLD + w * 16 + ((lane >> 3) & 1) * 8;
-#pragma unroll 1
-      for (int fg = 0; fg < 4; ++fg) {
-        float acc[4][4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-        for (int it = 0; it * 16 < LT; ++it) {
-          uint32_t ah[4], al[4];
-          ubm_ldsm4_trans(ah, tbase + it * 16 * UBM_CLD);
-          ubm_ldsm4_trans(al, tbase + it * 16 * UBM_CLD + (sL - sH));
-          ubm_mma_tile<DT>(acc, ah, al, sU + it * 16 * UBM_LD + fg * 32, lane);
-        }
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int f = fg * 32 + 8 * n + 2 * t;
-          if (cj0 >= 0) red_add_f2(d_cols + (int64_t)cj0 * UB_D + f, acc[n][0], acc[n][1]);
-          if (cj1 >= 0) red_add_f2(d_cols + (int64_t)cj1 * UB_D + f, acc[n][2], acc[n][3]);
-        }
-      }
-    }
+    if (w * 16 < LT) ubm_bwd_products<DT>(p, r0, len, LT, w, sU, sC, sH, sL, sCol, lane, d_u, d_cols);
   }
 }
 
+// (A warp-per-user variant for users with <= 16 rows -- four independent users per CTA, no block barriers -- was measured
+// and dropped: tools/ub_probe.py, backward 156 -> 165 us.  The kernels are bound by the row gathers and the item-gradient
+// reductions, not by the barriers.)
 }  // namespace rs
 
 using namespace rs;
