@@ -661,7 +661,12 @@ def run_bucketed(args, rs, dev, rank, world):
                                         f"{', columns % ' + str(args.col_bucket) if world == 1 else ''}): {n_graphs} "
                                         f"graphs, buckets of the timed steps {buckets}"
                                         if use_graph else "off (eager launches)"),
-                            l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), fresh batch per step"),
+                            l2="inputs larger than L2 (tables 2x54 MB + >2 GB activations per step), fresh batch per step",
+                            full_step="forward of both dropout views, main loss on every valid step + DuoRec, backward, "
+                                      "gradient clip, fused AdamW on both towers (dense table gradients) -- nothing the "
+                                      "reference step computes and a loss reads is skipped; the second dropout view's "
+                                      "last-layer rows that feed no loss are not computed (exact: DESIGN 3.7-3.8, "
+                                      "tests/test_gpu_batch_index.py::test_step_on_device_index_matches_step_on_host_index)"),
                 e2e=e2e, gpu_launches=int(launches), host_enqueue_ms_per_step=host_ms, clocks=clk.summary(),
                 roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=gpu_eager, loader=loader, kernels=kernels, extra=extra,
                 loss=dict(total=total, main=main, cl=cl), host_batch_generation_s=round(gen_s, 1))
