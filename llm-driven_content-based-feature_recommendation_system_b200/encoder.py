@@ -767,16 +767,26 @@ class _LinearColsumBias(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.xdt, ctx.wdt = x.dtype, weight.dtype
-        if x.shape[-1] % 8:
+        ctx.k = x.shape[-1]
+        ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
+        if x.shape[-1] % 8 and ad in (torch.bfloat16, torch.float16):
             # a 16-bit operand whose rows are not 16-byte aligned (static_mlp's Linear(100 -> 128)) sends the library to
-            # an sm_80 `align2` GEMM (profiles/r01e_launches.md); the layer is tiny: run it in fp32 (>= the reference's
-            # fp16 autocast precision), whose 400-byte rows are aligned
+            # an sm_80 `align2` GEMM, and the fp32 detour of round 1 to an sm_80 SIMT sgemm (profiles/r01e_launches.md,
+            # r02h_launches.md: 0.05 ms for a 0.4 GFLOP weight gradient).  Zero-pad the contraction dimension to a multiple
+            # of 8 instead (100 -> 104: a 3 MB copy): all three GEMMs of the layer run on the tensor cores, same values.
+            kp = (x.shape[-1] + 7) // 8 * 8
+            lead = x.shape[:-1]
+            x = F.pad(x.reshape(-1, x.shape[-1]).to(ad), (0, kp - ctx.k))
+            weight = F.pad(_w16(weight, ad), (0, kp - ctx.k))
+            with torch.autocast("cuda", enabled=False):
+                y = F.linear(x, weight, _w16(bias, ad)).view(*lead, weight.shape[0])
+        elif x.shape[-1] % 8:
             with torch.autocast("cuda", enabled=False):
                 x = x.float()
                 y = F.linear(x, weight.float(), bias.float())
         else:
-            if torch.is_autocast_enabled("cuda"):
-                x = x.to(torch.get_autocast_dtype("cuda"))   # the cast autocast applies; kept for the backward (one cast, not two)
+            if ad is not None:
+                x = x.to(ad)                                 # the cast autocast applies; kept for the backward (one cast, not two)
             weight = _w16(weight, x.dtype)                   # the step's prepared 16-bit copies (no per-use cast kernels)
             with torch.autocast("cuda", enabled=False):
                 y = F.linear(x, weight, _w16(bias, x.dtype))
@@ -787,13 +797,15 @@ class _LinearColsumBias(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
+        k = ctx.k
         g2 = g.reshape(-1, g.shape[-1])
         x2 = x.reshape(-1, x.shape[-1]).to(g2.dtype)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = (g2 @ weight.to(g2.dtype)).view(x.shape).to(ctx.xdt)
+            dx = (g2 @ weight.to(g2.dtype))[:, :k]
+            dx = dx.reshape(*g.shape[:-1], k).to(ctx.xdt)
         if ctx.needs_input_grad[1]:
-            dw = _mm32(g2.t(), x2).to(ctx.wdt)
+            dw = _mm32(g2.t(), x2)[:, :k].to(ctx.wdt)
         db = _colsum(g2).to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 
