@@ -189,3 +189,15 @@ def test_flat_batch_and_buckets_host_logic(rs):
     assert tr.bucket_of(100, 70, 64, 32) == (128, 96)
     bs = tr.BucketedStep(lambda b_: None, 16, 50, 501, "cpu", use_graph=False, tok_q=256, col_q=64)
     assert bs.bucket(300, 70) == (512, 128) and bs.bucket(300, None) == (512, 512)
+
+
+def test_zeros_many_is_one_allocation_of_aligned_views(rs):
+    shapes = [(3, 4), (1001, 128), (6,), (11, 16)]
+    outs = rs.ops.zeros_many(shapes, "cpu")
+    assert [tuple(o.shape) for o in outs] == shapes
+    base = outs[0].untyped_storage().data_ptr()
+    for o in outs:
+        assert o.is_contiguous() and (o == 0).all() and o.untyped_storage().data_ptr() == base
+        assert (o.data_ptr() - base) % 256 == 0
+    outs[1][5, 7] = 1.0                                   # views do not overlap
+    assert all((o == 0).all() for k, o in enumerate(outs) if k != 1)

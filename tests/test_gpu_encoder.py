@@ -404,7 +404,7 @@ def test_sequential_fuses_ln_gelu_dropout_like_the_stock_modules(rs):
     torch.testing.assert_close(xg.grad, xr.grad, rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_fused_head_matches_concat_linear_ln_gelu(rs, dtype):
     """encoder.fused_head (split Linear(256 -> 128), no concatenation, LN + GELU in one pass) against the stock modules in
     fp32 on cat([rows, prof[users]]): values and every gradient (rows, profile rows, Linear weight / bias, LN gamma /
@@ -595,8 +595,9 @@ def test_gelu_dropout_mask_law_and_fwd_bwd_agreement(rs):
     assert not torch.equal(f2 != 0, kept)
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("p_drop", [0.0, 0.25])
-def test_attn_one_tile_backward_matches_two_phase_backward(rs, p_drop):
+def test_attn_one_tile_backward_matches_two_phase_backward(rs, p_drop, dt):
     """16-bit operands without an in_proj bias: sequences of <= 16 tokens take the one-tile backward kernel (S and dP
     computed once, P^T / dS^T by movmatrix).  With an all-zero bias the same call takes the two-phase kernel for every
     sequence: same seed -> same dropout mask -> the two d_qkv must agree to 16-bit rounding, and both must match the
@@ -606,8 +607,8 @@ def test_attn_one_tile_backward_matches_two_phase_backward(rs, p_drop):
     H = 4
     cu = _cu(lens).to(DEV)
     T = sum(lens)
-    qkv = (torch.randn(T, 3 * H * 32, generator=g) * 0.7).bfloat16().to(DEV)
-    w = torch.randn(T, H * 32, generator=g).bfloat16().to(DEV)
+    qkv = (torch.randn(T, 3 * H * 32, generator=g) * 0.7).to(dt).to(DEV)
+    w = torch.randn(T, H * 32, generator=g).to(dt).to(DEV)
     zero_bias = torch.zeros(3 * H * 32, device=DEV)
     scale, seed = 1 / math.sqrt(32), 987654321
     res = []
