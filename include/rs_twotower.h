@@ -249,6 +249,21 @@ int rs_gelu_dropout_fwd(const void* z, int dtype, const float* bias, int64_t n_c
                         uint64_t seed, void* out, void* stream);
 int rs_gelu_dropout_bwd(const void* z, const void* g, int dtype, const float* bias, int64_t n_cols, int64_t n,
                         float dropout_p, uint64_t seed, void* dz, void* stream);
+/* The encoder's input x0 = dropout(LayerNorm_emb(e[index])) (tower_code/v1_refine_usertower.py:458-459) and the first
+ * layer's h = LayerNorm_1(x0) in one pass over the packed rows (x0 fp32, h in the GEMM operand dtype; both LayerNorms'
+ * statistics saved).  Backward, one warp per SOURCE row u of e (every u is read by exactly the two packed rows inv1[u],
+ * inv2[u] -- the two dropout views, rs_batch_index_build): d e[u] = LN_emb'( mask(residual_grad + LN_1'(dh))[inv1[u]] +
+ * the same at inv2[u] ), the four parameter gradients reduced in a fixed order.  dim == 128. */
+int rs_emb_ln2_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, int64_t dim, const float* w0,
+                   const float* b0, float eps0, float dropout_p, uint64_t seed, const float* w1, const float* b1,
+                   float eps1, float* x0, void* h, int h_dtype, float* mean0, float* rstd0, float* mean1, float* rstd1,
+                   void* stream);
+size_t rs_emb_ln2_bwd_workspace_bytes(int64_t n_src);
+int rs_emb_ln2_bwd(const void* dh, int dh_dtype, const void* x, int x_dtype, const float* x0, const float* residual_grad,
+                   const int64_t* inv1, const int64_t* inv2, int64_t n_src, int64_t dim, const float* w0, const float* w1,
+                   const float* mean0, const float* rstd0, const float* mean1, const float* rstd1, float dropout_p,
+                   uint64_t seed, void* dx, float* dw0, float* db0, float* dw1, float* db1, void* workspace,
+                   size_t workspace_bytes, void* stream);
 /* A pre-norm block ends with x1 = x + dropout(y + lin_bias) and the next one starts with h = LayerNorm(x1)
  * (nn.TransformerEncoderLayer, norm_first=True; tower_code/v1_refine_usertower.py:343-352): both in one pass (x, x1 fp32
  * residual stream; y the GEMM output; h in the next GEMM's operand dtype; mean/rstd saved), and one backward pass:

@@ -84,6 +84,10 @@ PROTOTYPES = {
     "rs_dropout_bwd": (i32, [vp, i32, i64, f32, u64, vp, i32, vp]),
     "rs_gelu_dropout_fwd": (i32, [vp, i32, vp, i64, i64, f32, u64, vp, vp]),
     "rs_gelu_dropout_bwd": (i32, [vp, vp, i32, vp, i64, i64, f32, u64, vp, vp]),
+    "rs_emb_ln2_fwd": (i32, [vp, i32, vp, i64, i64, vp, vp, f32, f32, u64, vp, vp, f32, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "rs_emb_ln2_bwd_workspace_bytes": (sz, [i64]),
+    "rs_emb_ln2_bwd": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, f32, u64, vp, vp, vp, vp, vp,
+                             vp, sz, vp]),
     "rs_dropout_add_ln_fwd": (i32, [vp, vp, i32, vp, i64, i64, f32, u64, vp, vp, f32, vp, vp, i32, vp, vp, vp]),
     "rs_ln_bwd_dropout_workspace_bytes": (sz, [i64]),
     "rs_ln_bwd_dropout": (i32, [vp, i32, vp, vp, i64, i64, vp, vp, vp, f32, u64, vp, vp, i32, vp, vp, vp, vp, sz, vp]),

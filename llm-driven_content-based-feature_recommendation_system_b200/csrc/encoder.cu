@@ -769,13 +769,14 @@ __global__ void __launch_bounds__(PS_WARPS * 32) partial_sum_kernel(const float*
   }
 }
 
-// the same fold for [n_blocks][3][128] partials -> three 128-vectors
-__global__ void __launch_bounds__(PS_WARPS * 32) partial_sum3_kernel(const float* __restrict__ part, int n_blocks,
+// the same fold for [n_blocks][NV][128] partials -> NV 128-vectors (NV = 3 or 4)
+template <int NV>
+__global__ void __launch_bounds__(PS_WARPS * 32) partial_sumv_kernel(const float* __restrict__ part, int n_blocks,
                                                                      float* __restrict__ out0, float* __restrict__ out1,
-                                                                     float* __restrict__ out2) {
+                                                                     float* __restrict__ out2, float* __restrict__ out3) {
   __shared__ float red[PS_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;                 // < 384
+  const int c = blockIdx.x * 32 + lane;                 // < NV * 128
   float s[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) s[q] = 0.f;
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32) partial_sum3_kernel(const float
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int bb = b + PS_WARPS * q;
-      if (bb < n_blocks) s[q] += part[(int64_t)bb * (3 * ENC_D) + c];
+      if (bb < n_blocks) s[q] += part[(int64_t)bb * (NV * ENC_D) + c];
     }
   }
   red[w][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
@@ -793,7 +794,8 @@ __global__ void __launch_bounds__(PS_WARPS * 32) partial_sum3_kernel(const float
 #pragma unroll
     for (int k = 0; k < PS_WARPS; k += 4) { t[0] += red[k][lane]; t[1] += red[k + 1][lane]; t[2] += red[k + 2][lane]; t[3] += red[k + 3][lane]; }
     const float r = (t[0] + t[1]) + (t[2] + t[3]);
-    if (c < ENC_D) out0[c] = r; else if (c < 2 * ENC_D) out1[c - ENC_D] = r; else out2[c - 2 * ENC_D] = r;
+    float* const outs[4] = {out0, out1, out2, out3};
+    outs[c / ENC_D][c % ENC_D] = r;
   }
 }
 
@@ -1139,6 +1141,125 @@ __global__ void __launch_bounds__(256) ln_bwd_dropout_kernel(const void* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ embedding LN + first LN
+// The encoder's input is x0 = dropout(LayerNorm_emb(e[index])) and its first layer starts with h = LayerNorm_1(x0)
+// (v1_refine_usertower.py:458-459 + the pre-norm layer): one pass over the packed rows instead of two.  In the backward
+// every source row u is read by exactly two packed rows (inv1[u], inv2[u]: the two dropout views), and LayerNorm_emb's
+// backward is linear in its incoming gradient: the two views' gradients are masked, added and pushed through it ONCE per
+// source row -- half the work of the per-packed-row backward and no separate fold pass.
+template <int DTI, int DTO>
+__global__ void __launch_bounds__(256) emb_ln2_fwd_kernel(const void* __restrict__ x, const int64_t* __restrict__ index,
+                                                          int64_t n_rows, const float* __restrict__ w0,
+                                                          const float* __restrict__ b0, float eps0, uint32_t drop_thresh,
+                                                          float inv_keep, uint64_t seed, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, float eps1, float* __restrict__ x0,
+                                                          void* __restrict__ h, float* __restrict__ mean0,
+                                                          float* __restrict__ rstd0, float* __restrict__ mean1,
+                                                          float* __restrict__ rstd1) {
+  seed = epoch_seed(seed);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 wa = ldg_f4(w0 + 4 * lane), ba = ldg_f4(b0 + 4 * lane);
+  const float4 wb = ldg_f4(w1 + 4 * lane), bb = ldg_f4(b1 + 4 * lane);
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const int64_t src = __ldg(index + r);
+    const float4 v = ld4<DTI>(x, src * ENC_D + 4 * lane);
+    const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / ENC_D);
+    const float4 c = make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu);
+    const float rs = rsqrtf(warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / ENC_D) + eps0);
+    float4 o = make_float4(c.x * rs * wa.x + ba.x, c.y * rs * wa.y + ba.y, c.z * rs * wa.z + ba.z, c.w * rs * wa.w + ba.w);
+    if (drop_thresh) {
+      const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+      o.x = (rnd32(seed, e, 0x5bd1e995u) >= drop_thresh) ? o.x * inv_keep : 0.f;
+      o.y = (rnd32(seed, e, 1u) >= drop_thresh) ? o.y * inv_keep : 0.f;
+      o.z = (rnd32(seed, e, 2u) >= drop_thresh) ? o.z * inv_keep : 0.f;
+      o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
+    }
+    *reinterpret_cast<float4*>(x0 + r * ENC_D + 4 * lane) = o;
+    const float mu1 = warp_sum(o.x + o.y + o.z + o.w) * (1.f / ENC_D);
+    const float4 d = make_float4(o.x - mu1, o.y - mu1, o.z - mu1, o.w - mu1);
+    const float rs1 = rsqrtf(warp_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w) * (1.f / ENC_D) + eps1);
+    st4<DTO>(h, r * ENC_D + 4 * lane,
+             make_float4(d.x * rs1 * wb.x + bb.x, d.y * rs1 * wb.y + bb.y, d.z * rs1 * wb.z + bb.z, d.w * rs1 * wb.w + bb.w));
+    if (lane == 0) { mean0[r] = mu; rstd0[r] = rs; mean1[r] = mu1; rstd1[r] = rs1; }
+  }
+}
+
+// one warp per SOURCE row u: the gradients of its two packed copies -> d e[u]; partials [grid][4][128] = d gamma_1,
+// d beta_1, d gamma_emb, d beta_emb
+template <int DTI, int DTO>
+__global__ void __launch_bounds__(256) emb_ln2_bwd_kernel(const void* __restrict__ dh, const void* __restrict__ x,
+                                                          const float* __restrict__ x0, const float* __restrict__ res,
+                                                          const int64_t* __restrict__ inv1, const int64_t* __restrict__ inv2,
+                                                          int64_t n_src, const float* __restrict__ w0,
+                                                          const float* __restrict__ w1, const float* __restrict__ mean0,
+                                                          const float* __restrict__ rstd0, const float* __restrict__ mean1,
+                                                          const float* __restrict__ rstd1, uint32_t drop_thresh,
+                                                          float inv_keep, uint64_t seed, void* __restrict__ dx,
+                                                          float* __restrict__ part) {
+  __shared__ float4 red[4][8][32];
+  seed = epoch_seed(seed);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 wa = ldg_f4(w0 + 4 * lane), wb = ldg_f4(w1 + 4 * lane);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw1 = z4, db1 = z4, dw0 = z4, db0 = z4;
+  for (int64_t u = warp; u < n_src; u += nw) {
+    const int64_t rr[2] = {__ldg(inv1 + u), __ldg(inv2 + u)};
+    const float4 ev = ld4<DTI>(x, u * ENC_D + 4 * lane);
+    float4 acc = z4;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t r = rr[q];
+      const float4 v = ldg_f4(x0 + r * ENC_D + 4 * lane);
+      const float4 g = ld4<DTO>(dh, r * ENC_D + 4 * lane);
+      const float mu = mean1[r], rs = rstd1[r];
+      const float4 xh = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+      dw1.x += g.x * xh.x; dw1.y += g.y * xh.y; dw1.z += g.z * xh.z; dw1.w += g.w * xh.w;
+      db1.x += g.x; db1.y += g.y; db1.z += g.z; db1.w += g.w;
+      const float4 gw = make_float4(g.x * wb.x, g.y * wb.y, g.z * wb.z, g.w * wb.w);
+      const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
+      const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
+      float4 o = make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
+                             rs * (gw.w - m1 - xh.w * m2));
+      if (res) {
+        const float4 rg = ldg_f4(res + r * ENC_D + 4 * lane);
+        o.x += rg.x; o.y += rg.y; o.z += rg.z; o.w += rg.w;
+      }
+      if (drop_thresh) {
+        const uint32_t e = (uint32_t)(r * (ENC_D / 4) + lane);
+        o.x = (rnd32(seed, e, 0x5bd1e995u) >= drop_thresh) ? o.x * inv_keep : 0.f;
+        o.y = (rnd32(seed, e, 1u) >= drop_thresh) ? o.y * inv_keep : 0.f;
+        o.z = (rnd32(seed, e, 2u) >= drop_thresh) ? o.z * inv_keep : 0.f;
+        o.w = (rnd32(seed, e, 3u) >= drop_thresh) ? o.w * inv_keep : 0.f;
+      }
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    const float mu = mean0[rr[0]], rs = rstd0[rr[0]];
+    const float4 xh = make_float4((ev.x - mu) * rs, (ev.y - mu) * rs, (ev.z - mu) * rs, (ev.w - mu) * rs);
+    dw0.x += acc.x * xh.x; dw0.y += acc.y * xh.y; dw0.z += acc.z * xh.z; dw0.w += acc.w * xh.w;
+    db0.x += acc.x; db0.y += acc.y; db0.z += acc.z; db0.w += acc.w;
+    const float4 gw = make_float4(acc.x * wa.x, acc.y * wa.y, acc.z * wa.z, acc.w * wa.w);
+    const float m1 = warp_sum(gw.x + gw.y + gw.z + gw.w) * (1.f / ENC_D);
+    const float m2 = warp_sum(gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w) * (1.f / ENC_D);
+    st4<DTI>(dx, u * ENC_D + 4 * lane,
+             make_float4(rs * (gw.x - m1 - xh.x * m2), rs * (gw.y - m1 - xh.y * m2), rs * (gw.z - m1 - xh.z * m2),
+                         rs * (gw.w - m1 - xh.w * m2)));
+  }
+  red[0][wib][lane] = dw1; red[1][wib][lane] = db1; red[2][wib][lane] = dw0; red[3][wib][lane] = db0;
+  __syncthreads();
+  if (wib < 4) {
+    float4 s = red[wib][0][lane];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      const float4 t = red[wib][k][lane];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 4 + wib) * ENC_D + 4 * lane) = s;
+  }
+}
+
 static inline void drop_consts(float p, uint32_t& thresh, float& inv_keep) {
   if (p <= 0.f) { thresh = 0u; inv_keep = 1.f; return; }
   double t = (double)p * 4294967296.0;
@@ -1450,7 +1571,55 @@ extern "C" int rs_ln_bwd_dropout(const void* dh, int dh_dtype, const float* x1, 
       dh, x1, residual_grad, n_rows, w, mean, rstd, th, ik, seed, dx, dy, part))));
   RS_LAUNCH_CHECK();
   // part rows are [d gamma | d beta | d bias]: the first two go to (dw, db), the third to d_lin_bias
-  partial_sum3_kernel<<<(3 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, dw, db, d_lin_bias);
+  partial_sumv_kernel<3><<<(3 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, dw, db, d_lin_bias, nullptr);
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" int rs_emb_ln2_fwd(const void* x, int x_dtype, const int64_t* index, int64_t n_rows, int64_t dim, const float* w0,
+                              const float* b0, float eps0, float dropout_p, uint64_t seed, const float* w1,
+                              const float* b1, float eps1, float* x0, void* h, int h_dtype, float* mean0, float* rstd0,
+                              float* mean1, float* rstd1, void* stream) {
+  if (n_rows == 0) return RS_OK;
+  if (!x || !index || !w0 || !b0 || !w1 || !b1 || !x0 || !h || !mean0 || !rstd0 || !mean1 || !rstd1 || n_rows < 0)
+    return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (n_rows * (ENC_D / 4) >= ((int64_t)1 << 32)) return RS_ERR_UNSUPPORTED;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_rows);
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(h_dtype, DTO, (emb_ln2_fwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
+      x, index, n_rows, w0, b0, eps0, th, ik, seed, w1, b1, eps1, x0, h, mean0, rstd0, mean1, rstd1))));
+  RS_LAUNCH_CHECK();
+  return RS_OK;
+}
+
+extern "C" size_t rs_emb_ln2_bwd_workspace_bytes(int64_t n_src) {
+  return (size_t)ln_grid(n_src) * 4 * ENC_D * sizeof(float);
+}
+
+extern "C" int rs_emb_ln2_bwd(const void* dh, int dh_dtype, const void* x, int x_dtype, const float* x0,
+                              const float* residual_grad, const int64_t* inv1, const int64_t* inv2, int64_t n_src,
+                              int64_t dim, const float* w0, const float* w1, const float* mean0, const float* rstd0,
+                              const float* mean1, const float* rstd1, float dropout_p, uint64_t seed, void* dx, float* dw0,
+                              float* db0, float* dw1, float* db1, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_src == 0) return RS_OK;
+  if (!dh || !x || !x0 || !inv1 || !inv2 || !w0 || !w1 || !mean0 || !rstd0 || !mean1 || !rstd1 || !dx || !dw0 || !db0 ||
+      !dw1 || !db1 || !workspace)
+    return RS_ERR_BAD_ARG;
+  if (dim != ENC_D) return RS_ERR_UNSUPPORTED;
+  if (workspace_bytes < rs_emb_ln2_bwd_workspace_bytes(n_src)) return RS_ERR_WORKSPACE;
+  uint32_t th; float ik;
+  drop_consts(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(n_src);
+  float* part = (float*)workspace;
+  ENC_DISPATCH1(x_dtype, DTI, ENC_DISPATCH1(dh_dtype, DTO, (emb_ln2_bwd_kernel<DTI, DTO><<<grid, 256, 0, st>>>(
+      dh, x, x0, residual_grad, inv1, inv2, n_src, w0, w1, mean0, rstd0, mean1, rstd1, th, ik, seed, dx, part))));
+  RS_LAUNCH_CHECK();
+  // part rows: [d gamma_1 | d beta_1 | d gamma_emb | d beta_emb]
+  partial_sumv_kernel<4><<<(4 * ENC_D + 31) / 32, PS_WARPS * 32, 0, st>>>(part, grid, dw1, db1, dw0, db0);
   RS_LAUNCH_CHECK();
   return RS_OK;
 }

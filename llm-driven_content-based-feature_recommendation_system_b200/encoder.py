@@ -218,6 +218,53 @@ def _(dy, x, add, add_rows, lin_bias, w, b, mean, rstd, act, dropout_p, seed):
     return [x.new_empty(dy.shape[0], x.shape[1]), torch.empty_like(w), torch.empty_like(w)]
 
 
+@torch.library.custom_op("rs::emb_ln2", mutates_args=())
+def emb_ln2_op(x: Tensor, index: Tensor, w0: Tensor, b0: Tensor, eps0: float, dropout_p: float, seed: int, w1: Tensor,
+               b1: Tensor, eps1: float, out_dtype: int) -> List[Tensor]:
+    """x0 = dropout(LN_emb(x[index])), h = LN_1(x0) -> [x0 fp32, h, mean0, rstd0, mean1, rstd1] (rs_emb_ln2_fwd)."""
+    L.require_cuda(x, index, w0, w1)
+    x = x.contiguous()
+    n = index.numel()
+    x0 = torch.empty(n, 128, dtype=torch.float32, device=x.device)
+    h = torch.empty(n, 128, dtype=L.torch_dtype(out_dtype), device=x.device)
+    st = [torch.empty(n, dtype=torch.float32, device=x.device) for _ in range(4)]
+    L.check(_lib.rs_emb_ln2_fwd(L.ptr(x), L.dt(x), L.ptr(index), n, x.shape[1], L.ptr(w0), L.ptr(b0), eps0, dropout_p, seed,
+                                L.ptr(w1), L.ptr(b1), eps1, L.ptr(x0), L.ptr(h), out_dtype, L.ptr(st[0]), L.ptr(st[1]),
+                                L.ptr(st[2]), L.ptr(st[3]), L.stream()), "rs_emb_ln2_fwd")
+    return [x0, h] + st
+
+
+@emb_ln2_op.register_fake
+def _(x, index, w0, b0, eps0, dropout_p, seed, w1, b1, eps1, out_dtype):
+    n = index.numel()
+    return [x.new_empty(n, 128, dtype=torch.float32), x.new_empty(n, 128, dtype=L.torch_dtype(out_dtype))] + \
+           [x.new_empty(n, dtype=torch.float32) for _ in range(4)]
+
+
+@torch.library.custom_op("rs::emb_ln2_bwd", mutates_args=())
+def emb_ln2_bwd_op(dh: Tensor, x: Tensor, x0: Tensor, res: Optional[Tensor], inv1: Tensor, inv2: Tensor, w0: Tensor,
+                   w1: Tensor, mean0: Tensor, rstd0: Tensor, mean1: Tensor, rstd1: Tensor, dropout_p: float,
+                   seed: int) -> List[Tensor]:
+    """-> [d x (x's dtype, one row per source row), d gamma_emb, d beta_emb, d gamma_1, d beta_1] (rs_emb_ln2_bwd)."""
+    dh = dh.contiguous()
+    if res is not None:
+        res = res.float().contiguous()
+    n_src = x.shape[0]
+    dx = torch.empty_like(x)
+    g = [torch.empty_like(w0) for _ in range(4)]
+    ws = L.workspace(_lib.rs_emb_ln2_bwd_workspace_bytes(n_src), x.device)
+    L.check(_lib.rs_emb_ln2_bwd(L.ptr(dh), L.dt(dh), L.ptr(x), L.dt(x), L.ptr(x0), L.ptr(res), L.ptr(inv1), L.ptr(inv2),
+                                n_src, x.shape[1], L.ptr(w0), L.ptr(w1), L.ptr(mean0), L.ptr(rstd0), L.ptr(mean1),
+                                L.ptr(rstd1), dropout_p, seed, L.ptr(dx), L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]),
+                                L.ptr(ws), ws.numel(), L.stream()), "rs_emb_ln2_bwd")
+    return [dx] + g
+
+
+@emb_ln2_bwd_op.register_fake
+def _(dh, x, x0, res, inv1, inv2, w0, w1, mean0, rstd0, mean1, rstd1, dropout_p, seed):
+    return [torch.empty_like(x)] + [torch.empty_like(w0) for _ in range(4)]
+
+
 @torch.library.custom_op("rs::dropout_add_ln", mutates_args=())
 def dropout_add_ln_op(x: Tensor, y: Tensor, lin_bias: Optional[Tensor], w: Tensor, b: Tensor, eps: float,
                       dropout_p: float, seed: int, out_dtype: int) -> List[Tensor]:
@@ -599,6 +646,37 @@ def residual_layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, out
     return _ResidualLN.apply(x, weight, bias, float(eps), L.dt(out_dtype))
 
 
+class _EmbLN2(torch.autograd.Function):
+    """(x0, h): x0 = dropout(LayerNorm_emb(x[index])) -- the encoder's input stream -- and h = LayerNorm_1(x0), the first
+    layer's normalised input, in one pass (rs_emb_ln2_fwd).  Every row of x is read by exactly the packed rows inv1 / inv2
+    (two dropout views): the backward folds the two views BEFORE LayerNorm_emb's (linear) backward, one warp per source
+    row (rs_emb_ln2_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, index, inv1, inv2, w0, b0, eps0, dropout_p, seed, w1, b1, eps1, out_dtype):
+        x0, h, m0, r0, m1, r1 = L.direct.emb_ln2(x, index, w0, b0, eps0, dropout_p, seed, w1, b1, eps1, out_dtype)
+        ctx.save_for_backward(x, x0, inv1, inv2, w0, w1, m0, r0, m1, r1)
+        ctx.meta = (dropout_p, seed)
+        return x0, h
+
+    @staticmethod
+    def backward(ctx, gx0, gh):
+        x, x0, inv1, inv2, w0, w1, m0, r0, m1, r1 = ctx.saved_tensors
+        if gh is None:
+            gh = torch.zeros(x0.shape, dtype=torch.bfloat16, device=x0.device)
+        dx, dw0, db0, dw1, db1 = L.direct.emb_ln2_bwd(gh, x, x0, gx0, inv1, inv2, w0, w1, m0, r0, m1, r1, *ctx.meta)
+        return dx, None, None, None, dw0, db0, None, None, None, dw1, db1, None, None
+
+
+def emb_layer_norm2(x: Tensor, index: Tensor, index_inv, emb_ln: torch.nn.LayerNorm, dropout_p: float,
+                    norm1: torch.nn.LayerNorm, out_dtype: torch.dtype):
+    """returns (x0, h) -- see _EmbLN2.  `index` [2 * len(x)], `index_inv` = (inv1, inv2) as for layer_norm(index_inv=...)."""
+    inv1, inv2 = index_inv
+    assert index.numel() == 2 * x.shape[0] and inv1.numel() == x.shape[0] == inv2.numel()
+    return _EmbLN2.apply(x, index, inv1, inv2, emb_ln.weight, emb_ln.bias, float(emb_ln.eps), float(dropout_p),
+                         _seed() if dropout_p > 0 else 0, norm1.weight, norm1.bias, float(norm1.eps), L.dt(out_dtype))
+
+
 class _DropoutAddLN(torch.autograd.Function):
     """(x1, h) with x1 = x + dropout(y + bias), h = LayerNorm(x1): the end of one pre-norm block and the start of the next
     in one pass each way (rs_dropout_add_ln_fwd / rs_ln_bwd_dropout).  The gradient reaching x1 through the residual
@@ -868,6 +946,14 @@ import os as _os
 BIAS_IN_GEMM = _os.environ.get('RS_BIAS_IN_GEMM', '1') == '1'
 
 
+def first_layer_fusable(encoder: torch.nn.TransformerEncoder, emb_ln: torch.nn.LayerNorm, x: Tensor) -> bool:
+    """can the embedding LayerNorm be fused with the first layer's LayerNorm (emb_layer_norm2)?"""
+    l0 = encoder.layers[0] if len(encoder.layers) else None
+    return (l0 is not None and l0.norm_first and tuple(emb_ln.normalized_shape) == (128,) and emb_ln.elementwise_affine
+            and emb_ln.bias is not None and l0.norm1.elementwise_affine and l0.norm1.bias is not None
+            and x.shape[-1] == 128 and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+
 def _add_norm(x: Tensor, pending, norm: torch.nn.LayerNorm, ad: torch.dtype):
     """(residual stream, LayerNorm of it); `pending` = (y, bias, p): a block's closing  x + dropout(y + bias)  that has not
     been applied yet -- it is then folded into the same pass as the LayerNorm (fp32 residual stream only)."""
@@ -881,7 +967,7 @@ def _add_norm(x: Tensor, pending, norm: torch.nn.LayerNorm, ad: torch.dtype):
 
 def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_seqlens: Tensor, max_len: int,
                          zero_tail: int = 0, rows=None, one_row_from: int = -1, one_rows=None, pending=None,
-                         defer_close: bool = False):
+                         defer_close: bool = False, first_h: Optional[Tensor] = None):
     """One pre-norm layer on the packed tokens.  `rows` = (n_prefix, idx): only the rows cat([arange(n_prefix), idx]) are
     wanted from this layer (idx: rows outside the prefix, -1 = none -> a zero row).  Attention still sees every token --
     the wanted rows attend to the others -- but everything behind it is position-wise, so the out-projection, the residual
@@ -893,7 +979,10 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
     tr = layer.training
     attn = layer.self_attn
     ad = _act_dtype(x)
-    x, h = _add_norm(x, pending, layer.norm1, ad)
+    if first_h is not None:            # LayerNorm_1(x) came with x out of the fused embedding pass (emb_layer_norm2)
+        h = first_h
+    else:
+        x, h = _add_norm(x, pending, layer.norm1, ad)
     # the four biases are folded into the kernels that consume the GEMM outputs: plain matmuls, and the bias
     # gradients are column sums of tensors those kernels' backward passes produce (no reduction behind each GEMM)
     # (in_proj: the bias rides in the GEMM's epilogue -- free there, one add per fragment load in the attention kernels
@@ -921,7 +1010,8 @@ def packed_encoder_layer(layer: torch.nn.TransformerEncoderLayer, x: Tensor, cu_
 
 
 def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: Tensor, max_len: int,
-                   zero_tail: int = 0, last_rows=None, one_row_from: int = -1, one_rows=None) -> Tensor:
+                   zero_tail: int = 0, last_rows=None, one_row_from: int = -1, one_rows=None,
+                   first_h: Optional[Tensor] = None) -> Tensor:
     """x: [T, 128] fp32 residual stream of the packed valid tokens -> same shape; with `last_rows` = (n_prefix, idx) only
     those rows of the LAST layer's output, [n_prefix + len(idx), 128] (see packed_encoder_layer).  `one_row_from` /
     `one_rows` (with last_rows): the caller vouches that of the sequences from that index on, `last_rows` names nothing
@@ -933,7 +1023,7 @@ def packed_encoder(encoder: torch.nn.TransformerEncoder, x: Tensor, cu_seqlens: 
         last = i == n_layers - 1
         out = packed_encoder_layer(layer, x, cu_seqlens, max_len, zero_tail, last_rows if last else None,
                                    one_row_from if last else -1, one_rows if last else None, pending=pending,
-                                   defer_close=not last)
+                                   defer_close=not last, first_h=first_h if i == 0 else None)
         x, pending = out if not last else (out, None)
     if encoder.norm is not None:
         x = encoder.norm(x)

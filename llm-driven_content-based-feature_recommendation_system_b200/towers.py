@@ -26,6 +26,10 @@ STATIC_TABLES = ("age_emb", "price_emb", "cnt_emb", "recency_emb", "channel_emb"
                  "news_freq_emb", "fn_emb", "active_emb")
 
 
+import os as _os
+FUSE_EMB_LN = _os.environ.get('RS_FUSE_EMB_LN', '1') == '1'      # (A/B switch for encoder.emb_layer_norm2)
+
+
 class _ZeroGradTables(torch.autograd.Function):
     """identity on x; the listed tables get explicit all-zero gradients (they take part with a gate of exactly 0)."""
 
@@ -197,9 +201,19 @@ class SASRecUserTower(nn.Module):
         `select_users` [len(select_index)]: the row of `user_profile_vec` that goes with every selected row (needed
         when several dropout views share the pass; default: the token's own batch row)."""
         tr = self.training
-        x = enc.layer_norm(seq_emb.reshape(-1, seq_emb.shape[-1]), self.emb_ln.weight, self.emb_ln.bias, self.emb_ln.eps,
-                           index=packed_index, dropout_p=self.emb_dropout.p if tr else 0.0, out_dtype=torch.float32,
-                           index_fold=packed_fold, index_inv=packed_fold_inv)
+        e = seq_emb.reshape(-1, seq_emb.shape[-1])
+        first_h = None
+        if (FUSE_EMB_LN and packed_fold_inv is not None and packed_index is not None
+                and packed_index.numel() == 2 * e.shape[0] and enc.first_layer_fusable(self.transformer_encoder, self.emb_ln, e)):
+            # embedding LayerNorm + dropout and the first layer's LayerNorm in one pass each way; the backward folds the two
+            # dropout views before the embedding LayerNorm's backward (one warp per U1 row)
+            ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+            x, first_h = enc.emb_layer_norm2(e, packed_index, packed_fold_inv, self.emb_ln,
+                                             self.emb_dropout.p if tr else 0.0, self.transformer_encoder.layers[0].norm1, ad)
+        else:
+            x = enc.layer_norm(e, self.emb_ln.weight, self.emb_ln.bias, self.emb_ln.eps, index=packed_index,
+                               dropout_p=self.emb_dropout.p if tr else 0.0, out_dtype=torch.float32,
+                               index_fold=packed_fold, index_inv=packed_fold_inv)
         if select_prefix is not None:
             # device-built index (ops.batch_index_build): the first `select_prefix` selected rows ARE the first packed
             # rows (identity), their users ascend (batch-major), and the remaining selected rows are one DuoRec row per
@@ -218,7 +232,7 @@ class SASRecUserTower(nn.Module):
             n_users = user_profile_vec.shape[0] // max(views, 1)
             one = dict(one_row_from=n_users, one_rows=tail[m - n_users:].contiguous()) if views == 2 and m == 2 * n_users else {}
             output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail,
-                                        last_rows=(n, torch.where(inside, -1, tail)), **one)
+                                        last_rows=(n, torch.where(inside, -1, tail)), first_h=first_h, **one)
             pick = torch.where(inside, tail, n + torch.arange(m, device=tail.device))
             # the head's first Linear autocasts its input: emit the rows in that dtype right away
             ad = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else output.dtype
@@ -235,7 +249,7 @@ class SASRecUserTower(nn.Module):
                               user_profile_vec.to(ad)])
             final_vec = enc.sequential(self.output_proj, torch.cat([output, prof], dim=-1))
             return enc.l2_normalize(final_vec)
-        output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail)
+        output = enc.packed_encoder(self.transformer_encoder, x, cu_seqlens, seq_len, zero_tail, first_h=first_h)
         if not training_mode:
             select_index = cu_seqlens[1:user_profile_vec.shape[0] + 1].to(torch.int64) - 1
         users = select_users

@@ -624,3 +624,44 @@ def test_attn_one_tile_backward_matches_two_phase_backward(rs, p_drop, dt):
         out32, lse32 = torch.ops.rs.attn_varlen(qkv.float(), None, cu, H, 64, 0, scale, 0.0, 0)
         d32, _ = torch.ops.rs.attn_varlen_bwd(qkv.float(), None, w.float(), out32, lse32, cu, H, 64, 0, scale, 0.0, 0)
         assert (a - d32).norm() / d32.norm() < 1e-2
+
+
+def test_emb_layer_norm2_matches_the_two_separate_passes(rs):
+    """encoder.emb_layer_norm2 (embedding LayerNorm + dropout + first-layer LayerNorm in one pass; backward folds the two
+    dropout views before the embedding LayerNorm's backward) against layer_norm(index, index_inv) + residual_layer_norm:
+    p = 0 -> values and all gradients; p > 0 -> same seed, same hash -> identical masks, so everything still matches."""
+    g = torch.Generator().manual_seed(41)
+    n_src = 600
+    e = (torch.randn(n_src, 128, generator=g) * 1.5 + 0.3).bfloat16().to(DEV)
+    perm = torch.randperm(2 * n_src, generator=g)
+    inv1, inv2 = perm[:n_src].to(DEV), perm[n_src:].to(DEV)            # packed slots of every source row
+    index = torch.empty(2 * n_src, dtype=torch.int64, device=DEV)
+    index[inv1] = torch.arange(n_src, device=DEV)
+    index[inv2] = torch.arange(n_src, device=DEV)
+    ln0, ln1 = torch.nn.LayerNorm(128).to(DEV), torch.nn.LayerNorm(128).to(DEV)
+    with torch.no_grad():
+        for ln in (ln0, ln1):
+            ln.weight.add_(torch.randn(128, generator=g).to(DEV) * 0.2)
+            ln.bias.add_(torch.randn(128, generator=g).to(DEV) * 0.2)
+    c0 = torch.randn(2 * n_src, 128, generator=g).to(DEV)
+    c1 = torch.randn(2 * n_src, 128, generator=g).to(DEV)
+    for p in (0.0, 0.3):
+        res = []
+        for fused in (False, True):
+            for ln in (ln0, ln1):
+                ln.weight.grad = ln.bias.grad = None
+            ee = e.clone().requires_grad_(True)
+            torch.manual_seed(77)                                       # same host seed -> same dropout stream
+            if fused:
+                x0, h = rs.encoder.emb_layer_norm2(ee, index, (inv1, inv2), ln0, p, ln1, torch.bfloat16)
+            else:
+                x0 = rs.encoder.layer_norm(ee, ln0.weight, ln0.bias, ln0.eps, index=index, dropout_p=p,
+                                           out_dtype=torch.float32, index_inv=(inv1, inv2))
+                x0, h = rs.encoder.residual_layer_norm(x0, ln1.weight, ln1.bias, ln1.eps, torch.bfloat16)
+            ((x0 * c0).sum() + (h.float() * c1).sum()).backward()
+            res.append([x0.detach(), h.detach().float(), ee.grad.float(), ln0.weight.grad.clone(), ln0.bias.grad.clone(),
+                        ln1.weight.grad.clone(), ln1.bias.grad.clone()])
+        for a, b in zip(res[1], res[0]):
+            rel = (a - b).norm() / b.norm()
+            assert rel < 5e-3, (p, rel)
+        torch.testing.assert_close(res[1][0], res[0][0], rtol=1e-5, atol=1e-5)
