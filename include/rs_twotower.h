@@ -198,7 +198,10 @@ int rs_masked_mean_bwd(const float* d_out, const int64_t* mask, int64_t n_seq, i
  * dropout view in the last encoder layer feeds nothing but its DuoRec row, v1_usertower_train.py:789,830-842):
  * one_rows[k] (int64) is the packed row of that token for sequence one_row_from + k (NULL: the last token; a row
  * outside the sequence: none).  That row is computed by a matrix-vector kernel, the sequence's other rows of `out` are
- * zeros, and the backward builds d_qkv of all its tokens from that row's gradient alone.  one_row_from = -1: none. */
+ * zeros, and the backward builds d_qkv of all its tokens from that row's gradient alone.  one_row_from = -1: none.
+ * Backward kernels (16-bit operands): with bias == NULL (the in_proj bias already inside qkv -- GEMM epilogue) every
+ * (query tile, key tile) pair of a sequence is visited once (one-tile sequences in registers only, longer ones with dQ
+ * summed in shared memory); with a bias pointer the two-phase kernel (dQ pass, then dK/dV pass) runs.  Same results. */
 int rs_attn_varlen_fwd(const void* qkv, int dtype, const float* bias /*[3*H*32] in_proj bias added on load, or NULL*/,
                        const int32_t* cu_seqlens, int64_t n_seq, int64_t total_tokens,
                        int n_heads, int head_dim, int max_len, int64_t zero_tail, int64_t one_row_from,
