@@ -19,7 +19,6 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import _lib as L
 from . import ops
 
 MATRIX_FILE = "pretrained_item_matrix.pt"

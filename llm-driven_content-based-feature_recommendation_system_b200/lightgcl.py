@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-from . import encoder, losses, ops
+from . import losses, ops
 
 
 def calc_bpr_loss(local_emb: Tensor, users: Tensor, pos_items: Tensor, neg_items: Tensor) -> Tensor:
